@@ -1,0 +1,131 @@
+"""Oracle (test infrastructure): Helmholtz.discretize, per-element loops as in the reference.
+
+Restates src/Helmholtz.jl:19-33 (outer), :54-81, :120-191 (element wrappers),
+:232-345 (descriptor parsing: :interior, :mass, :stiff-less subset, :admittance
+(sym,val), :flame 9/10-tuple n-tau, :flameresponse), :405-524 (element loops +
+sparse()), :528-540,:571-580 (mass weighting / __aux__ term).
+Bloch (b!=:__none__), :speaker, :fancyflame and custom-FTF variants are not on
+the round-1 path and raise NotImplementedError.
+"""
+import numpy as np
+import scipy.sparse as sp
+
+from . import fem
+from .mesh import aggregate_elements
+from .nlevp import LinearOperatorFamily, Term, exp_delay, pow1, pow2
+
+
+def _sparse(I, J, V, dim):
+    """SparseArrays.sparse(I,J,V,dim,dim): duplicates summed, explicit zeros kept."""
+    return sp.csc_matrix(sp.coo_matrix((np.asarray(V, dtype=complex), (I, J)), shape=(dim, dim)))
+
+
+def discretize(mesh, dscrp, C, order="lin", mass_weighting=True, triplets=None):
+    """Returns the LinearOperatorFamily.  If `triplets` is a dict, the raw COO
+    triplets of every operator are stored in it (used by the pattern tests)."""
+    o = 1 if order == "lin" else 2
+    triangles, tetrahedra, dim = aggregate_elements(mesh, order)
+    npts = mesh.points.shape[1]
+    C = np.asarray(C, dtype=float)
+    if len(C) == len(mesh.tetrahedra):
+        C_tet = [C[i] for i in range(len(C))]
+        if mesh.tri2tet is None:
+            mesh.link_triangles_to_tetrahedra()
+        C_tri = [C[j] for j in mesh.tri2tet]
+    elif len(C) == npts:
+        C_tet = [C[t[:4]] for t in tetrahedra]
+        C_tri = [C[t[:3]] for t in triangles]
+    else:
+        raise ValueError("C must be per-tetrahedron or per-point")
+    L = LinearOperatorFamily(["ω", "λ"], [0.0, float("inf")])
+    P = mesh.points
+
+    def stiff(ct, c):
+        return -c**2 * fem.tet_stiff(ct, o) if np.ndim(c) == 0 else -fem.tet_stiff_cc1(ct, c, o)
+
+    def bound(ct, c):
+        return c * fem.tri_mass(ct, o) if np.ndim(c) == 0 else fem.tri_mass_c1(ct, c, o)
+
+    for domain, (typ, data) in dscrp.items():
+        simplices = mesh.domains[domain]["simplices"]
+        if typ == "interior":
+            make = ["M", "K"]
+        elif typ == "mass":
+            make = ["M"]
+        elif typ == "admittance":
+            make = ["C"]
+            adm_sym, adm_val = data
+            L.params.setdefault(adm_sym, complex(adm_val))
+            bfunc, barg, btxt = (pow1, pow1), (("ω",), (adm_sym,)), "ω*" + adm_sym
+        elif typ in ("flame", "flameresponse"):
+            make = ["Q"]
+            if typ == "flame" and len(data) == 9:
+                gamma, rho, nglobal, x_ref, n_ref, n_sym, tau_sym, n_val, tau_val = data
+                ref_idx = -1
+            elif typ == "flame" and len(data) == 10:
+                gamma, rho, nglobal, ref_idx, x_ref, n_ref, n_sym, tau_sym, n_val, tau_val = data
+            elif typ == "flameresponse":
+                gamma, rho, nglobal, x_ref, n_ref, eps_sym, eps_val = data
+                ref_idx = -1
+            else:
+                raise NotImplementedError("flame descriptor variant")
+            nlocal = (gamma - 1) / rho * nglobal / mesh.compute_size(domain)
+            if typ == "flame":
+                L.params.setdefault(n_sym, complex(n_val))
+                L.params.setdefault(tau_sym, complex(tau_val))
+                ffunc, farg, ftxt = (pow1, exp_delay), ((n_sym,), ("ω", tau_sym)), f"{n_sym}*exp(-iω{tau_sym})"
+            else:
+                L.params.setdefault(eps_sym, complex(eps_val))
+                ffunc, farg, ftxt = (pow1,), ((eps_sym,),), eps_sym
+            if ref_idx < 0:
+                ref_idx = mesh.find_tetrahedron_containing_point(x_ref)
+        else:
+            raise NotImplementedError(typ)
+
+        for opr in make:
+            I, J, V = [], [], []
+            if opr in ("M", "K"):
+                for s in simplices:
+                    smplx = tetrahedra[s]
+                    ct = fem.CooTrafo(P[:, smplx[:4]])
+                    ii, jj = fem.create_indices(smplx)
+                    vv = fem.tet_mass(ct, o) if opr == "M" else stiff(ct, C_tet[s])
+                    V.extend(vv.T.ravel()); I.extend(ii.T.ravel()); J.extend(jj.T.ravel())
+                func, arg, txt = ((pow2,), (("ω",),), "ω^2") if opr == "M" else ((), (), "")
+            elif opr == "C":
+                for s in simplices:
+                    smplx = triangles[s]
+                    ct = fem.CooTrafo(P[:, smplx[:3]])
+                    ii, jj = fem.create_indices(smplx)
+                    vv = bound(ct, C_tri[s])
+                    V.extend(vv.T.ravel()); I.extend(ii.T.ravel()); J.extend(jj.T.ravel())
+                V = list(np.asarray(V, dtype=complex) * -1j)
+                func, arg, txt = bfunc, barg, btxt
+            elif opr == "Q":
+                S, Irow = [], []
+                for s in simplices:
+                    smplx = tetrahedra[s]
+                    ct = fem.CooTrafo(P[:, smplx[:4]])
+                    S.extend(fem.tet_src(ct, o)); Irow.extend(smplx)
+                smplx = tetrahedra[ref_idx]
+                ct = fem.CooTrafo(P[:, smplx[:4]])
+                G = -nlocal * fem.tet_grad_at(ct, n_ref, x_ref, o)
+                for a, i in zip(S, Irow):  # Helmholtz.jl:19-33 outer()
+                    for b, j in zip(G, smplx):
+                        V.append(a * b); I.append(i); J.append(j)
+                func, arg, txt = ffunc, farg, ftxt
+            if triplets is not None:
+                triplets.setdefault(opr, []).append((np.array(I), np.array(J), np.array(V, dtype=complex)))
+            L.push(Term(_sparse(I, J, V, dim), func, arg, txt, opr))
+
+    if mass_weighting:
+        I, J, V = [], [], []
+        for smplx in tetrahedra:
+            ct = fem.CooTrafo(P[:, smplx[:4]])
+            ii, jj = fem.create_indices(smplx)
+            vv = fem.tet_mass(ct, o)
+            V.extend(vv.T.ravel()); I.extend(ii.T.ravel()); J.extend(jj.T.ravel())
+        if triplets is not None:
+            triplets.setdefault("__aux__", []).append((np.array(I), np.array(J), -np.array(V, dtype=complex)))
+        L.push(Term(_sparse(I, J, -np.asarray(V), dim), (pow1,), (("λ",),), "-λ", "__aux__"))
+    return L

@@ -1,0 +1,106 @@
+"""Pin the CPU oracle to the reference's stored outputs."""
+import math
+
+import numpy as np
+import pytest
+
+from cases import load_raw_mesh, rijke_dscrp, speedofsound
+from oracle import fem
+from oracle.helmholtz import discretize
+from oracle.mesh import Mesh
+from oracle.nlevp import beyn, householder, mslp
+
+TOL = 1e-10  # relative eigenvalue tolerance of BASELINE.json
+
+
+@pytest.fixture(scope="module")
+def rijke():
+    mesh = Mesh("Rijke_mm.msh", scale=0.001, raw=load_raw_mesh("rijke_mm"))
+    c = mesh.generate_field(speedofsound)
+    return mesh, c
+
+
+def test_mesh_counts(rijke):
+    mesh, c = rijke
+    # docs/src/tutorial_01_rijke_tube.md:62-64
+    assert mesh.points.shape == (3, 1006) and len(mesh.triangles) == 1562 and len(mesh.tetrahedra) == 3380
+
+
+def test_fem_tables_match_reference_expressions():
+    g = np.load(__import__("os").path.join(__import__("cases").GOLDEN, "fem_tables.npz"))
+    rel = lambda a, b: np.abs(a - b).max() / np.abs(b).max()
+    T = fem.tables
+    assert rel(T(1, 4)["mass"], g["tab_s43v1u1"]) < 1e-15 and rel(T(2, 4)["mass"], g["tab_s43v2u2"]) < 1e-15
+    assert rel(T(1, 3)["mass"], g["tab_s33v1u1"]) < 1e-15 and rel(T(2, 3)["mass"], g["tab_s33v2u2"]) < 1e-15
+    assert rel(T(1, 4)["src"], g["tab_s43v1"][0]) < 1e-15 and rel(T(2, 4)["src"], g["tab_s43v2"][0]) < 1e-15
+    assert rel(T(1, 3)["src"], g["tab_s33v1"][0]) < 1e-15 and rel(T(2, 3)["src"], g["tab_s33v2"][0]) < 1e-15
+    for k in range(g["X"].shape[0]):
+        ct, c = fem.CooTrafo(g["X"][k]), g["C4"][k]
+        for o, n1, n2, n3 in [(1, "s43nv1nu1", "s43nv1nu1cc1", "s43v1u1c1"), (2, "s43nv2nu2", "s43nv2nu2cc1", "s43v2u2c1")]:
+            assert rel(fem.tet_stiff(ct, o), g["val_" + n1][k]) < 5e-15
+            assert rel(fem.tet_stiff_cc1(ct, c, o), g["val_" + n2][k]) < 5e-15
+            assert rel(fem.tet_mass_c1(ct, c, o), g["val_" + n3][k]) < 5e-15
+        assert rel(fem.tet_grad_at(ct, g["nref"][k], g["xref"][k], 2), g["val_s43nv2rx"][k]) < 5e-15
+        assert rel(fem.tet_grad_at(ct, g["nref"][k], g["xref"][k], 1), g["val_s43nv1rx"][k]) < 5e-15
+        ct, c = fem.CooTrafo(g["XT"][k]), g["C3"][k]
+        assert rel(fem.tri_mass_c1(ct, c, 1), g["val_s33v1u1c1"][k]) < 5e-15
+        assert rel(fem.tri_mass_c1(ct, c, 2), g["val_s33v2u2c1"][k]) < 5e-15
+        assert rel(fem.tri_src_c1(ct, c, 1), g["val_s33v1c1"][k]) < 5e-15
+        assert rel(fem.tri_src_c1(ct, c, 2), g["val_s33v2c1"][k]) < 5e-15
+
+
+G_HOUSEHOLDER = [  # (tau, omega) notebook cells 5, 16, 32
+    (0.001, 1710.6977772393461 + 9.615018460173488j),
+    (0.001 + 0.00001, 1710.864199971756 + 9.593830019670127j),
+    (0.001 + 0.0008798274754933992 + 0.001, 1707.4565281774599 - 9.11764397194075j),
+]
+G1_TRACE_RES = [1.6243873211323859e6, 147442.983718491, 1804.6396540359215, 0.2839458865676277]
+G1_TRACE_Z = [2136.2830044410593, 1753.640443755553 + 8.160610349893785j, 1711.2293969397867 + 9.58445933911067j,
+              1710.6978605746078 + 9.615009671129867j, 1710.6977772393602 + 9.615018460179712j]
+
+
+@pytest.mark.parametrize("tau,omega", G_HOUSEHOLDER)
+def test_householder_goldens(rijke, tau, omega):
+    mesh, c = rijke
+    L = discretize(mesh, rijke_dscrp(0.01, tau), c)
+    assert L.size() == 1006
+    trace = []
+    sol, n, flag = householder(L, 340 * 2 * math.pi, maxiter=20, tol=1e-11, trace=trace)
+    assert abs(sol.params["ω"] - omega) / abs(omega) < TOL
+    if tau == 0.001:
+        for k, r in enumerate(G1_TRACE_RES):
+            assert abs(trace[k + 1][1] - r) / r < 1e-6
+        for k, z in enumerate(G1_TRACE_Z):
+            assert abs(trace[k][3] - z) / abs(z) < 1e-9
+
+
+G_MSLP = [  # (tau, start, omega) docs/src/tutorial_04_perturbation_theory.md:75-88,147-172,386-408
+    (0.001, 340 * 2 * math.pi, 1075.325211506839 + 372.1017670372039j),
+    (0.0015, 916.7085040155473 + 494.3258317478708j, 916.7036137579256 + 494.32932528479967j),
+    (0.001 + 2 * 0.0007029896606802446, 668.5373997804821 + 529.4636751544649j, 668.537399929804 + 529.4636746814361j),
+]
+
+
+@pytest.mark.parametrize("tau,start,omega", G_MSLP)
+def test_mslp_goldens(rijke, tau, start, omega):
+    mesh, c = rijke
+    L = discretize(mesh, rijke_dscrp(1, tau), c)
+    sol, n, flag = mslp(L, start, maxiter=20, tol=1e-11)
+    assert flag == 0
+    assert abs(sol.params["ω"] - omega) / abs(omega) < TOL
+    if tau == 0.001:
+        assert n in (7, 8, 9)  # reference: 8; the last step is at round-off level (|dz|~1e-12)
+
+
+def test_beyn_prose_values(rijke):
+    """docs/src/tutorial_01_rijke_tube.md:202-212: two modes near 272 and 695 Hz (N reduced from 256 to 32)."""
+    mesh, c = rijke
+    L = discretize(mesh, rijke_dscrp(0.0, 0.001), c)
+    G = [z * 2 * math.pi for z in (150 + 5j, 150 - 5j, 1000 - 5j, 1000 + 5j)]
+    Om, P = beyn(L, G, l=5, N=32)
+    f = np.sort(Om.real / 2 / math.pi)
+    assert len(f) == 2 and abs(f[0] - 272) < 1.0 and abs(f[1] - 695) < 5.0
+    # the reference's own idiom (tutorial_06...jl:41-55): polish with a local solver
+    for om in Om:
+        sol, n, flag = householder(L, om, maxiter=10, tol=1e-10)
+        assert abs(sol.params["ω"] - om) < 1e-3 * abs(om)
