@@ -1,0 +1,152 @@
+/* wae_b200.h -- C ABI of libwae_b200.so, the B200 (sm_100a) implementation of the
+ * data-parallel hot path of WavesAndEigenvalues.jl:
+ *     Helmholtz.discretize -> LinearOperatorFamily L(z) -> householder / mslp / beyn.
+ *
+ * The reference is pure Julia and has no FFI for this path; these entry points are
+ * what its host code would bind with `ccall` (INTEGRATION.md shows the Julia stubs).
+ * Each group cites the reference code it replaces (paths relative to the reference
+ * repository root).
+ *
+ * Conventions
+ *  - Every function returns an int32 status: 0 ok, <0 error (WAE_E_*); the message
+ *    is available from wae_last_error().  No exceptions cross the ABI.
+ *  - Host arrays are caller-owned and never retained after the call returns.
+ *    Device memory is owned by the context and released by wae_destroy().
+ *  - Complex numbers are interleaved (re,im) doubles == Julia ComplexF64 / C99
+ *    double _Complex / numpy complex128.
+ *  - Index arrays handed in or out use the context's index base (wae_create:
+ *    1 for Julia, 0 for C/Python).  Integer widths are explicit.
+ *  - Matrices are CSC with sorted row indices inside columns, exactly the layout
+ *    of Julia's SparseMatrixCSC produced by `sparse(I,J,V,dim,dim)`.
+ *  - One host thread per context.  All work is issued on the context's stream
+ *    (wae_set_stream) and every function that returns data to the host
+ *    synchronises that stream before returning.
+ */
+#ifndef WAE_B200_H
+#define WAE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wae_ctx wae_ctx;
+
+enum {
+  WAE_OK = 0,
+  WAE_E_INVALID = -1,   /* bad argument / unknown id / wrong state           */
+  WAE_E_CUDA = -2,      /* CUDA runtime failure                              */
+  WAE_E_SINGULAR = -3,  /* zero / non-finite pivot: Julia shim throws SingularException(0)
+                           (Householder.jl:145-148 -> flag -6; iterative_solvers.jl:206-209) */
+  WAE_E_NOCONV = -4,    /* Arnoldi did not converge: shim throws ARPACKException
+                           (Householder.jl:140-144 -> flag -4)                */
+  WAE_E_NOMEM = -5
+};
+
+/* ---- context ------------------------------------------------------------------- */
+int32_t wae_create(wae_ctx** out, int32_t device, int32_t index_base);
+int32_t wae_destroy(wae_ctx* h);
+const char* wae_last_error(wae_ctx* h);
+/* Issue all later work on `cuda_stream` (a cudaStream_t; NULL = the legacy default stream). */
+int32_t wae_set_stream(wae_ctx* h, void* cuda_stream);
+int32_t wae_sync(wae_ctx* h);
+/* Number of kernels this library has launched since creation (bench.py: gpu_launches). */
+int64_t wae_launch_count(wae_ctx* h);
+/* Device-side duration of the most recent call of the named phase, in ms (CUDA events on the
+ * context stream).  Phases: "assemble", "combine", "factor", "solve", "spmv", "eigs". */
+double wae_last_ms(wae_ctx* h, const char* phase);
+
+/* ---- mesh + element DOF lists ---------------------------------------------------
+ * Replaces the per-element reads of mesh.points / tetrahedra / triangles inside the loops of
+ * src/Helmholtz.jl:411-463,468-476,532-539.  `order` is 1 (:lin) or 2 (:quad); `tets` is
+ * n_loc x n_tet (n_loc = 4 | 10, column-major == Julia vector-of-vectors flattened) and `tris`
+ * n_loc3 x n_tri (3 | 6), as produced by aggregate_elements (src/FEM/FEM.jl:84-116);
+ * xyz is 3 x n_pts column-major (== mesh.points); dim = number of DOFs.                     */
+int32_t wae_mesh_set(wae_ctx* h, int32_t order, int64_t n_pts, const double* xyz,
+                     int64_t n_tet, const uint32_t* tets, int64_t n_tri, const uint32_t* tris,
+                     int64_t dim);
+
+/* ---- sparsity pattern of one operator (symbolic, once per domain) -----------------
+ * Replaces the I/J triplet growth + SparseArrays.sparse pattern merge (Helmholtz.jl:406-417,515;
+ * FEM.jl:22-32 create_indices).  elem_kind: 3 = tetrahedra, 2 = triangles.  elem_ids index the
+ * element list given to wae_mesh_set (context index base); NULL = all elements.             */
+int32_t wae_pattern_build(wae_ctx* h, int32_t elem_kind, int64_t n_elem, const int64_t* elem_ids,
+                          int32_t* pattern_id, int64_t* nnz);
+int32_t wae_pattern_get(wae_ctx* h, int32_t pattern_id, int64_t* colptr /* dim+1 */, int64_t* rowval /* nnz */);
+
+/* ---- numeric assembly ---------------------------------------------------------------
+ * kind: element operator; values are produced directly on the pattern (duplicates summed).
+ *   WAE_OP_MASS      int phi_i phi_j                      FEM.jl:704-738      (Helmholtz.jl:409-425)
+ *   WAE_OP_STIFF     -c^2 int grad phi_i . grad phi_j     FEM.jl:1745-1874    (Helmholtz.jl:120-140,426-445)
+ *   WAE_OP_BOUNDARY  -i c int_tri phi_i phi_j             FEM.jl:435-450      (Helmholtz.jl:151-171,446-463)
+ * c: speed of sound, c_per_elem values per element of the pattern's element list, in list order
+ *    (1 = constant per element; 4 / 3 = linear, vertex values: FEM.jl:764-890, 2283-2424, 469-525);
+ *    ignored (may be NULL) for WAE_OP_MASS.
+ * scale: real factor applied to all values (the __aux__ term is -M: Helmholtz.jl:572).      */
+enum { WAE_OP_MASS = 1, WAE_OP_STIFF = 2, WAE_OP_BOUNDARY = 3 };
+int32_t wae_assemble(wae_ctx* h, int32_t pattern_id, int32_t kind, const double* c,
+                     int32_t c_per_elem, double scale, int32_t* mat_id);
+/* Mass and stiffness of the same tetrahedral pattern in one pass over the elements. */
+int32_t wae_assemble_mk(wae_ctx* h, int32_t pattern_id, const double* c, int32_t c_per_elem,
+                        int32_t* mass_id, int32_t* stiff_id);
+/* Flame-response operator Q = S (x) G (Helmholtz.jl:464-487, 19-33; FEM.jl:2429-2484):
+ * S_i = sum over flame tets of int phi_i, G_j = -nlocal * grad phi_j(x_ref) . n_ref on ref_tet.
+ * Builds its own (dense block) pattern.                                                      */
+int32_t wae_assemble_flame(wae_ctx* h, int64_t n_flame, const int64_t* flame_tets, int64_t ref_tet,
+                           const double* x_ref, const double* n_ref, double nlocal,
+                           int32_t* pattern_id, int32_t* mat_id, int64_t* nnz);
+/* Values of a matrix as complex numbers in pattern order (SparseMatrixCSC.nzval). */
+int32_t wae_mat_info(wae_ctx* h, int32_t mat_id, int32_t* pattern_id, int32_t* is_complex, int64_t* nnz);
+int32_t wae_mat_get(wae_ctx* h, int32_t mat_id, double* nzval_complex /* 2*nnz doubles */);
+/* Upload a user matrix (any CSC, e.g. a hand-built Term): builds pattern + values. */
+int32_t wae_mat_set(wae_ctx* h, int64_t dim, const int64_t* colptr, const int64_t* rowval,
+                    const double* nzval_complex, int32_t* pattern_id, int32_t* mat_id);
+int32_t wae_mat_free(wae_ctx* h, int32_t mat_id);
+
+/* ---- operator family:  L(z) = sum_i f_i(z) A_i  on one shared pattern ---------------
+ * Replaces LinOpFam.jl:482-529 (the n_terms allocating sparse adds).  The scalar functions
+ * stay on the host (arbitrary closures); only their values cross the boundary.              */
+int32_t wae_family_create(wae_ctx* h, int32_t n_terms, const int32_t* mat_ids, int32_t* fam_id,
+                          int64_t* nnz_union);
+int32_t wae_family_pattern_get(wae_ctx* h, int32_t fam_id, int64_t* colptr, int64_t* rowval);
+/* Evaluate into one of the family's value slots (slot 0..WAE_FAMILY_SLOTS-1). coeffs: n_terms
+ * interleaved complex; a term whose coefficient is exactly 0 is skipped.                    */
+#define WAE_FAMILY_SLOTS 4
+int32_t wae_combine(wae_ctx* h, int32_t fam_id, const double* coeffs, int32_t slot);
+int32_t wae_family_get(wae_ctx* h, int32_t fam_id, int32_t slot, double* nzval_complex);
+/* Y = op(slot) * X, X and Y dim x nrhs column-major complex host arrays.  trans: 0 N, 1 T, 2 C. */
+int32_t wae_family_spmm(wae_ctx* h, int32_t fam_id, int32_t slot, int32_t trans, int32_t nrhs,
+                        const double* X, double* Y);
+
+/* ---- sparse LU of a family slot -------------------------------------------------------
+ * Replaces SparseArrays.lu / `\` (UMFPACK) at perturbation.jl:329,359, beyn.jl:65 and inside
+ * Arpack.eigs (Householder.jl:100-101).  Symbolic analysis (nested dissection, supernodes,
+ * frontal structure) runs once per family on the host; numeric factorisation and the
+ * triangular solves run on the device.                                                      */
+int32_t wae_lu_analyze(wae_ctx* h, int32_t fam_id, int32_t* lu_id, int64_t* factor_nnz, double* factor_flops);
+int32_t wae_lu_factor(wae_ctx* h, int32_t lu_id, int32_t slot);
+/* In-place solve op(A) X = B; trans as above; X dim x nrhs column-major complex host array. */
+int32_t wae_lu_solve(wae_ctx* h, int32_t lu_id, int32_t trans, int32_t nrhs, double* X);
+
+/* ---- shift-invert Arnoldi: nev eigenpairs of A v = lambda M v nearest 0 ----------------
+ * Replaces Arpack.eigs(A,M;nev,sigma=0,v0) (Householder.jl:100-101, iterative_solvers.jl:132-133).
+ * A is the matrix factorised in lu_id, M the family slot m_slot.  trans=2 gives the adjoint
+ * problem eigs(A',M').  lam: nev complex; V: dim x nev complex.                               */
+int32_t wae_eigs_si(wae_ctx* h, int32_t lu_id, int32_t fam_id, int32_t m_slot, int32_t trans,
+                    int32_t nev, const double* v0, double* lam, double* V, int32_t* n_solves);
+
+/* ---- Beyn moments --------------------------------------------------------------------
+ * Replaces the integrand/gauss loop of beyn.jl:62-74,112-138 for the nodes handed in:
+ *   A_p += w_j z_j^p L(z_j)^{-1} V,  p = 0..n_mom-1, V = first l identity columns.
+ * coeffs: n_nodes x n_terms complex (host-evaluated term scalars at each node).
+ * A_out: device pointer (dim x l x n_mom complex, column-major) accumulated in place, so that
+ * the caller can all-reduce it over ranks with NCCL (torch.distributed).                    */
+int32_t wae_beyn_moments(wae_ctx* h, int32_t fam_id, int32_t lu_id, int32_t n_nodes,
+                         const double* z, const double* w, const double* coeffs,
+                         int32_t l, int32_t n_mom, void* A_out_device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WAE_B200_H */

@@ -1,0 +1,525 @@
+// C-ABI entry points of libwae_b200 (see include/wae_b200.h): context, mesh, patterns,
+// assembly, operator family (combine / SpMM).  LU, Arnoldi and Beyn live in lu_api.cu.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+
+#include "lu.h"
+#include "wae_internal.h"
+
+void wae_launch_flame(wae_ctx* h, const int32_t* d_tets, int64_t n, const int32_t* d_rowpos, double* d_S, double* d_vol,
+                      int64_t ref_tet, const double* x_ref, const double* n_ref, double fac, double* d_G,
+                      const int32_t* d_colsrc, int64_t nrows, int ncols, double* d_out);
+
+#define WAE_API_BEGIN \
+  if (!h) return WAE_E_INVALID; \
+  try {
+#define WAE_API_END                       \
+  }                                       \
+  catch (const WaeError& e) {             \
+    h->err = e.msg;                       \
+    return e.code;                        \
+  }                                       \
+  catch (const std::bad_alloc&) {         \
+    h->err = "host allocation failed";    \
+    return WAE_E_NOMEM;                   \
+  }                                       \
+  catch (const std::exception& e) {       \
+    h->err = e.what();                    \
+    return WAE_E_INVALID;                 \
+  }                                       \
+  return WAE_OK;
+
+extern "C" {
+
+int32_t wae_create(wae_ctx** out, int32_t device, int32_t index_base) {
+  if (!out || (index_base != 0 && index_base != 1)) return WAE_E_INVALID;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device < 0 || device >= ndev) return WAE_E_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return WAE_E_CUDA;
+  wae_ctx* h = new wae_ctx();
+  h->device = device;
+  h->base = index_base;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) h->sm_count = prop.multiProcessorCount;
+  cudaEventCreate(&h->ev0);
+  cudaEventCreate(&h->ev1);
+  *out = h;
+  return WAE_OK;
+}
+
+int32_t wae_destroy(wae_ctx* h) {
+  if (!h) return WAE_E_INVALID;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  h->lus.clear();
+  h->fams.clear();
+  h->mats.clear();
+  h->patterns.clear();
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  delete h;
+  return WAE_OK;
+}
+
+const char* wae_last_error(wae_ctx* h) { return h ? h->err.c_str() : "null context"; }
+
+int32_t wae_set_stream(wae_ctx* h, void* s) {
+  if (!h) return WAE_E_INVALID;
+  h->stream = (cudaStream_t)s;
+  return WAE_OK;
+}
+
+int32_t wae_sync(wae_ctx* h) {
+  WAE_API_BEGIN
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  WAE_API_END
+}
+
+int64_t wae_launch_count(wae_ctx* h) { return h ? h->launches : -1; }
+
+double wae_last_ms(wae_ctx* h, const char* phase) {
+  if (!h || !phase) return -1.0;
+  auto it = h->last_ms.find(phase);
+  return it == h->last_ms.end() ? -1.0 : it->second;
+}
+
+// ---- mesh -------------------------------------------------------------------------------
+int32_t wae_mesh_set(wae_ctx* h, int32_t order, int64_t n_pts, const double* xyz, int64_t n_tet, const uint32_t* tets,
+                     int64_t n_tri, const uint32_t* tris, int64_t dim) {
+  WAE_API_BEGIN
+  if (order != 1 && order != 2) WAE_THROW(WAE_E_INVALID, "order must be 1 (:lin) or 2 (:quad)");
+  if (n_pts <= 0 || !xyz || n_tet < 0 || n_tri < 0 || dim < n_pts) WAE_THROW(WAE_E_INVALID, "bad mesh sizes");
+  CUDA_CHECK(cudaSetDevice(h->device));
+  h->order = order;
+  h->nloc = order == 1 ? 4 : 10;
+  h->nloc3 = order == 1 ? 3 : 6;
+  h->n_pts = n_pts; h->n_tet = n_tet; h->n_tri = n_tri; h->dim = dim;
+  h->xyz.assign(xyz, xyz + 3 * n_pts);
+  auto conv = [&](const uint32_t* src, int64_t n, std::vector<uint32_t>& dst) {
+    dst.resize(n);
+    for (int64_t i = 0; i < n; i++) {
+      int64_t v = (int64_t)src[i] - h->base;
+      if (v < 0 || v >= dim) WAE_THROW(WAE_E_INVALID, "element DOF index %lld out of range [0,%lld)", (long long)v, (long long)dim);
+      dst[i] = (uint32_t)v;
+    }
+  };
+  conv(tets, n_tet * h->nloc, h->tets);
+  conv(tris, n_tri * h->nloc3, h->tris);
+  for (int64_t e = 0; e < n_tet; e++)
+    for (int k = 0; k < 4; k++)
+      if (h->tets[e * h->nloc + k] >= (uint64_t)n_pts) WAE_THROW(WAE_E_INVALID, "tet %lld: vertex DOF >= n_pts", (long long)e);
+  h->d_xyz.upload(h->xyz, h->stream);
+  h->d_tets.upload(h->tets, h->stream);
+  h->d_tris.upload(h->tris, h->stream);
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  WAE_API_END
+}
+
+// ---- patterns ---------------------------------------------------------------------------
+static int new_pattern(wae_ctx* h) {
+  h->patterns.emplace_back(new Pattern());
+  return (int)h->patterns.size() - 1;
+}
+
+static void upload_pattern(wae_ctx* h, Pattern& P) {
+  P.d_colptr.upload(P.colptr, h->stream);
+  P.d_rowval.upload(P.rowval, h->stream);
+}
+
+int32_t wae_pattern_build(wae_ctx* h, int32_t elem_kind, int64_t n_elem, const int64_t* elem_ids, int32_t* pattern_id,
+                          int64_t* nnz) {
+  WAE_API_BEGIN
+  if (!h->order) WAE_THROW(WAE_E_INVALID, "wae_mesh_set has not been called");
+  if (elem_kind != 2 && elem_kind != 3) WAE_THROW(WAE_E_INVALID, "elem_kind must be 2 (triangles) or 3 (tetrahedra)");
+  CUDA_CHECK(cudaSetDevice(h->device));
+  int64_t total = elem_kind == 3 ? h->n_tet : h->n_tri;
+  int id = new_pattern(h);
+  Pattern& P = *h->patterns[id];
+  P.elem_kind = elem_kind;
+  if (elem_ids) {
+    P.elems.resize(n_elem);
+    for (int64_t i = 0; i < n_elem; i++) {
+      int64_t e = elem_ids[i] - h->base;
+      if (e < 0 || e >= total) WAE_THROW(WAE_E_INVALID, "element id %lld out of range", (long long)elem_ids[i]);
+      P.elems[i] = e;
+    }
+  } else {
+    P.elems.resize(total);
+    std::iota(P.elems.begin(), P.elems.end(), 0);
+  }
+  const uint32_t* conn = elem_kind == 3 ? h->tets.data() : h->tris.data();
+  int nloc = elem_kind == 3 ? h->nloc : h->nloc3;
+  wae_build_pattern_from_elements(conn, nloc, P.elems, h->dim, P);
+  upload_pattern(h, P);
+  std::vector<int32_t> e32(P.elems.begin(), P.elems.end());
+  P.d_elems.upload(e32, h->stream);
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  if (pattern_id) *pattern_id = id;
+  if (nnz) *nnz = P.nnz;
+  WAE_API_END
+}
+
+int32_t wae_pattern_get(wae_ctx* h, int32_t pattern_id, int64_t* colptr, int64_t* rowval) {
+  WAE_API_BEGIN
+  Pattern& P = h->pat(pattern_id);
+  if (colptr)
+    for (int64_t j = 0; j <= P.dim; j++) colptr[j] = P.colptr[j] + h->base;
+  if (rowval)
+    for (int64_t k = 0; k < P.nnz; k++) rowval[k] = (int64_t)P.rowval[k] + h->base;
+  WAE_API_END
+}
+
+static void ensure_slotmap(wae_ctx* h, Pattern& P) {
+  if (P.slotmap_built) return;
+  const uint32_t* conn = P.elem_kind == 3 ? h->tets.data() : h->tris.data();
+  int nloc = P.elem_kind == 3 ? h->nloc : h->nloc3;
+  std::vector<int32_t> sm;
+  wae_build_slotmap(conn, nloc, P, sm);
+  P.d_slotmap.upload(sm, h->stream);
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  P.slotmap_built = true;
+}
+
+static int new_matrix(wae_ctx* h, int pattern, bool is_complex, int64_t nnz) {
+  h->mats.emplace_back(new Matrix());
+  Matrix& M = *h->mats.back();
+  M.pattern = pattern;
+  M.is_complex = is_complex;
+  M.d_val.alloc((size_t)nnz * (is_complex ? 2 : 1));
+  CUDA_CHECK(cudaMemsetAsync(M.d_val.p, 0, M.d_val.n * sizeof(double), h->stream));
+  return (int)h->mats.size() - 1;
+}
+
+static void upload_c(wae_ctx* h, Pattern& P, const double* c, int c_per_elem, DevBuf<double>& d_c) {
+  if (!c) WAE_THROW(WAE_E_INVALID, "speed-of-sound array is NULL");
+  int need = P.elem_kind == 3 ? 4 : 3;
+  if (c_per_elem != 1 && c_per_elem != need) WAE_THROW(WAE_E_INVALID, "c_per_elem must be 1 or %d", need);
+  d_c.upload(c, P.elems.size() * (size_t)c_per_elem, h->stream);
+}
+
+int32_t wae_assemble(wae_ctx* h, int32_t pattern_id, int32_t kind, const double* c, int32_t c_per_elem, double scale,
+                     int32_t* mat_id) {
+  WAE_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(h->device));
+  Pattern& P = h->pat(pattern_id);
+  if (kind == WAE_OP_BOUNDARY ? P.elem_kind != 2 : P.elem_kind != 3)
+    WAE_THROW(WAE_E_INVALID, "operator kind %d does not match the pattern's element kind", kind);
+  if (kind < WAE_OP_MASS || kind > WAE_OP_BOUNDARY) WAE_THROW(WAE_E_INVALID, "unknown operator kind %d", kind);
+  const bool use_gather = kind == WAE_OP_MASS && !getenv("WAE_FORCE_ATOMIC");
+  if (use_gather) wae_ensure_gather(h, P); else ensure_slotmap(h, P);
+  DevBuf<double> d_c;
+  if (kind != WAE_OP_MASS) upload_c(h, P, c, c_per_elem, d_c);
+  int id = new_matrix(h, pattern_id, kind == WAE_OP_BOUNDARY, P.nnz);
+  Matrix& M = *h->mats[id];
+  PhaseTimer t(h, "assemble");
+  if (kind == WAE_OP_MASS && use_gather)
+    wae_launch_assemble_gather(h, P, nullptr, M.d_val.p, nullptr, scale);
+  else if (kind == WAE_OP_MASS)
+    wae_launch_assemble_atomic(h, P, 1, nullptr, 1, scale, M.d_val.p, nullptr);
+  else if (kind == WAE_OP_STIFF) {
+    if (scale != 1.0) WAE_THROW(WAE_E_INVALID, "scale != 1 is only supported for WAE_OP_MASS / WAE_OP_BOUNDARY");
+    wae_launch_assemble_atomic(h, P, 2, d_c.p, c_per_elem, 1.0, nullptr, M.d_val.p);
+  } else
+    wae_launch_assemble_atomic(h, P, 0, d_c.p, c_per_elem, scale, M.d_val.p, nullptr);
+  t.stop();
+  if (mat_id) *mat_id = id;
+  WAE_API_END
+}
+
+int32_t wae_assemble_mk(wae_ctx* h, int32_t pattern_id, const double* c, int32_t c_per_elem, int32_t* mass_id,
+                        int32_t* stiff_id) {
+  WAE_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(h->device));
+  Pattern& P = h->pat(pattern_id);
+  if (P.elem_kind != 3) WAE_THROW(WAE_E_INVALID, "wae_assemble_mk needs a tetrahedral pattern");
+  DevBuf<double> d_c;
+  upload_c(h, P, c, c_per_elem, d_c);
+  int im = new_matrix(h, pattern_id, false, P.nnz);
+  int ik = new_matrix(h, pattern_id, false, P.nnz);
+  if (c_per_elem == 1 && !getenv("WAE_FORCE_ATOMIC")) {
+    wae_ensure_gather(h, P);
+    PhaseTimer t(h, "assemble");
+    wae_launch_assemble_gather(h, P, d_c.p, h->mats[im]->d_val.p, h->mats[ik]->d_val.p, 1.0);
+    t.stop();
+  } else {
+    ensure_slotmap(h, P);
+    PhaseTimer t(h, "assemble");
+    wae_launch_assemble_atomic(h, P, 3, d_c.p, c_per_elem, 1.0, h->mats[im]->d_val.p, h->mats[ik]->d_val.p);
+    t.stop();
+  }
+  if (mass_id) *mass_id = im;
+  if (stiff_id) *stiff_id = ik;
+  WAE_API_END
+}
+
+int32_t wae_assemble_flame(wae_ctx* h, int64_t n_flame, const int64_t* flame_tets, int64_t ref_tet, const double* x_ref,
+                           const double* n_ref, double nlocal, int32_t* pattern_id, int32_t* mat_id, int64_t* nnz) {
+  WAE_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(h->device));
+  if (!h->order || n_flame <= 0 || !flame_tets || !x_ref || !n_ref) WAE_THROW(WAE_E_INVALID, "bad flame arguments");
+  ref_tet -= h->base;
+  if (ref_tet < 0 || ref_tet >= h->n_tet) WAE_THROW(WAE_E_INVALID, "reference tetrahedron out of range");
+  const int nloc = h->nloc;
+  std::vector<int32_t> ft(n_flame);
+  std::vector<int32_t> rows;
+  rows.reserve(n_flame * nloc);
+  for (int64_t i = 0; i < n_flame; i++) {
+    int64_t e = flame_tets[i] - h->base;
+    if (e < 0 || e >= h->n_tet) WAE_THROW(WAE_E_INVALID, "flame tetrahedron out of range");
+    ft[i] = (int32_t)e;
+    for (int k = 0; k < nloc; k++) rows.push_back((int32_t)h->tets[e * nloc + k]);
+  }
+  std::vector<int32_t> urows(rows);
+  std::sort(urows.begin(), urows.end());
+  urows.erase(std::unique(urows.begin(), urows.end()), urows.end());
+  std::vector<int32_t> rowpos(rows.size());
+  for (size_t i = 0; i < rows.size(); i++)
+    rowpos[i] = (int32_t)(std::lower_bound(urows.begin(), urows.end(), rows[i]) - urows.begin());
+  // columns: DOFs of the reference tet, sorted; colsrc[c] = local index in the tet
+  std::vector<std::pair<int32_t, int32_t>> cols;
+  for (int k = 0; k < nloc; k++) cols.emplace_back((int32_t)h->tets[ref_tet * nloc + k], k);
+  std::sort(cols.begin(), cols.end());
+  int pid = new_pattern(h);
+  Pattern& P = *h->patterns[pid];
+  P.dim = h->dim;
+  P.colptr.assign(h->dim + 1, 0);
+  int64_t nr = (int64_t)urows.size();
+  for (auto& cpair : cols) P.colptr[cpair.first + 1] = nr;
+  for (int64_t j = 0; j < h->dim; j++) P.colptr[j + 1] += P.colptr[j];
+  P.nnz = nr * nloc;
+  P.rowval.resize(P.nnz);
+  for (int c = 0; c < nloc; c++) std::copy(urows.begin(), urows.end(), P.rowval.begin() + (size_t)c * nr);
+  upload_pattern(h, P);
+  std::vector<int32_t> colsrc(nloc);
+  for (int c = 0; c < nloc; c++) colsrc[c] = cols[c].second;
+  DevBuf<int32_t> d_ft, d_rowpos, d_colsrc;
+  DevBuf<double> d_S, d_G;
+  d_ft.upload(ft, h->stream);
+  d_rowpos.upload(rowpos, h->stream);
+  d_colsrc.upload(colsrc, h->stream);
+  d_S.alloc(nr + 1);
+  d_G.alloc(nloc);
+  CUDA_CHECK(cudaMemsetAsync(d_S.p, 0, (nr + 1) * sizeof(double), h->stream));
+  int mid = new_matrix(h, pid, false, P.nnz);
+  PhaseTimer t(h, "assemble");
+  wae_launch_flame(h, d_ft.p, n_flame, d_rowpos.p, d_S.p, d_S.p + nr, ref_tet, x_ref, n_ref, -nlocal, d_G.p, d_colsrc.p, nr,
+                   nloc, h->mats[mid]->d_val.p);
+  t.stop();
+  if (pattern_id) *pattern_id = pid;
+  if (mat_id) *mat_id = mid;
+  if (nnz) *nnz = P.nnz;
+  WAE_API_END
+}
+
+int32_t wae_mat_info(wae_ctx* h, int32_t mat_id, int32_t* pattern_id, int32_t* is_complex, int64_t* nnz) {
+  WAE_API_BEGIN
+  Matrix& M = h->mat(mat_id);
+  if (pattern_id) *pattern_id = M.pattern;
+  if (is_complex) *is_complex = M.is_complex;
+  if (nnz) *nnz = h->pat(M.pattern).nnz;
+  WAE_API_END
+}
+
+int32_t wae_mat_get(wae_ctx* h, int32_t mat_id, double* out) {
+  WAE_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(h->device));
+  Matrix& M = h->mat(mat_id);
+  int64_t nnz = h->pat(M.pattern).nnz;
+  if (M.is_complex) {
+    CUDA_CHECK(cudaMemcpyAsync(out, M.d_val.p, 2 * nnz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  } else {
+    std::vector<double> tmp(nnz);
+    CUDA_CHECK(cudaMemcpyAsync(tmp.data(), M.d_val.p, nnz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    for (int64_t k = 0; k < nnz; k++) {
+      out[2 * k] = tmp[k];
+      out[2 * k + 1] = 0.0;
+    }
+  }
+  WAE_API_END
+}
+
+int32_t wae_mat_set(wae_ctx* h, int64_t dim, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+                    int32_t* pattern_id, int32_t* mat_id) {
+  WAE_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(h->device));
+  if (dim <= 0 || !colptr || !rowval || !nzval) WAE_THROW(WAE_E_INVALID, "bad matrix arguments");
+  if (h->dim == 0) h->dim = dim;
+  if (dim != h->dim) WAE_THROW(WAE_E_INVALID, "matrix dimension %lld differs from the context dimension %lld", (long long)dim, (long long)h->dim);
+  int pid = new_pattern(h);
+  Pattern& P = *h->patterns[pid];
+  P.dim = dim;
+  P.colptr.resize(dim + 1);
+  for (int64_t j = 0; j <= dim; j++) P.colptr[j] = colptr[j] - h->base;
+  P.nnz = P.colptr[dim];
+  if (P.colptr[0] != 0 || P.nnz < 0 || P.nnz >= ((int64_t)1 << 31)) WAE_THROW(WAE_E_INVALID, "bad colptr");
+  P.rowval.resize(P.nnz);
+  for (int64_t j = 0; j < dim; j++)
+    for (int64_t k = P.colptr[j]; k < P.colptr[j + 1]; k++) {
+      int64_t r = rowval[k] - h->base;
+      if (r < 0 || r >= dim || (k > P.colptr[j] && r <= P.rowval[k - 1])) WAE_THROW(WAE_E_INVALID, "row indices must be sorted and unique inside columns");
+      P.rowval[k] = (int32_t)r;
+    }
+  upload_pattern(h, P);
+  int mid = new_matrix(h, pid, true, P.nnz);
+  CUDA_CHECK(cudaMemcpyAsync(h->mats[mid]->d_val.p, nzval, 2 * P.nnz * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  if (pattern_id) *pattern_id = pid;
+  if (mat_id) *mat_id = mid;
+  WAE_API_END
+}
+
+int32_t wae_mat_free(wae_ctx* h, int32_t mat_id) {
+  WAE_API_BEGIN
+  h->mat(mat_id);
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  h->mats[mat_id].reset();
+  WAE_API_END
+}
+
+// ---- family ---------------------------------------------------------------------------------
+int32_t wae_family_create(wae_ctx* h, int32_t n_terms, const int32_t* mat_ids, int32_t* fam_id, int64_t* nnz_union) {
+  WAE_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(h->device));
+  if (n_terms <= 0 || !mat_ids) WAE_THROW(WAE_E_INVALID, "empty family");
+  std::unique_ptr<Family> Fp(new Family());
+  Family& F = *Fp;
+  F.n_terms = n_terms;
+  F.mats.assign(mat_ids, mat_ids + n_terms);
+  int64_t dim = -1;
+  std::vector<int> pats;
+  for (int t = 0; t < n_terms; t++) {
+    Matrix& M = h->mat(mat_ids[t]);
+    Pattern& P = h->pat(M.pattern);
+    if (dim < 0) dim = P.dim;
+    if (P.dim != dim) WAE_THROW(WAE_E_INVALID, "terms have different dimensions");
+    if (std::find(pats.begin(), pats.end(), M.pattern) == pats.end()) pats.push_back(M.pattern);
+  }
+  // union pattern: reuse the largest pattern if it contains all others, else merge column-wise
+  int big = pats[0];
+  for (int p : pats)
+    if (h->pat(p).nnz > h->pat(big).nnz) big = p;
+  auto contains = [&](const Pattern& A, const Pattern& B) {  // B subset of A ?
+    for (int64_t j = 0; j < dim; j++) {
+      const int32_t *a = A.rowval.data() + A.colptr[j], *ae = A.rowval.data() + A.colptr[j + 1];
+      const int32_t *b = B.rowval.data() + B.colptr[j], *be = B.rowval.data() + B.colptr[j + 1];
+      if (!std::includes(a, ae, b, be)) return false;
+    }
+    return true;
+  };
+  bool all_in = true;
+  for (int p : pats)
+    if (p != big && !contains(h->pat(big), h->pat(p))) all_in = false;
+  int upid;
+  if (all_in) {
+    upid = big;
+  } else {
+    upid = new_pattern(h);
+    Pattern& U = *h->patterns[upid];
+    U.dim = dim;
+    U.colptr.assign(dim + 1, 0);
+    std::vector<int32_t> buf, tmp;
+    for (int pass = 0; pass < 2; pass++) {
+      for (int64_t j = 0; j < dim; j++) {
+        buf.clear();
+        for (int p : pats) {
+          const Pattern& A = h->pat(p);
+          tmp.clear();
+          std::set_union(buf.begin(), buf.end(), A.rowval.begin() + A.colptr[j], A.rowval.begin() + A.colptr[j + 1],
+                         std::back_inserter(tmp));
+          buf.swap(tmp);
+        }
+        if (pass == 0)
+          U.colptr[j + 1] = U.colptr[j] + (int64_t)buf.size();
+        else
+          std::copy(buf.begin(), buf.end(), U.rowval.begin() + U.colptr[j]);
+      }
+      if (pass == 0) {
+        U.nnz = U.colptr[dim];
+        if (U.nnz >= ((int64_t)1 << 31)) WAE_THROW(WAE_E_INVALID, "union pattern too large");
+        U.rowval.resize(U.nnz);
+      }
+    }
+    upload_pattern(h, U);
+  }
+  F.pattern = upid;
+  Pattern& U = h->pat(upid);
+  F.identity.resize(n_terms);
+  F.d_map.resize(n_terms);
+  for (int t = 0; t < n_terms; t++) {
+    Matrix& M = h->mat(mat_ids[t]);
+    if (M.pattern == upid) {
+      F.identity[t] = true;
+      continue;
+    }
+    F.identity[t] = false;
+    Pattern& A = h->pat(M.pattern);
+    std::vector<int32_t> map(A.nnz);
+    for (int64_t j = 0; j < dim; j++) {
+      const int32_t* ub = U.rowval.data() + U.colptr[j];
+      const int32_t* ue = U.rowval.data() + U.colptr[j + 1];
+      for (int64_t k = A.colptr[j]; k < A.colptr[j + 1]; k++)
+        map[k] = (int32_t)(std::lower_bound(ub, ue, A.rowval[k]) - U.rowval.data());
+    }
+    F.d_map[t].upload(map, h->stream);
+  }
+  for (int s = 0; s < WAE_FAMILY_SLOTS; s++) F.slot[s].alloc(0);
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  h->fams.emplace_back(std::move(Fp));
+  if (fam_id) *fam_id = (int)h->fams.size() - 1;
+  if (nnz_union) *nnz_union = U.nnz;
+  WAE_API_END
+}
+
+int32_t wae_family_pattern_get(wae_ctx* h, int32_t fam_id, int64_t* colptr, int64_t* rowval) {
+  if (!h) return WAE_E_INVALID;
+  try {
+    return wae_pattern_get(h, h->fam(fam_id).pattern, colptr, rowval);
+  } catch (const WaeError& e) {
+    h->err = e.msg;
+    return e.code;
+  }
+}
+
+int32_t wae_combine(wae_ctx* h, int32_t fam_id, const double* coeffs, int32_t slot) {
+  WAE_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(h->device));
+  if (!coeffs) WAE_THROW(WAE_E_INVALID, "coeffs is NULL");
+  PhaseTimer t(h, "combine");
+  wae_combine_device(h, h->fam(fam_id), coeffs, slot);
+  t.stop();
+  WAE_API_END
+}
+
+int32_t wae_family_get(wae_ctx* h, int32_t fam_id, int32_t slot, double* out) {
+  WAE_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(h->device));
+  Family& F = h->fam(fam_id);
+  if (slot < 0 || slot >= WAE_FAMILY_SLOTS || !F.slot[slot].p) WAE_THROW(WAE_E_INVALID, "family slot %d is empty", slot);
+  CUDA_CHECK(cudaMemcpyAsync(out, F.slot[slot].p, 2 * h->pat(F.pattern).nnz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  WAE_API_END
+}
+
+int32_t wae_family_spmm(wae_ctx* h, int32_t fam_id, int32_t slot, int32_t trans, int32_t nrhs, const double* X, double* Y) {
+  WAE_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(h->device));
+  Family& F = h->fam(fam_id);
+  if (slot < 0 || slot >= WAE_FAMILY_SLOTS || !F.slot[slot].p) WAE_THROW(WAE_E_INVALID, "family slot %d is empty", slot);
+  if (trans < 0 || trans > 2 || nrhs <= 0 || !X || !Y) WAE_THROW(WAE_E_INVALID, "bad spmm arguments");
+  int64_t dim = h->pat(F.pattern).dim;
+  DevBuf<double> dX, dY;
+  dX.upload(X, 2 * dim * nrhs, h->stream);
+  dY.alloc(2 * dim * nrhs);
+  PhaseTimer t(h, "spmv");
+  wae_spmm_device(h, F, slot, trans, nrhs, (const cplx*)dX.p, (cplx*)dY.p);
+  t.stop();
+  CUDA_CHECK(cudaMemcpyAsync(Y, dY.p, 2 * dim * nrhs * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  WAE_API_END
+}
+
+}  // extern "C"

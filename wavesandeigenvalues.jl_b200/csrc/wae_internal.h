@@ -1,0 +1,190 @@
+// Internal data structures of libwae_b200 (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/wae_b200.h"
+
+typedef double2 cplx;  // interleaved complex fp64 (x = re, y = im)
+
+struct WaeError {
+  int code;
+  std::string msg;
+};
+
+#define WAE_THROW(code, ...)                         \
+  do {                                               \
+    char _b[512];                                    \
+    snprintf(_b, sizeof(_b), __VA_ARGS__);           \
+    throw WaeError{(code), std::string(_b)};         \
+  } while (0)
+
+#define CUDA_CHECK(x)                                                                        \
+  do {                                                                                       \
+    cudaError_t _e = (x);                                                                    \
+    if (_e != cudaSuccess)                                                                   \
+      WAE_THROW(WAE_E_CUDA, "%s failed at %s:%d: %s", #x, __FILE__, __LINE__, cudaGetErrorString(_e)); \
+  } while (0)
+
+// RAII device buffer
+template <typename T>
+struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DevBuf& operator=(DevBuf&& o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+  }
+  void alloc(size_t count) {
+    release();
+    if (count == 0) return;
+    cudaError_t e = cudaMalloc((void**)&p, count * sizeof(T));
+    if (e != cudaSuccess) WAE_THROW(WAE_E_NOMEM, "cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+    n = count;
+  }
+  void upload(const T* h, size_t count, cudaStream_t s) {
+    if (n < count) alloc(count);
+    if (count) CUDA_CHECK(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+  }
+  void upload(const std::vector<T>& v, cudaStream_t s) { upload(v.data(), v.size(), s); }
+};
+
+// CSC pattern, 0-based, row indices sorted inside columns.
+struct Pattern {
+  int64_t dim = 0, nnz = 0;
+  std::vector<int64_t> colptr;  // dim+1
+  std::vector<int32_t> rowval;  // nnz
+  DevBuf<int64_t> d_colptr;
+  DevBuf<int32_t> d_rowval;
+  // element list the pattern was built from (kind 3 tets / 2 tris / 0 user)
+  int elem_kind = 0;
+  std::vector<int64_t> elems;   // 0-based element ids
+  DevBuf<int32_t> d_elems;
+  // owner-computes gather program (assembly): built lazily, see assembly_symbolic.cpp
+  struct Gather {
+    int n_patch = 0, max_tets = 0;
+    DevBuf<int64_t> d_patch_row_ptr;      // owned columns of patch p: patch_rows[patch_row_ptr[p] .. patch_row_ptr[p+1])
+    DevBuf<int64_t> d_patch_tet_ptr;      // staged elements of patch p: patch_tets[patch_tet_ptr[p] .. )
+    DevBuf<int32_t> d_patch_rows;         // owned DOF columns
+    DevBuf<int32_t> d_patch_tets;         // positions in the pattern's element list
+    DevBuf<int64_t> d_col_slot_ptr;       // per owned column (same order as patch_rows): start in d_slot_cnt
+    DevBuf<int64_t> d_col_src_ptr;        // per owned column: start in d_src
+    DevBuf<uint8_t> d_slot_cnt;           // number of sources of each owned nonzero
+    DevBuf<uint16_t> d_src;               // packed sources: tet_local * 64 + sym
+    int64_t n_src = 0, n_staged = 0;
+    bool built = false;
+  } gather;
+  // scatter map for the atomic (first-generation) kernels: n_loc^2 slots per element
+  DevBuf<int32_t> d_slotmap;
+  bool slotmap_built = false;
+};
+
+struct Matrix {
+  int pattern = -1;
+  bool is_complex = false;
+  DevBuf<double> d_val;  // nnz (real) or 2*nnz (complex, interleaved)
+};
+
+struct Family {
+  int n_terms = 0;
+  std::vector<int> mats;
+  int pattern = -1;                        // union pattern id
+  std::vector<bool> identity;              // term pattern == union pattern
+  std::vector<DevBuf<int32_t>> d_map;      // term nz -> union nz (empty if identity)
+  DevBuf<double> slot[WAE_FAMILY_SLOTS];   // complex values, 2*nnz doubles each
+  DevBuf<int32_t> d_tr_perm;               // CSC->CSR permutation for transposed SpMM (lazy)
+  DevBuf<int64_t> d_rowptr;
+  DevBuf<int32_t> d_colidx;
+  bool tr_built = false;
+};
+
+struct LuSolver;  // lu_symbolic.h
+
+struct wae_ctx {
+  int device = 0;
+  int base = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  std::map<std::string, double> last_ms;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int sm_count = 148;
+
+  // mesh
+  int order = 0, nloc = 0, nloc3 = 0;
+  int64_t n_pts = 0, n_tet = 0, n_tri = 0, dim = 0;
+  std::vector<double> xyz;        // 3*n_pts
+  std::vector<uint32_t> tets;     // nloc*n_tet, 0-based
+  std::vector<uint32_t> tris;     // nloc3*n_tri, 0-based
+  DevBuf<double> d_xyz;
+  DevBuf<uint32_t> d_tets, d_tris;
+
+  std::vector<std::unique_ptr<Pattern>> patterns;
+  std::vector<std::unique_ptr<Matrix>> mats;
+  std::vector<std::unique_ptr<Family>> fams;
+  std::vector<std::shared_ptr<LuSolver>> lus;  // shared_ptr: LuSolver is incomplete here
+
+  Pattern& pat(int id) {
+    if (id < 0 || id >= (int)patterns.size() || !patterns[id]) WAE_THROW(WAE_E_INVALID, "unknown pattern id %d", id);
+    return *patterns[id];
+  }
+  Matrix& mat(int id) {
+    if (id < 0 || id >= (int)mats.size() || !mats[id]) WAE_THROW(WAE_E_INVALID, "unknown matrix id %d", id);
+    return *mats[id];
+  }
+  Family& fam(int id) {
+    if (id < 0 || id >= (int)fams.size() || !fams[id]) WAE_THROW(WAE_E_INVALID, "unknown family id %d", id);
+    return *fams[id];
+  }
+};
+
+// timing helper: records ms of a phase on the context stream
+struct PhaseTimer {
+  wae_ctx* h;
+  const char* name;
+  PhaseTimer(wae_ctx* h_, const char* n) : h(h_), name(n) { cudaEventRecord(h->ev0, h->stream); }
+  void stop() {
+    cudaEventRecord(h->ev1, h->stream);
+    cudaEventSynchronize(h->ev1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, h->ev0, h->ev1);
+    h->last_ms[name] = ms;
+  }
+};
+
+// ---- symbolic (host) -------------------------------------------------------------
+void wae_build_pattern_from_elements(const uint32_t* conn, int nloc, const std::vector<int64_t>& elems,
+                                     int64_t dim, Pattern& P);
+void wae_build_slotmap(const uint32_t* conn, int nloc, const Pattern& P, std::vector<int32_t>& slotmap);
+struct GatherHost {
+  std::vector<int64_t> patch_row_ptr, patch_tet_ptr, col_slot_ptr, col_src_ptr;
+  std::vector<int32_t> patch_rows, patch_tets;
+  std::vector<uint8_t> slot_cnt;
+  std::vector<uint16_t> src;
+  int max_tets = 0;
+};
+void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const Pattern& P, int target_tets, GatherHost& G);
+void wae_ensure_gather(wae_ctx* h, Pattern& P);
+
+// ---- kernels launchers (device) ----------------------------------------------------
+void wae_launch_assemble_atomic(wae_ctx* h, Pattern& P, int kind, const double* d_c, int c_per_elem,
+                                double scale, double* d_out_a, double* d_out_b);
+void wae_launch_assemble_gather(wae_ctx* h, Pattern& P, const double* d_c, double* d_mass, double* d_stiff,
+                                double mass_scale);
+void wae_combine_device(wae_ctx* h, Family& F, const double* coeffs_host, int slot);
+void wae_spmm_device(wae_ctx* h, Family& F, int slot, int trans, int nrhs, const cplx* X, cplx* Y);
+void wae_family_ensure_csr(wae_ctx* h, Family& F);

@@ -1,0 +1,163 @@
+"""Host mirror of ``Helmholtz.discretize`` (src/Helmholtz.jl:54-581) over the CUDA assembly kernels.
+
+    L = discretize(mesh, dscrp, C; order="lin"|"quad", mass_weighting=True, output=False)
+
+``dscrp[domain] = (type, data)`` with the reference's types (Julia symbols -> strings):
+  "interior" ()                      M (omega^2) + K                Helmholtz.jl:233-237
+  "mass" ()                          M                              :239-240
+  "stiff" (funcs, args, txt)         K with a custom scalar         :242-249
+  "admittance" (sym, val)            C with omega*sym               :263-275
+  "admittance" (Yfunc,)              C with omega*Y(omega)          :276-279
+  "flame" 9/10-tuple                 Q with n*exp(-i omega tau)     :295-301, 325-344
+  "flame" 6-tuple (custom FTF)       Q with FTF(omega,k)            :302-311
+  "flame" 5-tuple                    Q with the plain parameter FTF :312-319
+  "flameresponse" 7-tuple            Q with eps                     :346-359
+and the auxiliary mass-weighting term -lambda*M_all (:528-540, 571-574).  Bloch periodicity (b=...),
+:speaker sources, :fancyflame and Hermite elements are outside the accelerated path and raise
+NotImplementedError.
+
+What changes relative to the reference is only where the work happens: the per-element loops
+(:411-463, 468-476, 532-539) and ``sparse()`` run as CUDA kernels on a pattern computed once per domain.
+"""
+import numpy as np
+
+from . import _lib
+from .meshutils import aggregate_elements
+from .nlevp import DeviceMatrix, LinearOperatorFamily, Term, exp_delay, generate_z_g_z, get_context, pow1, pow2
+
+
+class Discretization:
+    """Book-keeping of one discretize() call (kept on the family as ``L.discretization``)."""
+
+    def __init__(self):
+        self.patterns = {}   # (kind, domain) -> pattern id
+        self.timing = {}
+        self.n_tet = self.n_tri = self.dim = 0
+
+
+def discretize(mesh, dscrp, C, order="lin", b="__none__", mass_weighting=True, source=False, output=False, ctx=None):
+    if b != "__none__":
+        raise NotImplementedError("Bloch-periodic discretisation is not on the accelerated path yet")
+    if source:
+        raise NotImplementedError("source=True (experimental in the reference) is not on the accelerated path")
+    ctx = ctx or get_context()
+    triangles, tetrahedra, dim = aggregate_elements(mesh, order)
+    npts = mesh.points.shape[1]
+    C = np.asarray(C, dtype=float)
+    # Helmholtz.jl:59-74
+    if len(C) == len(mesh.tetrahedra):
+        C_tet = C
+        if mesh.tri2tet is None:
+            mesh.link_triangles_to_tetrahedra()
+        C_tri = C[mesh.tri2tet]
+    elif len(C) == npts:
+        C_tet = C[mesh.tetrahedra[:, :4]]
+        C_tri = C[mesh.triangles[:, :3]] if len(mesh.triangles) else np.zeros((0, 3))
+    else:
+        raise ValueError("length(C) must be the number of tetrahedra or the number of points")
+
+    ctx.mesh_set(1 if order == "lin" else 2, mesh.points.T, tetrahedra, triangles, dim)
+    L = LinearOperatorFamily(["ω", "λ"], [0.0, float("inf")])
+    disc = Discretization()
+    disc.n_tet, disc.n_tri, disc.dim = len(tetrahedra), len(triangles), dim
+    L.discretization = disc
+
+    def dm(mid):
+        return DeviceMatrix(ctx, dim, [(mid, 1.0)])
+
+    def tet_pattern(domain):
+        key = (3, domain)
+        if key not in disc.patterns:
+            s = np.asarray(mesh.domains[domain]["simplices"], dtype=np.int64)
+            full = len(s) == len(tetrahedra) and np.array_equal(s, np.arange(len(tetrahedra)))
+            full_key = (3, "__all__")
+            if full and full_key in disc.patterns:
+                disc.patterns[key] = disc.patterns[full_key]
+            else:
+                disc.patterns[key] = ctx.pattern_build(3, None if full else s)[0]
+                if full:
+                    disc.patterns[full_key] = disc.patterns[key]
+        return disc.patterns[key]
+
+    for domain, (typ, data) in dscrp.items():
+        simplices = np.asarray(mesh.domains[domain]["simplices"], dtype=np.int64)
+        if typ == "interior":
+            pid = tet_pattern(domain)
+            im, ik = ctx.assemble_mk(pid, C_tet[simplices])
+            disc.timing[f"{domain}/MK_ms"] = ctx.last_ms("assemble")
+            L.push(Term(dm(im), (pow2,), (("ω",),), "ω^2", "M"))
+            L.push(Term(dm(ik), (), (), "", "K"))
+        elif typ == "mass":
+            pid = tet_pattern(domain)
+            L.push(Term(dm(ctx.assemble(pid, _lib.OP_MASS)), (pow2,), (("ω",),), "ω^2", "M"))
+        elif typ == "stiff":
+            funcs, args, txt = data
+            for a in args:
+                for p in a:
+                    L.params[p] = 0.0
+            pid = tet_pattern(domain)
+            L.push(Term(dm(ctx.assemble(pid, _lib.OP_STIFF, C_tet[simplices])), tuple(funcs), tuple(args), txt, "K"))
+        elif typ == "admittance":
+            if len(data) == 2:
+                adm_sym, adm_val = data
+                L.params.setdefault(adm_sym, complex(adm_val))
+                bfunc, barg, btxt = (pow1, pow1), (("ω",), (adm_sym,)), "ω*" + adm_sym
+            elif len(data) == 1:
+                bfunc, barg, btxt = (generate_z_g_z(data[0]),), (("ω",),), "ω*Y(ω)"
+            else:
+                raise NotImplementedError("state-space admittance (A,B,C,D) is not on the accelerated path")
+            pid = ctx.pattern_build(2, simplices)[0]
+            disc.patterns[(2, domain)] = pid
+            L.push(Term(dm(ctx.assemble(pid, _lib.OP_BOUNDARY, C_tri[simplices])), bfunc, barg, btxt, "C"))
+        elif typ in ("flame", "flameresponse"):
+            ref_idx = -1
+            if typ == "flame" and len(data) == 9:
+                gamma, rho, nglobal, x_ref, n_ref, n_sym, tau_sym, n_val, tau_val = data
+                kind = "ntau"
+            elif typ == "flame" and len(data) == 10:
+                gamma, rho, nglobal, ref_idx, x_ref, n_ref, n_sym, tau_sym, n_val, tau_val = data
+                kind = "ntau"
+            elif typ == "flame" and len(data) == 6:
+                gamma, rho, nglobal, x_ref, n_ref, FTF = data
+                kind = "ftf"
+            elif typ == "flame" and len(data) == 5:
+                gamma, rho, nglobal, x_ref, n_ref = data
+                kind = "plain"
+            elif typ == "flameresponse":
+                gamma, rho, nglobal, x_ref, n_ref, eps_sym, eps_val = data
+                kind = "eps"
+            else:
+                raise ValueError("Data length does not match :flame option!")
+            nlocal = (gamma - 1) / rho * nglobal / mesh.compute_size(domain)
+            if kind == "ntau":
+                L.params.setdefault(n_sym, complex(n_val))
+                L.params.setdefault(tau_sym, complex(tau_val))
+                ffunc, farg, ftxt = (pow1, exp_delay), ((n_sym,), ("ω", tau_sym)), f"{n_sym}*exp(-iω{tau_sym})"
+            elif kind == "ftf":
+                ffunc, farg, ftxt = (FTF,), (("ω",),), "FTF(ω)"
+            elif kind == "plain":
+                L.params["FTF"] = 0.0
+                ffunc, farg, ftxt = (pow1,), (("FTF",),), "FTF"
+            else:
+                L.params.setdefault(eps_sym, complex(eps_val))
+                ffunc, farg, ftxt = (pow1,), ((eps_sym,),), eps_sym
+            if ref_idx < 0:
+                ref_idx = mesh.find_tetrahedron_containing_point(x_ref)
+                if ref_idx < 0:
+                    raise ValueError("reference point x_ref is not inside the mesh")
+            if ref_idx in set(simplices.tolist()):
+                print("Warning: your reference point is inside the domain of heat release. (short-circuited FTF!)")
+            pid, mid, _ = ctx.assemble_flame(simplices, ref_idx, x_ref, n_ref, nlocal)
+            disc.patterns[("Q", domain)] = pid
+            L.push(Term(dm(mid), ffunc, farg, ftxt, "Q"))
+        else:
+            raise NotImplementedError(f"descriptor type {typ!r} is not on the accelerated path")
+
+    if mass_weighting:
+        # Helmholtz.jl:528-540,572-574: -M over ALL tetrahedra
+        key = (3, "__all__")
+        if key not in disc.patterns:
+            disc.patterns[key] = ctx.pattern_build(3, None)[0]
+        mid = ctx.assemble(disc.patterns[key], _lib.OP_MASS, None, scale=-1.0)
+        L.push(Term(dm(mid), (pow1,), (("λ",),), "-λ", "__aux__"))
+    return L

@@ -1,0 +1,263 @@
+"""Host mirror of the parts of the reference's ``Meshutils`` the hot path consumes.
+
+Same names and numbering rules as the reference (0-based here, 1-based there), but
+sort-based and vectorised (the reference's ``insert_smplx!`` lists are O(n^2),
+src/Mesh/sorter.jl:141-150):
+
+  Mesh(file; scale)                 src/Meshutils.jl:92-165, read_msh4 :272-402
+  simplex ordering                  src/Mesh/sorter.jl:9-31  (ascending in the descending-sorted vertex tuple;
+                                    first occurrence of a vertex set wins, vertex order inside a simplex = file order)
+  collect_lines!                    src/Meshutils.jl:831-840
+  aggregate_elements                src/FEM/FEM.jl:84-116
+  link_triangles_to_tetrahedra!     src/Meshutils.jl:516-548
+  compute_size!                     src/Meshutils.jl:757-780
+  find_tetrahedron_containing_point src/Meshutils.jl:800-815
+  generate_field                    src/Meshutils.jl:1079-1098
+
+plus synthetic structured (Kuhn 6-tet) generators for the large benchmark configurations.
+"""
+import numpy as np
+
+
+def _sorted_unique(simp):
+    """simp: (n,k) int array in file order -> (unique sorted simplices, index map raw->sorted)."""
+    simp = np.asarray(simp, dtype=np.int64)
+    if len(simp) == 0:
+        return simp, np.zeros(0, dtype=np.int64)
+    simp = simp.reshape(len(simp), -1)
+    key = -np.sort(-simp, axis=1)  # descending-sorted vertex tuple
+    order = np.lexsort([np.arange(len(simp))] + [key[:, c] for c in range(key.shape[1] - 1, -1, -1)])
+    ks = key[order]
+    first = np.ones(len(simp), dtype=bool)
+    first[1:] = np.any(ks[1:] != ks[:-1], axis=1)
+    grp = np.cumsum(first) - 1
+    inv = np.empty(len(simp), dtype=np.int64)
+    inv[order] = grp
+    return simp[order[first]], inv
+
+
+def read_msh4(fname):
+    """gmsh 4.1 ASCII reader (PhysicalNames, Entities, Nodes, Elements of type 1/2/4)."""
+    with open(fname) as f:
+        lines = f.read().split("\n")
+    pos = 0
+    tag2dom, ent2dom, domains = {}, [dict(), dict(), dict(), dict()], {}
+    raw = {1: [], 2: [], 4: []}
+    points = None
+    n = len(lines)
+    while pos < n:
+        fld = lines[pos].strip()
+        pos += 1
+        if fld == "$PhysicalNames":
+            cnt = int(lines[pos]); pos += 1
+            for _ in range(cnt):
+                dim, tag, dom = lines[pos].split(); pos += 1
+                dom = dom[1:-1]
+                tag2dom[tag] = dom
+                domains[dom] = {"dimension": int(dim), "simplices": []}
+        elif fld == "$Entities":
+            counts = [int(x) for x in lines[pos].split()]; pos += 1
+            for d, c in enumerate(counts):
+                off = 4 if d == 0 else 7
+                for _ in range(c):
+                    sp = lines[pos].split(); pos += 1
+                    nph = int(sp[off])
+                    ent2dom[d][sp[0]] = [tag2dom[t] for t in sp[off + 1: off + 1 + nph]]
+        elif fld == "$Nodes":
+            nblk, nnodes = (int(x) for x in lines[pos].split()[:2]); pos += 1
+            points = np.empty((3, nnodes))
+            for _ in range(nblk):
+                nin = int(lines[pos].split()[3]); pos += 1
+                tags = np.array(lines[pos: pos + nin], dtype=np.int64) - 1; pos += nin
+                xyz = np.array([l.split()[:3] for l in lines[pos: pos + nin]], dtype=float).reshape(nin, 3); pos += nin
+                points[:, tags] = xyz.T
+        elif fld == "$Elements":
+            nblk = int(lines[pos].split()[0]); pos += 1
+            for _ in range(nblk):
+                sp = lines[pos].split(); pos += 1
+                edim, etag, etype, nin = int(sp[0]), sp[1], int(sp[2]), int(sp[3])
+                if etype in raw:
+                    start = len(raw[etype])
+                    raw[etype].extend([int(x) - 1 for x in l.split()[1:]] for l in lines[pos: pos + nin])
+                    for dom in ent2dom[edim].get(etag, []):
+                        domains[dom]["simplices"].extend(range(start, start + nin))
+                pos += nin
+    return points, raw[1], raw[2], raw[4], domains
+
+
+class Mesh:
+    """Tetrahedral mesh with the reference's fields: points (3xN), lines, triangles, tetrahedra (sorted unique
+    simplex arrays), domains[name] = {"dimension", "simplices"[, "size"]}, tri2tet."""
+
+    def __init__(self, file_name=None, scale=1.0, raw=None):
+        if raw is None:
+            raw = read_msh4(file_name)
+        points, lines, tris, tets, domains = raw
+        self.name = self.file = file_name
+        self.points = np.asarray(points, dtype=float) * scale
+        self.lines, lmap = _sorted_unique(np.asarray(lines, dtype=np.int64).reshape(-1, 2))
+        self.triangles, tmap = _sorted_unique(np.asarray(tris, dtype=np.int64).reshape(-1, 3))
+        self.tetrahedra, ttmap = _sorted_unique(np.asarray(tets, dtype=np.int64).reshape(-1, 4))
+        self.domains = {}
+        for dom, d in domains.items():
+            mp = {1: lmap, 2: tmap, 3: ttmap}[d["dimension"]]
+            idx = mp[np.asarray(d["simplices"], dtype=np.int64)] if len(d["simplices"]) else np.zeros(0, dtype=np.int64)
+            _, first = np.unique(idx, return_index=True)  # unique!, first-occurrence order
+            self.domains[dom] = {"dimension": d["dimension"], "simplices": idx[np.sort(first)]}
+        self.tri2tet = None
+        self.dos = 1
+        self._edge_of = None
+
+    def __repr__(self):
+        return (f"mesh: {self.name}\n#################\npoints:     {self.points.shape[1]}\nlines:      {len(self.lines)}\n"
+                f"triangles:  {len(self.triangles)}\ntetrahedra: {len(self.tetrahedra)}\n#################\ndomains: "
+                + ", ".join(sorted(self.domains)))
+
+    # -- Meshutils.jl:831-840 --------------------------------------------------------------------
+    def collect_lines(self):
+        """Populate mesh.lines; also caches tet_edges (n_tet,6) = index of each tet's edges 12,13,14,23,24,34."""
+        if self._edge_of is None:
+            t = self.tetrahedra
+            pairs = np.stack([t[:, [0, 1]], t[:, [0, 2]], t[:, [0, 3]], t[:, [1, 2]], t[:, [1, 3]], t[:, [2, 3]]], axis=1)
+            self.lines, inv = _sorted_unique(pairs.reshape(-1, 2))
+            self._edge_of = inv.reshape(-1, 6)
+        return self.lines
+
+    def edge_index(self, a, b):
+        """Index in mesh.lines of the edges (a[i], b[i]) (vectorised find_smplx)."""
+        self.collect_lines()
+        npts = self.points.shape[1]
+        hi, lo = np.maximum(a, b), np.minimum(a, b)
+        lk = -np.sort(-self.lines, axis=1)
+        keys = lk[:, 0] * npts + lk[:, 1]  # ascending, as the list is sorted by (max,min)
+        return np.searchsorted(keys, hi * npts + lo)
+
+    # -- Meshutils.jl:516-548 --------------------------------------------------------------------
+    def link_triangles_to_tetrahedra(self):
+        npts = self.points.shape[1]
+        t = self.tetrahedra
+        faces = np.stack([t[:, [0, 1, 2]], t[:, [0, 1, 3]], t[:, [0, 2, 3]], t[:, [1, 2, 3]]], axis=1).reshape(-1, 3)
+        fk = -np.sort(-faces, axis=1)
+        fkey = (fk[:, 0] * npts + fk[:, 1]) * npts + fk[:, 2]
+        tk = -np.sort(-self.triangles, axis=1)
+        tkey = (tk[:, 0] * npts + tk[:, 1]) * npts + tk[:, 2]
+        pos = np.searchsorted(tkey, fkey)
+        pos[pos >= len(tkey)] = 0
+        hit = tkey[pos] == fkey
+        t2t = np.full(len(self.triangles), -1, dtype=np.int64)
+        tet_of_face = np.repeat(np.arange(len(t)), 4)
+        t2t[pos[hit]] = tet_of_face[hit]  # ascending tet order: the last (highest) tet wins, as in the reference loop
+        self.tri2tet = t2t
+        return t2t
+
+    # -- Meshutils.jl:757-780 --------------------------------------------------------------------
+    def compute_size(self, dom):
+        d = self.domains[dom]
+        P = self.points
+        if d["dimension"] == 3:
+            X = P[:, self.tetrahedra[d["simplices"]]]  # 3 x n x 4
+            J = X[:, :, :3] - X[:, :, 3:4]
+            V = np.abs(np.linalg.det(np.moveaxis(J, 1, 0))).sum() / 6
+        elif d["dimension"] == 2:
+            X = P[:, self.triangles[d["simplices"]]]
+            V = np.linalg.norm(np.cross(X[:, :, 0] - X[:, :, 2], X[:, :, 1] - X[:, :, 2], axis=0), axis=0).sum() / 2
+        else:
+            X = P[:, self.lines[d["simplices"]]]
+            V = np.linalg.norm(X[:, :, 1] - X[:, :, 0], axis=0).sum()
+        d["size"] = float(V)
+        return d["size"]
+
+    # -- Meshutils.jl:800-815 --------------------------------------------------------------------
+    def find_tetrahedron_containing_point(self, point):
+        """Lowest-index tetrahedron with all barycentric coordinates in [0,1]; -1 if none (reference: 0)."""
+        p = np.asarray(point, dtype=float)
+        X = self.points[:, self.tetrahedra]  # 3 x n x 4
+        J = np.moveaxis(X[:, :, :3] - X[:, :, 3:4], 1, 0)  # n x 3 x 3
+        rhs = (p[:, None] - X[:, :, 3]).T  # n x 3
+        xi = np.linalg.solve(J, rhs[:, :, None])[:, :, 0]
+        xi = np.concatenate([xi, 1 - xi.sum(axis=1, keepdims=True)], axis=1)
+        ok = np.all((xi >= 0) & (xi <= 1), axis=1)
+        idx = np.flatnonzero(ok)
+        return int(idx[0]) if len(idx) else -1
+
+    # -- Meshutils.jl:1079-1098 ------------------------------------------------------------------
+    def generate_field(self, func, order="const"):
+        if order == "const":
+            cen = self.points[:, self.tetrahedra].sum(axis=2) / 4
+            return np.array([func(*cen[:, i]) for i in range(cen.shape[1])], dtype=float)
+        if order == "lin":
+            return np.array([func(*self.points[:, i]) for i in range(self.points.shape[1])], dtype=float)
+        raise ValueError(f"order {order} not supported")
+
+
+def aggregate_elements(mesh, order="lin"):
+    """FEM.jl:84-116 for :lin / :quad -> (triangles (n,3|6), tetrahedra (n,4|10), dim)."""
+    npts = mesh.points.shape[1]
+    if order == "lin":
+        return mesh.triangles, mesh.tetrahedra, npts
+    if order != "quad":
+        raise NotImplementedError("element order %r: only :lin and :quad are on the accelerated path" % (order,))
+    mesh.collect_lines()
+    tets = np.concatenate([mesh.tetrahedra, mesh._edge_of + npts], axis=1)
+    t = mesh.triangles
+    if len(t):
+        e = np.stack([mesh.edge_index(t[:, 0], t[:, 1]), mesh.edge_index(t[:, 0], t[:, 2]), mesh.edge_index(t[:, 1], t[:, 2])], axis=1)
+        tris = np.concatenate([t, e + npts], axis=1)
+    else:
+        tris = np.zeros((0, 6), dtype=np.int64)
+    return tris, tets, npts + len(mesh.lines)
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic structured meshes: Kuhn 6-tet boxes with seeded jitter
+# ---------------------------------------------------------------------------------------------
+_KUHN = np.array([[0, 1, 3, 7], [0, 1, 5, 7], [0, 2, 3, 7], [0, 2, 6, 7], [0, 4, 5, 7], [0, 4, 6, 7]])
+
+
+def kuhn_box(ncube, lo, hi, jitter=0.0, seed=0, flame_layer=None, name="kuhn_box"):
+    """Box [lo,hi] cut into ncube=(nx,ny,nz) cubes of 6 Kuhn tetrahedra each.
+
+    Domains: "Interior" (all tets), "Outlet" (z = hi face), "Inlet" (z = lo face), "Walls" (the rest of the
+    boundary) and, if flame_layer=(k0,k1), "Flame" = cube layers k0 <= k < k1 in z.
+    Interior vertices are moved by U(-jitter,jitter)*h per axis with numpy.random.default_rng(seed).
+    """
+    nx, ny, nz = ncube
+    lo, hi = np.asarray(lo, float), np.asarray(hi, float)
+    gx, gy, gz = np.meshgrid(np.arange(nx + 1), np.arange(ny + 1), np.arange(nz + 1), indexing="ij")
+    pid = (gz * (ny + 1) + gy) * (nx + 1) + gx  # x fastest
+    h = (hi - lo) / np.array([nx, ny, nz])
+    pts = np.empty((3, (nx + 1) * (ny + 1) * (nz + 1)))
+    for r, g in enumerate((gx, gy, gz)):
+        pts[r, pid.ravel()] = lo[r] + g.ravel() * h[r]
+    if jitter:
+        rng = np.random.default_rng(seed)
+        interior = ((gx > 0) & (gx < nx) & (gy > 0) & (gy < ny) & (gz > 0) & (gz < nz)).ravel()
+        d = rng.uniform(-jitter, jitter, size=(3, pts.shape[1])) * h[:, None]
+        pts[:, pid.ravel()[interior]] += d[:, pid.ravel()[interior]]
+    # cubes
+    cx, cy, cz = np.meshgrid(np.arange(nx), np.arange(ny), np.arange(nz), indexing="ij")
+    cx, cy, cz = cx.ravel(), cy.ravel(), cz.ravel()
+    corner = np.stack([pid[cx + (k & 1), cy + ((k >> 1) & 1), cz + ((k >> 2) & 1)] for k in range(8)], axis=1)
+    tets = corner[:, _KUHN].reshape(-1, 4)
+    tet_cz = np.repeat(cz, 6)
+    # boundary triangles: faces that occur once
+    faces = np.stack([tets[:, [0, 1, 2]], tets[:, [0, 1, 3]], tets[:, [0, 2, 3]], tets[:, [1, 2, 3]]], axis=1).reshape(-1, 3)
+    fs = np.sort(faces, axis=1)
+    npt = pts.shape[1]
+    key = (fs[:, 0] * npt + fs[:, 1]) * npt + fs[:, 2]
+    uk, idx, cnt = np.unique(key, return_index=True, return_counts=True)
+    tris = faces[idx[cnt == 1]]
+    zc = pts[2, tris]
+    tol = 1e-9 * (hi[2] - lo[2])
+    on_out = np.all(np.abs(zc - hi[2]) < tol, axis=1)
+    on_in = np.all(np.abs(zc - lo[2]) < tol, axis=1)
+    domains = {
+        "Interior": {"dimension": 3, "simplices": np.arange(len(tets))},
+        "Outlet": {"dimension": 2, "simplices": np.flatnonzero(on_out)},
+        "Inlet": {"dimension": 2, "simplices": np.flatnonzero(on_in)},
+        "Walls": {"dimension": 2, "simplices": np.flatnonzero(~on_out & ~on_in)},
+    }
+    if flame_layer is not None:
+        k0, k1 = flame_layer
+        domains["Flame"] = {"dimension": 3, "simplices": np.flatnonzero((tet_cz >= k0) & (tet_cz < k1))}
+    return Mesh(name, raw=(pts, np.zeros((0, 2), dtype=np.int64), tris, tets, domains))
