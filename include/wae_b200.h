@@ -129,6 +129,12 @@ int32_t wae_lu_factor(wae_ctx* h, int32_t lu_id, int32_t slot);
 /* In-place solve op(A) X = B; trans as above; X dim x nrhs column-major complex host array. */
 int32_t wae_lu_solve(wae_ctx* h, int32_t lu_id, int32_t trans, int32_t nrhs, double* X);
 
+/* Host-only diagnostic (needs no GPU and no context): run the symbolic phase on a CSC pattern (0-based) and
+ * report out[0..7] = supernodes, nnz(L+U), factorisation flops, largest pivot block, largest row structure,
+ * tree depth, factor array entries, largest per-depth update buffer.  coords (n x 3) may be NULL.          */
+int32_t wae_lu_symbolic_stats(int64_t n, const int64_t* colptr, const int64_t* rowval, const double* coords,
+                              int32_t leaf_size, double* out);
+
 /* ---- shift-invert Arnoldi: nev eigenpairs of A v = lambda M v nearest 0 ----------------
  * Replaces Arpack.eigs(A,M;nev,sigma=0,v0) (Householder.jl:100-101, iterative_solvers.jl:132-133).
  * A is the matrix factorised in lu_id, M the family slot m_slot.  trans=2 gives the adjoint

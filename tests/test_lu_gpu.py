@@ -1,0 +1,148 @@
+"""GPU parity: sparse LU (factor/solve), shift-invert Arnoldi and the NLEVP solvers vs the CPU oracle / goldens."""
+import math
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from cases import load_raw_mesh, rijke_dscrp, speedofsound
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-10  # BASELINE.json: eigenvalues within 1e-10 relative of the reference path
+
+
+def _gpu_family(order="lin", n=0.01, tau=0.001):
+    import wae_b200 as W
+    mesh = W.Mesh("Rijke_mm.msh", scale=0.001, raw=load_raw_mesh("rijke_mm"))
+    c = mesh.generate_field(speedofsound)
+    return W.discretize(mesh, rijke_dscrp(n, tau), c, order=order)
+
+
+@pytest.mark.parametrize("order", ["lin", "quad"])
+def test_solve_matches_superlu(order):
+    L = _gpu_family(order, n=1.0)
+    d = L.size()
+    rng = np.random.default_rng(11)
+    B = rng.standard_normal((d, 3)) + 1j * rng.standard_normal((d, 3))
+    for z in (340 * 2 * math.pi, 1075.0 + 372.0j):
+        op = L(z)
+        A = op.to_scipy()
+        lu = spla.splu(sp.csc_matrix(A))
+        dev = L.device()
+        ctx = dev.ctx
+        op.materialize(0)
+        lid = dev.lu()
+        ctx.lu_factor(lid, 0)
+        for trans, Aop, code in ((0, A, "N"), (1, A.T, "T"), (2, A.conj().T, "H")):
+            X = ctx.lu_solve(lid, B, trans=trans)
+            Xref = lu.solve(B, trans=code)
+            # backward error against the true matrix and agreement with SuperLU
+            res = np.abs(Aop @ X - B).max() / (abs(Aop).max() * np.abs(X).max())
+            assert res < 1e-13, (order, z, trans, res)
+            assert np.abs(X - Xref).max() <= 1e-7 * np.abs(Xref).max()
+        x1 = ctx.lu_solve(lid, B[:, 0])
+        assert np.abs(x1 - lu.solve(B[:, 0])).max() <= 1e-7 * np.abs(x1).max()
+
+
+def test_eigs_matches_arpack():
+    L = _gpu_family("lin", n=0.01)
+    z = 340 * 2 * math.pi
+    dev = L.device()
+    ctx = dev.ctx
+    A = L(z).to_scipy()
+    L(z).materialize(0)
+    mc = [None] * len(L.terms)
+    mc[-1] = -1.0
+    dev.combine(dev.flat(mc), 1)
+    M = -L.terms[-1].coeff.to_scipy()
+    lid = dev.lu()
+    ctx.lu_factor(lid, 0)
+    v0 = np.ones(L.size(), dtype=complex)
+    lam, V, ns = ctx.eigs_si(lid, dev.fid, 1, 1, v0, trans=0)
+    lam_ref = spla.eigs(sp.csc_matrix(A), k=1, M=sp.csc_matrix(M), sigma=0, v0=v0, tol=0)[0]
+    assert abs(lam[0] - lam_ref[0]) <= 1e-10 * abs(lam_ref[0])
+    r = A @ V[:, 0] - lam[0] * (M @ V[:, 0])
+    assert np.abs(r).max() <= 1e-10 * np.abs(A @ V[:, 0]).max()
+    lam3, V3, _ = ctx.eigs_si(lid, dev.fid, 1, 3, v0, trans=0)
+    ref3 = spla.eigs(sp.csc_matrix(A), k=3, M=sp.csc_matrix(M), sigma=0, v0=v0, tol=0)[0]
+    assert np.abs(np.sort_complex(lam3) - np.sort_complex(ref3)).max() <= 1e-8 * np.abs(ref3).max()
+    # adjoint problem eigs(A', M')
+    lama, Va, _ = ctx.eigs_si(lid, dev.fid, 1, 1, np.conj(v0), trans=2)
+    assert abs(lama[0] - np.conj(lam[0])) <= 1e-9 * abs(lam[0])
+
+
+G_HOUSEHOLDER = [
+    (0.001, 1710.6977772393461 + 9.615018460173488j),
+    (0.001 + 0.00001, 1710.864199971756 + 9.593830019670127j),
+    (0.001 + 0.0008798274754933992 + 0.001, 1707.4565281774599 - 9.11764397194075j),
+]
+
+
+@pytest.mark.parametrize("tau,omega", G_HOUSEHOLDER)
+def test_householder_goldens_gpu(tau, omega):
+    import wae_b200 as W
+    L = _gpu_family("lin", n=0.01, tau=tau)
+    sol, n, flag = W.householder(L, 340 * 2 * math.pi, maxiter=20, tol=1e-11, output=False)
+    assert flag in (0, 1)
+    assert abs(sol.params["ω"] - omega) / abs(omega) < TOL
+
+
+G_MSLP = [
+    (0.001, 340 * 2 * math.pi, 1075.325211506839 + 372.1017670372039j),
+    (0.0015, 916.7085040155473 + 494.3258317478708j, 916.7036137579256 + 494.32932528479967j),
+    (0.001 + 2 * 0.0007029896606802446, 668.5373997804821 + 529.4636751544649j, 668.537399929804 + 529.4636746814361j),
+]
+
+
+@pytest.mark.parametrize("tau,start,omega", G_MSLP)
+def test_mslp_goldens_gpu(tau, start, omega):
+    import wae_b200 as W
+    L = _gpu_family("lin", n=1.0, tau=tau)
+    sol, n, flag = W.mslp(L, start, maxiter=20, tol=1e-11, output=False)
+    assert flag == 0
+    assert abs(sol.params["ω"] - omega) / abs(omega) < TOL
+
+
+def test_householder_quad_and_eigenvectors_vs_oracle():
+    """P2 elements, higher-order Householder update and eigenvector parity (1e-8 after phase normalisation)."""
+    import wae_b200 as W
+    from oracle.helmholtz import discretize as odisc
+    from oracle.mesh import Mesh as OMesh
+    from oracle.nlevp import householder as ohouse
+    raw = load_raw_mesh("rijke_mm")
+    mo = OMesh("m", scale=0.001, raw=raw)
+    Lo = odisc(mo, rijke_dscrp(1.0, 0.001), mo.generate_field(speedofsound), order="quad")
+    Lg = _gpu_family("quad", n=1.0)
+    for order in (1, 3):
+        so, no, fo = ohouse(Lo, 340 * 2 * math.pi, maxiter=25, tol=1e-10, order=order)
+        sg, ng, fg = W.householder(Lg, 340 * 2 * math.pi, maxiter=25, tol=1e-10, order=order, output=False)
+        wo, wg = so.params["ω"], sg.params["ω"]
+        assert abs(wo - wg) / abs(wo) < TOL, (order, wo, wg)
+
+        def phase(v):
+            k = np.argmax(np.abs(v))
+            return v * (abs(v[k]) / v[k])
+        assert np.abs(phase(so.v) - phase(sg.v)).max() <= 1e-8 * np.abs(so.v).max()
+        assert np.abs(phase(so.v_adj) - phase(sg.v_adj)).max() <= 1e-6 * np.abs(so.v_adj).max()
+
+
+def test_beyn_gpu_vs_oracle():
+    import wae_b200 as W
+    from oracle.helmholtz import discretize as odisc
+    from oracle.mesh import Mesh as OMesh
+    from oracle.nlevp import beyn as obeyn
+    raw = load_raw_mesh("rijke_mm")
+    mo = OMesh("m", scale=0.001, raw=raw)
+    Lo = odisc(mo, rijke_dscrp(0.0, 0.001), mo.generate_field(speedofsound))
+    Lg = _gpu_family("lin", n=0.0)
+    G = [z * 2 * math.pi for z in (150 + 5j, 150 - 5j, 1000 - 5j, 1000 + 5j)]
+    Oo, Po = obeyn(Lo, G, l=5, N=16)
+    Og, Pg = W.beyn(Lg, G, l=5, N=16, output=False)
+    assert len(Og) == len(Oo) == 2
+    assert np.abs(np.sort_complex(Og) - np.sort_complex(Oo)).max() <= 1e-8 * np.abs(Oo).max()
+    # the reference's own idiom (tutorial_06...jl:41-55): polish with householder
+    for om in Og:
+        sol, n, flag = W.householder(Lg, om, maxiter=10, tol=1e-10, output=False)
+        assert abs(sol.params["ω"] - om) < 5e-2 * abs(om)

@@ -154,8 +154,11 @@ void wae_family_ensure_csr(wae_ctx* h, Family& F) {
 }
 
 void wae_spmm_device(wae_ctx* h, Family& F, int slot, int trans, int nrhs, const cplx* X, cplx* Y) {
+  wae_spmm_values(h, F, (const cplx*)F.slot[slot].p, trans, nrhs, X, Y);
+}
+
+void wae_spmm_values(wae_ctx* h, Family& F, const cplx* val, int trans, int nrhs, const cplx* X, cplx* Y) {
   Pattern& U = h->pat(F.pattern);
-  const double2* val = (const double2*)F.slot[slot].p;
   unsigned blocks = (unsigned)((U.dim * 32 + 255) / 256);
   if (trans == 0) {
     wae_family_ensure_csr(h, F);

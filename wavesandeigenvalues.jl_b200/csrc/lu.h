@@ -1,3 +1,66 @@
-// Sparse LU (symbolic on host, numeric on device) -- internal interface.
+// Sparse LU of a family slot: symbolic analysis on the host (once per pattern), numeric
+// multifrontal factorisation and triangular solves on the device.  Replaces the UMFPACK
+// calls of the reference (perturbation.jl:329,359; beyn.jl:65; inside Arpack.eigs at
+// Householder.jl:100-101).  Internal interface.
 #pragma once
 #include "wae_internal.h"
+
+#define WAE_LU_NB 32  // pivot block width of the blocked partial factorisation
+
+// Result of the symbolic phase.  "Positions" are indices in the elimination order.
+struct LuSymbolic {
+  int64_t n = 0;
+  std::vector<int32_t> perm;   // perm[pos] = original index
+  std::vector<int32_t> iperm;  // iperm[orig] = pos
+  int nsn = 0;                 // supernodes, numbered in elimination (post) order
+  std::vector<int32_t> sn_first;   // nsn+1: pivot positions of supernode k are [sn_first[k], sn_first[k+1])
+  std::vector<int32_t> sn_parent;  // assembly-tree parent (-1 root)
+  std::vector<int32_t> sn_depth;   // root = 0
+  std::vector<int64_t> struct_ptr; // nsn+1
+  std::vector<int32_t> struct_idx; // row structure below the pivot block (positions, ascending)
+  std::vector<int64_t> rel_ptr;    // nsn+1 (== struct_ptr): position of struct rows in the parent's front
+  std::vector<int32_t> rel_idx;
+  std::vector<int64_t> lp_off, up_off;  // offsets (complex units) of the L panel and U^T panel in the factor array
+  std::vector<int64_t> upd_off;         // offset of the r x r update matrix inside its depth-level buffer
+  std::vector<int64_t> level_upd_size;  // per depth: complex entries of all update matrices of that depth
+  std::vector<std::vector<int32_t>> levels;  // supernodes by depth
+  int64_t fac_size = 0;        // complex entries of the factor array (L panels + U^T panels)
+  int64_t factor_nnz = 0;      // structural nonzeros of L+U (supernodal, incl. dense pivot blocks)
+  double flops = 0;            // real flops of the numeric factorisation (8 per complex multiply-add)
+  std::vector<int64_t> amap;   // per nonzero of A: destination offset in the factor array
+  std::vector<int32_t> diagpos;  // nz index of A(i,i) in the pattern, -1 if structurally absent
+  int max_s = 0, max_r = 0;
+};
+
+// coords: optional n x 3 node coordinates (nullptr -> BFS level structure is used for the bisection)
+void wae_lu_symbolic(int64_t n, const int64_t* colptr, const int32_t* rowval, const double* coords, int leaf_size,
+                     LuSymbolic& S);
+
+struct LuSolver {
+  int fam = -1;
+  LuSymbolic sym;
+  // device copies of the symbolic data
+  DevBuf<int32_t> d_perm, d_iperm, d_sn_first, d_sn_parent, d_struct_idx, d_rel_idx, d_diagpos;
+  DevBuf<int64_t> d_struct_ptr, d_lp_off, d_up_off, d_upd_off, d_amap;
+  DevBuf<int32_t> d_colidx_nz;         // column index of every nonzero of A (for the scaling in the scatter)
+  std::vector<DevBuf<int32_t>> d_level;  // supernode ids per depth
+  std::vector<DevBuf<int32_t>> d_xa_tile_ptr;  // per depth: extend-add tile prefix over the supernodes of that depth
+  std::vector<int32_t> xa_tiles;       // per depth: number of extend-add tiles
+  DevBuf<cplx> d_Aval;                 // copy of the factorised matrix (iterative refinement)
+  // numeric
+  DevBuf<cplx> d_fac;
+  DevBuf<cplx> d_upd[2];
+  DevBuf<double> d_scale;              // equilibration D (A_s = D A D)
+  DevBuf<cplx> d_work;                 // solve workspace (n x nrhs) x 2
+  DevBuf<int32_t> d_flag;              // device-side status (bad pivot)
+  int work_nrhs = 0;
+  bool factored = false;
+  int refine_steps = 1;
+  double pivot_eps = 1e-14;
+};
+
+// numeric phase (lu_numeric.cu) -- all on the context stream, device pointers
+void wae_lu_setup_device(wae_ctx* h, LuSolver& S);
+void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval);
+// X (n x nrhs, column-major, device) <- op(A)^{-1} X; trans: 0 N, 1 T, 2 C
+void wae_lu_solve_device(wae_ctx* h, LuSolver& S, int trans, int nrhs, cplx* d_X, int refine);

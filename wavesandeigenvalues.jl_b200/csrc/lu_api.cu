@@ -1,10 +1,486 @@
-// placeholder until the LU lands
+// C-ABI entry points for the sparse LU, the shift-invert Arnoldi eigensolver and the Beyn
+// moment accumulation (see include/wae_b200.h).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <complex>
+#include <cstdlib>
+
 #include "lu.h"
-struct LuSolver { int dummy; };
-extern "C" {
-int32_t wae_lu_analyze(wae_ctx* h, int32_t, int32_t*, int64_t*, double*) { if (h) h->err = "LU not built yet"; return WAE_E_INVALID; }
-int32_t wae_lu_factor(wae_ctx* h, int32_t, int32_t) { if (h) h->err = "LU not built yet"; return WAE_E_INVALID; }
-int32_t wae_lu_solve(wae_ctx* h, int32_t, int32_t, int32_t, double*) { if (h) h->err = "LU not built yet"; return WAE_E_INVALID; }
-int32_t wae_eigs_si(wae_ctx* h, int32_t, int32_t, int32_t, int32_t, int32_t, const double*, double*, double*, int32_t*) { if (h) h->err = "LU not built yet"; return WAE_E_INVALID; }
-int32_t wae_beyn_moments(wae_ctx* h, int32_t, int32_t, int32_t, const double*, const double*, const double*, int32_t, int32_t, void*) { if (h) h->err = "LU not built yet"; return WAE_E_INVALID; }
+
+typedef std::complex<double> zc;
+
+#define WAE_API_BEGIN \
+  if (!h) return WAE_E_INVALID; \
+  try {
+#define WAE_API_END                    \
+  }                                    \
+  catch (const WaeError& e) {          \
+    h->err = e.msg;                    \
+    return e.code;                     \
+  }                                    \
+  catch (const std::bad_alloc&) {      \
+    h->err = "host allocation failed"; \
+    return WAE_E_NOMEM;                \
+  }                                    \
+  catch (const std::exception& e) {    \
+    h->err = e.what();                 \
+    return WAE_E_INVALID;              \
+  }                                    \
+  return WAE_OK;
+
+static LuSolver& get_lu(wae_ctx* h, int id) {
+  if (id < 0 || id >= (int)h->lus.size() || !h->lus[id]) WAE_THROW(WAE_E_INVALID, "unknown LU id %d", id);
+  return *h->lus[id];
 }
+
+// coordinates of every DOF (vertices, P2: edge midpoints) when the family lives on the context mesh
+static bool dof_coords(wae_ctx* h, int64_t dim, std::vector<double>& xyz) {
+  if (!h->order || h->dim != dim || h->n_tet == 0) return false;
+  xyz.assign((size_t)3 * dim, 0.0);
+  std::copy(h->xyz.begin(), h->xyz.end(), xyz.begin());
+  if (h->order == 2) {
+    static const int ea[6] = {0, 0, 0, 1, 1, 2}, eb[6] = {1, 2, 3, 2, 3, 3};
+    for (int64_t e = 0; e < h->n_tet; e++) {
+      const uint32_t* d = h->tets.data() + (size_t)e * 10;
+      for (int k = 0; k < 6; k++)
+        for (int r = 0; r < 3; r++) xyz[3 * (size_t)d[4 + k] + r] = 0.5 * (h->xyz[3 * (size_t)d[ea[k]] + r] + h->xyz[3 * (size_t)d[eb[k]] + r]);
+    }
+  }
+  return true;
+}
+
+// ---- small dense complex eigenproblem (upper Hessenberg, QR algorithm) ------------------------------------
+// H (n x n, row-major, destroyed) -> eigenvalues w and eigenvectors X (columns, row-major n x n)
+static void hessenberg_eig(int n, std::vector<zc>& H, std::vector<zc>& w, std::vector<zc>& X) {
+  auto A = [&](int i, int j) -> zc& { return H[(size_t)i * n + j]; };
+  std::vector<zc> Z((size_t)n * n, 0.0);
+  for (int i = 0; i < n; i++) Z[(size_t)i * n + i] = 1.0;
+  const double eps = 2.2e-16;
+  int hi = n - 1, iter = 0;
+  while (hi > 0) {
+    int l = hi;
+    for (; l > 0; l--) {
+      double sd = std::abs(A(l - 1, l - 1)) + std::abs(A(l, l));
+      if (sd == 0.0) sd = 1.0;
+      if (std::abs(A(l, l - 1)) <= eps * sd) {
+        A(l, l - 1) = 0.0;
+        break;
+      }
+    }
+    if (l == hi) {
+      hi--;
+      iter = 0;
+      continue;
+    }
+    // Wilkinson shift
+    zc a = A(hi - 1, hi - 1), b = A(hi - 1, hi), c = A(hi, hi - 1), d = A(hi, hi);
+    zc tr = a + d, det = a * d - b * c;
+    zc disc = std::sqrt(tr * tr - 4.0 * det);
+    zc m1 = 0.5 * (tr + disc), m2 = 0.5 * (tr - disc);
+    zc mu = std::abs(m1 - d) < std::abs(m2 - d) ? m1 : m2;
+    if (iter % 11 == 10) mu = d + std::abs(c);  // exceptional shift
+    if (++iter > 30 * n) break;
+    for (int i = l; i <= hi; i++) A(i, i) -= mu;
+    std::vector<double> cs(n);
+    std::vector<zc> sn(n);
+    for (int k = l; k < hi; k++) {
+      zc f = A(k, k), g = A(k + 1, k);
+      double nr = std::sqrt(std::norm(f) + std::norm(g));
+      double cc = 1.0;
+      zc ss = 0.0;
+      if (nr > 0.0) {
+        if (std::abs(f) == 0.0) {
+          cc = 0.0;
+          ss = 1.0;
+        } else {
+          cc = std::abs(f) / nr;
+          ss = (f / std::abs(f)) * std::conj(g) / nr;
+        }
+      }
+      cs[k] = cc;
+      sn[k] = ss;
+      for (int j = k; j < n; j++) {  // rows k,k+1 <- G * rows
+        zc x = A(k, j), y = A(k + 1, j);
+        A(k, j) = cc * x + ss * y;
+        A(k + 1, j) = -std::conj(ss) * x + cc * y;
+      }
+    }
+    for (int k = l; k < hi; k++) {  // columns k,k+1 <- columns * G^H
+      double cc = cs[k];
+      zc ss = sn[k];
+      for (int i = 0; i <= std::min(k + 2, hi); i++) {
+        zc x = A(i, k), y = A(i, k + 1);
+        A(i, k) = cc * x + std::conj(ss) * y;
+        A(i, k + 1) = -ss * x + cc * y;
+      }
+      for (int i = 0; i < n; i++) {
+        zc x = Z[(size_t)i * n + k], y = Z[(size_t)i * n + k + 1];
+        Z[(size_t)i * n + k] = cc * x + std::conj(ss) * y;
+        Z[(size_t)i * n + k + 1] = -ss * x + cc * y;
+      }
+    }
+    for (int i = l; i <= hi; i++) A(i, i) += mu;
+  }
+  w.resize(n);
+  for (int i = 0; i < n; i++) w[i] = A(i, i);
+  // eigenvectors of the triangular factor, back-transformed with Z
+  X.assign((size_t)n * n, 0.0);
+  double tn = 0;
+  for (int i = 0; i < n; i++)
+    for (int j = i; j < n; j++) tn = std::max(tn, std::abs(A(i, j)));
+  std::vector<zc> y(n);
+  for (int k = 0; k < n; k++) {
+    std::fill(y.begin(), y.end(), 0.0);
+    y[k] = 1.0;
+    for (int i = k - 1; i >= 0; i--) {
+      zc s = 0.0;
+      for (int j = i + 1; j <= k; j++) s += A(i, j) * y[j];
+      zc den = A(i, i) - A(k, k);
+      if (std::abs(den) < eps * std::max(tn, 1e-300)) den = eps * std::max(tn, 1e-300);
+      y[i] = -s / den;
+    }
+    double nrm = 0;
+    std::vector<zc> x(n, 0.0);
+    for (int i = 0; i < n; i++) {
+      zc s = 0.0;
+      for (int j = 0; j <= k; j++) s += Z[(size_t)i * n + j] * y[j];
+      x[i] = s;
+      nrm += std::norm(s);
+    }
+    nrm = std::sqrt(nrm);
+    for (int i = 0; i < n; i++) X[(size_t)i * n + k] = x[i] / nrm;
+  }
+}
+
+// ---- device helpers for the Arnoldi process -----------------------------------------------------------------
+// out[i] += sum_p conj(V_i[p]) w[p]   for i < nv   (grid.x chunks, grid.y = i)
+__global__ void __launch_bounds__(256) multi_dot_kernel(const cplx* __restrict__ V, int64_t n, const cplx* __restrict__ w, double* __restrict__ out) {
+  const cplx* v = V + (size_t)blockIdx.y * n;
+  double sr = 0.0, si = 0.0;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    cplx a = v[p], b = w[p];
+    sr += a.x * b.x + a.y * b.y;
+    si += a.x * b.y - a.y * b.x;
+  }
+  __shared__ double sh[2][8];
+#pragma unroll
+  for (int off = 16; off; off >>= 1) {
+    sr += __shfl_xor_sync(0xffffffffu, sr, off);
+    si += __shfl_xor_sync(0xffffffffu, si, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh[0][threadIdx.x >> 5] = sr;
+    sh[1][threadIdx.x >> 5] = si;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int k = 1; k < 8; k++) {
+      sr += sh[0][k];
+      si += sh[1][k];
+    }
+    atomicAdd(out + 2 * blockIdx.y, sr);
+    atomicAdd(out + 2 * blockIdx.y + 1, si);
+  }
+}
+// w -= sum_i c_i V_i
+__global__ void multi_axpy_kernel(const cplx* __restrict__ V, int64_t n, int nv, const cplx* __restrict__ c, cplx* __restrict__ w) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  cplx a = w[p];
+  for (int i = 0; i < nv; i++) {
+    cplx ci = c[i], v = V[(size_t)i * n + p];
+    a.x -= ci.x * v.x - ci.y * v.y;
+    a.y -= ci.x * v.y + ci.y * v.x;
+  }
+  w[p] = a;
+}
+// out = sum_i c_i V_i
+__global__ void lincomb_kernel(const cplx* __restrict__ V, int64_t n, int nv, const cplx* __restrict__ c, cplx* __restrict__ out) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  cplx a = make_double2(0.0, 0.0);
+  for (int i = 0; i < nv; i++) {
+    cplx ci = c[i], v = V[(size_t)i * n + p];
+    a.x += ci.x * v.x - ci.y * v.y;
+    a.y += ci.x * v.y + ci.y * v.x;
+  }
+  out[p] = a;
+}
+__global__ void scale_copy_kernel(const cplx* __restrict__ in, int64_t n, double s, cplx* __restrict__ out) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n) out[p] = make_double2(in[p].x * s, in[p].y * s);
+}
+// X[:, c] = e_c for c < l
+__global__ void identity_cols_kernel(int64_t n, int l, cplx* __restrict__ X) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n * l) return;
+  X[p] = make_double2((p % n) == (p / n) ? 1.0 : 0.0, 0.0);
+}
+// A_p[:, :] += w z^p X  for p < n_mom
+__global__ void moment_accum_kernel(const cplx* __restrict__ X, int64_t total, int n_mom, cplx w, cplx z, cplx* __restrict__ A) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  cplx x = X[i];
+  cplx f = w;
+  for (int p = 0; p < n_mom; p++) {
+    cplx* a = A + (size_t)p * total + i;
+    a->x += f.x * x.x - f.y * x.y;
+    a->y += f.x * x.y + f.y * x.x;
+    f = make_double2(f.x * z.x - f.y * z.y, f.x * z.y + f.y * z.x);
+  }
+}
+
+struct ArnoldiWork {
+  DevBuf<cplx> V, w, t, c;
+  DevBuf<double> dots;
+};
+
+extern "C" {
+
+// Host-only diagnostic (no GPU needed): statistics of the symbolic phase for a CSC pattern.
+// out[0]=supernodes, [1]=factor nnz, [2]=flops, [3]=max pivot block, [4]=max structure, [5]=depth,
+// [6]=factor array entries, [7]=max update-buffer entries of one depth
+int32_t wae_lu_symbolic_stats(int64_t n, const int64_t* colptr, const int64_t* rowval, const double* coords, int32_t leaf, double* out) {
+  try {
+    std::vector<int32_t> rv(colptr[n]);
+    for (int64_t k = 0; k < colptr[n]; k++) rv[k] = (int32_t)rowval[k];
+    LuSymbolic S;
+    wae_lu_symbolic(n, colptr, rv.data(), coords, leaf > 0 ? leaf : 64, S);
+    out[0] = S.nsn;
+    out[1] = (double)S.factor_nnz;
+    out[2] = S.flops;
+    out[3] = S.max_s;
+    out[4] = S.max_r;
+    out[5] = (double)S.levels.size();
+    out[6] = (double)S.fac_size;
+    out[7] = (double)*std::max_element(S.level_upd_size.begin(), S.level_upd_size.end());
+    // verify that perm is a permutation
+    std::vector<char> seen(n, 0);
+    for (int64_t p = 0; p < n; p++) {
+      if (seen[S.perm[p]]) return WAE_E_INVALID;
+      seen[S.perm[p]] = 1;
+    }
+    return WAE_OK;
+  } catch (...) {
+    return WAE_E_INVALID;
+  }
+}
+
+int32_t wae_lu_analyze(wae_ctx* h, int32_t fam_id, int32_t* lu_id, int64_t* factor_nnz, double* factor_flops) {
+  WAE_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(h->device));
+  Family& F = h->fam(fam_id);
+  Pattern& U = h->pat(F.pattern);
+  std::shared_ptr<LuSolver> S(new LuSolver());
+  S->fam = fam_id;
+  std::vector<double> xyz;
+  bool have = dof_coords(h, U.dim, xyz);
+  int leaf = 64;
+  if (const char* env = getenv("WAE_LU_LEAF")) leaf = atoi(env);
+  wae_lu_symbolic(U.dim, U.colptr.data(), U.rowval.data(), have ? xyz.data() : nullptr, leaf, S->sym);
+  wae_lu_setup_device(h, *S);
+  h->lus.push_back(S);
+  if (lu_id) *lu_id = (int)h->lus.size() - 1;
+  if (factor_nnz) *factor_nnz = S->sym.factor_nnz;
+  if (factor_flops) *factor_flops = S->sym.flops;
+  WAE_API_END
+}
+
+int32_t wae_lu_factor(wae_ctx* h, int32_t lu_id, int32_t slot) {
+  WAE_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(h->device));
+  LuSolver& S = get_lu(h, lu_id);
+  Family& F = h->fam(S.fam);
+  if (slot < 0 || slot >= WAE_FAMILY_SLOTS || !F.slot[slot].p) WAE_THROW(WAE_E_INVALID, "family slot %d is empty", slot);
+  PhaseTimer t(h, "factor");
+  wae_lu_factor_device(h, S, (const cplx*)F.slot[slot].p);
+  t.stop();
+  WAE_API_END
+}
+
+int32_t wae_lu_solve(wae_ctx* h, int32_t lu_id, int32_t trans, int32_t nrhs, double* X) {
+  WAE_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(h->device));
+  LuSolver& S = get_lu(h, lu_id);
+  if (trans < 0 || trans > 2 || nrhs <= 0 || !X) WAE_THROW(WAE_E_INVALID, "bad solve arguments");
+  int64_t n = S.sym.n;
+  DevBuf<cplx> dX;
+  dX.upload((const cplx*)X, (size_t)n * nrhs, h->stream);
+  PhaseTimer t(h, "solve");
+  wae_lu_solve_device(h, S, trans, nrhs, dX.p, S.refine_steps);
+  t.stop();
+  CUDA_CHECK(cudaMemcpyAsync(X, dX.p, (size_t)n * nrhs * sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  WAE_API_END
+}
+
+int32_t wae_eigs_si(wae_ctx* h, int32_t lu_id, int32_t fam_id, int32_t m_slot, int32_t trans, int32_t nev, const double* v0,
+                    double* lam, double* Vout, int32_t* n_solves) {
+  WAE_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(h->device));
+  LuSolver& S = get_lu(h, lu_id);
+  Family& F = h->fam(fam_id);
+  if (fam_id != S.fam) WAE_THROW(WAE_E_INVALID, "the LU belongs to another family");
+  if (m_slot < 0 || m_slot >= WAE_FAMILY_SLOTS || !F.slot[m_slot].p) WAE_THROW(WAE_E_INVALID, "family slot %d (M) is empty", m_slot);
+  if (trans != 0 && trans != 2) WAE_THROW(WAE_E_INVALID, "trans must be 0 (A,M) or 2 (A',M')");
+  const int64_t n = S.sym.n;
+  if (nev < 1 || nev >= n || !v0 || !lam || !Vout) WAE_THROW(WAE_E_INVALID, "bad eigs arguments");
+  const int m = (int)std::min<int64_t>(std::max(20, 2 * nev + 1), n);  // ncv as in Arpack.jl
+  cudaStream_t st = h->stream;
+  PhaseTimer timer(h, "eigs");
+  ArnoldiWork W;
+  W.V.alloc((size_t)n * (m + 1));
+  W.w.alloc(n);
+  W.t.alloc(n);
+  W.c.alloc(m + 1);
+  W.dots.alloc(2 * (m + 2));
+  const unsigned gb = (unsigned)((n + 255) / 256);
+  const int dot_blocks = (int)std::min<int64_t>((n + 255) / 256, 64);
+  auto dots = [&](const cplx* Vb, int nv, const cplx* w, std::vector<zc>& out) {
+    CUDA_CHECK(cudaMemsetAsync(W.dots.p, 0, 2 * nv * sizeof(double), st));
+    multi_dot_kernel<<<dim3(dot_blocks, nv), 256, 0, st>>>(Vb, n, w, W.dots.p);
+    h->launches++;
+    out.resize(nv);
+    CUDA_CHECK(cudaMemcpyAsync(out.data(), W.dots.p, 2 * nv * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  };
+  auto upload_c = [&](const std::vector<zc>& c) {
+    CUDA_CHECK(cudaMemcpyAsync(W.c.p, c.data(), c.size() * sizeof(zc), cudaMemcpyHostToDevice, st));
+  };
+  int solves = 0;
+  auto apply_op = [&](const cplx* x, cplx* y) {  // y = op(A)^{-1} op(M) x
+    wae_spmm_device(h, F, m_slot, trans, 1, x, y);
+    wae_lu_solve_device(h, S, trans, 1, y, S.refine_steps);
+    solves++;
+  };
+  // start vector
+  CUDA_CHECK(cudaMemcpyAsync(W.w.p, v0, n * sizeof(cplx), cudaMemcpyHostToDevice, st));
+  std::vector<zc> hcol, h2;
+  dots(W.w.p, 1, W.w.p, hcol);
+  double nrm = std::sqrt(hcol[0].real());
+  if (!(nrm > 0.0) || !std::isfinite(nrm)) WAE_THROW(WAE_E_INVALID, "start vector is zero or not finite");
+  scale_copy_kernel<<<gb, 256, 0, st>>>(W.w.p, n, 1.0 / nrm, W.V.p);
+  const double tol = 1e-13;
+  const int max_restart = 15;
+  std::vector<zc> H((size_t)(m + 1) * m, 0.0), Hs, theta, Y;
+  std::vector<int> order;
+  bool converged = false;
+  double best_res = 1e300;
+  int jdim = 0;
+  for (int restart = 0; restart <= max_restart && !converged; restart++) {
+    std::fill(H.begin(), H.end(), 0.0);
+    for (int j = 0; j < m; j++) {
+      apply_op(W.V.p + (size_t)j * n, W.w.p);
+      // classical Gram-Schmidt with one reorthogonalisation
+      dots(W.V.p, j + 1, W.w.p, hcol);
+      upload_c(hcol);
+      multi_axpy_kernel<<<gb, 256, 0, st>>>(W.V.p, n, j + 1, W.c.p, W.w.p);
+      dots(W.V.p, j + 1, W.w.p, h2);
+      upload_c(h2);
+      multi_axpy_kernel<<<gb, 256, 0, st>>>(W.V.p, n, j + 1, W.c.p, W.w.p);
+      h->launches += 2;
+      for (int i = 0; i <= j; i++) H[(size_t)i * m + j] = hcol[i] + h2[i];
+      std::vector<zc> nn;
+      dots(W.w.p, 1, W.w.p, nn);
+      double beta = std::sqrt(std::max(0.0, nn[0].real()));
+      if (!std::isfinite(beta)) WAE_THROW(WAE_E_SINGULAR, "non-finite Krylov vector (singular factorisation)");
+      H[(size_t)(j + 1) * m + j] = beta;
+      jdim = j + 1;
+      // Ritz pairs of the leading jdim x jdim block
+      Hs.assign((size_t)jdim * jdim, 0.0);
+      for (int a = 0; a < jdim; a++)
+        for (int b = 0; b < jdim; b++) Hs[(size_t)a * jdim + b] = H[(size_t)a * m + b];
+      hessenberg_eig(jdim, Hs, theta, Y);
+      order.resize(jdim);
+      for (int i = 0; i < jdim; i++) order[i] = i;
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return std::abs(theta[a]) > std::abs(theta[b]); });
+      bool ok = jdim >= nev;
+      double worst = 0;
+      for (int i = 0; i < nev && ok; i++) {
+        int q = order[i];
+        double res = beta * std::abs(Y[(size_t)(jdim - 1) * jdim + q]);
+        double rel = res / std::max(std::abs(theta[q]), 1e-300);
+        worst = std::max(worst, rel);
+        if (!(rel <= tol)) ok = false;
+      }
+      if (jdim >= nev) best_res = std::min(best_res, worst);
+      if (ok || beta <= 1e-300) {
+        converged = true;
+        break;
+      }
+      scale_copy_kernel<<<gb, 256, 0, st>>>(W.w.p, n, 1.0 / beta, W.V.p + (size_t)(j + 1) * n);
+      h->launches++;
+    }
+    if (!converged && restart < max_restart) {
+      // explicit restart with the sum of the wanted Ritz vectors
+      std::vector<zc> c(jdim, 0.0);
+      for (int i = 0; i < nev; i++)
+        for (int a = 0; a < jdim; a++) c[a] += Y[(size_t)a * jdim + order[i]];
+      upload_c(c);
+      lincomb_kernel<<<gb, 256, 0, st>>>(W.V.p, n, jdim, W.c.p, W.w.p);
+      std::vector<zc> nn;
+      dots(W.w.p, 1, W.w.p, nn);
+      scale_copy_kernel<<<gb, 256, 0, st>>>(W.w.p, n, 1.0 / std::sqrt(nn[0].real()), W.V.p);
+      h->launches += 2;
+    }
+  }
+  if (!converged && !(best_res <= 1e-8)) WAE_THROW(WAE_E_NOCONV, "Arnoldi did not converge (best relative Ritz residual %.3e)", best_res);
+  // Ritz vectors -> host; lambda = 1/theta
+  for (int i = 0; i < nev; i++) {
+    int q = order[i];
+    std::vector<zc> c(jdim);
+    for (int a = 0; a < jdim; a++) c[a] = Y[(size_t)a * jdim + q];
+    upload_c(c);
+    lincomb_kernel<<<gb, 256, 0, st>>>(W.V.p, n, jdim, W.c.p, W.t.p);
+    h->launches++;
+    CUDA_CHECK(cudaMemcpyAsync(Vout + 2 * (size_t)i * n, W.t.p, n * sizeof(cplx), cudaMemcpyDeviceToHost, st));
+    zc l = 1.0 / theta[q];
+    lam[2 * i] = l.real();
+    lam[2 * i + 1] = l.imag();
+  }
+  timer.stop();
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  if (n_solves) *n_solves = solves;
+  WAE_API_END
+}
+
+int32_t wae_beyn_moments(wae_ctx* h, int32_t fam_id, int32_t lu_id, int32_t n_nodes, const double* z, const double* w,
+                         const double* coeffs, int32_t l, int32_t n_mom, void* A_out) {
+  WAE_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(h->device));
+  LuSolver& S = get_lu(h, lu_id);
+  Family& F = h->fam(fam_id);
+  if (fam_id != S.fam) WAE_THROW(WAE_E_INVALID, "the LU belongs to another family");
+  const int64_t n = S.sym.n;
+  if (n_nodes < 0 || !z || !w || !coeffs || l < 1 || l > n || n_mom < 1 || !A_out) WAE_THROW(WAE_E_INVALID, "bad Beyn arguments");
+  cudaStream_t st = h->stream;
+  DevBuf<cplx> X;
+  X.alloc((size_t)n * l);
+  const int slot = WAE_FAMILY_SLOTS - 1;
+  double t_fac = 0, t_sol = 0;
+  for (int j = 0; j < n_nodes; j++) {
+    wae_combine_device(h, F, coeffs + 2 * (size_t)j * F.n_terms, slot);
+    {
+      PhaseTimer t(h, "factor");
+      wae_lu_factor_device(h, S, (const cplx*)F.slot[slot].p);
+      t.stop();
+      t_fac += h->last_ms["factor"];
+    }
+    PhaseTimer t(h, "solve");
+    identity_cols_kernel<<<(unsigned)(((size_t)n * l + 255) / 256), 256, 0, st>>>(n, l, X.p);
+    wae_lu_solve_device(h, S, 0, l, X.p, S.refine_steps);
+    moment_accum_kernel<<<(unsigned)(((size_t)n * l + 255) / 256), 256, 0, st>>>(X.p, n * l, n_mom, make_double2(w[2 * j], w[2 * j + 1]),
+                                                                                 make_double2(z[2 * j], z[2 * j + 1]), (cplx*)A_out);
+    h->launches += 2;
+    t.stop();
+    t_sol += h->last_ms["solve"];
+  }
+  h->last_ms["beyn_factor_total"] = t_fac;
+  h->last_ms["beyn_solve_total"] = t_sol;
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  WAE_API_END
+}
+
+}  // extern "C"

@@ -1,0 +1,730 @@
+// Numeric phase of the sparse complex LU on the device (multifrontal, supernodal).
+//
+// Storage per supernode k with s pivots and r structure rows (ld = s + r), all column-major complex:
+//   Lp  (ld x s)  rows 0..s-1: pivot block (L strictly below the diagonal of each NBxNB diagonal block and
+//                 in all blocks below it, U on/above the diagonal inside the diagonal blocks), rows s..: L21
+//   Up  (ld x s)  the U factor stored TRANSPOSED: diagonal blocks hold U_kk^T (lower incl. diagonal), blocks
+//                 below hold U[k, J]^T, rows s.. hold U12^T.  L and U^T panels therefore have the same shape and
+//                 the same kernels serve A x = b (forward with Lp, backward with Up) and A^T x = b (forward
+//                 with Up, backward with Lp).
+//   A22 (r x r)   Schur complement / update matrix, lives in a per-depth scratch buffer until the parent
+//                 has absorbed it (extend-add).
+// The assembly tree is processed by depth, deepest level first; all supernodes of one depth are independent
+// and are handled by batched kernels (grid.z = supernode).  The frontal updates are complex GEMMs
+// C -= A B^T on the FP64 tensor cores (mma.sync m8n8k4 f64 -> SASS DMMA.8x8x4).
+// No pivoting across blocks (the symbolic structure is static); tiny pivots are replaced (static
+// pivoting) and the solve applies iterative refinement against the original matrix.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+
+#include "lu.h"
+
+#define NB WAE_LU_NB
+
+struct SnView {
+  int s, r, ld, first;
+  cplx *lp, *up;
+};
+
+struct LuDev {  // plain device pointers handed to the kernels
+  const int32_t* sn_first;
+  const int64_t* struct_ptr;
+  const int32_t* struct_idx;
+  const int32_t* rel_idx;
+  const int32_t* sn_parent;
+  const int64_t *lp_off, *up_off, *upd_off;
+  cplx* fac;
+};
+
+__device__ __forceinline__ SnView sn_view(const LuDev& D, int k) {
+  SnView v;
+  v.first = D.sn_first[k];
+  v.s = D.sn_first[k + 1] - v.first;
+  v.r = (int)(D.struct_ptr[k + 1] - D.struct_ptr[k]);
+  v.ld = v.s + v.r;
+  v.lp = D.fac + D.lp_off[k];
+  v.up = D.fac + D.up_off[k];
+  return v;
+}
+
+__device__ __forceinline__ cplx cmul(cplx a, cplx b) { return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+__device__ __forceinline__ cplx csub(cplx a, cplx b) { return make_double2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ cplx cinv(cplx a) {
+  double d = 1.0 / (a.x * a.x + a.y * a.y);
+  return make_double2(a.x * d, -a.y * d);
+}
+__device__ __forceinline__ void catomic_sub(cplx* p, cplx v) {
+  atomicAdd(&p->x, -v.x);
+  atomicAdd(&p->y, -v.y);
+}
+
+// ---- equilibration + scatter of A into the fronts ----------------------------------------------
+__global__ void lu_scale_kernel(const cplx* __restrict__ A, const int32_t* __restrict__ diagpos, int64_t n, double* __restrict__ d) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double s = 1.0;
+  int32_t p = diagpos[i];
+  if (p >= 0) {
+    cplx a = A[p];
+    double m = sqrt(a.x * a.x + a.y * a.y);
+    if (m > 0.0 && isfinite(m)) s = rsqrt(m);
+  }
+  d[i] = s;
+}
+
+__global__ void lu_scatter_kernel(const cplx* __restrict__ A, const int64_t* __restrict__ amap, const int32_t* __restrict__ rowidx,
+                                  const int32_t* __restrict__ colidx, const double* __restrict__ d, int64_t nnz, cplx* __restrict__ fac) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nnz) return;
+  cplx a = A[k];
+  double s = d[rowidx[k]] * d[colidx[k]];
+  fac[amap[k]] = make_double2(a.x * s, a.y * s);
+}
+
+// ---- extend-add: child update matrices into the parent fronts ------------------------------------
+// grid.x = tiles over all children of the level (tile_ptr prefix), block 32x8
+__global__ void __launch_bounds__(256) lu_extend_add_kernel(LuDev D, const int32_t* __restrict__ children, const int32_t* __restrict__ tile_ptr,
+                                                            int nchild, const cplx* __restrict__ upd_child, cplx* __restrict__ upd_parent) {
+  // locate the child of this tile
+  int t = blockIdx.x;
+  int lo = 0, hi = nchild;
+  while (hi - lo > 1) {
+    int mid = (lo + hi) >> 1;
+    if (tile_ptr[mid] <= t) lo = mid; else hi = mid;
+  }
+  const int c = children[lo];
+  const int p = D.sn_parent[c];
+  if (p < 0) return;
+  const int rc = (int)(D.struct_ptr[c + 1] - D.struct_ptr[c]);
+  const int nt = (rc + 31) >> 5;
+  const int tl = t - tile_ptr[lo];
+  const int ti = tl % nt, tj = tl / nt;
+  const int32_t* rel = D.rel_idx + D.struct_ptr[c];
+  const cplx* U = upd_child + D.upd_off[c];
+  SnView P = sn_view(D, p);
+  cplx* A22 = upd_parent + D.upd_off[p];
+  const int x = ti * 32 + threadIdx.x;
+  if (x >= rc) return;
+  const int ia = rel[x];
+  for (int yy = threadIdx.y; yy < 32; yy += 8) {
+    int y = tj * 32 + yy;
+    if (y >= rc) break;
+    cplx v = U[x + (size_t)y * rc];
+    int jb = rel[y];
+    cplx* dst;
+    if (jb < P.s) {
+      if (ia >= P.s || ia / NB >= jb / NB) dst = P.lp + ia + (size_t)jb * P.ld;
+      else dst = P.up + jb + (size_t)ia * P.ld;
+    } else {
+      if (ia < P.s) dst = P.up + jb + (size_t)ia * P.ld;
+      else dst = A22 + (ia - P.s) + (size_t)(jb - P.s) * P.r;
+    }
+    atomicAdd(&dst->x, v.x);
+    atomicAdd(&dst->y, v.y);
+  }
+}
+
+// ---- step k, part 1: LU of the NB x NB diagonal block (no pivoting, static perturbation) ------------
+__global__ void __launch_bounds__(NB * NB) lu_diag_kernel(LuDev D, const int32_t* __restrict__ list, int k, double eps, int* __restrict__ flag) {
+  SnView S = sn_view(D, list[blockIdx.x]);
+  const int c0 = k * NB;
+  if (c0 >= S.s) return;
+  const int nb = min(NB, S.s - c0);
+  __shared__ cplx T[NB][NB + 1];
+  const int i = threadIdx.x, j = threadIdx.y;  // element (row i, col j)
+  cplx* blk = S.lp + c0 + (size_t)c0 * S.ld;
+  if (i < nb && j < nb) T[i][j] = blk[i + (size_t)j * S.ld];
+  __syncthreads();
+  for (int p = 0; p < nb; p++) {
+    if (i == 0 && j == 0) {
+      cplx d = T[p][p];
+      double m = d.x * d.x + d.y * d.y;
+      if (!(m >= eps * eps)) {  // tiny, zero or NaN pivot -> static pivoting
+        if (!isfinite(m)) atomicOr(flag, 2);
+        else atomicAdd(flag + 1, 1);
+        T[p][p] = make_double2(m > 0.0 && isfinite(m) ? d.x * eps / sqrt(m) : eps, m > 0.0 && isfinite(m) ? d.y * eps / sqrt(m) : 0.0);
+      }
+    }
+    __syncthreads();
+    cplx ip = cinv(T[p][p]);
+    if (j == p && i > p && i < nb) T[i][p] = cmul(T[i][p], ip);
+    __syncthreads();
+    if (i > p && j > p && i < nb && j < nb) T[i][j] = csub(T[i][j], cmul(T[i][p], T[p][j]));
+    __syncthreads();
+  }
+  if (i < nb && j < nb) {
+    blk[i + (size_t)j * S.ld] = T[i][j];
+    // U_kk^T into the U^T panel (lower triangle incl. diagonal)
+    if (i >= j) S.up[(c0 + i) + (size_t)(c0 + j) * S.ld] = T[j][i];
+  }
+}
+
+// ---- step k, part 2: panel solves below the diagonal block -------------------------------------------
+//   Lp rows:  X <- X * U_kk^{-1}        Up rows:  X <- X * L_kk^{-T}  (unit diagonal)
+// one thread per row, the NB row entries live in registers, the triangular factor in shared memory
+__global__ void __launch_bounds__(128) lu_panel_kernel(LuDev D, const int32_t* __restrict__ list, int k) {
+  SnView S = sn_view(D, list[blockIdx.z]);
+  const int c0 = k * NB;
+  if (c0 >= S.s) return;
+  const int nb = min(NB, S.s - c0);
+  const int r0 = c0 + nb;
+  const int nrows = S.ld - r0;
+  if ((int)(blockIdx.x * 128) >= nrows) return;
+  const bool upper = blockIdx.y == 1;  // 0: Lp with U_kk, 1: Up with L_kk^T
+  __shared__ cplx T[NB][NB + 1];       // T[m][j] = coefficient multiplying x_m in the equation of x_j
+  __shared__ cplx idiag[NB];
+  const cplx* blk = S.lp + c0 + (size_t)c0 * S.ld;
+  for (int e = threadIdx.x; e < NB * NB; e += 128) {
+    int m = e % NB, j = e / NB;
+    if (m < nb && j < nb) T[m][j] = upper ? blk[j + (size_t)m * S.ld] /* L[j][m] */ : blk[m + (size_t)j * S.ld] /* U[m][j] */;
+  }
+  if (threadIdx.x < nb) idiag[threadIdx.x] = upper ? make_double2(1.0, 0.0) : cinv(blk[threadIdx.x + (size_t)threadIdx.x * S.ld]);
+  __syncthreads();
+  const int row = blockIdx.x * 128 + threadIdx.x;
+  if (row >= nrows) return;
+  cplx* base = (upper ? S.up : S.lp) + (r0 + row) + (size_t)c0 * S.ld;
+  cplx x[NB];
+#pragma unroll
+  for (int j = 0; j < NB; j++) x[j] = j < nb ? base[(size_t)j * S.ld] : make_double2(0.0, 0.0);
+#pragma unroll
+  for (int j = 0; j < NB; j++) {
+    if (j < nb) {
+      cplx acc = x[j];
+#pragma unroll
+      for (int m = 0; m < j; m++) acc = csub(acc, cmul(x[m], T[m][j]));
+      x[j] = cmul(acc, idiag[j]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < NB; j++)
+    if (j < nb) base[(size_t)j * S.ld] = x[j];
+}
+
+// ---- complex GEMM  C -= A * B^T  on the FP64 tensor cores -----------------------------------------------
+// A: m x K (lda), B: n x K (ldb), C: m x n (ldc), all column-major complex.  CTA tile 64x64, 8 warps (4 along m,
+// 2 along n), warp tile 16x32 = 2x4 DMMA m8n8k4 tiles, K tile 16, operands split into re/im planes in smem.
+#define GT 64
+#define GK 16
+#define GLD 72  // padded leading dimension: (kk*GLD + mm) mod 16 hits every value twice -> conflict-free LDS.64
+
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+struct GemmProblem {
+  int m, n, K, lda, ldb, ldc;
+  const cplx *A, *B;
+  cplx* C;
+};
+
+__device__ __forceinline__ void zgemm_nt_tile(const GemmProblem& P, int tile_m, int tile_n) {
+  __shared__ double As[2][GK][GLD], Bs[2][GK][GLD];  // [re/im][k][row]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp & 3) * 16, wn = (warp >> 2) * 32;
+  const int m0 = tile_m * GT, n0 = tile_n * GT;
+  double acc_r[2][4][2], acc_i[2][4][2];
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) acc_r[a][b][0] = acc_r[a][b][1] = acc_i[a][b][0] = acc_i[a][b][1] = 0.0;
+  const int lr = tid & 63, lk = tid >> 6;  // loader: row lr, k-columns lk, lk+4, lk+8, lk+12
+  for (int k0 = 0; k0 < P.K; k0 += GK) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      int kk = lk + 4 * q;
+      cplx a = make_double2(0.0, 0.0), b = make_double2(0.0, 0.0);
+      if (k0 + kk < P.K) {
+        if (m0 + lr < P.m) a = P.A[(m0 + lr) + (size_t)(k0 + kk) * P.lda];
+        if (n0 + lr < P.n) b = P.B[(n0 + lr) + (size_t)(k0 + kk) * P.ldb];
+      }
+      As[0][kk][lr] = a.x; As[1][kk][lr] = a.y;
+      Bs[0][kk][lr] = b.x; Bs[1][kk][lr] = b.y;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < GK; ks += 4) {
+      const int kk = ks + (lane & 3), rr = lane >> 2;
+      double ar[2], ai[2], br[4], bi[4];
+#pragma unroll
+      for (int a = 0; a < 2; a++) {
+        ar[a] = As[0][kk][wm + a * 8 + rr];
+        ai[a] = As[1][kk][wm + a * 8 + rr];
+      }
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        br[b] = Bs[0][kk][wn + b * 8 + rr];
+        bi[b] = Bs[1][kk][wn + b * 8 + rr];
+      }
+#pragma unroll
+      for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+          dmma(acc_r[a][b][0], acc_r[a][b][1], ar[a], br[b]);
+          dmma(acc_r[a][b][0], acc_r[a][b][1], -ai[a], bi[b]);
+          dmma(acc_i[a][b][0], acc_i[a][b][1], ar[a], bi[b]);
+          dmma(acc_i[a][b][0], acc_i[a][b][1], ai[a], br[b]);
+        }
+    }
+    __syncthreads();
+  }
+  // C -= acc ; fragment: row = lane/4, cols = (lane%4)*2 + {0,1}
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        int row = m0 + wm + a * 8 + (lane >> 2), col = n0 + wn + b * 8 + (lane & 3) * 2 + e;
+        if (row < P.m && col < P.n) {
+          cplx* c = P.C + row + (size_t)col * P.ldc;
+          cplx v = *c;
+          v.x -= acc_r[a][b][e];
+          v.y -= acc_i[a][b][e];
+          *c = v;
+        }
+      }
+}
+
+// mode 0: Lp trailing pivot columns, mode 1: Up trailing pivot columns (step k), mode 2: Schur complement
+__global__ void __launch_bounds__(256) lu_gemm_kernel(LuDev D, const int32_t* __restrict__ list, int k, int mode, cplx* __restrict__ upd) {
+  const int sn = list[blockIdx.z];
+  SnView S = sn_view(D, sn);
+  GemmProblem P;
+  if (mode == 2) {
+    if (S.r == 0) return;
+    P.m = P.n = S.r; P.K = S.s;
+    P.lda = P.ldb = S.ld; P.ldc = S.r;
+    P.A = S.lp + S.s; P.B = S.up + S.s;
+    P.C = upd + D.upd_off[sn];
+  } else {
+    const int c0 = k * NB;
+    if (c0 + NB >= S.s) return;  // no trailing pivot columns
+    const int r0 = c0 + NB;
+    P.m = S.ld - r0; P.n = S.s - r0; P.K = NB;
+    P.lda = P.ldb = P.ldc = S.ld;
+    cplx* X = mode == 0 ? S.lp : S.up;
+    cplx* Y = mode == 0 ? S.up : S.lp;
+    P.A = X + r0 + (size_t)c0 * S.ld;
+    P.B = Y + r0 + (size_t)c0 * S.ld;
+    P.C = X + r0 + (size_t)r0 * S.ld;
+  }
+  if ((int)(blockIdx.x * GT) >= P.m || (int)(blockIdx.y * GT) >= P.n) return;
+  zgemm_nt_tile(P, blockIdx.x, blockIdx.y);
+}
+
+// ---- triangular solves ---------------------------------------------------------------------------------
+// forward substitution with a lower-trapezoidal panel P (Lp: unit diagonal, Up: general diagonal)
+// phase 1 (one CTA per supernode): pivot block, blocked by NB, warp-shuffle substitution inside a block
+__global__ void __launch_bounds__(256) lu_fwd_pivot_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int nrhs, int64_t n, cplx* __restrict__ x) {
+  SnView S = sn_view(D, list[blockIdx.x]);
+  const cplx* P = use_up ? S.up : S.lp;
+  const bool unit = !use_up;
+  __shared__ cplx yk[NB];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int rhs = 0; rhs < nrhs; rhs++) {
+    cplx* xs = x + (size_t)rhs * n + S.first;
+    for (int c0 = 0; c0 < S.s; c0 += NB) {
+      const int nb = min(NB, S.s - c0);
+      if (warp == 0) {
+        cplx v = lane < nb ? xs[c0 + lane] : make_double2(0.0, 0.0);
+        for (int m = 0; m < nb; m++) {
+          cplx ym;
+          if (!unit) {
+            cplx d = P[(c0 + m) + (size_t)(c0 + m) * S.ld];
+            if (lane == m) v = cmul(v, cinv(d));
+          }
+          ym.x = __shfl_sync(0xffffffffu, v.x, m);
+          ym.y = __shfl_sync(0xffffffffu, v.y, m);
+          if (lane > m && lane < nb) v = csub(v, cmul(P[(c0 + lane) + (size_t)(c0 + m) * S.ld], ym));
+        }
+        if (lane < nb) {
+          xs[c0 + lane] = v;
+          yk[lane] = v;
+        }
+      }
+      __syncthreads();
+      for (int i = c0 + nb + threadIdx.x; i < S.s; i += blockDim.x) {
+        cplx acc = make_double2(0.0, 0.0);
+        const cplx* row = P + i + (size_t)c0 * S.ld;
+        for (int j = 0; j < nb; j++) {
+          cplx a = row[(size_t)j * S.ld];
+          acc.x += a.x * yk[j].x - a.y * yk[j].y;
+          acc.y += a.x * yk[j].y + a.y * yk[j].x;
+        }
+        xs[i] = csub(xs[i], acc);
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// phase 2 (grid.x row chunks, grid.y supernode): x[struct rows] -= P21 * y_S  (atomic: siblings share ancestors)
+__global__ void __launch_bounds__(128) lu_fwd_struct_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int nrhs, int64_t n, cplx* __restrict__ x) {
+  SnView S = sn_view(D, list[blockIdx.y]);
+  const int i = blockIdx.x * 128 + threadIdx.x;
+  if (blockIdx.x * 128 >= S.r) return;
+  const cplx* P = (use_up ? S.up : S.lp) + S.s;
+  const int32_t* st = D.struct_idx + D.struct_ptr[list[blockIdx.y]];
+  __shared__ cplx ys[128];
+  for (int rhs = 0; rhs < nrhs; rhs++) {
+    const cplx* xs = x + (size_t)rhs * n + S.first;
+    cplx acc = make_double2(0.0, 0.0);
+    for (int c0 = 0; c0 < S.s; c0 += 128) {
+      __syncthreads();
+      if (c0 + threadIdx.x < S.s) ys[threadIdx.x] = xs[c0 + threadIdx.x];
+      __syncthreads();
+      if (i < S.r) {
+        const int nc = min(128, S.s - c0);
+        const cplx* row = P + i + (size_t)c0 * S.ld;
+        for (int j = 0; j < nc; j++) {
+          cplx a = row[(size_t)j * S.ld];
+          acc.x += a.x * ys[j].x - a.y * ys[j].y;
+          acc.y += a.x * ys[j].y + a.y * ys[j].x;
+        }
+      }
+    }
+    if (i < S.r) catomic_sub(x + (size_t)rhs * n + st[i], acc);
+  }
+}
+
+// backward substitution with the TRANSPOSE of a lower-trapezoidal panel.
+// phase 1 (grid.x column chunks of 8 columns = 8 warps, grid.y supernode): x_S[c] -= sum_i P21[i,c] * x[struct[i]]
+__global__ void __launch_bounds__(256) lu_bwd_struct_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int nrhs, int64_t n, cplx* __restrict__ x) {
+  SnView S = sn_view(D, list[blockIdx.y]);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 8 + warp;
+  if (c >= S.s || S.r == 0) return;
+  const cplx* col = (use_up ? S.up : S.lp) + S.s + (size_t)c * S.ld;
+  const int32_t* st = D.struct_idx + D.struct_ptr[list[blockIdx.y]];
+  for (int rhs = 0; rhs < nrhs; rhs++) {
+    cplx* xr = x + (size_t)rhs * n;
+    double sr = 0.0, si = 0.0;
+    for (int i = lane; i < S.r; i += 32) {
+      cplx a = col[i], v = xr[st[i]];
+      sr += a.x * v.x - a.y * v.y;
+      si += a.x * v.y + a.y * v.x;
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+      sr += __shfl_xor_sync(0xffffffffu, sr, off);
+      si += __shfl_xor_sync(0xffffffffu, si, off);
+    }
+    if (lane == 0) {
+      cplx* d = xr + S.first + c;
+      d->x -= sr;
+      d->y -= si;
+    }
+  }
+}
+
+// phase 2 (one CTA per supernode, 32 warps): pivot block, blocks from last to first.
+__global__ void __launch_bounds__(1024) lu_bwd_pivot_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int nrhs, int64_t n, cplx* __restrict__ x) {
+  SnView S = sn_view(D, list[blockIdx.x]);
+  const cplx* P = use_up ? S.up : S.lp;
+  const bool unit = !use_up;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int nblk = (S.s + NB - 1) / NB;
+  for (int rhs = 0; rhs < nrhs; rhs++) {
+    cplx* xs = x + (size_t)rhs * n + S.first;
+    for (int kb = nblk - 1; kb >= 0; kb--) {
+      const int c0 = kb * NB, nb = min(NB, S.s - c0);
+      // column c0+warp: subtract the contribution of the already solved pivot rows below this block
+      if (warp < nb) {
+        const cplx* col = P + (size_t)(c0 + warp) * S.ld;
+        double sr = 0.0, si = 0.0;
+        for (int i = c0 + nb + lane; i < S.s; i += 32) {
+          cplx a = col[i], v = xs[i];
+          sr += a.x * v.x - a.y * v.y;
+          si += a.x * v.y + a.y * v.x;
+        }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) {
+          sr += __shfl_xor_sync(0xffffffffu, sr, off);
+          si += __shfl_xor_sync(0xffffffffu, si, off);
+        }
+        if (lane == 0) {
+          xs[c0 + warp].x -= sr;
+          xs[c0 + warp].y -= si;
+        }
+      }
+      __syncthreads();
+      // in-block transposed solve: x_j = (x_j - sum_{m>j} T[m][j] x_m) / T[j][j]
+      if (warp == 0) {
+        cplx v = lane < nb ? xs[c0 + lane] : make_double2(0.0, 0.0);
+        for (int m = nb - 1; m >= 0; m--) {
+          if (!unit) {
+            cplx d = P[(c0 + m) + (size_t)(c0 + m) * S.ld];
+            if (lane == m) v = cmul(v, cinv(d));
+          }
+          cplx ym;
+          ym.x = __shfl_sync(0xffffffffu, v.x, m);
+          ym.y = __shfl_sync(0xffffffffu, v.y, m);
+          if (lane < m) v = csub(v, cmul(P[(c0 + m) + (size_t)(c0 + lane) * S.ld], ym));
+        }
+        if (lane < nb) xs[c0 + lane] = v;
+      }
+      __syncthreads();
+    }
+  }
+}
+
+// ---- vector utilities -------------------------------------------------------------------------------------
+// y[pos] = d[perm[pos]] * b[perm[pos]] (optionally conjugated)      /      x[perm[pos]] = d[perm[pos]] * y[pos]
+__global__ void lu_permute_in_kernel(const cplx* __restrict__ b, const int32_t* __restrict__ perm, const double* __restrict__ d,
+                                     int64_t n, int nrhs, int conj, cplx* __restrict__ y) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  int32_t o = perm[p];
+  double s = d[o];
+  for (int r = 0; r < nrhs; r++) {
+    cplx v = b[(size_t)r * n + o];
+    y[(size_t)r * n + p] = make_double2(v.x * s, conj ? -v.y * s : v.y * s);
+  }
+}
+__global__ void lu_permute_out_kernel(const cplx* __restrict__ y, const int32_t* __restrict__ perm, const double* __restrict__ d,
+                                      int64_t n, int nrhs, int conj, int accumulate, cplx* __restrict__ x) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  int32_t o = perm[p];
+  double s = d[o];
+  for (int r = 0; r < nrhs; r++) {
+    cplx v = y[(size_t)r * n + p];
+    v = make_double2(v.x * s, conj ? -v.y * s : v.y * s);
+    cplx* dst = x + (size_t)r * n + o;
+    if (accumulate) {
+      v.x += dst->x;
+      v.y += dst->y;
+    }
+    *dst = v;
+  }
+}
+// r = b - r
+__global__ void lu_residual_kernel(const cplx* __restrict__ b, int64_t total, cplx* __restrict__ r) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  r[i] = make_double2(b[i].x - r[i].x, b[i].y - r[i].y);
+}
+
+// ============================================================================================================
+static LuDev make_dev(LuSolver& S) {
+  LuDev D;
+  D.sn_first = S.d_sn_first.p;
+  D.struct_ptr = S.d_struct_ptr.p;
+  D.struct_idx = S.d_struct_idx.p;
+  D.rel_idx = S.d_rel_idx.p;
+  D.sn_parent = S.d_sn_parent.p;
+  D.lp_off = S.d_lp_off.p;
+  D.up_off = S.d_up_off.p;
+  D.upd_off = S.d_upd_off.p;
+  D.fac = S.d_fac.p;
+  return D;
+}
+
+void wae_lu_setup_device(wae_ctx* h, LuSolver& S) {
+  LuSymbolic& Y = S.sym;
+  cudaStream_t st = h->stream;
+  S.d_perm.upload(Y.perm, st);
+  S.d_iperm.upload(Y.iperm, st);
+  S.d_sn_first.upload(Y.sn_first, st);
+  S.d_sn_parent.upload(Y.sn_parent, st);
+  S.d_struct_ptr.upload(Y.struct_ptr, st);
+  S.d_struct_idx.upload(Y.struct_idx.empty() ? std::vector<int32_t>(1, 0) : Y.struct_idx, st);
+  S.d_rel_idx.upload(Y.rel_idx.empty() ? std::vector<int32_t>(1, 0) : Y.rel_idx, st);
+  S.d_diagpos.upload(Y.diagpos, st);
+  S.d_lp_off.upload(Y.lp_off, st);
+  S.d_up_off.upload(Y.up_off, st);
+  S.d_upd_off.upload(Y.upd_off, st);
+  S.d_amap.upload(Y.amap, st);
+  // per-depth lists, largest pivot block first (so that "supernodes with more than k blocks" is a prefix)
+  S.d_level.resize(Y.levels.size());
+  for (size_t d = 0; d < Y.levels.size(); d++) {
+    std::vector<int32_t>& L = Y.levels[d];
+    std::stable_sort(L.begin(), L.end(), [&](int32_t a, int32_t b) {
+      return Y.sn_first[a + 1] - Y.sn_first[a] > Y.sn_first[b + 1] - Y.sn_first[b];
+    });
+    S.d_level[d].upload(L, st);
+  }
+  S.d_xa_tile_ptr.resize(Y.levels.size());
+  S.xa_tiles.assign(Y.levels.size(), 0);
+  for (size_t d = 0; d < Y.levels.size(); d++) {
+    const std::vector<int32_t>& C = Y.levels[d];
+    std::vector<int32_t> tile_ptr(C.size() + 1, 0);
+    for (size_t i = 0; i < C.size(); i++) {
+      int64_t r = Y.struct_ptr[C[i] + 1] - Y.struct_ptr[C[i]];
+      int64_t nt = (r + 31) / 32;
+      tile_ptr[i + 1] = tile_ptr[i] + (int32_t)(nt * nt);
+    }
+    S.xa_tiles[d] = tile_ptr.back();
+    S.d_xa_tile_ptr[d].upload(tile_ptr, st);
+  }
+  // column index of every nonzero of A
+  {
+    Pattern& U = h->pat(h->fam(S.fam).pattern);
+    std::vector<int32_t> col(U.nnz);
+    for (int64_t j = 0; j < U.dim; j++)
+      for (int64_t k = U.colptr[j]; k < U.colptr[j + 1]; k++) col[k] = (int32_t)j;
+    S.d_colidx_nz.upload(col, st);
+    S.d_Aval.alloc((size_t)U.nnz);
+  }
+  int64_t e0 = 0, e1 = 0;
+  for (size_t d = 0; d < Y.level_upd_size.size(); d++) (d & 1 ? e1 : e0) = std::max<int64_t>(d & 1 ? e1 : e0, Y.level_upd_size[d]);
+  S.d_upd[0].alloc((size_t)std::max<int64_t>(e0, 1));
+  S.d_upd[1].alloc((size_t)std::max<int64_t>(e1, 1));
+  S.d_fac.alloc((size_t)std::max<int64_t>(Y.fac_size, 1));
+  S.d_scale.alloc(Y.n);
+  S.d_flag.alloc(2);
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  std::vector<int64_t>().swap(Y.amap);  // large and only needed on the device
+}
+
+void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval) {
+  LuSymbolic& Y = S.sym;
+  cudaStream_t st = h->stream;
+  Family& F = h->fam(S.fam);
+  Pattern& U = h->pat(F.pattern);
+  wae_family_ensure_csr(h, F);
+  CUDA_CHECK(cudaMemcpyAsync(S.d_Aval.p, d_Aval, (size_t)U.nnz * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
+  LuDev D = make_dev(S);
+  CUDA_CHECK(cudaMemsetAsync(S.d_fac.p, 0, (size_t)Y.fac_size * sizeof(cplx), st));
+  CUDA_CHECK(cudaMemsetAsync(S.d_flag.p, 0, 2 * sizeof(int32_t), st));
+  lu_scale_kernel<<<(unsigned)((Y.n + 255) / 256), 256, 0, st>>>(d_Aval, S.d_diagpos.p, Y.n, S.d_scale.p);
+  lu_scatter_kernel<<<(unsigned)((U.nnz + 255) / 256), 256, 0, st>>>(d_Aval, S.d_amap.p, U.d_rowval.p, S.d_colidx_nz.p, S.d_scale.p, U.nnz, S.d_fac.p);
+  h->launches += 2;
+  const int maxd = (int)Y.levels.size() - 1;
+  for (int d = maxd; d >= 0; d--) {
+    const std::vector<int32_t>& L = Y.levels[d];
+    const int nl = (int)L.size();
+    cplx* upd = S.d_upd[d & 1].p;
+    if (Y.level_upd_size[d]) CUDA_CHECK(cudaMemsetAsync(upd, 0, (size_t)Y.level_upd_size[d] * sizeof(cplx), st));
+    if (d < maxd && S.xa_tiles[d + 1] > 0) {
+      lu_extend_add_kernel<<<S.xa_tiles[d + 1], dim3(32, 8), 0, st>>>(D, S.d_level[d + 1].p, S.d_xa_tile_ptr[d + 1].p,
+                                                                        (int)Y.levels[d + 1].size(), S.d_upd[(d + 1) & 1].p, upd);
+      h->launches++;
+    }
+    // blocked partial factorisation of all fronts of this depth
+    int max_s = 0, max_ld = 0, max_r = 0;
+    for (int32_t k : L) {
+      int s = Y.sn_first[k + 1] - Y.sn_first[k], r = (int)(Y.struct_ptr[k + 1] - Y.struct_ptr[k]);
+      max_s = std::max(max_s, s);
+      max_ld = std::max(max_ld, s + r);
+      max_r = std::max(max_r, r);
+    }
+    const int nsteps = (max_s + NB - 1) / NB;
+    for (int k = 0; k < nsteps; k++) {
+      // supernodes with more than k blocks form a prefix of the (size-sorted) list
+      int cnt = 0;
+      while (cnt < nl && Y.sn_first[L[cnt] + 1] - Y.sn_first[L[cnt]] > k * NB) cnt++;
+      if (!cnt) break;
+      for (int z0 = 0; z0 < cnt; z0 += 32768) {
+        int zc = std::min(32768, cnt - z0);
+        const int32_t* lst = S.d_level[d].p + z0;
+        lu_diag_kernel<<<zc, dim3(NB, NB), 0, st>>>(D, lst, k, S.pivot_eps, S.d_flag.p);
+        int rows = max_ld - (k + 1) * NB;
+        if (rows > 0) {
+          lu_panel_kernel<<<dim3((rows + 127) / 128, 2, zc), 128, 0, st>>>(D, lst, k);
+          int tn = max_s - (k + 1) * NB;
+          if (tn > 0) {
+            dim3 g((rows + GT - 1) / GT, (tn + GT - 1) / GT, zc);
+            lu_gemm_kernel<<<g, 256, 0, st>>>(D, lst, k, 0, nullptr);
+            lu_gemm_kernel<<<g, 256, 0, st>>>(D, lst, k, 1, nullptr);
+            h->launches += 2;
+          }
+          h->launches++;
+        }
+        h->launches++;
+      }
+    }
+    if (max_r > 0) {
+      for (int z0 = 0; z0 < nl; z0 += 32768) {
+        int zc = std::min(32768, nl - z0);
+        dim3 g((max_r + GT - 1) / GT, (max_r + GT - 1) / GT, zc);
+        lu_gemm_kernel<<<g, 256, 0, st>>>(D, S.d_level[d].p + z0, 0, 2, upd);
+        h->launches++;
+      }
+    }
+  }
+  CUDA_CHECK(cudaGetLastError());
+  int32_t flag[2] = {0, 0};
+  CUDA_CHECK(cudaMemcpyAsync(flag, S.d_flag.p, sizeof(flag), cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  S.factored = true;
+  if (flag[0] & 2) {
+    S.factored = false;
+    WAE_THROW(WAE_E_SINGULAR, "non-finite pivot in the numeric factorisation");
+  }
+  h->last_ms["static_pivots"] = flag[1];
+}
+
+static void lu_sweeps(wae_ctx* h, LuSolver& S, int trans_t, int nrhs, cplx* y) {
+  LuSymbolic& Y = S.sym;
+  cudaStream_t st = h->stream;
+  LuDev D = make_dev(S);
+  const int maxd = (int)Y.levels.size() - 1;
+  const int fwd_up = trans_t ? 1 : 0;  // A: forward with Lp, backward with Up ; A^T: forward with Up, backward with Lp
+  for (int d = maxd; d >= 0; d--) {
+    const std::vector<int32_t>& L = Y.levels[d];
+    int max_r = 0;
+    for (int32_t k : L) max_r = std::max(max_r, (int)(Y.struct_ptr[k + 1] - Y.struct_ptr[k]));
+    for (int z0 = 0; z0 < (int)L.size(); z0 += 32768) {
+      int zc = std::min<int>(32768, (int)L.size() - z0);
+      lu_fwd_pivot_kernel<<<zc, 256, 0, st>>>(D, S.d_level[d].p + z0, fwd_up, nrhs, Y.n, y);
+      h->launches++;
+      if (max_r > 0) {
+        lu_fwd_struct_kernel<<<dim3((max_r + 127) / 128, zc), 128, 0, st>>>(D, S.d_level[d].p + z0, fwd_up, nrhs, Y.n, y);
+        h->launches++;
+      }
+    }
+  }
+  for (int d = 0; d <= maxd; d++) {
+    const std::vector<int32_t>& L = Y.levels[d];
+    int max_s = 0, max_r = 0;
+    for (int32_t k : L) {
+      max_s = std::max(max_s, Y.sn_first[k + 1] - Y.sn_first[k]);
+      max_r = std::max(max_r, (int)(Y.struct_ptr[k + 1] - Y.struct_ptr[k]));
+    }
+    for (int z0 = 0; z0 < (int)L.size(); z0 += 32768) {
+      int zc = std::min<int>(32768, (int)L.size() - z0);
+      if (max_r > 0) {
+        lu_bwd_struct_kernel<<<dim3((max_s + 7) / 8, zc), 256, 0, st>>>(D, S.d_level[d].p + z0, !fwd_up, nrhs, Y.n, y);
+        h->launches++;
+      }
+      lu_bwd_pivot_kernel<<<zc, 1024, 0, st>>>(D, S.d_level[d].p + z0, !fwd_up, nrhs, Y.n, y);
+      h->launches++;
+    }
+  }
+}
+
+void wae_lu_solve_device(wae_ctx* h, LuSolver& S, int trans, int nrhs, cplx* d_X, int refine) {
+  Family& F = h->fam(S.fam);
+  if (!S.factored) WAE_THROW(WAE_E_INVALID, "wae_lu_factor has not been called (or failed)");
+  LuSymbolic& Y = S.sym;
+  cudaStream_t st = h->stream;
+  const int64_t n = Y.n;
+  if (S.work_nrhs < nrhs) {
+    S.d_work.alloc((size_t)3 * n * nrhs);
+    S.work_nrhs = nrhs;
+  }
+  cplx* y = S.d_work.p;                       // permuted work vector
+  cplx* b0 = S.d_work.p + (size_t)n * nrhs;   // copy of the right-hand side
+  cplx* res = S.d_work.p + (size_t)2 * n * nrhs;
+  const int conj = trans == 2;
+  const int tt = trans != 0;
+  unsigned gb = (unsigned)((n + 255) / 256);
+  if (refine > 0) CUDA_CHECK(cudaMemcpyAsync(b0, d_X, (size_t)n * nrhs * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
+  // A^H x = b  <=>  A^T conj(x) = conj(b)
+  lu_permute_in_kernel<<<gb, 256, 0, st>>>(d_X, S.d_perm.p, S.d_scale.p, n, nrhs, conj, y);
+  lu_sweeps(h, S, tt, nrhs, y);
+  lu_permute_out_kernel<<<gb, 256, 0, st>>>(y, S.d_perm.p, S.d_scale.p, n, nrhs, conj, 0, d_X);
+  h->launches += 2;
+  for (int it = 0; it < refine; it++) {
+    // res = b - op(A) x ; x += op(A)^{-1} res
+    wae_spmm_values(h, F, S.d_Aval.p, trans, nrhs, d_X, res);
+    lu_residual_kernel<<<(unsigned)(((size_t)n * nrhs + 255) / 256), 256, 0, st>>>(b0, n * nrhs, res);
+    lu_permute_in_kernel<<<gb, 256, 0, st>>>(res, S.d_perm.p, S.d_scale.p, n, nrhs, conj, y);
+    lu_sweeps(h, S, tt, nrhs, y);
+    lu_permute_out_kernel<<<gb, 256, 0, st>>>(y, S.d_perm.p, S.d_scale.p, n, nrhs, conj, 1, d_X);
+    h->launches += 3;
+  }
+  CUDA_CHECK(cudaGetLastError());
+}

@@ -187,4 +187,5 @@ void wae_launch_assemble_gather(wae_ctx* h, Pattern& P, const double* d_c, doubl
                                 double mass_scale);
 void wae_combine_device(wae_ctx* h, Family& F, const double* coeffs_host, int slot);
 void wae_spmm_device(wae_ctx* h, Family& F, int slot, int trans, int nrhs, const cplx* X, cplx* Y);
+void wae_spmm_values(wae_ctx* h, Family& F, const cplx* val, int trans, int nrhs, const cplx* X, cplx* Y);
 void wae_family_ensure_csr(wae_ctx* h, Family& F);
