@@ -39,8 +39,8 @@ def test_solve_matches_superlu(order):
             X = ctx.lu_solve(lid, B, trans=trans)
             Xref = lu.solve(B, trans=code)
             # backward error against the true matrix and agreement with SuperLU
-            res = np.abs(Aop @ X - B).max() / (abs(Aop).max() * np.abs(X).max())
-            assert res < 1e-13, (order, z, trans, res)
+            res = (np.abs(Aop @ X - B) / (abs(Aop) @ np.abs(X) + np.abs(B))).max()  # componentwise backward error
+            assert res < 1e-12, (order, z, trans, res)
             assert np.abs(X - Xref).max() <= 1e-7 * np.abs(Xref).max()
         x1 = ctx.lu_solve(lid, B[:, 0])
         assert np.abs(x1 - lu.solve(B[:, 0])).max() <= 1e-7 * np.abs(x1).max()
@@ -61,10 +61,15 @@ def test_eigs_matches_arpack():
     ctx.lu_factor(lid, 0)
     v0 = np.ones(L.size(), dtype=complex)
     lam, V, ns = ctx.eigs_si(lid, dev.fid, 1, 1, v0, trans=0)
-    lam_ref = spla.eigs(sp.csc_matrix(A), k=1, M=sp.csc_matrix(M), sigma=0, v0=v0, tol=0)[0]
+    lam_ref, v_ref = spla.eigs(sp.csc_matrix(A), k=1, M=sp.csc_matrix(M), sigma=0, v0=v0, tol=0)
     assert abs(lam[0] - lam_ref[0]) <= 1e-10 * abs(lam_ref[0])
-    r = A @ V[:, 0] - lam[0] * (M @ V[:, 0])
-    assert np.abs(r).max() <= 1e-10 * np.abs(A @ V[:, 0]).max()
+
+    def phase(v):
+        v = v / np.linalg.norm(v)
+        k = np.argmax(np.abs(v))
+        return v * (abs(v[k]) / v[k])
+    # eigenvector parity after phase normalisation (BASELINE.json: 1e-8); the Y=1e15 penalty rows hold ~1e-17 values
+    assert np.abs(phase(V[:, 0]) - phase(v_ref[:, 0])).max() <= 1e-8
     lam3, V3, _ = ctx.eigs_si(lid, dev.fid, 1, 3, v0, trans=0)
     ref3 = spla.eigs(sp.csc_matrix(A), k=3, M=sp.csc_matrix(M), sigma=0, v0=v0, tol=0)[0]
     assert np.abs(np.sort_complex(lam3) - np.sort_complex(ref3)).max() <= 1e-8 * np.abs(ref3).max()
@@ -138,8 +143,14 @@ def test_beyn_gpu_vs_oracle():
     Lo = odisc(mo, rijke_dscrp(0.0, 0.001), mo.generate_field(speedofsound))
     Lg = _gpu_family("lin", n=0.0)
     G = [z * 2 * math.pi for z in (150 + 5j, 150 - 5j, 1000 - 5j, 1000 + 5j)]
-    Oo, Po = obeyn(Lo, G, l=5, N=16)
-    Og, Pg = W.beyn(Lg, G, l=5, N=16, output=False)
+    # moment matrices agree to solver accuracy ...
+    from oracle.nlevp import beyn_moments as omoments
+    Ao = omoments(Lo, G, 5, 1, 16)
+    Ag = W.compute_moment_matrices(Lg, G, l=5, K=1, N=16)
+    assert np.abs(Ag - Ao).max() <= 1e-9 * np.abs(Ao).max()
+    # ... and so do the eigenvalues once the noise singular values (~1e-14 vs 1e2) are cut (tol is absolute, beyn.jl:92-95)
+    Oo, Po = obeyn(Lo, G, l=5, N=16, tol=1e-8)
+    Og, Pg = W.beyn(Lg, G, l=5, N=16, tol=1e-8, output=False)
     assert len(Og) == len(Oo) == 2
     assert np.abs(np.sort_complex(Og) - np.sort_complex(Oo)).max() <= 1e-8 * np.abs(Oo).max()
     # the reference's own idiom (tutorial_06...jl:41-55): polish with householder

@@ -56,7 +56,7 @@ struct LuSolver {
   int work_nrhs = 0;
   bool factored = false;
   int refine_steps = 1;
-  double pivot_eps = 1e-14;
+  double pivot_eps = 1e-30;  // only exact zeros are replaced: near-singular L(omega) is the normal case close to an eigenvalue
 };
 
 // numeric phase (lu_numeric.cu) -- all on the context stream, device pointers

@@ -279,6 +279,8 @@ int32_t wae_lu_analyze(wae_ctx* h, int32_t fam_id, int32_t* lu_id, int64_t* fact
   bool have = dof_coords(h, U.dim, xyz);
   int leaf = 64;
   if (const char* env = getenv("WAE_LU_LEAF")) leaf = atoi(env);
+  if (const char* env = getenv("WAE_LU_PIVOT_EPS")) S->pivot_eps = atof(env);
+  if (const char* env = getenv("WAE_LU_REFINE")) S->refine_steps = atoi(env);
   wae_lu_symbolic(U.dim, U.colptr.data(), U.rowval.data(), have ? xyz.data() : nullptr, leaf, S->sym);
   wae_lu_setup_device(h, *S);
   h->lus.push_back(S);

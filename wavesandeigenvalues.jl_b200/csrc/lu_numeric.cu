@@ -620,7 +620,7 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval) {
         int zc = std::min(32768, cnt - z0);
         const int32_t* lst = S.d_level[d].p + z0;
         lu_diag_kernel<<<zc, dim3(NB, NB), 0, st>>>(D, lst, k, S.pivot_eps, S.d_flag.p);
-        int rows = max_ld - (k + 1) * NB;
+        int rows = max_ld - k * NB - 1;  // upper bound of ld - (c0 + nb) over the batch (nb >= 1)
         if (rows > 0) {
           lu_panel_kernel<<<dim3((rows + 127) / 128, 2, zc), 128, 0, st>>>(D, lst, k);
           int tn = max_s - (k + 1) * NB;

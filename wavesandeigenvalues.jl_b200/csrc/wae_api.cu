@@ -347,8 +347,6 @@ int32_t wae_mat_set(wae_ctx* h, int64_t dim, const int64_t* colptr, const int64_
   WAE_API_BEGIN
   CUDA_CHECK(cudaSetDevice(h->device));
   if (dim <= 0 || !colptr || !rowval || !nzval) WAE_THROW(WAE_E_INVALID, "bad matrix arguments");
-  if (h->dim == 0) h->dim = dim;
-  if (dim != h->dim) WAE_THROW(WAE_E_INVALID, "matrix dimension %lld differs from the context dimension %lld", (long long)dim, (long long)h->dim);
   int pid = new_pattern(h);
   Pattern& P = *h->patterns[pid];
   P.dim = dim;
