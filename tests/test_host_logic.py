@@ -1,0 +1,184 @@
+"""CPU tests of the product's host side (no GPU): mesh numbering rules, scalar algebra, family evaluation
+rules and the symbolic LU phase, each against the oracle restatement of the reference."""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+import wae_b200 as W
+from cases import load_raw_mesh, speedofsound
+from oracle import mesh as omesh
+from oracle import nlevp as onlevp
+from wae_b200 import nlevp
+
+
+@pytest.fixture(scope="module")
+def meshes():
+    raw = load_raw_mesh("rijke_mm")
+    return W.Mesh("m", scale=0.001, raw=raw), omesh.Mesh("m", scale=0.001, raw=raw)
+
+
+def test_simplex_ordering_and_domains(meshes):
+    mg, mo = meshes
+    assert np.array_equal(mg.tetrahedra, np.array(mo.tetrahedra))
+    assert np.array_equal(mg.triangles, np.array(mo.triangles))
+    for dom in mo.domains:
+        assert list(mg.domains[dom]["simplices"]) == list(mo.domains[dom]["simplices"]), dom
+        assert mg.domains[dom]["dimension"] == mo.domains[dom]["dimension"]
+
+
+def test_quadratic_dof_numbering(meshes):
+    mg, mo = meshes
+    tg, tt, dg = W.aggregate_elements(mg, "quad")
+    to, tto, do = omesh.aggregate_elements(mo, "quad")
+    assert dg == do
+    assert np.array_equal(tt, np.array(tto)) and np.array_equal(tg, np.array(to))
+    assert np.array_equal(mg.lines, np.array(mo.lines))
+
+
+def test_mesh_queries(meshes):
+    mg, mo = meshes
+    assert np.array_equal(mg.link_triangles_to_tetrahedra(), mo.link_triangles_to_tetrahedra())
+    for dom in ("Flame", "Outlet", "Interior"):
+        assert abs(mg.compute_size(dom) - mo.compute_size(dom)) <= 1e-13 * mo.compute_size(dom)
+    for p in ([0.0, 0.0, -0.00101], [0.01, 0.005, 0.1], [1.0, 1.0, 1.0]):
+        assert mg.find_tetrahedron_containing_point(p) == mo.find_tetrahedron_containing_point(p)
+    assert np.array_equal(mg.generate_field(speedofsound), mo.generate_field(speedofsound))
+
+
+def test_ragged_and_duplicate_input():
+    """duplicated simplices and an empty domain (Mesh constructor, Meshutils.jl:118-147)."""
+    pts = np.array([[0, 1, 0, 0, 1.0], [0, 0, 1, 0, 1.0], [0, 0, 0, 1, 1.0]])
+    tets = [[0, 1, 2, 3], [3, 2, 1, 0], [1, 2, 3, 4]]
+    tris = [[0, 1, 2], [2, 1, 0]]
+    dom = {"A": {"dimension": 3, "simplices": [0, 1, 2]}, "E": {"dimension": 2, "simplices": []}, "T": {"dimension": 2, "simplices": [1, 0]}}
+    mg = W.Mesh("x", raw=(pts, [], tris, tets, dom))
+    mo = omesh.Mesh("x", raw=(pts, [], tris, tets, dom))
+    assert np.array_equal(mg.tetrahedra, np.array(mo.tetrahedra)) and len(mg.tetrahedra) == 2
+    assert list(mg.domains["A"]["simplices"]) == mo.domains["A"]["simplices"]
+    assert list(mg.domains["T"]["simplices"]) == mo.domains["T"]["simplices"] == [0]
+    assert len(mg.domains["E"]["simplices"]) == 0
+
+
+def test_scalar_algebra():
+    rng = np.random.default_rng(0)
+    for _ in range(20):
+        z = complex(rng.standard_normal(), rng.standard_normal()) * 100
+        tau = complex(rng.random() * 1e-3)
+        for k in range(4):
+            assert nlevp.pow0(z, k) == onlevp.pow0(z, k)
+            assert nlevp.pow1(z, k) == onlevp.pow1(z, k)
+            assert nlevp.pow2(z, k) == onlevp.pow2(z, k)
+        for m in range(4):
+            for n in range(4):
+                a, b = nlevp.exp_delay(z, tau, m, n), onlevp.exp_delay(z, tau, m, n)
+                assert abs(a - b) <= 1e-15 * abs(b)
+    # derivative consistency of exp_delay by finite differences
+    z, tau, h = 500.0 + 3j, 1e-3 + 0j, 1e-4
+    fd = (nlevp.exp_delay(z + h, tau, 0, 0) - nlevp.exp_delay(z - h, tau, 0, 0)) / (2 * h)
+    assert abs(fd - nlevp.exp_delay(z, tau, 1, 0)) < 1e-8
+
+
+def test_update_formulas_and_pade():
+    rng = np.random.default_rng(1)
+    for o in range(1, 6):
+        f = list(rng.standard_normal(o + 1) + 1j * rng.standard_normal(o + 1))
+        assert abs(nlevp.householder_update(f) - onlevp.householder_update(f)) < 1e-14
+    w = list(rng.standard_normal(6) + 1j * rng.standard_normal(6))
+    for Lo, M in ((1, 0), (1, 2), (2, 3)):
+        a, b = nlevp.pade(w, Lo, M)
+        ao, bo = onlevp.pade(w, Lo, M)
+        assert np.allclose(a, ao) and np.allclose(b, bo)
+    assert np.allclose(np.sort_complex(nlevp.poly_roots([2.0, -3.0, 1.0])), [1.0, 2.0])
+    G = [0, 2, 2 + 2j, 2j]
+    assert nlevp.wn(1 + 1j, G) == onlevp.wn(1 + 1j, G) == 1 and nlevp.wn(3 + 1j, G) == 0
+    z1, w1 = nlevp.contour_nodes(G, 8)
+    z2, w2 = onlevp.contour_nodes(G, 8)
+    assert np.array_equal(z1, z2) and np.array_equal(w1, w2)
+    assert abs(w1.sum()) < 1e-14  # closed contour
+
+
+class _FakeMat:
+    dim = 5
+    parts = [(0, 1.0)]
+    ctx = None
+
+
+def _families():
+    fams = []
+    for mod in (nlevp, onlevp):
+        L = mod.LinearOperatorFamily(["ω", "λ"], [0.0, float("inf")])
+        coeff = _FakeMat() if mod is nlevp else __import__("scipy.sparse").sparse.identity(5, dtype=complex, format="csc")
+        for func, params, op in (((mod.pow2,), (("ω",),), "M"), ((), (), "K"), ((mod.pow1, mod.pow1), (("ω",), ("Y",)), "C"),
+                                 ((mod.pow1, mod.exp_delay), (("n",), ("ω", "τ")), "Q"), ((mod.pow1,), (("λ",),), "__aux__")):
+            L.terms.append(mod.Term(coeff, func, params, "", op))
+        L.params.update({"Y": 1e15 + 0j, "n": 0.5 + 0j, "τ": 1e-3 + 0j})
+        fams.append(L)
+    return fams
+
+
+def test_family_scalar_rules_match_oracle():
+    """Which terms enter L(z,...) and with which scalar (LinOpFam.jl:501-526), all three modes."""
+    Lg, Lo = _families()
+    for L in (Lg, Lo):
+        L.params["ω"] = 300.0 + 5j
+        L.params["λ"] = 0.25 + 0j
+    for mode, active, derivs_list in (("all", ["ω"], [[0], [1], [2], [3]]),
+                                      ("householder", ["λ", "ω"], [[0, 0], [1, 0], [0, 1], [0, 2], [1, 1], [2, 0]]),
+                                      ("compact", ["ω", "τ"], [[0, 0], [1, 1], [0, 3]])):
+        for L in (Lg, Lo):
+            L.mode, L.active = mode, list(active)
+        for derivs in derivs_list:
+            sg, so = Lg.scalars(derivs), Lo.scalars(derivs)
+            assert [x is None for x in sg] == [x is None for x in so], (mode, derivs)
+            for a, b in zip(sg, so):
+                if a is not None:
+                    assert abs(a - b) <= 1e-15 * max(abs(b), 1e-300), (mode, derivs)
+
+
+def test_partitions_match_oracle():
+    for n in range(1, 8):
+        assert [list(p) for p in nlevp._partitions(n)] == [list(p) for p in onlevp.partitions(n)]
+        assert len(list(nlevp._partitions(n))) == [1, 2, 3, 5, 7, 11, 15][n - 1]
+
+
+def test_symbolic_lu_phase_on_host(meshes):
+    """wae_lu_symbolic_stats runs without a GPU: valid permutation, bounded fill on the P2 Rijke pattern."""
+    import scipy.sparse as sp
+    from wae_b200 import _lib
+    mg, _ = meshes
+    _, tets, dim = W.aggregate_elements(mg, "quad")
+    n = tets.shape[1]
+    I = np.repeat(tets, n, axis=1).ravel()
+    J = np.tile(tets, (1, n)).ravel()
+    A = sp.csc_matrix((np.ones(len(I)), (I, J)), shape=(dim, dim))
+    A.sum_duplicates()
+    A.sort_indices()
+    lib = _lib.lib()
+    lib.wae_lu_symbolic_stats.restype = C.c_int32
+    lib.wae_lu_symbolic_stats.argtypes = [C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_double), C.c_int32,
+                                          C.POINTER(C.c_double)]
+    cp, rv = A.indptr.astype(np.int64), A.indices.astype(np.int64)
+    out = np.zeros(8)
+    for coords in (None, np.ascontiguousarray(np.random.default_rng(0).random((dim, 3)))):
+        rc = lib.wae_lu_symbolic_stats(dim, cp.ctypes.data_as(C.POINTER(C.c_int64)), rv.ctypes.data_as(C.POINTER(C.c_int64)),
+                                       None if coords is None else coords.ctypes.data_as(C.POINTER(C.c_double)), 64,
+                                       out.ctypes.data_as(C.POINTER(C.c_double)))
+        assert rc == 0
+        assert out[1] >= A.nnz and out[0] >= 1
+    # with the BFS key (no coordinates) the fill of this 6172-DOF tube must stay moderate
+    rc = lib.wae_lu_symbolic_stats(dim, cp.ctypes.data_as(C.POINTER(C.c_int64)), rv.ctypes.data_as(C.POINTER(C.c_int64)), None, 64,
+                                   out.ctypes.data_as(C.POINTER(C.c_double)))
+    assert rc == 0 and out[1] < 30 * A.nnz
+
+
+def test_kuhn_box_is_conforming():
+    m = W.kuhn_box((3, 2, 4), (0, 0, 0), (3, 2, 4), jitter=0.1, seed=3, flame_layer=(1, 2))
+    X = m.points[:, m.tetrahedra]
+    vol = np.abs(np.linalg.det(np.moveaxis(X[:, :, :3] - X[:, :, 3:4], 1, 0))).sum() / 6
+    assert abs(vol - 24.0) < 1e-9  # jitter moves interior points only: the volume is preserved
+    assert len(m.tetrahedra) == 3 * 2 * 4 * 6
+    assert len(m.triangles) == 2 * 2 * (3 * 2 + 3 * 4 + 2 * 4)
+    assert len(m.domains["Flame"]["simplices"]) == 3 * 2 * 6
+    assert abs(m.compute_size("Outlet") - 6.0) < 1e-12

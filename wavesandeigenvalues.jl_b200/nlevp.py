@@ -702,6 +702,21 @@ def contour_nodes(G, N):
     return np.array(zs), np.array(ws)
 
 
+def shard_nodes(n_nodes, rank, world):
+    """Quadrature nodes of rank `rank`: round-robin, so that every rank gets nodes from every polygon edge."""
+    return np.arange(rank, n_nodes, world)
+
+
+def allreduce_moments(A, group=None):
+    """Sum the per-rank partial moment tensors (torch complex tensor, in place) over the process group.
+    The only collective of the path: NCCL over NVLink on GPUs (gloo in the CPU tests)."""
+    import torch
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(torch.view_as_real(A), group=group)
+    return A
+
+
 def compute_moment_matrices(L, G, l=5, K=1, N=16, group=None, stats=None):
     """Moments A_p = sum_j w_j z_j^p L(z_j)^{-1} V, p < 2K, V = first l identity columns (beyn.jl:62-74).
 
@@ -709,15 +724,16 @@ def compute_moment_matrices(L, G, l=5, K=1, N=16, group=None, stats=None):
     each GPU factorises its own nodes, the moments are summed with one all-reduce.  Returns a (d, l, 2K)
     complex numpy array (on every rank)."""
     import torch
+    import torch.distributed as dist
     dev = L.device()
     ctx = dev.ctx
     d = dev.dim
     L(0)
     zs, ws = contour_nodes(G, N)
     rank, world = 0, 1
-    if group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-        rank, world = torch.distributed.get_rank(group), torch.distributed.get_world_size(group)
-    mine = np.arange(rank, len(zs), world)
+    if dist.is_available() and dist.is_initialized():
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+    mine = shard_nodes(len(zs), rank, world)
     coeffs = np.zeros((len(mine), dev.n_flat), dtype=np.complex128)
     for r, j in enumerate(mine):
         L.params[L.eigval] = complex(zs[j])
@@ -728,8 +744,9 @@ def compute_moment_matrices(L, G, l=5, K=1, N=16, group=None, stats=None):
         ctx.beyn_moments(dev.fid, dev.lu(), zs[mine], ws[mine], coeffs, l, 2 * K, A.data_ptr())
     if stats is not None:
         stats["factorizations"] = stats.get("factorizations", 0) + len(mine)
-    if world > 1:
-        torch.distributed.all_reduce(torch.view_as_real(A), group=group)
+        stats["factor_ms"] = stats.get("factor_ms", 0.0) + ctx.last_ms("beyn_factor_total")
+        stats["solve_ms"] = stats.get("solve_ms", 0.0) + ctx.last_ms("beyn_solve_total")
+    allreduce_moments(A, group)
     return A.permute(2, 1, 0).cpu().numpy()
 
 
