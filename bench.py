@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 hot path (contract: see the task statement / DESIGN.md section 6).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): synthetic Rijke tube 0.05 x 0.05 x 0.5 m, Kuhn grid 20 x 20 x 300 cubes
+-> 720 000 tetrahedra, 1 010 281 P2 DOFs, interior + outlet admittance (Y=1e15) + n-tau flame (n=1, tau=1 ms).
+One STEP = numeric re-assembly of all operators (M, K, C, Q, aux) on the GPU followed by householder (Newton,
+order 1) from 340*2*pi to |d omega| <= 1e-9 |omega|  ->  one eigenpair.  `value` = eigenpairs/s with mesh,
+patterns and the symbolic LU resident on the device; `e2e` additionally uploads the vertex coordinates and the
+speed-of-sound field from pinned host memory every step (the eigenvector always returns to the host).
+With N > 1 every rank solves its own replica (tau differs per rank): householder does not shard
+("replicas only", weak scaling).  The path that does shard -- Beyn's quadrature nodes -- is timed on every N
+as well and reported under "beyn" (strong scaling: 128 nodes in total, one NCCL all-reduce of the moments).
+
+Extra objects on the JSON line: roofline (numeric LU = DMMA ZGEMM, FP64 tensor pipe), roofline_assembly (HBM),
+assembly (Mtets/s on a larger box), beyn, cpu_baseline (the scipy/SuperLU oracle on a bounded sample), clocks.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+GAMMA, RHO = 1.4, 1.225
+Q02U0 = 101325.0 * (1200.0 / 300.0 - 1) * math.pi * 0.025**2 * GAMMA / (GAMMA - 1)
+Z0 = 340 * 2 * math.pi
+
+
+def tube_case(W, ncube, order="quad"):
+    nx, ny, nz = ncube
+    hz = 0.5 / nz
+    mesh = W.kuhn_box(ncube, (0, 0, -0.25), (0.05, 0.05, 0.25), jitter=0.1, seed=12345, flame_layer=(nz // 2, nz // 2 + 1),
+                      name=f"rijke_kuhn_{nx}x{ny}x{nz}")
+    c = mesh.generate_field(lambda x, y, z: 347.2 if z < 0 else 694.4) if len(mesh.tetrahedra) < 20000 else \
+        np.where(mesh.points[2, mesh.tetrahedra].sum(axis=1) / 4 < 0, 347.2, 694.4)
+    dscrp = {"Interior": ("interior", ()), "Outlet": ("admittance", ("Y", 1e15)),
+             "Flame": ("flame", (GAMMA, RHO, Q02U0, [0.025, 0.025, -0.6 * hz], [0.0, 0.0, 1.0], "n", "τ", 1.0, 0.001))}
+    return mesh, c, dscrp
+
+
+def oracle_step(ncube):
+    """One eigenpair with the CPU oracle (numpy/scipy restatement of the reference path) on a reduced tube."""
+    import wae_b200 as W
+    from oracle.helmholtz import discretize as odisc
+    from oracle.mesh import Mesh as OMesh
+    from oracle.nlevp import householder as ohouse
+    m, _, dscrp = tube_case(W, ncube)
+    raw = (m.points, [], [list(map(int, t)) for t in m.triangles], [list(map(int, t)) for t in m.tetrahedra],
+           {k: {"dimension": v["dimension"], "simplices": list(map(int, v["simplices"]))} for k, v in m.domains.items()})
+    t0 = time.perf_counter()
+    mo = OMesh("m", raw=raw)
+    c = mo.generate_field(lambda x, y, z: 347.2 if z < 0 else 694.4)
+    L = odisc(mo, dscrp, c, order="quad")
+    sol, n, flag = ohouse(L, Z0, maxiter=15, tol=1e-9 * Z0)
+    return time.perf_counter() - t0, L.size(), len(m.tetrahedra), n
+
+
+class Clocks:
+    """nvidia-smi sampler running during the timed region."""
+
+    def __init__(self, dev):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(dev), f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        os.unlink(self.f.name)
+        return out
+
+
+def fp64_peak(torch, dev):
+    """Measured FP64 GEMM peak of this GPU (cuBLAS via torch): DGEMM 8192^3 and ZGEMM 4096^3, best of 5, TFLOP/s."""
+    best = {}
+    for name, n, dt, fl in (("dgemm", 8192, torch.float64, 2.0), ("zgemm", 4096, torch.complex128, 8.0)):
+        a = torch.randn(n, n, dtype=dt, device=dev)
+        b = torch.randn(n, n, dtype=dt, device=dev)
+        torch.matmul(a, b)
+        torch.cuda.synchronize()
+        t = []
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            t.append(e0.elapsed_time(e1))
+        best[name] = fl * n**3 / (min(t) * 1e-3) / 1e12
+        del a, b
+    torch.cuda.empty_cache()
+    return best
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--tube", default="20,20,300", help="cubes of the Rijke tube grid (config 2: 20,20,300)")
+    ap.add_argument("--beyn-box", default="32,32,64", help="cubes of the P1 tube used for the sharded Beyn leg")
+    ap.add_argument("--beyn-edge-nodes", type=int, default=32, help="Gauss-Legendre nodes per polygon edge (4 edges -> 128 nodes)")
+    ap.add_argument("--assembly-cubes", type=int, default=64, help="n for the n^3-cube P2 assembly-only leg (0 = skip)")
+    ap.add_argument("--cpu-sample", default="4,4,60")
+    ap.add_argument("--ref-sample", default="3,3,45")
+    ap.add_argument("--skip-extras", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    tube = tuple(int(x) for x in args.tube.split(","))
+    workload = (f"Rijke tube {tube[0]}x{tube[1]}x{tube[2]} Kuhn cubes, P2, interior+outlet admittance+n-tau flame; "
+                "step = GPU re-assembly + householder(order 1) to |dw|<=1e-9|w|")
+
+    # ------------------------------------------------------------------ reference arm: the CPU oracle
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        sample = tuple(int(x) for x in args.ref_sample.split(","))
+        for _ in range(args.warmup):
+            oracle_step(sample)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            _, dim, ntet, nit = oracle_step(sample)
+        dt = time.perf_counter() - t0
+        val = args.steps / dt
+        smp = (f"reference cannot run here (pure Julia, no julia binary): CPU restatement (numpy + scipy SuperLU/ARPACK, not "
+               f"Julia/UMFPACK) on a bounded sample of the workload: tube {sample[0]}x{sample[1]}x{sample[2]} cubes, {ntet} tets, "
+               f"{dim} P2 DOFs, assembly + householder to convergence per step")
+        print(json.dumps({"impl": "reference", "metric": "NLEVP eigenpairs/s (householder)", "value": val, "unit": "eigenpairs/s",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+                          "config": {"workload": workload, "sample": smp},
+                          "cpu_baseline": {"value": val, "unit": "eigenpairs/s", "cores": 1, "kind": "port", "sample": smp},
+                          "e2e": {"value": val, "unit": "eigenpairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    import torch
+    import torch.distributed as dist
+
+    import wae_b200 as W
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    ctx = W.get_context(local)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    t_setup = time.perf_counter()
+    mesh, c, dscrp = tube_case(W, tube)
+    tau = 0.001 * (1.0 + 0.05 * rank)
+    L = W.discretize(mesh, dscrp, c, order="quad")
+    disc = L.discretization
+    dv = L.device()
+    lu = dv.lu()
+    t_setup = time.perf_counter() - t_setup
+    npts, ntet = mesh.points.shape[1], len(mesh.tetrahedra)
+    pts_pinned = torch.from_numpy(np.ascontiguousarray(mesh.points.T)).pin_memory()
+    c_pinned = torch.from_numpy(np.ascontiguousarray(c)).pin_memory()
+    tol = 1e-9 * Z0
+
+    def step(e2e, stats):
+        if e2e:
+            ctx.mesh_update_points(pts_pinned.numpy())
+        ms = disc.reassemble(c_pinned.numpy())
+        stats["assemble_ms"] = stats.get("assemble_ms", 0.0) + ms
+        L.params["n"], L.params["τ"] = 1.0 + 0j, complex(tau)
+        sol, n, flag = W.householder(L, Z0, maxiter=15, tol=tol, output=False, stats=stats)
+        stats["iterations"] = stats.get("iterations", 0) + n
+        if flag < 0:
+            raise RuntimeError(f"householder failed with flag {flag}")
+        return sol
+
+    for _ in range(args.warmup):
+        sol = step(False, {})
+    omega = sol.params["ω"]
+
+    def timed(e2e):
+        stats = {}
+        barrier()
+        l0 = ctx.launch_count()
+        clk = Clocks(local) if rank == 0 else None
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step(e2e, stats)
+        e1.record()
+        barrier()
+        ms = max_over_ranks(e0.elapsed_time(e1))
+        return ms, stats, ctx.launch_count() - l0, (clk.stop() if clk else None)
+
+    ms, stats, launches, clocks = timed(False)
+    ms_e2e, stats_e2e, _, _ = timed(True)
+    value = world * args.steps / (ms * 1e-3)
+    value_e2e = world * args.steps / (ms_e2e * 1e-3)
+    nfac = stats["factorizations"]
+    fac_tflops = dv.lu_flops * nfac / (stats["factor_ms"] * 1e-3) / 1e12
+    iters = stats["iterations"]
+    h2d = 3 * npts * 8 + ntet * 8 + (iters / args.steps) * 2 * 16 * dv.dim  # points + c + Krylov start vectors per iteration
+    d2h = (iters / args.steps) * 2 * 16 * dv.dim                              # eigenvector pairs back to the host
+
+    out = {"metric": "NLEVP eigenpairs/s (householder, config 2)", "value": value, "unit": "eigenpairs/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "c128", "data": "synthetic",
+           "config": {"workload": workload, "tets": ntet, "dofs": dv.dim, "nnz": dv.nnz, "factor_nnz": dv.lu_nnz,
+                      "factor_flops": dv.lu_flops, "parallelism": "replicas only (householder does not shard); Beyn nodes sharded under 'beyn'",
+                      "l2": "working set (LU factors, %.1f GB) is far larger than the 126 MB L2; no flush needed" % (dv.lu_nnz * 16 / 1e9),
+                      "setup_s_not_timed": t_setup, "omega": [omega.real, omega.imag]},
+           "e2e": {"value": value_e2e, "unit": "eigenpairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+           "gpu_launches": int(launches), "clocks": clocks,
+           "phases_ms_per_step": {"assemble": stats["assemble_ms"] / args.steps, "numeric_lu": stats["factor_ms"] / args.steps,
+                                  "eigs_wall": 1e3 * stats["eigs_wall_s"] / args.steps, "perturb_wall": 1e3 * stats["perturb_wall_s"] / args.steps,
+                                  "iterations": iters / args.steps, "factorizations": nfac / args.steps, "solves": stats["solves"] / args.steps}}
+
+    # ------------------------------------------------------------------ roofline of the dominant kernel
+    peaks = fp64_peak(torch, dev)
+    peak = max(peaks.values())
+    out["roofline"] = {"bound": "tensor", "achieved": fac_tflops, "peak": peak, "unit": "TFLOP/s", "frac": fac_tflops / peak,
+                       "traffic": None,
+                       "kernel": "lu_gemm_kernel (complex C -= A*B^T on DMMA m8n8k4 f64) inside the numeric LU",
+                       "note": ("achieved = exact factorisation flops of the symbolic phase (8 real flops per complex multiply-add) / "
+                                "CUDA-event time of the numeric LU (all its kernels); peak = cuBLAS FP64 GEMM measured in this run "
+                                f"(dgemm 8192^3 {peaks['dgemm']:.1f}, zgemm 4096^3 {peaks['zgemm']:.1f} TFLOP/s) -- MEASURED_PEAKS.json has no FP64 figure")}
+    # assembly kernel vs HBM
+    hbm = 6548.5
+    try:
+        hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        hbm_src = "MEASURED_PEAKS.json"
+    except Exception:
+        hbm_src = "fallback"
+    if not args.skip_extras and rank == 0:
+        out["assembly"] = assembly_leg(W, ctx, args.assembly_cubes, hbm, hbm_src) if args.assembly_cubes else None
+        # re-establish the tube mesh on the context for anything that follows
+    # ------------------------------------------------------------------ Beyn leg (sharded over all ranks)
+    if not args.skip_extras:
+        out["beyn"] = beyn_leg(W, torch, dist, ctx, args, rank, world, dev, barrier, max_over_ranks)
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1 only)
+    if rank == 0 and world == 1 and not args.skip_extras:
+        sample = tuple(int(x) for x in args.cpu_sample.split(","))
+        dt, dim, nt, nit = oracle_step(sample)
+        out["cpu_baseline"] = {"value": 1.0 / dt, "unit": "eigenpairs/s", "cores": 1, "kind": "port",
+                               "sample": (f"numpy/scipy (SuperLU+ARPACK) restatement of the reference path, NOT Julia/UMFPACK; one eigenpair on "
+                                          f"the same tube at {sample[0]}x{sample[1]}x{sample[2]} cubes = {nt} tets, {dim} P2 DOFs "
+                                          f"({dv.dim / dim:.0f}x fewer DOFs than the GPU workload), {nit} Newton iterations, {dt:.1f} s; "
+                                          f"host has {os.cpu_count()} cores, SuperLU is serial")}
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def assembly_leg(W, ctx0, n, hbm, hbm_src):
+    """M+K assembly of an n^3-cube P2 box (config 5 geometry at bench size), kernel time by CUDA events."""
+    from wae_b200 import _lib
+    ctx = _lib.Context(ctx0.device)
+    mesh = W.kuhn_box((n, n, n), (0, 0, 0), (1, 1, 1), jitter=0.1, seed=7)
+    tris, tets, dim = W.aggregate_elements(mesh, "quad")
+    ctx.mesh_set(2, mesh.points.T, tets, tris, dim)
+    pid, nnz = ctx.pattern_build(3, None)
+    c = np.random.default_rng(7).uniform(300, 700, len(tets))
+    im, ik = ctx.assemble_mk(pid, c)
+    ms = []
+    for _ in range(5):
+        ctx.assemble_mk(pid, c, reuse=(im, ik))
+        ms.append(ctx.last_ms("assemble"))
+    med = float(np.median(ms))
+    ntet, npts = len(tets), mesh.points.shape[1]
+    alg = ntet * (4 * 10 + 8) + 24 * npts + 2 * nnz * 8
+    res = {"value": ntet / med / 1e3, "unit": "Mtets/s", "tets": ntet, "dofs": dim, "nnz": int(nnz), "kernel_ms": med,
+           "roofline": {"bound": "hbm", "achieved": alg / med / 1e6, "peak": hbm, "unit": "GB/s", "frac": alg / med / 1e6 / hbm,
+                        "traffic": None, "peak_source": hbm_src, "algorithmic_bytes_per_tet": alg / ntet,
+                        "kernel": "assemble_tet_gather<10> (P2 M+K, owner-computes)"}}
+    ctx.close()
+    return res
+
+
+def beyn_leg(W, torch, dist, ctx0, args, rank, world, dev, barrier, max_over_ranks):
+    """Beyn contour integration, 4 x beyn_edge_nodes quadrature nodes sharded round-robin over the ranks,
+    one NCCL all-reduce of the moments (strong scaling: the total work is fixed)."""
+    from wae_b200 import _lib, nlevp
+    nb = tuple(int(x) for x in args.beyn_box.split(","))
+    ctx = _lib.Context(ctx0.device)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    mesh = W.kuhn_box(nb, (0, 0, -0.5), (0.1, 0.1, 0.5), jitter=0.1, seed=2024, name="beyn_tube")
+    c = np.full(len(mesh.tetrahedra), 347.2)
+    dscrp = {"Interior": ("interior", ()), "Outlet": ("admittance", ("Y", 1e15))}
+    L = W.discretize(mesh, dscrp, c, order="lin", ctx=ctx)
+    dv = L.device()
+    dv.lu()
+    G = [z * 2 * math.pi for z in (50 + 40j, 50 - 40j, 800 - 40j, 800 + 40j)]
+    l, N = 8, args.beyn_edge_nodes
+    # warm-up: one node per rank
+    nlevp.compute_moment_matrices(L, G[:2], l=l, K=1, N=1)
+    stats = {}
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    A = nlevp.compute_moment_matrices(L, G, l=l, K=1, N=N, stats=stats)
+    Om, P = nlevp.moments2eigs(A, G, rtol=1e-8, pos_test=True)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    res = {"value": len(Om) / (ms * 1e-3), "unit": "eigenpairs/s", "scaling": "strong", "n_gpus": world, "nodes": 4 * N, "l": l,
+           "dofs": dv.dim, "tets": len(mesh.tetrahedra), "eigenvalues_found": len(Om), "ms": ms,
+           "node_solves_per_s": 4 * N / (ms * 1e-3), "factor_ms_rank0": stats.get("factor_ms"), "solve_ms_rank0": stats.get("solve_ms"),
+           "freq_hz": sorted(float(x) for x in (Om.real / 2 / math.pi))[:8],
+           "collective": "one all_reduce (NCCL) of the 2K x l x d complex moment tensor"}
+    ctx.close()
+    return res
+
+
+if __name__ == "__main__":
+    main()

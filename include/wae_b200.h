@@ -67,6 +67,10 @@ int32_t wae_mesh_set(wae_ctx* h, int32_t order, int64_t n_pts, const double* xyz
                      int64_t n_tet, const uint32_t* tets, int64_t n_tri, const uint32_t* tris,
                      int64_t dim);
 
+/* New vertex coordinates on the same topology (patterns, gather programs and the symbolic LU stay valid):
+ * what shape_sensitivity.jl:111,120 needs when it re-runs discretize on a perturbed mesh.                */
+int32_t wae_mesh_update_points(wae_ctx* h, int64_t n_pts, const double* xyz);
+
 /* ---- sparsity pattern of one operator (symbolic, once per domain) -----------------
  * Replaces the I/J triplet growth + SparseArrays.sparse pattern merge (Helmholtz.jl:406-417,515;
  * FEM.jl:22-32 create_indices).  elem_kind: 3 = tetrahedra, 2 = triangles.  elem_ids index the
@@ -83,7 +87,9 @@ int32_t wae_pattern_get(wae_ctx* h, int32_t pattern_id, int64_t* colptr /* dim+1
  * c: speed of sound, c_per_elem values per element of the pattern's element list, in list order
  *    (1 = constant per element; 4 / 3 = linear, vertex values: FEM.jl:764-890, 2283-2424, 469-525);
  *    ignored (may be NULL) for WAE_OP_MASS.
- * scale: real factor applied to all values (the __aux__ term is -M: Helmholtz.jl:572).      */
+ * scale: real factor applied to all values (the __aux__ term is -M: Helmholtz.jl:572).
+ * mat_id is in/out: a valid id (>= 0) on entry means "overwrite this matrix in place" (re-assembly with new
+ * c or new coordinates, no new allocation); pass -1 to create a matrix.                       */
 enum { WAE_OP_MASS = 1, WAE_OP_STIFF = 2, WAE_OP_BOUNDARY = 3 };
 int32_t wae_assemble(wae_ctx* h, int32_t pattern_id, int32_t kind, const double* c,
                      int32_t c_per_elem, double scale, int32_t* mat_id);

@@ -55,6 +55,7 @@ SIGNATURES = {
     "wae_launch_count": (_i64, [_vp]),
     "wae_last_ms": (_dbl, [_vp, C.c_char_p]),
     "wae_mesh_set": (_i32, [_vp, _i32, _i64, _pd, _i64, _pu32, _i64, _pu32, _i64]),
+    "wae_mesh_update_points": (_i32, [_vp, _i64, _pd]),
     "wae_pattern_build": (_i32, [_vp, _i32, _i64, _pi64, _pi32, _pi64]),
     "wae_pattern_get": (_i32, [_vp, _i32, _pi64, _pi64]),
     "wae_assemble": (_i32, [_vp, _i32, _i32, _pd, _i32, _dbl, _pi32]),
@@ -158,8 +159,12 @@ class Context:
         self._chk(self._l.wae_pattern_get(self.h, pid, _p(colptr, _pi64), _p(rowval, _pi64)))
         return colptr, rowval
 
-    def assemble(self, pid, kind, c=None, scale=1.0):
-        mid = _i32()
+    def mesh_update_points(self, xyz):
+        xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+        self._chk(self._l.wae_mesh_update_points(self.h, xyz.shape[0], _p(xyz, _pd)))
+
+    def assemble(self, pid, kind, c=None, scale=1.0, reuse=-1):
+        mid = _i32(reuse)
         cpe = 1
         if c is not None:
             c = np.ascontiguousarray(c, dtype=np.float64)
@@ -167,18 +172,18 @@ class Context:
         self._chk(self._l.wae_assemble(self.h, pid, kind, _p(c, _pd), cpe, scale, C.byref(mid)))
         return mid.value
 
-    def assemble_mk(self, pid, c):
+    def assemble_mk(self, pid, c, reuse=(-1, -1)):
         c = np.ascontiguousarray(c, dtype=np.float64)
         cpe = 1 if c.ndim == 1 else c.shape[1]
-        im, ik = _i32(), _i32()
+        im, ik = _i32(reuse[0]), _i32(reuse[1])
         self._chk(self._l.wae_assemble_mk(self.h, pid, _p(c, _pd), cpe, C.byref(im), C.byref(ik)))
         return im.value, ik.value
 
-    def assemble_flame(self, flame_tets, ref_tet, x_ref, n_ref, nlocal):
+    def assemble_flame(self, flame_tets, ref_tet, x_ref, n_ref, nlocal, reuse=-1):
         ft = np.ascontiguousarray(flame_tets, dtype=np.int64)
         xr = np.ascontiguousarray(x_ref, dtype=np.float64)
         nr = np.ascontiguousarray(n_ref, dtype=np.float64)
-        pid, mid, nnz = _i32(), _i32(), _i64()
+        pid, mid, nnz = _i32(), _i32(reuse), _i64()
         self._chk(self._l.wae_assemble_flame(self.h, len(ft), _p(ft, _pi64), int(ref_tet), _p(xr, _pd), _p(nr, _pd), float(nlocal),
                                              C.byref(pid), C.byref(mid), C.byref(nnz)))
         return pid.value, mid.value, nnz.value

@@ -117,6 +117,16 @@ int32_t wae_mesh_set(wae_ctx* h, int32_t order, int64_t n_pts, const double* xyz
   WAE_API_END
 }
 
+int32_t wae_mesh_update_points(wae_ctx* h, int64_t n_pts, const double* xyz) {
+  WAE_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(h->device));
+  if (!h->order || n_pts != h->n_pts || !xyz) WAE_THROW(WAE_E_INVALID, "wae_mesh_update_points: point count differs from wae_mesh_set");
+  h->xyz.assign(xyz, xyz + 3 * n_pts);
+  CUDA_CHECK(cudaMemcpyAsync(h->d_xyz.p, xyz, 3 * n_pts * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  WAE_API_END
+}
+
 // ---- patterns ---------------------------------------------------------------------------
 static int new_pattern(wae_ctx* h) {
   h->patterns.emplace_back(new Pattern());
@@ -182,6 +192,9 @@ static void ensure_slotmap(wae_ctx* h, Pattern& P) {
   P.slotmap_built = true;
 }
 
+// *mat_id >= 0 on entry: overwrite that matrix in place (same pattern and type), else create a new one
+static int reuse_or_new_matrix(wae_ctx* h, const int32_t* mat_id, int pattern, bool is_complex, int64_t nnz);
+
 static int new_matrix(wae_ctx* h, int pattern, bool is_complex, int64_t nnz) {
   h->mats.emplace_back(new Matrix());
   Matrix& M = *h->mats.back();
@@ -190,6 +203,16 @@ static int new_matrix(wae_ctx* h, int pattern, bool is_complex, int64_t nnz) {
   M.d_val.alloc((size_t)nnz * (is_complex ? 2 : 1));
   CUDA_CHECK(cudaMemsetAsync(M.d_val.p, 0, M.d_val.n * sizeof(double), h->stream));
   return (int)h->mats.size() - 1;
+}
+
+static int reuse_or_new_matrix(wae_ctx* h, const int32_t* mat_id, int pattern, bool is_complex, int64_t nnz) {
+  if (mat_id && *mat_id >= 0) {
+    Matrix& M = h->mat(*mat_id);
+    if (M.pattern != pattern || M.is_complex != is_complex) WAE_THROW(WAE_E_INVALID, "matrix %d cannot be reused: different pattern or type", *mat_id);
+    CUDA_CHECK(cudaMemsetAsync(M.d_val.p, 0, M.d_val.n * sizeof(double), h->stream));
+    return *mat_id;
+  }
+  return new_matrix(h, pattern, is_complex, nnz);
 }
 
 static void upload_c(wae_ctx* h, Pattern& P, const double* c, int c_per_elem, DevBuf<double>& d_c) {
@@ -211,7 +234,7 @@ int32_t wae_assemble(wae_ctx* h, int32_t pattern_id, int32_t kind, const double*
   if (use_gather) wae_ensure_gather(h, P); else ensure_slotmap(h, P);
   DevBuf<double> d_c;
   if (kind != WAE_OP_MASS) upload_c(h, P, c, c_per_elem, d_c);
-  int id = new_matrix(h, pattern_id, kind == WAE_OP_BOUNDARY, P.nnz);
+  int id = reuse_or_new_matrix(h, mat_id, pattern_id, kind == WAE_OP_BOUNDARY, P.nnz);
   Matrix& M = *h->mats[id];
   PhaseTimer t(h, "assemble");
   if (kind == WAE_OP_MASS && use_gather)
@@ -236,8 +259,8 @@ int32_t wae_assemble_mk(wae_ctx* h, int32_t pattern_id, const double* c, int32_t
   if (P.elem_kind != 3) WAE_THROW(WAE_E_INVALID, "wae_assemble_mk needs a tetrahedral pattern");
   DevBuf<double> d_c;
   upload_c(h, P, c, c_per_elem, d_c);
-  int im = new_matrix(h, pattern_id, false, P.nnz);
-  int ik = new_matrix(h, pattern_id, false, P.nnz);
+  int im = reuse_or_new_matrix(h, mass_id, pattern_id, false, P.nnz);
+  int ik = reuse_or_new_matrix(h, stiff_id, pattern_id, false, P.nnz);
   if (c_per_elem == 1 && !getenv("WAE_FORCE_ATOMIC")) {
     wae_ensure_gather(h, P);
     PhaseTimer t(h, "assemble");
@@ -281,17 +304,21 @@ int32_t wae_assemble_flame(wae_ctx* h, int64_t n_flame, const int64_t* flame_tet
   std::vector<std::pair<int32_t, int32_t>> cols;
   for (int k = 0; k < nloc; k++) cols.emplace_back((int32_t)h->tets[ref_tet * nloc + k], k);
   std::sort(cols.begin(), cols.end());
-  int pid = new_pattern(h);
+  const bool reuse = mat_id && *mat_id >= 0;
+  int pid = reuse ? h->mat(*mat_id).pattern : new_pattern(h);
   Pattern& P = *h->patterns[pid];
+  int64_t nr = (int64_t)urows.size();
+  if (reuse && P.nnz != nr * nloc) WAE_THROW(WAE_E_INVALID, "flame matrix %d cannot be reused: different pattern", *mat_id);
+  if (!reuse) {
   P.dim = h->dim;
   P.colptr.assign(h->dim + 1, 0);
-  int64_t nr = (int64_t)urows.size();
   for (auto& cpair : cols) P.colptr[cpair.first + 1] = nr;
   for (int64_t j = 0; j < h->dim; j++) P.colptr[j + 1] += P.colptr[j];
   P.nnz = nr * nloc;
   P.rowval.resize(P.nnz);
   for (int c = 0; c < nloc; c++) std::copy(urows.begin(), urows.end(), P.rowval.begin() + (size_t)c * nr);
   upload_pattern(h, P);
+  }
   std::vector<int32_t> colsrc(nloc);
   for (int c = 0; c < nloc; c++) colsrc[c] = cols[c].second;
   DevBuf<int32_t> d_ft, d_rowpos, d_colsrc;
@@ -302,7 +329,7 @@ int32_t wae_assemble_flame(wae_ctx* h, int64_t n_flame, const int64_t* flame_tet
   d_S.alloc(nr + 1);
   d_G.alloc(nloc);
   CUDA_CHECK(cudaMemsetAsync(d_S.p, 0, (nr + 1) * sizeof(double), h->stream));
-  int mid = new_matrix(h, pid, false, P.nnz);
+  int mid = reuse_or_new_matrix(h, mat_id, pid, false, P.nnz);
   PhaseTimer t(h, "assemble");
   wae_launch_flame(h, d_ft.p, n_flame, d_rowpos.p, d_S.p, d_S.p + nr, ref_tet, x_ref, n_ref, -nlocal, d_G.p, d_colsrc.p, nr,
                    nloc, h->mats[mid]->d_val.p);

@@ -26,13 +26,55 @@ from .meshutils import aggregate_elements
 from .nlevp import DeviceMatrix, LinearOperatorFamily, Term, exp_delay, generate_z_g_z, get_context, pow1, pow2
 
 
+def _split_c(mesh, C, npts):
+    """Helmholtz.jl:59-74: per-tetrahedron or per-point speed of sound -> (C_tet, C_tri)."""
+    C = np.asarray(C, dtype=float)
+    if len(C) == len(mesh.tetrahedra):
+        if mesh.tri2tet is None:
+            mesh.link_triangles_to_tetrahedra()
+        return C, C[mesh.tri2tet]
+    if len(C) == npts:
+        return C[mesh.tetrahedra[:, :4]], (C[mesh.triangles[:, :3]] if len(mesh.triangles) else np.zeros((0, 3)))
+    raise ValueError("length(C) must be the number of tetrahedra or the number of points")
+
+
 class Discretization:
-    """Book-keeping of one discretize() call (kept on the family as ``L.discretization``)."""
+    """Book-keeping of one discretize() call (kept on the family as ``L.discretization``): the patterns, the
+    device matrices and the recipe that produced them, so that the numeric phase can be repeated in place
+    (new speed of sound and/or new vertex coordinates on the same topology) without any symbolic work."""
 
     def __init__(self):
         self.patterns = {}   # (kind, domain) -> pattern id
         self.timing = {}
+        self.ops = []        # recipe: dicts with "op", pattern/matrix ids and the element subsets
         self.n_tet = self.n_tri = self.dim = 0
+        self.ctx = self.mesh = None
+
+    def reassemble(self, C, points=None):
+        """Re-run every assembly kernel into the existing device matrices.  ``points`` (3 x N) replaces the vertex
+        coordinates first (shape_sensitivity.jl:111,120 re-discretises perturbed meshes this way)."""
+        ctx, mesh = self.ctx, self.mesh
+        if points is not None:
+            mesh.points = np.asarray(points, dtype=float)
+            ctx.mesh_update_points(mesh.points.T)
+        C_tet, C_tri = _split_c(mesh, C, mesh.points.shape[1])
+        ms = 0.0
+        for op in self.ops:
+            k = op["op"]
+            if k == "mk":
+                ctx.assemble_mk(op["pid"], C_tet[op["simplices"]], reuse=op["mats"])
+            elif k == "mass":
+                ctx.assemble(op["pid"], _lib.OP_MASS, None, scale=op["scale"], reuse=op["mat"])
+            elif k == "stiff":
+                ctx.assemble(op["pid"], _lib.OP_STIFF, C_tet[op["simplices"]], reuse=op["mat"])
+            elif k == "boundary":
+                ctx.assemble(op["pid"], _lib.OP_BOUNDARY, C_tri[op["simplices"]], reuse=op["mat"])
+            elif k == "flame":
+                nlocal = (op["gamma"] - 1) / op["rho"] * op["nglobal"] / mesh.compute_size(op["domain"])
+                ctx.assemble_flame(op["simplices"], op["ref_idx"], op["x_ref"], op["n_ref"], nlocal, reuse=op["mat"])
+            ms += ctx.last_ms("assemble")
+        self.timing["reassemble_ms"] = ms
+        return ms
 
 
 def discretize(mesh, dscrp, C, order="lin", b="__none__", mass_weighting=True, source=False, output=False, ctx=None):
@@ -43,23 +85,13 @@ def discretize(mesh, dscrp, C, order="lin", b="__none__", mass_weighting=True, s
     ctx = ctx or get_context()
     triangles, tetrahedra, dim = aggregate_elements(mesh, order)
     npts = mesh.points.shape[1]
-    C = np.asarray(C, dtype=float)
-    # Helmholtz.jl:59-74
-    if len(C) == len(mesh.tetrahedra):
-        C_tet = C
-        if mesh.tri2tet is None:
-            mesh.link_triangles_to_tetrahedra()
-        C_tri = C[mesh.tri2tet]
-    elif len(C) == npts:
-        C_tet = C[mesh.tetrahedra[:, :4]]
-        C_tri = C[mesh.triangles[:, :3]] if len(mesh.triangles) else np.zeros((0, 3))
-    else:
-        raise ValueError("length(C) must be the number of tetrahedra or the number of points")
+    C_tet, C_tri = _split_c(mesh, C, npts)
 
     ctx.mesh_set(1 if order == "lin" else 2, mesh.points.T, tetrahedra, triangles, dim)
     L = LinearOperatorFamily(["ω", "λ"], [0.0, float("inf")])
     disc = Discretization()
     disc.n_tet, disc.n_tri, disc.dim = len(tetrahedra), len(triangles), dim
+    disc.ctx, disc.mesh = ctx, mesh
     L.discretization = disc
 
     def dm(mid):
@@ -84,19 +116,24 @@ def discretize(mesh, dscrp, C, order="lin", b="__none__", mass_weighting=True, s
         if typ == "interior":
             pid = tet_pattern(domain)
             im, ik = ctx.assemble_mk(pid, C_tet[simplices])
+            disc.ops.append({"op": "mk", "pid": pid, "simplices": simplices, "mats": (im, ik)})
             disc.timing[f"{domain}/MK_ms"] = ctx.last_ms("assemble")
             L.push(Term(dm(im), (pow2,), (("ω",),), "ω^2", "M"))
             L.push(Term(dm(ik), (), (), "", "K"))
         elif typ == "mass":
             pid = tet_pattern(domain)
-            L.push(Term(dm(ctx.assemble(pid, _lib.OP_MASS)), (pow2,), (("ω",),), "ω^2", "M"))
+            mid = ctx.assemble(pid, _lib.OP_MASS)
+            disc.ops.append({"op": "mass", "pid": pid, "scale": 1.0, "mat": mid})
+            L.push(Term(dm(mid), (pow2,), (("ω",),), "ω^2", "M"))
         elif typ == "stiff":
             funcs, args, txt = data
             for a in args:
                 for p in a:
                     L.params[p] = 0.0
             pid = tet_pattern(domain)
-            L.push(Term(dm(ctx.assemble(pid, _lib.OP_STIFF, C_tet[simplices])), tuple(funcs), tuple(args), txt, "K"))
+            mid = ctx.assemble(pid, _lib.OP_STIFF, C_tet[simplices])
+            disc.ops.append({"op": "stiff", "pid": pid, "simplices": simplices, "mat": mid})
+            L.push(Term(dm(mid), tuple(funcs), tuple(args), txt, "K"))
         elif typ == "admittance":
             if len(data) == 2:
                 adm_sym, adm_val = data
@@ -108,7 +145,9 @@ def discretize(mesh, dscrp, C, order="lin", b="__none__", mass_weighting=True, s
                 raise NotImplementedError("state-space admittance (A,B,C,D) is not on the accelerated path")
             pid = ctx.pattern_build(2, simplices)[0]
             disc.patterns[(2, domain)] = pid
-            L.push(Term(dm(ctx.assemble(pid, _lib.OP_BOUNDARY, C_tri[simplices])), bfunc, barg, btxt, "C"))
+            mid = ctx.assemble(pid, _lib.OP_BOUNDARY, C_tri[simplices])
+            disc.ops.append({"op": "boundary", "pid": pid, "simplices": simplices, "mat": mid})
+            L.push(Term(dm(mid), bfunc, barg, btxt, "C"))
         elif typ in ("flame", "flameresponse"):
             ref_idx = -1
             if typ == "flame" and len(data) == 9:
@@ -148,6 +187,8 @@ def discretize(mesh, dscrp, C, order="lin", b="__none__", mass_weighting=True, s
             if ref_idx in set(simplices.tolist()):
                 print("Warning: your reference point is inside the domain of heat release. (short-circuited FTF!)")
             pid, mid, _ = ctx.assemble_flame(simplices, ref_idx, x_ref, n_ref, nlocal)
+            disc.ops.append({"op": "flame", "simplices": simplices, "ref_idx": ref_idx, "x_ref": x_ref, "n_ref": n_ref,
+                             "gamma": gamma, "rho": rho, "nglobal": nglobal, "domain": domain, "mat": mid})
             disc.patterns[("Q", domain)] = pid
             L.push(Term(dm(mid), ffunc, farg, ftxt, "Q"))
         else:
@@ -159,5 +200,6 @@ def discretize(mesh, dscrp, C, order="lin", b="__none__", mass_weighting=True, s
         if key not in disc.patterns:
             disc.patterns[key] = ctx.pattern_build(3, None)[0]
         mid = ctx.assemble(disc.patterns[key], _lib.OP_MASS, None, scale=-1.0)
+        disc.ops.append({"op": "mass", "pid": disc.patterns[key], "scale": -1.0, "mat": mid})
         L.push(Term(dm(mid), (pow1,), (("λ",),), "-λ", "__aux__"))
     return L

@@ -16,6 +16,7 @@ Scalar coefficient functions stay on the host (they are arbitrary closures in th
 only their values cross the ABI.
 """
 import math
+import time
 
 import numpy as np
 
@@ -556,13 +557,19 @@ def _iterate(L, z, maxiter, tol, relax, order, nev, v0, v0_adj, kind, num_order,
                 z0 = z
             L.params[L.eigval] = z
             L.params[L.auxval] = 0
+            _t0 = time.perf_counter()
             L(z).materialize(0)
             ctx.lu_factor(lu, 0)
+            _t1 = time.perf_counter()
             lams, v, ns1 = ctx.eigs_si(lu, dev.fid, 1, nev, v0, trans=0)
             lams_adj, v_adj, ns2 = ctx.eigs_si(lu, dev.fid, 1, nev, v0_adj, trans=2)
+            _t2 = time.perf_counter()
             if stats is not None:
                 stats["factorizations"] = stats.get("factorizations", 0) + 1
                 stats["solves"] = stats.get("solves", 0) + ns1 + ns2
+                stats["factor_ms"] = stats.get("factor_ms", 0.0) + ctx.last_ms("factor")
+                stats["combine_factor_wall_s"] = stats.get("combine_factor_wall_s", 0.0) + _t1 - _t0
+                stats["eigs_wall_s"] = stats.get("eigs_wall_s", 0.0) + _t2 - _t1
             idx = np.argsort(np.abs(lams), kind="stable")
             lams, v = lams[idx], v[:, idx]
             idx = np.argsort(np.abs(lams_adj), kind="stable")
@@ -583,6 +590,8 @@ def _iterate(L, z, maxiter, tol, relax, order, nev, v0, v0_adj, kind, num_order,
                     if z0 != complex("inf"):
                         back.append(lam0 - polyval(num, z0 - z) / polyval(den, z0 - z))
             L.active = [L.eigval]
+            if stats is not None:
+                stats["perturb_wall_s"] = stats.get("perturb_wall_s", 0.0) + time.perf_counter() - _t2
             sel = np.argsort(np.abs(back if back else dzs), kind="stable")[0]
             lam = lams[sel]
             L.params[L.auxval] = lam
@@ -750,8 +759,9 @@ def compute_moment_matrices(L, G, l=5, K=1, N=16, group=None, stats=None):
     return A.permute(2, 1, 0).cpu().numpy()
 
 
-def moments2eigs(A, G=None, tol=0.0, pos_test=True, output=False):
-    """Block-Hankel SVD + small eigenproblem (beyn.jl:77-107, 289-323)."""
+def moments2eigs(A, G=None, tol=0.0, pos_test=True, output=False, rtol=0.0):
+    """Block-Hankel SVD + small eigenproblem (beyn.jl:77-107, 289-323).  ``tol`` is the reference's absolute
+    singular-value threshold; ``rtol`` (extension) is relative to the largest singular value."""
     d, l, K2 = A.shape
     K = K2 // 2
     B0 = np.zeros((d * K, l * K), dtype=complex)
@@ -764,8 +774,8 @@ def moments2eigs(A, G=None, tol=0.0, pos_test=True, output=False):
     W = Wh.conj().T
     if output:
         print("############\nsingular values:\n", S)
-    if tol > 0:
-        m = S > tol
+    if tol > 0 or rtol > 0:
+        m = S > max(tol, rtol * S[0])
         V, S, W = V[:, m], S[m], W[:, m]
     Om, P = np.linalg.eig(V.conj().T @ B1 @ W @ np.diag(1 / S))
     P = V[:d, :] @ P
