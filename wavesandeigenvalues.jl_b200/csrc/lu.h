@@ -22,6 +22,8 @@ struct LuSymbolic {
   std::vector<int32_t> rel_idx;
   std::vector<int64_t> lp_off, up_off;  // offsets (complex units) of the L panel and U^T panel in the factor array
   std::vector<int64_t> upd_off;         // offset of the r x r update matrix inside its depth-level buffer
+  std::vector<int64_t> dinv_off;        // offset of the inverted diagonal blocks (per block: L_kk^-1, U_kk^-1, NB x NB each)
+  int64_t dinv_size = 0;
   std::vector<int64_t> level_upd_size;  // per depth: complex entries of all update matrices of that depth
   std::vector<std::vector<int32_t>> levels;  // supernodes by depth
   int64_t fac_size = 0;        // complex entries of the factor array (L panels + U^T panels)
@@ -41,7 +43,7 @@ struct LuSolver {
   LuSymbolic sym;
   // device copies of the symbolic data
   DevBuf<int32_t> d_perm, d_iperm, d_sn_first, d_sn_parent, d_struct_idx, d_rel_idx, d_diagpos;
-  DevBuf<int64_t> d_struct_ptr, d_lp_off, d_up_off, d_upd_off, d_amap;
+  DevBuf<int64_t> d_struct_ptr, d_lp_off, d_up_off, d_upd_off, d_dinv_off, d_amap;
   DevBuf<int32_t> d_colidx_nz;         // column index of every nonzero of A (for the scaling in the scatter)
   std::vector<DevBuf<int32_t>> d_level;  // supernode ids per depth
   std::vector<DevBuf<int32_t>> d_xa_tile_ptr;  // per depth: extend-add tile prefix over the supernodes of that depth
@@ -49,6 +51,7 @@ struct LuSolver {
   DevBuf<cplx> d_Aval;                 // copy of the factorised matrix (iterative refinement)
   // numeric
   DevBuf<cplx> d_fac;
+  DevBuf<cplx> d_dinv;                 // explicit inverses of the NB x NB diagonal blocks (triangular solves without a serial chain)
   DevBuf<cplx> d_upd[2];
   DevBuf<double> d_scale;              // equilibration D (A_s = D A D)
   DevBuf<cplx> d_work;                 // solve workspace (n x nrhs) x 2

@@ -33,8 +33,9 @@ struct LuDev {  // plain device pointers handed to the kernels
   const int32_t* struct_idx;
   const int32_t* rel_idx;
   const int32_t* sn_parent;
-  const int64_t *lp_off, *up_off, *upd_off;
+  const int64_t *lp_off, *up_off, *upd_off, *dinv_off;
   cplx* fac;
+  cplx* dinv;
 };
 
 __device__ __forceinline__ SnView sn_view(const LuDev& D, int k) {
@@ -158,6 +159,33 @@ __global__ void __launch_bounds__(NB * NB) lu_diag_kernel(LuDev D, const int32_t
     // U_kk^T into the U^T panel (lower triangle incl. diagonal)
     if (i >= j) S.up[(c0 + i) + (size_t)(c0 + j) * S.ld] = T[j][i];
   }
+  // explicit inverses of the two triangular factors (used by the solves): thread (c,0) builds column c of L^-1 by
+  // forward substitution, thread (c,1) column c of U^-1 by back substitution; stored NB x NB column-major, zero padded
+  // (both triangles share one array: strict lower = L^-1 (unit diagonal implied), upper incl. diagonal = U^-1)
+  __shared__ cplx X[NB][NB + 1];
+  X[i][j] = make_double2(0.0, 0.0);
+  __syncthreads();
+  if (j == 0 && i < nb) {
+    const int c = i;
+    for (int r = c + 1; r < nb; r++) {
+      cplx acc = make_double2(-T[r][c].x, -T[r][c].y);  // m = c term: X[c][c] = 1
+      for (int m = c + 1; m < r; m++) acc = csub(acc, cmul(T[r][m], X[m][c]));
+      X[r][c] = acc;
+    }
+  } else if (j == 1 && i < nb) {
+    const int c = i;
+    X[c][c] = cinv(T[c][c]);
+    for (int r = c - 1; r >= 0; r--) {
+      cplx acc = make_double2(0.0, 0.0);
+      for (int m = r + 1; m <= c; m++) acc = csub(acc, cmul(T[r][m], X[m][c]));
+      X[r][c] = cmul(acc, cinv(T[r][r]));
+    }
+  }
+  __syncthreads();
+  cplx* inv = D.dinv + D.dinv_off[list[blockIdx.x]] + (size_t)k * 2 * NB * NB;
+  const cplx zero = make_double2(0.0, 0.0), one = make_double2(1.0, 0.0);
+  inv[i + j * NB] = i > j ? X[i][j] : (i == j && i < nb ? one : zero);
+  inv[NB * NB + i + j * NB] = i <= j ? X[i][j] : zero;
 }
 
 // ---- step k, part 2: panel solves below the diagonal block -------------------------------------------
@@ -315,38 +343,40 @@ __global__ void __launch_bounds__(256) lu_gemm_kernel(LuDev D, const int32_t* __
 
 // ---- triangular solves ---------------------------------------------------------------------------------
 // forward substitution with a lower-trapezoidal panel P (Lp: unit diagonal, Up: general diagonal)
-// phase 1 (one CTA per supernode): pivot block, blocked by NB, warp-shuffle substitution inside a block
-__global__ void __launch_bounds__(256) lu_fwd_pivot_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int nrhs, int64_t n, cplx* __restrict__ x) {
-  SnView S = sn_view(D, list[blockIdx.x]);
+// phase 1 (one CTA of 32 warps per supernode): pivot block, blocked by NB.  The diagonal blocks were inverted at
+// factorisation time, so a block step is a 32x32 matrix-vector product (warp w = row w, shuffle reduction) followed
+// by the rank-NB update of the remaining pivot rows -- no serial substitution chain.
+//   use_up = 0: T_kk^-1 = L_kk^-1            use_up = 1: T_kk = U_kk^T  ->  T_kk^-1 = (U_kk^-1)^T
+__global__ void __launch_bounds__(1024) lu_fwd_pivot_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int nrhs, int64_t n, cplx* __restrict__ x) {
+  const int sn = list[blockIdx.x];
+  SnView S = sn_view(D, sn);
   const cplx* P = use_up ? S.up : S.lp;
-  const bool unit = !use_up;
+  const cplx* dinv = D.dinv + D.dinv_off[sn] + (use_up ? NB * NB : 0);
   __shared__ cplx yk[NB];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int rhs = 0; rhs < nrhs; rhs++) {
     cplx* xs = x + (size_t)rhs * n + S.first;
-    for (int c0 = 0; c0 < S.s; c0 += NB) {
+    for (int c0 = 0, kb = 0; c0 < S.s; c0 += NB, kb++) {
       const int nb = min(NB, S.s - c0);
-      if (warp == 0) {
+      {
+        const cplx* Tinv = dinv + (size_t)kb * 2 * NB * NB;
+        // y[warp] = sum_lane Tinv(warp, lane) x[lane]   (Tinv(r,c) stored at r + c*NB; transposed access for use_up)
+        cplx m = use_up ? Tinv[lane + warp * NB] : Tinv[warp + lane * NB];
         cplx v = lane < nb ? xs[c0 + lane] : make_double2(0.0, 0.0);
-        for (int m = 0; m < nb; m++) {
-          cplx ym;
-          if (!unit) {
-            cplx d = P[(c0 + m) + (size_t)(c0 + m) * S.ld];
-            if (lane == m) v = cmul(v, cinv(d));
-          }
-          ym.x = __shfl_sync(0xffffffffu, v.x, m);
-          ym.y = __shfl_sync(0xffffffffu, v.y, m);
-          if (lane > m && lane < nb) v = csub(v, cmul(P[(c0 + lane) + (size_t)(c0 + m) * S.ld], ym));
+        double sr = m.x * v.x - m.y * v.y, si = m.x * v.y + m.y * v.x;
+#pragma unroll
+        for (int off = 16; off; off >>= 1) {
+          sr += __shfl_xor_sync(0xffffffffu, sr, off);
+          si += __shfl_xor_sync(0xffffffffu, si, off);
         }
-        if (lane < nb) {
-          xs[c0 + lane] = v;
-          yk[lane] = v;
-        }
+        if (lane == 0) yk[warp] = make_double2(sr, si);
       }
       __syncthreads();
+      if (threadIdx.x < nb) xs[c0 + threadIdx.x] = yk[threadIdx.x];
       for (int i = c0 + nb + threadIdx.x; i < S.s; i += blockDim.x) {
         cplx acc = make_double2(0.0, 0.0);
         const cplx* row = P + i + (size_t)c0 * S.ld;
+#pragma unroll 8
         for (int j = 0; j < nb; j++) {
           cplx a = row[(size_t)j * S.ld];
           acc.x += a.x * yk[j].x - a.y * yk[j].y;
@@ -419,50 +449,50 @@ __global__ void __launch_bounds__(256) lu_bwd_struct_kernel(LuDev D, const int32
 }
 
 // phase 2 (one CTA per supernode, 32 warps): pivot block, blocks from last to first.
+//   use_up = 1 (A x = b): x_k = U_kk^-1 (...)        use_up = 0 (A^T x = b): x_k = (L_kk^-1)^T (...)
 __global__ void __launch_bounds__(1024) lu_bwd_pivot_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int nrhs, int64_t n, cplx* __restrict__ x) {
-  SnView S = sn_view(D, list[blockIdx.x]);
+  const int sn = list[blockIdx.x];
+  SnView S = sn_view(D, sn);
   const cplx* P = use_up ? S.up : S.lp;
-  const bool unit = !use_up;
+  const cplx* dinv = D.dinv + D.dinv_off[sn] + (use_up ? NB * NB : 0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nblk = (S.s + NB - 1) / NB;
+  __shared__ cplx yk[NB];
   for (int rhs = 0; rhs < nrhs; rhs++) {
     cplx* xs = x + (size_t)rhs * n + S.first;
     for (int kb = nblk - 1; kb >= 0; kb--) {
       const int c0 = kb * NB, nb = min(NB, S.s - c0);
       // column c0+warp: subtract the contribution of the already solved pivot rows below this block
-      if (warp < nb) {
-        const cplx* col = P + (size_t)(c0 + warp) * S.ld;
+      {
         double sr = 0.0, si = 0.0;
-        for (int i = c0 + nb + lane; i < S.s; i += 32) {
-          cplx a = col[i], v = xs[i];
-          sr += a.x * v.x - a.y * v.y;
-          si += a.x * v.y + a.y * v.x;
+        if (warp < nb) {
+          const cplx* col = P + (size_t)(c0 + warp) * S.ld;
+          for (int i = c0 + nb + lane; i < S.s; i += 32) {
+            cplx a = col[i], v = xs[i];
+            sr += a.x * v.x - a.y * v.y;
+            si += a.x * v.y + a.y * v.x;
+          }
         }
 #pragma unroll
         for (int off = 16; off; off >>= 1) {
           sr += __shfl_xor_sync(0xffffffffu, sr, off);
           si += __shfl_xor_sync(0xffffffffu, si, off);
         }
-        if (lane == 0) {
-          xs[c0 + warp].x -= sr;
-          xs[c0 + warp].y -= si;
-        }
+        if (lane == 0) yk[warp] = warp < nb ? make_double2(xs[c0 + warp].x - sr, xs[c0 + warp].y - si) : make_double2(0.0, 0.0);
       }
       __syncthreads();
-      // in-block transposed solve: x_j = (x_j - sum_{m>j} T[m][j] x_m) / T[j][j]
-      if (warp == 0) {
-        cplx v = lane < nb ? xs[c0 + lane] : make_double2(0.0, 0.0);
-        for (int m = nb - 1; m >= 0; m--) {
-          if (!unit) {
-            cplx d = P[(c0 + m) + (size_t)(c0 + m) * S.ld];
-            if (lane == m) v = cmul(v, cinv(d));
-          }
-          cplx ym;
-          ym.x = __shfl_sync(0xffffffffu, v.x, m);
-          ym.y = __shfl_sync(0xffffffffu, v.y, m);
-          if (lane < m) v = csub(v, cmul(P[(c0 + m) + (size_t)(c0 + lane) * S.ld], ym));
+      {
+        // x[warp] = sum_lane M(warp, lane) y[lane], M = U_kk^-1 (use_up) or (L_kk^-1)^T
+        const cplx* Tinv = dinv + (size_t)kb * 2 * NB * NB;
+        cplx m = use_up ? Tinv[warp + lane * NB] : Tinv[lane + warp * NB];
+        cplx v = yk[lane];
+        double sr = m.x * v.x - m.y * v.y, si = m.x * v.y + m.y * v.x;
+#pragma unroll
+        for (int off = 16; off; off >>= 1) {
+          sr += __shfl_xor_sync(0xffffffffu, sr, off);
+          si += __shfl_xor_sync(0xffffffffu, si, off);
         }
-        if (lane < nb) xs[c0 + lane] = v;
+        if (lane == 0 && warp < nb) xs[c0 + warp] = make_double2(sr, si);
       }
       __syncthreads();
     }
@@ -517,7 +547,9 @@ static LuDev make_dev(LuSolver& S) {
   D.lp_off = S.d_lp_off.p;
   D.up_off = S.d_up_off.p;
   D.upd_off = S.d_upd_off.p;
+  D.dinv_off = S.d_dinv_off.p;
   D.fac = S.d_fac.p;
+  D.dinv = S.d_dinv.p;
   return D;
 }
 
@@ -535,6 +567,8 @@ void wae_lu_setup_device(wae_ctx* h, LuSolver& S) {
   S.d_lp_off.upload(Y.lp_off, st);
   S.d_up_off.upload(Y.up_off, st);
   S.d_upd_off.upload(Y.upd_off, st);
+  S.d_dinv_off.upload(Y.dinv_off, st);
+  S.d_dinv.alloc((size_t)std::max<int64_t>(Y.dinv_size, 1));
   S.d_amap.upload(Y.amap, st);
   // per-depth lists, largest pivot block first (so that "supernodes with more than k blocks" is a prefix)
   S.d_level.resize(Y.levels.size());
@@ -668,7 +702,7 @@ static void lu_sweeps(wae_ctx* h, LuSolver& S, int trans_t, int nrhs, cplx* y) {
     for (int32_t k : L) max_r = std::max(max_r, (int)(Y.struct_ptr[k + 1] - Y.struct_ptr[k]));
     for (int z0 = 0; z0 < (int)L.size(); z0 += 32768) {
       int zc = std::min<int>(32768, (int)L.size() - z0);
-      lu_fwd_pivot_kernel<<<zc, 256, 0, st>>>(D, S.d_level[d].p + z0, fwd_up, nrhs, Y.n, y);
+      lu_fwd_pivot_kernel<<<zc, 1024, 0, st>>>(D, S.d_level[d].p + z0, fwd_up, nrhs, Y.n, y);
       h->launches++;
       if (max_r > 0) {
         lu_fwd_struct_kernel<<<dim3((max_r + 127) / 128, zc), 128, 0, st>>>(D, S.d_level[d].p + z0, fwd_up, nrhs, Y.n, y);

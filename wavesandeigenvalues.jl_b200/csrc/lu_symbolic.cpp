@@ -359,6 +359,8 @@ void wae_lu_symbolic(int64_t n, const int64_t* colptr, const int32_t* rowval, co
   S.lp_off.resize(S.nsn);
   S.up_off.resize(S.nsn);
   S.upd_off.resize(S.nsn);
+  S.dinv_off.resize(S.nsn);
+  int64_t doff = 0;
   S.level_upd_size.assign(maxd + 1, 0);
   int64_t off = 0;
   for (int k = 0; k < S.nsn; k++) {
@@ -367,6 +369,8 @@ void wae_lu_symbolic(int64_t n, const int64_t* colptr, const int32_t* rowval, co
     off += (s + r) * s;
     S.up_off[k] = off;
     off += (s + r) * s;
+    S.dinv_off[k] = doff;
+    doff += 2 * (int64_t)WAE_LU_NB * WAE_LU_NB * ((s + WAE_LU_NB - 1) / WAE_LU_NB);
     S.upd_off[k] = S.level_upd_size[S.sn_depth[k]];
     S.level_upd_size[S.sn_depth[k]] += r * r;
     S.factor_nnz += s * s + 2 * s * r;
@@ -380,6 +384,7 @@ void wae_lu_symbolic(int64_t n, const int64_t* colptr, const int32_t* rowval, co
     S.flops += 8.0 * (sum1 + sum2);
   }
   S.fac_size = off;
+  S.dinv_size = doff;
   // relative indices of every structure row in the parent's front
   S.rel_ptr = S.struct_ptr;
   S.rel_idx.resize(S.struct_idx.size());
