@@ -314,8 +314,12 @@ __device__ __forceinline__ void zgemm_nt_tile(const GemmProblem& P, int tile_m, 
       }
 }
 
-// mode 0: Lp trailing pivot columns, mode 1: Up trailing pivot columns (step k), mode 2: Schur complement
-__global__ void __launch_bounds__(256) lu_gemm_kernel(LuDev D, const int32_t* __restrict__ list, int k, int mode, cplx* __restrict__ upd) {
+// mode 0: Lp trailing pivot columns, mode 1: Up trailing pivot columns, mode 2: Schur complement.
+// Modes 0/1 update C = X[c0:ld, c0:min(s,cap)] -= X[c0:ld, k0:k0+kw] * Y[c0:min(s,cap), k0:k0+kw]^T  (X,Y = Lp,Up or Up,Lp).
+// Two-level blocking: inside an outer block of NBO columns the NB-wide steps only touch the columns of that outer block
+// (kw = NB, cap = end of the outer block); the rest of the pivot block is updated once per outer block with kw = NBO.
+__global__ void __launch_bounds__(256) lu_gemm_kernel(LuDev D, const int32_t* __restrict__ list, int mode, int k0, int kw, int c0, int cap,
+                                                      cplx* __restrict__ upd) {
   const int sn = list[blockIdx.z];
   SnView S = sn_view(D, sn);
   GemmProblem P;
@@ -326,16 +330,15 @@ __global__ void __launch_bounds__(256) lu_gemm_kernel(LuDev D, const int32_t* __
     P.A = S.lp + S.s; P.B = S.up + S.s;
     P.C = upd + D.upd_off[sn];
   } else {
-    const int c0 = k * NB;
-    if (c0 + NB >= S.s) return;  // no trailing pivot columns
-    const int r0 = c0 + NB;
-    P.m = S.ld - r0; P.n = S.s - r0; P.K = NB;
+    const int cend = min(S.s, cap);
+    if (c0 >= cend) return;  // no trailing pivot columns in range
+    P.m = S.ld - c0; P.n = cend - c0; P.K = kw;
     P.lda = P.ldb = P.ldc = S.ld;
     cplx* X = mode == 0 ? S.lp : S.up;
     cplx* Y = mode == 0 ? S.up : S.lp;
-    P.A = X + r0 + (size_t)c0 * S.ld;
-    P.B = Y + r0 + (size_t)c0 * S.ld;
-    P.C = X + r0 + (size_t)r0 * S.ld;
+    P.A = X + c0 + (size_t)k0 * S.ld;
+    P.B = Y + c0 + (size_t)k0 * S.ld;
+    P.C = X + c0 + (size_t)c0 * S.ld;
   }
   if ((int)(blockIdx.x * GT) >= P.m || (int)(blockIdx.y * GT) >= P.n) return;
   zgemm_nt_tile(P, blockIdx.x, blockIdx.y);
@@ -626,6 +629,8 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval) {
   lu_scatter_kernel<<<(unsigned)((U.nnz + 255) / 256), 256, 0, st>>>(d_Aval, S.d_amap.p, U.d_rowval.p, S.d_colidx_nz.p, S.d_scale.p, U.nnz, S.d_fac.p);
   h->launches += 2;
   const int maxd = (int)Y.levels.size() - 1;
+  int nbo_blocks = 4;  // outer block = 4 * NB = 128 columns
+  if (const char* env = getenv("WAE_LU_NBO")) nbo_blocks = std::max(1, atoi(env) / NB);
   for (int d = maxd; d >= 0; d--) {
     const std::vector<int32_t>& L = Y.levels[d];
     const int nl = (int)L.size();
@@ -657,11 +662,22 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval) {
         int rows = max_ld - k * NB - 1;  // upper bound of ld - (c0 + nb) over the batch (nb >= 1)
         if (rows > 0) {
           lu_panel_kernel<<<dim3((rows + 127) / 128, 2, zc), 128, 0, st>>>(D, lst, k);
-          int tn = max_s - (k + 1) * NB;
+          // inner update: columns of the current outer block only
+          const int c0 = (k + 1) * NB;
+          const int oend = (k / nbo_blocks + 1) * nbo_blocks * NB;  // end column of the outer block
+          int tn = std::min(max_s, oend) - c0;
           if (tn > 0) {
-            dim3 g((rows + GT - 1) / GT, (tn + GT - 1) / GT, zc);
-            lu_gemm_kernel<<<g, 256, 0, st>>>(D, lst, k, 0, nullptr);
-            lu_gemm_kernel<<<g, 256, 0, st>>>(D, lst, k, 1, nullptr);
+            dim3 g((max_ld - c0 + GT - 1) / GT, (tn + GT - 1) / GT, zc);
+            lu_gemm_kernel<<<g, 256, 0, st>>>(D, lst, 0, k * NB, NB, c0, oend, nullptr);
+            lu_gemm_kernel<<<g, 256, 0, st>>>(D, lst, 1, k * NB, NB, c0, oend, nullptr);
+            h->launches += 2;
+          }
+          // outer update once the outer block is complete
+          if (c0 == oend && max_s > oend) {
+            const int o0 = oend - nbo_blocks * NB;
+            dim3 g((max_ld - oend + GT - 1) / GT, (max_s - oend + GT - 1) / GT, zc);
+            lu_gemm_kernel<<<g, 256, 0, st>>>(D, lst, 0, o0, oend - o0, oend, 1 << 30, nullptr);
+            lu_gemm_kernel<<<g, 256, 0, st>>>(D, lst, 1, o0, oend - o0, oend, 1 << 30, nullptr);
             h->launches += 2;
           }
           h->launches++;
@@ -673,7 +689,7 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval) {
       for (int z0 = 0; z0 < nl; z0 += 32768) {
         int zc = std::min(32768, nl - z0);
         dim3 g((max_r + GT - 1) / GT, (max_r + GT - 1) / GT, zc);
-        lu_gemm_kernel<<<g, 256, 0, st>>>(D, S.d_level[d].p + z0, 0, 2, upd);
+        lu_gemm_kernel<<<g, 256, 0, st>>>(D, S.d_level[d].p + z0, 2, 0, 0, 0, 0, upd);
         h->launches++;
       }
     }
