@@ -54,11 +54,15 @@ struct LuSolver {
   DevBuf<cplx> d_dinv;                 // explicit inverses of the NB x NB diagonal blocks (triangular solves without a serial chain)
   DevBuf<cplx> d_upd[2];
   DevBuf<double> d_scale;              // equilibration D (A_s = D A D)
-  DevBuf<cplx> d_work;                 // solve workspace (n x nrhs) x 2
+  DevBuf<cplx> d_work;                 // solve workspace (n x nrhs) x 3
+  DevBuf<cplx> d_io;                   // cached staging buffer of wae_lu_solve / wae_beyn_moments
+  DevBuf<cplx> d_arn_V, d_arn_w, d_arn_t, d_arn_c;  // cached Arnoldi workspace of wae_eigs_si
+  DevBuf<double> d_arn_dots;
   DevBuf<int32_t> d_flag;              // device-side status (bad pivot)
   int work_nrhs = 0;
   bool factored = false;
-  int refine_steps = 1;
+  int refine_steps = 1;   // iterative refinement steps of wae_lu_solve / wae_beyn_moments
+  int eigs_refine = 0;    // ... inside the Arnoldi operator (goldens G1-G6 hold to 1e-10 without; WAE_EIGS_REFINE overrides)
   double pivot_eps = 1e-30;  // only exact zeros are replaced: near-singular L(omega) is the normal case close to an eigenvalue
 };
 

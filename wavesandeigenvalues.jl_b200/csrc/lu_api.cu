@@ -281,6 +281,7 @@ int32_t wae_lu_analyze(wae_ctx* h, int32_t fam_id, int32_t* lu_id, int64_t* fact
   if (const char* env = getenv("WAE_LU_LEAF")) leaf = atoi(env);
   if (const char* env = getenv("WAE_LU_PIVOT_EPS")) S->pivot_eps = atof(env);
   if (const char* env = getenv("WAE_LU_REFINE")) S->refine_steps = atoi(env);
+  if (const char* env = getenv("WAE_EIGS_REFINE")) S->eigs_refine = atoi(env);
   wae_lu_symbolic(U.dim, U.colptr.data(), U.rowval.data(), have ? xyz.data() : nullptr, leaf, S->sym);
   wae_lu_setup_device(h, *S);
   h->lus.push_back(S);
@@ -308,7 +309,7 @@ int32_t wae_lu_solve(wae_ctx* h, int32_t lu_id, int32_t trans, int32_t nrhs, dou
   LuSolver& S = get_lu(h, lu_id);
   if (trans < 0 || trans > 2 || nrhs <= 0 || !X) WAE_THROW(WAE_E_INVALID, "bad solve arguments");
   int64_t n = S.sym.n;
-  DevBuf<cplx> dX;
+  DevBuf<cplx>& dX = S.d_io;
   dX.upload((const cplx*)X, (size_t)n * nrhs, h->stream);
   PhaseTimer t(h, "solve");
   wae_lu_solve_device(h, S, trans, nrhs, dX.p, S.refine_steps);
@@ -332,12 +333,12 @@ int32_t wae_eigs_si(wae_ctx* h, int32_t lu_id, int32_t fam_id, int32_t m_slot, i
   const int m = (int)std::min<int64_t>(std::max(20, 2 * nev + 1), n);  // ncv as in Arpack.jl
   cudaStream_t st = h->stream;
   PhaseTimer timer(h, "eigs");
-  ArnoldiWork W;
-  W.V.alloc((size_t)n * (m + 1));
-  W.w.alloc(n);
-  W.t.alloc(n);
-  W.c.alloc(m + 1);
-  W.dots.alloc(2 * (m + 2));
+  struct { DevBuf<cplx>&V, &w, &t, &c; DevBuf<double>& dots; } W{S.d_arn_V, S.d_arn_w, S.d_arn_t, S.d_arn_c, S.d_arn_dots};
+  W.V.reserve((size_t)n * (m + 1));
+  W.w.reserve(n);
+  W.t.reserve(n);
+  W.c.reserve(m + 1);
+  W.dots.reserve(2 * (m + 2));
   const unsigned gb = (unsigned)((n + 255) / 256);
   const int dot_blocks = (int)std::min<int64_t>((n + 255) / 256, 64);
   auto dots = [&](const cplx* Vb, int nv, const cplx* w, std::vector<zc>& out) {
@@ -354,7 +355,7 @@ int32_t wae_eigs_si(wae_ctx* h, int32_t lu_id, int32_t fam_id, int32_t m_slot, i
   int solves = 0;
   auto apply_op = [&](const cplx* x, cplx* y) {  // y = op(A)^{-1} op(M) x
     wae_spmm_device(h, F, m_slot, trans, 1, x, y);
-    wae_lu_solve_device(h, S, trans, 1, y, S.refine_steps);
+    wae_lu_solve_device(h, S, trans, 1, y, S.eigs_refine);
     solves++;
   };
   // start vector
@@ -458,8 +459,8 @@ int32_t wae_beyn_moments(wae_ctx* h, int32_t fam_id, int32_t lu_id, int32_t n_no
   const int64_t n = S.sym.n;
   if (n_nodes < 0 || !z || !w || !coeffs || l < 1 || l > n || n_mom < 1 || !A_out) WAE_THROW(WAE_E_INVALID, "bad Beyn arguments");
   cudaStream_t st = h->stream;
-  DevBuf<cplx> X;
-  X.alloc((size_t)n * l);
+  DevBuf<cplx>& X = S.d_io;
+  X.reserve((size_t)n * l);
   const int slot = WAE_FAMILY_SLOTS - 1;
   double t_fac = 0, t_sol = 0;
   for (int j = 0; j < n_nodes; j++) {

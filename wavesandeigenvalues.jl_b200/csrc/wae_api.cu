@@ -536,9 +536,9 @@ int32_t wae_family_spmm(wae_ctx* h, int32_t fam_id, int32_t slot, int32_t trans,
   if (slot < 0 || slot >= WAE_FAMILY_SLOTS || !F.slot[slot].p) WAE_THROW(WAE_E_INVALID, "family slot %d is empty", slot);
   if (trans < 0 || trans > 2 || nrhs <= 0 || !X || !Y) WAE_THROW(WAE_E_INVALID, "bad spmm arguments");
   int64_t dim = h->pat(F.pattern).dim;
-  DevBuf<double> dX, dY;
+  DevBuf<double>&dX = F.d_io[0], &dY = F.d_io[1];
   dX.upload(X, 2 * dim * nrhs, h->stream);
-  dY.alloc(2 * dim * nrhs);
+  dY.reserve(2 * dim * nrhs);
   PhaseTimer t(h, "spmv");
   wae_spmm_device(h, F, slot, trans, nrhs, (const cplx*)dX.p, (cplx*)dY.p);
   t.stop();

@@ -56,6 +56,9 @@ struct DevBuf {
     if (e != cudaSuccess) WAE_THROW(WAE_E_NOMEM, "cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
     n = count;
   }
+  void reserve(size_t count) {
+    if (n < count) alloc(count);
+  }
   void upload(const T* h, size_t count, cudaStream_t s) {
     if (n < count) alloc(count);
     if (count) CUDA_CHECK(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
@@ -106,6 +109,7 @@ struct Family {
   std::vector<bool> identity;              // term pattern == union pattern
   std::vector<DevBuf<int32_t>> d_map;      // term nz -> union nz (empty if identity)
   DevBuf<double> slot[WAE_FAMILY_SLOTS];   // complex values, 2*nnz doubles each
+  DevBuf<double> d_io[2];                  // cached staging buffers of wae_family_spmm (grow-only)
   DevBuf<int32_t> d_tr_perm;               // CSC->CSR permutation for transposed SpMM (lazy)
   DevBuf<int64_t> d_rowptr;
   DevBuf<int32_t> d_colidx;
