@@ -357,7 +357,8 @@ __global__ void __launch_bounds__(1024) lu_fwd_pivot_kernel(LuDev D, const int32
   const cplx* dinv = D.dinv + D.dinv_off[sn] + (use_up ? NB * NB : 0);
   __shared__ cplx yk[NB];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int rhs = 0; rhs < nrhs; rhs++) {
+  {
+    const int rhs = blockIdx.y;  // one CTA per (supernode, right-hand side)
     cplx* xs = x + (size_t)rhs * n + S.first;
     for (int c0 = 0, kb = 0; c0 < S.s; c0 += NB, kb++) {
       const int nb = min(NB, S.s - c0);
@@ -400,7 +401,8 @@ __global__ void __launch_bounds__(128) lu_fwd_struct_kernel(LuDev D, const int32
   const cplx* P = (use_up ? S.up : S.lp) + S.s;
   const int32_t* st = D.struct_idx + D.struct_ptr[list[blockIdx.y]];
   __shared__ cplx ys[128];
-  for (int rhs = 0; rhs < nrhs; rhs++) {
+  {
+    const int rhs = blockIdx.z;
     const cplx* xs = x + (size_t)rhs * n + S.first;
     cplx acc = make_double2(0.0, 0.0);
     for (int c0 = 0; c0 < S.s; c0 += 128) {
@@ -430,7 +432,8 @@ __global__ void __launch_bounds__(256) lu_bwd_struct_kernel(LuDev D, const int32
   if (c >= S.s || S.r == 0) return;
   const cplx* col = (use_up ? S.up : S.lp) + S.s + (size_t)c * S.ld;
   const int32_t* st = D.struct_idx + D.struct_ptr[list[blockIdx.y]];
-  for (int rhs = 0; rhs < nrhs; rhs++) {
+  {
+    const int rhs = blockIdx.z;
     cplx* xr = x + (size_t)rhs * n;
     double sr = 0.0, si = 0.0;
     for (int i = lane; i < S.r; i += 32) {
@@ -461,7 +464,8 @@ __global__ void __launch_bounds__(1024) lu_bwd_pivot_kernel(LuDev D, const int32
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nblk = (S.s + NB - 1) / NB;
   __shared__ cplx yk[NB];
-  for (int rhs = 0; rhs < nrhs; rhs++) {
+  {
+    const int rhs = blockIdx.y;
     cplx* xs = x + (size_t)rhs * n + S.first;
     for (int kb = nblk - 1; kb >= 0; kb--) {
       const int c0 = kb * NB, nb = min(NB, S.s - c0);
@@ -718,10 +722,10 @@ static void lu_sweeps(wae_ctx* h, LuSolver& S, int trans_t, int nrhs, cplx* y) {
     for (int32_t k : L) max_r = std::max(max_r, (int)(Y.struct_ptr[k + 1] - Y.struct_ptr[k]));
     for (int z0 = 0; z0 < (int)L.size(); z0 += 32768) {
       int zc = std::min<int>(32768, (int)L.size() - z0);
-      lu_fwd_pivot_kernel<<<zc, 1024, 0, st>>>(D, S.d_level[d].p + z0, fwd_up, nrhs, Y.n, y);
+      lu_fwd_pivot_kernel<<<dim3(zc, nrhs), 1024, 0, st>>>(D, S.d_level[d].p + z0, fwd_up, nrhs, Y.n, y);
       h->launches++;
       if (max_r > 0) {
-        lu_fwd_struct_kernel<<<dim3((max_r + 127) / 128, zc), 128, 0, st>>>(D, S.d_level[d].p + z0, fwd_up, nrhs, Y.n, y);
+        lu_fwd_struct_kernel<<<dim3((max_r + 127) / 128, zc, nrhs), 128, 0, st>>>(D, S.d_level[d].p + z0, fwd_up, nrhs, Y.n, y);
         h->launches++;
       }
     }
@@ -736,10 +740,10 @@ static void lu_sweeps(wae_ctx* h, LuSolver& S, int trans_t, int nrhs, cplx* y) {
     for (int z0 = 0; z0 < (int)L.size(); z0 += 32768) {
       int zc = std::min<int>(32768, (int)L.size() - z0);
       if (max_r > 0) {
-        lu_bwd_struct_kernel<<<dim3((max_s + 7) / 8, zc), 256, 0, st>>>(D, S.d_level[d].p + z0, !fwd_up, nrhs, Y.n, y);
+        lu_bwd_struct_kernel<<<dim3((max_s + 7) / 8, zc, nrhs), 256, 0, st>>>(D, S.d_level[d].p + z0, !fwd_up, nrhs, Y.n, y);
         h->launches++;
       }
-      lu_bwd_pivot_kernel<<<zc, 1024, 0, st>>>(D, S.d_level[d].p + z0, !fwd_up, nrhs, Y.n, y);
+      lu_bwd_pivot_kernel<<<dim3(zc, nrhs), 1024, 0, st>>>(D, S.d_level[d].p + z0, !fwd_up, nrhs, Y.n, y);
       h->launches++;
     }
   }
