@@ -65,6 +65,7 @@ void wae_combine_device(wae_ctx* h, Family& F, const double* coeffs, int slot) {
   if (slot < 0 || slot >= WAE_FAMILY_SLOTS) WAE_THROW(WAE_E_INVALID, "slot %d out of range", slot);
   Pattern& U = h->pat(F.pattern);
   if (!F.slot[slot].p) F.slot[slot].alloc(2 * (size_t)U.nnz);
+  F.slot_coeffs[slot].assign(coeffs, coeffs + 2 * F.n_terms);
   double2* out = (double2*)F.slot[slot].p;
   int blocks = (int)std::min<int64_t>((U.nnz + 255) / 256, (int64_t)h->sm_count * 8);
   if (blocks < 1) blocks = 1;
@@ -168,4 +169,34 @@ void wae_spmm_values(wae_ctx* h, Family& F, const cplx* val, int trans, int nrhs
   }
   h->launches++;
   CUDA_CHECK(cudaGetLastError());
+}
+
+// out += (cr + i ci) * A_t  for one term of the family (out lives on the union pattern)
+__global__ void __launch_bounds__(256) axpy_identity_kernel(const double* __restrict__ val, int is_complex, double cr, double ci, int64_t nnz,
+                                                            double2* __restrict__ out) {
+  int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= nnz) return;
+  double vr, vi = 0.0;
+  if (is_complex) {
+    double2 v = reinterpret_cast<const double2*>(val)[k];
+    vr = v.x;
+    vi = v.y;
+  } else
+    vr = val[k];
+  double2 o = out[k];
+  o.x += cr * vr - ci * vi;
+  o.y += cr * vi + ci * vr;
+  out[k] = o;
+}
+
+void wae_axpy_term(wae_ctx* h, Family& F, int t, double cr, double ci, cplx* out) {
+  Matrix& M = h->mat(F.mats[t]);
+  int64_t nnz = h->pat(M.pattern).nnz;
+  if (!nnz) return;
+  unsigned blocks = (unsigned)((nnz + 255) / 256);
+  if (F.identity[t])
+    axpy_identity_kernel<<<blocks, 256, 0, h->stream>>>(M.d_val.p, M.is_complex, cr, ci, nnz, out);
+  else
+    combine_mapped_kernel<<<blocks, 256, 0, h->stream>>>(M.d_val.p, M.is_complex, cr, ci, F.d_map[t].p, nnz, out);
+  h->launches++;
 }

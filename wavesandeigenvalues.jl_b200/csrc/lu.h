@@ -61,6 +61,14 @@ struct LuSolver {
   DevBuf<int32_t> d_flag;              // device-side status (bad pivot)
   int work_nrhs = 0;
   bool factored = false;
+  bool sym_mode = false;               // last factorisation used the symmetric elimination
+  // rank-k correction A = S + sum_j f_j s_j g_j^T (flame terms) on top of the symmetric factorisation of S
+  int r1_k = 0;
+  DevBuf<cplx> d_Sval;                 // values of the symmetric part
+  DevBuf<cplx> d_r1_Sm, d_r1_Gm;       // n x k dense copies of the s_j / g_j vectors
+  DevBuf<cplx> d_r1_Z, d_r1_Zt;        // S^-1 Sm, S^-1 Gm
+  DevBuf<cplx> d_r1_Kinv, d_r1_KinvT;  // (F^-1 + Gm^T Z)^-1 and its transpose, k x k
+  DevBuf<cplx> d_r1_t;                 // k x nrhs scratch
   int refine_steps = 1;   // iterative refinement steps of wae_lu_solve / wae_beyn_moments
   int eigs_refine = 0;    // ... inside the Arnoldi operator (goldens G1-G6 hold to 1e-10 without; WAE_EIGS_REFINE overrides)
   double pivot_eps = 1e-30;  // only exact zeros are replaced: near-singular L(omega) is the normal case close to an eigenvalue
@@ -68,6 +76,10 @@ struct LuSolver {
 
 // numeric phase (lu_numeric.cu) -- all on the context stream, device pointers
 void wae_lu_setup_device(wae_ctx* h, LuSolver& S);
-void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval);
+// d_Aval: values that are factorised; d_full (may be NULL = d_Aval): the matrix the solves refer to (iterative refinement);
+// sym: d_Aval is complex symmetric -> LDL^T-type elimination (half of the GEMM work)
+void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cplx* d_full, int sym);
+// X <- (LU)^-1 X (tt = 0) or (LU)^-T X (tt = 1): factors only, no rank-k correction, no refinement
+void wae_lu_base_solve(wae_ctx* h, LuSolver& S, int tt, int nrhs, cplx* d_X);
 // X (n x nrhs, column-major, device) <- op(A)^{-1} X; trans: 0 N, 1 T, 2 C
 void wae_lu_solve_device(wae_ctx* h, LuSolver& S, int trans, int nrhs, cplx* d_X, int refine);

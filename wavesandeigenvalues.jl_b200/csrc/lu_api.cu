@@ -232,6 +232,129 @@ __global__ void moment_accum_kernel(const cplx* __restrict__ X, int64_t total, i
   }
 }
 
+// out[idx[i] + n*col] = vals[i]  (dense complex copy of a sparse real vector)
+__global__ void scatter_real_kernel(const double* __restrict__ vals, const int32_t* __restrict__ idx, int cnt, cplx* __restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < cnt) out[idx[i]] = make_double2(vals[i], 0.0);
+}
+__global__ void __launch_bounds__(256) r1_gram_kernel(const cplx* __restrict__ W, int64_t n, int k, const cplx* __restrict__ Z, double* __restrict__ out) {
+  // out[(i + k*j)] += sum_p W[p + n*i] * Z[p + n*j]   (plain transpose); grid (chunks, k, k)
+  const cplx* w = W + (size_t)blockIdx.y * n;
+  const cplx* z = Z + (size_t)blockIdx.z * n;
+  double sr = 0.0, si = 0.0;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    cplx a = w[p], b = z[p];
+    sr += a.x * b.x - a.y * b.y;
+    si += a.x * b.y + a.y * b.x;
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) {
+    sr += __shfl_xor_sync(0xffffffffu, sr, off);
+    si += __shfl_xor_sync(0xffffffffu, si, off);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out + 2 * (blockIdx.y + (size_t)k * blockIdx.z), sr);
+    atomicAdd(out + 2 * (blockIdx.y + (size_t)k * blockIdx.z) + 1, si);
+  }
+}
+
+// Numeric factorisation of a family slot.  If every active term is complex symmetric (M, K, C by construction) or a rank-1
+// flame operator S (x) G, the symmetric part is eliminated LDL^T-style (half of the GEMM work) and the flame terms enter
+// through the Sherman-Morrison-Woodbury formula; otherwise (user matrices, Bloch terms) the general LU is used.
+static void factor_slot(wae_ctx* h, LuSolver& S, Family& F, int slot) {
+  Pattern& U = h->pat(F.pattern);
+  const cplx* A = (const cplx*)F.slot[slot].p;
+  cudaStream_t st = h->stream;
+  const char* env = getenv("WAE_LU_SYM");
+  bool ok = !(env && atoi(env) == 0);
+  const std::vector<double>& cf = F.slot_coeffs[slot];
+  if ((int)cf.size() != 2 * F.n_terms) ok = false;
+  std::vector<int> r1;
+  for (int t = 0; ok && t < F.n_terms; t++) {
+    if (cf[2 * t] == 0.0 && cf[2 * t + 1] == 0.0) continue;
+    Matrix& M = h->mat(F.mats[t]);
+    if (M.rank1) r1.push_back(t);
+    else if (!M.symmetric) ok = false;
+  }
+  if (r1.size() > 8) ok = false;
+  S.r1_k = 0;
+  if (!ok) {
+    wae_lu_factor_device(h, S, A, nullptr, 0);
+    return;
+  }
+  const cplx* Sv = A;
+  const int k = (int)r1.size();
+  if (k) {
+    S.d_Sval.reserve((size_t)U.nnz);
+    CUDA_CHECK(cudaMemcpyAsync(S.d_Sval.p, A, (size_t)U.nnz * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
+    for (int t : r1) wae_axpy_term(h, F, t, -cf[2 * t], -cf[2 * t + 1], S.d_Sval.p);
+    Sv = S.d_Sval.p;
+  }
+  wae_lu_factor_device(h, S, Sv, A, 1);
+  if (!k) return;
+  const int64_t n = S.sym.n;
+  S.d_r1_Sm.reserve((size_t)n * k);
+  S.d_r1_Gm.reserve((size_t)n * k);
+  S.d_r1_Z.reserve((size_t)n * k);
+  S.d_r1_Zt.reserve((size_t)n * k);
+  S.d_r1_Kinv.reserve((size_t)k * k);
+  S.d_r1_KinvT.reserve((size_t)k * k);
+  CUDA_CHECK(cudaMemsetAsync(S.d_r1_Sm.p, 0, (size_t)n * k * sizeof(cplx), st));
+  CUDA_CHECK(cudaMemsetAsync(S.d_r1_Gm.p, 0, (size_t)n * k * sizeof(cplx), st));
+  for (int j = 0; j < k; j++) {
+    Matrix& Q = h->mat(F.mats[r1[j]]);
+    int nr = (int)Q.r1_rows.size(), nc = (int)Q.r1_cols.size();
+    scatter_real_kernel<<<(nr + 255) / 256, 256, 0, st>>>(Q.d_r1_S.p, Q.d_r1_rows.p, nr, S.d_r1_Sm.p + (size_t)j * n);
+    scatter_real_kernel<<<(nc + 255) / 256, 256, 0, st>>>(Q.d_r1_G.p, Q.d_r1_cols.p, nc, S.d_r1_Gm.p + (size_t)j * n);
+    h->launches += 2;
+  }
+  CUDA_CHECK(cudaMemcpyAsync(S.d_r1_Z.p, S.d_r1_Sm.p, (size_t)n * k * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
+  CUDA_CHECK(cudaMemcpyAsync(S.d_r1_Zt.p, S.d_r1_Gm.p, (size_t)n * k * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
+  wae_lu_base_solve(h, S, 0, k, S.d_r1_Z.p);   // Z  = S^-1 Sm
+  wae_lu_base_solve(h, S, 0, k, S.d_r1_Zt.p);  // Zt = S^-1 Gm  (S symmetric: S^-T = S^-1)
+  // K = F^-1 + Gm^T Z  (k x k), inverted on the host
+  S.d_arn_dots.reserve(2 * (size_t)k * k + 64);
+  CUDA_CHECK(cudaMemsetAsync(S.d_arn_dots.p, 0, 2 * (size_t)k * k * sizeof(double), st));
+  int chunks = (int)std::min<int64_t>((n + 255) / 256, 64);
+  r1_gram_kernel<<<dim3(chunks, k, k), 256, 0, st>>>(S.d_r1_Gm.p, n, k, S.d_r1_Z.p, S.d_arn_dots.p);
+  h->launches++;
+  std::vector<zc> K((size_t)k * k), Kinv((size_t)k * k, 0.0), KinvT((size_t)k * k);
+  CUDA_CHECK(cudaMemcpyAsync(K.data(), S.d_arn_dots.p, 2 * (size_t)k * k * sizeof(double), cudaMemcpyDeviceToHost, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  for (int j = 0; j < k; j++) K[j + (size_t)k * j] += 1.0 / zc(cf[2 * r1[j]], cf[2 * r1[j] + 1]);
+  // Gauss-Jordan with partial pivoting (column-major k x k)
+  for (int j = 0; j < k; j++) Kinv[j + (size_t)k * j] = 1.0;
+  for (int c = 0; c < k; c++) {
+    int piv = c;
+    for (int r = c + 1; r < k; r++)
+      if (std::abs(K[r + (size_t)k * c]) > std::abs(K[piv + (size_t)k * c])) piv = r;
+    if (std::abs(K[piv + (size_t)k * c]) == 0.0) WAE_THROW(WAE_E_SINGULAR, "singular capacitance matrix in the rank-%d update", k);
+    for (int q = 0; q < k; q++) {
+      std::swap(K[c + (size_t)k * q], K[piv + (size_t)k * q]);
+      std::swap(Kinv[c + (size_t)k * q], Kinv[piv + (size_t)k * q]);
+    }
+    zc d = 1.0 / K[c + (size_t)k * c];
+    for (int q = 0; q < k; q++) {
+      K[c + (size_t)k * q] *= d;
+      Kinv[c + (size_t)k * q] *= d;
+    }
+    for (int r = 0; r < k; r++) {
+      if (r == c) continue;
+      zc f = K[r + (size_t)k * c];
+      for (int q = 0; q < k; q++) {
+        K[r + (size_t)k * q] -= f * K[c + (size_t)k * q];
+        Kinv[r + (size_t)k * q] -= f * Kinv[c + (size_t)k * q];
+      }
+    }
+  }
+  for (int a = 0; a < k; a++)
+    for (int b = 0; b < k; b++) KinvT[a + (size_t)k * b] = Kinv[b + (size_t)k * a];
+  CUDA_CHECK(cudaMemcpyAsync(S.d_r1_Kinv.p, Kinv.data(), (size_t)k * k * sizeof(zc), cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaMemcpyAsync(S.d_r1_KinvT.p, KinvT.data(), (size_t)k * k * sizeof(zc), cudaMemcpyHostToDevice, st));
+  CUDA_CHECK(cudaStreamSynchronize(st));
+  S.r1_k = k;
+}
+
 struct ArnoldiWork {
   DevBuf<cplx> V, w, t, c;
   DevBuf<double> dots;
@@ -298,8 +421,9 @@ int32_t wae_lu_factor(wae_ctx* h, int32_t lu_id, int32_t slot) {
   Family& F = h->fam(S.fam);
   if (slot < 0 || slot >= WAE_FAMILY_SLOTS || !F.slot[slot].p) WAE_THROW(WAE_E_INVALID, "family slot %d is empty", slot);
   PhaseTimer t(h, "factor");
-  wae_lu_factor_device(h, S, (const cplx*)F.slot[slot].p);
+  factor_slot(h, S, F, slot);
   t.stop();
+  h->last_ms["factor_sym"] = S.sym_mode ? 1.0 : 0.0;
   WAE_API_END
 }
 
@@ -467,7 +591,7 @@ int32_t wae_beyn_moments(wae_ctx* h, int32_t fam_id, int32_t lu_id, int32_t n_no
     wae_combine_device(h, F, coeffs + 2 * (size_t)j * F.n_terms, slot);
     {
       PhaseTimer t(h, "factor");
-      wae_lu_factor_device(h, S, (const cplx*)F.slot[slot].p);
+      factor_slot(h, S, F, slot);
       t.stop();
       t_fac += h->last_ms["factor"];
     }

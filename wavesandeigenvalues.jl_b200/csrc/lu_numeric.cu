@@ -85,8 +85,10 @@ __global__ void lu_scatter_kernel(const cplx* __restrict__ A, const int64_t* __r
 
 // ---- extend-add: child update matrices into the parent fronts ------------------------------------
 // grid.x = tiles over all children of the level (tile_ptr prefix), block 32x8
+// sym != 0: the update matrices hold their lower triangle only (x >= y); upper entries are read from the mirror position
+// and only the lower part of the parent front is written (its U^T panel is regenerated from the L panel).
 __global__ void __launch_bounds__(256) lu_extend_add_kernel(LuDev D, const int32_t* __restrict__ children, const int32_t* __restrict__ tile_ptr,
-                                                            int nchild, const cplx* __restrict__ upd_child, cplx* __restrict__ upd_parent) {
+                                                            int nchild, const cplx* __restrict__ upd_child, cplx* __restrict__ upd_parent, int sym) {
   // locate the child of this tile
   int t = blockIdx.x;
   int lo = 0, hi = nchild;
@@ -111,16 +113,22 @@ __global__ void __launch_bounds__(256) lu_extend_add_kernel(LuDev D, const int32
   for (int yy = threadIdx.y; yy < 32; yy += 8) {
     int y = tj * 32 + yy;
     if (y >= rc) break;
-    cplx v = U[x + (size_t)y * rc];
     int jb = rel[y];
     cplx* dst;
     if (jb < P.s) {
       if (ia >= P.s || ia / NB >= jb / NB) dst = P.lp + ia + (size_t)jb * P.ld;
+      else if (sym) continue;
       else dst = P.up + jb + (size_t)ia * P.ld;
     } else {
-      if (ia < P.s) dst = P.up + jb + (size_t)ia * P.ld;
-      else dst = A22 + (ia - P.s) + (size_t)(jb - P.s) * P.r;
+      if (ia < P.s) {
+        if (sym) continue;
+        dst = P.up + jb + (size_t)ia * P.ld;
+      } else {
+        if (sym && ia < jb) continue;
+        dst = A22 + (ia - P.s) + (size_t)(jb - P.s) * P.r;
+      }
     }
+    cplx v = (sym && x < y) ? U[y + (size_t)x * rc] : U[x + (size_t)y * rc];
     atomicAdd(&dst->x, v.x);
     atomicAdd(&dst->y, v.y);
   }
@@ -191,6 +199,21 @@ __global__ void __launch_bounds__(NB * NB) lu_diag_kernel(LuDev D, const int32_t
 // ---- step k, part 2: panel solves below the diagonal block -------------------------------------------
 //   Lp rows:  X <- X * U_kk^{-1}        Up rows:  X <- X * L_kk^{-T}  (unit diagonal)
 // one thread per row, the NB row entries live in registers, the triangular factor in shared memory
+// sym != 0 (complex-symmetric front, F[k,J]^T == F[J,k]): launched with grid.y == 2 as well, but the U^T-panel rows are
+// computed from the (not yet solved) L-panel row copy that the symmetric copy kernel placed there.
+__global__ void __launch_bounds__(128) lu_sym_copy_kernel(LuDev D, const int32_t* __restrict__ list, int k) {
+  SnView S = sn_view(D, list[blockIdx.z]);
+  const int c0 = k * NB;
+  if (c0 >= S.s) return;
+  const int nb = min(NB, S.s - c0);
+  const int r0 = c0 + nb;
+  const int row = blockIdx.x * 128 + threadIdx.x;
+  if (row >= S.ld - r0) return;
+  const cplx* src = S.lp + (r0 + row) + (size_t)c0 * S.ld;
+  cplx* dst = S.up + (r0 + row) + (size_t)c0 * S.ld;
+  for (int j = 0; j < nb; j++) dst[(size_t)j * S.ld] = src[(size_t)j * S.ld];
+}
+
 __global__ void __launch_bounds__(128) lu_panel_kernel(LuDev D, const int32_t* __restrict__ list, int k) {
   SnView S = sn_view(D, list[blockIdx.z]);
   const int c0 = k * NB;
@@ -319,12 +342,13 @@ __device__ __forceinline__ void zgemm_nt_tile(const GemmProblem& P, int tile_m, 
 // Two-level blocking: inside an outer block of NBO columns the NB-wide steps only touch the columns of that outer block
 // (kw = NB, cap = end of the outer block); the rest of the pivot block is updated once per outer block with kw = NBO.
 __global__ void __launch_bounds__(256) lu_gemm_kernel(LuDev D, const int32_t* __restrict__ list, int mode, int k0, int kw, int c0, int cap,
-                                                      cplx* __restrict__ upd) {
+                                                      cplx* __restrict__ upd, int sym) {
   const int sn = list[blockIdx.z];
   SnView S = sn_view(D, sn);
   GemmProblem P;
   if (mode == 2) {
     if (S.r == 0) return;
+    if (sym && blockIdx.y > blockIdx.x) return;  // symmetric Schur complement: lower tiles only
     P.m = P.n = S.r; P.K = S.s;
     P.lda = P.ldb = S.ld; P.ldc = S.r;
     P.A = S.lp + S.s; P.B = S.up + S.s;
@@ -619,13 +643,14 @@ void wae_lu_setup_device(wae_ctx* h, LuSolver& S) {
   std::vector<int64_t>().swap(Y.amap);  // large and only needed on the device
 }
 
-void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval) {
+void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cplx* d_full, int sym) {
   LuSymbolic& Y = S.sym;
   cudaStream_t st = h->stream;
   Family& F = h->fam(S.fam);
   Pattern& U = h->pat(F.pattern);
   wae_family_ensure_csr(h, F);
-  CUDA_CHECK(cudaMemcpyAsync(S.d_Aval.p, d_Aval, (size_t)U.nnz * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
+  CUDA_CHECK(cudaMemcpyAsync(S.d_Aval.p, d_full ? d_full : d_Aval, (size_t)U.nnz * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
+  S.sym_mode = sym != 0;
   LuDev D = make_dev(S);
   CUDA_CHECK(cudaMemsetAsync(S.d_fac.p, 0, (size_t)Y.fac_size * sizeof(cplx), st));
   CUDA_CHECK(cudaMemsetAsync(S.d_flag.p, 0, 2 * sizeof(int32_t), st));
@@ -642,7 +667,7 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval) {
     if (Y.level_upd_size[d]) CUDA_CHECK(cudaMemsetAsync(upd, 0, (size_t)Y.level_upd_size[d] * sizeof(cplx), st));
     if (d < maxd && S.xa_tiles[d + 1] > 0) {
       lu_extend_add_kernel<<<S.xa_tiles[d + 1], dim3(32, 8), 0, st>>>(D, S.d_level[d + 1].p, S.d_xa_tile_ptr[d + 1].p,
-                                                                        (int)Y.levels[d + 1].size(), S.d_upd[(d + 1) & 1].p, upd);
+                                                                        (int)Y.levels[d + 1].size(), S.d_upd[(d + 1) & 1].p, upd, sym);
       h->launches++;
     }
     // blocked partial factorisation of all fronts of this depth
@@ -665,6 +690,10 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval) {
         lu_diag_kernel<<<zc, dim3(NB, NB), 0, st>>>(D, lst, k, S.pivot_eps, S.d_flag.p);
         int rows = max_ld - k * NB - 1;  // upper bound of ld - (c0 + nb) over the batch (nb >= 1)
         if (rows > 0) {
+          if (sym) {
+            lu_sym_copy_kernel<<<dim3((rows + 127) / 128, 1, zc), 128, 0, st>>>(D, lst, k);
+            h->launches++;
+          }
           lu_panel_kernel<<<dim3((rows + 127) / 128, 2, zc), 128, 0, st>>>(D, lst, k);
           // inner update: columns of the current outer block only
           const int c0 = (k + 1) * NB;
@@ -672,17 +701,17 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval) {
           int tn = std::min(max_s, oend) - c0;
           if (tn > 0) {
             dim3 g((max_ld - c0 + GT - 1) / GT, (tn + GT - 1) / GT, zc);
-            lu_gemm_kernel<<<g, 256, 0, st>>>(D, lst, 0, k * NB, NB, c0, oend, nullptr);
-            lu_gemm_kernel<<<g, 256, 0, st>>>(D, lst, 1, k * NB, NB, c0, oend, nullptr);
-            h->launches += 2;
+            lu_gemm_kernel<<<g, 256, 0, st>>>(D, lst, 0, k * NB, NB, c0, oend, nullptr, sym);
+            if (!sym) lu_gemm_kernel<<<g, 256, 0, st>>>(D, lst, 1, k * NB, NB, c0, oend, nullptr, sym);
+            h->launches += sym ? 1 : 2;
           }
           // outer update once the outer block is complete
           if (c0 == oend && max_s > oend) {
             const int o0 = oend - nbo_blocks * NB;
             dim3 g((max_ld - oend + GT - 1) / GT, (max_s - oend + GT - 1) / GT, zc);
-            lu_gemm_kernel<<<g, 256, 0, st>>>(D, lst, 0, o0, oend - o0, oend, 1 << 30, nullptr);
-            lu_gemm_kernel<<<g, 256, 0, st>>>(D, lst, 1, o0, oend - o0, oend, 1 << 30, nullptr);
-            h->launches += 2;
+            lu_gemm_kernel<<<g, 256, 0, st>>>(D, lst, 0, o0, oend - o0, oend, 1 << 30, nullptr, sym);
+            if (!sym) lu_gemm_kernel<<<g, 256, 0, st>>>(D, lst, 1, o0, oend - o0, oend, 1 << 30, nullptr, sym);
+            h->launches += sym ? 1 : 2;
           }
           h->launches++;
         }
@@ -693,7 +722,7 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval) {
       for (int z0 = 0; z0 < nl; z0 += 32768) {
         int zc = std::min(32768, nl - z0);
         dim3 g((max_r + GT - 1) / GT, (max_r + GT - 1) / GT, zc);
-        lu_gemm_kernel<<<g, 256, 0, st>>>(D, S.d_level[d].p + z0, 2, 0, 0, 0, 0, upd);
+        lu_gemm_kernel<<<g, 256, 0, st>>>(D, S.d_level[d].p + z0, 2, 0, 0, 0, 0, upd, sym);
         h->launches++;
       }
     }
@@ -749,36 +778,118 @@ static void lu_sweeps(wae_ctx* h, LuSolver& S, int trans_t, int nrhs, cplx* y) {
   }
 }
 
-void wae_lu_solve_device(wae_ctx* h, LuSolver& S, int trans, int nrhs, cplx* d_X, int refine) {
-  Family& F = h->fam(S.fam);
-  if (!S.factored) WAE_THROW(WAE_E_INVALID, "wae_lu_factor has not been called (or failed)");
-  LuSymbolic& Y = S.sym;
+// ---- rank-k (Sherman-Morrison-Woodbury) correction on top of the symmetric factorisation ------------------------------
+//   A = S + Sm F Gm^T :  A^-1 b = y - Z  (F^-1 + Gm^T Z )^-1 Gm^T y,   y = S^-1 b, Z  = S^-1 Sm
+//   A^T                : A^-T b = y - Zt (F^-1 + Sm^T Zt)^-1 Sm^T y,   Zt = S^-1 Gm
+// t[j + k*r] += sum_p W[p + n*j] * X[p + n*r]   (plain transpose, no conjugation); grid (chunks, k, nrhs)
+__global__ void __launch_bounds__(256) r1_dots_kernel(const cplx* __restrict__ W, int64_t n, int k, const cplx* __restrict__ X, cplx* __restrict__ t) {
+  const cplx* w = W + (size_t)blockIdx.y * n;
+  const cplx* x = X + (size_t)blockIdx.z * n;
+  double sr = 0.0, si = 0.0;
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < n; p += (int64_t)gridDim.x * blockDim.x) {
+    cplx a = w[p], b = x[p];
+    sr += a.x * b.x - a.y * b.y;
+    si += a.x * b.y + a.y * b.x;
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) {
+    sr += __shfl_xor_sync(0xffffffffu, sr, off);
+    si += __shfl_xor_sync(0xffffffffu, si, off);
+  }
+  if ((threadIdx.x & 31) == 0 && (sr != 0.0 || si != 0.0)) {
+    cplx* d = t + blockIdx.y + (size_t)k * blockIdx.z;
+    atomicAdd(&d->x, sr);
+    atomicAdd(&d->y, si);
+  }
+}
+// X[:, r] -= Zx * (Kinv * t[:, r])
+__global__ void r1_apply_kernel(const cplx* __restrict__ Zx, const cplx* __restrict__ Kinv, const cplx* __restrict__ t, int64_t n, int k,
+                                int nrhs, cplx* __restrict__ X) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n) return;
+  for (int r = 0; r < nrhs; r++) {
+    cplx acc = X[p + (size_t)r * n];
+    for (int j = 0; j < k; j++) {
+      cplx c = make_double2(0.0, 0.0);
+      for (int i = 0; i < k; i++) {
+        cplx m = Kinv[j + i * k], ti = t[i + (size_t)k * r];
+        c.x += m.x * ti.x - m.y * ti.y;
+        c.y += m.x * ti.y + m.y * ti.x;
+      }
+      cplx z = Zx[p + (size_t)j * n];
+      acc.x -= z.x * c.x - z.y * c.y;
+      acc.y -= z.x * c.y + z.y * c.x;
+    }
+    X[p + (size_t)r * n] = acc;
+  }
+}
+__global__ void conj_kernel(int64_t total, cplx* __restrict__ x) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) x[i].y = -x[i].y;
+}
+__global__ void add_kernel(const cplx* __restrict__ a, int64_t total, cplx* __restrict__ x) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < total) x[i] = make_double2(x[i].x + a[i].x, x[i].y + a[i].y);
+}
+
+// X <- (LU)^-1 X or (LU)^-T X in the original ordering (factors only: no rank-k correction, no refinement)
+void wae_lu_base_solve(wae_ctx* h, LuSolver& S, int tt, int nrhs, cplx* d_X) {
+  const int64_t n = S.sym.n;
   cudaStream_t st = h->stream;
-  const int64_t n = Y.n;
   if (S.work_nrhs < nrhs) {
     S.d_work.alloc((size_t)3 * n * nrhs);
     S.work_nrhs = nrhs;
   }
-  cplx* y = S.d_work.p;                       // permuted work vector
+  cplx* y = S.d_work.p;
+  unsigned gb = (unsigned)((n + 255) / 256);
+  lu_permute_in_kernel<<<gb, 256, 0, st>>>(d_X, S.d_perm.p, S.d_scale.p, n, nrhs, 0, y);
+  lu_sweeps(h, S, tt, nrhs, y);
+  lu_permute_out_kernel<<<gb, 256, 0, st>>>(y, S.d_perm.p, S.d_scale.p, n, nrhs, 0, 0, d_X);
+  h->launches += 2;
+}
+
+// X <- op(A)^-1 X with the rank-k correction (trans: 0 N, 1 T, 2 C)
+static void lu_apply_inverse(wae_ctx* h, LuSolver& S, int trans, int nrhs, cplx* d_X) {
+  const int64_t n = S.sym.n;
+  cudaStream_t st = h->stream;
+  const unsigned gt = (unsigned)(((size_t)n * nrhs + 255) / 256);
+  if (trans == 2) conj_kernel<<<gt, 256, 0, st>>>(n * nrhs, d_X);  // A^H x = b  <=>  A^T conj(x) = conj(b)
+  const int tt = trans != 0;
+  wae_lu_base_solve(h, S, tt, nrhs, d_X);
+  if (S.r1_k > 0) {
+    const int k = S.r1_k;
+    S.d_r1_t.reserve((size_t)k * nrhs);
+    CUDA_CHECK(cudaMemsetAsync(S.d_r1_t.p, 0, (size_t)k * nrhs * sizeof(cplx), st));
+    int chunks = (int)std::min<int64_t>((n + 255) / 256, 64);
+    r1_dots_kernel<<<dim3(chunks, k, nrhs), 256, 0, st>>>(tt ? S.d_r1_Sm.p : S.d_r1_Gm.p, n, k, d_X, S.d_r1_t.p);
+    r1_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(tt ? S.d_r1_Zt.p : S.d_r1_Z.p, tt ? S.d_r1_KinvT.p : S.d_r1_Kinv.p, S.d_r1_t.p,
+                                                                 n, k, nrhs, d_X);
+    h->launches += 2;
+  }
+  if (trans == 2) conj_kernel<<<gt, 256, 0, st>>>(n * nrhs, d_X);
+}
+
+void wae_lu_solve_device(wae_ctx* h, LuSolver& S, int trans, int nrhs, cplx* d_X, int refine) {
+  Family& F = h->fam(S.fam);
+  if (!S.factored) WAE_THROW(WAE_E_INVALID, "wae_lu_factor has not been called (or failed)");
+  const int64_t n = S.sym.n;
+  cudaStream_t st = h->stream;
+  if (S.work_nrhs < nrhs) {
+    S.d_work.alloc((size_t)3 * n * nrhs);
+    S.work_nrhs = nrhs;
+  }
   cplx* b0 = S.d_work.p + (size_t)n * nrhs;   // copy of the right-hand side
   cplx* res = S.d_work.p + (size_t)2 * n * nrhs;
-  const int conj = trans == 2;
-  const int tt = trans != 0;
-  unsigned gb = (unsigned)((n + 255) / 256);
+  const unsigned gt = (unsigned)(((size_t)n * nrhs + 255) / 256);
   if (refine > 0) CUDA_CHECK(cudaMemcpyAsync(b0, d_X, (size_t)n * nrhs * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
-  // A^H x = b  <=>  A^T conj(x) = conj(b)
-  lu_permute_in_kernel<<<gb, 256, 0, st>>>(d_X, S.d_perm.p, S.d_scale.p, n, nrhs, conj, y);
-  lu_sweeps(h, S, tt, nrhs, y);
-  lu_permute_out_kernel<<<gb, 256, 0, st>>>(y, S.d_perm.p, S.d_scale.p, n, nrhs, conj, 0, d_X);
-  h->launches += 2;
+  lu_apply_inverse(h, S, trans, nrhs, d_X);
   for (int it = 0; it < refine; it++) {
     // res = b - op(A) x ; x += op(A)^{-1} res
     wae_spmm_values(h, F, S.d_Aval.p, trans, nrhs, d_X, res);
-    lu_residual_kernel<<<(unsigned)(((size_t)n * nrhs + 255) / 256), 256, 0, st>>>(b0, n * nrhs, res);
-    lu_permute_in_kernel<<<gb, 256, 0, st>>>(res, S.d_perm.p, S.d_scale.p, n, nrhs, conj, y);
-    lu_sweeps(h, S, tt, nrhs, y);
-    lu_permute_out_kernel<<<gb, 256, 0, st>>>(y, S.d_perm.p, S.d_scale.p, n, nrhs, conj, 1, d_X);
-    h->launches += 3;
+    lu_residual_kernel<<<gt, 256, 0, st>>>(b0, n * nrhs, res);
+    lu_apply_inverse(h, S, trans, nrhs, res);
+    add_kernel<<<gt, 256, 0, st>>>(res, n * nrhs, d_X);
+    h->launches += 2;
   }
   CUDA_CHECK(cudaGetLastError());
 }

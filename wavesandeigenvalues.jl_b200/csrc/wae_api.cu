@@ -247,6 +247,7 @@ int32_t wae_assemble(wae_ctx* h, int32_t pattern_id, int32_t kind, const double*
   } else
     wae_launch_assemble_atomic(h, P, 0, d_c.p, c_per_elem, scale, M.d_val.p, nullptr);
   t.stop();
+  M.symmetric = true;  // int phi_i phi_j, int grad phi_i . grad phi_j and the boundary mass are symmetric by construction
   if (mat_id) *mat_id = id;
   WAE_API_END
 }
@@ -272,6 +273,7 @@ int32_t wae_assemble_mk(wae_ctx* h, int32_t pattern_id, const double* c, int32_t
     wae_launch_assemble_atomic(h, P, 3, d_c.p, c_per_elem, 1.0, h->mats[im]->d_val.p, h->mats[ik]->d_val.p);
     t.stop();
   }
+  h->mats[im]->symmetric = h->mats[ik]->symmetric = true;
   if (mass_id) *mass_id = im;
   if (stiff_id) *stiff_id = ik;
   WAE_API_END
@@ -334,6 +336,25 @@ int32_t wae_assemble_flame(wae_ctx* h, int64_t n_flame, const int64_t* flame_tet
   wae_launch_flame(h, d_ft.p, n_flame, d_rowpos.p, d_S.p, d_S.p + nr, ref_tet, x_ref, n_ref, -nlocal, d_G.p, d_colsrc.p, nr,
                    nloc, h->mats[mid]->d_val.p);
   t.stop();
+  {  // keep the rank-1 factors: Q = S (x) G
+    Matrix& Q = *h->mats[mid];
+    Q.rank1 = true;
+    Q.r1_rows = urows;
+    Q.r1_cols.resize(nloc);
+    for (int c = 0; c < nloc; c++) Q.r1_cols[c] = cols[c].first;
+    Q.d_r1_rows.upload(Q.r1_rows, h->stream);
+    Q.d_r1_cols.upload(Q.r1_cols, h->stream);
+    Q.d_r1_S.reserve(nr);
+    Q.d_r1_G.reserve(nloc);
+    CUDA_CHECK(cudaMemcpyAsync(Q.d_r1_S.p, d_S.p, nr * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    // G in the order of the sorted columns
+    std::vector<double> Gh(nloc), Gs(nloc);
+    CUDA_CHECK(cudaMemcpyAsync(Gh.data(), d_G.p, nloc * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+    for (int c = 0; c < nloc; c++) Gs[c] = Gh[colsrc[c]];
+    Q.d_r1_G.upload(Gs, h->stream);
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  }
   if (pattern_id) *pattern_id = pid;
   if (mat_id) *mat_id = mid;
   if (nnz) *nnz = P.nnz;
@@ -390,6 +411,21 @@ int32_t wae_mat_set(wae_ctx* h, int64_t dim, const int64_t* colptr, const int64_
     }
   upload_pattern(h, P);
   int mid = new_matrix(h, pid, true, P.nnz);
+  {  // exact (bitwise) complex symmetry check A(i,j) == A(j,i)
+    bool sym = true;
+    for (int64_t j = 0; j < dim && sym; j++)
+      for (int64_t k = P.colptr[j]; k < P.colptr[j + 1]; k++) {
+        int32_t i = P.rowval[k];
+        if (i == j) continue;
+        const int32_t* b = P.rowval.data() + P.colptr[i];
+        const int32_t* e = P.rowval.data() + P.colptr[i + 1];
+        const int32_t* it = std::lower_bound(b, e, (int32_t)j);
+        if (it == e || *it != j) { sym = false; break; }
+        int64_t q = it - P.rowval.data();
+        if (nzval[2 * k] != nzval[2 * q] || nzval[2 * k + 1] != nzval[2 * q + 1]) { sym = false; break; }
+      }
+    h->mats[mid]->symmetric = sym;
+  }
   CUDA_CHECK(cudaMemcpyAsync(h->mats[mid]->d_val.p, nzval, 2 * P.nnz * sizeof(double), cudaMemcpyHostToDevice, h->stream));
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
   if (pattern_id) *pattern_id = pid;

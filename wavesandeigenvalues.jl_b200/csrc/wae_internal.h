@@ -100,6 +100,13 @@ struct Matrix {
   int pattern = -1;
   bool is_complex = false;
   DevBuf<double> d_val;  // nnz (real) or 2*nnz (complex, interleaved)
+  // structure hints for the solver: complex-symmetric operators (M, K, C by construction) allow an LDL^T-type
+  // factorisation; a flame operator is the rank-1 matrix S (x) G and is handled by the Sherman-Morrison-Woodbury formula
+  bool symmetric = false;
+  bool rank1 = false;
+  DevBuf<double> d_r1_S, d_r1_G;          // rank-1 factors (real): S over r1_rows, G over r1_cols
+  std::vector<int32_t> r1_rows, r1_cols;  // DOF ids (cols in the order of d_r1_G)
+  DevBuf<int32_t> d_r1_rows, d_r1_cols;
 };
 
 struct Family {
@@ -109,6 +116,7 @@ struct Family {
   std::vector<bool> identity;              // term pattern == union pattern
   std::vector<DevBuf<int32_t>> d_map;      // term nz -> union nz (empty if identity)
   DevBuf<double> slot[WAE_FAMILY_SLOTS];   // complex values, 2*nnz doubles each
+  std::vector<double> slot_coeffs[WAE_FAMILY_SLOTS];  // term coefficients of the last wae_combine into each slot
   DevBuf<double> d_io[2];                  // cached staging buffers of wae_family_spmm (grow-only)
   DevBuf<int32_t> d_tr_perm;               // CSC->CSR permutation for transposed SpMM (lazy)
   DevBuf<int64_t> d_rowptr;
@@ -193,3 +201,4 @@ void wae_combine_device(wae_ctx* h, Family& F, const double* coeffs_host, int sl
 void wae_spmm_device(wae_ctx* h, Family& F, int slot, int trans, int nrhs, const cplx* X, cplx* Y);
 void wae_spmm_values(wae_ctx* h, Family& F, const cplx* val, int trans, int nrhs, const cplx* X, cplx* Y);
 void wae_family_ensure_csr(wae_ctx* h, Family& F);
+void wae_axpy_term(wae_ctx* h, Family& F, int t, double cr, double ci, cplx* out);
