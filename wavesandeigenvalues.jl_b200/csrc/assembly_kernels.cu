@@ -277,29 +277,45 @@ struct SymTab<10> {
   __device__ static void stiff(const double* g, double* K) { wae_p2_tet_stiff_sym(g, K); }
 };
 
+// Shared-memory staging layout: 64 doubles per staged element (NSYM stiffness entries, |det| at logical index 63), XOR-swizzled
+// with the element index so that lanes reading the same logical entry of different elements hit different banks:
+//   physical index of (element t, entry e) = t*64 + (e ^ (t & 63)).   A source code is t*64 + e, so the address of the
+// stiffness entry is one LOP3 away from the code and the |det| entry is (code | 63) ^ (t & 63).  Element index WAE_GATHER_PAD
+// is a block of zeros: padding sources point there, which removes every branch from the inner loop.
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+  double v;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));  // not volatile: smem is read-only after the barrier
+  return v;
+}
+
 template <int NLOC>
-__global__ void __launch_bounds__(512) assemble_tet_gather(
+__global__ void __launch_bounds__(512, 2) assemble_tet_gather(
     const double* __restrict__ xyz, const uint32_t* __restrict__ conn, const int32_t* __restrict__ elems,
-    const double* __restrict__ c, const int64_t* __restrict__ patch_row_ptr, const int64_t* __restrict__ patch_tet_ptr,
-    const int32_t* __restrict__ patch_rows, const int32_t* __restrict__ patch_tets, const int64_t* __restrict__ col_slot_ptr,
-    const int64_t* __restrict__ col_src_ptr, const uint8_t* __restrict__ slot_cnt, const uint16_t* __restrict__ src,
-    const int64_t* __restrict__ colptr, double mass_scale, double* __restrict__ out_m, double* __restrict__ out_k) {
+    const double* __restrict__ c, const int64_t* __restrict__ patch_tet_ptr, const int32_t* __restrict__ patch_tets,
+    const int64_t* __restrict__ patch_grp_ptr, const int64_t* __restrict__ patch_src_ptr, const uint32_t* __restrict__ grp,
+    const int32_t* __restrict__ out_idx, const uint16_t* __restrict__ src, int pad_elem, double mass_scale, double* __restrict__ out_m,
+    double* __restrict__ out_k, int dbg) {
   constexpr int NSYM = SymTab<NLOC>::NSYM;
-  constexpr int STRIDE = NSYM + 1;
+  constexpr int SL = NLOC == 4 ? 4 : 6;     // log2 of the staging stride (16 / 64 doubles per element)
+  constexpr unsigned SM_ = (1u << SL) - 1;  // mask of the entry index; |det| lives at logical entry SM_
   extern __shared__ double sm[];
   __shared__ double s_mass[NSYM];
+  __shared__ int s_next;
   const int p = blockIdx.x;
   const int64_t t0 = patch_tet_ptr[p];
   const int nt = (int)(patch_tet_ptr[p + 1] - t0);
   if (threadIdx.x < NSYM) s_mass[threadIdx.x] = SymTab<NLOC>::mass()[threadIdx.x] * mass_scale;
-  // phase A
-  for (int t = threadIdx.x; t < nt; t += blockDim.x) {
+  if (threadIdx.x == 0) s_next = blockDim.x >> 5;
+  if (threadIdx.x <= SM_) sm[(pad_elem << SL) + threadIdx.x] = 0.0;
+  // phase A: one staged element per thread
+  for (int t = threadIdx.x; t < nt && dbg != 2; t += blockDim.x) {
     int32_t e = patch_tets[t0 + t];
     const uint32_t* d = conn + (size_t)elems[e] * NLOC;
     uint32_t v[4] = {d[0], d[1], d[2], d[3]};
     TetGeom tg;
     tet_geom(xyz, v, tg);
-    double* dst = sm + (size_t)t * STRIDE;
+    double* dst = sm + ((size_t)t << SL);
+    const int sw = t & SM_;
     if (out_k) {
       double cc = c[e];
       double g[10];
@@ -307,47 +323,61 @@ __global__ void __launch_bounds__(512) assemble_tet_gather(
       double K[NSYM];
       SymTab<NLOC>::stiff(g, K);
 #pragma unroll
-      for (int k = 0; k < NSYM; k++) dst[k] = K[k];
+      for (int k = 0; k < NSYM; k++) dst[k ^ sw] = K[k];
     }
-    dst[NSYM] = tg.adet;
+    dst[SM_ ^ sw] = tg.adet;
   }
   __syncthreads();
-  // phase B
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
-  const int64_t r0 = patch_row_ptr[p], r1 = patch_row_ptr[p + 1];
-  for (int64_t r = r0 + warp; r < r1; r += nwarp) {
-    const int32_t col = patch_rows[r];
-    const int64_t o0 = colptr[col];
-    const int len = (int)(colptr[col + 1] - o0);
-    const uint8_t* cnts = slot_cnt + col_slot_ptr[r];
-    const uint16_t* sp = src + col_src_ptr[r];
-    int base = 0;
-    for (int s0 = 0; s0 < len; s0 += 32) {
-      int s = s0 + lane;
-      int cnt = s < len ? (int)cnts[s] : 0;
-      int pre = cnt;  // inclusive warp scan
+  if (dbg == 1) return;
+  // phase B: one group of WAE_GATHER_GROUP owned nonzeros per warp iteration (GS/32 per lane); the
+  // nonzeros of a patch are sorted by source count, so all lanes run (almost) the same trip count, branch-free
+  const int lane = threadIdx.x & 31;
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sm);
+  const int g0 = (int)patch_grp_ptr[p], ng = (int)(patch_grp_ptr[p + 1] - patch_grp_ptr[p]);
+  const uint16_t* psrc = src + patch_src_ptr[p] + lane;
+  constexpr int GS = WAE_GATHER_GROUP;
+  int g = threadIdx.x >> 5;
+  while (g < ng) {
+    const uint32_t hdr = grp[g0 + g];
+    const int niter = hdr & 255;
+    const uint16_t* sp = psrc + (hdr >> 8);
+    const int32_t* op = out_idx + (size_t)(g0 + g) * GS + lane;
+    constexpr int NJ = GS / 32;  // nonzeros per lane and group
+    int oi[NJ];
 #pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        int y = __shfl_up_sync(0xffffffffu, pre, off);
-        if (lane >= off) pre += y;
-      }
-      int total = __shfl_sync(0xffffffffu, pre, 31);
-      const uint16_t* my = sp + base + pre - cnt;
-      double ak = 0.0, ad = 0.0;
-      int sym = 0;
-      for (int k = 0; k < cnt; k++) {
-        unsigned code = my[k];
-        sym = code & 63;
-        const double* q = sm + (size_t)(code >> 6) * STRIDE;
-        if (out_k) ak += q[sym];
-        ad += q[NSYM];
-      }
-      if (s < len) {
-        if (out_k) out_k[o0 + s] = ak;
-        if (out_m) out_m[o0 + s] = cnt ? s_mass[sym] * ad : 0.0;
-      }
-      base += total;
+    for (int j = 0; j < NJ; j++) oi[j] = op[j * 32];
+    double ak[NJ], ad[NJ];
+    unsigned first[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      ak[j] = ad[j] = 0.0;
+      first[j] = niter ? sp[j * 32] : 0u;
     }
+#pragma unroll 4
+    for (int k = 0; k < niter; k++) {
+      unsigned cd[NJ];
+#pragma unroll
+      for (int j = 0; j < NJ; j++) cd[j] = sp[k * GS + j * 32];
+#pragma unroll
+      for (int j = 0; j < NJ; j++) {
+        const unsigned sw = (cd[j] >> SL) & SM_;
+        if (out_k) ak[j] += lds_f64(sbase + ((cd[j] ^ sw) << 3));
+        ad[j] += lds_f64(sbase + (((cd[j] | SM_) ^ sw) << 3));
+      }
+    }
+    if (dbg == 3) {  // timing experiment: no scattered stores (one dependent store per lane and group keeps the work alive)
+      double z = 0.0;
+      for (int j = 0; j < NJ; j++) z += ak[j] + ad[j];
+      if (z == 1.2345e-300 && out_k) out_k[oi[0] & 1023] = z;
+    } else
+#pragma unroll
+    for (int j = 0; j < NJ; j++)
+      if (oi[j] >= 0) {
+        if (out_k) out_k[oi[j]] = ak[j];
+        if (out_m) out_m[oi[j]] = s_mass[first[j] & SM_] * ad[j];
+      }
+    if (lane == 0) g = atomicAdd(&s_next, 1);
+    g = __shfl_sync(0xffffffffu, g, 0);
   }
 }
 
@@ -355,24 +385,25 @@ void wae_launch_assemble_gather(wae_ctx* h, Pattern& P, const double* d_c, doubl
   auto& G = P.gather;
   if (!G.built || G.n_patch == 0) return;
   const int nsym = h->nloc == 4 ? 10 : 55;
-  size_t smem = (size_t)G.max_tets * (nsym + 1) * sizeof(double);
+  size_t smem = (size_t)(G.max_tets + 1) * (h->nloc == 4 ? 16 : 64) * sizeof(double);  // +1: the zero block the padding sources point to
   static bool attr_set[2] = {false, false};
+  const int dbg = getenv("WAE_GATHER_DBG") ? atoi(getenv("WAE_GATHER_DBG")) : 0;
   if (h->nloc == 4) {
     if (!attr_set[0]) {
       CUDA_CHECK(cudaFuncSetAttribute(assemble_tet_gather<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
       attr_set[0] = true;
     }
-    assemble_tet_gather<4><<<G.n_patch, 512, smem, h->stream>>>(
-        h->d_xyz.p, h->d_tets.p, P.d_elems.p, d_c, G.d_patch_row_ptr.p, G.d_patch_tet_ptr.p, G.d_patch_rows.p, G.d_patch_tets.p,
-        G.d_col_slot_ptr.p, G.d_col_src_ptr.p, G.d_slot_cnt.p, G.d_src.p, P.d_colptr.p, mass_scale, d_mass, d_stiff);
+    assemble_tet_gather<4><<<G.n_patch, 512, smem, h->stream>>>(h->d_xyz.p, h->d_tets.p, P.d_elems.p, d_c, G.d_patch_tet_ptr.p, G.d_patch_tets.p,
+                                                                G.d_patch_grp_ptr.p, G.d_patch_src_ptr.p, G.d_grp.p, G.d_out_idx.p, G.d_src.p,
+                                                                G.max_tets, mass_scale, d_mass, d_stiff, dbg);
   } else {
     if (!attr_set[1]) {
       CUDA_CHECK(cudaFuncSetAttribute(assemble_tet_gather<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
       attr_set[1] = true;
     }
-    assemble_tet_gather<10><<<G.n_patch, 512, smem, h->stream>>>(
-        h->d_xyz.p, h->d_tets.p, P.d_elems.p, d_c, G.d_patch_row_ptr.p, G.d_patch_tet_ptr.p, G.d_patch_rows.p, G.d_patch_tets.p,
-        G.d_col_slot_ptr.p, G.d_col_src_ptr.p, G.d_slot_cnt.p, G.d_src.p, P.d_colptr.p, mass_scale, d_mass, d_stiff);
+    assemble_tet_gather<10><<<G.n_patch, 512, smem, h->stream>>>(h->d_xyz.p, h->d_tets.p, P.d_elems.p, d_c, G.d_patch_tet_ptr.p, G.d_patch_tets.p,
+                                                                 G.d_patch_grp_ptr.p, G.d_patch_src_ptr.p, G.d_grp.p, G.d_out_idx.p, G.d_src.p,
+                                                                 G.max_tets, mass_scale, d_mass, d_stiff, dbg);
   }
   h->launches++;
   CUDA_CHECK(cudaGetLastError());
@@ -381,26 +412,26 @@ void wae_launch_assemble_gather(wae_ctx* h, Pattern& P, const double* d_c, doubl
 void wae_ensure_gather(wae_ctx* h, Pattern& P) {
   auto& G = P.gather;
   if (G.built) return;
-  const int nsym = h->nloc == 4 ? 10 : 55;
   // staged elements per patch: bounded by shared memory; WAE_GATHER_TETS overrides for tuning
-  int target = h->nloc == 4 ? 1000 : 240;
+  const int stride = h->nloc == 4 ? 16 : 64;  // doubles per staged element
+  int target = h->nloc == 4 ? 840 : 208;      // 2 CTAs per SM
   if (const char* env = getenv("WAE_GATHER_TETS")) target = atoi(env);
-  int cap = (int)((226 * 1024 - 1024) / ((nsym + 1) * sizeof(double)));
+  int cap = (int)((226 * 1024 - 1024) / (stride * sizeof(double))) - 1;
+  if (cap > 1022) cap = 1022;
   if (target > cap) target = cap;
   if (target < 64) target = 64;
   GatherHost GH;
   wae_build_gather(h->xyz.data(), h->tets.data(), h->nloc, P, target, GH);
-  G.n_patch = (int)GH.patch_row_ptr.size() - 1;
+  G.n_patch = (int)GH.patch_tet_ptr.size() - 1;
   G.max_tets = GH.max_tets;
   G.n_src = (int64_t)GH.src.size();
   G.n_staged = (int64_t)GH.patch_tets.size();
-  G.d_patch_row_ptr.upload(GH.patch_row_ptr, h->stream);
   G.d_patch_tet_ptr.upload(GH.patch_tet_ptr, h->stream);
-  G.d_patch_rows.upload(GH.patch_rows, h->stream);
   G.d_patch_tets.upload(GH.patch_tets, h->stream);
-  G.d_col_slot_ptr.upload(GH.col_slot_ptr, h->stream);
-  G.d_col_src_ptr.upload(GH.col_src_ptr, h->stream);
-  G.d_slot_cnt.upload(GH.slot_cnt, h->stream);
+  G.d_patch_grp_ptr.upload(GH.patch_grp_ptr, h->stream);
+  G.d_patch_src_ptr.upload(GH.patch_src_ptr, h->stream);
+  G.d_grp.upload(GH.grp, h->stream);
+  G.d_out_idx.upload(GH.out_idx, h->stream);
   G.d_src.upload(GH.src, h->stream);
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
   G.built = true;

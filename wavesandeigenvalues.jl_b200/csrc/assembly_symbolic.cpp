@@ -138,7 +138,7 @@ static inline uint64_t spread21(uint64_t v) {  // interleave helper: 21 bits -> 
 void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const Pattern& P, int target_tets, GatherHost& G) {
   const int64_t ne = (int64_t)P.elems.size();
   const int64_t dim = P.dim;
-  const int max_tets = 1023 < target_tets ? 1023 : target_tets;
+  const int max_tets = 1022 < target_tets ? 1022 : target_tets;
   std::vector<int64_t> nptr;
   std::vector<int32_t> nadj;
   node_to_elem(conn, nloc, P.elems, dim, nptr, nadj);
@@ -221,31 +221,30 @@ void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const P
     G.patch_row_ptr.push_back((int64_t)G.patch_rows.size());
     G.patch_tet_ptr.push_back((int64_t)G.patch_tets.size());
   }
-  // pass 2: sources of every owned nonzero (parallel over patches)
+  // pass 2: bucketed gather program (parallel over patches).  All nonzeros owned by a patch are sorted by their number
+  // of sources (descending) and cut into groups of 32 (one per lane); a group stores its sources TRANSPOSED -- for
+  // iteration k the 32 codes of the 32 lanes are contiguous (0xFFFF = no source) -- so that every lane of a warp runs the
+  // same trip count and the source codes are read with one coalesced load per iteration.
   const int64_t npatch = (int64_t)G.patch_row_ptr.size() - 1;
-  const int64_t ncol = (int64_t)G.patch_rows.size();
-  G.col_slot_ptr.assign(ncol + 1, 0);
-  G.col_src_ptr.assign(ncol + 1, 0);
-  for (int64_t r = 0; r < ncol; r++) {
-    int32_t col = G.patch_rows[r];
-    G.col_slot_ptr[r + 1] = G.col_slot_ptr[r] + (P.colptr[col + 1] - P.colptr[col]);
-  }
-  G.slot_cnt.assign(G.col_slot_ptr[ncol], 0);
-  // count sources per column: sum over incident elements of nloc (every element of the column touches nloc rows)
-  for (int64_t r = 0; r < ncol; r++) {
-    int32_t col = G.patch_rows[r];
-    G.col_src_ptr[r + 1] = G.col_src_ptr[r] + (nptr[col + 1] - nptr[col]) * nloc;
-  }
-  G.src.assign(G.col_src_ptr[ncol], 0);
+  const int code_shift = nloc == 4 ? 4 : 6;  // staging stride of the kernel: 16 (P1) / 64 (P2) doubles per element
+  const uint16_t pad_code = (uint16_t)(G.max_tets << code_shift);  // element index max_tets = block of zeros in shared memory
+  std::vector<std::vector<uint16_t>> psrc(npatch);
+  std::vector<std::vector<int32_t>> pout(npatch);
+  std::vector<std::vector<uint32_t>> pgrp(npatch);
   std::atomic<int> too_many(0);
   parallel_for(npatch, [&](int64_t pa, int64_t pb) {
-    std::vector<std::pair<int32_t, int32_t>> lmap;  // (element, local index) sorted by element
-    std::vector<std::pair<int32_t, uint16_t>> contrib;  // (row, code)
+    std::vector<std::pair<int32_t, int32_t>> lmap;      // (element, staged index) sorted by element
+    std::vector<std::pair<int32_t, uint16_t>> contrib;  // (row, code) of one column
+    struct Slot { int32_t out; int32_t first; int32_t cnt; };
+    std::vector<Slot> slots;
+    std::vector<uint16_t> codes;
     for (int64_t p = pa; p < pb; p++) {
       lmap.clear();
       for (int64_t t = G.patch_tet_ptr[p]; t < G.patch_tet_ptr[p + 1]; t++)
         lmap.emplace_back(G.patch_tets[t], (int32_t)(t - G.patch_tet_ptr[p]));
       std::sort(lmap.begin(), lmap.end());
+      slots.clear();
+      codes.clear();
       for (int64_t r = G.patch_row_ptr[p]; r < G.patch_row_ptr[p + 1]; r++) {
         int32_t col = G.patch_rows[r];
         contrib.clear();
@@ -259,27 +258,61 @@ void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const P
           for (int a = 0; a < nloc; a++) {
             int lo_ = a < b ? a : b, hi_ = a < b ? b : a;
             int sym = lo_ * nloc - lo_ * (lo_ - 1) / 2 + (hi_ - lo_);
-            contrib.emplace_back((int32_t)d[a], (uint16_t)(tl * 64 + sym));
+            contrib.emplace_back((int32_t)d[a], (uint16_t)((tl << code_shift) + sym));
           }
         }
-        // fixed summation order: by row, then by staged position
-        std::sort(contrib.begin(), contrib.end());
-        int64_t so = G.col_src_ptr[r], sl = G.col_slot_ptr[r];
+        std::sort(contrib.begin(), contrib.end());  // fixed summation order: by row, then by staged position
         const int32_t* rows = P.rowval.data() + P.colptr[col];
         int64_t len = P.colptr[col + 1] - P.colptr[col];
         size_t ci = 0;
-        for (int64_t s = 0; s < len; s++) {
-          int cnt = 0;
-          while (ci < contrib.size() && contrib[ci].first == rows[s]) {
-            G.src[so++] = contrib[ci].second;
+        for (int64_t sidx = 0; sidx < len; sidx++) {
+          Slot sl{(int32_t)(P.colptr[col] + sidx), (int32_t)codes.size(), 0};
+          while (ci < contrib.size() && contrib[ci].first == rows[sidx]) {
+            codes.push_back(contrib[ci].second);
             ci++;
-            cnt++;
+            sl.cnt++;
           }
-          if (cnt > 255) too_many = cnt;
-          G.slot_cnt[sl + s] = (uint8_t)cnt;
+          slots.push_back(sl);
         }
+      }
+      std::stable_sort(slots.begin(), slots.end(), [](const Slot& x, const Slot& y) { return x.cnt > y.cnt; });
+      // groups of GS nonzeros: lane l of the warp owns nonzeros j*32 + l (j < GS/32) of the group;
+      // entry (iteration k, nonzero q) of a group is src[k*GS + q]
+      const size_t GS = WAE_GATHER_GROUP;
+      const size_t ng = (slots.size() + GS - 1) / GS;
+      pgrp[p].resize(ng);
+      pout[p].assign(ng * GS, -1);
+      size_t off = 0;
+      for (size_t g = 0; g < ng; g++) {
+        int niter = slots[g * GS].cnt;
+        if (niter > 255) too_many = niter;
+        if (off >= ((size_t)1 << 24)) too_many = 1 << 24;
+        pgrp[p][g] = (uint32_t)(off << 8) | (uint32_t)(niter & 255);
+        psrc[p].resize(off + (size_t)niter * GS, pad_code);
+        for (size_t q = 0; q < GS && g * GS + q < slots.size(); q++) {
+          const Slot& sl = slots[g * GS + q];
+          pout[p][g * GS + q] = sl.out;
+          for (int k = 0; k < sl.cnt; k++) psrc[p][off + (size_t)k * GS + q] = codes[sl.first + k];
+        }
+        off += (size_t)niter * GS;
       }
     }
   });
-  if (too_many) WAE_THROW(WAE_E_INVALID, "a nonzero has %d sources (>255)", (int)too_many);
+  if (too_many) WAE_THROW(WAE_E_INVALID, "gather program overflow (%d)", (int)too_many);
+  G.patch_grp_ptr.assign(npatch + 1, 0);
+  G.patch_src_ptr.assign(npatch + 1, 0);
+  for (int64_t p = 0; p < npatch; p++) {
+    G.patch_grp_ptr[p + 1] = G.patch_grp_ptr[p] + (int64_t)pgrp[p].size();
+    G.patch_src_ptr[p + 1] = G.patch_src_ptr[p] + (int64_t)psrc[p].size();
+  }
+  G.grp.resize(G.patch_grp_ptr[npatch]);
+  G.out_idx.resize(G.patch_grp_ptr[npatch] * WAE_GATHER_GROUP);
+  G.src.resize(G.patch_src_ptr[npatch]);
+  parallel_for(npatch, [&](int64_t pa, int64_t pb) {
+    for (int64_t p = pa; p < pb; p++) {
+      std::copy(pgrp[p].begin(), pgrp[p].end(), G.grp.begin() + G.patch_grp_ptr[p]);
+      std::copy(pout[p].begin(), pout[p].end(), G.out_idx.begin() + G.patch_grp_ptr[p] * WAE_GATHER_GROUP);
+      std::copy(psrc[p].begin(), psrc[p].end(), G.src.begin() + G.patch_src_ptr[p]);
+    }
+  });
 }

@@ -80,14 +80,13 @@ struct Pattern {
   // owner-computes gather program (assembly): built lazily, see assembly_symbolic.cpp
   struct Gather {
     int n_patch = 0, max_tets = 0;
-    DevBuf<int64_t> d_patch_row_ptr;      // owned columns of patch p: patch_rows[patch_row_ptr[p] .. patch_row_ptr[p+1])
     DevBuf<int64_t> d_patch_tet_ptr;      // staged elements of patch p: patch_tets[patch_tet_ptr[p] .. )
-    DevBuf<int32_t> d_patch_rows;         // owned DOF columns
     DevBuf<int32_t> d_patch_tets;         // positions in the pattern's element list
-    DevBuf<int64_t> d_col_slot_ptr;       // per owned column (same order as patch_rows): start in d_slot_cnt
-    DevBuf<int64_t> d_col_src_ptr;        // per owned column: start in d_src
-    DevBuf<uint8_t> d_slot_cnt;           // number of sources of each owned nonzero
-    DevBuf<uint16_t> d_src;               // packed sources: tet_local * 64 + sym
+    DevBuf<int64_t> d_patch_grp_ptr;      // groups (32 owned nonzeros each, sorted by source count) of patch p
+    DevBuf<int64_t> d_patch_src_ptr;      // start of patch p in d_src
+    DevBuf<uint32_t> d_grp;               // per group: (offset into the patch's sources << 8) | iterations
+    DevBuf<int32_t> d_out_idx;            // per group lane: global nonzero index (-1 = padding lane)
+    DevBuf<uint16_t> d_src;               // transposed packed sources: tet_local * 64 + sym, 0xFFFF = none
     int64_t n_src = 0, n_staged = 0;
     bool built = false;
   } gather;
@@ -182,10 +181,11 @@ struct PhaseTimer {
 void wae_build_pattern_from_elements(const uint32_t* conn, int nloc, const std::vector<int64_t>& elems,
                                      int64_t dim, Pattern& P);
 void wae_build_slotmap(const uint32_t* conn, int nloc, const Pattern& P, std::vector<int32_t>& slotmap);
+#define WAE_GATHER_GROUP 32  // owned nonzeros per gather group (multiple of 32: GS/32 per lane)
 struct GatherHost {
-  std::vector<int64_t> patch_row_ptr, patch_tet_ptr, col_slot_ptr, col_src_ptr;
-  std::vector<int32_t> patch_rows, patch_tets;
-  std::vector<uint8_t> slot_cnt;
+  std::vector<int64_t> patch_row_ptr, patch_tet_ptr, patch_grp_ptr, patch_src_ptr;
+  std::vector<int32_t> patch_rows, patch_tets, out_idx;
+  std::vector<uint32_t> grp;
   std::vector<uint16_t> src;
   int max_tets = 0;
 };
