@@ -102,6 +102,16 @@ int32_t wae_assemble_mk(wae_ctx* h, int32_t pattern_id, const double* c, int32_t
 int32_t wae_assemble_flame(wae_ctx* h, int64_t n_flame, const int64_t* flame_tets, int64_t ref_tet,
                            const double* x_ref, const double* n_ref, double nlocal,
                            int32_t* pattern_id, int32_t* mat_id, int64_t* nnz);
+/* Bloch-periodic variant (src/Bloch.jl:4-112, Helmholtz.jl:509-513,541-549): the element operator `kind` over the given
+ * elements, assembled on the FOLDED unit-cell DOFs and split by the reference's rule into n_class matrices:
+ * 3 = (plain, +, -), 6 = (plain, +, -, axis, +axis, -axis) when the mesh has axis DOFs, 1 = everything summed (the
+ * weighting matrix).  dof_new[d] = folded index of DOF d (context index base), dof_flag[d] bit 0 = image of the Bloch
+ * plane, bit 1 = axis DOF (the host derives both from mesh.dos exactly as blochify does); dim_red = folded dimension.
+ * pattern_ids / mat_ids receive n_class ids.  A family built from such terms is not symmetric: the general LU is used. */
+int32_t wae_assemble_bloch(wae_ctx* h, int32_t elem_kind, int64_t n_elem, const int64_t* elem_ids, int32_t kind,
+                           const double* c, int32_t c_per_elem, double scale, int64_t dim_red, const int64_t* dof_new,
+                           const uint8_t* dof_flag, int32_t n_class, int32_t* pattern_ids, int32_t* mat_ids);
+
 /* Values of a matrix as complex numbers in pattern order (SparseMatrixCSC.nzval). */
 int32_t wae_mat_info(wae_ctx* h, int32_t mat_id, int32_t* pattern_id, int32_t* is_complex, int64_t* nnz);
 int32_t wae_mat_get(wae_ctx* h, int32_t mat_id, double* nzval_complex /* 2*nnz doubles */);

@@ -20,7 +20,44 @@ def _sparse(I, J, V, dim):
     return sp.csc_matrix(sp.coo_matrix((np.asarray(V, dtype=complex), (I, J)), shape=(dim, dim)))
 
 
-def discretize(mesh, dscrp, C, order="lin", mass_weighting=True, triplets=None):
+def blochify(ii, jj, mm, naxis, nxbloch, nsector, naxis_ln, nsector_ln, N_points, axis=True):
+    """src/Bloch.jl:4-112 with 0-based indices: fold the image DOFs onto the Bloch reference plane and sort every
+    triplet into the plain / plus / minus (and axis) sets.  nsector, naxis_ln, nsector_ln are COUNTS as in the reference
+    (naxis_ln and nsector_ln already include N_points)."""
+    blochshift = nsector - naxis
+    blochshift_ln = nsector_ln - naxis_ln
+    sets = {k: ([], [], []) for k in ("", "+", "-", "a", "+a", "-a")}
+    for i, j, m in zip(ii, jj, mm):
+        i, j = int(i) + 1, int(j) + 1  # the reference's 1-based comparisons
+        if i <= N_points:
+            i_check = i > nsector
+            if i_check:
+                i -= blochshift
+        else:
+            i_check = i > nsector_ln
+            if i_check:
+                i -= blochshift_ln
+        if j <= N_points:
+            j_check = j > nsector
+            if j_check:
+                j -= blochshift
+        else:
+            j_check = j > nsector_ln
+            if j_check:
+                j -= blochshift_ln
+        axis_check = axis and (i <= naxis or j <= naxis or N_points < i <= naxis_ln or N_points < j <= naxis_ln)
+        if i > N_points:
+            i -= nxbloch
+        if j > N_points:
+            j -= nxbloch
+        key = ("" if i_check == j_check else ("+" if j_check else "-")) + ("a" if axis_check else "")
+        I, J, M = sets[key]
+        I.append(i - 1); J.append(j - 1); M.append(m)
+    keys = ("", "+", "-") if naxis == 0 else ("", "+", "-", "a", "+a", "-a")
+    return [sets[k] for k in keys]
+
+
+def discretize(mesh, dscrp, C, order="lin", mass_weighting=True, triplets=None, b=None):
     """Returns the LinearOperatorFamily.  If `triplets` is a dict, the raw COO
     triplets of every operator are stored in it (used by the pattern tests)."""
     o = 1 if order == "lin" else 2
@@ -39,6 +76,30 @@ def discretize(mesh, dscrp, C, order="lin", mass_weighting=True, triplets=None):
         raise ValueError("C must be per-tetrahedron or per-point")
     L = LinearOperatorFamily(["ω", "λ"], [0.0, float("inf")])
     P = mesh.points
+    bloch = b is not None
+    if bloch:  # Helmholtz.jl:82-118
+        import math
+        from .nlevp import exp_az
+        dos = mesh.dos
+        naxis, nxbloch = dos.naxis, dos.nxbloch
+        nsector = naxis + dos.nxsector
+        naxis_ln = dos.naxis_ln + npts
+        nsector_ln = dos.naxis_ln + dos.nxsector_ln + npts
+        dphi = 2 * math.pi / dos.DOS
+        exp_plus = lambda z, k: exp_az(z, dphi * 1j, k)
+        exp_minus = lambda z, k: exp_az(z, -dphi * 1j, k)
+        filt_y = np.fft.fft(np.concatenate([[1.0 / dos.DOS], np.zeros(dos.DOS - 1)]))
+
+        def bloch_filt(z, n):  # algebra.jl:276-288
+            N = len(filt_y)
+            f = sum((k**n if n else 1) * y * np.exp(2j * math.pi * k / N * z) for k, y in enumerate(filt_y))
+            return f * (2j * math.pi / N) ** n
+        anti_bloch_filt = lambda z, k: (1 - bloch_filt(z, k)) if k == 0 else -bloch_filt(z, k)
+        gz_hz = lambda g, h: (lambda z, k: sum(math.comb(k, i) * h(z, k - i) * g(z, i) for i in range(k + 1)))
+        bloch_funcs = [(), (exp_plus,), (exp_minus,), (bloch_filt,), (gz_hz(bloch_filt, exp_plus),), (gz_hz(bloch_filt, exp_minus),)]
+        L.params[b] = 0j
+        dim -= dos.nxbloch + (dos.nxbloch_ln if order == "quad" else 0)
+        L.bloch_funcs = bloch_funcs
 
     def stiff(ct, c):
         return -c**2 * fem.tet_stiff(ct, o) if np.ndim(c) == 0 else -fem.tet_stiff_cc1(ct, c, o)
@@ -116,9 +177,14 @@ def discretize(mesh, dscrp, C, order="lin", mass_weighting=True, triplets=None):
                 func, arg, txt = ffunc, farg, ftxt
             if triplets is not None:
                 triplets.setdefault(opr, []).append((np.array(I), np.array(J), np.array(V, dtype=complex)))
-            L.push(Term(_sparse(I, J, V, dim), func, arg, txt, opr))
+            if bloch:  # Helmholtz.jl:509-513
+                parts = blochify(I, J, V, naxis, nxbloch, nsector, naxis_ln, nsector_ln, npts)
+                for (i_, j_, v_), f in zip(parts, bloch_funcs):
+                    L.push(Term(_sparse(i_, j_, v_, dim), tuple(func) + f, tuple(arg) + (((b,),) if f else ()), txt, opr))
+            else:
+                L.push(Term(_sparse(I, J, V, dim), func, arg, txt, opr))
 
-    if mass_weighting:
+    if mass_weighting or bloch:
         I, J, V = [], [], []
         for smplx in tetrahedra:
             ct = fem.CooTrafo(P[:, smplx[:4]])
@@ -127,5 +193,19 @@ def discretize(mesh, dscrp, C, order="lin", mass_weighting=True, triplets=None):
             V.extend(vv.T.ravel()); I.extend(ii.T.ravel()); J.extend(jj.T.ravel())
         if triplets is not None:
             triplets.setdefault("__aux__", []).append((np.array(I), np.array(J), -np.array(V, dtype=complex)))
-        L.push(Term(_sparse(I, J, -np.asarray(V), dim), (pow1,), (("λ",),), "-λ", "__aux__"))
+        if bloch:  # Helmholtz.jl:541-569
+            parts = blochify(I, J, V, naxis, nxbloch, nsector, naxis_ln, nsector_ln, npts, axis=False)[:3]
+            I = [x for p_ in parts for x in p_[0]]
+            J = [x for p_ in parts for x in p_[1]]
+            V = [x for p_ in parts for x in p_[2]]
+            M = _sparse(I, J, -np.asarray(V), dim)
+            if naxis > 0:
+                DI = list(range(naxis))
+                if order == "quad":
+                    DI += [k - nxbloch for k in range(npts, naxis_ln)]
+                DV = [1 / M[k, k] for k in DI]
+                L.push(Term(_sparse(DI, DI, DV, dim), (anti_bloch_filt,), ((b,),), "(1-δ(b))", "D"))
+        else:
+            M = _sparse(I, J, -np.asarray(V), dim)
+        L.push(Term(M, (pow1,), (("λ",),), "-λ", "__aux__"))
     return L

@@ -61,6 +61,7 @@ SIGNATURES = {
     "wae_assemble": (_i32, [_vp, _i32, _i32, _pd, _i32, _dbl, _pi32]),
     "wae_assemble_mk": (_i32, [_vp, _i32, _pd, _i32, _pi32, _pi32]),
     "wae_assemble_flame": (_i32, [_vp, _i64, _pi64, _i64, _pd, _pd, _dbl, _pi32, _pi32, _pi64]),
+    "wae_assemble_bloch": (_i32, [_vp, _i32, _i64, _pi64, _i32, _pd, _i32, _dbl, _i64, _pi64, C.POINTER(C.c_uint8), _i32, _pi32, _pi32]),
     "wae_mat_info": (_i32, [_vp, _i32, _pi32, _pi32, _pi64]),
     "wae_mat_get": (_i32, [_vp, _i32, _pd]),
     "wae_mat_set": (_i32, [_vp, _i64, _pi64, _pi64, _pd, _pi32, _pi32]),
@@ -187,6 +188,21 @@ class Context:
         self._chk(self._l.wae_assemble_flame(self.h, len(ft), _p(ft, _pi64), int(ref_tet), _p(xr, _pd), _p(nr, _pd), float(nlocal),
                                              C.byref(pid), C.byref(mid), C.byref(nnz)))
         return pid.value, mid.value, nnz.value
+
+    def assemble_bloch(self, elem_kind, elem_ids, kind, c, scale, dim_red, dof_new, dof_flag, n_class):
+        ids = None if elem_ids is None else np.ascontiguousarray(elem_ids, dtype=np.int64)
+        cpe = 1
+        if c is not None:
+            c = np.ascontiguousarray(c, dtype=np.float64)
+            cpe = 1 if c.ndim == 1 else c.shape[1]
+        dn = np.ascontiguousarray(dof_new, dtype=np.int64)
+        df = np.ascontiguousarray(dof_flag, dtype=np.uint8)
+        pids = np.zeros(n_class, dtype=np.int32)
+        mids = np.zeros(n_class, dtype=np.int32)
+        self._chk(self._l.wae_assemble_bloch(self.h, elem_kind, 0 if ids is None else len(ids), _p(ids, _pi64), kind, _p(c, _pd), cpe, scale,
+                                             dim_red, _p(dn, _pi64), df.ctypes.data_as(C.POINTER(C.c_uint8)), n_class, _p(pids, _pi32),
+                                             _p(mids, _pi32)))
+        return list(map(int, pids)), list(map(int, mids))
 
     def mat_info(self, mid):
         pid, cx, nnz = _i32(), _i32(), _i64()

@@ -316,3 +316,79 @@ void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const P
     }
   });
 }
+
+// ------------------------------------------------------------------------------------
+// Bloch-periodic assembly (src/Bloch.jl:4-112): every element contribution (e, a, b) lands on the folded unit-cell DOFs
+// (dof_new) in one of n_class matrices chosen by the reference's rule -- plain if row and column are both (or neither)
+// images of the Bloch plane, "+" if only the column is, "-" if only the row is; with axis DOFs (n_class == 6) the entries
+// touching an axis DOF go to the three axis variants.  n_class == 1 sums everything into one matrix (the blochified
+// weighting matrix of Helmholtz.jl:545-549).  Patterns are built from the sorted unique (class, col, row) keys;
+// slotmap[e*nloc^2 + a*nloc + b] = offset of the contribution in the concatenation of the class value arrays.
+// ------------------------------------------------------------------------------------
+void wae_build_bloch(const uint32_t* conn, int nloc, const std::vector<int64_t>& elems, int64_t dim_red, const int64_t* dof_new,
+                     const uint8_t* dof_flag, int n_class, std::vector<Pattern>& P, std::vector<int32_t>& slotmap,
+                     std::vector<int64_t>& class_base) {
+  const int64_t ne = (int64_t)elems.size();
+  const size_t nc = (size_t)ne * nloc * nloc;
+  struct Key { uint64_t k; uint32_t src; };
+  std::vector<Key> keys(nc);
+  const uint64_t D = (uint64_t)dim_red;
+  parallel_for(ne, [&](int64_t a0, int64_t b0) {
+    for (int64_t e = a0; e < b0; e++) {
+      const uint32_t* d = conn + (size_t)elems[e] * nloc;
+      for (int a = 0; a < nloc; a++)
+        for (int b = 0; b < nloc; b++) {
+          uint8_t fa = dof_flag[d[a]], fb = dof_flag[d[b]];
+          int cls = 0;
+          if (n_class > 1) {
+            bool ic = fa & 1, jc = fb & 1;
+            cls = ic == jc ? 0 : (jc ? 1 : 2);
+            if (n_class == 6 && ((fa | fb) & 2)) cls += 3;
+          }
+          uint64_t row = (uint64_t)dof_new[d[a]], col = (uint64_t)dof_new[d[b]];
+          size_t q = ((size_t)e * nloc + a) * nloc + b;
+          keys[q].k = ((uint64_t)cls * D + col) * D + row;
+          keys[q].src = (uint32_t)q;
+        }
+    }
+  });
+  if (nc >= ((size_t)1 << 32)) WAE_THROW(WAE_E_INVALID, "Bloch assembly: too many element contributions");
+  std::sort(keys.begin(), keys.end(), [](const Key& x, const Key& y) { return x.k < y.k; });
+  P.clear();
+  P.resize(n_class);
+  for (auto& p : P) {
+    p.dim = dim_red;
+    p.colptr.assign(dim_red + 1, 0);
+  }
+  slotmap.resize(nc);
+  class_base.assign(n_class + 1, 0);
+  // first pass: count unique keys per class / column
+  uint64_t prev = ~0ull;
+  for (size_t i = 0; i < nc; i++) {
+    if (keys[i].k == prev) continue;
+    prev = keys[i].k;
+    int cls = (int)(prev / (D * D));
+    int64_t col = (int64_t)((prev / D) % D);
+    P[cls].colptr[col + 1]++;
+  }
+  for (int c = 0; c < n_class; c++) {
+    for (int64_t j = 0; j < dim_red; j++) P[c].colptr[j + 1] += P[c].colptr[j];
+    P[c].nnz = P[c].colptr[dim_red];
+    P[c].rowval.resize(P[c].nnz);
+    class_base[c + 1] = class_base[c] + P[c].nnz;
+  }
+  if (class_base[n_class] >= ((int64_t)1 << 31)) WAE_THROW(WAE_E_INVALID, "Bloch assembly: pattern too large");
+  std::vector<int64_t> fill(n_class, 0);
+  prev = ~0ull;
+  int64_t cur = -1;
+  for (size_t i = 0; i < nc; i++) {
+    if (keys[i].k != prev) {
+      prev = keys[i].k;
+      int cls = (int)(prev / (D * D));
+      P[cls].rowval[fill[cls]] = (int32_t)(prev % D);
+      cur = class_base[cls] + fill[cls];
+      fill[cls]++;
+    }
+    slotmap[keys[i].src] = (int32_t)cur;
+  }
+}

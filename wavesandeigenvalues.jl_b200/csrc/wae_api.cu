@@ -361,6 +361,76 @@ int32_t wae_assemble_flame(wae_ctx* h, int64_t n_flame, const int64_t* flame_tet
   WAE_API_END
 }
 
+int32_t wae_assemble_bloch(wae_ctx* h, int32_t elem_kind, int64_t n_elem, const int64_t* elem_ids, int32_t kind, const double* c,
+                           int32_t c_per_elem, double scale, int64_t dim_red, const int64_t* dof_new, const uint8_t* dof_flag,
+                           int32_t n_class, int32_t* pattern_ids, int32_t* mat_ids) {
+  WAE_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(h->device));
+  if (!h->order) WAE_THROW(WAE_E_INVALID, "wae_mesh_set has not been called");
+  if (n_class != 1 && n_class != 3 && n_class != 6) WAE_THROW(WAE_E_INVALID, "n_class must be 1, 3 or 6");
+  if (kind < WAE_OP_MASS || kind > WAE_OP_BOUNDARY || (kind == WAE_OP_BOUNDARY) != (elem_kind == 2)) WAE_THROW(WAE_E_INVALID, "operator kind does not match the element kind");
+  if (!dof_new || !dof_flag || dim_red <= 0 || !pattern_ids || !mat_ids) WAE_THROW(WAE_E_INVALID, "bad Bloch arguments");
+  const int64_t total = elem_kind == 3 ? h->n_tet : h->n_tri;
+  Pattern work;  // carries the element list for the kernels
+  work.elem_kind = elem_kind;
+  if (elem_ids) {
+    work.elems.resize(n_elem);
+    for (int64_t i = 0; i < n_elem; i++) {
+      int64_t e = elem_ids[i] - h->base;
+      if (e < 0 || e >= total) WAE_THROW(WAE_E_INVALID, "element id out of range");
+      work.elems[i] = e;
+    }
+  } else {
+    work.elems.resize(total);
+    std::iota(work.elems.begin(), work.elems.end(), 0);
+  }
+  std::vector<int64_t> dn(h->dim);
+  for (int64_t d = 0; d < h->dim; d++) {
+    dn[d] = dof_new[d] - h->base;
+    if (dn[d] < 0 || dn[d] >= dim_red) WAE_THROW(WAE_E_INVALID, "folded DOF index out of range");
+  }
+  const uint32_t* conn = elem_kind == 3 ? h->tets.data() : h->tris.data();
+  const int nloc = elem_kind == 3 ? h->nloc : h->nloc3;
+  std::vector<Pattern> cls;
+  std::vector<int32_t> slotmap;
+  std::vector<int64_t> base;
+  wae_build_bloch(conn, nloc, work.elems, dim_red, dn.data(), dof_flag, n_class, cls, slotmap, base);
+  std::vector<int32_t> e32(work.elems.begin(), work.elems.end());
+  work.d_elems.upload(e32, h->stream);
+  work.d_slotmap.upload(slotmap, h->stream);
+  work.slotmap_built = true;
+  const bool cx = kind == WAE_OP_BOUNDARY;
+  DevBuf<double> d_all, d_c;
+  d_all.alloc((size_t)std::max<int64_t>(base[n_class], 1) * (cx ? 2 : 1));
+  CUDA_CHECK(cudaMemsetAsync(d_all.p, 0, d_all.n * sizeof(double), h->stream));
+  if (kind != WAE_OP_MASS) upload_c(h, work, c, c_per_elem, d_c);
+  PhaseTimer t(h, "assemble");
+  if (kind == WAE_OP_MASS)
+    wae_launch_assemble_atomic(h, work, 1, nullptr, 1, scale, d_all.p, nullptr);
+  else if (kind == WAE_OP_STIFF)
+    wae_launch_assemble_atomic(h, work, 2, d_c.p, c_per_elem, 1.0, nullptr, d_all.p);
+  else
+    wae_launch_assemble_atomic(h, work, 0, d_c.p, c_per_elem, scale, d_all.p, nullptr);
+  t.stop();
+  for (int k = 0; k < n_class; k++) {
+    int pid = new_pattern(h);
+    Pattern& P = *h->patterns[pid];
+    P.dim = dim_red;
+    P.nnz = cls[k].nnz;
+    P.colptr.swap(cls[k].colptr);
+    P.rowval.swap(cls[k].rowval);
+    upload_pattern(h, P);
+    int mid = new_matrix(h, pid, cx, P.nnz);
+    if (P.nnz)
+      CUDA_CHECK(cudaMemcpyAsync(h->mats[mid]->d_val.p, d_all.p + (size_t)base[k] * (cx ? 2 : 1), (size_t)P.nnz * (cx ? 2 : 1) * sizeof(double),
+                                 cudaMemcpyDeviceToDevice, h->stream));
+    pattern_ids[k] = pid;
+    mat_ids[k] = mid;
+  }
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  WAE_API_END
+}
+
 int32_t wae_mat_info(wae_ctx* h, int32_t mat_id, int32_t* pattern_id, int32_t* is_complex, int64_t* nnz) {
   WAE_API_BEGIN
   Matrix& M = h->mat(mat_id);

@@ -191,6 +191,9 @@ struct GatherHost {
 };
 void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const Pattern& P, int target_tets, GatherHost& G);
 void wae_ensure_gather(wae_ctx* h, Pattern& P);
+void wae_build_bloch(const uint32_t* conn, int nloc, const std::vector<int64_t>& elems, int64_t dim_red, const int64_t* dof_new,
+                     const uint8_t* dof_flag, int n_class, std::vector<Pattern>& P, std::vector<int32_t>& slotmap,
+                     std::vector<int64_t>& class_base);
 
 // ---- kernels launchers (device) ----------------------------------------------------
 void wae_launch_assemble_atomic(wae_ctx* h, Pattern& P, int kind, const double* d_c, int c_per_elem,

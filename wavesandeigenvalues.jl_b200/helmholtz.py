@@ -12,8 +12,9 @@
   "flame" 6-tuple (custom FTF)       Q with FTF(omega,k)            :302-311
   "flame" 5-tuple                    Q with the plain parameter FTF :312-319
   "flameresponse" 7-tuple            Q with eps                     :346-359
-and the auxiliary mass-weighting term -lambda*M_all (:528-540, 571-574).  Bloch periodicity (b=...),
-:speaker sources, :fancyflame and Hermite elements are outside the accelerated path and raise
+and the auxiliary mass-weighting term -lambda*M_all (:528-540, 571-574).  With ``b="b"`` (a unit-cell mesh carrying
+``mesh.dos``) the operators are blochified (src/Bloch.jl:4-112, Helmholtz.jl:82-118,509-513,541-569).  :speaker
+sources, :fancyflame, flames on Bloch meshes and Hermite elements are outside the accelerated path and raise
 NotImplementedError.
 
 What changes relative to the reference is only where the work happens: the per-element loops
@@ -77,9 +78,32 @@ class Discretization:
         return ms
 
 
+def _bloch_setup(mesh, order, b, L):
+    """Helmholtz.jl:82-118: scalar functions of the Bloch wave number and the DOF folding of blochify."""
+    import math
+    from .meshutils import bloch_dof_maps
+    from .nlevp import exp_az, generate_1_gz, generate_gz_hz, generate_Sigma_y_exp_ikx
+    dos = mesh.dos
+    dphi = 2 * math.pi / dos.DOS
+
+    def exp_plus(z, k):
+        return exp_az(z, dphi * 1j, k)
+
+    def exp_minus(z, k):
+        return exp_az(z, -dphi * 1j, k)
+    filt = np.fft.fft(np.concatenate([[1.0 / dos.DOS], np.zeros(dos.DOS - 1)]))  # Helmholtz.jl:92-95 (FFTW.fft of a scaled delta)
+    bloch_filt = generate_Sigma_y_exp_ikx(filt)
+    funcs = [(), (exp_plus,), (exp_minus,), (bloch_filt,), (generate_gz_hz(bloch_filt, exp_plus),), (generate_gz_hz(bloch_filt, exp_minus),)]
+    txts = ["", f"*exp(i{b}2π/{dos.DOS})", f"*exp(-i{b}2π/{dos.DOS})", f"*δ({b})", f"*δ({b})*exp(i{b}2π/{dos.DOS})", f"*δ({b})*exp(-i{b}2π/{dos.DOS})"]
+    new, image, axis, red = bloch_dof_maps(mesh, order)
+    flag = image.astype(np.uint8) | (axis.astype(np.uint8) << 1)
+    L.params[b] = 0j
+    return {"funcs": funcs, "txts": txts, "new": new, "flag": flag, "dim": red, "n_class": 3 if dos.naxis == 0 else 6,
+            "anti_filt": generate_1_gz(bloch_filt), "naxis": dos.naxis, "naxis_ln": dos.naxis_ln, "nxbloch": dos.nxbloch}
+
+
 def discretize(mesh, dscrp, C, order="lin", b="__none__", mass_weighting=True, source=False, output=False, ctx=None):
-    if b != "__none__":
-        raise NotImplementedError("Bloch-periodic discretisation is not on the accelerated path yet")
+    bloch = None
     if source:
         raise NotImplementedError("source=True (experimental in the reference) is not on the accelerated path")
     ctx = ctx or get_context()
@@ -94,8 +118,22 @@ def discretize(mesh, dscrp, C, order="lin", b="__none__", mass_weighting=True, s
     disc.ctx, disc.mesh = ctx, mesh
     L.discretization = disc
 
+    if b != "__none__":
+        if getattr(mesh, "dos", 1) == 1:
+            raise ValueError("Bloch discretisation needs a unit-cell mesh (mesh.dos)")
+        bloch = _bloch_setup(mesh, order, b, L)
+        full_dim, dim = dim, bloch["dim"]
+
     def dm(mid):
         return DeviceMatrix(ctx, dim, [(mid, 1.0)])
+
+    def push_bloch(elem_kind, simplices, kind, c, func, arg, txt, opr):
+        """Helmholtz.jl:509-513: one Term per Bloch class with the class scalar appended to the term's functions."""
+        _, mids = ctx.assemble_bloch(elem_kind, simplices, kind, c, 1.0, dim, bloch["new"], bloch["flag"], bloch["n_class"])
+        for mid, f, t in zip(mids, bloch["funcs"], bloch["txts"]):
+            if ctx.mat_info(mid)[2] == 0:
+                continue
+            L.push(Term(dm(mid), tuple(func) + f, tuple(arg) + (((b,),) if f else ()), txt + t, opr))
 
     def tet_pattern(domain):
         key = (3, domain)
@@ -113,7 +151,26 @@ def discretize(mesh, dscrp, C, order="lin", b="__none__", mass_weighting=True, s
 
     for domain, (typ, data) in dscrp.items():
         simplices = np.asarray(mesh.domains[domain]["simplices"], dtype=np.int64)
-        if typ == "interior":
+        if bloch is not None and typ in ("interior", "mass", "stiff", "admittance"):
+            if typ in ("interior", "mass"):
+                push_bloch(3, simplices, _lib.OP_MASS, None, (pow2,), (("ω",),), "ω^2", "M")
+            if typ == "interior":
+                push_bloch(3, simplices, _lib.OP_STIFF, C_tet[simplices], (), (), "", "K")
+            elif typ == "stiff":
+                funcs, args, txt = data
+                for a in args:
+                    for p_ in a:
+                        L.params[p_] = 0.0
+                push_bloch(3, simplices, _lib.OP_STIFF, C_tet[simplices], tuple(funcs), tuple(args), txt, "K")
+            elif typ == "admittance":
+                if len(data) != 2:
+                    raise NotImplementedError("Bloch + functional admittance is not on the accelerated path")
+                adm_sym, adm_val = data
+                L.params.setdefault(adm_sym, complex(adm_val))
+                push_bloch(2, simplices, _lib.OP_BOUNDARY, C_tri[simplices], (pow1, pow1), (("ω",), (adm_sym,)), "ω*" + adm_sym, "C")
+        elif bloch is not None:
+            raise NotImplementedError(f"descriptor type {typ!r} with Bloch periodicity is not on the accelerated path")
+        elif typ == "interior":
             pid = tet_pattern(domain)
             im, ik = ctx.assemble_mk(pid, C_tet[simplices])
             disc.ops.append({"op": "mk", "pid": pid, "simplices": simplices, "mats": (im, ik)})
@@ -194,6 +251,21 @@ def discretize(mesh, dscrp, C, order="lin", b="__none__", mass_weighting=True, s
         else:
             raise NotImplementedError(f"descriptor type {typ!r} is not on the accelerated path")
 
+    if bloch is not None:
+        # Helmholtz.jl:541-574: weighting matrix = blochified mass with the three parts summed; axis DOFs get the penalty term D
+        _, mids = ctx.assemble_bloch(3, None, _lib.OP_MASS, None, -1.0, dim, bloch["new"], bloch["flag"], 1)
+        aux = dm(mids[0])
+        if bloch["naxis"] > 0:
+            import scipy.sparse as sp
+            npts = mesh.points.shape[1]
+            DI = list(range(bloch["naxis"]))
+            if order == "quad":
+                DI += [k - bloch["nxbloch"] for k in range(npts, npts + bloch["naxis_ln"])]
+            diag = aux.to_scipy().diagonal()
+            D = sp.csc_matrix((1.0 / diag[DI], (DI, DI)), shape=(dim, dim))
+            L.push(Term(DeviceMatrix.from_scipy(D, ctx), (bloch["anti_filt"],), ((b,),), "(1-δ(b))", "D"))
+        L.push(Term(aux, (pow1,), (("λ",),), "-λ", "__aux__"))
+        return L
     if mass_weighting:
         # Helmholtz.jl:528-540,572-574: -M over ALL tetrahedra
         key = (3, "__all__")

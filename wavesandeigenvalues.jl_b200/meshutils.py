@@ -124,13 +124,23 @@ class Mesh:
         return self.lines
 
     def edge_index(self, a, b):
-        """Index in mesh.lines of the edges (a[i], b[i]) (vectorised find_smplx)."""
+        """Index in mesh.lines of the edges (a[i], b[i]) (vectorised find_smplx / get_line_idx, annular_meshes.jl:603)."""
         self.collect_lines()
         npts = self.points.shape[1]
         hi, lo = np.maximum(a, b), np.minimum(a, b)
         lk = -np.sort(-self.lines, axis=1)
-        keys = lk[:, 0] * npts + lk[:, 1]  # ascending, as the list is sorted by (max,min)
-        return np.searchsorted(keys, hi * npts + lo)
+        keys = lk[:, 0] * npts + lk[:, 1]
+        order = np.argsort(keys, kind="stable")  # identity for the default (sorted) line list
+        return order[np.searchsorted(keys[order], hi * npts + lo)]
+
+    def reorder_lines(self, new_of_old):
+        """Renumber mesh.lines (unit-cell meshes keep their edges sector-wise as [axis | Bloch plane | rest | image plane],
+        annular_meshes.jl:459-496); new_of_old[i] = new index of the line currently at index i."""
+        self.collect_lines()
+        inv = np.empty_like(new_of_old)
+        inv[new_of_old] = np.arange(len(new_of_old))
+        self.lines = self.lines[inv]
+        self._edge_of = np.asarray(new_of_old)[self._edge_of]
 
     # -- Meshutils.jl:516-548 --------------------------------------------------------------------
     def link_triangles_to_tetrahedra(self):
@@ -208,6 +218,40 @@ def aggregate_elements(mesh, order="lin"):
     return tris, tets, npts + len(mesh.lines)
 
 
+class SymInfo:
+    """Symmetry bookkeeping of a unit-cell mesh (the fields of Meshutils.jl:28-44 that discretize/blochify read)."""
+
+    def __init__(self, DOS, naxis, nxbloch, nxsector, naxis_ln, nxbloch_ln, nxsector_ln, unit=True):
+        self.DOS, self.naxis, self.nxbloch, self.nxsector = DOS, naxis, nxbloch, nxsector
+        self.naxis_ln, self.nxbloch_ln, self.nxsector_ln, self.unit = naxis_ln, nxbloch_ln, nxsector_ln, unit
+
+
+def bloch_dof_maps(mesh, order):
+    """DOF folding of blochify (Bloch.jl:4-66) as arrays over the unfolded DOFs:
+    (new_index, is_image, is_axis, reduced_dim).  Point DOFs > nsector and line DOFs > nsector_ln are images of the
+    Bloch reference plane; line DOFs move down by nxbloch because the image points disappear."""
+    d = mesh.dos
+    npts = mesh.points.shape[1]
+    nsector = d.naxis + d.nxsector
+    dim = npts + (len(mesh.collect_lines()) if order == "quad" else 0)
+    idx = np.arange(dim)
+    new = idx.copy()
+    image = np.zeros(dim, dtype=bool)
+    image[:npts] = idx[:npts] >= nsector
+    new[:npts] -= np.where(image[:npts], nsector - d.naxis, 0)
+    axis = np.zeros(dim, dtype=bool)
+    axis[:npts] = new[:npts] < d.naxis
+    if order == "quad":
+        ln = idx[npts:] - npts
+        img_ln = ln >= d.naxis_ln + d.nxsector_ln
+        image[npts:] = img_ln
+        ln_new = ln - np.where(img_ln, d.nxsector_ln, 0)
+        axis[npts:] = ln_new < d.naxis_ln
+        new[npts:] = npts + ln_new - d.nxbloch
+    red = dim - d.nxbloch - (d.nxbloch_ln if order == "quad" else 0)
+    return new, image, axis, red
+
+
 # ---------------------------------------------------------------------------------------------
 # synthetic structured meshes (SURVEY section 7, step 2): Kuhn 6-tet boxes with seeded jitter
 # ---------------------------------------------------------------------------------------------
@@ -261,3 +305,68 @@ def kuhn_box(ncube, lo, hi, jitter=0.0, seed=0, flame_layer=None, name="kuhn_box
         k0, k1 = flame_layer
         domains["Flame"] = {"dimension": 3, "simplices": np.flatnonzero((tet_cz >= k0) & (tet_cz < k1))}
     return Mesh(name, raw=(pts, np.zeros((0, 2), dtype=np.int64), tris, tets, domains))
+
+
+def kuhn_unit_cell(ncube, lo, hi, DOS, jitter=0.0, seed=0, name="kuhn_unit_cell"):
+    """One period (in x) of a DOS-periodic duct as a unit-cell mesh with the reference's index layout
+    (annular_meshes.jl:292-368, naxis = 0): points [Bloch reference plane x=lo | body | image plane x=hi], image point
+    k = reference point k + nxsector; edges [Bloch plane | rest | image plane] with the same pairing.  The two periodic
+    planes carry no boundary triangles.  Domains: "Interior", "Outlet" (z=hi), "Inlet" (z=lo), "Walls" (y faces)."""
+    nx, ny, nz = ncube
+    base = kuhn_box(ncube, lo, hi, jitter=0.0, seed=seed)
+    pts = base.points.copy()
+    lo, hi = np.asarray(lo, float), np.asarray(hi, float)
+    tol = 1e-9 * (hi[0] - lo[0])
+    on_ref = np.abs(pts[0] - lo[0]) < tol
+    on_img = np.abs(pts[0] - hi[0]) < tol
+    if jitter:  # periodic jitter: interior points only (the planes stay congruent)
+        rng = np.random.default_rng(seed)
+        h = (hi - lo) / np.array(ncube)
+        inner = np.ones(pts.shape[1], dtype=bool)
+        for r in range(3):
+            inner &= (pts[r] > lo[r] + tol) & (pts[r] < hi[r] - tol)
+        pts[:, inner] += rng.uniform(-jitter, jitter, size=(3, int(inner.sum()))) * h[:, None]
+    # new point numbering: reference plane, body, image plane (partner order = (y,z) lexicographic on both planes)
+    key = np.round((pts[1] - lo[1]) / (hi[1] - lo[1]) * ny).astype(np.int64) * (nz + 1) + np.round((pts[2] - lo[2]) / (hi[2] - lo[2]) * nz).astype(np.int64)
+    ref = np.flatnonzero(on_ref)
+    ref = ref[np.argsort(key[ref], kind="stable")]
+    img = np.flatnonzero(on_img)
+    img = img[np.argsort(key[img], kind="stable")]
+    body = np.flatnonzero(~on_ref & ~on_img)
+    order = np.concatenate([ref, body, img])
+    new_of_old = np.empty(len(order), dtype=np.int64)
+    new_of_old[order] = np.arange(len(order))
+    tets = new_of_old[base.tetrahedra]
+    tris = new_of_old[base.triangles]
+    pts = pts[:, order]
+    nxb, npt = len(ref), pts.shape[1]
+    nxsector = npt - nxb
+    keep = ~(np.all(tris < nxb, axis=1) | np.all(tris >= nxsector, axis=1))  # drop the periodic planes
+    tris = tris[keep]
+    zc, yc = pts[2, tris], pts[1, tris]
+    tz, ty = 1e-9 * (hi[2] - lo[2]), 1e-9 * (hi[1] - lo[1])
+    out = np.all(np.abs(zc - hi[2]) < tz, axis=1)
+    inn = np.all(np.abs(zc - lo[2]) < tz, axis=1)
+    domains = {"Interior": {"dimension": 3, "simplices": np.arange(len(tets))},
+               "Outlet": {"dimension": 2, "simplices": np.flatnonzero(out)},
+               "Inlet": {"dimension": 2, "simplices": np.flatnonzero(inn)},
+               "Walls": {"dimension": 2, "simplices": np.flatnonzero(~out & ~inn)}}
+    mesh = Mesh(name, raw=(pts, np.zeros((0, 2), dtype=np.int64), tris, tets, domains))
+    # edges: [Bloch plane | rest | image plane], image edge k <-> Bloch edge k
+    lines = mesh.collect_lines()
+    on_b = np.all(lines < nxb, axis=1)
+    on_i = np.all(lines >= nxsector, axis=1)
+    lb = np.flatnonzero(on_b)
+    li = np.flatnonzero(on_i)
+    kb = np.sort(lines[lb], axis=1)
+    ki = np.sort(lines[li] - nxsector, axis=1)
+    lb = lb[np.lexsort((kb[:, 1], kb[:, 0]))]
+    li = li[np.lexsort((ki[:, 1], ki[:, 0]))]
+    assert len(lb) == len(li) and np.array_equal(np.sort(lines[lb], axis=1), np.sort(lines[li] - nxsector, axis=1))
+    rest = np.flatnonzero(~on_b & ~on_i)
+    lorder = np.concatenate([lb, rest, li])
+    new_of_old_ln = np.empty(len(lorder), dtype=np.int64)
+    new_of_old_ln[lorder] = np.arange(len(lorder))
+    mesh.reorder_lines(new_of_old_ln)
+    mesh.dos = SymInfo(DOS, 0, nxb, nxsector, 0, len(lb), len(lines) - len(lb))
+    return mesh

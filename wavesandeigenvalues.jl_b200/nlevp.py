@@ -793,3 +793,17 @@ def beyn(L, G, l=5, K=1, N=16, tol=0.0, pos_test=True, output=True, random=False
     K = max(K, l // d + int(l % d != 0))
     A = compute_moment_matrices(L, G, l=min(l, d), K=K, N=N, group=group, stats=stats)
     return moments2eigs(A, G, tol=tol, pos_test=pos_test, output=output)
+
+
+def bloch_expand(mesh, sol_or_vec, b="b"):
+    """Bloch.jl:120-143: expand a unit-cell vector to the full annulus, sector s multiplied by exp(2 pi i b s / DOS)."""
+    d = mesh.dos
+    if isinstance(sol_or_vec, Solution):
+        vec, B = sol_or_vec.v, sol_or_vec.params[b]
+    else:
+        vec, B = np.asarray(sol_or_vec), (0 if isinstance(b, str) else b)
+    v = np.zeros(d.naxis + d.nxsector * d.DOS, dtype=complex)
+    v[: d.naxis] = vec[: d.naxis]
+    for s_ in range(d.DOS):
+        v[d.naxis + s_ * d.nxsector: d.naxis + (s_ + 1) * d.nxsector] = vec[d.naxis: d.naxis + d.nxsector] * np.exp(2j * math.pi / d.DOS * B * s_)
+    return v
