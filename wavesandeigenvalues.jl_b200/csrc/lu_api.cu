@@ -278,6 +278,7 @@ static void factor_slot(wae_ctx* h, LuSolver& S, Family& F, int slot) {
   }
   if (r1.size() > 8) ok = false;
   S.r1_k = 0;
+  h->last_ms["factor_sym"] = ok ? 1.0 : 0.0;
   if (!ok) {
     wae_lu_factor_device(h, S, A, nullptr, 0);
     return;
@@ -423,7 +424,6 @@ int32_t wae_lu_factor(wae_ctx* h, int32_t lu_id, int32_t slot) {
   PhaseTimer t(h, "factor");
   factor_slot(h, S, F, slot);
   t.stop();
-  h->last_ms["factor_sym"] = S.sym_mode ? 1.0 : 0.0;
   WAE_API_END
 }
 
