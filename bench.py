@@ -355,7 +355,9 @@ def beyn_leg(W, torch, dist, ctx0, args, rank, world, dev, barrier, max_over_ran
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    A = nlevp.compute_moment_matrices(L, G, l=l, K=1, N=N, stats=stats)
+    rng = np.random.default_rng(0)
+    Vp = rng.random((dv.dim, l)) + 1j * rng.random((dv.dim, l))  # beyn(...; random=true), seeded: same V on every rank
+    A = nlevp.compute_moment_matrices(L, G, l=l, K=1, N=N, stats=stats, V=Vp)
     Om, P = nlevp.moments2eigs(A, G, rtol=1e-8, pos_test=True)
     e1.record()
     barrier()

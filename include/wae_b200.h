@@ -160,13 +160,15 @@ int32_t wae_eigs_si(wae_ctx* h, int32_t lu_id, int32_t fam_id, int32_t m_slot, i
 
 /* ---- Beyn moments --------------------------------------------------------------------
  * Replaces the integrand/gauss loop of beyn.jl:62-74,112-138 for the nodes handed in:
- *   A_p += w_j z_j^p L(z_j)^{-1} V,  p = 0..n_mom-1, V = first l identity columns.
+ *   A_p += w_j z_j^p L(z_j)^{-1} V,  p = 0..n_mom-1, V = first l identity columns (beyn.jl:45-48) or the
+ *   caller's (random, beyn.jl:42-43) probing matrix.
  * coeffs: n_nodes x n_terms complex (host-evaluated term scalars at each node).
  * A_out: device pointer (dim x l x n_mom complex, column-major) accumulated in place, so that
  * the caller can all-reduce it over ranks with NCCL (torch.distributed).                    */
 int32_t wae_beyn_moments(wae_ctx* h, int32_t fam_id, int32_t lu_id, int32_t n_nodes,
                          const double* z, const double* w, const double* coeffs,
-                         int32_t l, int32_t n_mom, void* A_out_device);
+                         int32_t l, int32_t n_mom, const double* V /* dim x l complex host array, NULL = identity columns */,
+                         void* A_out_device);
 
 #ifdef __cplusplus
 }

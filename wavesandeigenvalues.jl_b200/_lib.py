@@ -75,7 +75,7 @@ SIGNATURES = {
     "wae_lu_factor": (_i32, [_vp, _i32, _i32]),
     "wae_lu_solve": (_i32, [_vp, _i32, _i32, _i32, _pd]),
     "wae_eigs_si": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _pd, _pd, _pd, _pi32]),
-    "wae_beyn_moments": (_i32, [_vp, _i32, _i32, _i32, _pd, _pd, _pd, _i32, _i32, _vp]),
+    "wae_beyn_moments": (_i32, [_vp, _i32, _i32, _i32, _pd, _pd, _pd, _i32, _i32, _pd, _vp]),
 }
 
 
@@ -281,8 +281,10 @@ class Context:
         self._chk(self._l.wae_eigs_si(self.h, lid, fid, m_slot, trans, nev, _p(v0, _pd), _p(lam, _pd), _p(V, _pd), C.byref(ns)))
         return lam, V, ns.value
 
-    def beyn_moments(self, fid, lid, z, w, coeffs, l, n_mom, out_ptr):
+    def beyn_moments(self, fid, lid, z, w, coeffs, l, n_mom, out_ptr, V=None):
         z = np.ascontiguousarray(z, dtype=np.complex128)
         w = np.ascontiguousarray(w, dtype=np.complex128)
         cf = np.ascontiguousarray(coeffs, dtype=np.complex128)
-        self._chk(self._l.wae_beyn_moments(self.h, fid, lid, len(z), _p(z, _pd), _p(w, _pd), _p(cf, _pd), l, n_mom, _vp(out_ptr)))
+        if V is not None:
+            V = np.asfortranarray(V, dtype=np.complex128)
+        self._chk(self._l.wae_beyn_moments(self.h, fid, lid, len(z), _p(z, _pd), _p(w, _pd), _p(cf, _pd), l, n_mom, _p(V, _pd), _vp(out_ptr)))

@@ -574,7 +574,7 @@ int32_t wae_eigs_si(wae_ctx* h, int32_t lu_id, int32_t fam_id, int32_t m_slot, i
 }
 
 int32_t wae_beyn_moments(wae_ctx* h, int32_t fam_id, int32_t lu_id, int32_t n_nodes, const double* z, const double* w,
-                         const double* coeffs, int32_t l, int32_t n_mom, void* A_out) {
+                         const double* coeffs, int32_t l, int32_t n_mom, const double* V, void* A_out) {
   WAE_API_BEGIN
   CUDA_CHECK(cudaSetDevice(h->device));
   LuSolver& S = get_lu(h, lu_id);
@@ -586,6 +586,7 @@ int32_t wae_beyn_moments(wae_ctx* h, int32_t fam_id, int32_t lu_id, int32_t n_no
   DevBuf<cplx>& X = S.d_io;
   X.reserve((size_t)n * l);
   const int slot = WAE_FAMILY_SLOTS - 1;
+  if (V) S.d_arn_V.upload((const cplx*)V, (size_t)n * l, st);  // the probing matrix is kept in the (otherwise idle) Arnoldi workspace
   double t_fac = 0, t_sol = 0;
   for (int j = 0; j < n_nodes; j++) {
     wae_combine_device(h, F, coeffs + 2 * (size_t)j * F.n_terms, slot);
@@ -596,7 +597,10 @@ int32_t wae_beyn_moments(wae_ctx* h, int32_t fam_id, int32_t lu_id, int32_t n_no
       t_fac += h->last_ms["factor"];
     }
     PhaseTimer t(h, "solve");
-    identity_cols_kernel<<<(unsigned)(((size_t)n * l + 255) / 256), 256, 0, st>>>(n, l, X.p);
+    if (V)
+      CUDA_CHECK(cudaMemcpyAsync(X.p, S.d_arn_V.p, (size_t)n * l * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
+    else
+      identity_cols_kernel<<<(unsigned)(((size_t)n * l + 255) / 256), 256, 0, st>>>(n, l, X.p);
     wae_lu_solve_device(h, S, 0, l, X.p, S.refine_steps);
     moment_accum_kernel<<<(unsigned)(((size_t)n * l + 255) / 256), 256, 0, st>>>(X.p, n * l, n_mom, make_double2(w[2 * j], w[2 * j + 1]),
                                                                                  make_double2(z[2 * j], z[2 * j + 1]), (cplx*)A_out);

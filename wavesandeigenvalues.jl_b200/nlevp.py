@@ -726,7 +726,7 @@ def allreduce_moments(A, group=None):
     return A
 
 
-def compute_moment_matrices(L, G, l=5, K=1, N=16, group=None, stats=None):
+def compute_moment_matrices(L, G, l=5, K=1, N=16, group=None, stats=None, V=None):
     """Moments A_p = sum_j w_j z_j^p L(z_j)^{-1} V, p < 2K, V = first l identity columns (beyn.jl:62-74).
 
     The quadrature nodes are sharded round-robin over the ranks of ``group`` (torch.distributed, NCCL):
@@ -750,7 +750,7 @@ def compute_moment_matrices(L, G, l=5, K=1, N=16, group=None, stats=None):
     A = torch.zeros((2 * K, l, d), dtype=torch.complex128, device=f"cuda:{ctx.device}")  # == (d,l,2K) column-major
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     if len(mine):
-        ctx.beyn_moments(dev.fid, dev.lu(), zs[mine], ws[mine], coeffs, l, 2 * K, A.data_ptr())
+        ctx.beyn_moments(dev.fid, dev.lu(), zs[mine], ws[mine], coeffs, l, 2 * K, A.data_ptr(), V=V)
     if stats is not None:
         stats["factorizations"] = stats.get("factorizations", 0) + len(mine)
         stats["factor_ms"] = stats.get("factor_ms", 0.0) + ctx.last_ms("beyn_factor_total")
@@ -785,13 +785,17 @@ def moments2eigs(A, G=None, tol=0.0, pos_test=True, output=False, rtol=0.0):
     return Om, P
 
 
-def beyn(L, G, l=5, K=1, N=16, tol=0.0, pos_test=True, output=True, random=False, group=None, stats=None):
+def beyn(L, G, l=5, K=1, N=16, tol=0.0, pos_test=True, output=True, random=False, group=None, stats=None, seed=0):
     """beyn.jl:34-110.  N is the number of quadrature nodes PER polygon edge."""
-    if random:
-        raise NotImplementedError("random=True: the accelerated path uses V = first l identity columns (beyn.jl:45-48)")
     d = L.size()
     K = max(K, l // d + int(l % d != 0))
-    A = compute_moment_matrices(L, G, l=min(l, d), K=K, N=N, group=group, stats=stats)
+    V = None
+    if random and l < d:
+        # beyn.jl:42-43 uses rand(ComplexF64,d,l) (unseeded); here the probing matrix is seeded so that every rank of a
+        # sharded run draws the same V (and runs are reproducible)
+        rng = np.random.default_rng(seed)
+        V = rng.random((d, l)) + 1j * rng.random((d, l))
+    A = compute_moment_matrices(L, G, l=min(l, d), K=K, N=N, group=group, stats=stats, V=V)
     return moments2eigs(A, G, tol=tol, pos_test=pos_test, output=output)
 
 
