@@ -329,7 +329,7 @@ def assembly_leg(W, ctx0, n, hbm, hbm_src):
     res = {"value": ntet / med / 1e3, "unit": "Mtets/s", "tets": ntet, "dofs": dim, "nnz": int(nnz), "kernel_ms": med,
            "roofline": {"bound": "hbm", "achieved": alg / med / 1e6, "peak": hbm, "unit": "GB/s", "frac": alg / med / 1e6 / hbm,
                         "traffic": None, "peak_source": hbm_src, "algorithmic_bytes_per_tet": alg / ntet,
-                        "kernel": "assemble_tet_gather<10> (P2 M+K, owner-computes)"}}
+                        "kernel": "assemble_tet_pairs<10> (P2 M+K, owner-computes pair program)"}}
     ctx.close()
     return res
 

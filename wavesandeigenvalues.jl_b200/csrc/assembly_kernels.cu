@@ -5,10 +5,12 @@
 // Two generations of the tetrahedral M/K kernel live here:
 //   * assemble_tet_atomic : scatter through a precomputed slot map with fp64 RED atomics
 //     (any operator, any c; used for small sub-domain operators and as cross-check)
-//   * assemble_tet_gather : owner-computes patches, element matrices staged in shared memory,
-//     every nonzero written exactly once in a fixed summation order (the production path
-//     for the big M+K pass; see assembly_symbolic.cpp for the gather program).
+//   * assemble_tet_pairs  : owner-computes patches, coordinates and program staged in shared memory by bulk
+//     copies, every nonzero written exactly once in a fixed summation order (the production path
+//     for the big M+K pass; see assembly_symbolic.cpp for the pair program).
 #include <cuda_runtime.h>
+
+#include <algorithm>
 
 #include "fem_gen.h"
 #include "wae_internal.h"
@@ -255,155 +257,261 @@ void wae_launch_flame(wae_ctx* h, const int32_t* d_tets, int64_t n, const int32_
   CUDA_CHECK(cudaGetLastError());
 }
 
-// ---- generation 2: owner-computes gather ------------------------------------------------
-// One CTA per patch.  Phase A: one staged element per thread -> packed symmetric stiffness
-// (NSYM entries, already scaled by -c^2 |det|) and |det| into shared memory.  Phase B: one warp
-// per owned column; lanes walk the column's nonzeros, a warp scan of the per-slot source counts
-// gives each lane its offset into the packed source list; K = sum of staged entries,
-// M = table(sym) * sum of |det| (the mass entry of a DOF pair depends only on the pair's type,
-// which is the same in every element that contains the pair).  Every output is written once.
+// ---- generation 2: owner-computes pair program ---------------------------------------------
+// Persistent kernel, one CTA per SM, patches round-robin (see assembly_symbolic.cpp for the program).  Per patch:
+//   fetch        the program blob (local vertex numbers, element ids, group words, counts, store chunks) and the patch's vertex
+//                coordinates arrive in shared memory by one bulk copy each (TMA, mbarrier), double-buffered: the copies for the
+//                next patch run while the current one is processed; its slot words / store program are prefetched into L2.
+//   element pass one staged element per lane.  Coordinates come from shared memory; the gram entries stay in registers; the packed
+//                upper triangle of the stiffness (already times -c^2 |det|) and mass matrix is visited entry by entry (compile-time
+//                index s) and every entry the patch owns is stored as a (K, M) pair into its shared-memory slot.
+//   summation    one group of 32 units per warp step; lane l adds the slots base + 32 k + (l xor (k mod 8)), k < count -- 16-byte
+//                loads, conflict-free -- and leaves the sum in slot base + l.
+//   store pass   32 consecutive nonzeros of a column per warp step, each fetched from the slot the program names: full-line stores.
+// Every nonzero is written exactly once, no atomics, fixed summation order (bit-reproducible), no memset of the outputs.
 template <int NLOC>
-struct SymTab;
+struct SymVisit;
 template <>
-struct SymTab<4> {
-  static constexpr int NSYM = 10;
-  __device__ static const double* mass() { return WAE_P1_TET_MASS_SYM; }
-  __device__ static void stiff(const double* g, double* K) { wae_p1_tet_stiff_sym(g, K); }
+struct SymVisit<4> {
+  template <class F>
+  __device__ __forceinline__ static void run(const double* g, F&& f) { wae_p1_tet_sym_visit(g, f); }
 };
 template <>
-struct SymTab<10> {
-  static constexpr int NSYM = 55;
-  __device__ static const double* mass() { return WAE_P2_TET_MASS_SYM; }
-  __device__ static void stiff(const double* g, double* K) { wae_p2_tet_stiff_sym(g, K); }
+struct SymVisit<10> {
+  template <class F>
+  __device__ __forceinline__ static void run(const double* g, F&& f) { wae_p2_tet_sym_visit(g, f); }
 };
 
-// Shared-memory staging layout: 64 doubles per staged element (NSYM stiffness entries, |det| at logical index 63), XOR-swizzled
-// with the element index so that lanes reading the same logical entry of different elements hit different banks:
-//   physical index of (element t, entry e) = t*64 + (e ^ (t & 63)).   A source code is t*64 + e, so the address of the
-// stiffness entry is one LOP3 away from the code and the |det| entry is (code | 63) ^ (t & 63).  Element index WAE_GATHER_PAD
-// is a block of zeros: padding sources point there, which removes every branch from the inner loop.
-__device__ __forceinline__ double lds_f64(uint32_t addr) {
-  double v;
-  asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));  // not volatile: smem is read-only after the barrier
-  return v;
+__device__ __forceinline__ void sts_pair(uint32_t addr, double k, double m) {
+  asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(k), "d"(m) : "memory");
 }
 
-template <int NLOC>
-__global__ void __launch_bounds__(512, 2) assemble_tet_gather(
-    const double* __restrict__ xyz, const uint32_t* __restrict__ conn, const int32_t* __restrict__ elems,
-    const double* __restrict__ c, const int64_t* __restrict__ patch_tet_ptr, const int32_t* __restrict__ patch_tets,
-    const int64_t* __restrict__ patch_grp_ptr, const int64_t* __restrict__ patch_src_ptr, const uint32_t* __restrict__ grp,
-    const int32_t* __restrict__ out_idx, const uint16_t* __restrict__ src, int pad_elem, double mass_scale, double* __restrict__ out_m,
-    double* __restrict__ out_k, int dbg) {
-  constexpr int NSYM = SymTab<NLOC>::NSYM;
-  constexpr int SL = NLOC == 4 ? 4 : 6;     // log2 of the staging stride (16 / 64 doubles per element)
-  constexpr unsigned SM_ = (1u << SL) - 1;  // mask of the entry index; |det| lives at logical entry SM_
-  extern __shared__ double sm[];
-  __shared__ double s_mass[NSYM];
-  __shared__ int s_next;
-  const int p = blockIdx.x;
-  const int64_t t0 = patch_tet_ptr[p];
-  const int nt = (int)(patch_tet_ptr[p + 1] - t0);
-  if (threadIdx.x < NSYM) s_mass[threadIdx.x] = SymTab<NLOC>::mass()[threadIdx.x] * mass_scale;
-  if (threadIdx.x == 0) s_next = blockDim.x >> 5;
-  if (threadIdx.x <= SM_) sm[(pad_elem << SL) + threadIdx.x] = 0.0;
-  // phase A: one staged element per thread
-  for (int t = threadIdx.x; t < nt && dbg != 2; t += blockDim.x) {
-    int32_t e = patch_tets[t0 + t];
-    const uint32_t* d = conn + (size_t)elems[e] * NLOC;
-    uint32_t v[4] = {d[0], d[1], d[2], d[3]};
-    TetGeom tg;
-    tet_geom(xyz, v, tg);
-    double* dst = sm + ((size_t)t << SL);
-    const int sw = t & SM_;
-    if (out_k) {
-      double cc = c[e];
-      double g[10];
-      tet_gram(tg, -cc * cc * tg.adet, g);
-      double K[NSYM];
-      SymTab<NLOC>::stiff(g, K);
+// ---- bulk copy (TMA, 1-D) + mbarrier helpers ----------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t mbar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t mbar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t mbar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(mbar)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok)
+                 : "r"(mbar), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+
+// vertex coordinates in patch order: pxyz[3 i .. 3 i + 2] = xyz of mesh vertex gvtx[i]
+__global__ void gather_patch_xyz_kernel(const double* __restrict__ xyz, const uint32_t* __restrict__ gvtx, int64_t n, double* __restrict__ pxyz) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * n) return;
+  pxyz[i] = xyz[3 * (size_t)gvtx[i / 3] + (i % 3)];
+}
+
+// CooTrafo from coordinates staged in shared memory (3 doubles per patch-local vertex)
+__device__ __forceinline__ void tet_geom_smem(const double* __restrict__ px, const uint2 lv, TetGeom& t) {
+  const double* p0 = px + 3 * (lv.x & 0xFFFFu);
+  const double* p1 = px + 3 * (lv.x >> 16);
+  const double* p2 = px + 3 * (lv.y & 0xFFFFu);
+  const double* p3 = px + 3 * (lv.y >> 16);
+  const double x3 = p3[0], y3 = p3[1], z3 = p3[2];
+  double a[3][3];  // a[r][k] = component r of edge k
+  a[0][0] = p0[0] - x3; a[1][0] = p0[1] - y3; a[2][0] = p0[2] - z3;
+  a[0][1] = p1[0] - x3; a[1][1] = p1[1] - y3; a[2][1] = p1[2] - z3;
+  a[0][2] = p2[0] - x3; a[1][2] = p2[1] - y3; a[2][2] = p2[2] - z3;
+  double c00 = a[1][1] * a[2][2] - a[1][2] * a[2][1];
+  double c01 = a[1][2] * a[2][0] - a[1][0] * a[2][2];
+  double c02 = a[1][0] * a[2][1] - a[1][1] * a[2][0];
+  double det = a[0][0] * c00 + a[0][1] * c01 + a[0][2] * c02;
+  double id = 1.0 / det;
+  t.G[0][0] = c00 * id;
+  t.G[0][1] = (a[0][2] * a[2][1] - a[0][1] * a[2][2]) * id;
+  t.G[0][2] = (a[0][1] * a[1][2] - a[0][2] * a[1][1]) * id;
+  t.G[1][0] = c01 * id;
+  t.G[1][1] = (a[0][0] * a[2][2] - a[0][2] * a[2][0]) * id;
+  t.G[1][2] = (a[0][2] * a[1][0] - a[0][0] * a[1][2]) * id;
+  t.G[2][0] = c02 * id;
+  t.G[2][1] = (a[0][1] * a[2][0] - a[0][0] * a[2][1]) * id;
+  t.G[2][2] = (a[0][0] * a[1][1] - a[0][1] * a[1][0]) * id;
 #pragma unroll
-      for (int k = 0; k < NSYM; k++) dst[k ^ sw] = K[k];
+  for (int d = 0; d < 3; d++) t.G[3][d] = -(t.G[0][d] + t.G[1][d] + t.G[2][d]);
+  t.adet = fabs(det);
+}
+
+// entries s in [LO, HI) of one staged element: the element's gram entries from the staged coordinates, then the owned (K, M) pairs
+template <int NLOC, int LO, int HI>
+__device__ __forceinline__ void element_part(const double* __restrict__ px, const uint2 lv, double cc, double mass_scale,
+                                             const uint32_t* __restrict__ dp, uint32_t sbase) {
+  TetGeom tg;
+  tet_geom_smem(px, lv, tg);
+  double g[10];
+  tet_gram(tg, -cc * cc * tg.adet, g);
+  const double md = tg.adet * mass_scale;
+  uint32_t w = 0;
+  SymVisit<NLOC>::run(g, [&](auto S, double k, double m) {
+    constexpr int s = decltype(S)::value;
+    if constexpr (s >= LO && s < HI) {
+      if (!(s & 1) || s == LO) w = dp[(s >> 1) * 32];  // the compiler hoists these independent loads as far as registers allow
+      const uint32_t sl = (s & 1) ? (w >> 16) : (w & 0xFFFFu);
+      if (sl != 0xFFFFu) sts_pair(sbase + (sl << 4), k, m * md);
     }
-    dst[SM_ ^ sw] = tg.adet;
+  });
+}
+
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
+
+// Persistent: CTA b works on patches b, b + gridDim.x, ...  While patch i is processed, the program blob and the staged
+// coordinates of patch i+1 arrive in the other shared-memory buffer (bulk copy + mbarrier), its slot words and store program
+// are prefetched into L2, and the descriptor of patch i+2 is fetched.
+// MODE bit 0: mass -> out_m, bit 1: stiffness -> out_k
+template <int NLOC, int MODE>
+__global__ void __launch_bounds__(1024, 1) assemble_tet_pairs(const int64_t* __restrict__ desc, int n_patch, const uint8_t* __restrict__ blob,
+                                                               const double* __restrict__ pxyz, const double* __restrict__ c,
+                                                               const uint32_t* __restrict__ dest, const uint16_t* __restrict__ res,
+                                                               int slot_bytes, int pxyz_bytes, int buf_bytes, double mass_scale,
+                                                               double* __restrict__ out_m, double* __restrict__ out_k, int dbg) {
+  constexpr int NSYM = NLOC * (NLOC + 1) / 2, NPK = (NSYM + 1) / 2;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ __align__(8) unsigned long long mbar_storage[2];
+  __shared__ __align__(16) long long sdesc[3][8];
+  double2* slots = reinterpret_cast<double2*>(smem_raw);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(slots);
+  const uint32_t mbar0 = (uint32_t)__cvta_generic_to_shared(&mbar_storage[0]);
+  const uint32_t lane16 = (uint32_t)lane << 4;
+  const int G = gridDim.x;
+  int p = blockIdx.x;
+  if (p >= n_patch) return;
+  // issue the bulk copies of the patch described by sdesc[ds] into buffer b (one thread)
+  auto fetch = [&](int ds, int b) {
+    const long long* D = sdesc[ds];
+    const int* I = reinterpret_cast<const int*>(D + 4);
+    const uint32_t mb = mbar0 + 8u * b, dst = sbase + slot_bytes + (uint32_t)b * buf_bytes;
+    mbar_expect_tx(mb, (uint32_t)I[4] + (uint32_t)I[1] * 24u);
+    bulk_g2s(dst + pxyz_bytes, blob + D[0], (uint32_t)I[4], mb);
+    bulk_g2s(dst, pxyz + D[1], (uint32_t)I[1] * 24u, mb);
+    bulk_prefetch_l2(dest + (size_t)D[2] * NPK * 32, (uint32_t)((I[0] + 31) >> 5) * NPK * 128u);
+    bulk_prefetch_l2(res + (size_t)D[3] * 32, (uint32_t)I[3] * 64u);
+  };
+  if (threadIdx.x < 8) {
+    sdesc[0][threadIdx.x] = desc[(size_t)p * 8 + threadIdx.x];
+    if (p + G < n_patch) sdesc[1][threadIdx.x] = desc[(size_t)(p + G) * 8 + threadIdx.x];
+  }
+  if (threadIdx.x == 0) {
+    mbar_init(mbar0, 1);
+    mbar_init(mbar0 + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (dbg == 1) return;
-  // phase B: one group of WAE_GATHER_GROUP owned nonzeros per warp iteration (GS/32 per lane); the
-  // nonzeros of a patch are sorted by source count, so all lanes run (almost) the same trip count, branch-free
-  const int lane = threadIdx.x & 31;
-  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(sm);
-  const int g0 = (int)patch_grp_ptr[p], ng = (int)(patch_grp_ptr[p + 1] - patch_grp_ptr[p]);
-  const uint16_t* psrc = src + patch_src_ptr[p] + lane;
-  constexpr int GS = WAE_GATHER_GROUP;
-  int g = threadIdx.x >> 5;
-  while (g < ng) {
-    const uint32_t hdr = grp[g0 + g];
-    const int niter = hdr & 255;
-    const uint16_t* sp = psrc + (hdr >> 8);
-    const int32_t* op = out_idx + (size_t)(g0 + g) * GS + lane;
-    constexpr int NJ = GS / 32;  // nonzeros per lane and group
-    int oi[NJ];
-#pragma unroll
-    for (int j = 0; j < NJ; j++) oi[j] = op[j * 32];
-    double ak[NJ], ad[NJ];
-    unsigned first[NJ];
-#pragma unroll
-    for (int j = 0; j < NJ; j++) {
-      ak[j] = ad[j] = 0.0;
-      first[j] = niter ? sp[j * 32] : 0u;
+  if (threadIdx.x == 0) fetch(0, 0);
+  for (int i = 0; p < n_patch; i++, p += G) {
+    const int b = i & 1, ds = i % 3;
+    if (threadIdx.x == 0 && p + G < n_patch) fetch((i + 1) % 3, b ^ 1);
+    long long dnext = 0;
+    if (threadIdx.x < 8 && p + 2 * G < n_patch) dnext = desc[(size_t)(p + 2 * G) * 8 + threadIdx.x];
+    const longlong2 d23 = *reinterpret_cast<const longlong2*>(&sdesc[ds][2]);
+    const int4 i03 = *reinterpret_cast<const int4*>(&sdesc[ds][4]);
+    const int4 i47 = *reinterpret_cast<const int4*>(&sdesc[ds][6]);
+    const int nt = i03.x, ng = i03.z, nc = i03.w;
+    const unsigned char* buf = smem_raw + slot_bytes + (size_t)b * buf_bytes;
+    const double* px = reinterpret_cast<const double*>(buf);
+    const unsigned char* pb = buf + pxyz_bytes;
+    const uint2* lvtx = reinterpret_cast<const uint2*>(pb);
+    const int32_t* tets = reinterpret_cast<const int32_t*>(pb + i47.y);
+    const uint32_t* grp = reinterpret_cast<const uint32_t*>(pb + i47.z);
+    const unsigned char* cnt = pb + i47.w;
+    const uint2* chunk = reinterpret_cast<const uint2*>(pb + i47.w + 32 * ng);
+    const int nwb = (nt + 31) >> 5;
+    mbar_wait(mbar0 + 8u * b, (uint32_t)(i >> 1) & 1u);
+    // ---- element pass: one staged element per lane, 32 elements per warp step
+    for (int wb = warp; wb < nwb && dbg != 2; wb += nwarp) {
+      const int t = wb * 32 + lane;
+      if (t >= nt) continue;
+      const uint32_t* dp = dest + ((size_t)(d23.x + wb) * NPK) * 32 + lane;
+      const double cc = (MODE & 2) ? c[tets[t]] : 0.0;
+      element_part<NLOC, 0, NSYM>(px, lvtx[t], cc, mass_scale, dp, sbase);
     }
-#pragma unroll 4
-    for (int k = 0; k < niter; k++) {
-      unsigned cd[NJ];
+    __syncthreads();
+    // first batch of the store pass: issued here so that its latency hides behind the summation pass
+    const uint16_t* rp = res + (size_t)d23.y * 32 + lane;
+    uint32_t r[4];
 #pragma unroll
-      for (int j = 0; j < NJ; j++) cd[j] = sp[k * GS + j * 32];
-#pragma unroll
-      for (int j = 0; j < NJ; j++) {
-        const unsigned sw = (cd[j] >> SL) & SM_;
-        if (out_k) ak[j] += lds_f64(sbase + ((cd[j] ^ sw) << 3));
-        ad[j] += lds_f64(sbase + (((cd[j] | SM_) ^ sw) << 3));
+    for (int u = 0; u < 4; u++) r[u] = warp + u * nwarp < nc ? rp[(size_t)(warp + u * nwarp) * 32] : 0;
+    // ---- summation pass: lane l of group g adds slots base + 32 k + (l xor (k mod 8)), k < count; the sum stays in slot base + l
+    for (int g = warp; g < ng && dbg != 1; g += nwarp) {
+      const uint32_t hdr = grp[g];
+      const int cn = cnt[g * 32 + lane];
+      const uint32_t base = sbase + ((hdr >> 8) << 4);
+      double ak = 0.0, am = 0.0;
+#pragma unroll 1
+      for (int k = 0; k < cn; k++) {
+        double vx, vy;
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(vx), "=d"(vy) : "r"(base + (k << 9) + (lane16 ^ ((k & 7) << 4))) : "memory");
+        ak += vx;
+        am += vy;
       }
+      if (cn) sts_pair(base + lane16, ak, am);
     }
-    if (dbg == 3) {  // timing experiment: no scattered stores (one dependent store per lane and group keeps the work alive)
-      double z = 0.0;
-      for (int j = 0; j < NJ; j++) z += ak[j] + ad[j];
-      if (z == 1.2345e-300 && out_k) out_k[oi[0] & 1023] = z;
-    } else
+    __syncthreads();
+    // ---- store pass: at most 32 consecutive nonzeros (one 256-byte line of each value array) per step, four steps in flight
+    for (int ch = warp; ch < nc && dbg != 1 && dbg != 3; ch += 4 * nwarp) {
+      uint2 h[4];
 #pragma unroll
-    for (int j = 0; j < NJ; j++)
-      if (oi[j] >= 0) {
-        if (out_k) out_k[oi[j]] = ak[j];
-        if (out_m) out_m[oi[j]] = s_mass[first[j] & SM_] * ad[j];
+      for (int u = 0; u < 4; u++) {
+        const int cu = ch + u * nwarp;
+        h[u] = cu < nc ? chunk[cu] : make_uint2(0, 0);
+        if (ch != warp) r[u] = cu < nc ? rp[(size_t)cu * 32] : 0;
       }
-    if (lane == 0) g = atomicAdd(&s_next, 1);
-    g = __shfl_sync(0xffffffffu, g, 0);
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (lane < (int)h[u].y) {
+          const double2 v = slots[r[u]];
+          if (MODE & 2) out_k[(size_t)h[u].x + lane] = v.x;
+          if (MODE & 1) out_m[(size_t)h[u].x + lane] = v.y;
+        }
+    }
+    if (threadIdx.x < 8 && p + 2 * G < n_patch) sdesc[(i + 2) % 3][threadIdx.x] = dnext;
+    __syncthreads();  // slots, the program buffer and the descriptor ring are free for the next patches
   }
 }
 
 void wae_launch_assemble_gather(wae_ctx* h, Pattern& P, const double* d_c, double* d_mass, double* d_stiff, double mass_scale) {
   auto& G = P.gather;
   if (!G.built || G.n_patch == 0) return;
-  const int nsym = h->nloc == 4 ? 10 : 55;
-  size_t smem = (size_t)(G.max_tets + 1) * (h->nloc == 4 ? 16 : 64) * sizeof(double);  // +1: the zero block the padding sources point to
-  static bool attr_set[2] = {false, false};
+  if (G.xyz_version != h->xyz_version) {  // refresh the patch-ordered coordinates
+    gather_patch_xyz_kernel<<<(unsigned)((3 * G.n_pv + 255) / 256), 256, 0, h->stream>>>(h->d_xyz.p, G.d_gvtx.p, G.n_pv, G.d_pxyz.p);
+    G.xyz_version = h->xyz_version;
+    h->launches++;
+  }
+  const int slot_bytes = G.max_slots * 16, pxyz_bytes = (G.max_nv * 24 + 15) & ~15, buf_bytes = pxyz_bytes + ((G.max_blob + 15) & ~15);
+  const size_t smem = (size_t)slot_bytes + 2 * (size_t)buf_bytes;
+  static bool attr_set[4] = {false, false, false, false};
   const int dbg = getenv("WAE_GATHER_DBG") ? atoi(getenv("WAE_GATHER_DBG")) : 0;
+  int threads = smem > 113 * 1024 ? 1024 : 512;  // one or two CTAs per SM, 64 registers per thread either way
+  if (const char* env = getenv("WAE_GATHER_THREADS")) threads = atoi(env);
+  const int grid = std::min(G.n_patch, h->sm_count * (smem > 113 * 1024 ? 1 : 2));
+  auto launch = [&](auto kern, int which) {
+    if (!attr_set[which]) {
+      CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
+      attr_set[which] = true;
+    }
+    kern<<<grid, threads, smem, h->stream>>>(G.d_desc.p, G.n_patch, G.d_blob.p, G.d_pxyz.p, d_c, G.d_dest.p, G.d_res.p, slot_bytes, pxyz_bytes,
+                                             buf_bytes, mass_scale, d_mass, d_stiff, dbg);
+  };
+  const bool both = d_stiff != nullptr;
   if (h->nloc == 4) {
-    if (!attr_set[0]) {
-      CUDA_CHECK(cudaFuncSetAttribute(assemble_tet_gather<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
-      attr_set[0] = true;
-    }
-    assemble_tet_gather<4><<<G.n_patch, 512, smem, h->stream>>>(h->d_xyz.p, h->d_tets.p, P.d_elems.p, d_c, G.d_patch_tet_ptr.p, G.d_patch_tets.p,
-                                                                G.d_patch_grp_ptr.p, G.d_patch_src_ptr.p, G.d_grp.p, G.d_out_idx.p, G.d_src.p,
-                                                                G.max_tets, mass_scale, d_mass, d_stiff, dbg);
+    if (both) launch(assemble_tet_pairs<4, 3>, 0); else launch(assemble_tet_pairs<4, 1>, 1);
   } else {
-    if (!attr_set[1]) {
-      CUDA_CHECK(cudaFuncSetAttribute(assemble_tet_gather<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
-      attr_set[1] = true;
-    }
-    assemble_tet_gather<10><<<G.n_patch, 512, smem, h->stream>>>(h->d_xyz.p, h->d_tets.p, P.d_elems.p, d_c, G.d_patch_tet_ptr.p, G.d_patch_tets.p,
-                                                                 G.d_patch_grp_ptr.p, G.d_patch_src_ptr.p, G.d_grp.p, G.d_out_idx.p, G.d_src.p,
-                                                                 G.max_tets, mass_scale, d_mass, d_stiff, dbg);
+    if (both) launch(assemble_tet_pairs<10, 3>, 2); else launch(assemble_tet_pairs<10, 1>, 3);
   }
   h->launches++;
   CUDA_CHECK(cudaGetLastError());
@@ -412,27 +520,35 @@ void wae_launch_assemble_gather(wae_ctx* h, Pattern& P, const double* d_c, doubl
 void wae_ensure_gather(wae_ctx* h, Pattern& P) {
   auto& G = P.gather;
   if (G.built) return;
-  // staged elements per patch: bounded by shared memory; WAE_GATHER_TETS overrides for tuning
-  const int stride = h->nloc == 4 ? 16 : 64;  // doubles per staged element
-  int target = h->nloc == 4 ? 840 : 208;      // 2 CTAs per SM
-  if (const char* env = getenv("WAE_GATHER_TETS")) target = atoi(env);
-  int cap = (int)((226 * 1024 - 1024) / (stride * sizeof(double))) - 1;
-  if (cap > 1022) cap = 1022;
-  if (target > cap) target = cap;
-  if (target < 64) target = 64;
+  // shared memory = slots (16 B each) + two buffers (staged coordinates + program blob of the current and the next patch);
+  // the loop below shrinks the slot count until everything fits one SM (one CTA per SM); WAE_GATHER_SLOTS overrides for tuning
+  int slot_cap = 12288;
+  if (const char* env = getenv("WAE_GATHER_SLOTS")) slot_cap = atoi(env);
+  slot_cap = std::max(1024, std::min(slot_cap, (226 * 1024) / 16));
   GatherHost GH;
-  wae_build_gather(h->xyz.data(), h->tets.data(), h->nloc, P, target, GH);
-  G.n_patch = (int)GH.patch_tet_ptr.size() - 1;
-  G.max_tets = GH.max_tets;
-  G.n_src = (int64_t)GH.src.size();
-  G.n_staged = (int64_t)GH.patch_tets.size();
-  G.d_patch_tet_ptr.upload(GH.patch_tet_ptr, h->stream);
-  G.d_patch_tets.upload(GH.patch_tets, h->stream);
-  G.d_patch_grp_ptr.upload(GH.patch_grp_ptr, h->stream);
-  G.d_patch_src_ptr.upload(GH.patch_src_ptr, h->stream);
-  G.d_grp.upload(GH.grp, h->stream);
-  G.d_out_idx.upload(GH.out_idx, h->stream);
-  G.d_src.upload(GH.src, h->stream);
+  const size_t smem_max = 226 * 1024;
+  for (;;) {
+    wae_build_gather(h->xyz.data(), h->tets.data(), h->nloc, P, slot_cap, GH);
+    const size_t need = (size_t)GH.max_slots * 16 + 2 * ((((size_t)GH.max_nv * 24 + 15) & ~(size_t)15) + (((size_t)GH.max_blob + 15) & ~(size_t)15));
+    if (need <= smem_max) break;
+    slot_cap -= (int)((need - smem_max) / 16) + 256;
+    if (slot_cap < 1024) WAE_THROW(WAE_E_INVALID, "pair program does not fit shared memory");
+  }
+  G.n_patch = GH.n_patch;
+  G.max_slots = GH.max_slots;
+  G.max_blob = GH.max_blob;
+  G.max_nv = GH.max_nv;
+  G.n_pairs = GH.n_pairs;
+  G.n_sources = GH.n_sources;
+  G.n_staged = GH.n_staged;
+  G.n_pv = (int64_t)GH.gvtx.size();
+  G.d_desc.upload(GH.desc, h->stream);
+  G.d_blob.upload(GH.blob, h->stream);
+  G.d_gvtx.upload(GH.gvtx, h->stream);
+  G.d_pxyz.alloc((size_t)G.n_pv * 3 + 2);
+  G.d_dest.upload(GH.dest, h->stream);
+  G.d_res.upload(GH.res, h->stream);
+  G.xyz_version = 0;
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
   G.built = true;
 }

@@ -106,24 +106,27 @@ void wae_build_slotmap(const uint32_t* conn, int nloc, const Pattern& P, std::ve
 }
 
 // ------------------------------------------------------------------------------------
-// Owner-computes gather program (tetrahedral patterns, symmetric operators M and K).
+// Owner-computes pair program (tetrahedral patterns, symmetric operators M and K).
 //
-// The elements of the pattern are cut into spatially compact patches; every DOF column is
-// owned by exactly one patch, which stages the element matrices of ALL elements touching
-// its owned columns in shared memory and then produces each owned nonzero by summing its
-// sources in a fixed order -- no atomics, every output written exactly once, bit-reproducible.
-// Element order inside the pattern is expected to be spatially coherent (the host mirror
-// sorts elements along a Morton curve before calling; any order is correct, only the halo
-// factor suffers).
+// Every entry (i, j) of M and K is the sum, over the elements that contain both DOFs, of one entry of the packed upper
+// triangle of the (symmetric) element matrix.  No atomics: every nonzero is written exactly once, sums run in a fixed
+// order (bit-reproducible), and all global stores are full, consecutive runs of the value arrays.
 //
-// Per patch p:
-//   patch_tets [patch_tet_ptr[p]..)   positions (in P.elems) of the staged elements
-//   patch_rows [patch_row_ptr[p]..)   owned DOF columns
-//   for each owned column, for each of its nonzeros (in pattern order):
-//       slot_cnt (u8)  number of sources,  src (u16) = tet_local*128 + a*nloc+b ... packed below
-// A source is (tet_local, sym) with sym = index of (min(a,b), max(a,b)) in the packed upper
-// triangle of the (symmetric) element matrix, a/b = local indices of the row / owned column
-// DOF, packed as tet_local * 64 + sym (sym < 55), tet_local < 1024, so that it fits 16 bits.
+//  * elements are ranked along a Morton curve; a DOF is owned by its incident element of lowest rank; DOFs are put in
+//    owner order ("positions") and cut into patches of consecutive positions.  A patch owns the COLUMNS of its DOFs and
+//    stages every element touching one of them, so it sees all sources of its nonzeros.
+//  * a source is (staged element t, packed index s of a local DOF pair).  If both DOFs of the pair are owned by the patch
+//    the source feeds nz(i,j) and nz(j,i) at once (one summation unit), otherwise only the entry in the owned column.
+//  * the units of a patch are sorted by their number of sources and cut into groups of 32 (one per lane); the k-th source
+//    of lane l of a group lives in shared-memory slot  group_base + 32 k + (l xor (k mod 8)), so the summation pass reads its slots with
+//    conflict-free, fully coalesced 16-byte loads and all lanes of a warp run (almost) the same trip count.  The sum is
+//    left in slot group_base + l.
+//  * the element pass needs, per staged element and local pair, the slot (0xFFFF: not owned): two 16-bit slots per word,
+//    stored (32-element block, word, lane)-major so that a warp reads them with coalesced 128-byte loads.
+//  * the store pass walks the owned columns in DOF order, 32 consecutive nonzeros per warp step: 2 bytes per nonzero
+//    name the slot that holds its sum.
+// Program size per tetrahedron of a P2 Kuhn mesh: 112 B per STAGED element (2.0-2.5 staged per tetrahedron), 2 B per
+// nonzero, 1 B per unit -- about 350 B next to 671 B of algorithmic traffic.
 // ------------------------------------------------------------------------------------
 static inline uint64_t spread21(uint64_t v) {  // interleave helper: 21 bits -> every third bit
   v &= 0x1fffff;
@@ -135,10 +138,10 @@ static inline uint64_t spread21(uint64_t v) {  // interleave helper: 21 bits -> 
   return v;
 }
 
-void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const Pattern& P, int target_tets, GatherHost& G) {
+void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const Pattern& P, int slot_cap, GatherHost& G) {
   const int64_t ne = (int64_t)P.elems.size();
   const int64_t dim = P.dim;
-  const int max_tets = 1022 < target_tets ? 1022 : target_tets;
+  const int nsym = nloc * (nloc + 1) / 2;
   std::vector<int64_t> nptr;
   std::vector<int32_t> nadj;
   node_to_elem(conn, nloc, P.elems, dim, nptr, nadj);
@@ -171,8 +174,10 @@ void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const P
     std::sort(key.begin(), key.end());
     for (int64_t i = 0; i < ne; i++) rank[key[i].second] = (int32_t)i;
   }
-  // owner of a DOF = its incident element of lowest Morton rank; DOFs processed in owner order
-  std::vector<int32_t> order;
+  // owner of a DOF = its incident element of lowest Morton rank; position = index in owner order
+  std::vector<int32_t> order;      // position -> DOF
+  std::vector<int32_t> pos(dim, -1);  // DOF -> position (-1: DOF not touched by the pattern's elements)
+  int max_inc = 1;
   {
     std::vector<std::pair<int32_t, int32_t>> key;
     key.reserve(dim);
@@ -181,138 +186,274 @@ void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const P
       int32_t best = rank[nadj[nptr[i]]];
       for (int64_t q = nptr[i] + 1; q < nptr[i + 1]; q++) best = std::min(best, rank[nadj[q]]);
       key.emplace_back(best, (int32_t)i);
+      max_inc = std::max<int>(max_inc, (int)(nptr[i + 1] - nptr[i]));
     }
     std::sort(key.begin(), key.end());
     order.reserve(key.size());
-    for (auto& k : key) order.push_back(k.second);
-  }
-  G = GatherHost();
-  G.patch_row_ptr.push_back(0);
-  G.patch_tet_ptr.push_back(0);
-  // pass 1: cut the owner-ordered DOF list into patches (serial, cheap)
-  std::vector<int32_t> mark(ne, -1);
-  std::vector<int32_t> cur;
-  size_t pos = 0;
-  while (pos < order.size()) {
-    cur.clear();
-    while (pos < order.size()) {
-      int32_t dof = order[pos];
-      int nnew = 0;
-      for (int64_t q = nptr[dof]; q < nptr[dof + 1]; q++) nnew += mark[nadj[q]] < 0;
-      if (!cur.empty() && (int)cur.size() + nnew > max_tets) break;
-      if (nnew > max_tets) WAE_THROW(WAE_E_INVALID, "a DOF is shared by %d elements; gather patches hold at most %d", nnew, max_tets);
-      for (int64_t q = nptr[dof]; q < nptr[dof + 1]; q++) {
-        int32_t e = nadj[q];
-        if (mark[e] < 0) {
-          mark[e] = (int32_t)cur.size();
-          cur.push_back(e);
-        }
-      }
-      G.patch_rows.push_back(dof);
-      pos++;
+    for (auto& k : key) {
+      pos[k.second] = (int32_t)order.size();
+      order.push_back(k.second);
     }
-    // stage elements in Morton order inside the patch (coherent coordinate reads)
-    std::sort(cur.begin(), cur.end(), [&](int32_t a, int32_t b) { return rank[a] < rank[b]; });
-    for (int32_t e : cur) {
-      G.patch_tets.push_back(e);
-      mark[e] = -1;
-    }
-    G.max_tets = std::max<int>(G.max_tets, (int)cur.size());
-    G.patch_row_ptr.push_back((int64_t)G.patch_rows.size());
-    G.patch_tet_ptr.push_back((int64_t)G.patch_tets.size());
   }
-  // pass 2: bucketed gather program (parallel over patches).  All nonzeros owned by a patch are sorted by their number
-  // of sources (descending) and cut into groups of 32 (one per lane); a group stores its sources TRANSPOSED -- for
-  // iteration k the 32 codes of the 32 lanes are contiguous (0xFFFF = no source) -- so that every lane of a warp runs the
-  // same trip count and the source codes are read with one coalesced load per iteration.
-  const int64_t npatch = (int64_t)G.patch_row_ptr.size() - 1;
-  const int code_shift = nloc == 4 ? 4 : 6;  // staging stride of the kernel: 16 (P1) / 64 (P2) doubles per element
-  const uint16_t pad_code = (uint16_t)(G.max_tets << code_shift);  // element index max_tets = block of zeros in shared memory
-  std::vector<std::vector<uint16_t>> psrc(npatch);
-  std::vector<std::vector<int32_t>> pout(npatch);
-  std::vector<std::vector<uint32_t>> pgrp(npatch);
-  std::atomic<int> too_many(0);
-  parallel_for(npatch, [&](int64_t pa, int64_t pb) {
-    std::vector<std::pair<int32_t, int32_t>> lmap;      // (element, staged index) sorted by element
-    std::vector<std::pair<int32_t, uint16_t>> contrib;  // (row, code) of one column
-    struct Slot { int32_t out; int32_t first; int32_t cnt; };
-    std::vector<Slot> slots;
-    std::vector<uint16_t> codes;
-    for (int64_t p = pa; p < pb; p++) {
-      lmap.clear();
-      for (int64_t t = G.patch_tet_ptr[p]; t < G.patch_tet_ptr[p + 1]; t++)
-        lmap.emplace_back(G.patch_tets[t], (int32_t)(t - G.patch_tet_ptr[p]));
-      std::sort(lmap.begin(), lmap.end());
-      slots.clear();
-      codes.clear();
-      for (int64_t r = G.patch_row_ptr[p]; r < G.patch_row_ptr[p + 1]; r++) {
-        int32_t col = G.patch_rows[r];
-        contrib.clear();
-        for (int64_t q = nptr[col]; q < nptr[col + 1]; q++) {
-          int32_t e = nadj[q];
-          int32_t tl = std::lower_bound(lmap.begin(), lmap.end(), std::make_pair(e, (int32_t)-1))->second;
-          const uint32_t* d = conn + (size_t)P.elems[e] * nloc;
-          int b = 0;
-          for (int k = 0; k < nloc; k++)
-            if ((int32_t)d[k] == col) b = k;
+  if (max_inc > 255) WAE_THROW(WAE_E_INVALID, "a DOF is shared by %d elements; the pair program holds at most 255 sources per entry", max_inc);
+  const int64_t npos = (int64_t)order.size();
+  // ---- cut the positions into patches by their exact number of sources --------------------------------------------------
+  // A patch [lo, hi) owns the columns of its positions.  Its sources are the (element, local pair {a,b}) with at least one of the
+  // two DOFs owned; a pair with BOTH DOFs owned is one source feeding nz(i,j) and nz(j,i).  Adding position q to the patch
+  // [lo, q) therefore adds the (element, a) combinations of q's column whose other DOF is not an earlier position of the
+  // patch.  The padding of the count-sorted groups stays below 32 * (largest source count + 1) slots except for degenerate
+  // patches; on overflow the cut is repeated with a wider margin.
+  struct PatchOut {
+    std::vector<int32_t> tets;
+    std::vector<uint32_t> dest;    // per 32-element block: npk x 32 words, two 16-bit slots each (0xFFFF = not owned)
+    std::vector<uint32_t> grp;     // (first slot << 8) | iterations
+    std::vector<uint8_t> cnt;      // per group lane
+    std::vector<uint16_t> lvtx;    // four patch-local vertex numbers per staged element
+    std::vector<uint32_t> gv;      // patch-local vertex -> mesh vertex (even count: padded with a repeat of the last one)
+    std::vector<uint16_t> res;     // per chunk lane: slot that holds the sum of that nonzero after the summation pass
+    std::vector<uint32_t> chunk;   // pairs of words: first global nonzero, length (<= 32, inside one 32-nonzero line)
+    int slots = 0;
+    int64_t units = 0, sources = 0;
+  };
+  const int npk = (nsym + 1) / 2;  // packed slot words per element
+  std::vector<int64_t> cut;
+  std::vector<PatchOut> po;
+  int64_t npatch = 0;
+  std::atomic<int> bad(0);
+  for (int attempt = 1; attempt <= 4; attempt++) {
+    const int64_t raw_cap = (int64_t)slot_cap - 32 * (int64_t)(max_inc + 1) * attempt;
+    if (raw_cap < 4 * (int64_t)max_inc * nloc) WAE_THROW(WAE_E_INVALID, "pair program: slot capacity %d is too small for this mesh", slot_cap);
+    cut.assign(1, 0);
+    {
+      int64_t acc = 0;
+      int32_t lo = 0;
+      for (int64_t q = 0; q < npos; q++) {
+        const int32_t j = order[q];
+        int full = 0, back = 0;  // all (element, a) of the column / those whose other DOF is an earlier position of the patch
+        for (int64_t r = nptr[j]; r < nptr[j + 1]; r++) {
+          const uint32_t* d = conn + (size_t)P.elems[nadj[r]] * nloc;
           for (int a = 0; a < nloc; a++) {
-            int lo_ = a < b ? a : b, hi_ = a < b ? b : a;
-            int sym = lo_ * nloc - lo_ * (lo_ - 1) / 2 + (hi_ - lo_);
-            contrib.emplace_back((int32_t)d[a], (uint16_t)((tl << code_shift) + sym));
+            const int32_t o = pos[d[a]];
+            full++;
+            back += o >= lo && o < q;
           }
         }
-        std::sort(contrib.begin(), contrib.end());  // fixed summation order: by row, then by staged position
-        const int32_t* rows = P.rowval.data() + P.colptr[col];
-        int64_t len = P.colptr[col + 1] - P.colptr[col];
-        size_t ci = 0;
-        for (int64_t sidx = 0; sidx < len; sidx++) {
-          Slot sl{(int32_t)(P.colptr[col] + sidx), (int32_t)codes.size(), 0};
-          while (ci < contrib.size() && contrib[ci].first == rows[sidx]) {
-            codes.push_back(contrib[ci].second);
-            ci++;
-            sl.cnt++;
-          }
-          slots.push_back(sl);
+        if (acc + full - back > raw_cap && acc > 0) {
+          cut.push_back(q);
+          acc = 0;
+          lo = (int32_t)q;
+          back = 0;
         }
+        acc += full - back;
       }
-      std::stable_sort(slots.begin(), slots.end(), [](const Slot& x, const Slot& y) { return x.cnt > y.cnt; });
-      // groups of GS nonzeros: lane l of the warp owns nonzeros j*32 + l (j < GS/32) of the group;
-      // entry (iteration k, nonzero q) of a group is src[k*GS + q]
-      const size_t GS = WAE_GATHER_GROUP;
-      const size_t ng = (slots.size() + GS - 1) / GS;
-      pgrp[p].resize(ng);
-      pout[p].assign(ng * GS, -1);
-      size_t off = 0;
-      for (size_t g = 0; g < ng; g++) {
-        int niter = slots[g * GS].cnt;
-        if (niter > 255) too_many = niter;
-        if (off >= ((size_t)1 << 24)) too_many = 1 << 24;
-        pgrp[p][g] = (uint32_t)(off << 8) | (uint32_t)(niter & 255);
-        psrc[p].resize(off + (size_t)niter * GS, pad_code);
-        for (size_t q = 0; q < GS && g * GS + q < slots.size(); q++) {
-          const Slot& sl = slots[g * GS + q];
-          pout[p][g * GS + q] = sl.out;
-          for (int k = 0; k < sl.cnt; k++) psrc[p][off + (size_t)k * GS + q] = codes[sl.first + k];
-        }
-        off += (size_t)niter * GS;
-      }
+      cut.push_back(npos);
     }
-  });
-  if (too_many) WAE_THROW(WAE_E_INVALID, "gather program overflow (%d)", (int)too_many);
-  G.patch_grp_ptr.assign(npatch + 1, 0);
-  G.patch_src_ptr.assign(npatch + 1, 0);
-  for (int64_t p = 0; p < npatch; p++) {
-    G.patch_grp_ptr[p + 1] = G.patch_grp_ptr[p] + (int64_t)pgrp[p].size();
-    G.patch_src_ptr[p + 1] = G.patch_src_ptr[p] + (int64_t)psrc[p].size();
+    npatch = (int64_t)cut.size() - 1;
+    po.clear();
+    po.resize(npatch);
+    bad = 0;
+    parallel_for(npatch, [&](int64_t pa, int64_t pb) {
+      struct Src { uint64_t key; int32_t t; int32_t s; };
+      struct Unit { uint64_t key; int32_t first; int32_t cnt; int32_t slot; };
+      std::vector<std::pair<int32_t, int32_t>> st;  // (rank, element)
+      std::vector<Src> src;
+      std::vector<Unit> units;
+      std::vector<int32_t> by_cnt, cols;
+      for (int64_t p = pa; p < pb; p++) {
+        PatchOut& O = po[p];
+        const int32_t lo = (int32_t)cut[p], hi = (int32_t)cut[p + 1];
+        st.clear();
+        for (int32_t q = lo; q < hi; q++) {
+          const int32_t j = order[q];
+          for (int64_t r = nptr[j]; r < nptr[j + 1]; r++) st.emplace_back(rank[nadj[r]], nadj[r]);
+        }
+        std::sort(st.begin(), st.end());
+        st.erase(std::unique(st.begin(), st.end()), st.end());
+        const int nt = (int)st.size();
+        // stage the elements by the number of local DOFs the patch owns (interior elements first, then Morton rank): the lanes
+        // of a 32-element block then own (almost) the same entries, so the predicated slot stores are either full or empty
+        {
+          std::vector<std::pair<int32_t, std::pair<int32_t, int32_t>>> key(nt);
+          for (int t = 0; t < nt; t++) {
+            const uint32_t* d = conn + (size_t)P.elems[st[t].second] * nloc;
+            int32_t own = 0;
+            for (int a = 0; a < nloc; a++) own |= (pos[d[a]] >= lo && pos[d[a]] < hi) << a;
+            key[t] = {-(int32_t)__builtin_popcount(own) * 1024 - own, st[t]};
+          }
+          std::sort(key.begin(), key.end());
+          for (int t = 0; t < nt; t++) st[t] = key[t].second;
+        }
+        O.tets.resize(nt);
+        O.lvtx.resize((size_t)nt * 4);
+        O.gv.clear();
+        for (int t = 0; t < nt; t++) {
+          const uint32_t* d = conn + (size_t)P.elems[st[t].second] * nloc;
+          for (int a = 0; a < 4; a++) O.gv.push_back(d[a]);
+        }
+        std::sort(O.gv.begin(), O.gv.end());
+        O.gv.erase(std::unique(O.gv.begin(), O.gv.end()), O.gv.end());
+        if (O.gv.size() >= 0xFFFF) bad = 1 << 28;
+        // sources: key = (local position of the column, row DOF).  Both DOFs owned -> the column is the one of lower position.
+        src.clear();
+        for (int t = 0; t < nt; t++) {
+          const int32_t e = st[t].second;
+          O.tets[t] = e;
+          const uint32_t* d = conn + (size_t)P.elems[e] * nloc;
+          for (int a = 0; a < 4; a++)
+            O.lvtx[(size_t)t * 4 + a] = (uint16_t)(std::lower_bound(O.gv.begin(), O.gv.end(), d[a]) - O.gv.begin());
+          int32_t o[10];
+          for (int a = 0; a < nloc; a++) o[a] = pos[d[a]];
+          int s = 0;
+          for (int a = 0; a < nloc; a++)
+            for (int b = a; b < nloc; b++, s++) {
+              const bool ia = o[a] >= lo && o[a] < hi, ib = o[b] >= lo && o[b] < hi;
+              if (!ia && !ib) continue;
+              int32_t cpos;
+              uint32_t row;
+              if (ia && ib) {
+                cpos = std::min(o[a], o[b]);
+                row = o[a] <= o[b] ? d[b] : d[a];
+              } else if (ia) {
+                cpos = o[a];
+                row = d[b];
+              } else {
+                cpos = o[b];
+                row = d[a];
+              }
+              src.push_back(Src{((uint64_t)(uint32_t)(cpos - lo) << 32) | row, t, s});
+            }
+        }
+        O.sources = (int64_t)src.size();
+        std::sort(src.begin(), src.end(), [](const Src& x, const Src& y) { return x.key != y.key ? x.key < y.key : x.t < y.t; });
+        units.clear();
+        for (size_t i = 0; i < src.size();) {
+          size_t j = i;
+          while (j < src.size() && src[j].key == src[i].key) j++;
+          units.push_back(Unit{src[i].key, (int32_t)i, (int32_t)(j - i), -1});
+          i = j;
+        }
+        O.units = (int64_t)units.size();
+        by_cnt.resize(units.size());
+        for (size_t i = 0; i < units.size(); i++) by_cnt[i] = (int32_t)i;
+        std::stable_sort(by_cnt.begin(), by_cnt.end(), [&](int32_t x, int32_t y) { return units[x].cnt > units[y].cnt; });
+        const size_t ng = (units.size() + 31) / 32;
+        O.grp.resize(ng);
+        O.cnt.assign(ng * 32, 0);
+        const int nwb = (nt + 31) / 32;
+        O.dest.assign((size_t)nwb * npk * 32, 0xFFFFFFFFu);
+        int sb = 0;
+        for (size_t g = 0; g < ng; g++) {
+          const int niter = units[by_cnt[g * 32]].cnt;
+          O.grp[g] = ((uint32_t)sb << 8) | (uint32_t)niter;
+          for (size_t l = 0; l < 32 && g * 32 + l < units.size(); l++) {
+            Unit& u = units[by_cnt[g * 32 + l]];
+            u.slot = sb + (int)l;
+            O.cnt[g * 32 + l] = (uint8_t)u.cnt;
+            for (int k = 0; k < u.cnt; k++) {
+              const Src& sc = src[u.first + k];
+              const uint32_t slot = (uint32_t)(sb + 32 * k + ((int)l ^ (k & 7)));  // the sources of one unit sit in 8 different bank groups
+              uint32_t& w = O.dest[((size_t)(sc.t >> 5) * npk + (sc.s >> 1)) * 32 + (sc.t & 31)];
+              w = (sc.s & 1) ? ((w & 0x0000FFFFu) | (slot << 16)) : ((w & 0xFFFF0000u) | slot);
+            }
+          }
+          sb += 32 * niter;
+        }
+        O.slots = sb;
+        if (sb > slot_cap || sb >= 0xFFFF) bad = sb;
+        // store program: owned columns by DOF id (adjacent DOFs have adjacent nonzero ranges), cut into chunks of at most 32
+        // consecutive nonzeros that do not straddle a 32-nonzero (256-byte) boundary of the value arrays
+        cols.resize(hi - lo);
+        for (int32_t q = lo; q < hi; q++) cols[q - lo] = order[q];
+        std::sort(cols.begin(), cols.end());
+        O.res.clear();
+        O.chunk.clear();
+        auto find_unit = [&](uint64_t key) -> int32_t {
+          size_t a0 = 0, b0 = units.size();
+          while (a0 < b0) {
+            size_t m = (a0 + b0) >> 1;
+            if (units[m].key < key) a0 = m + 1; else b0 = m;
+          }
+          return (a0 < units.size() && units[a0].key == key) ? units[a0].slot : -1;
+        };
+        for (int32_t j : cols) {
+          const int32_t qj = pos[j];
+          for (int64_t z = P.colptr[j]; z < P.colptr[j + 1]; z++) {
+            const int32_t i = P.rowval[z];
+            const int32_t qi = pos[i];
+            const bool mirror = qi >= lo && qi < hi && qi < qj;  // summed as the pair (column i, row j)
+            const int32_t sl = mirror ? find_unit(((uint64_t)(uint32_t)(qi - lo) << 32) | (uint32_t)j)
+                                      : find_unit(((uint64_t)(uint32_t)(qj - lo) << 32) | (uint32_t)i);
+            if (sl < 0) bad = 1 << 30;
+            const size_t nc = O.chunk.size();
+            if (nc && O.chunk[nc - 2] + O.chunk[nc - 1] == (uint32_t)z && (z & 31) != 0)
+              O.chunk[nc - 1]++;
+            else {
+              O.chunk.push_back((uint32_t)z);
+              O.chunk.push_back(1u);
+              O.res.resize(O.res.size() + 32, 0);
+            }
+            O.res[O.res.size() - 32 + (O.chunk.back() - 1)] = (uint16_t)sl;
+          }
+        }
+      }
+    });
+    if (!bad) break;
   }
-  G.grp.resize(G.patch_grp_ptr[npatch]);
-  G.out_idx.resize(G.patch_grp_ptr[npatch] * WAE_GATHER_GROUP);
-  G.src.resize(G.patch_src_ptr[npatch]);
+  if (bad) WAE_THROW(WAE_E_INVALID, "pair program overflow (%d; slot capacity %d)", (int)bad, slot_cap);
+  // ---- pack: one descriptor + one contiguous, 16-byte aligned blob per patch (fetched with a single bulk copy) -----------
+  //   blob = [ lvtx: nt x 4 u16 | tets: nt i32 | grp: ng u32 | cnt: ng x 32 u8 | chunk: nc x (u32 first, u32 length) ]
+  auto pad16 = [](int64_t x) { return (x + 15) & ~(int64_t)15; };
+  G = GatherHost();
+  G.npk = npk;
+  G.n_patch = (int)npatch;
+  G.desc.assign((size_t)npatch * 8, 0);
+  std::vector<int64_t> tet_ptr(npatch + 1, 0);
+  int64_t blob_total = 0, pv_total = 0, wb_total = 0, chunk_total = 0;
+  for (int64_t p = 0; p < npatch; p++) {
+    PatchOut& O = po[p];
+    if (O.gv.size() & 1) O.gv.push_back(O.gv.back());
+    const int64_t nt = (int64_t)O.tets.size(), ng = (int64_t)O.grp.size(), nc = (int64_t)O.chunk.size() / 2, nv = (int64_t)O.gv.size();
+    const int64_t o_tets = pad16(8 * nt), o_grp = o_tets + pad16(4 * nt), o_cnt = o_grp + pad16(4 * ng), o_chunk = o_cnt + 32 * ng;
+    const int64_t bytes = o_chunk + pad16(8 * nc);
+    int64_t* D = &G.desc[(size_t)p * 8];
+    D[0] = blob_total;
+    D[1] = pv_total * 3;  // doubles
+    D[2] = wb_total;
+    D[3] = chunk_total;
+    int32_t* I = reinterpret_cast<int32_t*>(D + 4);
+    I[0] = (int32_t)nt; I[1] = (int32_t)nv; I[2] = (int32_t)ng; I[3] = (int32_t)nc;
+    I[4] = (int32_t)bytes; I[5] = (int32_t)o_tets; I[6] = (int32_t)o_grp; I[7] = (int32_t)o_cnt;
+    tet_ptr[p + 1] = tet_ptr[p] + nt;
+    blob_total += bytes;
+    pv_total += nv;
+    wb_total += (nt + 31) / 32;
+    chunk_total += nc;
+    G.max_slots = std::max(G.max_slots, O.slots);
+    G.max_blob = std::max<int>(G.max_blob, (int)bytes);
+    G.max_nv = std::max<int>(G.max_nv, (int)nv);
+    G.n_pairs += O.units;
+    G.n_sources += O.sources;
+  }
+  G.n_staged = tet_ptr[npatch];
+  G.blob.assign((size_t)blob_total, 0);
+  G.gvtx.resize(pv_total);
+  G.dest.resize((size_t)wb_total * npk * 32);
+  G.res.resize((size_t)chunk_total * 32);
   parallel_for(npatch, [&](int64_t pa, int64_t pb) {
     for (int64_t p = pa; p < pb; p++) {
-      std::copy(pgrp[p].begin(), pgrp[p].end(), G.grp.begin() + G.patch_grp_ptr[p]);
-      std::copy(pout[p].begin(), pout[p].end(), G.out_idx.begin() + G.patch_grp_ptr[p] * WAE_GATHER_GROUP);
-      std::copy(psrc[p].begin(), psrc[p].end(), G.src.begin() + G.patch_src_ptr[p]);
+      PatchOut& O = po[p];
+      const int64_t* D = &G.desc[(size_t)p * 8];
+      const int32_t* I = reinterpret_cast<const int32_t*>(D + 4);
+      uint8_t* B = G.blob.data() + D[0];
+      std::memcpy(B, O.lvtx.data(), O.lvtx.size() * 2);
+      std::memcpy(B + I[5], O.tets.data(), O.tets.size() * 4);
+      std::memcpy(B + I[6], O.grp.data(), O.grp.size() * 4);
+      std::memcpy(B + I[7], O.cnt.data(), O.cnt.size());
+      std::memcpy(B + I[7] + 32 * (int64_t)I[2], O.chunk.data(), O.chunk.size() * 4);
+      std::copy(O.gv.begin(), O.gv.end(), G.gvtx.begin() + D[1] / 3);
+      std::copy(O.dest.begin(), O.dest.end(), G.dest.begin() + (size_t)D[2] * npk * 32);
+      std::copy(O.res.begin(), O.res.end(), G.res.begin() + (size_t)D[3] * 32);
+      O = PatchOut();
     }
   });
 }

@@ -111,6 +111,7 @@ int32_t wae_mesh_set(wae_ctx* h, int32_t order, int64_t n_pts, const double* xyz
     for (int k = 0; k < 4; k++)
       if (h->tets[e * h->nloc + k] >= (uint64_t)n_pts) WAE_THROW(WAE_E_INVALID, "tet %lld: vertex DOF >= n_pts", (long long)e);
   h->d_xyz.upload(h->xyz, h->stream);
+  h->xyz_version++;
   h->d_tets.upload(h->tets, h->stream);
   h->d_tris.upload(h->tris, h->stream);
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
@@ -123,6 +124,7 @@ int32_t wae_mesh_update_points(wae_ctx* h, int64_t n_pts, const double* xyz) {
   if (!h->order || n_pts != h->n_pts || !xyz) WAE_THROW(WAE_E_INVALID, "wae_mesh_update_points: point count differs from wae_mesh_set");
   h->xyz.assign(xyz, xyz + 3 * n_pts);
   CUDA_CHECK(cudaMemcpyAsync(h->d_xyz.p, xyz, 3 * n_pts * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+  h->xyz_version++;
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
   WAE_API_END
 }
@@ -193,26 +195,27 @@ static void ensure_slotmap(wae_ctx* h, Pattern& P) {
 }
 
 // *mat_id >= 0 on entry: overwrite that matrix in place (same pattern and type), else create a new one
-static int reuse_or_new_matrix(wae_ctx* h, const int32_t* mat_id, int pattern, bool is_complex, int64_t nnz);
+// zero = false: the caller overwrites every nonzero (pair-program assembly) -- no memset pass
+static int reuse_or_new_matrix(wae_ctx* h, const int32_t* mat_id, int pattern, bool is_complex, int64_t nnz, bool zero = true);
 
-static int new_matrix(wae_ctx* h, int pattern, bool is_complex, int64_t nnz) {
+static int new_matrix(wae_ctx* h, int pattern, bool is_complex, int64_t nnz, bool zero = true) {
   h->mats.emplace_back(new Matrix());
   Matrix& M = *h->mats.back();
   M.pattern = pattern;
   M.is_complex = is_complex;
   M.d_val.alloc((size_t)nnz * (is_complex ? 2 : 1));
-  CUDA_CHECK(cudaMemsetAsync(M.d_val.p, 0, M.d_val.n * sizeof(double), h->stream));
+  if (zero) CUDA_CHECK(cudaMemsetAsync(M.d_val.p, 0, M.d_val.n * sizeof(double), h->stream));
   return (int)h->mats.size() - 1;
 }
 
-static int reuse_or_new_matrix(wae_ctx* h, const int32_t* mat_id, int pattern, bool is_complex, int64_t nnz) {
+static int reuse_or_new_matrix(wae_ctx* h, const int32_t* mat_id, int pattern, bool is_complex, int64_t nnz, bool zero) {
   if (mat_id && *mat_id >= 0) {
     Matrix& M = h->mat(*mat_id);
     if (M.pattern != pattern || M.is_complex != is_complex) WAE_THROW(WAE_E_INVALID, "matrix %d cannot be reused: different pattern or type", *mat_id);
-    CUDA_CHECK(cudaMemsetAsync(M.d_val.p, 0, M.d_val.n * sizeof(double), h->stream));
+    if (zero) CUDA_CHECK(cudaMemsetAsync(M.d_val.p, 0, M.d_val.n * sizeof(double), h->stream));
     return *mat_id;
   }
-  return new_matrix(h, pattern, is_complex, nnz);
+  return new_matrix(h, pattern, is_complex, nnz, zero);
 }
 
 static void upload_c(wae_ctx* h, Pattern& P, const double* c, int c_per_elem, DevBuf<double>& d_c) {
@@ -234,7 +237,7 @@ int32_t wae_assemble(wae_ctx* h, int32_t pattern_id, int32_t kind, const double*
   if (use_gather) wae_ensure_gather(h, P); else ensure_slotmap(h, P);
   DevBuf<double> d_c;
   if (kind != WAE_OP_MASS) upload_c(h, P, c, c_per_elem, d_c);
-  int id = reuse_or_new_matrix(h, mat_id, pattern_id, kind == WAE_OP_BOUNDARY, P.nnz);
+  int id = reuse_or_new_matrix(h, mat_id, pattern_id, kind == WAE_OP_BOUNDARY, P.nnz, !use_gather);
   Matrix& M = *h->mats[id];
   PhaseTimer t(h, "assemble");
   if (kind == WAE_OP_MASS && use_gather)
@@ -260,9 +263,10 @@ int32_t wae_assemble_mk(wae_ctx* h, int32_t pattern_id, const double* c, int32_t
   if (P.elem_kind != 3) WAE_THROW(WAE_E_INVALID, "wae_assemble_mk needs a tetrahedral pattern");
   DevBuf<double> d_c;
   upload_c(h, P, c, c_per_elem, d_c);
-  int im = reuse_or_new_matrix(h, mass_id, pattern_id, false, P.nnz);
-  int ik = reuse_or_new_matrix(h, stiff_id, pattern_id, false, P.nnz);
-  if (c_per_elem == 1 && !getenv("WAE_FORCE_ATOMIC")) {
+  const bool use_gather = c_per_elem == 1 && !getenv("WAE_FORCE_ATOMIC");
+  int im = reuse_or_new_matrix(h, mass_id, pattern_id, false, P.nnz, !use_gather);
+  int ik = reuse_or_new_matrix(h, stiff_id, pattern_id, false, P.nnz, !use_gather);
+  if (use_gather) {
     wae_ensure_gather(h, P);
     PhaseTimer t(h, "assemble");
     wae_launch_assemble_gather(h, P, d_c.p, h->mats[im]->d_val.p, h->mats[ik]->d_val.p, 1.0);

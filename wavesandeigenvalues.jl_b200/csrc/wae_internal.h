@@ -77,17 +77,17 @@ struct Pattern {
   int elem_kind = 0;
   std::vector<int64_t> elems;   // 0-based element ids
   DevBuf<int32_t> d_elems;
-  // owner-computes gather program (assembly): built lazily, see assembly_symbolic.cpp
+  // owner-computes pair program (assembly): built lazily, see assembly_symbolic.cpp
   struct Gather {
-    int n_patch = 0, max_tets = 0;
-    DevBuf<int64_t> d_patch_tet_ptr;      // staged elements of patch p: patch_tets[patch_tet_ptr[p] .. )
-    DevBuf<int32_t> d_patch_tets;         // positions in the pattern's element list
-    DevBuf<int64_t> d_patch_grp_ptr;      // groups (32 owned nonzeros each, sorted by source count) of patch p
-    DevBuf<int64_t> d_patch_src_ptr;      // start of patch p in d_src
-    DevBuf<uint32_t> d_grp;               // per group: (offset into the patch's sources << 8) | iterations
-    DevBuf<int32_t> d_out_idx;            // per group lane: global nonzero index (-1 = padding lane)
-    DevBuf<uint16_t> d_src;               // transposed packed sources: tet_local * 64 + sym, 0xFFFF = none
-    int64_t n_src = 0, n_staged = 0;
+    int n_patch = 0, max_slots = 0, max_blob = 0, max_nv = 0;
+    DevBuf<int64_t> d_desc;               // 64-byte patch descriptors
+    DevBuf<uint8_t> d_blob;               // per patch: local vertex numbers, element ids, group words, counts, store chunks
+    DevBuf<uint32_t> d_gvtx;              // patch-local vertex -> mesh vertex
+    DevBuf<double> d_pxyz;                // vertex coordinates in patch order (3 per local vertex), refreshed when the points change
+    DevBuf<uint32_t> d_dest;              // per 32-element block: npk x 32 words = two 16-bit shared-memory slots per (element, local pair)
+    DevBuf<uint16_t> d_res;               // per chunk lane: slot holding the sum of that nonzero
+    int64_t n_pairs = 0, n_sources = 0, n_staged = 0, n_pv = 0;
+    uint64_t xyz_version = 0;             // h->xyz_version the pxyz copy was gathered from
     bool built = false;
   } gather;
   // scatter map for the atomic (first-generation) kernels: n_loc^2 slots per element
@@ -142,6 +142,7 @@ struct wae_ctx {
   std::vector<uint32_t> tets;     // nloc*n_tet, 0-based
   std::vector<uint32_t> tris;     // nloc3*n_tri, 0-based
   DevBuf<double> d_xyz;
+  uint64_t xyz_version = 1;       // bumped whenever d_xyz changes (patch-ordered coordinate copies are refreshed lazily)
   DevBuf<uint32_t> d_tets, d_tris;
 
   std::vector<std::unique_ptr<Pattern>> patterns;
@@ -181,15 +182,16 @@ struct PhaseTimer {
 void wae_build_pattern_from_elements(const uint32_t* conn, int nloc, const std::vector<int64_t>& elems,
                                      int64_t dim, Pattern& P);
 void wae_build_slotmap(const uint32_t* conn, int nloc, const Pattern& P, std::vector<int32_t>& slotmap);
-#define WAE_GATHER_GROUP 32  // owned nonzeros per gather group (multiple of 32: GS/32 per lane)
 struct GatherHost {
-  std::vector<int64_t> patch_row_ptr, patch_tet_ptr, patch_grp_ptr, patch_src_ptr;
-  std::vector<int32_t> patch_rows, patch_tets, out_idx;
-  std::vector<uint32_t> grp;
-  std::vector<uint16_t> src;
-  int max_tets = 0;
+  std::vector<int64_t> desc;     // 8 words per patch: blob offset (bytes), pxyz offset (doubles), first 32-element block, first chunk,
+                                 // then 8 x int32: nt, nv, ng, nc, blob bytes, offsets of the tets / grp / cnt sections
+  std::vector<uint8_t> blob;
+  std::vector<uint32_t> gvtx, dest;
+  std::vector<uint16_t> res;
+  int n_patch = 0, max_slots = 0, max_blob = 0, max_nv = 0, npk = 0;
+  int64_t n_pairs = 0, n_sources = 0, n_staged = 0;
 };
-void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const Pattern& P, int target_tets, GatherHost& G);
+void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const Pattern& P, int slot_cap, GatherHost& G);
 void wae_ensure_gather(wae_ctx* h, Pattern& P);
 void wae_build_bloch(const uint32_t* conn, int nloc, const std::vector<int64_t>& elems, int64_t dim_red, const int64_t* dof_new,
                      const uint8_t* dof_flag, int n_class, std::vector<Pattern>& P, std::vector<int32_t>& slotmap,
