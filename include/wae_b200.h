@@ -151,6 +151,14 @@ int32_t wae_lu_solve(wae_ctx* h, int32_t lu_id, int32_t trans, int32_t nrhs, dou
 int32_t wae_lu_symbolic_stats(int64_t n, const int64_t* colptr, const int64_t* rowval, const double* coords,
                               int32_t leaf_size, double* out);
 
+/* Host-only diagnostic (needs no GPU and no context): build the sparsity pattern and the owner-computes pair program of the
+ * M/K assembly kernel for a tetrahedral mesh (order 1: 4, order 2: 10 DOFs per element, 0-based, n_loc x n_tet) and replay the
+ * kernel's three passes (slot scatter, fixed-order summation, chunked stores) on the host with synthetic element entries.
+ * out[0..7] = nnz, patches, staged elements, sources, summation units, largest slot count, max |error| against the plain
+ * triplet sum, number of violated invariants (every nonzero written exactly once, slots used once, alignment).          */
+int32_t wae_pair_program_check(int32_t order, int64_t n_pts, const double* xyz, int64_t n_tet, const uint32_t* tets,
+                               int32_t slot_cap, double* out);
+
 /* ---- shift-invert Arnoldi: nev eigenpairs of A v = lambda M v nearest 0 ----------------
  * Replaces Arpack.eigs(A,M;nev,sigma=0,v0) (Householder.jl:100-101, iterative_solvers.jl:132-133).
  * A is the matrix factorised in lu_id, M the family slot m_slot.  trans=2 gives the adjoint

@@ -173,6 +173,41 @@ def test_symbolic_lu_phase_on_host(meshes):
     assert rc == 0 and out[1] < 30 * A.nnz
 
 
+def _pair_program_check(mesh, order, slot_cap):
+    from wae_b200 import _lib
+    _, tets, dim = W.aggregate_elements(mesh, order)
+    lib = _lib.lib()
+    lib.wae_pair_program_check.restype = C.c_int32
+    lib.wae_pair_program_check.argtypes = [C.c_int32, C.c_int64, C.POINTER(C.c_double), C.c_int64, C.POINTER(C.c_uint32), C.c_int32,
+                                           C.POINTER(C.c_double)]
+    xyz = np.ascontiguousarray(mesh.points.T, dtype=np.float64)
+    t32 = np.ascontiguousarray(tets, dtype=np.uint32)
+    out = np.zeros(8)
+    rc = lib.wae_pair_program_check(1 if order == "lin" else 2, xyz.shape[0], xyz.ctypes.data_as(C.POINTER(C.c_double)), len(t32),
+                                    t32.ctypes.data_as(C.POINTER(C.c_uint32)), slot_cap, out.ctypes.data_as(C.POINTER(C.c_double)))
+    assert rc == 0
+    nsym = 10 if order == "lin" else 55
+    return dict(nnz=int(out[0]), patches=int(out[1]), staged=int(out[2]), sources=int(out[3]), units=int(out[4]), max_slots=int(out[5]),
+                err=out[6], bad=int(out[7]), ntet=len(t32), nsym=nsym)
+
+
+def test_assembly_pair_program_on_host(meshes):
+    """The owner-computes pair program of the M/K assembly kernel, replayed on the host (no GPU): every nonzero is written exactly
+    once, every slot is used once, the fixed-order sums equal the plain triplet sums; on the unstructured Rijke mesh (P1 and P2) and
+    on a structured Kuhn box cut into many patches and into a single patch."""
+    mg, _ = meshes
+    box = W.kuhn_box((6, 5, 7), (0, 0, 0), (1, 1, 1), jitter=0.1, seed=5)
+    for mesh, order, cap in ((mg, "lin", 6000), (mg, "quad", 7168), (mg, "quad", 14000), (box, "quad", 5000), (box, "lin", 14000)):
+        r = _pair_program_check(mesh, order, cap)
+        assert r["bad"] == 0 and r["err"] < 1e-12, r
+        assert r["max_slots"] <= cap
+        # a source is owned at least once and at most twice (once per owning column patch)
+        assert r["nsym"] * r["ntet"] <= r["sources"] <= 2 * r["nsym"] * r["ntet"]
+        assert r["staged"] >= r["ntet"] and r["units"] <= r["nnz"]
+    one = _pair_program_check(box, "lin", 14000)
+    assert one["patches"] == 1 and one["staged"] == one["ntet"] and one["sources"] == 10 * one["ntet"]
+
+
 def test_kuhn_box_is_conforming():
     m = W.kuhn_box((3, 2, 4), (0, 0, 0), (3, 2, 4), jitter=0.1, seed=3, flame_layer=(1, 2))
     X = m.points[:, m.tetrahedra]

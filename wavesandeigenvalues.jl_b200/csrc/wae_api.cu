@@ -1,6 +1,7 @@
 // C-ABI entry points of libwae_b200 (see include/wae_b200.h): context, mesh, patterns,
 // assembly, operator family (combine / SpMM).  LU, Arnoldi and Beyn live in lu_api.cu.
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <numeric>
@@ -657,4 +658,102 @@ int32_t wae_family_spmm(wae_ctx* h, int32_t fam_id, int32_t slot, int32_t trans,
   WAE_API_END
 }
 
+
+// Host-only diagnostic (no GPU, no context): build pattern + pair program of a tetrahedral mesh and replay the three passes of
+// assemble_tet_pairs on the host with synthetic element entries; see include/wae_b200.h.
+int32_t wae_pair_program_check(int32_t order, int64_t n_pts, const double* xyz, int64_t n_tet, const uint32_t* tets, int32_t slot_cap,
+                               double* out) {
+  try {
+    const int nloc = order == 1 ? 4 : 10, nsym = nloc * (nloc + 1) / 2;
+    int64_t dim = 0;
+    for (int64_t k = 0; k < n_tet * nloc; k++) dim = std::max<int64_t>(dim, (int64_t)tets[k] + 1);
+    Pattern P;
+    P.elem_kind = 3;
+    P.elems.resize(n_tet);
+    std::iota(P.elems.begin(), P.elems.end(), 0);
+    wae_build_pattern_from_elements(tets, nloc, P.elems, dim, P);
+    GatherHost G;
+    wae_build_gather(xyz, tets, nloc, P, slot_cap, G);
+    auto val = [](int64_t e, int s) { return std::sin(1.0 + 0.37 * (double)e + 1.3 * s); };
+    auto nz = [&](int32_t i, int32_t j) {
+      return std::lower_bound(P.rowval.begin() + P.colptr[j], P.rowval.begin() + P.colptr[j + 1], i) - P.rowval.begin();
+    };
+    std::vector<double> ref(P.nnz, 0.0), got(P.nnz, 0.0);
+    std::vector<int> written(P.nnz, 0);
+    for (int64_t e = 0; e < n_tet; e++) {
+      const uint32_t* d = tets + e * nloc;
+      int s = 0;
+      for (int a = 0; a < nloc; a++)
+        for (int b = a; b < nloc; b++, s++) {
+          ref[nz(d[a], d[b])] += val(e, s);
+          if (a != b) ref[nz(d[b], d[a])] += val(e, s);
+        }
+    }
+    int64_t bad = 0;
+    const double unset = -1e300;
+    for (int p = 0; p < G.n_patch; p++) {
+      const int64_t* D = &G.desc[(size_t)p * 8];
+      const int32_t* I = reinterpret_cast<const int32_t*>(D + 4);
+      const int nt = I[0], nv = I[1], ng = I[2], nc = I[3];
+      const uint8_t* B = G.blob.data() + D[0];
+      if (D[0] % 16 || I[4] % 16 || (D[1] * 8) % 16) bad++;
+      const uint16_t* lv = reinterpret_cast<const uint16_t*>(B);
+      const int32_t* pt = reinterpret_cast<const int32_t*>(B + I[5]);
+      const uint32_t* grp = reinterpret_cast<const uint32_t*>(B + I[6]);
+      const uint8_t* cnt = B + I[7];
+      const uint32_t* chunk = reinterpret_cast<const uint32_t*>(B + I[7] + 32 * (int64_t)ng);
+      std::vector<double> slots(G.max_slots, unset);
+      for (int t = 0; t < nt; t++) {  // element pass
+        const int32_t e = pt[t];
+        for (int a = 0; a < 4; a++)
+          if (lv[4 * t + a] >= nv || G.gvtx[D[1] / 3 + lv[4 * t + a]] != tets[(int64_t)e * nloc + a]) bad++;
+        const uint32_t* dp = &G.dest[((size_t)(D[2] + t / 32) * G.npk) * 32 + (t & 31)];
+        for (int s = 0; s < nsym; s++) {
+          const uint32_t w = dp[(s >> 1) * 32], sl = (s & 1) ? (w >> 16) : (w & 0xFFFFu);
+          if (sl == 0xFFFFu) continue;
+          if ((int)sl >= G.max_slots || slots[sl] != unset) { bad++; continue; }
+          slots[sl] = val(e, s);
+        }
+      }
+      for (int g = 0; g < ng; g++) {  // summation pass
+        const int sb = (int)(grp[g] >> 8), niter = (int)(grp[g] & 255);
+        for (int l = 0; l < 32; l++) {
+          const int c = cnt[g * 32 + l];
+          if (c > niter) bad++;
+          double acc = 0.0;
+          for (int k = 0; k < c; k++) {
+            const double v = slots[sb + 32 * k + (l ^ (k & 7))];
+            if (v == unset) bad++;
+            acc += v;
+          }
+          if (c) slots[sb + l] = acc;
+        }
+      }
+      for (int ch = 0; ch < nc; ch++) {  // store pass
+        const uint32_t z0 = chunk[2 * ch], len = chunk[2 * ch + 1];
+        if (len < 1 || len > 32 || (z0 >> 5) != ((z0 + len - 1) >> 5)) { bad++; continue; }
+        for (uint32_t l = 0; l < len; l++) {
+          got[z0 + l] = slots[G.res[(size_t)(D[3] + ch) * 32 + l]];
+          written[z0 + l]++;
+        }
+      }
+    }
+    double err = 0.0;
+    for (int64_t k = 0; k < P.nnz; k++) {
+      err = std::max(err, std::fabs(got[k] - ref[k]));
+      if (written[k] != 1) bad++;
+    }
+    out[0] = (double)P.nnz;
+    out[1] = G.n_patch;
+    out[2] = (double)G.n_staged;
+    out[3] = (double)G.n_sources;
+    out[4] = (double)G.n_pairs;
+    out[5] = G.max_slots;
+    out[6] = err;
+    out[7] = (double)bad;
+    return WAE_OK;
+  } catch (...) {
+    return WAE_E_INVALID;
+  }
+}
 }  // extern "C"
