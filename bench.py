@@ -109,6 +109,16 @@ class Clocks:
         return out
 
 
+def ncu_traffic(key):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of a kernel, from the committed `ncu --set full` summaries
+    (profiles/r01_traffic.json: kernel/workload -> bytes, with the capture it was read from); None if not captured."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[key]
+        return t["dram_bytes_per_launch"] / 1e9, t["source"]
+    except Exception:
+        return None, None
+
+
 def fp64_peak(torch, dev):
     """Measured FP64 GEMM peak of this GPU (cuBLAS via torch): DGEMM 8192^3 and ZGEMM 4096^3, best of 5, TFLOP/s."""
     best = {}
@@ -273,7 +283,8 @@ def main():
     peaks = fp64_peak(torch, dev)
     peak = max(peaks.values())
     out["roofline"] = {"bound": "tensor", "achieved": fac_tflops, "peak": peak, "unit": "TFLOP/s", "frac": fac_tflops / peak,
-                       "traffic": None,
+                       "traffic": ncu_traffic("lu_gemm_kernel/config2/schur_level")[0],
+                       "traffic_note": "GB (dram read+write) of the largest Schur-complement launch of one factorisation, " + str(ncu_traffic("lu_gemm_kernel/config2/schur_level")[1]),
                        "kernel": "lu_gemm_kernel (complex C -= A*B^T on DMMA m8n8k4 f64) inside the numeric LU",
                        "elimination": "symmetric (LDL^T-type) + rank-1 Woodbury for the flame term" if sym else "general LU",
                        "flops_per_factorisation": fac_flops,
@@ -281,13 +292,26 @@ def main():
                                 "count for the symmetric elimination; includes the 2 extra solves of the Woodbury set-up in the time) / "
                                 "CUDA-event time of the numeric LU (all its kernels); peak = cuBLAS FP64 GEMM measured in this run "
                                 f"(dgemm 8192^3 {peaks['dgemm']:.1f}, zgemm 4096^3 {peaks['zgemm']:.1f} TFLOP/s) -- MEASURED_PEAKS.json has no FP64 figure")}
-    # assembly kernel vs HBM
+    # triangular solves vs HBM: one refined solve (2 sweeps pairs: L then U^T panel each) of a random right-hand side
     hbm = 6548.5
     try:
         hbm = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
         hbm_src = "MEASURED_PEAKS.json"
     except Exception:
         hbm_src = "fallback"
+    rng = np.random.default_rng(1)
+    bvec = rng.standard_normal(dv.dim) + 1j * rng.standard_normal(dv.dim)
+    sol_ms = []
+    for _ in range(4):
+        ctx.lu_solve(lu, bvec)
+        sol_ms.append(ctx.last_ms("solve"))
+    sol_med = float(np.median(sol_ms[1:]))
+    sol_bytes = 2 * (16.0 * dv.lu_nnz + 2 * 16.0 * dv.dim)  # 16 (nnz(L)+nnz(U)) + 16 d nrhs 2 per solve; one refinement step = 2 solves
+    out["solve"] = {"ms": sol_med, "nrhs": 1, "refinement_steps": 1,
+                    "roofline": {"bound": "hbm", "achieved": sol_bytes / sol_med / 1e6, "peak": hbm, "unit": "GB/s", "frac": sol_bytes / sol_med / 1e6 / hbm,
+                                 "traffic": None, "peak_source": hbm_src,
+                                 "kernel": "lu_fwd_update / lu_bwd_update / lu_fwd_tri / lu_bwd_tri (level-scheduled, windowed)",
+                                 "algorithmic_bytes": sol_bytes}}
     if not args.skip_extras and rank == 0:
         out["assembly"] = assembly_leg(W, ctx, args.assembly_cubes, hbm, hbm_src) if args.assembly_cubes else None
         # re-establish the tube mesh on the context for anything that follows
@@ -328,8 +352,9 @@ def assembly_leg(W, ctx0, n, hbm, hbm_src):
     alg = ntet * (4 * 10 + 8) + 24 * npts + 2 * nnz * 8
     res = {"value": ntet / med / 1e3, "unit": "Mtets/s", "tets": ntet, "dofs": dim, "nnz": int(nnz), "kernel_ms": med,
            "roofline": {"bound": "hbm", "achieved": alg / med / 1e6, "peak": hbm, "unit": "GB/s", "frac": alg / med / 1e6 / hbm,
-                        "traffic": None, "peak_source": hbm_src, "algorithmic_bytes_per_tet": alg / ntet,
-                        "kernel": "assemble_tet_pairs<10> (P2 M+K, owner-computes pair program)"}}
+                        "traffic": ncu_traffic(f"assemble_tet_pairs/p2_box_{n}")[0], "traffic_note": "GB per launch, " + str(ncu_traffic(f"assemble_tet_pairs/p2_box_{n}")[1]),
+                        "peak_source": hbm_src, "algorithmic_bytes_per_tet": alg / ntet,
+                        "kernel": "assemble_tet_pairs<10,3> (P2 M+K, owner-computes pair program, persistent, TMA-staged)"}}
     ctx.close()
     return res
 

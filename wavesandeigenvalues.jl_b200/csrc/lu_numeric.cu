@@ -369,164 +369,225 @@ __global__ void __launch_bounds__(256) lu_gemm_kernel(LuDev D, const int32_t* __
 }
 
 // ---- triangular solves ---------------------------------------------------------------------------------
-// forward substitution with a lower-trapezoidal panel P (Lp: unit diagonal, Up: general diagonal)
-// phase 1 (one CTA of 32 warps per supernode): pivot block, blocked by NB.  The diagonal blocks were inverted at
-// factorisation time, so a block step is a 32x32 matrix-vector product (warp w = row w, shuffle reduction) followed
-// by the rank-NB update of the remaining pivot rows -- no serial substitution chain.
+// Forward substitution with a lower-trapezoidal panel P (Lp: unit diagonal, Up: general diagonal), backward substitution with its
+// transpose.  The pivot block of a supernode is cut into windows of LU_SOLVE_W columns; per window two kernels run:
+//   tri     (one CTA of 32 warps per supernode and right-hand side): the W x W triangle of the window, blocked by NB.  The
+//           diagonal blocks were inverted at factorisation time, so a block step is a 32x32 matrix-vector product (warp w = row w,
+//           shuffle reduction) followed by the rank-NB update of the remaining rows of the window -- no serial substitution chain.
+//   update  (many CTAs per supernode, NR right-hand sides per pass over the panel): all rows below the window -- the rest of the
+//           pivot block and the structure rows -- i.e. the bulk of the factor, streamed once at full width.
+// Large supernodes (the top of the assembly tree, where a level has fewer supernodes than the GPU has SMs) are thereby spread
+// over the whole GPU instead of one CTA each.
 //   use_up = 0: T_kk^-1 = L_kk^-1            use_up = 1: T_kk = U_kk^T  ->  T_kk^-1 = (U_kk^-1)^T
-__global__ void __launch_bounds__(1024) lu_fwd_pivot_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int nrhs, int64_t n, cplx* __restrict__ x) {
+#define LU_SOLVE_W 256
+
+__global__ void __launch_bounds__(1024) lu_fwd_tri_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int c_lo, int64_t n, cplx* __restrict__ x) {
   const int sn = list[blockIdx.x];
   SnView S = sn_view(D, sn);
+  if (c_lo >= S.s) return;
+  const int c_hi = min(c_lo + LU_SOLVE_W, S.s);
   const cplx* P = use_up ? S.up : S.lp;
   const cplx* dinv = D.dinv + D.dinv_off[sn] + (use_up ? NB * NB : 0);
   __shared__ cplx yk[NB];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  {
-    const int rhs = blockIdx.y;  // one CTA per (supernode, right-hand side)
-    cplx* xs = x + (size_t)rhs * n + S.first;
-    for (int c0 = 0, kb = 0; c0 < S.s; c0 += NB, kb++) {
-      const int nb = min(NB, S.s - c0);
-      {
-        const cplx* Tinv = dinv + (size_t)kb * 2 * NB * NB;
-        // y[warp] = sum_lane Tinv(warp, lane) x[lane]   (Tinv(r,c) stored at r + c*NB; transposed access for use_up)
-        cplx m = use_up ? Tinv[lane + warp * NB] : Tinv[warp + lane * NB];
-        cplx v = lane < nb ? xs[c0 + lane] : make_double2(0.0, 0.0);
-        double sr = m.x * v.x - m.y * v.y, si = m.x * v.y + m.y * v.x;
+  cplx* xs = x + (size_t)blockIdx.y * n + S.first;  // one CTA per (supernode, right-hand side)
+  for (int c0 = c_lo, kb = c_lo / NB; c0 < c_hi; c0 += NB, kb++) {
+    const int nb = min(NB, S.s - c0);
+    {
+      const cplx* Tinv = dinv + (size_t)kb * 2 * NB * NB;
+      // y[warp] = sum_lane Tinv(warp, lane) x[lane]   (Tinv(r,c) stored at r + c*NB; transposed access for use_up)
+      cplx m = use_up ? Tinv[lane + warp * NB] : Tinv[warp + lane * NB];
+      cplx v = lane < nb ? xs[c0 + lane] : make_double2(0.0, 0.0);
+      double sr = m.x * v.x - m.y * v.y, si = m.x * v.y + m.y * v.x;
 #pragma unroll
-        for (int off = 16; off; off >>= 1) {
-          sr += __shfl_xor_sync(0xffffffffu, sr, off);
-          si += __shfl_xor_sync(0xffffffffu, si, off);
-        }
-        if (lane == 0) yk[warp] = make_double2(sr, si);
+      for (int off = 16; off; off >>= 1) {
+        sr += __shfl_xor_sync(0xffffffffu, sr, off);
+        si += __shfl_xor_sync(0xffffffffu, si, off);
       }
-      __syncthreads();
-      if (threadIdx.x < nb) xs[c0 + threadIdx.x] = yk[threadIdx.x];
-      for (int i = c0 + nb + threadIdx.x; i < S.s; i += blockDim.x) {
-        cplx acc = make_double2(0.0, 0.0);
-        const cplx* row = P + i + (size_t)c0 * S.ld;
+      if (lane == 0) yk[warp] = make_double2(sr, si);
+    }
+    __syncthreads();
+    if (threadIdx.x < nb) xs[c0 + threadIdx.x] = yk[threadIdx.x];
+    {
+      // rank-NB update of the remaining rows of the window: 4 threads per row, 8 columns each (the window has at most 256 rows)
+      const int i = c0 + nb + (threadIdx.x >> 2), part = (threadIdx.x & 3) * (NB / 4);
+      cplx acc = make_double2(0.0, 0.0);
+      if (i < c_hi) {
+        const cplx* row = P + i + (size_t)(c0 + part) * S.ld;
+#pragma unroll
+        for (int j = 0; j < NB / 4; j++)
+          if (part + j < nb) {
+            const cplx a = row[(size_t)j * S.ld], v = yk[part + j];
+            acc.x += a.x * v.x - a.y * v.y;
+            acc.y += a.x * v.y + a.y * v.x;
+          }
+      }
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 1);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 1);
+      acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 2);
+      acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 2);
+      if (i < c_hi && (threadIdx.x & 3) == 0) xs[i] = csub(xs[i], acc);
+    }
+    __syncthreads();
+  }
+}
+
+// x[rows below the window] -= P[rows, window] * y_window.  grid.x row chunks of 64, grid.y supernode, grid.z groups of NR
+// right-hand sides; a CTA is 64 rows x 4 column quarters (the quarters are summed through shared memory), so a level with few, large
+// supernodes still keeps many loads in flight.  Pivot rows are owned by one thread; structure rows are shared with sibling
+// supernodes -> atomic.
+template <int NR>
+__global__ void __launch_bounds__(256) lu_fwd_update_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int c_lo, int nrhs, int64_t n,
+                                                            cplx* __restrict__ x) {
+  SnView S = sn_view(D, list[blockIdx.y]);
+  if (c_lo >= S.s) return;
+  const int c_hi = min(c_lo + LU_SOLVE_W, S.s);
+  const int nrows = S.ld - c_hi;
+  if (blockIdx.x * 64 >= nrows) return;
+  const int r = threadIdx.x & 63, quarter = threadIdx.x >> 6;
+  const int i = blockIdx.x * 64 + r;
+  const int rhs0 = blockIdx.z * NR, nr = min(NR, nrhs - rhs0);
+  const cplx* P = (use_up ? S.up : S.lp) + c_hi;
+  const int32_t* st = D.struct_idx + D.struct_ptr[list[blockIdx.y]];
+  __shared__ cplx ys[NR][LU_SOLVE_W];  // window part of x, later the partial sums of quarters 1..3 ([q][quarter-1][row])
+  const int ncol = c_hi - c_lo;
+  for (int j = threadIdx.x; j < ncol; j += 256)
+#pragma unroll
+    for (int q = 0; q < NR; q++)
+      if (q < nr) ys[q][j] = x[(size_t)(rhs0 + q) * n + S.first + c_lo + j];
+  __syncthreads();
+  cplx acc[NR];
+#pragma unroll
+  for (int q = 0; q < NR; q++) acc[q] = make_double2(0.0, 0.0);
+  if (i < nrows) {
+    const int j0 = quarter * (LU_SOLVE_W / 4), j1 = min(ncol, j0 + LU_SOLVE_W / 4);
+    const cplx* row = P + i + (size_t)c_lo * S.ld;
 #pragma unroll 8
-        for (int j = 0; j < nb; j++) {
-          cplx a = row[(size_t)j * S.ld];
-          acc.x += a.x * yk[j].x - a.y * yk[j].y;
-          acc.y += a.x * yk[j].y + a.y * yk[j].x;
-        }
-        xs[i] = csub(xs[i], acc);
+    for (int j = j0; j < j1; j++) {
+      const cplx a = row[(size_t)j * S.ld];
+#pragma unroll
+      for (int q = 0; q < NR; q++) {
+        acc[q].x += a.x * ys[q][j].x - a.y * ys[q][j].y;
+        acc[q].y += a.x * ys[q][j].y + a.y * ys[q][j].x;
       }
-      __syncthreads();
     }
+  }
+  __syncthreads();
+  if (quarter)
+#pragma unroll
+    for (int q = 0; q < NR; q++) ys[q][(quarter - 1) * 64 + r] = acc[q];
+  __syncthreads();
+  if (quarter == 0 && i < nrows) {
+    const int g = c_hi + i;
+#pragma unroll
+    for (int q = 0; q < NR; q++)
+      if (q < nr) {
+        cplx t = acc[q];
+#pragma unroll
+        for (int u = 0; u < 3; u++) {
+          t.x += ys[q][u * 64 + r].x;
+          t.y += ys[q][u * 64 + r].y;
+        }
+        cplx* xr = x + (size_t)(rhs0 + q) * n;
+        if (g < S.s) {
+          cplx* d = xr + S.first + g;
+          *d = csub(*d, t);
+        } else
+          catomic_sub(xr + st[g - S.s], t);
+      }
   }
 }
 
-// phase 2 (grid.x row chunks, grid.y supernode): x[struct rows] -= P21 * y_S  (atomic: siblings share ancestors)
-__global__ void __launch_bounds__(128) lu_fwd_struct_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int nrhs, int64_t n, cplx* __restrict__ x) {
+// backward: x_S[c] -= sum_{rows below the window} P[row, c] * x[row]   for the columns c of the window.
+// grid.x = (column groups of 8 = 8 warps) x (row chunks), grid.y supernode, grid.z groups of NR right-hand sides
+template <int NR>
+__global__ void __launch_bounds__(256) lu_bwd_update_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int c_lo, int ncg, int row_chunk,
+                                                            int nrhs, int64_t n, cplx* __restrict__ x) {
   SnView S = sn_view(D, list[blockIdx.y]);
-  const int i = blockIdx.x * 128 + threadIdx.x;
-  if (blockIdx.x * 128 >= S.r) return;
-  const cplx* P = (use_up ? S.up : S.lp) + S.s;
-  const int32_t* st = D.struct_idx + D.struct_ptr[list[blockIdx.y]];
-  __shared__ cplx ys[128];
-  {
-    const int rhs = blockIdx.z;
-    const cplx* xs = x + (size_t)rhs * n + S.first;
-    cplx acc = make_double2(0.0, 0.0);
-    for (int c0 = 0; c0 < S.s; c0 += 128) {
-      __syncthreads();
-      if (c0 + threadIdx.x < S.s) ys[threadIdx.x] = xs[c0 + threadIdx.x];
-      __syncthreads();
-      if (i < S.r) {
-        const int nc = min(128, S.s - c0);
-        const cplx* row = P + i + (size_t)c0 * S.ld;
-        for (int j = 0; j < nc; j++) {
-          cplx a = row[(size_t)j * S.ld];
-          acc.x += a.x * ys[j].x - a.y * ys[j].y;
-          acc.y += a.x * ys[j].y + a.y * ys[j].x;
-        }
-      }
-    }
-    if (i < S.r) catomic_sub(x + (size_t)rhs * n + st[i], acc);
-  }
-}
-
-// backward substitution with the TRANSPOSE of a lower-trapezoidal panel.
-// phase 1 (grid.x column chunks of 8 columns = 8 warps, grid.y supernode): x_S[c] -= sum_i P21[i,c] * x[struct[i]]
-__global__ void __launch_bounds__(256) lu_bwd_struct_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int nrhs, int64_t n, cplx* __restrict__ x) {
-  SnView S = sn_view(D, list[blockIdx.y]);
+  if (c_lo >= S.s) return;
+  const int c_hi = min(c_lo + LU_SOLVE_W, S.s);
+  const int nrows = S.ld - c_hi;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = blockIdx.x * 8 + warp;
-  if (c >= S.s || S.r == 0) return;
-  const cplx* col = (use_up ? S.up : S.lp) + S.s + (size_t)c * S.ld;
+  const int c = c_lo + (blockIdx.x % ncg) * 8 + warp;  // ncg = column groups of the widest window on the level
+  const int r_begin = (blockIdx.x / ncg) * row_chunk;
+  if (c >= c_hi || r_begin >= nrows) return;
+  const int r_end = min(nrows, r_begin + row_chunk);
+  const int rhs0 = blockIdx.z * NR, nr = min(NR, nrhs - rhs0);
+  const cplx* col = (use_up ? S.up : S.lp) + c_hi + (size_t)c * S.ld;
   const int32_t* st = D.struct_idx + D.struct_ptr[list[blockIdx.y]];
-  {
-    const int rhs = blockIdx.z;
-    cplx* xr = x + (size_t)rhs * n;
-    double sr = 0.0, si = 0.0;
-    for (int i = lane; i < S.r; i += 32) {
-      cplx a = col[i], v = xr[st[i]];
-      sr += a.x * v.x - a.y * v.y;
-      si += a.x * v.y + a.y * v.x;
-    }
+  double sr[NR], si[NR];
+#pragma unroll
+  for (int q = 0; q < NR; q++) sr[q] = si[q] = 0.0;
+  for (int i = r_begin + lane; i < r_end; i += 32) {
+    const cplx a = col[i];
+    const int g = c_hi + i;
+    const int64_t idx = g < S.s ? (int64_t)S.first + g : (int64_t)st[g - S.s];
+#pragma unroll
+    for (int q = 0; q < NR; q++)
+      if (q < nr) {
+        const cplx v = x[(size_t)(rhs0 + q) * n + idx];
+        sr[q] += a.x * v.x - a.y * v.y;
+        si[q] += a.x * v.y + a.y * v.x;
+      }
+  }
+#pragma unroll
+  for (int q = 0; q < NR; q++) {
 #pragma unroll
     for (int off = 16; off; off >>= 1) {
-      sr += __shfl_xor_sync(0xffffffffu, sr, off);
-      si += __shfl_xor_sync(0xffffffffu, si, off);
+      sr[q] += __shfl_xor_sync(0xffffffffu, sr[q], off);
+      si[q] += __shfl_xor_sync(0xffffffffu, si[q], off);
     }
-    if (lane == 0) {
-      cplx* d = xr + S.first + c;
-      d->x -= sr;
-      d->y -= si;
-    }
+    if (lane == 0 && q < nr) catomic_sub(x + (size_t)(rhs0 + q) * n + S.first + c, make_double2(sr[q], si[q]));
   }
 }
 
-// phase 2 (one CTA per supernode, 32 warps): pivot block, blocks from last to first.
+// backward, W x W triangle of the window (one CTA per supernode and right-hand side, 32 warps): blocks from last to first.
 //   use_up = 1 (A x = b): x_k = U_kk^-1 (...)        use_up = 0 (A^T x = b): x_k = (L_kk^-1)^T (...)
-__global__ void __launch_bounds__(1024) lu_bwd_pivot_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int nrhs, int64_t n, cplx* __restrict__ x) {
+__global__ void __launch_bounds__(1024) lu_bwd_tri_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int c_lo, int64_t n, cplx* __restrict__ x) {
   const int sn = list[blockIdx.x];
   SnView S = sn_view(D, sn);
+  if (c_lo >= S.s) return;
+  const int c_hi = min(c_lo + LU_SOLVE_W, S.s);
   const cplx* P = use_up ? S.up : S.lp;
   const cplx* dinv = D.dinv + D.dinv_off[sn] + (use_up ? NB * NB : 0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int nblk = (S.s + NB - 1) / NB;
   __shared__ cplx yk[NB];
-  {
-    const int rhs = blockIdx.y;
-    cplx* xs = x + (size_t)rhs * n + S.first;
-    for (int kb = nblk - 1; kb >= 0; kb--) {
-      const int c0 = kb * NB, nb = min(NB, S.s - c0);
-      // column c0+warp: subtract the contribution of the already solved pivot rows below this block
-      {
-        double sr = 0.0, si = 0.0;
-        if (warp < nb) {
-          const cplx* col = P + (size_t)(c0 + warp) * S.ld;
-          for (int i = c0 + nb + lane; i < S.s; i += 32) {
-            cplx a = col[i], v = xs[i];
-            sr += a.x * v.x - a.y * v.y;
-            si += a.x * v.y + a.y * v.x;
-          }
+  cplx* xs = x + (size_t)blockIdx.y * n + S.first;
+  for (int kb = (c_hi - 1) / NB; kb >= c_lo / NB; kb--) {
+    const int c0 = kb * NB, nb = min(NB, S.s - c0);
+    // column c0+warp: subtract the contribution of the already solved rows of the window below this block
+    {
+      double sr = 0.0, si = 0.0;
+      if (warp < nb) {
+        const cplx* col = P + (size_t)(c0 + warp) * S.ld;
+        for (int i = c0 + nb + lane; i < c_hi; i += 32) {
+          cplx a = col[i], v = xs[i];
+          sr += a.x * v.x - a.y * v.y;
+          si += a.x * v.y + a.y * v.x;
         }
-#pragma unroll
-        for (int off = 16; off; off >>= 1) {
-          sr += __shfl_xor_sync(0xffffffffu, sr, off);
-          si += __shfl_xor_sync(0xffffffffu, si, off);
-        }
-        if (lane == 0) yk[warp] = warp < nb ? make_double2(xs[c0 + warp].x - sr, xs[c0 + warp].y - si) : make_double2(0.0, 0.0);
       }
-      __syncthreads();
-      {
-        // x[warp] = sum_lane M(warp, lane) y[lane], M = U_kk^-1 (use_up) or (L_kk^-1)^T
-        const cplx* Tinv = dinv + (size_t)kb * 2 * NB * NB;
-        cplx m = use_up ? Tinv[warp + lane * NB] : Tinv[lane + warp * NB];
-        cplx v = yk[lane];
-        double sr = m.x * v.x - m.y * v.y, si = m.x * v.y + m.y * v.x;
 #pragma unroll
-        for (int off = 16; off; off >>= 1) {
-          sr += __shfl_xor_sync(0xffffffffu, sr, off);
-          si += __shfl_xor_sync(0xffffffffu, si, off);
-        }
-        if (lane == 0 && warp < nb) xs[c0 + warp] = make_double2(sr, si);
+      for (int off = 16; off; off >>= 1) {
+        sr += __shfl_xor_sync(0xffffffffu, sr, off);
+        si += __shfl_xor_sync(0xffffffffu, si, off);
       }
-      __syncthreads();
+      if (lane == 0) yk[warp] = warp < nb ? make_double2(xs[c0 + warp].x - sr, xs[c0 + warp].y - si) : make_double2(0.0, 0.0);
     }
+    __syncthreads();
+    {
+      // x[warp] = sum_lane M(warp, lane) y[lane], M = U_kk^-1 (use_up) or (L_kk^-1)^T
+      const cplx* Tinv = dinv + (size_t)kb * 2 * NB * NB;
+      cplx m = use_up ? Tinv[warp + lane * NB] : Tinv[lane + warp * NB];
+      cplx v = yk[lane];
+      double sr = m.x * v.x - m.y * v.y, si = m.x * v.y + m.y * v.x;
+#pragma unroll
+      for (int off = 16; off; off >>= 1) {
+        sr += __shfl_xor_sync(0xffffffffu, sr, off);
+        si += __shfl_xor_sync(0xffffffffu, si, off);
+      }
+      if (lane == 0 && warp < nb) xs[c0 + warp] = make_double2(sr, si);
+    }
+    __syncthreads();
   }
 }
 
@@ -739,43 +800,72 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
   h->last_ms["static_pivots"] = flag[1];
 }
 
-static void lu_sweeps(wae_ctx* h, LuSolver& S, int trans_t, int nrhs, cplx* y) {
+template <int NR>
+static void lu_sweeps_nr(wae_ctx* h, LuSolver& S, int trans_t, int nrhs, cplx* y) {
   LuSymbolic& Y = S.sym;
   cudaStream_t st = h->stream;
   LuDev D = make_dev(S);
   const int maxd = (int)Y.levels.size() - 1;
   const int fwd_up = trans_t ? 1 : 0;  // A: forward with Lp, backward with Up ; A^T: forward with Up, backward with Lp
+  const int zr = (nrhs + NR - 1) / NR;
+  const int W = LU_SOLVE_W;
   for (int d = maxd; d >= 0; d--) {
     const std::vector<int32_t>& L = Y.levels[d];
-    int max_r = 0;
-    for (int32_t k : L) max_r = std::max(max_r, (int)(Y.struct_ptr[k + 1] - Y.struct_ptr[k]));
+    int max_s = 0, max_ld = 0;
+    for (int32_t k : L) {
+      const int s = Y.sn_first[k + 1] - Y.sn_first[k];
+      max_s = std::max(max_s, s);
+      max_ld = std::max(max_ld, s + (int)(Y.struct_ptr[k + 1] - Y.struct_ptr[k]));
+    }
     for (int z0 = 0; z0 < (int)L.size(); z0 += 32768) {
-      int zc = std::min<int>(32768, (int)L.size() - z0);
-      lu_fwd_pivot_kernel<<<dim3(zc, nrhs), 1024, 0, st>>>(D, S.d_level[d].p + z0, fwd_up, nrhs, Y.n, y);
-      h->launches++;
-      if (max_r > 0) {
-        lu_fwd_struct_kernel<<<dim3((max_r + 127) / 128, zc, nrhs), 128, 0, st>>>(D, S.d_level[d].p + z0, fwd_up, nrhs, Y.n, y);
+      const int zc = std::min<int>(32768, (int)L.size() - z0);
+      const int32_t* lst = S.d_level[d].p + z0;
+      for (int c_lo = 0; c_lo < max_s; c_lo += W) {
+        lu_fwd_tri_kernel<<<dim3(zc, nrhs), 1024, 0, st>>>(D, lst, fwd_up, c_lo, Y.n, y);
         h->launches++;
+        const int rows = max_ld - std::min(c_lo + W, max_s);  // upper bound of the rows below the window over the level
+        if (max_ld > c_lo + 1 && rows + W > 0) {
+          const int rmax = max_ld - c_lo;  // a supernode with a short pivot block has its window end (and first row) earlier
+          lu_fwd_update_kernel<NR><<<dim3((rmax + 63) / 64, zc, zr), 256, 0, st>>>(D, lst, fwd_up, c_lo, nrhs, Y.n, y);
+          h->launches++;
+        }
       }
     }
   }
   for (int d = 0; d <= maxd; d++) {
     const std::vector<int32_t>& L = Y.levels[d];
-    int max_s = 0, max_r = 0;
+    int max_s = 0, max_ld = 0;
     for (int32_t k : L) {
-      max_s = std::max(max_s, Y.sn_first[k + 1] - Y.sn_first[k]);
-      max_r = std::max(max_r, (int)(Y.struct_ptr[k + 1] - Y.struct_ptr[k]));
+      const int s = Y.sn_first[k + 1] - Y.sn_first[k];
+      max_s = std::max(max_s, s);
+      max_ld = std::max(max_ld, s + (int)(Y.struct_ptr[k + 1] - Y.struct_ptr[k]));
     }
     for (int z0 = 0; z0 < (int)L.size(); z0 += 32768) {
-      int zc = std::min<int>(32768, (int)L.size() - z0);
-      if (max_r > 0) {
-        lu_bwd_struct_kernel<<<dim3((max_s + 7) / 8, zc, nrhs), 256, 0, st>>>(D, S.d_level[d].p + z0, !fwd_up, nrhs, Y.n, y);
+      const int zc = std::min<int>(32768, (int)L.size() - z0);
+      const int32_t* lst = S.d_level[d].p + z0;
+      for (int c_lo = ((max_s - 1) / W) * W; c_lo >= 0; c_lo -= W) {
+        const int rmax = max_ld - c_lo;
+        if (rmax > 1) {
+          // few supernodes on the level: cut the rows into chunks so that the level still fills the GPU
+          const int ncg = (std::min(W, max_s - c_lo) + 7) / 8;
+          int row_chunk = rmax;
+          if (zc * ncg < 4 * h->sm_count) row_chunk = std::max(256, (int)((int64_t)rmax * zc * ncg / (4 * h->sm_count)) / 32 * 32 + 32);
+          const int nrc = (rmax + row_chunk - 1) / row_chunk;
+          lu_bwd_update_kernel<NR><<<dim3(ncg * nrc, zc, zr), 256, 0, st>>>(D, lst, !fwd_up, c_lo, ncg, row_chunk, nrhs, Y.n, y);
+          h->launches++;
+        }
+        lu_bwd_tri_kernel<<<dim3(zc, nrhs), 1024, 0, st>>>(D, lst, !fwd_up, c_lo, Y.n, y);
         h->launches++;
       }
-      lu_bwd_pivot_kernel<<<dim3(zc, nrhs), 1024, 0, st>>>(D, S.d_level[d].p + z0, !fwd_up, nrhs, Y.n, y);
-      h->launches++;
     }
   }
+}
+
+static void lu_sweeps(wae_ctx* h, LuSolver& S, int trans_t, int nrhs, cplx* y) {
+  if (nrhs >= 8) lu_sweeps_nr<8>(h, S, trans_t, nrhs, y);
+  else if (nrhs >= 4) lu_sweeps_nr<4>(h, S, trans_t, nrhs, y);
+  else if (nrhs >= 2) lu_sweeps_nr<2>(h, S, trans_t, nrhs, y);
+  else lu_sweeps_nr<1>(h, S, trans_t, nrhs, y);
 }
 
 // ---- rank-k (Sherman-Morrison-Woodbury) correction on top of the symmetric factorisation ------------------------------
