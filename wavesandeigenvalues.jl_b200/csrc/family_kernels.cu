@@ -10,6 +10,7 @@
 #define WAE_MAX_FUSED 8
 struct CombineArgs {
   const double* val[WAE_MAX_FUSED];
+  const int32_t* inv[WAE_MAX_FUSED];  // NULL: the term lives on the union pattern; else union nz -> term nz (-1: absent)
   double cr[WAE_MAX_FUSED], ci[WAE_MAX_FUSED];
   int is_complex[WAE_MAX_FUSED];
   int n;
@@ -20,6 +21,7 @@ __global__ void __launch_bounds__(256) combine_identity_kernel(CombineArgs a, in
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += stride) {
     double re = 0.0, im = 0.0;
+    int64_t qprev = k;
     if (accumulate) {
       double2 o = out[k];
       re = o.x;
@@ -28,12 +30,17 @@ __global__ void __launch_bounds__(256) combine_identity_kernel(CombineArgs a, in
 #pragma unroll
     for (int t = 0; t < WAE_MAX_FUSED; t++) {
       if (t < a.n) {
+        // consecutive terms on the same sub-pattern (M, K) share the inverse map: one load serves both
+        int64_t q = k;
+        if (a.inv[t]) q = (t > 0 && a.inv[t] == a.inv[t - 1]) ? qprev : (int64_t)a.inv[t][k];
+        qprev = q;
+        if (q < 0) continue;
         if (a.is_complex[t]) {
-          double2 v = reinterpret_cast<const double2*>(a.val[t])[k];
+          double2 v = reinterpret_cast<const double2*>(a.val[t])[q];
           re += a.cr[t] * v.x - a.ci[t] * v.y;
           im += a.cr[t] * v.y + a.ci[t] * v.x;
         } else {
-          double v = a.val[t][k];
+          double v = a.val[t][q];
           re += a.cr[t] * v;
           im += a.ci[t] * v;
         }
@@ -82,9 +89,10 @@ void wae_combine_device(wae_ctx* h, Family& F, const double* coeffs, int slot) {
   };
   for (int t = 0; t < F.n_terms; t++) {
     double cr = coeffs[2 * t], ci = coeffs[2 * t + 1];
-    if (!F.identity[t] || (cr == 0.0 && ci == 0.0)) continue;
+    if ((!F.identity[t] && F.inv_of[t] < 0) || (cr == 0.0 && ci == 0.0)) continue;
     Matrix& M = h->mat(F.mats[t]);
     a.val[a.n] = M.d_val.p;
+    a.inv[a.n] = F.identity[t] ? nullptr : F.d_inv[F.inv_of[t]].p;
     a.cr[a.n] = cr;
     a.ci[a.n] = ci;
     a.is_complex[a.n] = M.is_complex;
@@ -93,11 +101,11 @@ void wae_combine_device(wae_ctx* h, Family& F, const double* coeffs, int slot) {
   if (a.n || !any) flush();  // also zero-fills when no identity term is active
   for (int t = 0; t < F.n_terms; t++) {
     double cr = coeffs[2 * t], ci = coeffs[2 * t + 1];
-    if (F.identity[t] || (cr == 0.0 && ci == 0.0)) continue;
+    if (F.identity[t] || F.inv_of[t] >= 0 || (cr == 0.0 && ci == 0.0)) continue;
     Matrix& M = h->mat(F.mats[t]);
     int64_t nnz = h->pat(M.pattern).nnz;
     if (!nnz) continue;
-    combine_mapped_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, h->stream>>>(M.d_val.p, M.is_complex, cr, ci, F.d_map[t].p, nnz, out);
+    combine_mapped_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, h->stream>>>(M.d_val.p, M.is_complex, cr, ci, F.d_map[F.map_of[t]].p, nnz, out);
     h->launches++;
   }
   CUDA_CHECK(cudaGetLastError());
@@ -197,6 +205,6 @@ void wae_axpy_term(wae_ctx* h, Family& F, int t, double cr, double ci, cplx* out
   if (F.identity[t])
     axpy_identity_kernel<<<blocks, 256, 0, h->stream>>>(M.d_val.p, M.is_complex, cr, ci, nnz, out);
   else
-    combine_mapped_kernel<<<blocks, 256, 0, h->stream>>>(M.d_val.p, M.is_complex, cr, ci, F.d_map[t].p, nnz, out);
+    combine_mapped_kernel<<<blocks, 256, 0, h->stream>>>(M.d_val.p, M.is_complex, cr, ci, F.d_map[F.map_of[t]].p, nnz, out);
   h->launches++;
 }

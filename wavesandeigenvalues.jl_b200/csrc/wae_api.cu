@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <numeric>
+#include <thread>
 
 #include "lu.h"
 #include "wae_internal.h"
@@ -585,6 +586,9 @@ int32_t wae_family_create(wae_ctx* h, int32_t n_terms, const int32_t* mat_ids, i
   Pattern& U = h->pat(upid);
   F.identity.resize(n_terms);
   F.d_map.resize(n_terms);
+  F.d_inv.resize(n_terms);
+  F.map_of.assign(n_terms, -1);
+  F.inv_of.assign(n_terms, -1);
   for (int t = 0; t < n_terms; t++) {
     Matrix& M = h->mat(mat_ids[t]);
     if (M.pattern == upid) {
@@ -592,15 +596,40 @@ int32_t wae_family_create(wae_ctx* h, int32_t n_terms, const int32_t* mat_ids, i
       continue;
     }
     F.identity[t] = false;
+    for (int t2 = 0; t2 < t; t2++)  // terms on the same pattern (M and K) share their maps
+      if (!F.identity[t2] && h->mat(mat_ids[t2]).pattern == M.pattern) {
+        F.map_of[t] = F.map_of[t2];
+        F.inv_of[t] = F.inv_of[t2];
+      }
+    if (F.map_of[t] >= 0) continue;
     Pattern& A = h->pat(M.pattern);
     std::vector<int32_t> map(A.nnz);
-    for (int64_t j = 0; j < dim; j++) {
-      const int32_t* ub = U.rowval.data() + U.colptr[j];
-      const int32_t* ue = U.rowval.data() + U.colptr[j + 1];
-      for (int64_t k = A.colptr[j]; k < A.colptr[j + 1]; k++)
-        map[k] = (int32_t)(std::lower_bound(ub, ue, A.rowval[k]) - U.rowval.data());
-    }
+    const unsigned nthr = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+    auto fill = [&](int64_t j0, int64_t j1) {
+      for (int64_t j = j0; j < j1; j++) {
+        const int32_t* ub = U.rowval.data() + U.colptr[j];
+        const int32_t* ue = U.rowval.data() + U.colptr[j + 1];
+        for (int64_t k = A.colptr[j]; k < A.colptr[j + 1]; k++) {
+          ub = std::lower_bound(ub, ue, A.rowval[k]);
+          map[k] = (int32_t)(ub - U.rowval.data());
+        }
+      }
+    };
+    if (A.nnz > (1 << 20)) {
+      std::vector<std::thread> th;
+      for (unsigned q = 0; q < nthr; q++) th.emplace_back(fill, dim * q / nthr, dim * (q + 1) / nthr);
+      for (auto& x : th) x.join();
+    } else
+      fill(0, dim);
     F.d_map[t].upload(map, h->stream);
+    F.map_of[t] = t;
+    if (2 * A.nnz >= U.nnz) {  // a large term: inverse map for the fused gather pass of wae_combine
+      std::vector<int32_t> inv(U.nnz, -1);
+      for (int64_t k = 0; k < A.nnz; k++) inv[map[k]] = (int32_t)k;
+      F.d_inv[t].upload(inv, h->stream);
+      F.inv_of[t] = t;
+    }
+    CUDA_CHECK(cudaStreamSynchronize(h->stream));
   }
   for (int s = 0; s < WAE_FAMILY_SLOTS; s++) F.slot[s].alloc(0);
   CUDA_CHECK(cudaStreamSynchronize(h->stream));

@@ -113,7 +113,10 @@ struct Family {
   std::vector<int> mats;
   int pattern = -1;                        // union pattern id
   std::vector<bool> identity;              // term pattern == union pattern
-  std::vector<DevBuf<int32_t>> d_map;      // term nz -> union nz (empty if identity)
+  std::vector<DevBuf<int32_t>> d_map;      // term nz -> union nz (empty if identity); terms on the same pattern share the map of the first one
+  std::vector<int> map_of;                 // term -> index into d_map (the term that owns the map)
+  std::vector<DevBuf<int32_t>> d_inv;      // large sub-pattern terms: union nz -> term nz (-1: absent), so that they join the fused gather pass
+  std::vector<int> inv_of;                 // term -> index into d_inv (owner term) or -1
   DevBuf<double> slot[WAE_FAMILY_SLOTS];   // complex values, 2*nnz doubles each
   std::vector<double> slot_coeffs[WAE_FAMILY_SLOTS];  // term coefficients of the last wae_combine into each slot
   DevBuf<double> d_io[2];                  // cached staging buffers of wae_family_spmm (grow-only)

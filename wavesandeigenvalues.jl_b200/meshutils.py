@@ -284,13 +284,21 @@ def kuhn_box(ncube, lo, hi, jitter=0.0, seed=0, flame_layer=None, name="kuhn_box
     corner = np.stack([pid[cx + (k & 1), cy + ((k >> 1) & 1), cz + ((k >> 2) & 1)] for k in range(8)], axis=1)
     tets = corner[:, _KUHN].reshape(-1, 4)
     tet_cz = np.repeat(cz, 6)
-    # boundary triangles: faces that occur once
-    faces = np.stack([tets[:, [0, 1, 2]], tets[:, [0, 1, 3]], tets[:, [0, 2, 3]], tets[:, [1, 2, 3]]], axis=1).reshape(-1, 3)
-    fs = np.sort(faces, axis=1)
-    npt = pts.shape[1]
-    key = (fs[:, 0] * npt + fs[:, 1]) * npt + fs[:, 2]
-    uk, idx, cnt = np.unique(key, return_index=True, return_counts=True)
-    tris = faces[idx[cnt == 1]]
+    # boundary triangles: the faces whose three vertices lie on one of the six planes of the box (each occurs once); this
+    # needs no global sort of the 4 n_tet faces, so it scales to the 50 M-tetrahedra stress configuration
+    on_plane = []
+    vx, vy, vz = (np.arange(pts.shape[1]) % (nx + 1)), (np.arange(pts.shape[1]) // (nx + 1)) % (ny + 1), np.arange(pts.shape[1]) // ((nx + 1) * (ny + 1))
+    for g, nmax in ((vx, nx), (vy, ny), (vz, nz)):
+        on_plane.append((g == 0).astype(np.int8))
+        on_plane.append((g == nmax).astype(np.int8))
+    tris = []
+    for f in ([0, 1, 2], [0, 1, 3], [0, 2, 3], [1, 2, 3]):
+        face = tets[:, f]
+        hit = np.zeros(len(tets), dtype=bool)
+        for m in on_plane:
+            hit |= (m[face[:, 0]] & m[face[:, 1]] & m[face[:, 2]]).astype(bool)
+        tris.append(face[hit])
+    tris = np.concatenate(tris)
     zc = pts[2, tris]
     tol = 1e-9 * (hi[2] - lo[2])
     on_out = np.all(np.abs(zc - hi[2]) < tol, axis=1)
