@@ -176,3 +176,198 @@ def aggregate_elements(mesh, order):
         e = [mesh.line_idx(t[a], t[b]) + npts for a, b in ((0, 1), (0, 2), (1, 2))]
         tris.append(list(t) + e)
     return tris, tets, npts + len(mesh.lines)
+
+
+# ---------------------------------------------------------------------------------------------
+# extend_mesh: half-cell -> unit cell / full annulus           src/Mesh/annular_meshes.jl:14-181, 269-570
+# ---------------------------------------------------------------------------------------------
+def three_points_to_plane(A):  # annular_meshes.jl:14-26 (the d < 1e-7 -> 0 rule included)
+    a, b, c = A[:, 0], A[:, 1], A[:, 2]
+    n = np.cross(a - c, b - c)
+    n = n / np.linalg.norm(n)
+    d = -float(np.dot(n, c))
+    if d < 1e-7:
+        d = 0.0
+    return np.array([n[0], n[1], n[2], d])
+
+
+def find_foot_of_perpendicular(pnt, pln):  # :61-66
+    a, d = pln[:3], pln[3]
+    return a * (-np.dot(a, pnt) - d) + pnt
+
+
+def reflect_point_at_plane(pnt, pln):  # :46-52
+    return 2 * find_foot_of_perpendicular(pnt, pln) - pnt
+
+
+def make_normal_outwards(pln, testpoint):  # :74-79
+    foot = find_foot_of_perpendicular(testpoint, pln)
+    return pln * (-np.sign(np.dot(pln[:3], testpoint - foot)))
+
+
+def find_intersection_of_two_planes(p1, p2):  # :92-109 (p = rhs \ M: least squares with a 5-vector on the left)
+    n = np.cross(p1[:3], p2[:3])
+    n = n / np.linalg.norm(n)
+    f1 = find_foot_of_perpendicular(np.zeros(3), p1)
+    f2 = find_foot_of_perpendicular(np.zeros(3), p2)
+    M = np.array([[2.0, 0, 0, p1[0], p2[0]], [2.0, 0, 0, p1[1], p2[1]], [2.0, 0, 0, p1[2], p2[2]],
+                  [p1[0], p1[1], p1[2], 0, 0], [p2[0], p2[1], p2[2], 0, 0]])
+    rhs = np.array([0, 0, 0, np.dot(f1, p1[:3]), np.dot(f2, p2[:3])], dtype=float)
+    p = np.linalg.lstsq(rhs.reshape(5, 1), M, rcond=None)[0].ravel()
+    return p[:3], n
+
+
+def create_rotation_matrix_around_axis(n, al):  # :116-121
+    c, s = np.cos(al), np.sin(al)
+    return np.array([[n[0] ** 2 * (1 - c) + c, n[0] * n[1] * (1 - c) - n[2] * s, n[0] * n[2] * (1 - c) + n[1] * s],
+                     [n[1] * n[0] * (1 - c) + n[2] * s, n[1] ** 2 * (1 - c) + c, n[1] * n[2] * (1 - c) - n[0] * s],
+                     [n[2] * n[0] * (1 - c) - n[1] * s, n[2] * n[1] * (1 - c) + n[0] * s, n[2] ** 2 * (1 - c) + c]])
+
+
+class SymInfoO:
+    pass
+
+
+def extend_mesh(mesh, doms, sym_name="Symmetry", blch_name="Bloch", unit=False):
+    """annular_meshes.jl:269-546 with 0-based indices.  One deviation: the reference's counter of axis lines (:484-492) yields
+    naxis_ln = 1 for a mesh without axis points (its `naxis_ln==0` guard fires twice), which breaks second-order unit cells; here
+    naxis_ln is the number of leading lines that lie on the axis (0 then).  First-order meshes are not affected."""
+    mesh.collect_lines()
+    npoints = mesh.points.shape[1]
+    bloch = sorted({p for i in mesh.domains[blch_name]["simplices"] for p in mesh.triangles[i]})
+    symmetry = sorted({p for i in mesh.domains[sym_name]["simplices"] for p in mesh.triangles[i]})
+    sset = set(symmetry)
+    axis = [p for p in bloch if p in sset]
+    new_order = list(axis)
+    placed = set(new_order)
+    for p in bloch:
+        if p not in placed:
+            new_order.append(p)
+            placed.add(p)
+    for p in range(npoints):
+        if p not in placed and p not in sset:
+            new_order.append(p)
+            placed.add(p)
+    for p in symmetry:
+        if p not in placed:
+            new_order.append(p)
+            placed.add(p)
+    trace = np.empty(npoints, dtype=np.int64)
+    trace[np.array(new_order)] = np.arange(npoints)
+    t2t = mesh.link_triangles_to_tetrahedra()
+
+    def plane_of(dom):
+        si = mesh.domains[dom]["simplices"][0]
+        tri = mesh.triangles[si]
+        pl = three_points_to_plane(mesh.points[:, tri])
+        test = [p for p in mesh.tetrahedra[t2t[si]] if p not in tri][-1]  # find_testpoint_idx: the last vertex not in the triangle
+        return make_normal_outwards(pl, mesh.points[:, test])
+
+    pln, bpln = plane_of(sym_name), plane_of(blch_name)
+    nbloch, naxis, nsym = len(bloch), len(axis), len(symmetry)
+    nxsym, nxbloch = nsym - naxis, nbloch - naxis
+    nbody = npoints - nbloch - nxsym
+    shiftbody = npoints - nbloch
+    nxsector = nxbloch + nbody + nxsym + nbody
+    nsector = nxsector + naxis
+    pts = np.zeros((3, 2 * npoints - nsym))
+    pts[:, :npoints] = mesh.points[:, new_order]
+    for i in range(nbloch, npoints - nxsym):
+        pts[:, i + shiftbody] = reflect_point_at_plane(pts[:, i], pln)
+    for i in range(naxis, nbloch):
+        pts[:, i + nxsector] = reflect_point_at_plane(pts[:, i], pln)
+    phi = np.arccos(np.dot(pln[:3], -bpln[:3]))
+    DOS = int(round(np.pi / phi))
+    p0, n = find_intersection_of_two_planes(pln, bpln)
+    phi = 2 * np.pi / DOS
+    if unit:
+        fpts, dos_lim = pts, 1
+    else:
+        dos_lim = DOS
+        fpts = np.zeros((3, naxis + nxsector * DOS))
+        fpts[:, :nsector] = pts[:, :nsector]
+        for s in range(1, DOS):
+            R = create_rotation_matrix_around_axis(n, s * phi)
+            fpts[:, naxis + nxsector * s: naxis + nxsector * (s + 1)] = R @ (pts[:, naxis:naxis + nxsector] - p0[:, None]) + p0[:, None]
+
+    def refl(i):  # get_reflected_index
+        if i < naxis:
+            return i
+        if i < naxis + nxbloch:
+            return i + nxsector
+        if i < naxis + nxbloch + nbody:
+            return i + shiftbody
+        if i < naxis + nxbloch + nbody + nxsym:
+            return i
+        raise ValueError("reflected index out of range")
+
+    def rot(i, s):  # get_rotated_index
+        if i < naxis:
+            return i
+        return (i + nxsector * s - naxis) % (nxsector * DOS) + naxis
+
+    def build(simplices, skip=()):
+        out = []
+        for si, smp in enumerate(simplices):
+            if si in skip:
+                continue
+            t = [int(trace[p]) for p in smp]
+            r = [refl(p) for p in t]
+            for s in range(dos_lim):
+                out.append([rot(p, s) for p in t])
+                out.append([rot(p, s) for p in r])
+        return unique_sorted(out)
+
+    tets, tetmap = build(mesh.tetrahedra)
+    skip = set(mesh.domains[sym_name]["simplices"])
+    if not unit:
+        skip |= set(mesh.domains[blch_name]["simplices"])
+    tris, trimap = build(mesh.triangles, skip)
+    lns = []
+    for ln in mesh.lines:
+        t = [int(trace[p]) for p in ln]
+        lns.append(t)
+        if not all(p < nbloch for p in t):
+            lns.append([refl(p) for p in t])
+    lines, _ = unique_sorted(lns)
+    naxis_ln = sum(1 for ln in lines if all(p < naxis for p in ln))
+    nbloch_ln = sum(1 for ln in lines if all(p < nbloch for p in ln))
+    nxbloch_ln = nbloch_ln - naxis_ln
+    nsector_ln = len(lines)
+    nxsector_ln = nsector_ln - naxis_ln
+    if unit:
+        lines = lines + [[rot(p, 1) for p in ln] for ln in lines[naxis_ln:nbloch_ln]]
+    else:
+        first = lines[naxis_ln:nsector_ln]
+        for s in range(1, DOS):
+            lines = lines + [[rot(p, s) for p in ln] for ln in first]
+    domains = {}
+    for dom, deg in doms:
+        dim = mesh.domains[dom]["dimension"]
+        src, mp = (mesh.tetrahedra, tetmap) if dim == 3 else (mesh.triangles, trimap)
+        names = {}
+        for si in mesh.domains[dom]["simplices"]:
+            t = [int(trace[p]) for p in src[si]]
+            r = [refl(p) for p in t]
+            for s in range(dos_lim):
+                i0 = mp[simplex_key([rot(p, s) for p in t])]
+                i1 = mp[simplex_key([rot(p, s) for p in r])]
+                if deg == "full":
+                    names.setdefault(dom, []).extend([i0, i1])
+                elif deg == "unit":
+                    names.setdefault(f"{dom}#{s}", []).extend([i0, i1])
+                elif deg == "half":
+                    names.setdefault(f"{dom}#{s}.0", []).append(i0)
+                    names.setdefault(f"{dom}#{s}.1", []).append(i1)
+                else:
+                    raise ValueError(f"copy_degree {deg!r} not supported")
+        for k, v in names.items():
+            domains[k] = {"dimension": dim, "simplices": v}
+    out = Mesh.__new__(Mesh)
+    out.name = mesh.name
+    out.points, out.lines, out.triangles, out.tetrahedra, out.domains, out.tri2tet = fpts, lines, tris, tets, domains, None
+    d = SymInfoO()
+    d.DOS, d.naxis, d.nxbloch, d.nbody, d.shiftbody, d.nxsymmetry, d.nxsector = DOS, naxis, nxbloch, nbody, shiftbody, nxsym, nxsector
+    d.naxis_ln, d.nxbloch_ln, d.nxsector_ln, d.unit, d.n, d.p = naxis_ln, nxbloch_ln, nxsector_ln, unit, n, p0
+    out.dos = d
+    return out

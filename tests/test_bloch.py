@@ -84,3 +84,101 @@ def test_bloch_terms_and_mslp_sweep_match_oracle(order):
             assert abs(so.params["ω"] - sg.params["ω"]) <= 1e-10 * max(abs(so.params["ω"]), 2 * math.pi * f0), (bb, f0)
     v = W.bloch_expand(m, sg)
     assert len(v) == m.dos.naxis + m.dos.nxsector * DOS
+
+
+# ---- config 4 on the reference's own mesh: docs/src/NTNU_12.msh (half cell) -> extend_mesh -> Bloch-periodic unit cell ----------
+NTNU_DOMS = [("Interior", "full"), ("Inlet", "full"), ("Outlet_high", "full"), ("Outlet_low", "full"), ("Flame", "unit")]
+NTNU_DSCRP = {"Interior": ("interior", ()), "Outlet_high": ("admittance", ("Y_in", 0)), "Outlet_low": ("admittance", ("Y_out", 0))}
+# full-annulus eigenfrequencies of the oracle (extend_mesh(unit=false) + discretize(:lin) + mslp, 22 987 DOFs), generated once with
+# oracle.mesh.extend_mesh / oracle.nlevp.mslp from 1000 Hz and 863.5 Hz; the first one is the plenum-dominant "1124 Hz" mode the
+# reference's tutorial quotes (docs/src/tutorial_07_Bloch_periodicity.md:85)
+NTNU_FULL_HZ = (1123.6102620891118, 863.4776837907286)
+
+
+def _ntnu_sos(x, y, z):
+    return 347.0 if z < 0.415 else 850.0  # tutorial_07_Bloch_periodicity.md:75
+
+
+def _ntnu_meshes():
+    import wae_b200 as W
+    from cases import load_raw_mesh
+    from oracle.mesh import Mesh as OMesh
+    raw = load_raw_mesh("ntnu_12")
+    return W.Mesh("NTNU_12.msh", raw=raw), OMesh("NTNU_12.msh", raw=raw)
+
+
+def test_extend_mesh_matches_oracle_on_ntnu():
+    """Vectorised extend_mesh (product) vs the loop restatement of annular_meshes.jl:269-546 (oracle): identical points, simplex
+    lists, line order, domains and symmetry bookkeeping for the unit cell and the full annulus; DOS = 12 is recognised."""
+    import wae_b200 as W
+    from oracle.mesh import aggregate_elements as oagg
+    from oracle.mesh import extend_mesh as oext
+    mg, mo = _ntnu_meshes()
+    doms = NTNU_DOMS + [("CC", "half")]
+    for unit in (True, False):
+        g, o = W.extend_mesh(mg, doms, unit=unit), oext(mo, doms, unit=unit)
+        assert np.array_equal(g.points, o.points)
+        assert np.array_equal(g.tetrahedra, np.array(o.tetrahedra)) and np.array_equal(g.triangles, np.array(o.triangles))
+        assert np.array_equal(g.lines, np.array(o.lines))
+        assert sorted(g.domains) == sorted(o.domains)
+        for k, v in o.domains.items():
+            assert list(map(int, g.domains[k]["simplices"])) == list(v["simplices"]), k
+        d, e = g.sym_info, o.dos
+        assert (d.DOS, d.naxis, d.nxbloch, d.nxsector, d.naxis_ln, d.nxbloch_ln, d.nxsector_ln) == \
+               (e.DOS, e.naxis, e.nxbloch, e.nxsector, e.naxis_ln, e.nxbloch_ln, e.nxsector_ln)
+        assert d.DOS == 12
+        if unit:
+            tr, te, dim = W.aggregate_elements(g, "quad")
+            otr, ote, odim = oagg(o, "quad")
+            assert dim == odim and np.array_equal(te, np.array(ote)) and np.array_equal(tr, np.array(otr))
+        X = g.points[:, g.tetrahedra]
+        vol = np.abs(np.linalg.det(np.moveaxis(X[:, :, :3] - X[:, :, 3:4], 1, 0))).sum() / 6
+        X0 = mg.points[:, mg.tetrahedra]
+        vol0 = np.abs(np.linalg.det(np.moveaxis(X0[:, :, :3] - X0[:, :, 3:4], 1, 0))).sum() / 6
+        assert abs(vol / vol0 - (2 if unit else 24)) < 1e-9
+
+
+def test_oracle_ntnu_unit_cell_reproduces_full_annulus_modes():
+    """Bloch-periodic unit cell (b = 1) of NTNU_12 in the oracle: the ~1124 Hz mode of the tutorial and the 863 Hz mode equal the
+    full-annulus eigenfrequencies (pinned above) to round-off -- "the eigenfrequency is exactly the same" (tutorial_07:138-139)."""
+    from oracle.helmholtz import discretize
+    from oracle.mesh import extend_mesh as oext
+    from oracle.nlevp import mslp
+    _, mo = _ntnu_meshes()
+    u = oext(mo, NTNU_DOMS, unit=True)
+    l = discretize(u, NTNU_DSCRP, u.generate_field(_ntnu_sos), order="lin", b="b")
+    l.params["b"] = 1 + 0j
+    for f0, ref in zip((1100.0, 900.0), NTNU_FULL_HZ):
+        sol, n, flag = mslp(l, f0, tol=1e-9, scale=2 * math.pi, maxiter=15)
+        assert flag == 0 and abs(sol.params["ω"] / 2 / math.pi - ref) < 1e-8 * ref
+    assert abs(NTNU_FULL_HZ[0] - 1124) < 1.0
+
+
+@pytest.mark.gpu
+def test_ntnu_config4_unit_cell_and_full_annulus_on_the_gpu():
+    """Config 4: NTNU_12 -> extend_mesh -> discretize(b) -> mslp sweep over shifts and Bloch numbers on the GPU vs the oracle, and the
+    full annulus (22 987 DOFs) on the GPU: unit-cell omega == full-mesh omega, the 1124 Hz mode is found for b = 1."""
+    import wae_b200 as W
+    from oracle.helmholtz import discretize as odisc
+    from oracle.mesh import extend_mesh as oext
+    from oracle.nlevp import mslp as omslp
+    mg, mo = _ntnu_meshes()
+    ug, uo = W.extend_mesh(mg, NTNU_DOMS, unit=True), oext(mo, NTNU_DOMS, unit=True)
+    lg = W.discretize(ug, NTNU_DSCRP, ug.generate_field(_ntnu_sos), b="b")
+    lo = odisc(uo, NTNU_DSCRP, uo.generate_field(_ntnu_sos), order="lin", b="b")
+    assert [t.operator for t in lg.terms] == [t.operator for t in lo.terms]
+    found = {}
+    for bb in (0, 1, 2):
+        lg.params["b"] = lo.params["b"] = complex(bb)
+        for f0 in (500.0, 750.0, 1100.0, 1250.0, 1500.0):
+            sg, ng, fg = W.mslp(lg, f0, maxiter=20, tol=1e-9, scale=2 * math.pi, output=False)
+            so, no, fo = omslp(lo, f0, maxiter=20, tol=1e-9, scale=2 * math.pi)
+            assert fg == fo == 0
+            assert abs(sg.params["ω"] - so.params["ω"]) <= 1e-10 * abs(so.params["ω"]), (bb, f0)
+            found[(bb, f0)] = sg.params["ω"].real / 2 / math.pi
+    assert abs(found[(1, 1100.0)] - NTNU_FULL_HZ[0]) < 1e-8 * NTNU_FULL_HZ[0]
+    fg_ = W.extend_mesh(mg, NTNU_DOMS, unit=False)
+    Lf = W.discretize(fg_, NTNU_DSCRP, fg_.generate_field(_ntnu_sos))
+    for f0, ref in zip((1000.0, 863.5), NTNU_FULL_HZ):
+        sol, n, flag = W.mslp(Lf, f0, maxiter=15, tol=1e-9, scale=2 * math.pi, output=False)
+        assert flag == 0 and abs(sol.params["ω"].real / 2 / math.pi - ref) < 1e-9 * ref

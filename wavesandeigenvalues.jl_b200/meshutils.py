@@ -378,3 +378,172 @@ def kuhn_unit_cell(ncube, lo, hi, DOS, jitter=0.0, seed=0, name="kuhn_unit_cell"
     mesh.reorder_lines(new_of_old_ln)
     mesh.dos = SymInfo(DOS, 0, nxb, nxsector, 0, len(lb), len(lines) - len(lb))
     return mesh
+
+
+# ---------------------------------------------------------------------------------------------
+# extend_mesh: half-cell -> unit cell / full annulus (src/Mesh/annular_meshes.jl:269-546), vectorised
+# ---------------------------------------------------------------------------------------------
+def _plane(A):
+    """three_points_to_plane (annular_meshes.jl:14-26), including its d < 1e-7 -> 0 rule."""
+    n = np.cross(A[:, 0] - A[:, 2], A[:, 1] - A[:, 2])
+    n = n / np.linalg.norm(n)
+    d = -float(n @ A[:, 2])
+    return np.array([n[0], n[1], n[2], 0.0 if d < 1e-7 else d])
+
+
+def _reflect(P, pln):
+    """reflect_point_at_plane (:46-52) for the columns of P."""
+    k = -(pln[:3] @ P) - pln[3]
+    return P + 2 * np.outer(pln[:3], k)
+
+
+def _find_rows(table_sorted_keys, order, keys):
+    pos = np.searchsorted(table_sorted_keys, keys)
+    assert np.all(table_sorted_keys[np.minimum(pos, len(table_sorted_keys) - 1)] == keys), "simplex not found"
+    return order[pos]
+
+
+def _desc_key(simp, npts):
+    k = -np.sort(-np.asarray(simp, dtype=np.int64), axis=1)
+    key = k[:, 0]
+    for c in range(1, k.shape[1]):
+        key = key * npts + k[:, c]
+    return key
+
+
+def extend_mesh(mesh, doms, sym_name="Symmetry", blch_name="Bloch", unit=False):
+    """Mirror a half-cell mesh at its symmetry plane (unit=True: one unit cell with the Bloch image plane) and rotate the unit cell
+    DOS times around the axis (unit=False: full annulus).  Same point, simplex and domain numbering as the reference
+    (annular_meshes.jl:269-546): points [axis | Bloch plane | body | symmetry plane | mirrored body | (image plane)], simplices sorted
+    and uniquified by the reference's rule, lines of the first cell sorted and the image / rotated lines appended.  `doms` is a list
+    of (domain, "full" | "unit" | "half").  naxis_ln counts the leading lines on the axis (the reference's counter returns 1 instead
+    of 0 for meshes without axis points, which only matters for second-order unit cells and breaks them there)."""
+    mesh.collect_lines()
+    npts = mesh.points.shape[1]
+    tri, tet = mesh.triangles, mesh.tetrahedra
+    on_b = np.zeros(npts, dtype=bool)
+    on_s = np.zeros(npts, dtype=bool)
+    on_b[tri[np.asarray(mesh.domains[blch_name]["simplices"], dtype=np.int64)].ravel()] = True
+    on_s[tri[np.asarray(mesh.domains[sym_name]["simplices"], dtype=np.int64)].ravel()] = True
+    axis = np.flatnonzero(on_b & on_s)
+    new_order = np.concatenate([axis, np.flatnonzero(on_b & ~on_s), np.flatnonzero(~on_b & ~on_s), np.flatnonzero(on_s & ~on_b)])
+    trace = np.empty(npts, dtype=np.int64)
+    trace[new_order] = np.arange(npts)
+    t2t = mesh.link_triangles_to_tetrahedra() if mesh.tri2tet is None else mesh.tri2tet
+
+    def plane_of(dom):
+        si = int(mesh.domains[dom]["simplices"][0])
+        t = tri[si]
+        pl = _plane(mesh.points[:, t])
+        test = [p for p in tet[t2t[si]] if p not in t][-1]  # find_testpoint_idx (:124-132)
+        x = mesh.points[:, test]
+        foot = x + pl[:3] * (-(pl[:3] @ x) - pl[3])
+        return pl * (-np.sign(pl[:3] @ (x - foot)))  # make_normal_outwards (:74-79)
+
+    pln, bpln = plane_of(sym_name), plane_of(blch_name)
+    naxis, nbloch, nsym = len(axis), int(on_b.sum()), int(on_s.sum())
+    nxsym, nxbloch = nsym - naxis, nbloch - naxis
+    nbody = npts - nbloch - nxsym
+    shiftbody = npts - nbloch
+    nxsector = nxbloch + 2 * nbody + nxsym
+    nsector = nxsector + naxis
+    pts = np.zeros((3, 2 * npts - nsym))
+    pts[:, :npts] = mesh.points[:, new_order]
+    pts[:, nbloch + shiftbody: npts - nxsym + shiftbody] = _reflect(pts[:, nbloch: npts - nxsym], pln)
+    pts[:, naxis + nxsector: nbloch + nxsector] = _reflect(pts[:, naxis:nbloch], pln)
+    DOS = int(round(np.pi / np.arccos(pln[:3] @ -bpln[:3])))
+    n = np.cross(pln[:3], bpln[:3])
+    n = n / np.linalg.norm(n)
+    # find_intersection_of_two_planes (:92-109): p = rhs \ M, least squares with the 5-vector rhs on the left
+    f1, f2 = pln[:3] * (-pln[3]), bpln[:3] * (-bpln[3])
+    M = np.array([[2.0, 0, 0, pln[0], bpln[0]], [2.0, 0, 0, pln[1], bpln[1]], [2.0, 0, 0, pln[2], bpln[2]],
+                  [pln[0], pln[1], pln[2], 0, 0], [bpln[0], bpln[1], bpln[2], 0, 0]])
+    rhs = np.array([0, 0, 0, f1 @ pln[:3], f2 @ bpln[:3]], dtype=float)
+    p0 = np.linalg.lstsq(rhs.reshape(5, 1), M, rcond=None)[0].ravel()[:3]
+    phi = 2 * np.pi / DOS
+    if unit:
+        fpts, dos_lim = pts, 1
+    else:
+        dos_lim = DOS
+        fpts = np.zeros((3, naxis + nxsector * DOS))
+        fpts[:, :nsector] = pts[:, :nsector]
+        for s in range(1, DOS):
+            c, sn = np.cos(s * phi), np.sin(s * phi)
+            K = np.array([[0, -n[2], n[1]], [n[2], 0, -n[0]], [-n[1], n[0], 0]])
+            R = c * np.eye(3) + sn * K + (1 - c) * np.outer(n, n)  # create_rotation_matrix_around_axis (:116-121)
+            fpts[:, naxis + nxsector * s: naxis + nxsector * (s + 1)] = R @ (pts[:, naxis:nsector] - p0[:, None]) + p0[:, None]
+
+    def refl(i):  # get_reflected_index (:168-181)
+        i = np.asarray(i, dtype=np.int64)
+        assert np.all(i < naxis + nxbloch + nbody + nxsym)
+        return np.where(i < naxis, i, np.where(i < nbloch, i + nxsector, np.where(i < nbloch + nbody, i + shiftbody, i)))
+
+    def rot(i, s):  # get_rotated_index (:142-154)
+        i = np.asarray(i, dtype=np.int64)
+        return np.where(i < naxis, i, (i + nxsector * s - naxis) % (nxsector * DOS) + naxis)
+
+    def build(simp, keep):
+        t = trace[simp[keep]]
+        r = refl(t)
+        parts = []
+        for s in range(dos_lim):  # insertion order of the reference: per simplex (direct, mirrored) per sector
+            parts.append(np.stack([rot(t, s), rot(r, s)], axis=1))
+        allp = np.stack(parts, axis=1).reshape(-1, simp.shape[1])
+        return _sorted_unique(allp)[0]
+
+    nfp = fpts.shape[1]
+    tets = build(tet, np.ones(len(tet), dtype=bool))
+    keep = np.ones(len(tri), dtype=bool)
+    keep[np.asarray(mesh.domains[sym_name]["simplices"], dtype=np.int64)] = False
+    if not unit:
+        keep[np.asarray(mesh.domains[blch_name]["simplices"], dtype=np.int64)] = False
+    tris = build(tri, keep)
+    ln = trace[mesh.lines]
+    not_bloch = ~np.all(ln < nbloch, axis=1)
+    lines = _sorted_unique(np.concatenate([ln, refl(ln[not_bloch])]))[0]
+    naxis_ln = int(np.all(lines < naxis, axis=1).sum())
+    nbloch_ln = int(np.all(lines < nbloch, axis=1).sum())
+    nsector_ln = len(lines)
+    if unit:
+        lines = np.concatenate([lines, rot(lines[naxis_ln:nbloch_ln], 1)])
+    else:
+        first = lines[naxis_ln:nsector_ln]
+        lines = np.concatenate([lines] + [rot(first, s) for s in range(1, DOS)])
+    domains = {}
+    for dom, deg in doms:
+        dim = mesh.domains[dom]["dimension"]
+        src, full = (tet, tets) if dim == 3 else (tri, tris)
+        fkey = _desc_key(full, nfp)
+        fo = np.argsort(fkey, kind="stable")
+        fk = fkey[fo]
+        t = trace[src[np.asarray(mesh.domains[dom]["simplices"], dtype=np.int64)]]
+        r = refl(t)
+        for s in range(dos_lim):
+            i0 = _find_rows(fk, fo, _desc_key(rot(t, s), nfp))
+            i1 = _find_rows(fk, fo, _desc_key(rot(r, s), nfp))
+            if deg == "full":
+                domains.setdefault(dom, []).append(np.stack([i0, i1], axis=1))
+            elif deg == "unit":
+                domains[f"{dom}#{s}"] = [np.stack([i0, i1], axis=1).ravel()]
+            elif deg == "half":
+                domains[f"{dom}#{s}.0"], domains[f"{dom}#{s}.1"] = [i0], [i1]
+            else:
+                raise ValueError(f"copy_degree {deg!r} not supported; use 'full', 'unit' or 'half'")
+        if deg == "full":  # reference order: per simplex, per sector, (direct, mirrored)
+            domains[dom] = [np.stack(domains[dom], axis=1).reshape(-1)]
+        for k in [k for k in domains if k == dom or k.startswith(dom + "#")]:
+            domains[k] = {"dimension": dim, "simplices": np.concatenate(domains[k]).astype(np.int64)} if isinstance(domains[k], list) else domains[k]
+    out = Mesh.__new__(Mesh)
+    out.name = out.file = mesh.file
+    out.points, out.triangles, out.tetrahedra, out.domains = fpts, tris, tets, domains
+    out.tri2tet, out._edge_of = None, None
+    out.lines = lines
+    a, b = tets[:, [0, 0, 0, 1, 1, 2]], tets[:, [1, 2, 3, 2, 3, 3]]
+    lkey = _desc_key(lines, nfp)
+    lo = np.argsort(lkey, kind="stable")
+    out._edge_of = _find_rows(lkey[lo], lo, _desc_key(np.stack([a.ravel(), b.ravel()], axis=1), nfp)).reshape(-1, 6)
+    d = SymInfo(DOS, naxis, nxbloch, nxsector, naxis_ln, nbloch_ln - naxis_ln, nsector_ln - naxis_ln, unit=unit)
+    d.nbody, d.shiftbody, d.nxsymmetry, d.n, d.p = nbody, shiftbody, nxsym, n, p0
+    out.dos = d if unit else 1
+    out.sym_info = d
+    return out
