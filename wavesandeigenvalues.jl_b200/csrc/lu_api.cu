@@ -213,6 +213,22 @@ __global__ void scale_copy_kernel(const cplx* __restrict__ in, int64_t n, double
   if (p < n) out[p] = make_double2(in[p].x * s, in[p].y * s);
 }
 // X[:, c] = e_c for c < l
+// start vector of the Arnoldi process: v += amp * r_i with a deterministic pseudo-random r_i in (-1, 1) (splitmix-style hash of i).
+// ARPACK recovers eigenvectors the start vector is exactly orthogonal to (v0 = ones against an antisymmetric mode) from round-off
+// during its >= ncv steps; this process stops as soon as the wanted Ritz pairs have converged, so the missing components are
+// seeded explicitly instead.
+__global__ void perturb_start_kernel(cplx* __restrict__ v, int64_t n, double amp) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t z = (uint64_t)i + 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const double a = (double)(z >> 11) * (1.0 / 9007199254740992.0), b = (double)((z * 0x9E3779B97F4A7C15ull) >> 11) * (1.0 / 9007199254740992.0);
+  v[i].x += amp * (2.0 * a - 1.0);
+  v[i].y += amp * (2.0 * b - 1.0);
+}
+
 __global__ void identity_cols_kernel(int64_t n, int l, cplx* __restrict__ X) {
   int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= n * l) return;
@@ -488,6 +504,10 @@ int32_t wae_eigs_si(wae_ctx* h, int32_t lu_id, int32_t fam_id, int32_t m_slot, i
   dots(W.w.p, 1, W.w.p, hcol);
   double nrm = std::sqrt(hcol[0].real());
   if (!(nrm > 0.0) || !std::isfinite(nrm)) WAE_THROW(WAE_E_INVALID, "start vector is zero or not finite");
+  perturb_start_kernel<<<gb, 256, 0, st>>>(W.w.p, n, 1e-6 * nrm / std::sqrt((double)n));
+  h->launches++;
+  dots(W.w.p, 1, W.w.p, hcol);
+  nrm = std::sqrt(hcol[0].real());
   scale_copy_kernel<<<gb, 256, 0, st>>>(W.w.p, n, 1.0 / nrm, W.V.p);
   const double tol = 1e-13;
   const int max_restart = 15;
