@@ -12,7 +12,8 @@ import scipy.sparse as sp
 
 from . import fem
 from .mesh import aggregate_elements
-from .nlevp import LinearOperatorFamily, Term, exp_delay, pow1, pow2
+from .nlevp import (LinearOperatorFamily, Term, exp_az2mzit, exp_delay, generate_stsp_z, generate_z_g_z, pow1, pow2,
+                    sigma_nexp_az2mzit)
 
 
 def _sparse(I, J, V, dim):
@@ -115,9 +116,30 @@ def discretize(mesh, dscrp, C, order="lin", mass_weighting=True, triplets=None, 
             make = ["M"]
         elif typ == "admittance":
             make = ["C"]
-            adm_sym, adm_val = data
-            L.params.setdefault(adm_sym, complex(adm_val))
-            bfunc, barg, btxt = (pow1, pow1), (("ω",), (adm_sym,)), "ω*" + adm_sym
+            if len(data) == 2:  # Helmholtz.jl:262-273
+                adm_sym, adm_val = data
+                L.params.setdefault(adm_sym, complex(adm_val))
+                bfunc, barg, btxt = (pow1, pow1), (("ω",), (adm_sym,)), "ω*" + adm_sym
+            elif len(data) == 1:  # :274-278
+                bfunc, barg, btxt = (generate_z_g_z(data[0]),), (("ω",),), "ω*Y(ω)"
+            else:  # :279-285 state space
+                bfunc, barg, btxt = (generate_z_g_z(generate_stsp_z(*data)),), (("ω",),), "ω*C_s(iωI-A)^{-1}B"
+        elif typ == "fancyflame":  # Helmholtz.jl:363-400
+            make = ["Q"]
+            gamma, rho, nglobal, x_ref, n_ref, n_sym, tau_sym, a_sym, n_val, tau_val, a_val = data
+            nlocal = (gamma - 1) / rho * nglobal / mesh.compute_size(domain)
+            if isinstance(n_val, (int, float, complex)):
+                for sym_, val_ in ((n_sym, n_val), (tau_sym, tau_val), (a_sym, a_val)):
+                    L.params.setdefault(sym_, complex(val_))
+                ffunc, farg, ftxt = (pow1, exp_az2mzit), ((n_sym,), ("ω", tau_sym, a_sym)), f"{n_sym}* exp({a_sym}ω^2-iω{tau_sym})"
+            else:
+                arg, ftxt = ["ω"], ""
+                for ns, ts, as_, nv, tv, av in zip(n_sym, tau_sym, a_sym, n_val, tau_val, a_val):
+                    L.params[ns], L.params[ts], L.params[as_] = complex(nv), complex(tv), complex(av)
+                    arg += [ns, ts, as_]
+                    ftxt += f"[{ns}* exp({as_}ω^2-iω{ts})+"
+                ffunc, farg, ftxt = (sigma_nexp_az2mzit,), (tuple(arg),), ftxt[:-1] + "]"
+            ref_idx = mesh.find_tetrahedron_containing_point(x_ref)
         elif typ in ("flame", "flameresponse"):
             make = ["Q"]
             if typ == "flame" and len(data) == 9:

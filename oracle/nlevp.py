@@ -74,6 +74,63 @@ def exp_az(z, a, k):
 # ----------------------------------------------------------------------------- family
 
 
+def generate_z_g_z(g):  # algebra.jl:169-179
+    def z_g_z(z, n):
+        return z * g(z, 0) if n == 0 else z * g(z, n) + n * g(z, n - 1)
+    return z_g_z
+
+
+def generate_stsp_z(A, B, C, D):  # algebra.jl:158-167
+    A = np.atleast_2d(np.asarray(A, dtype=complex))
+    B = np.asarray(B, dtype=complex).reshape(A.shape[0], 1)
+    C = np.asarray(C, dtype=complex).reshape(1, A.shape[0])
+    D = complex(np.asarray(D).ravel()[0])
+
+    def stsp_z(z, n):
+        inv = np.linalg.inv(1j * z * np.eye(A.shape[0]) - A)
+        P = np.eye(A.shape[0], dtype=complex)
+        for _ in range(n + 1):
+            P = P @ inv
+        f = (-1j) ** n * math.factorial(n) * (C @ P @ B)[0, 0]
+        return f + D if n == 0 else f
+    return stsp_z
+
+
+def exp_ax2(z, a, n):  # algebra.jl:229-253, with the running A /= a, Z /= z^2 of the reference
+    if a == 0:
+        return complex(1) if n == 0 else complex(0)
+    f = 0j
+    A, Z = np.complex128(a) ** n, np.complex128(z) ** n
+    cnst = 2**n * math.factorial(n)
+    with np.errstate(all="ignore"):  # IEEE semantics as in Julia: at z = 0 the running quotient becomes Inf/NaN instead of raising
+        for k in range(n // 2 + 1):
+            f += cnst * 4.0 ** (-k) / math.factorial(k) / math.factorial(n - 2 * k) * A * Z
+            A = A / np.complex128(a)
+            Z = Z / np.complex128(z) ** 2
+    return complex(f * np.exp(a * z**2))
+
+
+def exp_az2mzit(z, tau, a, m, n, k):  # algebra.jl:255-274
+    coeff = 0j
+    for ii in range(m + 1):
+        for jj in range(m - ii + 1):
+            kk = m - jj - ii
+            multi = math.factorial(m) / math.factorial(ii) / math.factorial(jj) / math.factorial(kk)
+            coeff += multi * _pow(z, kk, n + 2 * k) * exp_ax2(z, a, jj) * exp_delay(z, tau, ii, 0)
+    return coeff * (-1j) ** n
+
+
+def sigma_nexp_az2mzit(*args):  # algebra.jl:313-325 (0-based: z, then J triples (n, tau, a), then m, then J triples (l, n, k))
+    J = (len(args) - 2) // 6
+    z, m = args[0], args[3 * J + 1]
+    f = 0j
+    for j in range(J):
+        nn, tau, a = args[1 + 3 * j], args[2 + 3 * j], args[3 + 3 * j]
+        l, n, k = args[3 * J + 2 + 3 * j], args[3 * J + 3 + 3 * j], args[3 * J + 4 + 3 * j]
+        f += pow1(nn, l) * exp_az2mzit(z, tau, a, m, n, k)
+    return f
+
+
 class Term:
     def __init__(self, coeff, func, params, symbol, operator):
         self.coeff, self.func, self.params, self.symbol, self.operator = coeff, tuple(func), tuple(params), symbol, operator

@@ -217,3 +217,37 @@ def test_kuhn_box_is_conforming():
     assert len(m.triangles) == 2 * 2 * (3 * 2 + 3 * 4 + 2 * 4)
     assert len(m.domains["Flame"]["simplices"]) == 3 * 2 * 6
     assert abs(m.compute_size("Outlet") - 6.0) < 1e-12
+
+
+def _num_deriv(f, x, order, h):
+    """central finite-difference derivative of the given order (complex step sizes are fine: f is analytic)."""
+    if order == 0:
+        return f(x)
+    return (_num_deriv(f, x + h, order - 1, h) - _num_deriv(f, x - h, order - 1, h)) / (2 * h)
+
+
+def test_fancyflame_and_state_space_scalars():
+    """exp_az2mzit (algebra.jl:255-274), Σnexp_az2mzit (:313-325), exp_ax2 (:229-253) and generate_stsp_z (:158-167): the product's
+    functions agree with the oracle's restatement and with finite differences of the closed form exp(a z^2 - i z tau)."""
+    z, tau, a = 900.0 + 40.0j, 1.3e-3 + 0j, -2.0e-7 + 0j
+    F = lambda z_, t_, a_: np.exp(a_ * z_ * z_ - 1j * z_ * t_)
+    for m, n, k in ((0, 0, 0), (1, 0, 0), (2, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 0), (1, 0, 1), (2, 1, 1), (3, 2, 0)):
+        g = nlevp.exp_az2mzit(z, tau, a, m, n, k)
+        o = onlevp.exp_az2mzit(z, tau, a, m, n, k)
+        assert abs(g - o) <= 1e-12 * abs(o)
+        # d^n/dtau^n d^k/da^k of the closed form is (-i z)^n z^(2k) F; the m z-derivatives by central differences
+        fd = _num_deriv(lambda zz: (-1j * zz) ** n * zz ** (2 * k) * F(zz, tau, a), z, m, 0.5)
+        assert abs(g - fd) <= 2e-5 * abs(fd) + 1e-30, (m, n, k)
+    for nn in range(5):
+        assert abs(nlevp.exp_ax2(z, a, nn) - onlevp.exp_ax2(z, a, nn)) <= 1e-12 * abs(onlevp.exp_ax2(z, a, nn))
+    args = (z, 1.5 + 0j, tau, a, 0.5 + 0j, 2 * tau, 3 * a, 1, 0, 0, 0, 0, 0, 0)
+    s = nlevp.Sigma_nexp_az2mzit(*args)
+    assert abs(s - onlevp.sigma_nexp_az2mzit(*args)) <= 1e-12 * abs(s)
+    assert abs(s - (1.5 * nlevp.exp_az2mzit(z, tau, a, 1, 0, 0) + 0.5 * nlevp.exp_az2mzit(z, 2 * tau, 3 * a, 1, 0, 0))) <= 1e-12 * abs(s)
+    A, B, Cm, D = np.array([[-50.0, 20.0], [-20.0, -80.0]]), np.array([1.0, 0.5]), np.array([2.0, -1.0]), np.array([0.3])
+    fg, fo = nlevp.generate_stsp_z(A, B, Cm, D), onlevp.generate_stsp_z(A, B, Cm, D)
+    H = lambda w: (Cm @ np.linalg.solve(1j * w * np.eye(2) - A, B)) + 0.3
+    for n in range(4):
+        assert abs(fg(z, n) - fo(z, n)) <= 1e-12 * abs(fo(z, n))
+        if n <= 2:  # (finite differences of higher order drown in round-off: the values are ~1e-11)
+            assert abs(fg(z, n) - _num_deriv(H, z, n, 2.0)) <= 1e-4 * abs(fg(z, n)) + 1e-30

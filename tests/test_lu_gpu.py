@@ -157,3 +157,35 @@ def test_beyn_gpu_vs_oracle():
     for om in Og:
         sol, n, flag = W.householder(Lg, om, maxiter=10, tol=1e-10, output=False)
         assert abs(sol.params["ω"] - om) < 5e-2 * abs(om)
+
+
+def test_fancyflame_and_state_space_admittance_match_oracle():
+    """Descriptor variants of Helmholtz.discretize (Helmholtz.jl:279-285, 363-400): Gaussian-filtered n-tau flame (:fancyflame, scalar
+    and summed form) and state-space outlet admittance -- the flame term is not a rank-1 update of a symmetric family only through
+    its scalar, the admittance scalar is a rational function; householder must agree with the oracle to 1e-10."""
+    import wae_b200 as W
+    from cases import GAMMA, N_REF, Q02U0, RHO, X_REF
+    from oracle.helmholtz import discretize as odisc
+    from oracle.mesh import Mesh as OMesh
+    from oracle.nlevp import householder as ohouse
+    raw = load_raw_mesh("rijke_mm")
+    mg, mo = W.Mesh("Rijke_mm.msh", scale=0.001, raw=raw), OMesh("Rijke_mm.msh", scale=0.001, raw=raw)
+    A, B, Cm, D = np.array([[-2.0e3, 0.0], [0.0, -5.0e3]]), np.array([1.0, 1.0]), np.array([4.0e3, -1.0e3]), np.array([0.5])
+    cases = {
+        "scalar": {"Interior": ("interior", ()), "Outlet": ("admittance", (A, B, Cm, D)),
+                   "Flame": ("fancyflame", (GAMMA, RHO, Q02U0, X_REF, N_REF, "n", "τ", "a", 1.0, 0.001, -1e-8))},
+        "summed": {"Interior": ("interior", ()), "Outlet": ("admittance", ("Y", 1e15)),
+                   "Flame": ("fancyflame", (GAMMA, RHO, Q02U0, X_REF, N_REF, ("n1", "n2"), ("τ1", "τ2"), ("a1", "a2"),
+                                            (0.6, 0.4), (0.001, 0.0013), (-1e-8, -2e-8)))},
+    }
+    for name, dscrp in cases.items():
+        Lg = W.discretize(mg, dscrp, mg.generate_field(speedofsound))
+        Lo = odisc(mo, dscrp, mo.generate_field(speedofsound))
+        assert [t.operator for t in Lg.terms] == [t.operator for t in Lo.terms]
+        z = 1000.0 + 200.0j
+        assert abs(Lg(z).to_scipy() - Lo(z)).max() <= 1e-11 * abs(Lo(z)).max(), name
+        assert abs(Lg(z, 1).to_scipy() - Lo(z, 1)).max() <= 1e-11 * abs(Lo(z, 1)).max(), name
+        sg, ng, fg = W.householder(Lg, 340 * 2 * math.pi, maxiter=25, tol=1e-11, output=False)
+        so, no, fo = ohouse(Lo, 340 * 2 * math.pi, maxiter=25, tol=1e-11)
+        assert fg == fo and fg >= 0
+        assert abs(sg.params["ω"] - so.params["ω"]) <= TOL * abs(so.params["ω"]), (name, sg.params["ω"], so.params["ω"])

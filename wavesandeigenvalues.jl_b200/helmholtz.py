@@ -24,7 +24,8 @@ import numpy as np
 
 from . import _lib
 from .meshutils import aggregate_elements
-from .nlevp import DeviceMatrix, LinearOperatorFamily, Term, exp_delay, generate_z_g_z, get_context, pow1, pow2
+from .nlevp import (DeviceMatrix, LinearOperatorFamily, Sigma_nexp_az2mzit, Term, exp_az2mzit, exp_delay, generate_stsp_z, generate_z_g_z,
+                    get_context, pow1, pow2)
 
 
 def _split_c(mesh, C, npts):
@@ -198,14 +199,16 @@ def discretize(mesh, dscrp, C, order="lin", b="__none__", mass_weighting=True, s
                 bfunc, barg, btxt = (pow1, pow1), (("ω",), (adm_sym,)), "ω*" + adm_sym
             elif len(data) == 1:
                 bfunc, barg, btxt = (generate_z_g_z(data[0]),), (("ω",),), "ω*Y(ω)"
+            elif len(data) == 4:  # Helmholtz.jl:279-285: state-space admittance C_s (i omega I - A)^-1 B + D
+                bfunc, barg, btxt = (generate_z_g_z(generate_stsp_z(*data)),), (("ω",),), "ω*C_s(iωI-A)^{-1}B"
             else:
-                raise NotImplementedError("state-space admittance (A,B,C,D) is not on the accelerated path")
+                raise ValueError("Data length does not match :admittance option!")
             pid = ctx.pattern_build(2, simplices)[0]
             disc.patterns[(2, domain)] = pid
             mid = ctx.assemble(pid, _lib.OP_BOUNDARY, C_tri[simplices])
             disc.ops.append({"op": "boundary", "pid": pid, "simplices": simplices, "mat": mid})
             L.push(Term(dm(mid), bfunc, barg, btxt, "C"))
-        elif typ in ("flame", "flameresponse"):
+        elif typ in ("flame", "flameresponse", "fancyflame"):
             ref_idx = -1
             if typ == "flame" and len(data) == 9:
                 gamma, rho, nglobal, x_ref, n_ref, n_sym, tau_sym, n_val, tau_val = data
@@ -222,6 +225,9 @@ def discretize(mesh, dscrp, C, order="lin", b="__none__", mass_weighting=True, s
             elif typ == "flameresponse":
                 gamma, rho, nglobal, x_ref, n_ref, eps_sym, eps_val = data
                 kind = "eps"
+            elif typ == "fancyflame":  # Helmholtz.jl:363-400
+                gamma, rho, nglobal, x_ref, n_ref, n_sym, tau_sym, a_sym, n_val, tau_val, a_val = data
+                kind = "fancy"
             else:
                 raise ValueError("Data length does not match :flame option!")
             nlocal = (gamma - 1) / rho * nglobal / mesh.compute_size(domain)
@@ -231,6 +237,19 @@ def discretize(mesh, dscrp, C, order="lin", b="__none__", mass_weighting=True, s
                 ffunc, farg, ftxt = (pow1, exp_delay), ((n_sym,), ("ω", tau_sym)), f"{n_sym}*exp(-iω{tau_sym})"
             elif kind == "ftf":
                 ffunc, farg, ftxt = (FTF,), (("ω",),), "FTF(ω)"
+            elif kind == "fancy":
+                if isinstance(n_val, (int, float, complex)):
+                    for sym_, val_ in ((n_sym, n_val), (tau_sym, tau_val), (a_sym, a_val)):
+                        L.params.setdefault(sym_, complex(val_))
+                    ffunc, farg = (pow1, exp_az2mzit), ((n_sym,), ("ω", tau_sym, a_sym))
+                    ftxt = f"{n_sym}* exp({a_sym}ω^2-iω{tau_sym})"
+                else:
+                    arg, ftxt = ["ω"], ""
+                    for ns, ts, as_, nv, tv, av in zip(n_sym, tau_sym, a_sym, n_val, tau_val, a_val):
+                        L.params[ns], L.params[ts], L.params[as_] = complex(nv), complex(tv), complex(av)
+                        arg += [ns, ts, as_]
+                        ftxt += f"[{ns}* exp({as_}ω^2-iω{ts})+"
+                    ffunc, farg, ftxt = (Sigma_nexp_az2mzit,), (tuple(arg),), ftxt[:-1] + "]"
             elif kind == "plain":
                 L.params["FTF"] = 0.0
                 ffunc, farg, ftxt = (pow1,), (("FTF",),), "FTF"

@@ -93,6 +93,52 @@ def generate_z_g_z(g):
     return z_g_z
 
 
+def generate_stsp_z(A, B, C, D):
+    """algebra.jl:158-167: n-th derivative of the state-space transfer function C (i z I - A)^-1 B + D."""
+    A, B, C = np.atleast_2d(np.asarray(A, dtype=complex)), np.asarray(B, dtype=complex).reshape(-1, 1), np.asarray(C, dtype=complex).reshape(1, -1)
+
+    def stsp_z(z, n):
+        R = np.linalg.matrix_power(np.linalg.inv(1j * z * np.eye(A.shape[0]) - A), n + 1)
+        f = (-1j) ** n * math.factorial(n) * (C @ R @ B)[0, 0]
+        return f + (np.asarray(D, dtype=complex).ravel()[0] if n == 0 else 0)
+    return stsp_z
+
+
+def exp_ax2(z, a, n):
+    """algebra.jl:229-253: n-th derivative of exp(a z^2) with respect to z."""
+    if a == 0:
+        return complex(1) if n == 0 else complex(0)
+    f = 0j
+    for k in range(n // 2 + 1):
+        f += 2**n * math.factorial(n) * 4.0 ** (-k) / math.factorial(k) / math.factorial(n - 2 * k) * complex(a) ** (n - k) * complex(z) ** (n - 2 * k)
+    return f * np.exp(a * z * z)
+
+
+def exp_az2mzit(z, tau, a, m, n, k):
+    """algebra.jl:255-274: d^m/dz^m d^n/dtau^n d^k/da^k exp(a z^2 - i z tau) (Gaussian-filtered time delay of :fancyflame)."""
+    f = pow_a(n + 2 * k)
+    coeff = 0j
+    for ii in range(m + 1):
+        h_ii = exp_delay(z, tau, ii, 0)
+        for jj in range(m - ii + 1):
+            kk = m - jj - ii
+            multi = math.factorial(m) / math.factorial(ii) / math.factorial(jj) / math.factorial(kk)
+            coeff += multi * f(z, kk) * exp_ax2(z, a, jj) * h_ii
+    return coeff * (-1j) ** n
+
+
+def Sigma_nexp_az2mzit(*args):
+    """algebra.jl:313-325 (the reference's Σnexp_az2mzit): sum_j n_j exp(a_j z^2 - i z tau_j); args = (z, n_1, tau_1, a_1, ..., m, l_1, n_1, k_1, ...)."""
+    J = (len(args) - 2) // 6
+    z, m = args[0], args[3 * J + 1]
+    f = 0j
+    for j in range(J):
+        nn, tau, a = args[1 + 3 * j: 4 + 3 * j]
+        l, n, k = args[2 + 3 * J + 3 * j: 5 + 3 * J + 3 * j]
+        f += pow1(nn, l) * exp_az2mzit(z, tau, a, m, n, k)
+    return f
+
+
 def generate_Sigma_y_exp_ikx(y):
     """algebra.jl:276-288"""
     N = len(y)
