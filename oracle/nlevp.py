@@ -286,6 +286,128 @@ def perturb(L, N, v0, v0Adj):
     return lam, v
 
 
+def perturb_disk(L, N, v0, v0Adj):
+    """perturbation.jl:373-450: the same power series as perturb(), summed per derivative pair (m, n) -- r = sum L(m,n) w_mn with
+    w_mn = sum over the multi-indices mu with |mu| = m of v[k-n-weight(mu)] * multinomial(mu) * prod lambda_g^mu_g -- and with the
+    eigenvector normalisation c = -1/2 sum_l v_l' v_(k-l).  The reference reads the multi-indices from files shipped with the package
+    (compressed_perturbation_data/k/m_n); here they are generated (all partitions of every weight W <= k - n except {k})."""
+    v0 = v0 / np.sqrt(np.vdot(v0, v0))
+    L10v0 = L(1, 0) @ v0
+    v0Adj = v0Adj / np.vdot(v0Adj, L10v0)
+    den = np.vdot(v0Adj, L10v0)
+    lam = np.zeros(N + 1, dtype=complex)
+    v = [None] * (N + 1)
+    v[0] = v0
+    L00 = spla.splu(sp.csc_matrix(L(0, 0)))
+    for k in range(1, N + 1):
+        w = {}
+        for n in range(1, k + 1):
+            w[(0, n)] = v[k - n].copy()
+        for W in range(1, k + 1):
+            for p in partitions(W):
+                if p == [k]:
+                    continue
+                mu = part2mult(p)
+                coeff = multinomcoeff(mu)
+                for g, mg in enumerate(mu):
+                    coeff = coeff * lam[g + 1] ** mg
+                for n in range(0, k - W + 1):
+                    key = (len(p), n)
+                    if key in w:
+                        w[key] = w[key] + v[k - n - W] * coeff
+                    else:
+                        w[key] = v[k - n - W] * coeff
+        r = np.zeros(len(v0), dtype=complex)
+        for (m, n), wv in sorted(w.items()):
+            r += L(m, n) @ wv
+        lam[k] = -np.vdot(v0Adj, r) / den
+        v[k] = L00.solve(-(r + lam[k] * L10v0))
+        v[k] = v[k] - np.vdot(v0, v[k]) * v0
+        c = 0j
+        for l in range(1, k):
+            c -= 0.5 * np.vdot(v[l], v[k - l])
+        v[k] = v[k] + c * v[0]
+    return lam, v
+
+
+def perturb_norm(L, N, v0, v0Adj):
+    """perturbation.jl:470-545: perturb_disk with the mass matrix Y = -coeff(__aux__) in every inner product (literal restatement,
+    including the lu(Y) solve of v0Adj)."""
+    Y = sp.csc_matrix(-L.terms[-1].coeff).astype(complex)
+    v0 = v0 / np.sqrt(np.vdot(v0, Y @ v0))
+    v0Adj = spla.splu(Y).solve(v0Adj)
+    L10v0 = L(1, 0) @ v0
+    v0Adj = v0Adj / np.vdot(v0Adj, Y @ L10v0)
+    lam = np.zeros(N + 1, dtype=complex)
+    v = [None] * (N + 1)
+    v[0] = v0
+    L00 = spla.splu(sp.csc_matrix(L(0, 0)))
+    for k in range(1, N + 1):
+        w = {}
+        for n in range(1, k + 1):
+            w[(0, n)] = v[k - n].copy()
+        for W in range(1, k + 1):
+            for p in partitions(W):
+                if p == [k]:
+                    continue
+                mu = part2mult(p)
+                coeff = multinomcoeff(mu)
+                for g, mg in enumerate(mu):
+                    coeff = coeff * lam[g + 1] ** mg
+                for n in range(0, k - W + 1):
+                    key = (len(p), n)
+                    w[key] = w[key] + v[k - n - W] * coeff if key in w else v[k - n - W] * coeff
+        r = np.zeros(len(v0), dtype=complex)
+        for (m, n), wv in sorted(w.items()):
+            r += L(m, n) @ wv
+        lam[k] = -np.vdot(v0Adj, Y @ r) / np.vdot(v0Adj, Y @ L10v0)
+        v[k] = L00.solve(-(r + lam[k] * L10v0))
+        v[k] = v[k] - np.vdot(v0, Y @ v[k]) * v0
+        c = 0j
+        for l in range(1, k):
+            c -= 0.5 * np.vdot(v[l], Y @ v[k - l])
+        v[k] = v[k] + c * v[0]
+    return lam, v
+
+
+def perturb_norm_bang(sol, L, param, N, mode="compact"):
+    """perturb_norm! (LinOpFam.jl:606-620)."""
+    active, params, cur = L.active, L.params, L.mode
+    L.params = sol.params
+    L.active = [sol.eigval, param]
+    L.mode = mode
+    key = f"{param}/Taylor"
+    try:
+        sol.eigval_pert[key], sol.v_pert[key] = perturb_norm(L, N, sol.v, sol.v_adj)
+        sol.eigval_pert[key][0] = sol.params[sol.eigval]
+    finally:
+        L.active, L.mode, L.params = active, cur, params
+
+
+def perturb_fast_bang(sol, L, param, N, mode="compact"):
+    """perturb_fast! (LinOpFam.jl:576-590)."""
+    active, params, cur = L.active, L.params, L.mode
+    L.params = sol.params
+    L.active = [sol.eigval, param]
+    L.mode = mode
+    key = f"{param}/Taylor"
+    try:
+        sol.eigval_pert[key], sol.v_pert[key] = perturb_disk(L, N, sol.v, sol.v_adj)
+        sol.eigval_pert[key][0] = sol.params[sol.eigval]
+    finally:
+        L.active, L.mode, L.params = active, cur, params
+
+
+def solution_eval(sol, param, eps, Lo=0, M=0):
+    """(sol::Solution)(param, eps, L, M) (LinOpFam.jl:680-696): [L/M] Pade approximant of the eigenvalue at param = eps."""
+    key = f"{param}/[{Lo}/{M}]"
+    if key not in sol.eigval_pert:
+        sol.eigval_pert[key] = pade(sol.eigval_pert[f"{param}/Taylor"], Lo, M)
+    a, b = sol.eigval_pert[key]
+    d = eps - sol.params[param]
+    return polyval(a, d) / polyval(b, d)
+
+
 def perturb_bang(sol, L, param, N, mode="compact"):
     """LinOpFam.jl:546-560."""
     active, params, cur = L.active, L.params, L.mode

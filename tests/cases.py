@@ -35,3 +35,15 @@ def rijke_dscrp(n, tau):
         "Outlet": ("admittance", ("Y", 1e15)),
         "Flame": ("flame", (GAMMA, RHO, Q02U0, X_REF, N_REF, "n", "τ", n, tau)),
     }
+
+
+# High-order perturbation theory, docs/src/tutorial_04_perturbation_theory.md:112-155: Rijke P1, n = 1, tau = 1 ms, mslp to 1e-11, then
+# perturb_fast!(sol, L, :tau, 20).  G8: the 21 Taylor coefficients of omega(tau) as printed (6 significant digits);
+# G9: sol(:tau, tau + 0.0005, 20) and the first-order value (printed in Hz) at full precision.
+G8_TAYLOR = [1075.33 + 372.102j, -2.62868e5 + 3.40796e5j, -1.79944e8 - 1.475e8j, 9.4741e10 - 1.57309e11j, 1.66943e14 + 8.14274e13j,
+             -8.3483e16 + 1.86246e17j, -2.15622e20 - 9.17653e19j, 1.05357e23 - 2.58704e23j, 3.19354e26 + 1.25588e26j,
+             -1.54315e29 + 4.02817e29j, -5.16822e32 - 1.94111e32j, 2.48748e35 - 6.72431e35j, 8.85193e38 + 3.23647e38j,
+             -4.26474e41 + 1.17688e42j, -1.57803e45 - 5.68031e44j, 7.63541e47 - 2.13155e48j, 2.89779e51 + 1.0345e51j,
+             -1.41133e54 + 3.9619e54j, -5.44414e57 - 1.93716e57j, 2.67322e60 - 7.51468e60j, 1.04148e64 + 3.70668e63j]
+G9_APPROX_20 = 916.7085040155473 + 494.3258317478708j
+G9_APPROX_1_HZ = 150.22496667319837 + 86.34150633981955j

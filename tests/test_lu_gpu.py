@@ -189,3 +189,45 @@ def test_fancyflame_and_state_space_admittance_match_oracle():
         so, no, fo = ohouse(Lo, 340 * 2 * math.pi, maxiter=25, tol=1e-11)
         assert fg == fo and fg >= 0
         assert abs(sg.params["ω"] - so.params["ω"]) <= TOL * abs(so.params["ω"]), (name, sg.params["ω"], so.params["ω"])
+
+
+def test_perturb_fast_goldens_on_the_gpu():
+    """G8/G9 (tutorial_04_perturbation_theory.md:112-155) through the CUDA path: one factorisation of L(0,0), 20 solves, one
+    combine + SpMV per derivative pair; plus the eigenvector series against the oracle and perturb_norm! / perturb! consistency."""
+    import wae_b200 as W
+    from cases import G8_TAYLOR, G9_APPROX_1_HZ, G9_APPROX_20
+    from oracle.helmholtz import discretize as odisc
+    from oracle.mesh import Mesh as OMesh
+    from oracle.nlevp import mslp as omslp
+    from oracle.nlevp import perturb_fast_bang as ofast
+    L = _gpu_family("lin", n=1.0)
+    sol, n, flag = W.mslp(L, 150 * 2 * math.pi, maxiter=30, tol=1e-11, output=False)
+    assert flag == 0
+    W.perturb_fast_bang(sol, L, "τ", 20)
+    tay = sol.eigval_pert["τ/Taylor"]
+    for a, b in zip(tay, G8_TAYLOR):
+        assert abs(a - b) <= 1e-5 * abs(b)
+    assert abs(sol("τ", 0.0015, 20) - G9_APPROX_20) <= TOL * abs(G9_APPROX_20)
+    assert abs(sol("τ", 0.0015, 1) / 2 / math.pi - G9_APPROX_1_HZ) <= TOL * abs(G9_APPROX_1_HZ)
+    # Pade [10/10] from the same coefficients is closer to the exact eigenvalue at tau + 0.5 ms (G5) than the Taylor polynomial
+    exact = 916.7036137579256 + 494.32932528479967j
+    assert abs(sol("τ", 0.0015, 10, 10) - exact) < abs(sol("τ", 0.0015, 20) - exact)
+    # oracle: same series (eigenvalue coefficients to 1e-9, eigenvector coefficients up to the phase of v0)
+    mo = OMesh("Rijke_mm.msh", scale=0.001, raw=load_raw_mesh("rijke_mm"))
+    Lo = odisc(mo, rijke_dscrp(1.0, 0.001), mo.generate_field(speedofsound))
+    so, _, _ = omslp(Lo, 150 * 2 * math.pi, maxiter=30, tol=1e-11)
+    ofast(so, Lo, "τ", 8)
+    for k in range(9):
+        assert abs(tay[k] - so.eigval_pert["τ/Taylor"][k]) <= 1e-8 * abs(tay[k])
+    vg, vo = sol.v_pert["τ/Taylor"], so.v_pert["τ/Taylor"]
+    ph = np.vdot(vo[0], vg[0])
+    ph /= abs(ph)
+    for k in range(4):
+        assert np.abs(vg[k] - ph * vo[k]).max() <= 1e-6 * np.abs(vo[k]).max(), k
+    sol2, _, _ = W.mslp(L, 150 * 2 * math.pi, maxiter=30, tol=1e-11, output=False)
+    W.perturb_norm_bang(sol2, L, "τ", 6)
+    sol3, _, _ = W.mslp(L, 150 * 2 * math.pi, maxiter=30, tol=1e-11, output=False)
+    W.perturb_bang(sol3, L, "τ", 4)
+    for k in range(5):
+        assert abs(sol2.eigval_pert["τ/Taylor"][k] - tay[k]) <= 1e-8 * abs(tay[k])
+        assert abs(sol3.eigval_pert["τ/Taylor"][k] - tay[k]) <= 1e-8 * abs(tay[k])

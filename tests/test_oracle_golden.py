@@ -104,3 +104,29 @@ def test_beyn_prose_values(rijke):
     for om in Om:
         sol, n, flag = householder(L, om, maxiter=10, tol=1e-10)
         assert abs(sol.params["ω"] - om) < 5e-3 * abs(om)  # N=32 on a thin rectangle: quadrature-limited
+
+
+def test_perturb_fast_goldens(rijke):
+    """G8/G9 (docs/src/tutorial_04_perturbation_theory.md:112-155): 20th-order power series of omega(tau) by perturb_fast!, its value
+    at tau + 0.5 ms and the first-order value; perturb! (the slow algorithm) and perturb_norm! give the same eigenvalue series."""
+    from cases import G8_TAYLOR, G9_APPROX_1_HZ, G9_APPROX_20
+    from oracle.nlevp import perturb_bang, perturb_fast_bang, perturb_norm_bang, solution_eval
+    mesh, c = rijke
+    L = discretize(mesh, rijke_dscrp(1, 0.001), c)
+    sol, n, flag = mslp(L, 150 * 2 * math.pi, maxiter=30, tol=1e-11)
+    assert flag == 0
+    mode0, active0 = L.mode, list(L.active)
+    perturb_fast_bang(sol, L, "τ", 20)
+    assert L.mode == mode0 and L.active == active0  # perturb_fast! restores the family (LinOpFam.jl:586-588)
+    tay = sol.eigval_pert["τ/Taylor"]
+    for a, b in zip(tay, G8_TAYLOR):
+        assert abs(a - b) <= 1e-5 * abs(b)  # printed with 6 significant digits
+    assert abs(solution_eval(sol, "τ", 0.0015, 20, 0) - G9_APPROX_20) <= 1e-11 * abs(G9_APPROX_20)
+    assert abs(solution_eval(sol, "τ", 0.0015, 1, 0) / 2 / math.pi - G9_APPROX_1_HZ) <= 1e-11 * abs(G9_APPROX_1_HZ)
+    sol2, _, _ = mslp(L, 150 * 2 * math.pi, maxiter=30, tol=1e-11)
+    perturb_bang(sol2, L, "τ", 6)
+    sol3, _, _ = mslp(L, 150 * 2 * math.pi, maxiter=30, tol=1e-11)
+    perturb_norm_bang(sol3, L, "τ", 6)
+    for k in range(7):
+        assert abs(sol2.eigval_pert["τ/Taylor"][k] - tay[k]) <= 1e-9 * abs(tay[k])
+        assert abs(sol3.eigval_pert["τ/Taylor"][k] - tay[k]) <= 1e-9 * abs(tay[k])

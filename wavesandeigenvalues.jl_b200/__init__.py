@@ -10,7 +10,8 @@ from . import _lib  # noqa: F401
 from .helmholtz import discretize  # noqa: F401
 from .meshutils import Mesh, SymInfo, aggregate_elements, extend_mesh, kuhn_box, kuhn_unit_cell  # noqa: F401
 from .nlevp import (bloch_expand, LinearOperatorFamily, Solution, Term, beyn, compute_moment_matrices, exp_az, exp_delay,  # noqa: F401
-                    get_context, householder, inpoly, moments2eigs, mslp, perturb_bang, pow0, pow1, pow2, pow_a,
+                    get_context, householder, inpoly, moments2eigs, mslp, pade_bang, perturb_bang, perturb_fast_bang, perturb_norm_bang, pow0,
+                    pow1, pow2, pow_a,
                     reset_context, wn)
 
 __all__ = ["Mesh", "discretize", "LinearOperatorFamily", "Term", "Solution", "householder", "mslp", "beyn", "pow0", "pow1",

@@ -261,6 +261,20 @@ class Solution:
         self.v, self.v_adj, self.eigval, self.auxval = v, v_adj, eigval, auxval
         self.eigval_pert, self.v_pert = {}, {}
 
+    def __call__(self, param, eps, Lo=0, M=0, vector=False):
+        """(sol::Solution)(param, eps, L, M; vector) (LinOpFam.jl:680-696): evaluate the [Lo/M] Pade approximant (M = 0: Taylor
+        polynomial of order Lo) of the eigenvalue (and eigenvector) at param = eps from the stored perturbation coefficients."""
+        key = f"{param}/[{Lo}/{M}]"
+        if key not in self.eigval_pert or (vector and key not in self.v_pert):
+            pade_bang(self, param, Lo, M, vector=vector)
+        a, b = self.eigval_pert[key]
+        d = eps - self.params[param]
+        val = polyval(a, d) / polyval(b, d)
+        if not vector:
+            return val
+        A, B = self.v_pert[key]
+        return val, polyval(A, d) / polyval(B, d)
+
     def __str__(self):
         txt = f"####Solution####\neigval:\n{self.eigval} = {self.params[self.eigval]}\n\nParameters:\n"
         for k, v in self.params.items():
@@ -501,6 +515,93 @@ def perturb(L, N, v0, v0Adj):
             vk = ctx.lu_solve(lu, -(r + lam[k] * L10v0))
             v[k] = vk - np.vdot(v0, vk) * v0
     return lam, v
+
+
+def perturb_disk(L, N, v0, v0Adj, weighted=False):
+    """perturbation.jl:373-450 (perturb_disk) and :470-545 (perturb_norm, weighted=True): power-series coefficients of the eigenvalue
+    and the eigenvector to order N with ONE factorisation of L(0,0) and N solves on the device.  The sum is organised per derivative
+    pair: r = sum_(m,n) L(m,n) w_mn, w_mn = sum over the multi-indices mu with |mu| = m of v[k-n-weight(mu)] multinomial(mu)
+    prod_g lambda_g^mu_g -- one combine + SpMV per pair instead of one per multi-index.  The reference reads the multi-indices from
+    files shipped with the package; here all partitions of every weight W <= k-n (except {k}) are generated on the fly.
+    weighted: inner products in the mass matrix Y = -coeff(__aux__) (v0'Y v0 = 1).  With Y real symmetric the reference's
+    lu(Y)\v0Adj followed by v0Adj'Y(.) is v0Adj'(.), which is what is evaluated here (no factorisation of Y)."""
+    dv = L.device()
+    ctx = dv.ctx
+    if weighted:
+        Y = (-L.terms[-1].coeff).to_scipy().real
+        ip = lambda a, b: np.vdot(a, Y @ b)
+    else:
+        ip = np.vdot
+    v0 = v0 / np.sqrt(ip(v0, v0))
+    L10v0 = L(1, 0).matvec(v0, slot=2)
+    v0Adj = v0Adj / np.vdot(v0Adj, L10v0)
+    den = np.vdot(v0Adj, L10v0)
+    lam = np.zeros(N + 1, dtype=complex)
+    v = [None] * (N + 1)
+    v[0] = v0
+    L(0, 0).materialize(3)
+    lu = dv.lu()
+    ctx.lu_factor(lu, 3)
+    for k in range(1, N + 1):
+        w = {(0, n): v[k - n].copy() for n in range(1, k + 1)}
+        for W in range(1, k + 1):
+            for p in _partitions(W):
+                if p == [k]:
+                    continue
+                mu = _part2mult(p)
+                coeff = math.factorial(sum(mu)) / math.prod(math.factorial(x) for x in mu)
+                for g, mg in enumerate(mu):
+                    coeff = coeff * lam[g + 1] ** mg
+                for n in range(0, k - W + 1):
+                    key = (len(p), n)
+                    w[key] = w[key] + v[k - n - W] * coeff if key in w else v[k - n - W] * coeff
+        r = np.zeros(len(v0), dtype=complex)
+        for (m, n), wv in sorted(w.items()):
+            r += L(m, n).matvec(wv, slot=2)
+        lam[k] = -np.vdot(v0Adj, r) / den
+        vk = ctx.lu_solve(lu, -(r + lam[k] * L10v0))
+        vk = vk - ip(v0, vk) * v0
+        c = 0j
+        for l in range(1, k):
+            c -= 0.5 * ip(v[l], v[k - l])
+        v[k] = vk + c * v[0]
+    return lam, v
+
+
+def _perturb_driver(fn, sol, L, param, N, mode):
+    active, params, cur = L.active, L.params, L.mode
+    L.params = sol.params
+    L.active = [sol.eigval, param]
+    L.mode = mode
+    key = f"{param}/Taylor"
+    try:
+        sol.eigval_pert[key], sol.v_pert[key] = fn(L, N, sol.v, sol.v_adj)
+        sol.eigval_pert[key][0] = sol.params[sol.eigval]
+    finally:
+        L.active, L.mode, L.params = active, cur, params
+
+
+def perturb_fast_bang(sol, L, param, N, mode="compact"):
+    """perturb_fast! (LinOpFam.jl:576-590)"""
+    _perturb_driver(perturb_disk, sol, L, param, N, mode)
+
+
+def perturb_norm_bang(sol, L, param, N, mode="compact"):
+    """perturb_norm! (LinOpFam.jl:606-620): as perturb_fast! with mass-weighted normalisation of the eigenvector series."""
+    _perturb_driver(lambda L_, N_, v_, va_: perturb_disk(L_, N_, v_, va_, weighted=True), sol, L, param, N, mode)
+
+
+def pade_bang(sol, param, Lo, M, vector=False):
+    """pade! (LinOpFam.jl:644-676): [Lo/M] Pade approximant of the eigenvalue (and, component-wise, of the eigenvector) series."""
+    key, tkey = f"{param}/[{Lo}/{M}]", f"{param}/Taylor"
+    sol.eigval_pert[key] = pade(sol.eigval_pert[tkey], Lo, M)
+    if vector:
+        V = np.array(sol.v_pert[tkey][: Lo + M + 1])  # (order, dof)
+        A = np.empty((Lo + 1, V.shape[1]), dtype=complex)
+        B = np.empty((M + 1, V.shape[1]), dtype=complex)
+        for i in range(V.shape[1]):
+            A[:, i], B[:, i] = pade(V[:, i], Lo, M)
+        sol.v_pert[key] = (A, B)
 
 
 def perturb_bang(sol, L, param, N, mode="compact"):
