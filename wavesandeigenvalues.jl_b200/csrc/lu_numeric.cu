@@ -389,8 +389,12 @@ __global__ void __launch_bounds__(1024) lu_fwd_tri_kernel(LuDev D, const int32_t
   const cplx* P = use_up ? S.up : S.lp;
   const cplx* dinv = D.dinv + D.dinv_off[sn] + (use_up ? NB * NB : 0);
   __shared__ cplx yk[NB];
+  __shared__ cplx xw[LU_SOLVE_W];  // the window of x: the block steps work on shared memory only
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  cplx* xs = x + (size_t)blockIdx.y * n + S.first;  // one CTA per (supernode, right-hand side)
+  cplx* xg = x + (size_t)blockIdx.y * n + S.first;  // one CTA per (supernode, right-hand side)
+  if (threadIdx.x < c_hi - c_lo) xw[threadIdx.x] = xg[c_lo + threadIdx.x];
+  __syncthreads();
+  cplx* xs = xw - c_lo;  // xs[i] = entry i of the pivot block, valid for c_lo <= i < c_hi
   for (int c0 = c_lo, kb = c_lo / NB; c0 < c_hi; c0 += NB, kb++) {
     const int nb = min(NB, S.s - c0);
     {
@@ -430,6 +434,7 @@ __global__ void __launch_bounds__(1024) lu_fwd_tri_kernel(LuDev D, const int32_t
     }
     __syncthreads();
   }
+  if (threadIdx.x < c_hi - c_lo) xg[c_lo + threadIdx.x] = xw[threadIdx.x];
 }
 
 // x[rows below the window] -= P[rows, window] * y_window.  grid.x row chunks of 64, grid.y supernode, grid.z groups of NR
@@ -552,7 +557,11 @@ __global__ void __launch_bounds__(1024) lu_bwd_tri_kernel(LuDev D, const int32_t
   const cplx* dinv = D.dinv + D.dinv_off[sn] + (use_up ? NB * NB : 0);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __shared__ cplx yk[NB];
-  cplx* xs = x + (size_t)blockIdx.y * n + S.first;
+  __shared__ cplx xw[LU_SOLVE_W];  // the window of x in shared memory
+  cplx* xg = x + (size_t)blockIdx.y * n + S.first;
+  if (threadIdx.x < c_hi - c_lo) xw[threadIdx.x] = xg[c_lo + threadIdx.x];
+  __syncthreads();
+  cplx* xs = xw - c_lo;
   for (int kb = (c_hi - 1) / NB; kb >= c_lo / NB; kb--) {
     const int c0 = kb * NB, nb = min(NB, S.s - c0);
     // column c0+warp: subtract the contribution of the already solved rows of the window below this block
@@ -589,6 +598,7 @@ __global__ void __launch_bounds__(1024) lu_bwd_tri_kernel(LuDev D, const int32_t
     }
     __syncthreads();
   }
+  if (threadIdx.x < c_hi - c_lo) xg[c_lo + threadIdx.x] = xw[threadIdx.x];
 }
 
 // ---- vector utilities -------------------------------------------------------------------------------------
