@@ -47,3 +47,8 @@ G8_TAYLOR = [1075.33 + 372.102j, -2.62868e5 + 3.40796e5j, -1.79944e8 - 1.475e8j,
              -1.41133e54 + 3.9619e54j, -5.44414e57 - 1.93716e57j, 2.67322e60 - 7.51468e60j, 1.04148e64 + 3.70668e63j]
 G9_APPROX_20 = 916.7085040155473 + 494.3258317478708j
 G9_APPROX_1_HZ = 150.22496667319837 + 86.34150633981955j
+# G10 (examples/tutorials/tutorial_04_perturbation_theory.ipynb cells 5-14): the same at the G1 set-up (n = 0.01, householder to 1e-11):
+# perturb_fast!(sol, L, :tau, 20), then sol(:tau, tau + 1e-5, 20); first two coefficients as printed in cell 11.  (The later cells of that
+# notebook -- conv_radius, the [10/10] Pade value -- were produced after L.params had been modified in place and are not reproducible.)
+G10_APPROX_20 = 1710.8641999717368 + 9.593830019669932j
+G10_TAYLOR_01 = (1710.7 + 9.61502j, 16655.8 - 1972.54j)

@@ -231,3 +231,11 @@ def test_perturb_fast_goldens_on_the_gpu():
     for k in range(5):
         assert abs(sol2.eigval_pert["τ/Taylor"][k] - tay[k]) <= 1e-8 * abs(tay[k])
         assert abs(sol3.eigval_pert["τ/Taylor"][k] - tay[k]) <= 1e-8 * abs(tay[k])
+    # G10: the same at the G1 solution (householder, n = 0.01), notebook cells 5-14
+    from cases import G10_APPROX_20
+    L1 = _gpu_family("lin", n=0.01)
+    s1, _, _ = W.householder(L1, 340 * 2 * math.pi, maxiter=20, tol=1e-11, output=False)
+    W.perturb_fast_bang(s1, L1, "τ", 20)
+    assert abs(s1("τ", 0.001 + 1e-5, 20) - G10_APPROX_20) <= TOL * abs(G10_APPROX_20)
+    r = W.conv_radius(s1, "τ")
+    assert len(r) == 20 and 1e-3 < r[-1] < 3e-3

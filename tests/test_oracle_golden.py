@@ -130,3 +130,19 @@ def test_perturb_fast_goldens(rijke):
     for k in range(7):
         assert abs(sol2.eigval_pert["τ/Taylor"][k] - tay[k]) <= 1e-9 * abs(tay[k])
         assert abs(sol3.eigval_pert["τ/Taylor"][k] - tay[k]) <= 1e-9 * abs(tay[k])
+
+
+def test_perturb_fast_golden_at_g1(rijke):
+    """G10 (notebook cells 5-14): 20th-order series at the G1 solution, evaluated 1e-5 s away; equals the exact eigenvalue G2 to 1e-11."""
+    from cases import G10_APPROX_20, G10_TAYLOR_01
+    from oracle.nlevp import perturb_fast_bang, solution_eval
+    mesh, c = rijke
+    L = discretize(mesh, rijke_dscrp(0.01, 0.001), c)
+    sol, n, flag = householder(L, 340 * 2 * math.pi, maxiter=20, tol=1e-11)
+    perturb_fast_bang(sol, L, "τ", 20)
+    tay = sol.eigval_pert["τ/Taylor"]
+    for a, b in zip(tay, G10_TAYLOR_01):
+        assert abs(a - b) <= 1e-5 * abs(b)
+    w = solution_eval(sol, "τ", 0.001 + 1e-5, 20, 0)
+    assert abs(w - G10_APPROX_20) <= 1e-11 * abs(w)
+    assert abs(w - G_HOUSEHOLDER[1][1]) <= 1e-10 * abs(w)  # G2: the exact eigenvalue at tau = 1.01 ms

@@ -604,6 +604,13 @@ def pade_bang(sol, param, Lo, M, vector=False):
         sol.v_pert[key] = (A, B)
 
 
+def conv_radius(sol_or_coeffs, param=None):
+    """conv_radius (LinOpFam.jl:754-766): ratio estimates |a_n / a_(n+1)| of the convergence radius of the power series."""
+    a = sol_or_coeffs.eigval_pert[f"{param}/Taylor"] if param is not None else sol_or_coeffs
+    a = np.asarray(a)
+    return np.abs(a[:-1] / a[1:])
+
+
 def perturb_bang(sol, L, param, N, mode="compact"):
     """perturb! (LinOpFam.jl:546-560)"""
     active, params, cur = L.active, L.params, L.mode
