@@ -494,24 +494,21 @@ void wae_launch_assemble_gather(wae_ctx* h, Pattern& P, const double* d_c, doubl
   }
   const int slot_bytes = G.max_slots * 16, pxyz_bytes = (G.max_nv * 24 + 15) & ~15, buf_bytes = pxyz_bytes + ((G.max_blob + 15) & ~15);
   const size_t smem = (size_t)slot_bytes + 2 * (size_t)buf_bytes;
-  static bool attr_set[4] = {false, false, false, false};
   const int dbg = getenv("WAE_GATHER_DBG") ? atoi(getenv("WAE_GATHER_DBG")) : 0;
   int threads = smem > 113 * 1024 ? 1024 : 512;  // one or two CTAs per SM, 64 registers per thread either way
   if (const char* env = getenv("WAE_GATHER_THREADS")) threads = atoi(env);
   const int grid = std::min(G.n_patch, h->sm_count * (smem > 113 * 1024 ? 1 : 2));
-  auto launch = [&](auto kern, int which) {
-    if (!attr_set[which]) {
-      CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
-      attr_set[which] = true;
-    }
+  auto launch = [&](auto kern) {
+    // per device, and cheap: set on every launch (a process may hold contexts on several GPUs)
+    CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
     kern<<<grid, threads, smem, h->stream>>>(G.d_desc.p, G.n_patch, G.d_blob.p, G.d_pxyz.p, d_c, G.d_dest.p, G.d_res.p, slot_bytes, pxyz_bytes,
                                              buf_bytes, mass_scale, d_mass, d_stiff, dbg);
   };
   const bool both = d_stiff != nullptr;
   if (h->nloc == 4) {
-    if (both) launch(assemble_tet_pairs<4, 3>, 0); else launch(assemble_tet_pairs<4, 1>, 1);
+    if (both) launch(assemble_tet_pairs<4, 3>); else launch(assemble_tet_pairs<4, 1>);
   } else {
-    if (both) launch(assemble_tet_pairs<10, 3>, 2); else launch(assemble_tet_pairs<10, 1>, 3);
+    if (both) launch(assemble_tet_pairs<10, 3>); else launch(assemble_tet_pairs<10, 1>);
   }
   h->launches++;
   CUDA_CHECK(cudaGetLastError());
@@ -520,6 +517,11 @@ void wae_launch_assemble_gather(wae_ctx* h, Pattern& P, const double* d_c, doubl
 void wae_ensure_gather(wae_ctx* h, Pattern& P) {
   auto& G = P.gather;
   if (G.built) return;
+  if (P.elems.empty() || P.nnz == 0) {  // nothing to assemble: no program, no launch
+    G.n_patch = 0;
+    G.built = true;
+    return;
+  }
   // shared memory = slots (16 B each) + two buffers (staged coordinates + program blob of the current and the next patch);
   // the loop below shrinks the slot count until everything fits one SM (one CTA per SM); WAE_GATHER_SLOTS overrides for tuning
   int slot_cap = 12288;
