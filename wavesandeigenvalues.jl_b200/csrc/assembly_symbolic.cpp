@@ -6,12 +6,24 @@
 // zeros kept, rows sorted inside columns).
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <thread>
 
 #include "wae_internal.h"
 
 namespace {
+struct PhaseClock {  // WAE_SYMB_TIMING=1 prints the wall time of the symbolic phases to stderr
+  std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+  bool on = getenv("WAE_SYMB_TIMING") != nullptr;
+  void tick(const char* what) {
+    auto n = std::chrono::steady_clock::now();
+    if (on) fprintf(stderr, "[wae symbolic] %-34s %8.3f s\n", what, std::chrono::duration<double>(n - t).count());
+    t = n;
+  }
+};
 template <typename F>
 void parallel_for(int64_t n, F f) {
   unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
@@ -49,38 +61,50 @@ void wae_build_pattern_from_elements(const uint32_t* conn, int nloc, const std::
   std::vector<int64_t> nptr;
   std::vector<int32_t> nadj;
   node_to_elem(conn, nloc, elems, dim, nptr, nadj);
-  // pass 1: column counts, pass 2: fill.  Column j holds the union of the DOFs of its elements.
-  std::vector<int64_t> cnt(dim + 1, 0);
-  std::vector<std::vector<int32_t>> cols;  // only used transiently per thread
+  // Column j holds the union of the DOFs of its elements.  One pass: every thread builds the sorted, uniquified rows of a
+  // contiguous range of columns into its own buffer; the buffers are then copied behind each other (column ranges are
+  // contiguous, so each buffer is one contiguous piece of rowval).
   P.dim = dim;
   P.colptr.assign(dim + 1, 0);
-  auto column = [&](int64_t j, std::vector<int32_t>& buf) {
-    buf.clear();
-    for (int64_t q = nptr[j]; q < nptr[j + 1]; q++) {
-      const uint32_t* d = conn + (size_t)elems[nadj[q]] * nloc;
-      for (int k = 0; k < nloc; k++) buf.push_back((int32_t)d[k]);
-    }
-    std::sort(buf.begin(), buf.end());
-    buf.erase(std::unique(buf.begin(), buf.end()), buf.end());
-  };
-  parallel_for(dim, [&](int64_t a, int64_t b) {
-    std::vector<int32_t> buf;
-    for (int64_t j = a; j < b; j++) {
-      column(j, buf);
-      cnt[j + 1] = (int64_t)buf.size();
-    }
-  });
+  const unsigned nthr = dim < 4096 ? 1u : std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  std::vector<std::vector<int32_t>> rows(nthr);
+  std::vector<int64_t> cnt(dim + 1, 0);
+  {
+    std::vector<std::thread> th;
+    for (unsigned q = 0; q < nthr; q++)
+      th.emplace_back([&, q]() {
+        const int64_t a = dim * q / nthr, b = dim * (q + 1) / nthr;
+        std::vector<int32_t> buf;
+        std::vector<int32_t>& out = rows[q];
+        out.reserve((size_t)(nptr[b] - nptr[a]) * 3);
+        for (int64_t j = a; j < b; j++) {
+          buf.clear();
+          for (int64_t r = nptr[j]; r < nptr[j + 1]; r++) {
+            const uint32_t* d = conn + (size_t)elems[nadj[r]] * nloc;
+            for (int k = 0; k < nloc; k++) buf.push_back((int32_t)d[k]);
+          }
+          std::sort(buf.begin(), buf.end());
+          buf.erase(std::unique(buf.begin(), buf.end()), buf.end());
+          cnt[j + 1] = (int64_t)buf.size();
+          out.insert(out.end(), buf.begin(), buf.end());
+        }
+      });
+    for (auto& x : th) x.join();
+  }
   for (int64_t j = 0; j < dim; j++) P.colptr[j + 1] = P.colptr[j] + cnt[j + 1];
   P.nnz = P.colptr[dim];
   if (P.nnz >= (int64_t)1 << 31) WAE_THROW(WAE_E_INVALID, "pattern has %lld nonzeros (>= 2^31)", (long long)P.nnz);
   P.rowval.resize(P.nnz);
-  parallel_for(dim, [&](int64_t a, int64_t b) {
-    std::vector<int32_t> buf;
-    for (int64_t j = a; j < b; j++) {
-      column(j, buf);
-      std::memcpy(P.rowval.data() + P.colptr[j], buf.data(), buf.size() * sizeof(int32_t));
-    }
-  });
+  {
+    std::vector<std::thread> th;
+    for (unsigned q = 0; q < nthr; q++)
+      th.emplace_back([&, q]() {
+        const int64_t a = dim * q / nthr;
+        if (!rows[q].empty()) std::memcpy(P.rowval.data() + P.colptr[a], rows[q].data(), rows[q].size() * sizeof(int32_t));
+        std::vector<int32_t>().swap(rows[q]);
+      });
+    for (auto& x : th) x.join();
+  }
 }
 
 // slot of (row i, col j) by binary search in column j
@@ -142,9 +166,11 @@ void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const P
   const int64_t ne = (int64_t)P.elems.size();
   const int64_t dim = P.dim;
   const int nsym = nloc * (nloc + 1) / 2;
+  PhaseClock clk;
   std::vector<int64_t> nptr;
   std::vector<int32_t> nadj;
   node_to_elem(conn, nloc, P.elems, dim, nptr, nadj);
+  clk.tick("node -> element adjacency");
   // Morton rank of every element (centroid on a 2^21 grid over the bounding box)
   std::vector<int32_t> rank(ne);
   {
@@ -174,6 +200,7 @@ void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const P
     std::sort(key.begin(), key.end());
     for (int64_t i = 0; i < ne; i++) rank[key[i].second] = (int32_t)i;
   }
+  clk.tick("Morton ranks");
   // owner of a DOF = its incident element of lowest Morton rank; position = index in owner order
   std::vector<int32_t> order;      // position -> DOF
   std::vector<int32_t> pos(dim, -1);  // DOF -> position (-1: DOF not touched by the pattern's elements)
@@ -197,6 +224,7 @@ void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const P
   }
   if (max_inc > 255) WAE_THROW(WAE_E_INVALID, "a DOF is shared by %d elements; the pair program holds at most 255 sources per entry", max_inc);
   const int64_t npos = (int64_t)order.size();
+  clk.tick("DOF owner order");
   // ---- cut the positions into patches by their exact number of sources --------------------------------------------------
   // A patch [lo, hi) owns the columns of its positions.  Its sources are the (element, local pair {a,b}) with at least one of the
   // two DOFs owned; a pair with BOTH DOFs owned is one source feeding nz(i,j) and nz(j,i).  Adding position q to the patch
@@ -249,6 +277,7 @@ void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const P
       cut.push_back(npos);
     }
     npatch = (int64_t)cut.size() - 1;
+    clk.tick("patch cut");
     po.clear();
     po.resize(npatch);
     bad = 0;
@@ -256,9 +285,9 @@ void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const P
       struct Src { uint64_t key; int32_t t; int32_t s; };
       struct Unit { uint64_t key; int32_t first; int32_t cnt; int32_t slot; };
       std::vector<std::pair<int32_t, int32_t>> st;  // (rank, element)
-      std::vector<Src> src;
+      std::vector<Src> src, tmp;
       std::vector<Unit> units;
-      std::vector<int32_t> by_cnt, cols;
+      std::vector<int32_t> by_cnt, cols, colptr, fill, ucol;
       for (int64_t p = pa; p < pb; p++) {
         PatchOut& O = po[p];
         const int32_t lo = (int32_t)cut[p], hi = (int32_t)cut[p + 1];
@@ -324,7 +353,20 @@ void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const P
             }
         }
         O.sources = (int64_t)src.size();
-        std::sort(src.begin(), src.end(), [](const Src& x, const Src& y) { return x.key != y.key ? x.key < y.key : x.t < y.t; });
+        // order by (column, row, staged element): the sources were generated in ascending t, so a stable counting sort by column
+        // followed by a stable sort of every (short) column bucket by row is all that is needed
+        {
+          const int ncol = hi - lo;
+          colptr.assign(ncol + 1, 0);
+          for (const Src& x : src) colptr[(x.key >> 32) + 1]++;
+          for (int cc = 0; cc < ncol; cc++) colptr[cc + 1] += colptr[cc];
+          tmp.resize(src.size());
+          fill.assign(colptr.begin(), colptr.end() - 1);
+          for (const Src& x : src) tmp[fill[x.key >> 32]++] = x;
+          for (int cc = 0; cc < ncol; cc++)
+            std::stable_sort(tmp.begin() + colptr[cc], tmp.begin() + colptr[cc + 1], [](const Src& x, const Src& y) { return x.key < y.key; });
+          src.swap(tmp);
+        }
         units.clear();
         for (size_t i = 0; i < src.size();) {
           size_t j = i;
@@ -333,6 +375,9 @@ void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const P
           i = j;
         }
         O.units = (int64_t)units.size();
+        ucol.assign(hi - lo + 1, 0);  // units are sorted by key: first unit of every column
+        for (const Unit& u : units) ucol[(u.key >> 32) + 1]++;
+        for (int cc = 0; cc < hi - lo; cc++) ucol[cc + 1] += ucol[cc];
         by_cnt.resize(units.size());
         for (size_t i = 0; i < units.size(); i++) by_cnt[i] = (int32_t)i;
         std::stable_sort(by_cnt.begin(), by_cnt.end(), [&](int32_t x, int32_t y) { return units[x].cnt > units[y].cnt; });
@@ -368,12 +413,13 @@ void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const P
         O.res.clear();
         O.chunk.clear();
         auto find_unit = [&](uint64_t key) -> int32_t {
-          size_t a0 = 0, b0 = units.size();
+          size_t a0 = (size_t)ucol[key >> 32], b0 = (size_t)ucol[(key >> 32) + 1];
+          const size_t end = b0;
           while (a0 < b0) {
             size_t m = (a0 + b0) >> 1;
             if (units[m].key < key) a0 = m + 1; else b0 = m;
           }
-          return (a0 < units.size() && units[a0].key == key) ? units[a0].slot : -1;
+          return (a0 < end && units[a0].key == key) ? units[a0].slot : -1;
         };
         for (int32_t j : cols) {
           const int32_t qj = pos[j];
@@ -397,6 +443,7 @@ void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const P
         }
       }
     });
+    clk.tick("per-patch programs");
     if (!bad) break;
   }
   if (bad) WAE_THROW(WAE_E_INVALID, "pair program overflow (%d; slot capacity %d)", (int)bad, slot_cap);
@@ -456,6 +503,7 @@ void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const P
       O = PatchOut();
     }
   });
+  clk.tick("pack");
 }
 
 // ------------------------------------------------------------------------------------
