@@ -558,23 +558,31 @@ int32_t wae_family_create(wae_ctx* h, int32_t n_terms, const int32_t* mat_ids, i
     Pattern& U = *h->patterns[upid];
     U.dim = dim;
     U.colptr.assign(dim + 1, 0);
-    std::vector<int32_t> buf, tmp;
+    // column-wise union of the term patterns, two passes (count, fill), both parallel over contiguous column ranges
+    const unsigned nthr = dim < 4096 ? 1u : std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
     for (int pass = 0; pass < 2; pass++) {
-      for (int64_t j = 0; j < dim; j++) {
-        buf.clear();
-        for (int p : pats) {
-          const Pattern& A = h->pat(p);
-          tmp.clear();
-          std::set_union(buf.begin(), buf.end(), A.rowval.begin() + A.colptr[j], A.rowval.begin() + A.colptr[j + 1],
-                         std::back_inserter(tmp));
-          buf.swap(tmp);
-        }
-        if (pass == 0)
-          U.colptr[j + 1] = U.colptr[j] + (int64_t)buf.size();
-        else
-          std::copy(buf.begin(), buf.end(), U.rowval.begin() + U.colptr[j]);
-      }
+      std::vector<std::thread> th;
+      for (unsigned q = 0; q < nthr; q++)
+        th.emplace_back([&, q, pass]() {
+          std::vector<int32_t> buf, tmp;
+          for (int64_t j = dim * q / nthr; j < dim * (q + 1) / nthr; j++) {
+            buf.clear();
+            for (int p : pats) {
+              const Pattern& A = h->pat(p);
+              tmp.clear();
+              std::set_union(buf.begin(), buf.end(), A.rowval.begin() + A.colptr[j], A.rowval.begin() + A.colptr[j + 1],
+                             std::back_inserter(tmp));
+              buf.swap(tmp);
+            }
+            if (pass == 0)
+              U.colptr[j + 1] = (int64_t)buf.size();  // counts first, prefix sum below
+            else
+              std::copy(buf.begin(), buf.end(), U.rowval.begin() + U.colptr[j]);
+          }
+        });
+      for (auto& x : th) x.join();
       if (pass == 0) {
+        for (int64_t j = 0; j < dim; j++) U.colptr[j + 1] += U.colptr[j];
         U.nnz = U.colptr[dim];
         if (U.nnz >= ((int64_t)1 << 31)) WAE_THROW(WAE_E_INVALID, "union pattern too large");
         U.rowval.resize(U.nnz);
