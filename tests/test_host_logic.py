@@ -1,6 +1,7 @@
 """CPU tests of the product's host side (no GPU): mesh numbering rules, scalar algebra, family evaluation
 rules and the symbolic LU phase, each against the oracle restatement of the reference."""
 import ctypes as C
+import os
 import math
 
 import numpy as np
@@ -251,3 +252,20 @@ def test_fancyflame_and_state_space_scalars():
         assert abs(fg(z, n) - fo(z, n)) <= 1e-12 * abs(fo(z, n))
         if n <= 2:  # (finite differences of higher order drown in round-off: the values are ~1e-11)
             assert abs(fg(z, n) - _num_deriv(H, z, n, 2.0)) <= 1e-4 * abs(fg(z, n)) + 1e-30
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm the driver times beside the GPU arm) prints one JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--ref-sample", "2,2,8"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
+    d = json.loads(line)
+    assert d["impl"] == "reference" and d["unit"] == "eigenpairs/s" and d["higher_is_better"] is True
+    assert d["value"] > 0 and d["steps"] == 1 and d["vs_baseline"] is None
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
