@@ -545,11 +545,11 @@ void wae_ensure_gather(wae_ctx* h, Pattern& P) {
   G.n_staged = GH.n_staged;
   G.n_pv = (int64_t)GH.gvtx.size();
   G.d_desc.upload(GH.desc, h->stream);
-  G.d_blob.upload(GH.blob, h->stream);
-  G.d_gvtx.upload(GH.gvtx, h->stream);
+  G.d_blob.upload(GH.blob.data(), GH.blob.size(), h->stream);
+  G.d_gvtx.upload(GH.gvtx.data(), GH.gvtx.size(), h->stream);
   G.d_pxyz.alloc((size_t)G.n_pv * 3 + 2);
-  G.d_dest.upload(GH.dest, h->stream);
-  G.d_res.upload(GH.res, h->stream);
+  G.d_dest.upload(GH.dest.data(), GH.dest.size(), h->stream);
+  G.d_res.upload(GH.res.data(), GH.res.size(), h->stream);
   G.xyz_version = 0;
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
   G.built = true;

@@ -37,6 +37,31 @@ void parallel_for(int64_t n, F f) {
   }
   for (auto& x : th) x.join();
 }
+// sort with the host threads: sorted chunks, then pairwise merges (stable enough for unique keys)
+template <typename T>
+void parallel_sort(std::vector<T>& v) {
+  const size_t n = v.size();
+  unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  if (n < (size_t)1 << 16 || nt == 1) {
+    std::sort(v.begin(), v.end());
+    return;
+  }
+  unsigned parts = 1;
+  while (parts * 2 <= nt) parts *= 2;
+  std::vector<size_t> b(parts + 1);
+  for (unsigned q = 0; q <= parts; q++) b[q] = n * q / parts;
+  {
+    std::vector<std::thread> th;
+    for (unsigned q = 0; q < parts; q++) th.emplace_back([&, q]() { std::sort(v.begin() + b[q], v.begin() + b[q + 1]); });
+    for (auto& x : th) x.join();
+  }
+  for (unsigned w = 1; w < parts; w *= 2) {
+    std::vector<std::thread> th;
+    for (unsigned q = 0; q + w < parts; q += 2 * w)
+      th.emplace_back([&, q, w]() { std::inplace_merge(v.begin() + b[q], v.begin() + b[q + w], v.begin() + b[std::min(parts, q + 2 * w)]); });
+    for (auto& x : th) x.join();
+  }
+}
 }  // namespace
 
 // node -> incident elements (positions in `elems`), CSR
@@ -197,7 +222,7 @@ void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const P
         key[e] = {k, (int32_t)e};
       }
     });
-    std::sort(key.begin(), key.end());
+    parallel_sort(key);
     for (int64_t i = 0; i < ne; i++) rank[key[i].second] = (int32_t)i;
   }
   clk.tick("Morton ranks");
@@ -215,7 +240,7 @@ void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const P
       key.emplace_back(best, (int32_t)i);
       max_inc = std::max<int>(max_inc, (int)(nptr[i + 1] - nptr[i]));
     }
-    std::sort(key.begin(), key.end());
+    parallel_sort(key);
     order.reserve(key.size());
     for (auto& k : key) {
       pos[k.second] = (int32_t)order.size();
@@ -482,7 +507,7 @@ void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const P
     G.n_sources += O.sources;
   }
   G.n_staged = tet_ptr[npatch];
-  G.blob.assign((size_t)blob_total, 0);
+  G.blob.resize((size_t)blob_total);  // (padding bytes between the sections stay uninitialised: never read)
   G.gvtx.resize(pv_total);
   G.dest.resize((size_t)wb_total * npk * 32);
   G.res.resize((size_t)chunk_total * 32);

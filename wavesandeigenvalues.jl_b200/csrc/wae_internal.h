@@ -185,12 +185,31 @@ struct PhaseTimer {
 void wae_build_pattern_from_elements(const uint32_t* conn, int nloc, const std::vector<int64_t>& elems,
                                      int64_t dim, Pattern& P);
 void wae_build_slotmap(const uint32_t* conn, int nloc, const Pattern& P, std::vector<int32_t>& slotmap);
+// std::vector whose resize() leaves trivially constructible elements uninitialised (multi-GB program arrays that are fully
+// overwritten right after: no zero-fill pass)
+template <class T>
+struct default_init_alloc : std::allocator<T> {
+  template <class U>
+  struct rebind {
+    using other = default_init_alloc<U>;
+  };
+  template <class U, class... A>
+  void construct(U* p, A&&... a) {
+    if constexpr (sizeof...(A) == 0)
+      ::new ((void*)p) U;
+    else
+      ::new ((void*)p) U(std::forward<A>(a)...);
+  }
+};
+template <class T>
+using raw_vector = std::vector<T, default_init_alloc<T>>;
+
 struct GatherHost {
   std::vector<int64_t> desc;     // 8 words per patch: blob offset (bytes), pxyz offset (doubles), first 32-element block, first chunk,
                                  // then 8 x int32: nt, nv, ng, nc, blob bytes, offsets of the tets / grp / cnt sections
-  std::vector<uint8_t> blob;
-  std::vector<uint32_t> gvtx, dest;
-  std::vector<uint16_t> res;
+  raw_vector<uint8_t> blob;
+  raw_vector<uint32_t> gvtx, dest;
+  raw_vector<uint16_t> res;
   int n_patch = 0, max_slots = 0, max_blob = 0, max_nv = 0, npk = 0;
   int64_t n_pairs = 0, n_sources = 0, n_staged = 0;
 };
