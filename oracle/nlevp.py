@@ -257,6 +257,24 @@ def multinomcoeff(mu):
     return math.factorial(sum(mu)) / math.prod(math.factorial(m) for m in mu)
 
 
+class _LstsqSolver:
+    def __init__(self, A):
+        self.A = sp.csc_matrix(A).toarray()
+
+    def solve(self, b):
+        return np.linalg.lstsq(self.A, b, rcond=None)[0]
+
+
+def _factor_singular(A):
+    """lu(L(0,0), check=false) with the QR fallback of perturbation.jl:329-332: L(0,0) is singular by construction; SuperLU raises on
+    an exactly singular pivot (tiny dense examples) where UMFPACK reports a status -- then a least-squares solve stands in for SPQR
+    (the null-space component of the solution is projected out right after, perturbation.jl:361)."""
+    try:
+        return spla.splu(sp.csc_matrix(A))
+    except RuntimeError:
+        return _LstsqSolver(A)
+
+
 def perturb(L, N, v0, v0Adj):
     """perturbation.jl:319-367: Taylor coefficients of the auxiliary eigenvalue."""
     v0 = v0 / np.sqrt(np.vdot(v0, v0))
@@ -265,7 +283,7 @@ def perturb(L, N, v0, v0Adj):
     lam = np.zeros(N + 1, dtype=complex)
     v = [None] * (N + 1)
     v[0] = v0
-    L00 = spla.splu(sp.csc_matrix(L(0, 0)))
+    L00 = _factor_singular(L(0, 0))
     for k in range(1, N + 1):
         r = np.zeros(len(v0), dtype=complex)
         for n in range(1, k + 1):
@@ -477,6 +495,25 @@ def householder_update(f):
 
 
 def _eigs(A, M, nev, v0):
+    """Arpack.eigs(A, M; nev, sigma=0, v0) (Householder.jl:100-101, iterative_solvers.jl:132-133).  For the tiny dense examples of
+    tutorial_00 (dimension 3) scipy's ARPACK wrapper cannot build a Krylov space of the default ncv = 20 and fails where Arpack.jl
+    succeeds; there the generalised eigenproblem is solved densely and the nev eigenvalues of smallest modulus are returned."""
+    if A.shape[0] <= 20:
+        import scipy.linalg as sla
+        lam, v = sla.eig(sp.csc_matrix(A).toarray(), sp.csc_matrix(M).toarray())
+        lam = np.where(np.isfinite(lam), lam, np.inf)
+        idx = np.argsort(np.abs(lam), kind="stable")[:nev]
+        lam_s, v_s = lam[idx], v[:, idx].astype(complex)
+        # a degenerate eigenvalue: the Krylov method returns the component of the start vector in the eigenspace, not an arbitrary
+        # basis vector of it (matters for T(0) = I of tutorial_00, where all three auxiliary eigenvalues coincide)
+        for i in range(len(idx)):
+            cluster = np.flatnonzero(np.abs(lam - lam_s[i]) <= 1e-8 * max(1.0, abs(lam_s[i])))
+            if len(cluster) > 1 and v0 is not None:
+                Vc = v[:, cluster]
+                proj = Vc @ np.linalg.lstsq(Vc, np.asarray(v0, dtype=complex), rcond=None)[0]
+                if np.linalg.norm(proj) > 1e-12 * np.linalg.norm(v0):
+                    v_s[:, i] = proj / np.linalg.norm(proj)
+        return lam_s, v_s
     lam, v = spla.eigs(sp.csc_matrix(A), k=nev, M=sp.csc_matrix(M), sigma=0, v0=v0, tol=0)
     idx = np.argsort(np.abs(lam), kind="stable")
     return lam[idx], v[:, idx]
@@ -557,6 +594,9 @@ def householder(L, z, maxiter=10, tol=0.0, relax=1.0, lam_tol=float("inf"), orde
 
 
 def mslp(L, z, maxiter=10, tol=0.0, relax=1.0, lam_tol=float("inf"), order=1, nev=1, v0=None, v0_adj=None, num_order=1, scale=1, trace=None):
+    if L.terms[-1].operator != "__aux__":  # iterative_solvers.jl:119-123: a generic family gets the auxiliary term -I * __aux__
+        L.push(Term(-sp.identity(L.size(), dtype=complex, format="csc"), (pow1,), (("__aux__",),), "__aux__", "__aux__"))
+        L.auxval = "__aux__"
     sol, n, z, z0, lam = _iterate(L, z * scale, maxiter, tol * scale, relax, order, nev, v0, v0_adj, "mslp", num_order, trace=trace)
     if n >= maxiter:
         flag = 1

@@ -146,3 +146,34 @@ def test_perturb_fast_golden_at_g1(rijke):
     w = solution_eval(sol, "τ", 0.001 + 1e-5, 20, 0)
     assert abs(w - G10_APPROX_20) <= 1e-11 * abs(w)
     assert abs(w - G_HOUSEHOLDER[1][1]) <= 1e-10 * abs(w)  # G2: the exact eigenvalue at tau = 1.01 ms
+
+
+def _qep1():
+    """Quadratic eigenvalue problem 1 of the NLEVP collection as in docs/src/tutorial_00_NLEVP.md:28-43."""
+    import scipy.sparse as sp
+    from oracle.nlevp import LinearOperatorFamily, Term, pow1, pow2
+    A2 = np.array([[0, 6, 0], [0, 6, 0], [0, 0, 1]], dtype=complex)
+    A1 = np.array([[1, -6, 0], [2, -7, 0], [0, 0, 0]], dtype=complex)
+    T = LinearOperatorFamily()
+    T.push(Term(sp.csc_matrix(A2), (pow2,), (("λ",),), "λ^2", "A2"))
+    T.push(Term(sp.csc_matrix(A1), (pow1,), (("λ",),), "λ", "A1"))
+    T.push(Term(sp.identity(3, dtype=complex, format="csc"), (), (), "", "A0"))
+    return T
+
+
+def test_generic_nlevp_tutorial_00():
+    """tutorial_00_NLEVP.md:144 (mslp(T, 0): eigenvalue 1/3, ten iterations, warning flag 1 = maxiter) and :282-286 (Beyn on the
+    square +-2 +-2i with l = 6 finds the 5 eigenvalues inside: 1/3, 1/2, 1, +-i).  A generic family gets the auxiliary term
+    -I * __aux__ (iterative_solvers.jl:119-123)."""
+    T = _qep1()
+    sol, n, flag = mslp(T, 0, maxiter=10)
+    assert (n, flag) == (10, 1) and abs(sol.params["λ"] - 1 / 3) < 1e-12
+    assert T.terms[-1].operator == "__aux__" and T.auxval == "__aux__"
+    Om, P = beyn(_qep1(), [2 + 2j, -2 + 2j, -2 - 2j, 2 - 2j], l=6, N=64)
+    exact = np.array([1 / 3, 0.5, 1.0, 1j, -1j])
+    assert len(Om) == 5
+    for z in exact:
+        assert np.abs(Om - z).min() < 1e-9
+    for i, lam in enumerate(Om):  # residual check of the tutorial
+        v = P[:, i] / np.linalg.norm(P[:, i])
+        assert np.linalg.norm(_qep1()(lam) @ v) < 1e-8
