@@ -371,3 +371,47 @@ def extend_mesh(mesh, doms, sym_name="Symmetry", blch_name="Bloch", unit=False):
     d.naxis_ln, d.nxbloch_ln, d.nxsector_ln, d.unit, d.n, d.p = naxis_ln, nxbloch_ln, nxsector_ln, unit, n, p0
     out.dos = d
     return out
+
+
+def octosplit(mesh):
+    """Meshutils.jl:589-747: every tetrahedron into 8, every triangle into 4 (loop restatement, 0-based)."""
+    lmap = mesh.collect_lines()
+    npts = mesh.points.shape[1]
+    pts = np.zeros((3, npts + len(mesh.lines)))
+    pts[:, :npts] = mesh.points
+    for i, ln in enumerate(mesh.lines):
+        pts[:, npts + i] = mesh.points[:, ln].sum(axis=1) / 2
+    mid = lambda a, b: npts + lmap[simplex_key((a, b))]
+
+    def children(tet):
+        A, B, C, D = tet
+        AB, AC, AD, BC, BD, CD = mid(A, B), mid(A, C), mid(A, D), mid(B, C), mid(B, D), mid(C, D)
+        out = [[A, AB, AC, AD], [B, AB, BC, BD], [C, AC, BC, CD], [D, AD, BD, CD]]
+        ab_cd = np.linalg.norm(pts[:, AB] - pts[:, CD])
+        ac_bd = np.linalg.norm(pts[:, AC] - pts[:, BD])
+        ad_bc = np.linalg.norm(pts[:, AD] - pts[:, BC])
+        if ab_cd <= ac_bd and ab_cd <= ad_bc:
+            out += [[AB, CD, AC, AD], [AB, CD, AD, BD], [AB, CD, BD, BC], [AB, CD, BC, AC]]
+        elif ac_bd <= ab_cd and ac_bd <= ad_bc:
+            out += [[AC, BD, AB, AD], [AC, BD, AD, CD], [AC, BD, CD, BC], [AC, BD, BC, AB]]
+        else:
+            out += [[AD, BC, AC, CD], [AD, BC, CD, BD], [AD, BC, BD, AB], [AD, BC, AB, AC]]
+        return out
+
+    def tri_children(t):
+        A, B, C = t
+        AB, AC, BC = mid(A, B), mid(A, C), mid(B, C)
+        return [[A, AB, AC], [B, AB, BC], [C, AC, BC], [AB, AC, BC]]
+
+    tet_kids = [children(t) for t in mesh.tetrahedra]
+    tri_kids = [tri_children(t) for t in mesh.triangles]
+    tets, tetmap = unique_sorted([k for ks in tet_kids for k in ks])
+    tris, trimap = unique_sorted([k for ks in tri_kids for k in ks])
+    domains = {}
+    for dom, d in mesh.domains.items():
+        kids, mp = (tet_kids, tetmap) if d["dimension"] == 3 else (tri_kids, trimap)
+        domains[dom] = {"dimension": d["dimension"], "simplices": sorted(mp[simplex_key(k)] for s in d["simplices"] for k in kids[s])}
+    out = Mesh.__new__(Mesh)
+    out.name = mesh.name
+    out.points, out.lines, out.triangles, out.tetrahedra, out.domains, out.tri2tet = pts, [], tris, tets, domains, None
+    return out

@@ -269,3 +269,46 @@ def test_bench_reference_arm_contract():
     assert d["value"] > 0 and d["steps"] == 1 and d["vs_baseline"] is None
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+@pytest.mark.parametrize("name,scale", [("rijke_mm", 0.001), ("ntnu_12", 1.0)])
+def test_octosplit_matches_oracle(name, scale):
+    """octosplit (Meshutils.jl:589-747): the vectorised product against the loop restatement -- points, sorted child lists,
+    domain relabelling -- plus the size-independent properties: 8x / 4x counts, volume and surface area conserved, children
+    of a boundary triangle are faces of exactly one child tetrahedron, and the refined mesh is conforming."""
+    raw = load_raw_mesh(name)
+    mg, mo = W.Mesh("m", scale=scale, raw=raw), omesh.Mesh("m", scale=scale, raw=raw)
+    sg, so = W.octosplit(mg), omesh.octosplit(mo)
+    assert np.array_equal(sg.points, so.points)
+    assert np.array_equal(sg.tetrahedra, np.array(so.tetrahedra)) and np.array_equal(sg.triangles, np.array(so.triangles))
+    assert len(sg.tetrahedra) == 8 * len(mg.tetrahedra) and len(sg.triangles) == 4 * len(mg.triangles)
+    assert sg.points.shape[1] == mg.points.shape[1] + len(mg.lines)
+    assert np.array_equal(sg.points[:, : mg.points.shape[1]], mg.points)
+    for dom, d in so.domains.items():
+        assert list(sg.domains[dom]["simplices"]) == list(d["simplices"]), dom
+    for dom, d in mg.domains.items():
+        if d["dimension"] in (2, 3) and len(d["simplices"]):
+            a, b = mg.compute_size(dom), sg.compute_size(dom)
+            assert abs(a - b) <= 1e-12 * a, dom
+    # conforming: every face belongs to one (boundary) or two (interior) tetrahedra, boundary faces = the triangles of the surface
+    t = sg.tetrahedra
+    faces = np.sort(np.concatenate([t[:, [0, 1, 2]], t[:, [0, 1, 3]], t[:, [0, 2, 3]], t[:, [1, 2, 3]]]), axis=1)
+    uf, cnt = np.unique(faces, axis=0, return_counts=True)
+    assert cnt.max() == 2
+    t2t = sg.link_triangles_to_tetrahedra()
+    assert (t2t >= 0).all()
+    # second level: the numbering rules hold on the refined mesh as well (P2 DOFs of the split mesh)
+    tg, tt, dim = W.aggregate_elements(sg, "quad")
+    assert dim == sg.points.shape[1] + len(sg.lines) and tt.max() == dim - 1
+
+
+def test_octosplit_tie_break_and_empty_surface():
+    """Regular tetrahedron: all three inner diagonals have equal length, the reference takes AB-CD (first branch, '<=')."""
+    pts = np.array([[1.0, 1, -1, -1], [1, -1, 1, -1], [1, -1, -1, 1]])
+    dom = {"A": {"dimension": 3, "simplices": [0]}}
+    mg, mo = W.Mesh("x", raw=(pts, [], [], [[0, 1, 2, 3]], dom)), omesh.Mesh("x", raw=(pts, [], [], [[0, 1, 2, 3]], dom))
+    sg, so = W.octosplit(mg), omesh.octosplit(mo)
+    assert np.array_equal(sg.tetrahedra, np.array(so.tetrahedra)) and len(sg.triangles) == 0
+    ab, cd = 4 + mg.edge_index(np.array([0]), np.array([1]))[0], 4 + mg.edge_index(np.array([2]), np.array([3]))[0]
+    assert sum(1 for t in sg.tetrahedra if ab in t and cd in t) == 4
+    assert list(sg.domains["A"]["simplices"]) == list(range(8))

@@ -547,3 +547,46 @@ def extend_mesh(mesh, doms, sym_name="Symmetry", blch_name="Bloch", unit=False):
     out.dos = d if unit else 1
     out.sym_info = d
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# octosplit: uniform refinement, every tetrahedron -> 8 (src/Meshutils.jl:589-747), vectorised
+# ---------------------------------------------------------------------------------------------
+def octosplit(mesh):
+    """Split every edge at its centre: 8 tetrahedra per tetrahedron (the inner octahedron is cut along its shortest diagonal, ties in
+    the reference's order AB-CD, AC-BD, AD-BC), 4 triangles per triangle; the first N points of the new mesh are the old points, the
+    edge midpoints follow in the order of mesh.lines; domains hold the (sorted) children of their simplices."""
+    mesh.collect_lines()
+    npts = mesh.points.shape[1]
+    lines, tet, tri = mesh.lines, mesh.tetrahedra, mesh.triangles
+    pts = np.concatenate([mesh.points, 0.5 * (mesh.points[:, lines[:, 0]] + mesh.points[:, lines[:, 1]])], axis=1)
+    A, B, Cc, D = tet.T
+    AB, AC, AD, BC, BD, CD = (mesh._edge_of + npts).T
+    d1 = np.linalg.norm(pts[:, AB] - pts[:, CD], axis=0)
+    d2 = np.linalg.norm(pts[:, AC] - pts[:, BD], axis=0)
+    d3 = np.linalg.norm(pts[:, AD] - pts[:, BC], axis=0)
+    c1 = (d1 <= d2) & (d1 <= d3)
+    c2 = ~c1 & (d2 <= d1) & (d2 <= d3)
+    sel = lambda x, y, z: np.where(c1, x, np.where(c2, y, z))
+    P, Q = sel(AB, AC, AD), sel(CD, BD, BC)  # the chosen diagonal
+    ring = [(sel(AC, AB, AC), sel(AD, AD, CD)), (sel(AD, AD, CD), sel(BD, CD, BD)),
+            (sel(BD, CD, BD), sel(BC, BC, AB)), (sel(BC, BC, AB), sel(AC, AB, AC))]
+    kids = [np.stack([A, AB, AC, AD], axis=1), np.stack([B, AB, BC, BD], axis=1), np.stack([Cc, AC, BC, CD], axis=1),
+            np.stack([D, AD, BD, CD], axis=1)] + [np.stack([P, Q, r0, r1], axis=1) for r0, r1 in ring]
+    tets = np.stack(kids, axis=1).reshape(-1, 4)  # child k of tet i at 8 i + k
+    if len(tri):
+        a, b, c = tri.T
+        ab, ac, bc = (mesh.edge_index(a, b) + npts, mesh.edge_index(a, c) + npts, mesh.edge_index(b, c) + npts)
+        tris = np.stack([np.stack([a, ab, ac], axis=1), np.stack([b, ab, bc], axis=1), np.stack([c, ac, bc], axis=1),
+                         np.stack([ab, ac, bc], axis=1)], axis=1).reshape(-1, 3)
+    else:
+        tris = np.zeros((0, 3), dtype=np.int64)
+    domains = {}
+    for dom, d in mesh.domains.items():
+        s = np.asarray(d["simplices"], dtype=np.int64)
+        k = 8 if d["dimension"] == 3 else 4
+        domains[dom] = {"dimension": d["dimension"], "simplices": (s[:, None] * k + np.arange(k)[None, :]).ravel()}
+    new = Mesh(mesh.file, raw=(pts, np.zeros((0, 2), dtype=np.int64), tris, tets, domains))
+    for d in new.domains.values():
+        d["simplices"] = np.sort(d["simplices"])
+    return new
