@@ -178,6 +178,33 @@ int32_t wae_beyn_moments(wae_ctx* h, int32_t fam_id, int32_t lu_id, int32_t n_no
                          int32_t l, int32_t n_mom, const double* V /* dim x l complex host array, NULL = identity columns */,
                          void* A_out_device);
 
+/* ---- discrete-adjoint shape sensitivity ------------------------------------------------
+ * Replaces the loop of discrete_adjoint_shape_sensitivity (src/shape_sensitivity.jl:16-141; non-unit meshes): per surface
+ * point and coordinate the reference calls discretize() twice on a mesh whose domains are cut down to the simplices touching
+ * the point (:50-69,:111,:120) and evaluates  sens = -v_adj' * (D_right(w0) - D_left(w0)) / (2h) * v  (:125,:129).  Here one
+ * kernel thread per (point, coordinate) evaluates the element matrices of those simplices at the two positions and contracts
+ * the difference with the eigenvectors; no matrix is formed.  First-order meshes only (the reference's call has no `order`).
+ *   begin: n_sp moved points (context index base), step h, v and v_adj (dim complex, normalised by the caller, :21-25).
+ *   add:   one descriptor term.  ptr (n_sp+1, 0-based offsets) / elems (context index base): for every moved point the
+ *          simplices of the term's domain that touch it (tet_mask / tri_mask cut with the domain, :50-69), tetrahedra for
+ *          MASS / STIFF / FLAME, triangles for BOUNDARY; c: speed of sound per list entry (c_per_elem 1, or 4 / 3 vertex
+ *          values) for STIFF / BOUNDARY; coef: the term's scalar at w0 (one complex number: w0^2, 1, w0*Y, n*exp(-i w0 tau));
+ *          FLAME: ref_tet, n_ref and nl = (gamma-1)/rho*nglobal -- the kernel divides by the volume of the listed flame
+ *          tetrahedra, which is what compute_size! returns on the reduced domain (Helmholtz.jl:325).
+ *   end:   sens (3 x n_sp complex, column-major) = sum over the added terms.                                              */
+enum { WAE_SENS_MASS = 1, WAE_SENS_STIFF = 2, WAE_SENS_BOUNDARY = 3, WAE_SENS_FLAME = 4 };
+int32_t wae_shape_sens_begin(wae_ctx* h, int64_t n_sp, const int64_t* points, double step, const double* v, const double* v_adj);
+int32_t wae_shape_sens_add(wae_ctx* h, int32_t kind, const int64_t* ptr, const int64_t* elems, const double* c, int32_t c_per_elem,
+                           const double* coef, int64_t ref_tet, const double* n_ref, double nl);
+int32_t wae_shape_sens_end(wae_ctx* h, double* sens);
+/* Host-only diagnostic (needs no GPU and no context; used by the CPU tests, never by the product path): the per-thread
+ * function of the kernel above evaluated in a plain host loop.  0-based indices, first-order connectivity (4 x n_tet,
+ * 3 x n_tri); ACCUMULATES one term into sens (3 x n_sp complex).                                                          */
+int32_t wae_shape_sens_check(int64_t n_pts, const double* xyz, int64_t n_tet, const uint32_t* tets, int64_t n_tri, const uint32_t* tris,
+                             int64_t n_sp, const int64_t* points, double step, const double* v, const double* v_adj, int32_t kind,
+                             const int64_t* ptr, const int64_t* elems, const double* c, int32_t c_per_elem, const double* coef,
+                             int64_t ref_tet, const double* n_ref, double nl, double* sens);
+
 #ifdef __cplusplus
 }
 #endif

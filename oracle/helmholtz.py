@@ -16,6 +16,12 @@ from .nlevp import (LinearOperatorFamily, Term, exp_az2mzit, exp_delay, generate
                     sigma_nexp_az2mzit)
 
 
+def _div(a, b):
+    """IEEE division (Julia: x/0.0 == Inf): an empty flame domain has size 0 (shape_sensitivity.jl:50-69 builds such domains)."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return float(np.float64(a) / np.float64(b))
+
+
 def _sparse(I, J, V, dim):
     """SparseArrays.sparse(I,J,V,dim,dim): duplicates summed, explicit zeros kept."""
     return sp.csc_matrix(sp.coo_matrix((np.asarray(V, dtype=complex), (I, J)), shape=(dim, dim)))
@@ -127,7 +133,7 @@ def discretize(mesh, dscrp, C, order="lin", mass_weighting=True, triplets=None, 
         elif typ == "fancyflame":  # Helmholtz.jl:363-400
             make = ["Q"]
             gamma, rho, nglobal, x_ref, n_ref, n_sym, tau_sym, a_sym, n_val, tau_val, a_val = data
-            nlocal = (gamma - 1) / rho * nglobal / mesh.compute_size(domain)
+            nlocal = _div((gamma - 1) / rho * nglobal, mesh.compute_size(domain))
             if isinstance(n_val, (int, float, complex)):
                 for sym_, val_ in ((n_sym, n_val), (tau_sym, tau_val), (a_sym, a_val)):
                     L.params.setdefault(sym_, complex(val_))
@@ -152,7 +158,7 @@ def discretize(mesh, dscrp, C, order="lin", mass_weighting=True, triplets=None, 
                 ref_idx = -1
             else:
                 raise NotImplementedError("flame descriptor variant")
-            nlocal = (gamma - 1) / rho * nglobal / mesh.compute_size(domain)
+            nlocal = _div((gamma - 1) / rho * nglobal, mesh.compute_size(domain))
             if typ == "flame":
                 L.params.setdefault(n_sym, complex(n_val))
                 L.params.setdefault(tau_sym, complex(tau_val))

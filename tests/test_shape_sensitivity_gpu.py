@@ -1,0 +1,54 @@
+"""GPU parity of the discrete-adjoint shape sensitivity (src/shape_sensitivity.jl:16-141) through the C ABI
+(wae_shape_sens_begin / _add / _end): the set-up of examples/shape/tutorial_09_shape_sensitivity.jl on the Rijke mesh against the
+oracle's literal loop and against the host replay of the same per-thread function.
+
+NOTE (round 1): written after the round's GPU budget was spent -- the kernel's per-thread function is verified on the host
+(tests/test_shape_sensitivity.py), this launch path has not run on a B200 yet."""
+import math
+
+import numpy as np
+import pytest
+
+from cases import GAMMA, N_REF, Q02U0, RHO, X_REF, load_raw_mesh, speedofsound
+
+pytestmark = pytest.mark.gpu
+
+
+def test_shape_sensitivity_matches_oracle_and_host_replay():
+    import wae_b200 as W
+    from oracle import helmholtz as ohelm
+    from oracle import mesh as omesh
+    from oracle import nlevp as onlevp
+    from oracle import shape as oshape
+    from test_shape_sensitivity import _normalised, host_replay
+
+    raw = load_raw_mesh("rijke_mm")
+    mg, mo = W.Mesh("m", scale=0.001, raw=raw), omesh.Mesh("m", scale=0.001, raw=raw)
+    c = mg.generate_field(speedofsound)
+    ref_idx = mg.find_tetrahedron_containing_point(X_REF)
+    dscrp = {"Interior": ("interior", ()), "Outlet": ("admittance", ("Y", 1e15)),
+             "Flame": ("flame", (GAMMA, RHO, Q02U0, ref_idx, X_REF, N_REF, "n", "τ", 1.0, 0.001))}
+    L = W.discretize(mg, dscrp, c)
+    sol, n, flag = W.householder(L, 700 * 2 * math.pi, maxiter=14, tol=1e-11, output=False)
+    assert flag == 1
+    sp_, trm, ttm = W.get_surface_points(mg)
+    launches = L.device().ctx.launch_count()
+    sens = W.discrete_adjoint_shape_sensitivity(mg, dscrp, c, sp_, trm, ttm, L, sol, h=1e-9)
+    assert L.device().ctx.launch_count() - launches >= 4  # M, K, C, Q passes (+ the combine / SpMV of the normalisation)
+
+    Lo = ohelm.discretize(mo, dscrp, c)
+    solo, _, flo = onlevp.householder(Lo, 700 * 2 * math.pi, maxiter=14, tol=1e-11)
+    assert abs(solo.params["ω"] - sol.params["ω"]) <= 1e-10 * abs(solo.params["ω"])
+    so, tro, tto = oshape.get_surface_points(mo)
+    want = oshape.discrete_adjoint_shape_sensitivity(mo, dscrp, c, so, tro, tto, Lo, solo)
+    scale = np.abs(want).max()
+    assert np.abs(sens - want).max() <= 1e-5 * scale
+    # same inputs through the host replay of the kernel's per-thread function: identical arithmetic up to FMA contraction
+    w0, v0, va = _normalised(Lo, solo)
+    rep = host_replay(mg, dscrp, c, sp_, trm, ttm, w0, v0, va)
+    assert np.abs(sens - rep).max() <= 1e-5 * scale
+    # the product's own eigenvectors through the replay: the launch path itself (indexing, accumulation over the four terms)
+    v0g = sol.v / np.sqrt(np.vdot(sol.v, sol.v))
+    vag = sol.v_adj / np.conj(np.vdot(sol.v_adj, L(sol.params["ω"], 1) @ v0g))
+    rep_g = host_replay(mg, dscrp, c, sp_, trm, ttm, sol.params["ω"], v0g, vag)
+    assert np.abs(sens - rep_g).max() <= 1e-7 * scale

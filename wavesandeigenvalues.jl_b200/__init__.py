@@ -13,6 +13,8 @@ from .nlevp import (bloch_expand, conv_radius, LinearOperatorFamily, Solution, T
                     get_context, householder, inpoly, moments2eigs, mslp, pade_bang, perturb_bang, perturb_fast_bang, perturb_norm_bang, pow0,
                     pow1, pow2, pow_a,
                     reset_context, wn)
+from .shape import (bound_mass_normalize, discrete_adjoint_shape_sensitivity, get_normal_vectors, get_surface_points,  # noqa: F401
+                    normal_sensitivity, normalize_sensitivity)
 
 __all__ = ["Mesh", "discretize", "LinearOperatorFamily", "Term", "Solution", "householder", "mslp", "beyn", "pow0", "pow1",
            "pow2", "exp_delay", "kuhn_box", "aggregate_elements", "get_context"]

@@ -76,7 +76,13 @@ SIGNATURES = {
     "wae_lu_solve": (_i32, [_vp, _i32, _i32, _i32, _pd]),
     "wae_eigs_si": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _pd, _pd, _pd, _pi32]),
     "wae_beyn_moments": (_i32, [_vp, _i32, _i32, _i32, _pd, _pd, _pd, _i32, _i32, _pd, _vp]),
+    "wae_shape_sens_begin": (_i32, [_vp, _i64, _pi64, _dbl, _pd, _pd]),
+    "wae_shape_sens_add": (_i32, [_vp, _i32, _pi64, _pi64, _pd, _i32, _pd, _i64, _pd, _dbl]),
+    "wae_shape_sens_end": (_i32, [_vp, _pd]),
 }
+# host-only diagnostics (no context, no GPU): used by the CPU tests, never by the product path
+HOST_DIAGNOSTICS = ("wae_lu_symbolic_stats", "wae_pair_program_check", "wae_shape_sens_check")
+SENS_MASS, SENS_STIFF, SENS_BOUNDARY, SENS_FLAME = 1, 2, 3, 4
 
 
 def _declare(l):
@@ -288,3 +294,28 @@ class Context:
         if V is not None:
             V = np.asfortranarray(V, dtype=np.complex128)
         self._chk(self._l.wae_beyn_moments(self.h, fid, lid, len(z), _p(z, _pd), _p(w, _pd), _p(cf, _pd), l, n_mom, _p(V, _pd), _vp(out_ptr)))
+
+    # -- shape sensitivity -----------------------------------------------------------------------
+    def shape_sens_begin(self, points, step, v, v_adj):
+        pts = np.ascontiguousarray(points, dtype=np.int64)
+        v = np.ascontiguousarray(v, dtype=np.complex128)
+        va = np.ascontiguousarray(v_adj, dtype=np.complex128)
+        self._chk(self._l.wae_shape_sens_begin(self.h, len(pts), _p(pts, _pi64), float(step), _p(v, _pd), _p(va, _pd)))
+        self._sens_n = len(pts)
+
+    def shape_sens_add(self, kind, ptr, elems, coef, c=None, ref_tet=0, n_ref=None, nl=0.0):
+        ptr = np.ascontiguousarray(ptr, dtype=np.int64)
+        elems = np.ascontiguousarray(elems, dtype=np.int64)
+        cpe = 1
+        if c is not None:
+            c = np.ascontiguousarray(c, dtype=np.float64)
+            cpe = 1 if c.ndim == 1 else c.shape[1]
+        cf = np.array([complex(coef)], dtype=np.complex128)
+        nr = None if n_ref is None else np.ascontiguousarray(n_ref, dtype=np.float64)
+        self._chk(self._l.wae_shape_sens_add(self.h, kind, _p(ptr, _pi64), _p(elems, _pi64), _p(c, _pd), cpe, _p(cf, _pd), int(ref_tet),
+                                             _p(nr, _pd), float(nl)))
+
+    def shape_sens_end(self):
+        out = np.empty((self._sens_n, 3), dtype=np.complex128)  # == 3 x n_sp column-major
+        self._chk(self._l.wae_shape_sens_end(self.h, _p(out, _pd)))
+        return out.T

@@ -127,6 +127,7 @@ struct Family {
 };
 
 struct LuSolver;  // lu_symbolic.h
+struct WaeShapeSens;  // shape_sens.cu
 
 struct wae_ctx {
   int device = 0;
@@ -152,6 +153,7 @@ struct wae_ctx {
   std::vector<std::unique_ptr<Matrix>> mats;
   std::vector<std::unique_ptr<Family>> fams;
   std::vector<std::shared_ptr<LuSolver>> lus;  // shared_ptr: LuSolver is incomplete here
+  std::shared_ptr<WaeShapeSens> shape;         // state of a wae_shape_sens_begin/add/end sequence
 
   Pattern& pat(int id) {
     if (id < 0 || id >= (int)patterns.size() || !patterns[id]) WAE_THROW(WAE_E_INVALID, "unknown pattern id %d", id);
