@@ -267,7 +267,11 @@ def test_bench_reference_arm_contract():
     d = json.loads(line)
     assert d["impl"] == "reference" and d["unit"] == "eigenpairs/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["steps"] == 1 and d["vs_baseline"] is None
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    # the value is the sample scaled to the full workload (config 2), phase by phase, and says so
+    sc = d["cpu_baseline"]["scaling"]
+    assert d["cpu_baseline"]["extrapolated"] is True and sc["growth"]["factor_flops"] > sc["growth"]["factor_nnz"] > sc["growth"]["tets"] > 1
+    assert abs(d["value"] * sc["estimated_full_size_s"] - 1) < 1e-12 and d["value"] < sc["sample_eigenpairs_per_s"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
 
 
