@@ -184,7 +184,13 @@ int32_t wae_beyn_moments(wae_ctx* h, int32_t fam_id, int32_t lu_id, int32_t n_no
  * the point (:50-69,:111,:120) and evaluates  sens = -v_adj' * (D_right(w0) - D_left(w0)) / (2h) * v  (:125,:129).  Here one
  * kernel thread per (point, coordinate) evaluates the element matrices of those simplices at the two positions and contracts
  * the difference with the eigenvectors; no matrix is formed.  First-order meshes only (the reference's call has no `order`).
- *   begin: n_sp moved points (context index base), step h, v and v_adj (dim complex, normalised by the caller, :21-25).
+ *   begin: n_sp moved points (context index base), step h, v and v_adj (vdim complex, normalised by the caller, :21-25).
+ *          Unit-cell meshes (:84-118; b = :b evaluated at params[b] = 1): cylindrical != 0 moves every point along its local
+ *          cylindrical basis (get_cylindrics, :361-370), partner[s] (or < base: none) is the image of a Bloch-plane point that
+ *          moves with it, dof_new / dof_flag (per mesh point: folded DOF, bit 0 image, bit 1 axis -- the arrays given to
+ *          wae_assemble_bloch) fold the DOFs as blochify does, vdim is the folded dimension and phase = exp(i 2 pi / DOS);
+ *          entries touching an axis DOF are dropped (their class scalar delta(b) is 0 at b = 1) and the axis penalty term D is
+ *          not evaluated (both eigenvectors vanish there).  NULL for partner / dof_new / dof_flag / phase = plain mesh.
  *   add:   one descriptor term.  ptr (n_sp+1, 0-based offsets) / elems (context index base): for every moved point the
  *          simplices of the term's domain that touch it (tet_mask / tri_mask cut with the domain, :50-69), tetrahedra for
  *          MASS / STIFF / FLAME, triangles for BOUNDARY; c: speed of sound per list entry (c_per_elem 1, or 4 / 3 vertex
@@ -193,7 +199,9 @@ int32_t wae_beyn_moments(wae_ctx* h, int32_t fam_id, int32_t lu_id, int32_t n_no
  *          tetrahedra, which is what compute_size! returns on the reduced domain (Helmholtz.jl:325).
  *   end:   sens (3 x n_sp complex, column-major) = sum over the added terms.                                              */
 enum { WAE_SENS_MASS = 1, WAE_SENS_STIFF = 2, WAE_SENS_BOUNDARY = 3, WAE_SENS_FLAME = 4 };
-int32_t wae_shape_sens_begin(wae_ctx* h, int64_t n_sp, const int64_t* points, double step, const double* v, const double* v_adj);
+int32_t wae_shape_sens_begin(wae_ctx* h, int64_t n_sp, const int64_t* points, const int64_t* partner, double step, int32_t cylindrical,
+                             int64_t vdim, const double* v, const double* v_adj, const int64_t* dof_new, const uint8_t* dof_flag,
+                             const double* phase);
 int32_t wae_shape_sens_add(wae_ctx* h, int32_t kind, const int64_t* ptr, const int64_t* elems, const double* c, int32_t c_per_elem,
                            const double* coef, int64_t ref_tet, const double* n_ref, double nl);
 int32_t wae_shape_sens_end(wae_ctx* h, double* sens);
@@ -201,7 +209,8 @@ int32_t wae_shape_sens_end(wae_ctx* h, double* sens);
  * function of the kernel above evaluated in a plain host loop.  0-based indices, first-order connectivity (4 x n_tet,
  * 3 x n_tri); ACCUMULATES one term into sens (3 x n_sp complex).                                                          */
 int32_t wae_shape_sens_check(int64_t n_pts, const double* xyz, int64_t n_tet, const uint32_t* tets, int64_t n_tri, const uint32_t* tris,
-                             int64_t n_sp, const int64_t* points, double step, const double* v, const double* v_adj, int32_t kind,
+                             int64_t n_sp, const int64_t* points, const int64_t* partner, double step, int32_t cylindrical, const double* v,
+                             const double* v_adj, const int32_t* dof_new, const uint8_t* dof_flag, const double* phase, int32_t kind,
                              const int64_t* ptr, const int64_t* elems, const double* c, int32_t c_per_elem, const double* coef,
                              int64_t ref_tet, const double* n_ref, double nl, double* sens);
 

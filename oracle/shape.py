@@ -1,8 +1,8 @@
 """Oracle (test infrastructure): discrete-adjoint shape sensitivity, restated literally.
 
-  get_surface_points                    src/Meshutils.jl:884-966 (non-unit meshes)
+  get_surface_points                    src/Meshutils.jl:884-966
   get_normal_vectors                    src/Meshutils.jl:1030-1069
-  discrete_adjoint_shape_sensitivity    src/shape_sensitivity.jl:16-141 (non-unit meshes: b = :__none__)
+  discrete_adjoint_shape_sensitivity    src/shape_sensitivity.jl:16-141, get_cylindrics :361-370
   normalize_sensitivity                 src/shape_sensitivity.jl:149-184
   bound_mass_normalize                  src/shape_sensitivity.jl:191-229
   normal_sensitivity                    src/shape_sensitivity.jl:237-246
@@ -33,6 +33,25 @@ def get_surface_points(mesh):
         for p in tet:
             if int(p) in pos:
                 tet_mask[pos[int(p)]].append(it)
+    dos = getattr(mesh, "dos", 1)
+    if dos != 1 and dos.unit:  # Meshutils.jl:946-964 (the lists are indexed by POINT number there; 0-based here)
+        def unique_inplace(lst):
+            seen, out = set(), []
+            for x in lst:
+                if x not in seen:
+                    seen.add(x)
+                    out.append(x)
+            lst[:] = out
+        n = len(surface_points)
+        for idx in surface_points:
+            bidx = idx - dos.naxis  # 0-based: 0 <= bidx < nxbloch
+            if 0 <= bidx < dos.nxbloch:
+                img = n - dos.nxbloch + bidx
+                for mask in (tri_mask, tet_mask):
+                    mask[idx].extend(mask[img])
+                    unique_inplace(mask[idx])
+                    mask[img].extend(mask[idx])
+                    unique_inplace(mask[img])
     return surface_points, tri_mask, tet_mask
 
 
@@ -54,6 +73,9 @@ def _reduced_mesh(mesh, dscrp, tris, tets):
     m.name = "mesh_h"
     m.points = mesh.points.copy()
     m.lines, m.triangles, m.tetrahedra, m.tri2tet = mesh.lines, mesh.triangles, mesh.tetrahedra, mesh.tri2tet
+    m.dos = getattr(mesh, "dos", 1)
+    if hasattr(mesh, "_lmap"):
+        m._lmap = mesh._lmap
     m.domains = {}
     for dom in dscrp:
         d = copy.deepcopy(mesh.domains[dom])
@@ -61,6 +83,17 @@ def _reduced_mesh(mesh, dscrp, tris, tets):
         d["simplices"] = [s for s in d["simplices"] if s in keep]
         m.domains[dom] = d
     return m
+
+
+def get_cylindrics(pnt):
+    """shape_sensitivity.jl:361-370: columns = local radial, azimuthal, axial unit vectors."""
+    X = np.zeros((3, 3))
+    X[:, 2] = [0, 0, 1]
+    X[:, 0] = pnt
+    X[2, 0] = 0.0
+    X[:, 0] /= np.linalg.norm(X[:, 0])
+    X[:, 1] = np.cross(X[:, 2], X[:, 0])
+    return X
 
 
 def discrete_adjoint_shape_sensitivity(mesh, dscrp, C, surface_points, tri_mask, tet_mask, L, sol, h=1e-9):
@@ -71,16 +104,43 @@ def discrete_adjoint_shape_sensitivity(mesh, dscrp, C, surface_points, tri_mask,
     va = va / np.conj(np.vdot(va, L(w0, 1) @ v0))
     if mesh.tri2tet is None:
         mesh.link_triangles_to_tetrahedra()
-    sens = np.zeros((3, mesh.points.shape[1]), dtype=complex)
+    dos = getattr(mesh, "dos", 1)
+    unit = dos != 1 and dos.unit
+    b = "b" if unit else None
+    npts = mesh.points.shape[1]
+    sens = np.zeros((3, npts), dtype=complex)
     for idx, pnt_idx in enumerate(surface_points):
         mh = _reduced_mesh(mesh, dscrp, tri_mask[idx], tet_mask[idx])
         pnt = mh.points[:, pnt_idx].copy()
+        bloch = False
+        if unit:
+            if 0 <= pnt_idx - dos.naxis < dos.nxbloch:  # :86-91 identify the Bloch image point
+                pnt_bloch_idx = npts - dos.nxbloch + (pnt_idx - dos.naxis)
+                pnt_bloch = mesh.points[:, pnt_bloch_idx].copy()
+                bloch = True
+            elif pnt_idx < dos.naxis:  # :100-105 axis points are skipped
+                continue
         for crd in range(3):
             mh.points[:, pnt_idx] = pnt
-            mh.points[crd, pnt_idx] += h
-            D_right = discretize(mh, dscrp, C, mass_weighting=False)
-            mh.points[crd, pnt_idx] -= 2 * h
-            D_left = discretize(mh, dscrp, C, mass_weighting=False)
+            if unit:
+                X = get_cylindrics(pnt)
+                mh.points[:, pnt_idx] += h * X[:, crd]
+                if bloch:
+                    mh.points[:, pnt_bloch_idx] = pnt_bloch
+                    Xb = get_cylindrics(pnt_bloch)
+                    mh.points[:, pnt_bloch_idx] += h * Xb[:, crd]
+            else:
+                mh.points[crd, pnt_idx] += h
+            D_right = discretize(mh, dscrp, C, mass_weighting=False, b=b)
+            if unit:
+                mh.points[:, pnt_idx] -= 2 * h * X[:, crd]
+                if bloch:
+                    mh.points[:, pnt_bloch_idx] -= 2 * h * Xb[:, crd]
+            else:
+                mh.points[crd, pnt_idx] -= 2 * h
+            D_left = discretize(mh, dscrp, C, mass_weighting=False, b=b)
+            if unit:
+                D_right.params[b] = D_left.params[b] = 1 + 0j
             D = (D_right(w0) - D_left(w0)) / (2 * h)
             sens[crd, pnt_idx] = -np.vdot(va, D @ v0)
     return sens

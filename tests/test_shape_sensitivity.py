@@ -26,18 +26,34 @@ def host_replay(mesh, dscrp, c, surface_points, tri_mask, tet_mask, w0, v0, va, 
     """The product's host logic + the kernel's per-thread function on the host (test-only entry of the library)."""
     lib = C.CDLL(os.path.join(ROOT, "wavesandeigenvalues.jl_b200", "libwae_b200.so"))
     f = lib.wae_shape_sens_check
+    _pi32, _pu8 = C.POINTER(C.c_int32), C.POINTER(C.c_uint8)
     f.restype = C.c_int32
-    f.argtypes = [C.c_int64, _pd, C.c_int64, _pu32, C.c_int64, _pu32, C.c_int64, _pi64, C.c_double, _pd, _pd, C.c_int32, _pi64, _pi64, _pd,
-                  C.c_int32, _pd, C.c_int64, _pd, C.c_double, _pd]
+    f.argtypes = [C.c_int64, _pd, C.c_int64, _pu32, C.c_int64, _pu32, C.c_int64, _pi64, _pi64, C.c_double, C.c_int32, _pd, _pd, _pi32, _pu8, _pd,
+                  C.c_int32, _pi64, _pi64, _pd, C.c_int32, _pd, C.c_int64, _pd, C.c_double, _pd]
     xyz = np.ascontiguousarray(mesh.points.T, dtype=np.float64)
     tets = np.ascontiguousarray(mesh.tetrahedra, dtype=np.uint32)
     tris = np.ascontiguousarray(mesh.triangles, dtype=np.uint32)
+    npts = xyz.shape[0]
     pts = np.ascontiguousarray(surface_points, dtype=np.int64)
+    unit = shape._is_unit(mesh)
+    partner = dof_new = dof_flag = phase = None
+    if unit:  # the same preparation as discrete_adjoint_shape_sensitivity
+        from wae_b200.meshutils import bloch_dof_maps
+        d = mesh.dos
+        keep = np.flatnonzero(pts >= d.naxis)
+        pts = np.ascontiguousarray(pts[keep])
+        tri_mask, tet_mask = [tri_mask[k] for k in keep], [tet_mask[k] for k in keep]
+        partner = np.ascontiguousarray(np.where(pts < d.naxis + d.nxbloch, npts - d.nxbloch + (pts - d.naxis), -1), dtype=np.int64)
+        new, image, axis, red = bloch_dof_maps(mesh, "lin")
+        dof_new = np.ascontiguousarray(new, dtype=np.int32)
+        dof_flag = np.ascontiguousarray(image.astype(np.uint8) | (axis.astype(np.uint8) << 1))
+        phase = np.array([np.exp(2j * math.pi / d.DOS)])
+        assert len(v0) == red
     v0 = np.ascontiguousarray(v0, dtype=np.complex128)
     va = np.ascontiguousarray(va, dtype=np.complex128)
     out = np.zeros((len(pts), 3), dtype=np.complex128)
     P = lambda a, t: None if a is None else a.ctypes.data_as(t)
-    for term in shape.sensitivity_terms(mesh, dscrp, c, w0):
+    for term in shape.sensitivity_terms(mesh, dscrp, c, w0, bloch=unit):
         n_elem = len(tris) if term["dim"] == 2 else len(tets)
         ptr, elems, cc = shape.sensitivity_lists(term, n_elem, tri_mask, tet_mask)
         cpe = 1
@@ -46,11 +62,12 @@ def host_replay(mesh, dscrp, c, surface_points, tri_mask, tet_mask, w0, v0, va, 
             cpe = 1 if cc.ndim == 1 else cc.shape[1]
         coef = np.array([complex(term["coef"])])
         nref = None if "n_ref" not in term else np.ascontiguousarray(term["n_ref"], dtype=np.float64)
-        rc = f(xyz.shape[0], P(xyz, _pd), len(tets), P(tets, _pu32), len(tris), P(tris, _pu32), len(pts), P(pts, _pi64), h, P(v0, _pd), P(va, _pd),
+        rc = f(npts, P(xyz, _pd), len(tets), P(tets, _pu32), len(tris), P(tris, _pu32), len(pts), P(pts, _pi64), P(partner, _pi64), h, int(unit),
+               P(v0, _pd), P(va, _pd), P(dof_new, _pi32), P(dof_flag, _pu8), P(phase, _pd),
                term["kind"], P(ptr, _pi64), P(elems, _pi64), P(cc, _pd), cpe, P(coef, _pd), term.get("ref_tet", 0), P(nref, _pd),
                float(term.get("nl", 0.0)), P(out, _pd))
         assert rc == 0, (rc, term["kind"])
-    sens = np.zeros((3, mesh.points.shape[1]), dtype=np.complex128)
+    sens = np.zeros((3, npts), dtype=np.complex128)
     sens[:, pts] = out.T
     return sens
 
@@ -175,8 +192,45 @@ def test_post_processing_matches_oracle(rijke):
     assert np.abs(a2 - b2).max() <= 1e-10 * np.abs(b2).max()
 
 
-def test_unit_cell_meshes_are_rejected(rijke):
-    mg = rijke[0]
-    cell = W.kuhn_unit_cell((2, 2, 2), (0, 0, 0), (1, 1, 1), DOS=4)
-    with pytest.raises(NotImplementedError):
-        W.get_surface_points(cell)
+def test_unit_cell_variant_on_the_ntnu_combustor():
+    """shape_sensitivity.jl:84-118 on the reference's own annular-combustor mesh (docs/src/NTNU_12.msh -> extend_mesh(unit=true), 19 axis
+    points, 396 Bloch-plane points): cylindrical moves, Bloch-plane points moving with their images, blochified operators at b = 1.
+    The oracle re-discretises the unit cell six times per point (incl. the weighting matrix over all 8446 tetrahedra), so only a
+    handful of points of every kind is compared; the surface bookkeeping is compared for all 846 points."""
+    from oracle.mesh import extend_mesh as oext
+    from test_bloch import NTNU_DOMS, NTNU_DSCRP, _ntnu_meshes, _ntnu_sos
+    mg, mo = _ntnu_meshes()
+    doms = NTNU_DOMS + [("CC", "half")]
+    g, o = W.extend_mesh(mg, doms, unit=True), oext(mo, doms, unit=True)
+    sg, trg, ttg = W.get_surface_points(g)
+    so, tro, tto = oshape.get_surface_points(o)
+    assert list(sg) == so and all(list(a) == b for a, b in zip(trg, tro)) and all(list(a) == b for a, b in zip(ttg, tto))
+    c = o.generate_field(_ntnu_sos)
+    dscrp = dict(NTNU_DSCRP)
+    dscrp["Outlet_high"] = ("admittance", ("Y_in", 0.2 + 0.1j))  # a non-zero admittance so that the boundary term takes part
+    L = ohelm.discretize(o, dscrp, c, b="b")
+    L.params["b"] = 1 + 0j
+    sol, n, flag = onlevp.mslp(L, 1000.0, maxiter=20, tol=1e-10, scale=2 * math.pi)
+    assert flag == 0 and 500 < sol.params["ω"].real / 2 / math.pi < 1500  # one of the two b = 1 modes near 863 / 1124 Hz
+    w0, v0, va = _normalised(L, sol)
+    d = g.dos
+    npts = g.points.shape[1]
+    outlet = set(np.asarray(g.triangles)[g.domains["Outlet_high"]["simplices"]].ravel().tolist())
+    kinds = {"axis": [k for k, p in enumerate(sg) if p < d.naxis][:1],
+             "plane": [k for k, p in enumerate(sg) if d.naxis <= p < d.naxis + d.nxbloch][5:7],
+             "image": [k for k, p in enumerate(sg) if p >= npts - d.nxbloch][5:7],
+             "outlet": [k for k, p in enumerate(sg) if p in outlet and d.naxis + d.nxbloch <= p < npts - d.nxbloch][:2],
+             "body": [k for k, p in enumerate(sg) if d.naxis + d.nxbloch <= p < npts - d.nxbloch and p not in outlet][10:12]}
+    sub = sorted(k for ks in kinds.values() for k in ks)
+    assert all(len(v) > 0 for v in kinds.values())
+    pick = lambda lst: [lst[k] for k in sub]
+    got = host_replay(g, dscrp, c, sg[sub], pick(trg), pick(ttg), w0, v0, va)
+    want = oshape.discrete_adjoint_shape_sensitivity(o, dscrp, c, [so[k] for k in sub], pick(tro), pick(tto), L, sol)
+    scale = np.abs(want).max()
+    assert scale > 0 and np.abs(want[:, sg[kinds["axis"]]]).max() == 0  # axis points are skipped
+    assert np.abs(got - want).max() <= 1e-5 * scale, np.abs(got - want).max() / scale
+    if os.environ.get("WAE_TEST_VERBOSE"):
+        for name, ks in kinds.items():
+            print(name, [(float(np.abs(want[:, sg[k]]).max()), float(np.abs(got - want)[:, sg[k]].max())) for k in ks])
+    for k in kinds["plane"] + kinds["image"] + kinds["outlet"] + kinds["body"]:
+        assert np.abs(want[:, sg[k]]).max() > 0

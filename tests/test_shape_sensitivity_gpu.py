@@ -52,3 +52,45 @@ def test_shape_sensitivity_matches_oracle_and_host_replay():
     vag = sol.v_adj / np.conj(np.vdot(sol.v_adj, L(sol.params["ω"], 1) @ v0g))
     rep_g = host_replay(mg, dscrp, c, sp_, trm, ttm, sol.params["ω"], v0g, vag)
     assert np.abs(sens - rep_g).max() <= 1e-7 * scale
+
+
+def test_unit_cell_shape_sensitivity_on_the_ntnu_combustor():
+    """Unit-cell variant (shape_sensitivity.jl:84-118) on docs/src/NTNU_12.msh -> extend_mesh(unit=true): the launch path against the
+    host replay of the same function for all 846 surface points, and against the oracle's literal loop for a few of them."""
+    import wae_b200 as W
+    from oracle import helmholtz as ohelm
+    from oracle import nlevp as onlevp
+    from oracle import shape as oshape
+    from oracle.mesh import extend_mesh as oext
+    from test_bloch import NTNU_DOMS, NTNU_DSCRP, _ntnu_meshes, _ntnu_sos
+    from test_shape_sensitivity import host_replay
+
+    mg, mo = _ntnu_meshes()
+    doms = NTNU_DOMS + [("CC", "half")]
+    g, o = W.extend_mesh(mg, doms, unit=True), oext(mo, doms, unit=True)
+    c = g.generate_field(_ntnu_sos)
+    dscrp = dict(NTNU_DSCRP)
+    dscrp["Outlet_high"] = ("admittance", ("Y_in", 0.2 + 0.1j))
+    L = W.discretize(g, dscrp, c, b="b")
+    L.params["b"] = 1 + 0j
+    sol, n, flag = W.mslp(L, 1000.0, maxiter=20, tol=1e-10, scale=2 * math.pi, output=False)
+    assert flag == 0
+    sp_, trm, ttm = W.get_surface_points(g)
+    sens = W.discrete_adjoint_shape_sensitivity(g, dscrp, c, sp_, trm, ttm, L, sol)
+    w0 = sol.params["ω"]
+    v0 = sol.v / np.sqrt(np.vdot(sol.v, sol.v))
+    va = sol.v_adj / np.conj(np.vdot(sol.v_adj, L(w0, 1) @ v0))
+    rep = host_replay(g, dscrp, c, sp_, trm, ttm, w0, v0, va)
+    scale = np.abs(rep).max()
+    assert scale > 0 and np.abs(sens - rep).max() <= 1e-7 * scale
+    assert np.abs(sens[:, : g.dos.naxis]).max() == 0  # axis points are skipped
+
+    Lo = ohelm.discretize(o, dscrp, c, b="b")
+    Lo.params["b"] = 1 + 0j
+    solo, _, flo = onlevp.mslp(Lo, 1000.0, maxiter=20, tol=1e-10, scale=2 * math.pi)
+    assert flo == 0 and abs(solo.params["ω"] - w0) <= 1e-9 * abs(w0)
+    so, tro, tto = oshape.get_surface_points(o)
+    sub = [25, 26, 400, 401, len(so) - 20, len(so) - 19]
+    want = oshape.discrete_adjoint_shape_sensitivity(o, dscrp, c, [so[k] for k in sub], [tro[k] for k in sub], [tto[k] for k in sub], Lo, solo)
+    pts = [so[k] for k in sub]
+    assert np.abs(sens[:, pts] - want[:, pts]).max() <= 1e-5 * scale

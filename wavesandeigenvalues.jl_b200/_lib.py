@@ -76,7 +76,7 @@ SIGNATURES = {
     "wae_lu_solve": (_i32, [_vp, _i32, _i32, _i32, _pd]),
     "wae_eigs_si": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _pd, _pd, _pd, _pi32]),
     "wae_beyn_moments": (_i32, [_vp, _i32, _i32, _i32, _pd, _pd, _pd, _i32, _i32, _pd, _vp]),
-    "wae_shape_sens_begin": (_i32, [_vp, _i64, _pi64, _dbl, _pd, _pd]),
+    "wae_shape_sens_begin": (_i32, [_vp, _i64, _pi64, _pi64, _dbl, _i32, _i64, _pd, _pd, _pi64, C.POINTER(C.c_uint8), _pd]),
     "wae_shape_sens_add": (_i32, [_vp, _i32, _pi64, _pi64, _pd, _i32, _pd, _i64, _pd, _dbl]),
     "wae_shape_sens_end": (_i32, [_vp, _pd]),
 }
@@ -296,11 +296,16 @@ class Context:
         self._chk(self._l.wae_beyn_moments(self.h, fid, lid, len(z), _p(z, _pd), _p(w, _pd), _p(cf, _pd), l, n_mom, _p(V, _pd), _vp(out_ptr)))
 
     # -- shape sensitivity -----------------------------------------------------------------------
-    def shape_sens_begin(self, points, step, v, v_adj):
+    def shape_sens_begin(self, points, step, v, v_adj, partner=None, cylindrical=False, dof_new=None, dof_flag=None, phase=None):
         pts = np.ascontiguousarray(points, dtype=np.int64)
         v = np.ascontiguousarray(v, dtype=np.complex128)
         va = np.ascontiguousarray(v_adj, dtype=np.complex128)
-        self._chk(self._l.wae_shape_sens_begin(self.h, len(pts), _p(pts, _pi64), float(step), _p(v, _pd), _p(va, _pd)))
+        par = None if partner is None else np.ascontiguousarray(partner, dtype=np.int64)
+        dn = None if dof_new is None else np.ascontiguousarray(dof_new, dtype=np.int64)
+        df = None if dof_flag is None else np.ascontiguousarray(dof_flag, dtype=np.uint8)
+        ph = None if phase is None else np.array([complex(phase)], dtype=np.complex128)
+        self._chk(self._l.wae_shape_sens_begin(self.h, len(pts), _p(pts, _pi64), _p(par, _pi64), float(step), int(bool(cylindrical)), len(v),
+                                               _p(v, _pd), _p(va, _pd), _p(dn, _pi64), _p(df, C.POINTER(C.c_uint8)), _p(ph, _pd)))
         self._sens_n = len(pts)
 
     def shape_sens_add(self, kind, ptr, elems, coef, c=None, ref_tet=0, n_ref=None, nl=0.0):

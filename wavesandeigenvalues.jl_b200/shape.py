@@ -10,8 +10,9 @@ The reference re-runs ``discretize`` six times per surface point on a mesh whose
 touching the point (``mass_weighting=false`` and no ``order``: first-order elements).  Here the host only turns the model
 descriptor into a list of terms (operator kind, scalar at omega_0, simplex lists per point) and one kernel launch per term
 evaluates  -v_adj^H (E(x+h) - E(x-h)) v / (2h)  for all points and coordinates at once; no operator is assembled.
-Unit-cell (Bloch) meshes move points in cylindrical coordinates together with their periodic images (:84-118); that variant is
-not on the accelerated path and raises NotImplementedError.  Indices are 0-based.
+Unit-cell (Bloch) meshes (:84-118): points move along their local cylindrical basis, a point of the Bloch reference plane together
+with its image, the operators are the blochified ones at b = 1 -- the kernel folds the DOFs and applies the class phases itself
+(flames on Bloch meshes are not on the accelerated path, as in ``discretize``).  Indices are 0-based.
 """
 import numpy as np
 
@@ -29,11 +30,13 @@ def _group(keys, vals, n):
     return [v[cuts[i]:cuts[i + 1]] for i in range(n)]
 
 
+def _is_unit(mesh):
+    return getattr(mesh, "dos", 1) != 1 and bool(getattr(mesh.dos, "unit", False))
+
+
 def get_surface_points(mesh, output=False):
     """surface_points (sorted point indices of all triangles), tri_mask[k] / tet_mask[k] = indices of the triangles / tetrahedra
     that contain surface point k, in ascending order (Meshutils.jl:884-944)."""
-    if getattr(mesh, "dos", 1) != 1 and getattr(mesh.dos, "unit", False):
-        raise NotImplementedError("get_surface_points on unit-cell meshes (Meshutils.jl:946-964) is not on the accelerated path")
     tri, tet = mesh.triangles, mesh.tetrahedra
     surface_points = np.unique(tri)
     npts = mesh.points.shape[1]
@@ -44,6 +47,24 @@ def get_surface_points(mesh, output=False):
     ts = slot[tet].ravel()
     keep = ts >= 0
     tet_mask = _group(ts[keep], np.repeat(np.arange(len(tet)), 4)[keep], n)
+    if _is_unit(mesh):
+        # Meshutils.jl:946-964: a point of the Bloch reference plane and its image share their simplex lists.  The reference indexes
+        # the lists by point number, i.e. it relies on the first naxis + nxbloch points (and the last nxbloch ones) all being surface
+        # points -- true for extend_mesh(unit=true), which keeps the triangles of the two periodic planes
+        d = mesh.dos
+        n0 = d.naxis + d.nxbloch
+        if not (np.array_equal(surface_points[:n0], np.arange(n0)) and np.array_equal(surface_points[n - d.nxbloch:], np.arange(npts - d.nxbloch, npts))):
+            raise ValueError("unit-cell mesh whose Bloch planes carry no triangles: the reference's get_surface_points is undefined here")
+
+        def uniq(a, b):
+            x = np.concatenate([a, b])
+            _, first = np.unique(x, return_index=True)
+            return x[np.sort(first)]
+        for k in range(d.naxis, n0):
+            img = n - d.nxbloch + (k - d.naxis)
+            for mask in (tri_mask, tet_mask):
+                mask[k] = uniq(mask[k], mask[img])
+                mask[img] = uniq(mask[img], mask[k])
     return surface_points, tri_mask, tet_mask
 
 
@@ -62,7 +83,7 @@ def get_normal_vectors(mesh, output=False):
 
 
 # --------------------------------------------------------------------------------------------- descriptor -> terms
-def sensitivity_terms(mesh, dscrp, C, w0):
+def sensitivity_terms(mesh, dscrp, C, w0, bloch=False):
     """What ``discretize(mesh_h, dscrp, C, mass_weighting=false)(w0)`` is made of (Helmholtz.jl:232-403): a list of dicts
     {kind, dim, simplices, coef[, c][, ref_tet, n_ref, nl]}; ``coef`` is the term's scalar at w0 with the parameter values the
     descriptor itself provides (the reference evaluates the freshly discretised families, not ``L``)."""
@@ -102,6 +123,8 @@ def sensitivity_terms(mesh, dscrp, C, w0):
                 raise ValueError("Data length does not match :admittance option!")
             terms.append({"kind": _lib.SENS_BOUNDARY, "dim": 2, "simplices": simplices, "coef": coef, "c": C_tri})
         elif typ in ("flame", "flameresponse", "fancyflame"):
+            if bloch:
+                raise NotImplementedError(f"descriptor type {typ!r} with Bloch periodicity is not on the accelerated path")
             ref_idx = -1
             if typ == "flame" and len(data) == 9:
                 gamma, rho, nglobal, x_ref, n_ref, n_sym, tau_sym, n_val, tau_val = data
@@ -172,11 +195,22 @@ def sensitivity_lists(term, n_elem, tri_mask, tet_mask):
 
 
 def discrete_adjoint_shape_sensitivity(mesh, dscrp, C, surface_points, tri_mask, tet_mask, L, sol, h=1e-9, output=False, ctx=None):
-    """sens (3 x N_points complex): d omega / d x_p for every listed surface point, zero elsewhere."""
-    if getattr(mesh, "dos", 1) != 1 and getattr(mesh.dos, "unit", False):
-        raise NotImplementedError("shape sensitivity on unit-cell meshes (shape_sensitivity.jl:84-118) is not on the accelerated path")
+    """sens (3 x N_points complex): d omega / d x_p for every listed surface point, zero elsewhere; on unit-cell meshes the three
+    rows are the radial, azimuthal and axial directions of the point (and axis points are skipped, :100-105)."""
     npts = mesh.points.shape[1]
-    if L.size() != npts:
+    unit = _is_unit(mesh)
+    fold = {}
+    if unit:
+        import math
+
+        from .meshutils import bloch_dof_maps
+        d = mesh.dos
+        new, image, axis, red = bloch_dof_maps(mesh, "lin")
+        if L.size() != red:
+            raise ValueError("shape sensitivity is a first-order path: L must be discretize(mesh, dscrp, C, b='b') with order='lin'")
+        fold = {"dof_new": new, "dof_flag": image.astype(np.uint8) | (axis.astype(np.uint8) << 1), "phase": np.exp(2j * math.pi / d.DOS),
+                "cylindrical": True}
+    elif L.size() != npts:
         raise ValueError("shape sensitivity is a first-order path: L must be discretize(mesh, dscrp, C) with order='lin'")
     w0 = sol.params[sol.eigval]
     v0 = np.asarray(sol.v, dtype=np.complex128)
@@ -188,14 +222,22 @@ def discrete_adjoint_shape_sensitivity(mesh, dscrp, C, surface_points, tri_mask,
     # mesh_set, so its patterns stay valid
     ctx.mesh_set(1, mesh.points.T, mesh.tetrahedra, mesh.triangles, npts)
     surface_points = np.asarray(surface_points, dtype=np.int64)
-    ctx.shape_sens_begin(surface_points, h, v0, va)
-    for term in sensitivity_terms(mesh, dscrp, C, w0):
+    keep = np.arange(len(surface_points))
+    if unit:
+        keep = keep[surface_points >= d.naxis]  # axis points are skipped (:100-105)
+        pts = surface_points[keep]
+        on_plane = (pts >= d.naxis) & (pts < d.naxis + d.nxbloch)
+        fold["partner"] = np.where(on_plane, npts - d.nxbloch + (pts - d.naxis), -1)  # :88-91
+        tri_mask, tet_mask = [tri_mask[k] for k in keep], [tet_mask[k] for k in keep]
+    pts = surface_points[keep]
+    ctx.shape_sens_begin(pts, h, v0, va, **fold)
+    for term in sensitivity_terms(mesh, dscrp, C, w0, bloch=unit):
         n_elem = len(mesh.triangles) if term["dim"] == 2 else len(mesh.tetrahedra)
         ptr, elems, c = sensitivity_lists(term, n_elem, tri_mask, tet_mask)
         ctx.shape_sens_add(term["kind"], ptr, elems, term["coef"], c=c, ref_tet=term.get("ref_tet", 0), n_ref=term.get("n_ref"),
                            nl=term.get("nl", 0.0))
     sens = np.zeros((3, npts), dtype=np.complex128)
-    sens[:, surface_points] = ctx.shape_sens_end()
+    sens[:, pts] = ctx.shape_sens_end()
     return sens
 
 
