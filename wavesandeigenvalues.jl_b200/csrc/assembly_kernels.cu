@@ -373,7 +373,11 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes
 // coordinates of patch i+1 arrive in the other shared-memory buffer (bulk copy + mbarrier), its slot words and store program
 // are prefetched into L2, and the descriptor of patch i+2 is fetched.
 // MODE bit 0: mass -> out_m, bit 1: stiffness -> out_k
-template <int NLOC, int MODE>
+// VAR selects variants prepared from the phase shares of profiles/r01_ncu_assembly_phase_shares.txt (WAE_ASM_VARIANT, default 0 =
+// the measured kernel).  bit 0: summation loop unrolled by four (the pass is latency-bound: one 16-byte load in flight per warp);
+// bit 1: the element pass of a P2 patch split into three parts per element (a patch stages ~350 elements, i.e. 11 of the 32 warps
+// had work; every part recomputes the geometry and visits a third of the packed triangle).  Same sums in the same order.
+template <int NLOC, int MODE, int VAR>
 __global__ void __launch_bounds__(1024, 1) assemble_tet_pairs(const int64_t* __restrict__ desc, int n_patch, const uint8_t* __restrict__ blob,
                                                                const double* __restrict__ pxyz, const double* __restrict__ c,
                                                                const uint32_t* __restrict__ dest, const uint16_t* __restrict__ res,
@@ -433,12 +437,29 @@ __global__ void __launch_bounds__(1024, 1) assemble_tet_pairs(const int64_t* __r
     const int nwb = (nt + 31) >> 5;
     mbar_wait(mbar0 + 8u * b, (uint32_t)(i >> 1) & 1u);
     // ---- element pass: one staged element per lane, 32 elements per warp step
-    for (int wb = warp; wb < nwb && dbg != 2; wb += nwarp) {
-      const int t = wb * 32 + lane;
-      if (t >= nt) continue;
-      const uint32_t* dp = dest + ((size_t)(d23.x + wb) * NPK) * 32 + lane;
-      const double cc = (MODE & 2) ? c[tets[t]] : 0.0;
-      element_part<NLOC, 0, NSYM>(px, lvtx[t], cc, mass_scale, dp, sbase);
+    if constexpr ((VAR & 2) && NLOC == 10) {
+      constexpr int C1 = 18, C2 = 36;  // even cuts: a part starts on a fresh slot word
+      for (int job = warp; job < 3 * nwb && dbg != 2; job += nwarp) {
+        const int wb = job / 3, part = job - 3 * wb;
+        const int t = wb * 32 + lane;
+        if (t >= nt) continue;
+        const uint32_t* dp = dest + ((size_t)(d23.x + wb) * NPK) * 32 + lane;
+        const double cc = (MODE & 2) ? c[tets[t]] : 0.0;
+        if (part == 0)
+          element_part<NLOC, 0, C1>(px, lvtx[t], cc, mass_scale, dp, sbase);
+        else if (part == 1)
+          element_part<NLOC, C1, C2>(px, lvtx[t], cc, mass_scale, dp, sbase);
+        else
+          element_part<NLOC, C2, NSYM>(px, lvtx[t], cc, mass_scale, dp, sbase);
+      }
+    } else {
+      for (int wb = warp; wb < nwb && dbg != 2; wb += nwarp) {
+        const int t = wb * 32 + lane;
+        if (t >= nt) continue;
+        const uint32_t* dp = dest + ((size_t)(d23.x + wb) * NPK) * 32 + lane;
+        const double cc = (MODE & 2) ? c[tets[t]] : 0.0;
+        element_part<NLOC, 0, NSYM>(px, lvtx[t], cc, mass_scale, dp, sbase);
+      }
     }
     __syncthreads();
     // first batch of the store pass: issued here so that its latency hides behind the summation pass
@@ -452,10 +473,26 @@ __global__ void __launch_bounds__(1024, 1) assemble_tet_pairs(const int64_t* __r
       const int cn = cnt[g * 32 + lane];
       const uint32_t base = sbase + ((hdr >> 8) << 4);
       double ak = 0.0, am = 0.0;
-#pragma unroll 1
-      for (int k = 0; k < cn; k++) {
-        double vx, vy;
+      auto lds = [&](int k, double& vx, double& vy) {
         asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(vx), "=d"(vy) : "r"(base + (k << 9) + (lane16 ^ ((k & 7) << 4))) : "memory");
+      };
+      int k = 0;
+      if constexpr (VAR & 1) {
+#pragma unroll 1
+        for (; k + 4 <= cn; k += 4) {  // four loads in flight, then the same left-to-right sum as the rolled loop
+          double x0, y0, x1, y1, x2, y2, x3, y3;
+          lds(k, x0, y0);
+          lds(k + 1, x1, y1);
+          lds(k + 2, x2, y2);
+          lds(k + 3, x3, y3);
+          ak = (((ak + x0) + x1) + x2) + x3;
+          am = (((am + y0) + y1) + y2) + y3;
+        }
+      }
+#pragma unroll 1
+      for (; k < cn; k++) {
+        double vx, vy;
+        lds(k, vx, vy);
         ak += vx;
         am += vy;
       }
@@ -505,10 +542,20 @@ void wae_launch_assemble_gather(wae_ctx* h, Pattern& P, const double* d_c, doubl
                                              buf_bytes, mass_scale, d_mass, d_stiff, dbg);
   };
   const bool both = d_stiff != nullptr;
+  const int var = getenv("WAE_ASM_VARIANT") ? atoi(getenv("WAE_ASM_VARIANT")) & 3 : 0;
+  auto pick = [&](auto nloc_c, auto mode_c) {
+    constexpr int NL = decltype(nloc_c)::value, MD = decltype(mode_c)::value;
+    switch (var) {
+      case 1: launch(assemble_tet_pairs<NL, MD, 1>); break;
+      case 2: launch(assemble_tet_pairs<NL, MD, 2>); break;
+      case 3: launch(assemble_tet_pairs<NL, MD, 3>); break;
+      default: launch(assemble_tet_pairs<NL, MD, 0>); break;
+    }
+  };
   if (h->nloc == 4) {
-    if (both) launch(assemble_tet_pairs<4, 3>); else launch(assemble_tet_pairs<4, 1>);
+    if (both) pick(WaeIdx<4>{}, WaeIdx<3>{}); else pick(WaeIdx<4>{}, WaeIdx<1>{});
   } else {
-    if (both) launch(assemble_tet_pairs<10, 3>); else launch(assemble_tet_pairs<10, 1>);
+    if (both) pick(WaeIdx<10>{}, WaeIdx<3>{}); else pick(WaeIdx<10>{}, WaeIdx<1>{});
   }
   h->launches++;
   CUDA_CHECK(cudaGetLastError());
