@@ -391,6 +391,15 @@ def main():
     # ------------------------------------------------------------------ Beyn leg (sharded over all ranks)
     if not args.skip_extras:
         out["beyn"] = beyn_leg(W, torch, dist, ctx, args, rank, world, dev, barrier, max_over_ranks)
+    # ------------------------------------------------------------------ diagnostic leg: shape sensitivity (rank 0, N = 1 only), in a subprocess
+    if rank == 0 and world == 1 and not args.skip_extras:
+        try:
+            p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_shape_sens.py"), "10", "10", "150", "5"], capture_output=True,
+                               text=True, timeout=300)
+            line = [l for l in p.stdout.splitlines() if l.startswith("{")]
+            out["shape_sensitivity"] = json.loads(line[-1]) if line else {"error": (p.stderr or p.stdout)[-400:]}
+        except Exception as e:  # noqa: BLE001 -- diagnostic leg only
+            out["shape_sensitivity"] = {"error": repr(e)[:400]}
     # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1 only)
     if rank == 0 and world == 1 and not args.skip_extras:
         sample = tuple(int(x) for x in args.cpu_sample.split(","))
@@ -433,6 +442,15 @@ def assembly_leg(W, ctx0, n, hbm, hbm_src):
                         "peak_source": hbm_src, "algorithmic_bytes_per_tet": alg / ntet,
                         "kernel": "assemble_tet_pairs<10,3> (P2 M+K, owner-computes pair program, persistent, TMA-staged)"}}
     ctx.close()
+    # opt-in kernel variants (WAE_ASM_VARIANT; prepared from the per-phase profile): timed and checked against the
+    # default kernel in a SUBPROCESS, so that nothing they do can disturb this run; the headline above is always the default kernel
+    try:
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_assembly_variants.py"), str(n), "quad", "7"], capture_output=True,
+                           text=True, timeout=240, env={**os.environ, "CUDA_VISIBLE_DEVICES": os.environ.get("CUDA_VISIBLE_DEVICES", str(ctx0.device))})
+        line = [l for l in p.stdout.splitlines() if l.startswith("{")]
+        res["variants"] = json.loads(line[-1])["variants"] if line else {"error": (p.stderr or p.stdout)[-400:]}
+    except Exception as e:  # noqa: BLE001 -- diagnostic leg only
+        res["variants"] = {"error": repr(e)[:400]}
     return res
 
 

@@ -307,6 +307,7 @@ class Context:
         self._chk(self._l.wae_shape_sens_begin(self.h, len(pts), _p(pts, _pi64), _p(par, _pi64), float(step), int(bool(cylindrical)), len(v),
                                                _p(v, _pd), _p(va, _pd), _p(dn, _pi64), _p(df, C.POINTER(C.c_uint8)), _p(ph, _pd)))
         self._sens_n = len(pts)
+        self.sens_kernel_ms = 0.0  # summed over the wae_shape_sens_add launches of this sequence
 
     def shape_sens_add(self, kind, ptr, elems, coef, c=None, ref_tet=0, n_ref=None, nl=0.0):
         ptr = np.ascontiguousarray(ptr, dtype=np.int64)
@@ -319,6 +320,8 @@ class Context:
         nr = None if n_ref is None else np.ascontiguousarray(n_ref, dtype=np.float64)
         self._chk(self._l.wae_shape_sens_add(self.h, kind, _p(ptr, _pi64), _p(elems, _pi64), _p(c, _pd), cpe, _p(cf, _pd), int(ref_tet),
                                              _p(nr, _pd), float(nl)))
+        if len(elems):
+            self.sens_kernel_ms += max(self.last_ms("shape_sens"), 0.0)
 
     def shape_sens_end(self):
         out = np.empty((self._sens_n, 3), dtype=np.complex128)  # == 3 x n_sp column-major
