@@ -177,3 +177,35 @@ def test_generic_nlevp_tutorial_00():
     for i, lam in enumerate(Om):  # residual check of the tutorial
         v = P[:, i] / np.linalg.norm(P[:, i])
         assert np.linalg.norm(_qep1()(lam) @ v) < 1e-8
+
+
+def test_gallery_rijke_tube_against_the_analytic_duct():
+    """Gallery.rijke_tube (src/NLEVP/gallery.jl:171-260), the assembly-free fixture of SURVEY 8(c).  Passive (n = 0) it is a closed-open
+    duct with a jump of the speed of sound, whose eigenfrequencies solve  c1 tan(w x_m / c1) = c2 cot(w (l - x_m) / c2);  first-order
+    elements converge to them like h^2.  Active (n = 1, tau = 2) householder and mslp must agree, and Beyn must find the same mode."""
+    import scipy.optimize as so
+    from oracle.gallery import rijke_tube
+    from oracle.nlevp import beyn, householder, mslp
+    errs = []
+    for res in (129, 257):
+        L, grid = rijke_tube(res)
+        assert L.size() == res and [t.operator for t in L.terms] == ["M", "K", "C", "Q", "__aux__"]
+        L.params["n"] = 0j
+        mid = res // 2 + 1
+        xm, l, c1, c2 = grid[mid - 1], grid[-1], 1.0, 2.0  # elements 1..mid-1 (1-based) carry c_min: the jump sits at node mid-1 (0-based)
+        f = lambda w: c1 * math.tan(w * xm / c1) - c2 / math.tan(w * (l - xm) / c2)
+        exact = so.brentq(f, 1.0, 2.5)
+        sol, n, flag = householder(L, exact * 1.05, maxiter=20, tol=1e-10)
+        assert flag == 1 and abs(sol.params["ω"].imag) < 1e-9
+        errs.append(abs(sol.params["ω"].real - exact) / exact)
+    assert errs[0] < 2e-4 and 3.5 < errs[0] / errs[1] < 4.5  # second-order convergence to the analytic eigenfrequency
+    L, _ = rijke_tube(129)
+    sh, nh, fh = householder(L, 1.7, maxiter=30, tol=1e-10)
+    L2, _ = rijke_tube(129)
+    sm, nm, fm = mslp(L2, 1.7, maxiter=30, tol=1e-10)
+    assert fh == 1 and fm == 0 and abs(sh.params["ω"] - sm.params["ω"]) < 1e-9
+    w = sh.params["ω"]
+    assert abs(w.imag) > 1e-3  # the flame makes the mode grow or decay
+    L3, _ = rijke_tube(129)
+    Om, P = beyn(L3, [w + 0.3 + 0.3j, w - 0.3 + 0.3j, w - 0.3 - 0.3j, w + 0.3 - 0.3j], l=4, N=32)
+    assert len(Om) >= 1 and np.abs(Om - w).min() < 1e-8
