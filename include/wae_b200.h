@@ -96,6 +96,11 @@ int32_t wae_assemble(wae_ctx* h, int32_t pattern_id, int32_t kind, const double*
 /* Mass and stiffness of the same tetrahedral pattern in one pass over the elements. */
 int32_t wae_assemble_mk(wae_ctx* h, int32_t pattern_id, const double* c, int32_t c_per_elem,
                         int32_t* mass_id, int32_t* stiff_id);
+/* Speaker source vector of discretize(...; source=true) (Helmholtz.jl:488-503 opr == :m, wallsrc :193-210; FEM.jl:2557-2589):
+ * out[i] = -i * sum over the listed triangles of c * |det| * int phi_i (c_per_elem 1) or of |det| * sum_k c_k int phi_i lambda_k
+ * (c_per_elem 3, vertex values).  out: dim complex values (interleaved), written in full -- the dense form of the reference's
+ * sparsevec(I, V, dim); the scalar (boundary_func..., pow1) stays on the host.                  */
+int32_t wae_assemble_wallsrc(wae_ctx* h, int64_t n_tri, const int64_t* tri_ids, const double* c, int32_t c_per_elem, double* out);
 /* Flame-response operator Q = S (x) G (Helmholtz.jl:464-487, 19-33; FEM.jl:2429-2484):
  * S_i = sum over flame tets of int phi_i, G_j = -nlocal * grad phi_j(x_ref) . n_ref on ref_tet.
  * Builds its own (dense block) pattern.                                                      */

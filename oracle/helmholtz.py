@@ -4,8 +4,8 @@ Restates src/Helmholtz.jl:19-33 (outer), :54-81, :120-191 (element wrappers),
 :232-345 (descriptor parsing: :interior, :mass, :stiff-less subset, :admittance
 (sym,val), :flame 9/10-tuple n-tau, :flameresponse), :405-524 (element loops +
 sparse()), :528-540,:571-580 (mass weighting / __aux__ term).
-Bloch (b!=:__none__), :speaker, :fancyflame and custom-FTF variants are not on
-the round-1 path and raise NotImplementedError.
+:speaker descriptors and the source=true return mode (:251-258, 488-503, 524-526,
+576-577) are restated too; custom-FTF flame variants raise NotImplementedError.
 """
 import numpy as np
 import scipy.sparse as sp
@@ -64,9 +64,9 @@ def blochify(ii, jj, mm, naxis, nxbloch, nsector, naxis_ln, nsector_ln, N_points
     return [sets[k] for k in keys]
 
 
-def discretize(mesh, dscrp, C, order="lin", mass_weighting=True, triplets=None, b=None):
-    """Returns the LinearOperatorFamily.  If `triplets` is a dict, the raw COO
-    triplets of every operator are stored in it (used by the pattern tests)."""
+def discretize(mesh, dscrp, C, order="lin", mass_weighting=True, triplets=None, b=None, source=False):
+    """Returns the LinearOperatorFamily (and, with source=True, the vector family `rhs`, Helmholtz.jl:576-577).  If `triplets`
+    is a dict, the raw COO triplets of every operator are stored in it (used by the pattern tests)."""
     o = 1 if order == "lin" else 2
     triangles, tetrahedra, dim = aggregate_elements(mesh, order)
     npts = mesh.points.shape[1]
@@ -82,6 +82,7 @@ def discretize(mesh, dscrp, C, order="lin", mass_weighting=True, triplets=None, 
     else:
         raise ValueError("C must be per-tetrahedron or per-point")
     L = LinearOperatorFamily(["ω", "λ"], [0.0, float("inf")])
+    rhs = LinearOperatorFamily(["ω"], [0.0])  # Helmholtz.jl:79
     P = mesh.points
     bloch = b is not None
     if bloch:  # Helmholtz.jl:82-118
@@ -114,21 +115,34 @@ def discretize(mesh, dscrp, C, order="lin", mass_weighting=True, triplets=None, 
     def bound(ct, c):
         return c * fem.tri_mass(ct, o) if np.ndim(c) == 0 else fem.tri_mass_c1(ct, c, o)
 
+    def wallsrc(ct, c):  # Helmholtz.jl:193-210
+        return c * fem.tri_src(ct, o) if np.ndim(c) == 0 else fem.tri_src_c1(ct, c, o)
+
     for domain, (typ, data) in dscrp.items():
         simplices = mesh.domains[domain]["simplices"]
         if typ == "interior":
             make = ["M", "K"]
         elif typ == "mass":
             make = ["M"]
-        elif typ == "admittance":
-            make = ["C"]
+        elif typ in ("admittance", "speaker"):
+            make = []
+            if typ == "speaker":  # Helmholtz.jl:253-258
+                make.append("m")
+                speak_sym, speak_val = data[:2]
+                rhs.params[speak_sym] = complex(speak_val)
+                data = tuple(data[2:])
+            if len(data) > 0:
+                make.append("C")
             if len(data) == 2:  # Helmholtz.jl:262-273
                 adm_sym, adm_val = data
-                L.params.setdefault(adm_sym, complex(adm_val))
+                if adm_sym not in L.params:
+                    L.params[adm_sym] = complex(adm_val)
+                    if typ == "speaker":
+                        rhs.params[adm_sym] = complex(adm_val)
                 bfunc, barg, btxt = (pow1, pow1), (("ω",), (adm_sym,)), "ω*" + adm_sym
             elif len(data) == 1:  # :274-278
                 bfunc, barg, btxt = (generate_z_g_z(data[0]),), (("ω",),), "ω*Y(ω)"
-            else:  # :279-285 state space
+            elif len(data) == 4:  # :279-285 state space
                 bfunc, barg, btxt = (generate_z_g_z(generate_stsp_z(*data)),), (("ω",),), "ω*C_s(iωI-A)^{-1}B"
         elif typ == "fancyflame":  # Helmholtz.jl:363-400
             make = ["Q"]
@@ -203,6 +217,17 @@ def discretize(mesh, dscrp, C, order="lin", mass_weighting=True, triplets=None, 
                     for b, j in zip(G, smplx):
                         V.append(a * b); I.append(i); J.append(j)
                 func, arg, txt = ffunc, farg, ftxt
+            elif opr == "m":  # Helmholtz.jl:488-503: source vector of a speaker (membrane) boundary
+                if bloch:
+                    raise NotImplementedError("speaker on a Bloch mesh")
+                for s in simplices:
+                    smplx = triangles[s]
+                    ct = fem.CooTrafo(P[:, smplx[:3]])
+                    V.extend(wallsrc(ct, C_tri[s])); I.extend(smplx)
+                V = np.asarray(V, dtype=complex) / 1j
+                vec = sp.csc_matrix(sp.coo_matrix((V, (I, np.zeros(len(I), dtype=int))), shape=(dim, 1)))  # sparsevec(I,V,dim)
+                rhs.push(Term(vec, tuple(bfunc) + (pow1,), tuple(barg) + ((speak_sym,),), "speaker", "m"))
+                continue
             if triplets is not None:
                 triplets.setdefault(opr, []).append((np.array(I), np.array(J), np.array(V, dtype=complex)))
             if bloch:  # Helmholtz.jl:509-513
@@ -236,4 +261,4 @@ def discretize(mesh, dscrp, C, order="lin", mass_weighting=True, triplets=None, 
         else:
             M = _sparse(I, J, -np.asarray(V), dim)
         L.push(Term(M, (pow1,), (("λ",),), "-λ", "__aux__"))
-    return L
+    return (L, rhs) if source else L

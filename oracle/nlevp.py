@@ -209,8 +209,7 @@ class LinearOperatorFamily:
             derivs = [0] * na
         else:
             derivs = [int(a) for a in args[len(args) - na :]]
-        n = self.size()
-        coeff = sp.csc_matrix((n, n), dtype=complex)
+        coeff = sp.csc_matrix(self.terms[0].coeff.shape, dtype=complex)  # spzeros(size(L.terms[1].coeff)...): matrices or vectors
         for t, s in zip(self.terms, self.scalars(derivs)):
             if s is not None:
                 coeff = coeff + s * t.coeff

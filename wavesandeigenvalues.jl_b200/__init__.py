@@ -9,12 +9,12 @@ anywhere, but creating a context without the built library or without a GPU rais
 from . import _lib  # noqa: F401
 from .helmholtz import discretize  # noqa: F401
 from .meshutils import Mesh, SymInfo, aggregate_elements, extend_mesh, kuhn_box, kuhn_unit_cell, octosplit  # noqa: F401
-from .nlevp import (bloch_expand, conv_radius, LinearOperatorFamily, Solution, Term, beyn, compute_moment_matrices, exp_az, exp_delay,  # noqa: F401
+from .nlevp import (bloch_expand, conv_radius, LinearOperatorFamily, VectorFamily, Solution, Term, beyn, compute_moment_matrices, exp_az, exp_delay,  # noqa: F401
                     get_context, householder, inpoly, moments2eigs, mslp, pade_bang, perturb_bang, perturb_fast_bang, perturb_norm_bang, pow0,
                     pow1, pow2, pow_a,
                     reset_context, wn)
 from .shape import (bound_mass_normalize, discrete_adjoint_shape_sensitivity, get_normal_vectors, get_surface_points,  # noqa: F401
                     normal_sensitivity, normalize_sensitivity)
 
-__all__ = ["Mesh", "discretize", "LinearOperatorFamily", "Term", "Solution", "householder", "mslp", "beyn", "pow0", "pow1",
+__all__ = ["Mesh", "discretize", "LinearOperatorFamily", "VectorFamily", "Term", "Solution", "householder", "mslp", "beyn", "pow0", "pow1",
            "pow2", "exp_delay", "kuhn_box", "aggregate_elements", "get_context"]

@@ -76,6 +76,7 @@ SIGNATURES = {
     "wae_lu_solve": (_i32, [_vp, _i32, _i32, _i32, _pd]),
     "wae_eigs_si": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _pd, _pd, _pd, _pi32]),
     "wae_beyn_moments": (_i32, [_vp, _i32, _i32, _i32, _pd, _pd, _pd, _i32, _i32, _pd, _vp]),
+    "wae_assemble_wallsrc": (_i32, [_vp, _i64, _pi64, _pd, _i32, _pd]),
     "wae_shape_sens_begin": (_i32, [_vp, _i64, _pi64, _pi64, _dbl, _i32, _i64, _pd, _pd, _pi64, C.POINTER(C.c_uint8), _pd]),
     "wae_shape_sens_add": (_i32, [_vp, _i32, _pi64, _pi64, _pd, _i32, _pd, _i64, _pd, _dbl]),
     "wae_shape_sens_end": (_i32, [_vp, _pd]),
@@ -194,6 +195,15 @@ class Context:
         self._chk(self._l.wae_assemble_flame(self.h, len(ft), _p(ft, _pi64), int(ref_tet), _p(xr, _pd), _p(nr, _pd), float(nlocal),
                                              C.byref(pid), C.byref(mid), C.byref(nnz)))
         return pid.value, mid.value, nnz.value
+
+    def assemble_wallsrc(self, tri_ids, c, dim):
+        """Speaker source vector over the listed triangles -> dense complex vector of length dim."""
+        ids = np.ascontiguousarray(tri_ids, dtype=np.int64)
+        c = np.ascontiguousarray(c, dtype=np.float64)
+        cpe = 1 if c.ndim == 1 else c.shape[1]
+        out = np.empty(dim, dtype=np.complex128)
+        self._chk(self._l.wae_assemble_wallsrc(self.h, len(ids), _p(ids, _pi64), _p(c, _pd), cpe, _p(out, _pd)))
+        return out
 
     def assemble_bloch(self, elem_kind, elem_ids, kind, c, scale, dim_red, dof_new, dof_flag, n_class):
         ids = None if elem_ids is None else np.ascontiguousarray(elem_ids, dtype=np.int64)

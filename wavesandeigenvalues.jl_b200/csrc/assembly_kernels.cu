@@ -162,6 +162,48 @@ __global__ void __launch_bounds__(128) assemble_tri_atomic(const double* __restr
   }
 }
 
+// speaker source vector (Helmholtz.jl:193-210, 489-497; FEM.jl:2557-2589): m_i = -i * sum_tri c |det| int phi_i  (c constant per
+// triangle) or -i * sum_tri |det| sum_k c_k int phi_i lambda_k (c linear); out is a dense complex vector over the DOFs
+template <int NLOC3>
+__global__ void __launch_bounds__(128) wallsrc_kernel(const double* __restrict__ xyz, const uint32_t* __restrict__ conn,
+                                                      const int32_t* __restrict__ elems, int64_t n_elem, const double* __restrict__ c,
+                                                      int c_per_elem, double* __restrict__ out /* complex */) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_elem) return;
+  const uint32_t* d = conn + (size_t)elems[e] * NLOC3;
+  double X[3][3];
+  for (int k = 0; k < 3; k++)
+    for (int r = 0; r < 3; r++) X[k][r] = xyz[3 * (size_t)d[k] + r];
+  double e1[3], e2[3];
+  for (int r = 0; r < 3; r++) {
+    e1[r] = X[0][r] - X[2][r];
+    e2[r] = X[1][r] - X[2][r];
+  }
+  double nx = e1[1] * e2[2] - e1[2] * e2[1], ny = e1[2] * e2[0] - e1[0] * e2[2], nz = e1[0] * e2[1] - e1[1] * e2[0];
+  double adet = sqrt(nx * nx + ny * ny + nz * nz);
+  const double* Ts = NLOC3 == 3 ? WAE_P1_TRI_SRC : WAE_P2_TRI_SRC;
+  const double* Tc = NLOC3 == 3 ? WAE_P1_TRI_SRCC : WAE_P2_TRI_SRCC;
+  for (int k = 0; k < NLOC3; k++) {
+    double m;
+    if (c_per_elem == 1)
+      m = c[e] * Ts[k];
+    else
+      m = c[3 * e] * Tc[3 * k] + c[3 * e + 1] * Tc[3 * k + 1] + c[3 * e + 2] * Tc[3 * k + 2];
+    if (m != 0.0) atomicAdd(out + 2 * (size_t)d[k] + 1, -m * adet);  // V ./= 1im  ->  imaginary part only
+  }
+}
+
+void wae_launch_wallsrc(wae_ctx* h, const int32_t* d_elems, int64_t n, const double* d_c, int c_per_elem, double* d_out) {
+  if (n == 0) return;
+  unsigned blocks = (unsigned)((n + 127) / 128);
+  if (h->nloc3 == 3)
+    wallsrc_kernel<3><<<blocks, 128, 0, h->stream>>>(h->d_xyz.p, h->d_tris.p, d_elems, n, d_c, c_per_elem, d_out);
+  else
+    wallsrc_kernel<6><<<blocks, 128, 0, h->stream>>>(h->d_xyz.p, h->d_tris.p, d_elems, n, d_c, c_per_elem, d_out);
+  h->launches++;
+  CUDA_CHECK(cudaGetLastError());
+}
+
 // ---- flame: S_i = sum_t |det_t| src[loc] over flame tets, G_j on the reference tet ------
 template <int NLOC>
 __global__ void flame_src_kernel(const double* __restrict__ xyz, const uint32_t* __restrict__ conn,

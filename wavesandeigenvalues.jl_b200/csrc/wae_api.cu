@@ -285,6 +285,31 @@ int32_t wae_assemble_mk(wae_ctx* h, int32_t pattern_id, const double* c, int32_t
   WAE_API_END
 }
 
+int32_t wae_assemble_wallsrc(wae_ctx* h, int64_t n_tri, const int64_t* tri_ids, const double* c, int32_t c_per_elem, double* out) {
+  WAE_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(h->device));
+  if (!h->order || n_tri < 0 || (n_tri && (!tri_ids || !c)) || !out || (c_per_elem != 1 && c_per_elem != 3))
+    WAE_THROW(WAE_E_INVALID, "bad speaker-source arguments (c holds 1 or 3 values per triangle)");
+  std::vector<int32_t> el(n_tri);
+  for (int64_t i = 0; i < n_tri; i++) {
+    const int64_t e = tri_ids[i] - h->base;
+    if (e < 0 || e >= h->n_tri) WAE_THROW(WAE_E_INVALID, "speaker triangle %lld out of range", (long long)tri_ids[i]);
+    el[i] = (int32_t)e;
+  }
+  DevBuf<int32_t> d_el;
+  DevBuf<double> d_c, d_out;
+  d_el.upload(el, h->stream);
+  d_c.upload(c, (size_t)n_tri * c_per_elem, h->stream);
+  d_out.alloc((size_t)2 * h->dim);
+  CUDA_CHECK(cudaMemsetAsync(d_out.p, 0, (size_t)2 * h->dim * sizeof(double), h->stream));
+  PhaseTimer t(h, "assemble");
+  wae_launch_wallsrc(h, d_el.p, n_tri, d_c.p, c_per_elem, d_out.p);
+  t.stop();
+  CUDA_CHECK(cudaMemcpyAsync(out, d_out.p, (size_t)2 * h->dim * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  WAE_API_END
+}
+
 int32_t wae_assemble_flame(wae_ctx* h, int64_t n_flame, const int64_t* flame_tets, int64_t ref_tet, const double* x_ref,
                            const double* n_ref, double nlocal, int32_t* pattern_id, int32_t* mat_id, int64_t* nnz) {
   WAE_API_BEGIN

@@ -226,6 +226,7 @@ void wae_launch_assemble_atomic(wae_ctx* h, Pattern& P, int kind, const double* 
                                 double scale, double* d_out_a, double* d_out_b);
 void wae_launch_assemble_gather(wae_ctx* h, Pattern& P, const double* d_c, double* d_mass, double* d_stiff,
                                 double mass_scale);
+void wae_launch_wallsrc(wae_ctx* h, const int32_t* d_elems, int64_t n, const double* d_c, int c_per_elem, double* d_out);
 void wae_combine_device(wae_ctx* h, Family& F, const double* coeffs_host, int slot);
 void wae_spmm_device(wae_ctx* h, Family& F, int slot, int trans, int nrhs, const cplx* X, cplx* Y);
 void wae_spmm_values(wae_ctx* h, Family& F, const cplx* val, int trans, int nrhs, const cplx* X, cplx* Y);

@@ -13,9 +13,11 @@
   "flame" 5-tuple                    Q with the plain parameter FTF :312-319
   "flameresponse" 7-tuple            Q with eps                     :346-359
 and the auxiliary mass-weighting term -lambda*M_all (:528-540, 571-574).  With ``b="b"`` (a unit-cell mesh carrying
-``mesh.dos``) the operators are blochified (src/Bloch.jl:4-112, Helmholtz.jl:82-118,509-513,541-569).  :speaker
-sources, :fancyflame, flames on Bloch meshes and Hermite elements are outside the accelerated path and raise
-NotImplementedError.
+``mesh.dos``) the operators are blochified (src/Bloch.jl:4-112, Helmholtz.jl:82-118,509-513,541-569).
+  "speaker" (sym, val, *admittance)  source vector m with (admittance scalar)*sym, plus C   :251-257, 488-503
+With ``source=True`` the call returns ``(L, rhs)`` as in the reference (:576-577; tutorial_09_forcing.md: ``sol = L(ω) \\ Array(rhs(ω))``
+is ``L(ω).solve(rhs(ω))`` here).  Flames and speakers on Bloch meshes and Hermite elements are outside the accelerated path and
+raise NotImplementedError.
 
 What changes relative to the reference is only where the work happens: the per-element loops
 (:411-463, 468-476, 532-539) and ``sparse()`` run as CUDA kernels on a pattern computed once per domain.
@@ -24,8 +26,8 @@ import numpy as np
 
 from . import _lib
 from .meshutils import aggregate_elements
-from .nlevp import (DeviceMatrix, LinearOperatorFamily, Sigma_nexp_az2mzit, Term, exp_az2mzit, exp_delay, generate_stsp_z, generate_z_g_z,
-                    get_context, pow1, pow2)
+from .nlevp import (DeviceMatrix, LinearOperatorFamily, Sigma_nexp_az2mzit, Term, VectorFamily, exp_az2mzit, exp_delay, generate_stsp_z,
+                    generate_z_g_z, get_context, pow1, pow2)
 
 
 def _split_c(mesh, C, npts):
@@ -71,6 +73,8 @@ class Discretization:
                 ctx.assemble(op["pid"], _lib.OP_STIFF, C_tet[op["simplices"]], reuse=op["mat"])
             elif k == "boundary":
                 ctx.assemble(op["pid"], _lib.OP_BOUNDARY, C_tri[op["simplices"]], reuse=op["mat"])
+            elif k == "wallsrc":  # refreshed in place (the rhs term holds this array unless push merged it with another speaker)
+                op["vec"][:] = ctx.assemble_wallsrc(op["simplices"], C_tri[op["simplices"]], self.dim)
             elif k == "flame":
                 nlocal = (op["gamma"] - 1) / op["rho"] * op["nglobal"] / mesh.compute_size(op["domain"])
                 ctx.assemble_flame(op["simplices"], op["ref_idx"], op["x_ref"], op["n_ref"], nlocal, reuse=op["mat"])
@@ -105,8 +109,6 @@ def _bloch_setup(mesh, order, b, L):
 
 def discretize(mesh, dscrp, C, order="lin", b="__none__", mass_weighting=True, source=False, output=False, ctx=None):
     bloch = None
-    if source:
-        raise NotImplementedError("source=True (experimental in the reference) is not on the accelerated path")
     ctx = ctx or get_context()
     triangles, tetrahedra, dim = aggregate_elements(mesh, order)
     npts = mesh.points.shape[1]
@@ -114,6 +116,7 @@ def discretize(mesh, dscrp, C, order="lin", b="__none__", mass_weighting=True, s
 
     ctx.mesh_set(1 if order == "lin" else 2, mesh.points.T, tetrahedra, triangles, dim)
     L = LinearOperatorFamily(["ω", "λ"], [0.0, float("inf")])
+    rhs = VectorFamily(["ω"], [0.0])  # Helmholtz.jl:79
     disc = Discretization()
     disc.n_tet, disc.n_tri, disc.dim = len(tetrahedra), len(triangles), dim
     disc.ctx, disc.mesh = ctx, mesh
@@ -192,10 +195,19 @@ def discretize(mesh, dscrp, C, order="lin", b="__none__", mass_weighting=True, s
             mid = ctx.assemble(pid, _lib.OP_STIFF, C_tet[simplices])
             disc.ops.append({"op": "stiff", "pid": pid, "simplices": simplices, "mat": mid})
             L.push(Term(dm(mid), tuple(funcs), tuple(args), txt, "K"))
-        elif typ == "admittance":
+        elif typ in ("admittance", "speaker"):
+            if typ == "speaker":  # Helmholtz.jl:253-258
+                speak_sym, speak_val = data[:2]
+                rhs.params[speak_sym] = complex(speak_val)
+                data = tuple(data[2:])
+                if not data:
+                    raise ValueError(":speaker needs an admittance after (symbol, value): the source scalar is built from it")
             if len(data) == 2:
                 adm_sym, adm_val = data
-                L.params.setdefault(adm_sym, complex(adm_val))
+                if adm_sym not in L.params:  # :266-271
+                    L.params[adm_sym] = complex(adm_val)
+                    if typ == "speaker":
+                        rhs.params[adm_sym] = complex(adm_val)
                 bfunc, barg, btxt = (pow1, pow1), (("ω",), (adm_sym,)), "ω*" + adm_sym
             elif len(data) == 1:
                 bfunc, barg, btxt = (generate_z_g_z(data[0]),), (("ω",),), "ω*Y(ω)"
@@ -207,6 +219,10 @@ def discretize(mesh, dscrp, C, order="lin", b="__none__", mass_weighting=True, s
             disc.patterns[(2, domain)] = pid
             mid = ctx.assemble(pid, _lib.OP_BOUNDARY, C_tri[simplices])
             disc.ops.append({"op": "boundary", "pid": pid, "simplices": simplices, "mat": mid})
+            if typ == "speaker":  # opr == :m (:488-503) comes before :C in the reference's `make`; the two families are independent
+                m = ctx.assemble_wallsrc(simplices, C_tri[simplices], dim)
+                disc.ops.append({"op": "wallsrc", "simplices": simplices, "vec": m})
+                rhs.push(Term(m, bfunc + (pow1,), barg + ((speak_sym,),), "speaker", "m"))
             L.push(Term(dm(mid), bfunc, barg, btxt, "C"))
         elif typ in ("flame", "flameresponse", "fancyflame"):
             ref_idx = -1
@@ -284,7 +300,7 @@ def discretize(mesh, dscrp, C, order="lin", b="__none__", mass_weighting=True, s
             D = sp.csc_matrix((1.0 / diag[DI], (DI, DI)), shape=(dim, dim))
             L.push(Term(DeviceMatrix.from_scipy(D, ctx), (bloch["anti_filt"],), ((b,),), "(1-δ(b))", "D"))
         L.push(Term(aux, (pow1,), (("λ",),), "-λ", "__aux__"))
-        return L
+        return (L, rhs) if source else L
     if mass_weighting:
         # Helmholtz.jl:528-540,572-574: -M over ALL tetrahedra
         key = (3, "__all__")
@@ -293,4 +309,4 @@ def discretize(mesh, dscrp, C, order="lin", b="__none__", mass_weighting=True, s
         mid = ctx.assemble(disc.patterns[key], _lib.OP_MASS, None, scale=-1.0)
         disc.ops.append({"op": "mass", "pid": disc.patterns[key], "scale": -1.0, "mat": mid})
         L.push(Term(dm(mid), (pow1,), (("λ",),), "-λ", "__aux__"))
-    return L
+    return (L, rhs) if source else L

@@ -447,6 +447,47 @@ class LinearOperatorFamily:
         return DeviceOperator(dev, dev.flat(sc))
 
 
+class VectorFamily(LinearOperatorFamily):
+    """The ``rhs`` of ``discretize(...; source=true)`` (Helmholtz.jl:79, 524-526): a LinearOperatorFamily whose coefficients are
+    vectors.  The coefficients are boundary-sized and live on the host as dense complex arrays (assembled on the device by
+    wae_assemble_wallsrc); calling the family returns ``Array(rhs(ω))``, ready for ``L(ω).solve(...)``."""
+
+    def push(self, T):
+        for idx, t in enumerate(self.terms):
+            if (t.func, t.params) == (T.func, T.params):
+                coeff = t.coeff + T.coeff
+                if not np.any(coeff):
+                    del self.terms[idx]
+                else:
+                    self.terms[idx] = Term(coeff, t.func, t.params, t.symbol, t.operator)
+                return self
+        for pars in T.params:
+            for p in pars:
+                self.params.setdefault(p, _NAN)
+        self.terms.append(T)
+        return self
+
+    def size(self):
+        return len(self.terms[0].coeff) if self.terms else 0
+
+    def device(self):
+        raise TypeError("a vector family has no device operator")
+
+    def __call__(self, *args):
+        na = len(self.active)
+        if self.mode == "all":
+            for v, val in zip(self.active, args):
+                self.params[v] = complex(val)
+        derivs = [0] * na if (self.mode == "all" and len(args) == na) else [int(a) for a in args[len(args) - na:]]
+        out = np.zeros(self.size(), dtype=np.complex128)
+        for t, s in zip(self.terms, self.scalars(derivs)):
+            if s is not None:
+                out += s * t.coeff
+        if self.mode in ("compact", "householder"):
+            out /= math.prod(math.factorial(int(a)) for a in args[len(args) - na:])
+        return out
+
+
 # --------------------------------------------------------------------------------------------- perturbation
 def _partitions(n):
     a = [0] * (n + 1)
