@@ -106,6 +106,22 @@ def test_beyn_prose_values(rijke):
         assert abs(sol.params["ω"] - om) < 5e-3 * abs(om)  # N=32 on a thin rectangle: quadrature-limited
 
 
+def test_tutorial_01_local_solver_prose(rijke):
+    """docs/src/tutorial_01_rijke_tube.md:216-269: `mslp(L, 250*2*pi)` without a stopping criterion runs its ten iterations and returns
+    flag 1 ("the maximum number of iterations has been reached") at the 272 Hz mode; after `L.params[:n] = 1` the third-order call
+    `mslp(L, 245*2*pi - 82im*2*pi, order=3)` lands on the active mode whose growth rate is "≈ 59.22" -- the same eigenvalue as G4."""
+    mesh, c = rijke
+    L = discretize(mesh, rijke_dscrp(0.0, 0.001), c)
+    sol, n, flag = mslp(L, 250 * 2 * math.pi)
+    assert (n, flag) == (10, 1) and abs(sol.params["ω"].real / 2 / math.pi - 272) < 0.5 and abs(sol.params["ω"].imag) < 1e-6
+    L.params["n"] = 1
+    sol, n, flag = mslp(L, (245 - 82j) * 2 * math.pi, order=3)
+    w = sol.params["ω"]
+    assert round(abs(w.imag) / 2 / math.pi, 2) == 59.22
+    g4 = 1075.325211506839 + 372.1017670372039j
+    assert abs(w - g4) / abs(g4) < TOL
+
+
 def test_perturb_fast_goldens(rijke):
     """G8/G9 (docs/src/tutorial_04_perturbation_theory.md:112-155): 20th-order power series of omega(tau) by perturb_fast!, its value
     at tau + 0.5 ms and the first-order value; perturb! (the slow algorithm) and perturb_norm! give the same eigenvalue series."""
