@@ -575,8 +575,14 @@ void wae_launch_assemble_gather(wae_ctx* h, Pattern& P, const double* d_c, doubl
   const size_t smem = (size_t)slot_bytes + 2 * (size_t)buf_bytes;
   const int dbg = getenv("WAE_GATHER_DBG") ? atoi(getenv("WAE_GATHER_DBG")) : 0;
   int threads = smem > 113 * 1024 ? 1024 : 512;  // one or two CTAs per SM, 64 registers per thread either way
-  if (const char* env = getenv("WAE_GATHER_THREADS")) threads = atoi(env);
-  const int grid = std::min(G.n_patch, h->sm_count * (smem > 113 * 1024 ? 1 : 2));
+  int ctas = smem > 113 * 1024 ? 1 : 2;
+  if (const char* env = getenv("WAE_GATHER_CTAS")) {  // tuning: more, smaller CTAs per SM (with WAE_GATHER_SLOTS small enough to fit)
+    const int fit = (int)((227 * 1024) / (smem + 1024));
+    ctas = std::max(1, std::min(atoi(env), fit));
+    threads = std::max(128, (1024 / ctas) & ~31);
+  }
+  if (const char* env = getenv("WAE_GATHER_THREADS")) threads = std::max(32, std::min(1024, atoi(env) & ~31));
+  const int grid = std::min(G.n_patch, h->sm_count * ctas);
   auto launch = [&](auto kern) {
     // per device, and cheap: set on every launch (a process may hold contexts on several GPUs)
     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
