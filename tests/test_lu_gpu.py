@@ -110,17 +110,6 @@ def test_mslp_goldens_gpu(tau, start, omega):
     assert abs(sol.params["ω"] - omega) / abs(omega) < TOL
 
 
-def test_tutorial_01_third_order_mslp_gpu():
-    """docs/src/tutorial_01_rijke_tube.md:258-269: mslp(L, 245*2*pi - 82im*2*pi, order=3) at n = 1 -> growth rate "≈ 59.22", the G4
-    eigenvalue (a stopping criterion is given here: without one the iteration keeps factorising the converged, singular L(ω))."""
-    import wae_b200 as W
-    L = _gpu_family("lin", n=1.0, tau=0.001)
-    sol, n, flag = W.mslp(L, (245 - 82j) * 2 * math.pi, order=3, maxiter=15, tol=1e-10, output=False)
-    g4 = 1075.325211506839 + 372.1017670372039j
-    assert flag == 0 and abs(sol.params["ω"] - g4) / abs(g4) < TOL
-    assert round(abs(sol.params["ω"].imag) / 2 / math.pi, 2) == 59.22
-
-
 def test_householder_quad_and_eigenvectors_vs_oracle():
     """P2 elements, higher-order Householder update and eigenvector parity (1e-8 after phase normalisation)."""
     import wae_b200 as W

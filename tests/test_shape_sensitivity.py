@@ -2,7 +2,7 @@
 descriptor -> terms, per-point simplex lists, post-processing) and the per-thread function of the CUDA kernel replayed on the
 host (wae_shape_sens_check) against the oracle's literal restatement (six discretize calls per point on reduced domains), and
 the oracle itself against true finite differences of the eigenvalue.  The GPU launch of the same function is tested in
-test_shape_sensitivity_gpu.py."""
+test_zy_shape_sensitivity_gpu.py."""
 import ctypes as C
 import math
 import os
