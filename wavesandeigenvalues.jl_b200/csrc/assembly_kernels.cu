@@ -416,7 +416,8 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes
 // are prefetched into L2, and the descriptor of patch i+2 is fetched.
 // MODE bit 0: mass -> out_m, bit 1: stiffness -> out_k
 // VAR selects variants prepared from the phase shares of profiles/r01_ncu_assembly_phase_shares.txt (WAE_ASM_VARIANT, default 0 =
-// the measured kernel).  bit 0: summation loop unrolled by four (the pass is latency-bound: one 16-byte load in flight per warp);
+// the measured kernel).  bit 0: summation with four 16-byte loads in flight per warp -- the first four sources under predicates, the rest
+// unrolled by four (the pass is latency-bound: the rolled loop has one load in flight per warp);
 // bit 1: the element pass of a P2 patch split into three parts per element (a patch stages ~350 elements, i.e. 11 of the 32 warps
 // had work; every part recomputes the geometry and visits a third of the packed triangle).  Same sums in the same order.
 template <int NLOC, int MODE, int VAR>
@@ -520,6 +521,16 @@ __global__ void __launch_bounds__(1024, 1) assemble_tet_pairs(const int64_t* __r
       };
       int k = 0;
       if constexpr (VAR & 1) {
+        // most units have two to four sources (74 sources on 28 units per P2 tetrahedron): the first four loads are issued back to back
+        // under predicates, missing sources contribute +0.0 (bitwise neutral after the first addition to the +0.0 start value)
+        double x0 = 0.0, y0 = 0.0, x1 = 0.0, y1 = 0.0, x2 = 0.0, y2 = 0.0, x3 = 0.0, y3 = 0.0;
+        if (cn > 0) lds(0, x0, y0);
+        if (cn > 1) lds(1, x1, y1);
+        if (cn > 2) lds(2, x2, y2);
+        if (cn > 3) lds(3, x3, y3);
+        ak = (((ak + x0) + x1) + x2) + x3;
+        am = (((am + y0) + y1) + y2) + y3;
+        k = cn < 4 ? cn : 4;
 #pragma unroll 1
         for (; k + 4 <= cn; k += 4) {  // four loads in flight, then the same left-to-right sum as the rolled loop
           double x0, y0, x1, y1, x2, y2, x3, y3;
