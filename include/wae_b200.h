@@ -150,6 +150,13 @@ int32_t wae_lu_factor(wae_ctx* h, int32_t lu_id, int32_t slot);
 /* In-place solve op(A) X = B; trans as above; X dim x nrhs column-major complex host array. */
 int32_t wae_lu_solve(wae_ctx* h, int32_t lu_id, int32_t trans, int32_t nrhs, double* X);
 
+/* Host-only (needs no GPU and no context): the reference's simplex numbering rule for n simplices of k = 2, 3 or 4 vertices
+ * (simp: n x k, row-major, ids in [0, 2^32)): unique vertex sets in ascending order of their DESCENDING-sorted vertex tuple, the
+ * first occurrence of a set is its representative (src/Mesh/sorter.jl:9-31; Meshutils.jl:92-165; collect_lines! :831-840).
+ * first[u] (u < *n_unique, array of n) = input row of unique simplex u, inv[i] (n) = unique index of input row i.
+ * Replaces the reference's O(n^2) list insertion with one thread-parallel sort.                                 */
+int32_t wae_sorted_unique_simplices(int64_t n, int32_t k, const int64_t* simp, int64_t* first, int64_t* inv, int64_t* n_unique);
+
 /* Host-only diagnostic (needs no GPU and no context): run the symbolic phase on a CSC pattern (0-based) and
  * report out[0..7] = supernodes, nnz(L+U), factorisation flops, largest pivot block, largest row structure,
  * tree depth, factor array entries, largest per-depth update buffer.  coords (n x 3) may be NULL.          */

@@ -316,3 +316,32 @@ def test_octosplit_tie_break_and_empty_surface():
     ab, cd = 4 + mg.edge_index(np.array([0]), np.array([1]))[0], 4 + mg.edge_index(np.array([2]), np.array([3]))[0]
     assert sum(1 for t in sg.tetrahedra if ab in t and cd in t) == 4
     assert list(sg.domains["A"]["simplices"]) == list(range(8))
+
+
+def test_native_simplex_numbering_equals_the_numpy_path():
+    """wae_sorted_unique_simplices (csrc/mesh_symbolic.cpp, thread-parallel sort) against the vectorised numpy rule it replaces for large
+    inputs: unique simplices, representatives (first occurrence, input vertex order) and the raw -> unique map, for edges, triangles and
+    tetrahedra, with many repeated vertex sets, ids up to 2^31 and sizes on both sides of the threading threshold."""
+    import numpy as np
+    from wae_b200 import meshutils as mu
+    rng = np.random.default_rng(11)
+    for k in (2, 3, 4):
+        for n, hi in ((1, 5), (7, 3), (3000, 40), (70000, 900), (70000, 2**31)):
+            s = rng.integers(0, hi, size=(n, k))
+            a, ia = mu._sorted_unique(s, native=False)
+            b, ib = mu._sorted_unique(s, native=True)
+            assert np.array_equal(a, b) and np.array_equal(ia, ib), (k, n, hi)
+    # the six edges of every tetrahedron of a Kuhn box (collect_lines): what the P2 numbering of the big configurations is built from
+    mesh = mu.kuhn_box((12, 9, 11), (0, 0, 0), (1, 1, 1))
+    t = mesh.tetrahedra
+    pairs = np.stack([t[:, [0, 1]], t[:, [0, 2]], t[:, [0, 3]], t[:, [1, 2]], t[:, [1, 3]], t[:, [2, 3]]], axis=1).reshape(-1, 2)
+    a, ia = mu._sorted_unique(pairs, native=False)
+    b, ib = mu._sorted_unique(pairs, native=True)
+    nx, ny, nz = 12, 9, 11  # Kuhn triangulation: axis edges + one diagonal per cube face + one body diagonal per cube
+    n_edges = (nx * (ny + 1) * (nz + 1) + (nx + 1) * ny * (nz + 1) + (nx + 1) * (ny + 1) * nz
+               + nx * ny * (nz + 1) + nx * (ny + 1) * nz + (nx + 1) * ny * nz + nx * ny * nz)
+    assert np.array_equal(a, b) and np.array_equal(ia, ib) and len(a) == n_edges
+    # ids outside [0, 2^32) are rejected by the library and fall back to the numpy rule
+    big = np.array([[2**33, 1], [1, 2**33], [0, 1]])
+    c, ic = mu._sorted_unique(big, native=True)
+    assert np.array_equal(c, np.array([[0, 1], [2**33, 1]])) and list(ic) == [1, 1, 0]

@@ -80,6 +80,7 @@ SIGNATURES = {
     "wae_shape_sens_begin": (_i32, [_vp, _i64, _pi64, _pi64, _dbl, _i32, _i64, _pd, _pd, _pi64, C.POINTER(C.c_uint8), _pd]),
     "wae_shape_sens_add": (_i32, [_vp, _i32, _pi64, _pi64, _pd, _i32, _pd, _i64, _pd, _dbl]),
     "wae_shape_sens_end": (_i32, [_vp, _pd]),
+    "wae_sorted_unique_simplices": (_i32, [_i64, _i32, _pi64, _pi64, _pi64, _pi64]),  # host-only: no context argument
 }
 # host-only diagnostics (no context, no GPU): used by the CPU tests, never by the product path
 HOST_DIAGNOSTICS = ("wae_lu_symbolic_stats", "wae_pair_program_check", "wae_shape_sens_check")
@@ -95,6 +96,20 @@ def _declare(l):
 
 def _p(a, typ):
     return None if a is None else a.ctypes.data_as(typ)
+
+
+def sorted_unique_simplices(simp):
+    """(first, inv) of the reference's simplex numbering rule (host-side, thread-parallel sort; see include/wae_b200.h): the unique
+    simplices in order are ``simp[first]``, ``inv[i]`` is the unique index of input row i."""
+    simp = np.ascontiguousarray(simp, dtype=np.int64)
+    n, k = simp.shape
+    first = np.empty(n, dtype=np.int64)
+    inv = np.empty(n, dtype=np.int64)
+    nu = _i64()
+    rc = lib().wae_sorted_unique_simplices(n, k, _p(simp, _pi64), _p(first, _pi64), _p(inv, _pi64), C.byref(nu))
+    if rc != OK:
+        raise WaeError(rc, "wae_sorted_unique_simplices: vertex ids must lie in [0, 2^32) and simplices have 2, 3 or 4 vertices")
+    return first[:nu.value], inv
 
 
 class Context:

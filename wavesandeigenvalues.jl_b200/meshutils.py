@@ -19,12 +19,10 @@ plus synthetic structured (Kuhn 6-tet) generators for the large benchmark config
 import numpy as np
 
 
-def _sorted_unique(simp):
-    """simp: (n,k) int array in file order -> (unique sorted simplices, index map raw->sorted)."""
-    simp = np.asarray(simp, dtype=np.int64)
-    if len(simp) == 0:
-        return simp, np.zeros(0, dtype=np.int64)
-    simp = simp.reshape(len(simp), -1)
+_NATIVE_MIN = 1 << 15  # below this the numpy path is as fast as the call into the library
+
+
+def _sorted_unique_numpy(simp):
     key = -np.sort(-simp, axis=1)  # descending-sorted vertex tuple
     order = np.lexsort([np.arange(len(simp))] + [key[:, c] for c in range(key.shape[1] - 1, -1, -1)])
     ks = key[order]
@@ -34,6 +32,23 @@ def _sorted_unique(simp):
     inv = np.empty(len(simp), dtype=np.int64)
     inv[order] = grp
     return simp[order[first]], inv
+
+
+def _sorted_unique(simp, native=None):
+    """simp: (n,k) int array in file order -> (unique sorted simplices, index map raw->sorted).  Large inputs (the 6 n_tet edges of
+    collect_lines, the simplex lists of big meshes) go through the library's thread-parallel sort (csrc/mesh_symbolic.cpp); both
+    paths give the same numbering (tests/test_host_logic.py)."""
+    simp = np.asarray(simp, dtype=np.int64)
+    if len(simp) == 0:
+        return simp, np.zeros(0, dtype=np.int64)
+    simp = simp.reshape(len(simp), -1)
+    if native is None:
+        native = len(simp) >= _NATIVE_MIN
+    if native and 2 <= simp.shape[1] <= 4 and simp.min() >= 0 and simp.max() < 2**32:
+        from ._lib import sorted_unique_simplices
+        first, inv = sorted_unique_simplices(simp)
+        return simp[first], inv
+    return _sorted_unique_numpy(simp)
 
 
 def read_msh4(fname):
