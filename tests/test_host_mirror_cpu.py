@@ -1,0 +1,118 @@
+"""The product's HOST MIRROR of the reference interface (wavesandeigenvalues.jl_b200/{helmholtz,nlevp,shape}.py) exercised without a GPU:
+the context object is replaced by the test double of tests/host_standin.py (oracle element routines + scipy behind the Context method
+names), so what is tested here is the Python above the C ABI -- descriptor parsing, term and parameter bookkeeping, the Newton / mslp
+loops with their flags, perturbation series, the forced-response wiring and the argument marshalling of the shape-sensitivity sequence --
+against the reference's golden values and the oracle.  The CUDA kernels themselves are covered by the `-m gpu` tests only."""
+import math
+
+import numpy as np
+import pytest
+import scipy.sparse.linalg as spla
+
+import wae_b200 as W
+from cases import G9_APPROX_20, GAMMA, N_REF, Q02U0, RHO, X_REF, load_raw_mesh, rijke_dscrp, speedofsound
+from host_standin import HostStandIn
+from oracle import helmholtz as ohelm
+from oracle import mesh as omesh
+
+TOL = 1e-10
+
+
+@pytest.fixture(scope="module")
+def rijke():
+    raw = load_raw_mesh("rijke_mm")
+    mg, mo = W.Mesh("m", scale=0.001, raw=raw), omesh.Mesh("m", scale=0.001, raw=raw)
+    return mg, mo, mg.generate_field(speedofsound)
+
+
+def test_discretize_terms_and_householder_golden(rijke):
+    """G1 (tutorial_04 notebook cell 5) through the product's discretize + LinearOperatorFamily + householder."""
+    mg, mo, c = rijke
+    ctx = HostStandIn()
+    L = W.discretize(mg, rijke_dscrp(0.01, 0.001), c, ctx=ctx)
+    Lo = ohelm.discretize(mo, rijke_dscrp(0.01, 0.001), c)
+    assert [(t.operator, t.symbol, t.params) for t in L.terms] == [(t.operator, t.symbol, t.params) for t in Lo.terms]
+    assert L.params == Lo.params
+    for tg, to in zip(L.terms, Lo.terms):
+        assert abs(tg.coeff.to_scipy() - to.coeff).max() <= 1e-12 * abs(to.coeff).max()
+    sol, n, flag = W.householder(L, 340 * 2 * math.pi, maxiter=20, tol=1e-11, output=False)
+    g1 = 1710.6977772393461 + 9.615018460173488j
+    assert flag == 1 and n in (6, 7, 8) and abs(sol.params["ω"] - g1) / abs(g1) < TOL
+    assert L.active == ["ω"] and L.mode == "all"  # restored (LinOpFam.jl:546-560 toggles them around the perturbation calls)
+    # the returned vectors are normalised as at Householder.jl:189-190
+    M = -L.terms[-1].coeff.to_scipy()
+    assert abs(np.vdot(sol.v, M @ sol.v) - 1) < 1e-10
+
+
+def test_mslp_golden_flags_and_perturb_fast(rijke):
+    """G4 (mslp, flag 0) and G9 (20th-order perturb_fast! evaluated at tau + 0.5 ms) through the product's host loops."""
+    mg, mo, c = rijke
+    L = W.discretize(mg, rijke_dscrp(1.0, 0.001), c, ctx=HostStandIn())
+    sol, n, flag = W.mslp(L, 340 * 2 * math.pi, maxiter=20, tol=1e-11, output=False)
+    g4 = 1075.325211506839 + 372.1017670372039j
+    assert flag == 0 and abs(sol.params["ω"] - g4) / abs(g4) < TOL
+    sol2, n2, flag2 = W.mslp(L, 340 * 2 * math.pi, maxiter=3, tol=1e-11, output=False)
+    assert flag2 == 1 and n2 == 3  # maxiter reached (iterative_solvers.jl:232-234)
+    W.perturb_fast_bang(sol, L, "τ", 20)
+    assert abs(sol("τ", 0.001 + 0.0005, 20) - G9_APPROX_20) / abs(G9_APPROX_20) < 1e-9
+
+
+@pytest.mark.parametrize("order", ["lin", "quad"])
+def test_forced_response_wiring(rijke, order):
+    """discretize(...; source=True) / :speaker / VectorFamily / L(ω).solve(rhs(ω)) against the oracle (tutorial_09_forcing.md)."""
+    mg, mo, c = rijke
+    dscrp = rijke_dscrp(0.01, 0.001)
+    dscrp["Outlet"] = ("speaker", ("A", 1, "Y", 1e15))
+    L, rhs = W.discretize(mg, dscrp, c, order=order, source=True, ctx=HostStandIn())
+    Lo, rhso = ohelm.discretize(mo, dscrp, c, order=order, source=True)
+    assert rhs.params == rhso.params and [(t.operator, t.params) for t in rhs.terms] == [(t.operator, t.params) for t in rhso.terms]
+    assert [(t.operator, t.params) for t in L.terms] == [(t.operator, t.params) for t in Lo.terms]
+    w = 2 * math.pi * 150.0
+    b, bo = rhs(w), rhso(w).toarray().ravel()
+    assert np.abs(b - bo).max() <= 1e-13 * np.abs(bo).max()
+    sol, want = L(w).solve(b), spla.spsolve(Lo(w).tocsc(), bo)
+    assert np.abs(sol - want).max() <= 1e-9 * np.abs(want).max()
+    rhs.params["A"] = 2.0  # tutorial_09_forcing.md:82-86: the excitation level can be reset afterwards
+    assert np.allclose(rhs(w), 2 * b, rtol=1e-14, atol=0)
+    # two speakers, per-point c, functional admittance; in-place re-assembly refreshes the source vectors
+    Yf = lambda w_, k=0: (2.0 + 0.001j * w_) if k == 0 else (0.001j if k == 1 else 0.0)
+    cpt = np.array([speedofsound(*mo.points[:, i]) * (1 + 0.1 * math.sin(40 * mo.points[2, i])) for i in range(mo.points.shape[1])])
+    dscrp2 = {"Interior": ("interior", ()), "Outlet": ("speaker", ("A", 1.5, "Y", 0.7)), "Inlet": ("speaker", ("B", 0.5j, Yf))}
+    L2, rhs2 = W.discretize(mg, dscrp2, cpt, order=order, source=True, ctx=HostStandIn())
+    _, rhso2 = ohelm.discretize(mo, dscrp2, cpt, order=order, source=True)
+    bo = rhso2(w).toarray().ravel()
+    assert len(rhs2.terms) == 2 and np.abs(rhs2(w) - bo).max() <= 1e-13 * np.abs(bo).max()
+    L2.discretization.reassemble(1.1 * cpt)
+    _, rhso3 = ohelm.discretize(mo, dscrp2, 1.1 * cpt, order=order, source=True)
+    b3 = rhso3(w).toarray().ravel()
+    assert np.abs(rhs2(w) - b3).max() <= 1e-13 * np.abs(b3).max()
+    with pytest.raises(ValueError):
+        W.discretize(mg, {"Interior": ("interior", ()), "Outlet": ("speaker", ("A", 1))}, c, source=True, ctx=HostStandIn())
+
+
+def test_shape_sensitivity_call_sequence(rijke):
+    """discrete_adjoint_shape_sensitivity of the product (normalisation, descriptor -> terms, per-point lists, begin/add/end marshalling)
+    with the kernel's per-thread function replayed on the host, against the oracle's literal loop on a subset of the surface points."""
+    from oracle import nlevp as onlevp
+    from oracle import shape as oshape
+    mg, mo, c = rijke
+    ref_idx = mg.find_tetrahedron_containing_point(X_REF)
+    dscrp = {"Interior": ("interior", ()), "Outlet": ("admittance", ("Y", 1e15)),
+             "Flame": ("flame", (GAMMA, RHO, Q02U0, ref_idx, X_REF, N_REF, "n", "τ", 1.0, 0.001))}
+    ctx = HostStandIn()
+    L = W.discretize(mg, dscrp, c, ctx=ctx)
+    sol, n, flag = W.householder(L, 700 * 2 * math.pi, maxiter=14, tol=1e-11, output=False)
+    assert flag == 1
+    sp_, trm, ttm = W.get_surface_points(mg)
+    flame = set(np.asarray(mg.tetrahedra)[mg.domains["Flame"]["simplices"]].ravel().tolist())
+    sub = sorted(set(range(0, len(sp_), 60)) | set([k for k, p in enumerate(sp_) if p in flame][:4]))
+    pick = lambda lst: [lst[k] for k in sub]
+    sens = W.discrete_adjoint_shape_sensitivity(mg, dscrp, c, sp_[sub], pick(trm), pick(ttm), L, sol, ctx=ctx)
+    assert sens.shape == (3, mg.points.shape[1]) and np.count_nonzero(np.abs(sens).sum(axis=0)) == len(sub)
+    Lo = ohelm.discretize(mo, dscrp, c)
+    solo, _, _ = onlevp.householder(Lo, 700 * 2 * math.pi, maxiter=14, tol=1e-11)
+    so, tro, tto = oshape.get_surface_points(mo)
+    want = oshape.discrete_adjoint_shape_sensitivity(mo, dscrp, c, [so[k] for k in sub], [tro[k] for k in sub], [tto[k] for k in sub], Lo, solo)
+    assert np.abs(sens - want).max() <= 1e-5 * np.abs(want).max()
+    # the family and the solution survive the call (the context keeps one mesh at a time: same topology, patterns stay valid)
+    assert abs(L(sol.params["ω"]).matvec(sol.v)).max() <= 1e-6 * abs(L(sol.params["ω"], 1).matvec(sol.v)).max() * abs(sol.params["ω"])
