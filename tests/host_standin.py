@@ -83,13 +83,12 @@ class HostStandIn:
         return len(self.mats) - 1
 
     # -- assembly (element routines of the oracle, Helmholtz.jl:405-503) -----------------------------------------------------------
-    def _elements(self, pid, kind, c, scale):
-        p = self.pats[pid]
-        conn = self.tets if p["kind"] == 3 else self.tris
+    def _triplets(self, elem_kind, ids, kind, c, scale):
+        conn = self.tets if elem_kind == 3 else self.tris
         I, J, V = [], [], []
-        for k, e in enumerate(p["elems"]):
+        for k, e in enumerate(ids):
             s = conn[e]
-            ct = fem.CooTrafo(self.P[:, s[:4 if p["kind"] == 3 else 3]])
+            ct = fem.CooTrafo(self.P[:, s[:4 if elem_kind == 3 else 3]])
             if kind == _lib.OP_MASS:
                 vv = fem.tet_mass(ct, self.order) * scale
             elif kind == _lib.OP_STIFF:
@@ -98,7 +97,11 @@ class HostStandIn:
                 vv = (c[k] * fem.tri_mass(ct, self.order) if np.ndim(c[k]) == 0 else fem.tri_mass_c1(ct, c[k], self.order)) * (-1j * scale)
             ii, jj = fem.create_indices(s)
             I.extend(ii.T.ravel()); J.extend(jj.T.ravel()); V.extend(np.asarray(vv).T.ravel())
-        return self._align(pid, I, J, np.asarray(V, dtype=complex))
+        return np.asarray(I, dtype=np.int64), np.asarray(J, dtype=np.int64), np.asarray(V, dtype=complex)
+
+    def _elements(self, pid, kind, c, scale):
+        p = self.pats[pid]
+        return self._align(pid, *self._triplets(p["kind"], p["elems"], kind, c, scale))
 
     def assemble(self, pid, kind, c=None, scale=1.0, reuse=-1):
         self._ms["assemble"] = 0.0
@@ -137,8 +140,30 @@ class HostStandIn:
         self.launches += 1
         return out
 
-    def assemble_bloch(self, *a, **k):
-        raise NotImplementedError("the Bloch class split is device code: covered by the GPU tests (tests/test_bloch.py)")
+    def assemble_bloch(self, elem_kind, elem_ids, kind, c, scale, dim_red, dof_new, dof_flag, n_class):
+        """Bloch.jl:4-112 as the library does it: DOFs folded through dof_new, every element entry sorted into the classes plain / +
+        (column DOF is an image) / - (row DOF is an image), each once more for entries touching an axis DOF when n_class == 6;
+        n_class == 1 sums everything (the weighting matrix, Helmholtz.jl:541-549)."""
+        conn = self.tets if elem_kind == 3 else self.tris
+        ids = np.arange(len(conn)) if elem_ids is None else np.asarray(elem_ids, dtype=np.int64)
+        I, J, V = self._triplets(elem_kind, ids, kind, None if c is None else np.asarray(c, dtype=float), scale)
+        dof_new, dof_flag = np.asarray(dof_new, dtype=np.int64), np.asarray(dof_flag, dtype=np.uint8)
+        fi, fj = dof_flag[I], dof_flag[J]
+        cls = np.zeros(len(I), dtype=np.int64)
+        if n_class > 1:
+            ic, jc = (fi & 1).astype(bool), (fj & 1).astype(bool)
+            cls = np.where(ic == jc, 0, np.where(jc, 1, 2))
+            if n_class == 6:
+                cls = cls + 3 * (((fi | fj) & 2) != 0)
+        pids, mids = [], []
+        for k in range(n_class):
+            m = cls == k
+            pid, _ = self._new_pattern(dim_red, dof_new[I[m]], dof_new[J[m]])
+            pids.append(pid)
+            mids.append(self._store(pid, self._align(pid, dof_new[I[m]], dof_new[J[m]], V[m])))
+        self._ms["assemble"] = 0.0
+        self.launches += 1
+        return pids, mids
 
     # -- matrices / families -----------------------------------------------------------------------------------------------------
     def mat_info(self, mid):

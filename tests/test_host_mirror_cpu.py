@@ -116,3 +116,43 @@ def test_shape_sensitivity_call_sequence(rijke):
     assert np.abs(sens - want).max() <= 1e-5 * np.abs(want).max()
     # the family and the solution survive the call (the context keeps one mesh at a time: same topology, patterns stay valid)
     assert abs(L(sol.params["ω"]).matvec(sol.v)).max() <= 1e-6 * abs(L(sol.params["ω"], 1).matvec(sol.v)).max() * abs(sol.params["ω"])
+
+
+def test_bloch_discretize_and_unit_cell_shape_sensitivity():
+    """Config-4 host path on the reference's NTNU_12 mesh: extend_mesh(unit=true) -> discretize(b) (term list, class scalars, folded
+    dimension, penalty term) vs the oracle; mslp at b = 1 next to the plenum mode; then the unit-cell branch of
+    discrete_adjoint_shape_sensitivity (shape_sensitivity.jl:84-118: axis points skipped, Bloch-plane points paired with their images,
+    cylindrical moves, DOF folding and class phase handed to the kernel) against the independent replay of test_shape_sensitivity.py for
+    ALL 846 surface points."""
+    from oracle import nlevp as onlevp
+    from oracle.mesh import extend_mesh as oext
+    from test_bloch import NTNU_DOMS, NTNU_DSCRP, _ntnu_meshes, _ntnu_sos
+    from test_shape_sensitivity import host_replay
+    mg, mo = _ntnu_meshes()
+    doms = NTNU_DOMS + [("CC", "half")]
+    g, o = W.extend_mesh(mg, doms, unit=True), oext(mo, doms, unit=True)
+    c = g.generate_field(_ntnu_sos)
+    dscrp = dict(NTNU_DSCRP)
+    dscrp["Outlet_high"] = ("admittance", ("Y_in", 0.2 + 0.1j))
+    ctx = HostStandIn()
+    L = W.discretize(g, dscrp, c, b="b", ctx=ctx)
+    Lo = ohelm.discretize(o, dscrp, c, b="b")
+    assert [t.operator for t in L.terms] == [t.operator for t in Lo.terms] and L.size() == Lo.size()
+    for bb in (0, 1, 2):
+        L.params["b"] = Lo.params["b"] = complex(bb)
+        A, Ao = L(5000.0).to_scipy(), Lo(5000.0)
+        assert abs(A - Ao).max() <= 1e-12 * abs(Ao).max()
+    L.params["b"] = Lo.params["b"] = 1 + 0j
+    sol, n, flag = W.mslp(L, 1146.0, maxiter=20, tol=1e-9, scale=2 * math.pi, output=False)
+    solo, _, flo = onlevp.mslp(Lo, 1146.0, maxiter=20, tol=1e-9, scale=2 * math.pi)
+    assert flag == flo == 0 and abs(sol.params["ω"] - solo.params["ω"]) <= 1e-9 * abs(solo.params["ω"])
+    assert 1000 < sol.params["ω"].real / 2 / math.pi < 1250
+    sp_, trm, ttm = W.get_surface_points(g)
+    sens = W.discrete_adjoint_shape_sensitivity(g, dscrp, c, sp_, trm, ttm, L, sol, ctx=ctx)
+    w0 = sol.params["ω"]
+    v0 = sol.v / np.sqrt(np.vdot(sol.v, sol.v))
+    va = sol.v_adj / np.conj(np.vdot(sol.v_adj, L(w0, 1) @ v0))
+    rep = host_replay(g, dscrp, c, sp_, trm, ttm, w0, v0, va)
+    scale = np.abs(rep).max()
+    assert scale > 0 and np.abs(sens - rep).max() <= 1e-12 * scale
+    assert np.abs(sens[:, : g.dos.naxis]).max() == 0 and np.count_nonzero(np.abs(sens).sum(axis=0)) == len(sp_) - g.dos.naxis
