@@ -156,3 +156,37 @@ def test_bloch_discretize_and_unit_cell_shape_sensitivity():
     scale = np.abs(rep).max()
     assert scale > 0 and np.abs(sens - rep).max() <= 1e-12 * scale
     assert np.abs(sens[:, : g.dos.naxis]).max() == 0 and np.count_nonzero(np.abs(sens).sum(axis=0)) == len(sp_) - g.dos.naxis
+
+
+def test_tutorial_01_third_order_mslp_and_descriptor_variants(rijke):
+    """The host loop behind tests/test_zw_tutorial_01_gpu.py (mslp(L, 245*2*pi - 82im*2*pi, order=3) at n = 1 -> G4, growth rate 59.22) and a
+    sweep over descriptor variants (:fancyflame scalar and summed, state-space and functional admittance, :flameresponse, per-point c):
+    the product's term list, parameters and L(z) against the oracle's."""
+    mg, mo, c = rijke
+    L = W.discretize(mg, rijke_dscrp(1.0, 0.001), c, ctx=HostStandIn())
+    sol, n, flag = W.mslp(L, (245 - 82j) * 2 * math.pi, order=3, maxiter=15, tol=1e-10, output=False)
+    g4 = 1075.325211506839 + 372.1017670372039j
+    assert flag == 0 and abs(sol.params["ω"] - g4) / abs(g4) < TOL and round(abs(sol.params["ω"].imag) / 2 / math.pi, 2) == 59.22
+    sol3, n3, flag3 = W.householder(L, 170 * 2 * math.pi + 350j, maxiter=15, tol=1e-10, order=3, nev=2, output=False)
+    assert flag3 == 1 and abs(sol3.params["ω"] - g4) / abs(g4) < 1e-9
+
+    Yf = lambda w_, k=0: (2.0 + 0.001j * w_) if k == 0 else (0.001j if k == 1 else 0.0)
+    Ass, Bss, Css, Dss = np.array([[-50.0, 20.0], [-20.0, -80.0]]), np.array([[1.0], [0.5]]), np.array([[0.3, -0.2]]), np.array([[0.05]])
+    cpt = np.array([speedofsound(*mo.points[:, i]) * (1 + 0.05 * math.cos(30 * mo.points[2, i])) for i in range(mo.points.shape[1])])
+    flame = (GAMMA, RHO, Q02U0, X_REF, N_REF)
+    variants = [
+        ({"Interior": ("interior", ()), "Outlet": ("admittance", (Yf,)), "Flame": ("fancyflame", flame + ("n", "τ", "a", 0.8, 0.0011, 1e-9))}, c),
+        ({"Interior": ("interior", ()), "Outlet": ("admittance", (Ass, Bss, Css, Dss)),
+          "Flame": ("fancyflame", flame + (["n1", "n2"], ["t1", "t2"], ["a1", "a2"], [0.5, 0.3], [0.001, 0.002], [1e-9, 2e-9]))}, c),
+        ({"Interior": ("interior", ()), "Inlet": ("admittance", ("Yin", 0.4 - 0.1j)), "Outlet": ("admittance", ("Y", 1e15)),
+          "Flame": ("flameresponse", flame + ("ε", 0.02))}, cpt),
+    ]
+    for dscrp, cc in variants:
+        Lg, Lo = W.discretize(mg, dscrp, cc, order="quad", ctx=HostStandIn()), ohelm.discretize(mo, dscrp, cc, order="quad")
+        assert [(t.operator, t.params) for t in Lg.terms] == [(t.operator, t.params) for t in Lo.terms]
+        assert Lg.params.keys() == Lo.params.keys() and all(Lg.params[k] == Lo.params[k] or (Lg.params[k] != Lg.params[k]) for k in Lo.params)
+        for z in (900.0 + 30j, 2500.0 - 10j):
+            A, Ao = Lg(z).to_scipy(), Lo(z)
+            assert abs(A - Ao).max() <= 1e-12 * abs(Ao).max()
+            A1, Ao1 = Lg(z, 1).to_scipy(), Lo(z, 1)
+            assert abs(A1 - Ao1).max() <= 1e-12 * abs(Ao1).max()
