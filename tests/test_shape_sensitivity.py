@@ -142,7 +142,7 @@ def test_linear_speed_of_sound_and_descriptor_variants(rijke):
     sol, n, flag = onlevp.householder(L, 300 * 2 * math.pi, maxiter=20, tol=1e-10)
     w0, v0, va = _normalised(L, sol)
     sp_, trm, ttm = W.get_surface_points(mg)
-    sub = np.r_[0:len(sp_):9]
+    sub = np.r_[0:len(sp_):20]
     flame_pts = [k for k, p in enumerate(sp_) if p in set(np.asarray(mg.tetrahedra)[mg.domains["Flame"]["simplices"]].ravel().tolist())][:12]
     sub = np.unique(np.r_[sub, flame_pts])
     pick = lambda lst: [lst[k] for k in sub]
@@ -159,7 +159,7 @@ def test_adjoint_sensitivity_is_the_eigenvalue_derivative(rijke):
     mg, mo, c, dscrp, L, sol, ref_idx = rijke
     so, tro, tto = oshape.get_surface_points(mo)
     flame = set(np.asarray(mo.tetrahedra)[mo.domains["Flame"]["simplices"]].ravel().tolist()) | set(mo.tetrahedra[ref_idx])
-    picks = [k for k in range(5, len(so), 97) if so[k] not in flame][:6]
+    picks = [k for k in range(5, len(so), 190) if so[k] not in flame][:3]
     sens = oshape.discrete_adjoint_shape_sensitivity(mo, dscrp, c, [so[k] for k in picks], [tro[k] for k in picks], [tto[k] for k in picks], L, sol)
     w0 = sol.params[sol.eigval]
     step = 1e-6
