@@ -5,7 +5,7 @@ Restates src/Helmholtz.jl:19-33 (outer), :54-81, :120-191 (element wrappers),
 (sym,val), :flame 9/10-tuple n-tau, :flameresponse), :405-524 (element loops +
 sparse()), :528-540,:571-580 (mass weighting / __aux__ term).
 :speaker descriptors and the source=true return mode (:251-258, 488-503, 524-526,
-576-577) are restated too; custom-FTF flame variants raise NotImplementedError.
+576-577) and the custom-FTF / plain-FTF flame variants (:302-319) are restated too.
 """
 import numpy as np
 import scipy.sparse as sp
@@ -167,16 +167,27 @@ def discretize(mesh, dscrp, C, order="lin", mass_weighting=True, triplets=None, 
                 ref_idx = -1
             elif typ == "flame" and len(data) == 10:
                 gamma, rho, nglobal, ref_idx, x_ref, n_ref, n_sym, tau_sym, n_val, tau_val = data
+            elif typ == "flame" and len(data) == 6:  # :302-311 custom FTF(ω, k)
+                gamma, rho, nglobal, x_ref, n_ref, FTF = data
+                ref_idx = -1
+            elif typ == "flame" and len(data) == 5:  # :312-319 plain parameter FTF
+                gamma, rho, nglobal, x_ref, n_ref = data
+                ref_idx = -1
             elif typ == "flameresponse":
                 gamma, rho, nglobal, x_ref, n_ref, eps_sym, eps_val = data
                 ref_idx = -1
             else:
-                raise NotImplementedError("flame descriptor variant")
+                raise ValueError("Data length does not match :flame option!")
             nlocal = _div((gamma - 1) / rho * nglobal, mesh.compute_size(domain))
-            if typ == "flame":
+            if typ == "flame" and len(data) in (9, 10):
                 L.params.setdefault(n_sym, complex(n_val))
                 L.params.setdefault(tau_sym, complex(tau_val))
                 ffunc, farg, ftxt = (pow1, exp_delay), ((n_sym,), ("ω", tau_sym)), f"{n_sym}*exp(-iω{tau_sym})"
+            elif typ == "flame" and len(data) == 6:
+                ffunc, farg, ftxt = (FTF,), (("ω",),), "FTF(ω)"
+            elif typ == "flame":
+                L.params["FTF"] = 0j
+                ffunc, farg, ftxt = (pow1,), (("FTF",),), "FTF"
             else:
                 L.params.setdefault(eps_sym, complex(eps_val))
                 ffunc, farg, ftxt = (pow1,), ((eps_sym,),), eps_sym

@@ -180,11 +180,18 @@ def test_tutorial_01_third_order_mslp_and_descriptor_variants(rijke):
           "Flame": ("fancyflame", flame + (["n1", "n2"], ["t1", "t2"], ["a1", "a2"], [0.5, 0.3], [0.001, 0.002], [1e-9, 2e-9]))}, c),
         ({"Interior": ("interior", ()), "Inlet": ("admittance", ("Yin", 0.4 - 0.1j)), "Outlet": ("admittance", ("Y", 1e15)),
           "Flame": ("flameresponse", flame + ("ε", 0.02))}, cpt),
+        # docs/src/tutorial_08_custom_FTF.md: a user closure FTF(ω, k) (value and derivatives), and the plain parameter :FTF
+        ({"Interior": ("interior", ()), "Outlet": ("admittance", ("Y", 1e15)),
+          "Flame": ("flame", flame + (lambda w_, k=0: (0.7 * np.exp(-0.001j * w_) * (-0.001j) ** k),))}, c),
+        ({"Interior": ("interior", ()), "Outlet": ("admittance", ("Y", 1e15)), "Flame": ("flame", flame)}, c),
     ]
     for dscrp, cc in variants:
         Lg, Lo = W.discretize(mg, dscrp, cc, order="quad", ctx=HostStandIn()), ohelm.discretize(mo, dscrp, cc, order="quad")
         assert [(t.operator, t.params) for t in Lg.terms] == [(t.operator, t.params) for t in Lo.terms]
         assert Lg.params.keys() == Lo.params.keys() and all(Lg.params[k] == Lo.params[k] or (Lg.params[k] != Lg.params[k]) for k in Lo.params)
+        if "FTF" in Lg.params:
+            assert Lg.params["FTF"] == Lo.params["FTF"] == 0
+            Lg.params["FTF"] = Lo.params["FTF"] = 0.3 - 0.2j
         for z in (900.0 + 30j, 2500.0 - 10j):
             A, Ao = Lg(z).to_scipy(), Lo(z)
             assert abs(A - Ao).max() <= 1e-12 * abs(Ao).max()
