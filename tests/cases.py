@@ -52,3 +52,37 @@ G9_APPROX_1_HZ = 150.22496667319837 + 86.34150633981955j
 # notebook -- conv_radius, the [10/10] Pade value -- were produced after L.params had been modified in place and are not reproducible.)
 G10_APPROX_20 = 1710.8641999717368 + 9.593830019669932j
 G10_TAYLOR_01 = (1710.7 + 9.61502j, 16655.8 - 1972.54j)
+
+
+def tutorial_08_check(discretize, mslp, perturb_fast_bang, pade, polyval, mesh, c, **kw):
+    """docs/src/tutorial_08_custom_FTF.md:44-203 with either implementation: (i) the n-tau flame written as a user closure FTF(ω, k) gives
+    the eigenvalue of the built-in model (G4); (ii) the plain-FTF family H, solved passive, expanded to 16th order in the flame response
+    and closed with the FTF by Newton-Raphson on the [8/8] Pade approximant, lands on the same eigenvalue ("works like a charm")."""
+    import math
+
+    import numpy as np
+    n, tau = 1.0, 0.001
+    FTF = lambda w, k=0: n * np.exp(-1j * w * tau) * (-1j * tau) ** k
+    flame = (GAMMA, RHO, Q02U0, X_REF, N_REF)
+    base = {"Interior": ("interior", ()), "Outlet": ("admittance", ("Y", 1e15))}
+    g4 = 1075.325211506839 + 372.1017670372039j
+    L = discretize(mesh, {**base, "Flame": ("flame", flame + (FTF,))}, c, **kw)
+    sol, nn, flag = mslp(L, 340, maxiter=20, tol=1e-9, scale=2 * math.pi)
+    assert flag == 0 and abs(sol.params["ω"] - g4) / abs(g4) < 1e-10
+    H = discretize(mesh, {**base, "Flame": ("flame", flame)}, c, **kw)
+    H.params["FTF"] = 0j
+    sb, nn, flag = mslp(H, 340 * 2 * math.pi, maxiter=20, tol=1e-11)
+    assert flag == 0 and abs(sb.params["ω"].real / 2 / math.pi - 272.064) < 1e-3
+    perturb_fast_bang(sb, H, "FTF", 16)
+    a, b = pade(sb.eigval_pert["FTF/Taylor"], 8, 8)
+    d = lambda p: np.array([k * p[k] for k in range(1, len(p))])
+
+    def w(z, k=0):
+        P, Q = polyval(a, z), polyval(b, z)
+        return P / Q if k == 0 else (polyval(d(a), z) * Q - P * polyval(d(b), z)) / Q**2
+    eta = 0j
+    for _ in range(10):
+        om = w(eta)
+        eta -= (FTF(om) - eta) / (FTF(om, 1) * w(eta, 1) - 1)
+    assert abs(FTF(w(eta)) - eta) < 1e-12 and abs(w(eta) - g4) / abs(g4) < 1e-7
+    return w(eta)

@@ -197,3 +197,11 @@ def test_tutorial_01_third_order_mslp_and_descriptor_variants(rijke):
             assert abs(A - Ao).max() <= 1e-12 * abs(Ao).max()
             A1, Ao1 = Lg(z, 1).to_scipy(), Lo(z, 1)
             assert abs(A1 - Ao1).max() <= 1e-12 * abs(Ao1).max()
+
+
+def test_tutorial_08_through_the_host_mirror(rijke):
+    """The same tutorial_08 sequence through the product's discretize / mslp / perturb_fast! / pade."""
+    from cases import tutorial_08_check
+    mg, mo, c = rijke
+    ctx = HostStandIn()
+    tutorial_08_check(W.discretize, lambda L, z, **k: W.mslp(L, z, output=False, **k), W.perturb_fast_bang, W.pade, W.polyval, mg, c, ctx=ctx)

@@ -122,6 +122,16 @@ def test_tutorial_01_local_solver_prose(rijke):
     assert abs(w - g4) / abs(g4) < TOL
 
 
+def test_tutorial_08_custom_ftf_and_flame_response_closure(rijke):
+    """docs/src/tutorial_08_custom_FTF.md: custom FTF closure == built-in n-tau model (G4); flame-response parametrisation + [8/8] Pade +
+    Newton-Raphson on the scalar closure reproduces it to 1e-8."""
+    from cases import tutorial_08_check
+    from oracle.nlevp import pade, perturb_fast_bang, polyval
+    mesh, c = rijke
+    quiet = lambda L, z, **k: mslp(L, z, **k)
+    tutorial_08_check(discretize, quiet, perturb_fast_bang, pade, polyval, mesh, c)
+
+
 def test_perturb_fast_goldens(rijke):
     """G8/G9 (docs/src/tutorial_04_perturbation_theory.md:112-155): 20th-order power series of omega(tau) by perturb_fast!, its value
     at tau + 0.5 ms and the first-order value; perturb! (the slow algorithm) and perturb_norm! give the same eigenvalue series."""

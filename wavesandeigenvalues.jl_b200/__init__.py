@@ -10,7 +10,7 @@ from . import _lib  # noqa: F401
 from .helmholtz import discretize  # noqa: F401
 from .meshutils import Mesh, SymInfo, aggregate_elements, extend_mesh, kuhn_box, kuhn_unit_cell, octosplit  # noqa: F401
 from .nlevp import (bloch_expand, conv_radius, LinearOperatorFamily, VectorFamily, Solution, Term, beyn, compute_moment_matrices, exp_az, exp_delay,  # noqa: F401
-                    get_context, householder, inpoly, moments2eigs, mslp, pade_bang, perturb_bang, perturb_fast_bang, perturb_norm_bang, pow0,
+                    get_context, householder, inpoly, moments2eigs, mslp, pade, pade_bang, poly_roots, polyval, perturb_bang, perturb_fast_bang, perturb_norm_bang, pow0,
                     pow1, pow2, pow_a,
                     reset_context, wn)
 from .shape import (bound_mass_normalize, discrete_adjoint_shape_sensitivity, get_normal_vectors, get_surface_points,  # noqa: F401
