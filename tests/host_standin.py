@@ -46,6 +46,8 @@ class HostStandIn:
     def mesh_set(self, order, xyz, tets, tris, dim):
         self.order, self.P = order, np.ascontiguousarray(np.asarray(xyz, dtype=float).T)
         self.tets, self.tris, self.dim = np.asarray(tets, dtype=np.int64), np.asarray(tris, dtype=np.int64), dim
+        self.mesh_serial = getattr(self, "mesh_serial", 0) + 1
+        return self.mesh_serial
 
     def mesh_update_points(self, xyz):
         self.P = np.ascontiguousarray(np.asarray(xyz, dtype=float).T)

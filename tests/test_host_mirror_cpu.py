@@ -88,6 +88,15 @@ def test_forced_response_wiring(rijke, order):
     assert np.abs(rhs2(w) - b3).max() <= 1e-13 * np.abs(b3).max()
     with pytest.raises(ValueError):
         W.discretize(mg, {"Interior": ("interior", ()), "Outlet": ("speaker", ("A", 1))}, c, source=True, ctx=HostStandIn())
+    # one context, two families: a context holds one mesh at a time, so re-assembling the OLDER family (other element order) after a
+    # newer discretize() must make its own mesh resident again
+    ctx = HostStandIn()
+    other = "quad" if order == "lin" else "lin"
+    La = W.discretize(mg, rijke_dscrp(0.01, 0.001), c, order=order, ctx=ctx)
+    ref = [t.coeff.csc()[2].copy() for t in La.terms]
+    W.discretize(mg, rijke_dscrp(0.01, 0.001), c, order=other, ctx=ctx)
+    La.discretization.reassemble(c)
+    assert all(np.array_equal(t.coeff.csc()[2], r) for t, r in zip(La.terms, ref))
 
 
 def test_shape_sensitivity_call_sequence(rijke):

@@ -166,6 +166,8 @@ class Context:
         self._keep = (xyz, tets, tris)
         self._chk(self._l.wae_mesh_set(self.h, order, xyz.shape[0], _p(xyz, _pd), tets.shape[0], _p(tets, _pu32),
                                        tris.shape[0], _p(tris, _pu32), dim))
+        self.mesh_serial = getattr(self, "mesh_serial", 0) + 1  # the context holds ONE mesh: see Discretization.reassemble
+        return self.mesh_serial
 
     def pattern_build(self, elem_kind, elem_ids=None):
         pid, nnz = _i32(), _i64()

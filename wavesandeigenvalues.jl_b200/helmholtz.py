@@ -53,11 +53,16 @@ class Discretization:
         self.ops = []        # recipe: dicts with "op", pattern/matrix ids and the element subsets
         self.n_tet = self.n_tri = self.dim = 0
         self.ctx = self.mesh = None
+        self.mesh_serial, self.mesh_args = None, None  # what wae_mesh_set was called with (order, tets, tris, dim) and when
 
     def reassemble(self, C, points=None):
         """Re-run every assembly kernel into the existing device matrices.  ``points`` (3 x N) replaces the vertex
         coordinates first (shape_sensitivity.jl:111,120 re-discretises perturbed meshes this way)."""
         ctx, mesh = self.ctx, self.mesh
+        if getattr(ctx, "mesh_serial", None) != self.mesh_serial:
+            # the context holds one mesh at a time and a later discretize() / shape-sensitivity call replaced this family's: make it
+            # resident again (same connectivity, so the patterns and pair programs of this family stay valid)
+            self.mesh_serial = ctx.mesh_set(*self.mesh_args[:1], mesh.points.T, *self.mesh_args[1:])
         if points is not None:
             mesh.points = np.asarray(points, dtype=float)
             ctx.mesh_update_points(mesh.points.T)
@@ -114,10 +119,11 @@ def discretize(mesh, dscrp, C, order="lin", b="__none__", mass_weighting=True, s
     npts = mesh.points.shape[1]
     C_tet, C_tri = _split_c(mesh, C, npts)
 
-    ctx.mesh_set(1 if order == "lin" else 2, mesh.points.T, tetrahedra, triangles, dim)
+    serial = ctx.mesh_set(1 if order == "lin" else 2, mesh.points.T, tetrahedra, triangles, dim)
     L = LinearOperatorFamily(["ω", "λ"], [0.0, float("inf")])
     rhs = VectorFamily(["ω"], [0.0])  # Helmholtz.jl:79
     disc = Discretization()
+    disc.mesh_serial, disc.mesh_args = serial, (1 if order == "lin" else 2, tetrahedra, triangles, dim)
     disc.n_tet, disc.n_tri, disc.dim = len(tetrahedra), len(triangles), dim
     disc.ctx, disc.mesh = ctx, mesh
     L.discretization = disc
