@@ -247,8 +247,22 @@ class HostStandIn:
         lam, V = spla.eigs(sp.csc_matrix(A), k=nev, M=sp.csc_matrix(M), sigma=0, v0=np.asarray(v0, dtype=complex), tol=0)
         return lam, V, 20
 
-    def beyn_moments(self, *a, **k):
-        raise NotImplementedError("the node loop writes into device memory: covered by the GPU tests")
+    def moment_buffer(self, n_mom, l, d):
+        import torch
+        return torch.zeros((n_mom, l, d), dtype=torch.complex128)
+
+    def beyn_moments(self, fid, lid, z, w, coeffs, l, n_mom, out_ptr, V=None):
+        """beyn.jl:62-74 for the nodes handed in: A_p += w_j z_j^p L(z_j)^-1 V, V = first l identity columns unless given."""
+        f = self.fams[fid]
+        d = self.pats[f["pid"]]["dim"]
+        A = np.ctypeslib.as_array((C.c_double * (2 * n_mom * l * d)).from_address(out_ptr)).view(np.complex128).reshape(n_mom, l, d)
+        Vm = np.eye(d, l, dtype=complex) if V is None else np.asarray(V, dtype=complex)
+        for zj, wj, cf in zip(np.asarray(z), np.asarray(w), np.asarray(coeffs)):
+            self.combine(fid, cf, 0)
+            X = spla.splu(self._slot(fid, 0)).solve(Vm)
+            for p in range(n_mom):
+                A[p] += (wj * zj**p) * X.T
+        self._ms["beyn_factor_total"] = self._ms["beyn_solve_total"] = 0.0
 
     # -- shape sensitivity: the library's host replay of the kernel's per-thread function -----------------------------------------
     def shape_sens_begin(self, points, step, v, v_adj, partner=None, cylindrical=False, dof_new=None, dof_flag=None, phase=None):

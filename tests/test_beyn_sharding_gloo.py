@@ -32,6 +32,13 @@ def _worker(rank, world, port, out_dir):
     A = torch.from_numpy(beyn_moments(L, G, 3, 1, 4, nodes=mine))
     allreduce_moments(A)
     np.save(os.path.join(out_dir, f"A{rank}.npy"), A.numpy())
+    # the product's own sharded routine (node shard -> per-rank moments -> one all-reduce), with the context replaced by the CPU test
+    # double: every rank must end up with the serial moments
+    import wae_b200 as W
+    from host_standin import HostStandIn
+    Lp = W.discretize(W.Mesh("m", scale=0.001, raw=load_raw_mesh("rijke_mm")), rijke_dscrp(0.0, 0.001), mesh.generate_field(speedofsound),
+                      ctx=HostStandIn())
+    np.save(os.path.join(out_dir, f"P{rank}.npy"), W.compute_moment_matrices(Lp, G, l=3, K=1, N=4))
     if rank == 0:
         np.save(os.path.join(out_dir, "Afull.npy"), beyn_moments(L, G, 3, 1, 4))
     dist.destroy_process_group()
@@ -46,3 +53,5 @@ def test_sharded_moments_equal_serial(tmp_path):
     A0, A1, Af = (np.load(tmp_path / n) for n in ("A0.npy", "A1.npy", "Afull.npy"))
     assert np.array_equal(A0, A1)
     assert np.abs(A0 - Af).max() <= 1e-12 * np.abs(Af).max()
+    P0, P1 = np.load(tmp_path / "P0.npy"), np.load(tmp_path / "P1.npy")
+    assert np.array_equal(P0, P1) and P0.shape == Af.shape and np.abs(P0 - Af).max() <= 1e-10 * np.abs(Af).max()

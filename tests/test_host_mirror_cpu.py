@@ -214,3 +214,25 @@ def test_tutorial_08_through_the_host_mirror(rijke):
     mg, mo, c = rijke
     ctx = HostStandIn()
     tutorial_08_check(W.discretize, lambda L, z, **k: W.mslp(L, z, output=False, **k), W.perturb_fast_bang, W.pade, W.polyval, mg, c, ctx=ctx)
+
+
+def test_beyn_host_logic(rijke):
+    """beyn / compute_moment_matrices / moments2eigs of the product (node generation, per-node scalars, K from l and d, probing matrix,
+    singular-value cut, position test) against the oracle on the tutorial's contour (docs/src/tutorial_01_rijke_tube.md:202-212, N reduced)."""
+    from oracle.nlevp import beyn as obeyn
+    from oracle.nlevp import beyn_moments as omoments
+    mg, mo, c = rijke
+    L = W.discretize(mg, rijke_dscrp(0.0, 0.001), c, ctx=HostStandIn())
+    Lo = ohelm.discretize(mo, rijke_dscrp(0.0, 0.001), c)
+    G = [z * 2 * math.pi for z in (150 + 5j, 150 - 5j, 1000 - 5j, 1000 + 5j)]
+    Ao = omoments(Lo, G, 5, 1, 8)
+    Ag = W.compute_moment_matrices(L, G, l=5, K=1, N=8)
+    assert Ag.shape == Ao.shape == (L.size(), 5, 2) and np.abs(Ag - Ao).max() <= 1e-10 * np.abs(Ao).max()
+    Oo, Po = obeyn(Lo, G, l=5, N=8, tol=1e-8)
+    Og, Pg = W.beyn(L, G, l=5, N=8, tol=1e-8, output=False)
+    assert len(Og) == len(Oo) == 2 and np.abs(np.sort_complex(Og) - np.sort_complex(Oo)).max() <= 1e-8 * np.abs(Oo).max()
+    f = np.sort(Og.real) / 2 / math.pi
+    assert abs(f[0] - 272) < 2 and abs(f[1] - 695) < 10
+    # higher moments (K = 2) and a seeded random probing matrix give the same two eigenvalues
+    O2, _ = W.beyn(L, G, l=3, K=2, N=8, tol=1e-8, output=False, random=True, seed=3)
+    assert len(O2) == 2 and np.abs(np.sort_complex(O2) - np.sort_complex(Og)).max() <= 1e-3 * np.abs(Og).max()

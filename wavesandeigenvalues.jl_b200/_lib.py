@@ -314,6 +314,14 @@ class Context:
         self._chk(self._l.wae_eigs_si(self.h, lid, fid, m_slot, trans, nev, _p(v0, _pd), _p(lam, _pd), _p(V, _pd), C.byref(ns)))
         return lam, V, ns.value
 
+    def moment_buffer(self, n_mom, l, d):
+        """Zeroed (n_mom, l, d) complex tensor on this context's GPU for wae_beyn_moments (== d x l x n_mom column-major); the context is
+        bound to torch's current stream so that the all-reduce that follows is ordered after the node loop."""
+        import torch
+        A = torch.zeros((n_mom, l, d), dtype=torch.complex128, device=f"cuda:{self.device}")
+        self.set_stream(torch.cuda.current_stream().cuda_stream)
+        return A
+
     def beyn_moments(self, fid, lid, z, w, coeffs, l, n_mom, out_ptr, V=None):
         z = np.ascontiguousarray(z, dtype=np.complex128)
         w = np.ascontiguousarray(w, dtype=np.complex128)

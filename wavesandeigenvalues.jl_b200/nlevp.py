@@ -942,8 +942,7 @@ def compute_moment_matrices(L, G, l=5, K=1, N=16, group=None, stats=None, V=None
     for r, j in enumerate(mine):
         L.params[L.eigval] = complex(zs[j])
         coeffs[r] = dev.flat(L.scalars([0] * len(L.active)))
-    A = torch.zeros((2 * K, l, d), dtype=torch.complex128, device=f"cuda:{ctx.device}")  # == (d,l,2K) column-major
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    A = ctx.moment_buffer(2 * K, l, d)  # device tensor, == (d,l,2K) column-major
     if len(mine):
         ctx.beyn_moments(dev.fid, dev.lu(), zs[mine], ws[mine], coeffs, l, 2 * K, A.data_ptr(), V=V)
     if stats is not None:
