@@ -448,7 +448,10 @@ def assembly_leg(W, ctx0, n, hbm, hbm_src):
         p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_assembly_variants.py"), str(n), "quad", "7"], capture_output=True,
                            text=True, timeout=240, env={**os.environ, "CUDA_VISIBLE_DEVICES": os.environ.get("CUDA_VISIBLE_DEVICES", str(ctx0.device))})
         line = [l for l in p.stdout.splitlines() if l.startswith("{")]
-        res["variants"] = json.loads(line[-1])["variants"] if line else {"error": (p.stderr or p.stdout)[-400:]}
+        diag = json.loads(line[-1]) if line else None
+        res["variants"] = diag["variants"] if diag else {"error": (p.stderr or p.stdout)[-400:]}
+        if diag and "layouts" in diag:  # short patch-size x CTAs-per-SM sweep (the default layout stays 12288 slots, one CTA per SM)
+            res["layouts"] = diag["layouts"]
     except Exception as e:  # noqa: BLE001 -- diagnostic leg only
         res["variants"] = {"error": repr(e)[:400]}
     return res

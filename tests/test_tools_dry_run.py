@@ -47,3 +47,4 @@ def test_assembly_tools(monkeypatch, tool):
         assert out["n_failed"] == 0 and len(out["best"]) == 8 and all(r["ok"] for r in out["best"])
     else:
         assert set(out["variants"]) == {"0", "1", "2", "3", "0_again"} and all(v["ok"] for v in out["variants"].values())
+        assert len(out["layouts"]) == 6 and all(r["ok"] for r in out["layouts"])
