@@ -150,6 +150,15 @@ int32_t wae_lu_factor(wae_ctx* h, int32_t lu_id, int32_t slot);
 /* In-place solve op(A) X = B; trans as above; X dim x nrhs column-major complex host array. */
 int32_t wae_lu_solve(wae_ctx* h, int32_t lu_id, int32_t trans, int32_t nrhs, double* X);
 
+/* ---- release (the Julia side would call these from finalizers: SparseMatrixCSC / UMFPACK factors are garbage-collected in the
+ * reference, e.g. the `lu` objects of beyn.jl:65 and perturbation.jl:329 die at the end of their scope).  Everything a handle owns is
+ * released by wae_destroy at the latest.  Order: LU handles of a family, then the family, then its matrices (wae_mat_free), then
+ * their patterns; each call fails with WAE_E_INVALID (and releases nothing) while something still refers to the object.  Ids are
+ * never reused.  wae_lu_free returns the factor storage (the largest allocation of the path) to the device.                  */
+int32_t wae_lu_free(wae_ctx* h, int32_t lu_id);
+int32_t wae_family_free(wae_ctx* h, int32_t fam_id);
+int32_t wae_pattern_free(wae_ctx* h, int32_t pattern_id);
+
 /* Host-only (needs no GPU and no context): the reference's simplex numbering rule for n simplices of k = 2, 3 or 4 vertices
  * (simp: n x k, row-major, ids in [0, 2^32)): unique vertex sets in ascending order of their DESCENDING-sorted vertex tuple, the
  * first occurrence of a set is its representative (src/Mesh/sorter.jl:9-31; Meshutils.jl:92-165; collect_lines! :831-840).

@@ -225,6 +225,18 @@ class HostStandIn:
         self.lus.append({"fid": fid, "A": None, "lu": None})
         return len(self.lus) - 1, 0, 0.0
 
+    def lu_free(self, lid):
+        if self.lus[lid] is None:
+            raise _lib.WaeError(_lib.E_INVALID, f"unknown LU id {lid}")
+        self.lus[lid] = None
+
+    def family_free(self, fid):
+        if self.fams[fid] is None:
+            raise _lib.WaeError(_lib.E_INVALID, f"unknown family id {fid}")
+        if any(S is not None and S["fid"] == fid for S in self.lus):
+            raise _lib.WaeError(_lib.E_INVALID, f"family {fid} still has an LU handle (wae_lu_free first)")
+        self.fams[fid] = None
+
     def lu_factor(self, lid, slot):
         S = self.lus[lid]
         S["A"] = self._slot(S["fid"], slot)

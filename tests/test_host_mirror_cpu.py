@@ -236,3 +236,23 @@ def test_beyn_host_logic(rijke):
     # higher moments (K = 2) and a seeded random probing matrix give the same two eigenvalues
     O2, _ = W.beyn(L, G, l=3, K=2, N=8, tol=1e-8, output=False, random=True, seed=3)
     assert len(O2) == 2 and np.abs(np.sort_complex(O2) - np.sort_complex(Og)).max() <= 1e-3 * np.abs(Og).max()
+
+
+def test_release_drops_and_rebuilds_the_device_side(rijke):
+    """L.release() (wae_lu_free + wae_family_free: what Julia's GC does for the reference's sparse sums and UMFPACK factors) returns the
+    device side of a family; the next use rebuilds it and gives the same eigenvalue.  A family with a live LU handle cannot be freed."""
+    from wae_b200 import _lib
+    mg, mo, c = rijke
+    ctx = HostStandIn()
+    L = W.discretize(mg, rijke_dscrp(0.01, 0.001), c, ctx=ctx)
+    sol, _, _ = W.householder(L, 340 * 2 * math.pi, maxiter=20, tol=1e-11, output=False)
+    dev = L.device()
+    fid, lid = dev.fid, dev.lu()
+    with pytest.raises(_lib.WaeError):
+        ctx.family_free(fid)  # its LU handle is still alive
+    L.release()
+    assert ctx.fams[fid] is None and ctx.lus[lid] is None and L._dev is None
+    with pytest.raises(_lib.WaeError):
+        ctx.lu_free(lid)  # ids are never reused
+    sol2, _, _ = W.householder(L, 340 * 2 * math.pi, maxiter=20, tol=1e-11, output=False)
+    assert L.device().fid != fid and abs(sol2.params["ω"] - sol.params["ω"]) <= 1e-12 * abs(sol.params["ω"])

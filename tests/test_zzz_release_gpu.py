@@ -1,0 +1,54 @@
+"""GPU check of the release entry points (wae_lu_free, wae_family_free, wae_pattern_free; include/wae_b200.h): device memory comes back,
+freed ids are rejected, objects in use are refused, and a released family rebuilds itself on the next use.
+
+NOTE (round 1): added after the round's GPU budget was spent -- not yet run on a B200; the file sorts last."""
+import math
+
+import pytest
+
+from cases import load_raw_mesh, rijke_dscrp, speedofsound
+
+pytestmark = pytest.mark.gpu
+
+
+def test_release_returns_device_memory_and_family_rebuilds():
+    import torch
+
+    import wae_b200 as W
+    from wae_b200 import _lib
+    ctx = _lib.Context(0)  # a private context: nothing of the other tests is touched
+    try:
+        mesh = W.kuhn_box((12, 12, 40), (0, 0, -0.25), (0.05, 0.05, 0.25), jitter=0.1, seed=3, flame_layer=(20, 21))
+        c = mesh.generate_field(lambda x, y, z: 347.2 if z < 0 else 694.4)
+        gam, rho = 1.4, 1.225
+        q = 101325.0 * 3 * math.pi * 0.025**2 * gam / (gam - 1)
+        dscrp = {"Interior": ("interior", ()), "Outlet": ("admittance", ("Y", 1e15)),
+                 "Flame": ("flame", (gam, rho, q, [0.025, 0.025, -0.6 * 0.5 / 40], [0, 0, 1.0], "n", "τ", 1.0, 0.001))}
+        L = W.discretize(mesh, dscrp, c, order="quad", ctx=ctx)
+        z0 = 340 * 2 * math.pi
+        W.householder(L, z0, maxiter=15, tol=1e-9 * z0, output=False)  # warm-up: kernels loaded, context-level buffers in place
+        L.release()
+        free0 = torch.cuda.mem_get_info(0)[0]
+        sol, _, flag = W.householder(L, z0, maxiter=15, tol=1e-9 * z0, output=False)
+        assert flag >= 0
+        dev = L.device()
+        fid, lid = dev.fid, dev.lu()
+        used = free0 - torch.cuda.mem_get_info(0)[0]
+        assert used > 16 * dev.lu_nnz  # at least the factor storage
+        with pytest.raises(_lib.WaeError):
+            ctx.family_free(fid)  # the LU handle is alive
+        pid = ctx.mat_info(L.terms[0].coeff.parts[0][0])[0]
+        with pytest.raises(_lib.WaeError):
+            ctx.pattern_free(pid)  # a matrix lives on it
+        L.release()
+        assert free0 - torch.cuda.mem_get_info(0)[0] < 0.1 * used  # factors, slots and maps are back
+        with pytest.raises(_lib.WaeError):
+            ctx.lu_free(lid)  # ids are never reused
+        with pytest.raises(_lib.WaeError):
+            ctx.family_free(fid)
+        with pytest.raises(_lib.WaeError):
+            ctx.lu_factor(lid, 0)
+        sol2, _, _ = W.householder(L, z0, maxiter=15, tol=1e-9 * z0, output=False)
+        assert L.device().fid != fid and abs(sol2.params["ω"] - sol.params["ω"]) <= 1e-9 * abs(sol.params["ω"])
+    finally:
+        ctx.close()

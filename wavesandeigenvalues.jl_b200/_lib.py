@@ -74,6 +74,9 @@ SIGNATURES = {
     "wae_lu_analyze": (_i32, [_vp, _i32, _pi32, _pi64, _pd]),
     "wae_lu_factor": (_i32, [_vp, _i32, _i32]),
     "wae_lu_solve": (_i32, [_vp, _i32, _i32, _i32, _pd]),
+    "wae_lu_free": (_i32, [_vp, _i32]),
+    "wae_family_free": (_i32, [_vp, _i32]),
+    "wae_pattern_free": (_i32, [_vp, _i32]),
     "wae_eigs_si": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _pd, _pd, _pd, _pi32]),
     "wae_beyn_moments": (_i32, [_vp, _i32, _i32, _i32, _pd, _pd, _pd, _i32, _i32, _pd, _vp]),
     "wae_assemble_wallsrc": (_i32, [_vp, _i64, _pi64, _pd, _i32, _pd]),
@@ -304,6 +307,15 @@ class Context:
         X = np.array(B.reshape(B.shape[0], -1), dtype=np.complex128, order="F", copy=True)
         self._chk(self._l.wae_lu_solve(self.h, lid, trans, X.shape[1], _p(X, _pd)))
         return X[:, 0] if one else X
+
+    def lu_free(self, lid):
+        self._chk(self._l.wae_lu_free(self.h, lid))
+
+    def family_free(self, fid):
+        self._chk(self._l.wae_family_free(self.h, fid))
+
+    def pattern_free(self, pid):
+        self._chk(self._l.wae_pattern_free(self.h, pid))
 
     def eigs_si(self, lid, fid, m_slot, nev, v0, trans=0):
         v0 = np.ascontiguousarray(v0, dtype=np.complex128)

@@ -30,6 +30,8 @@ typedef std::complex<double> zc;
   }                                    \
   return WAE_OK;
 
+int wae_lu_family_of(const LuSolver& S) { return S.fam; }
+
 static LuSolver& get_lu(wae_ctx* h, int id) {
   if (id < 0 || id >= (int)h->lus.size() || !h->lus[id]) WAE_THROW(WAE_E_INVALID, "unknown LU id %d", id);
   return *h->lus[id];
@@ -428,6 +430,17 @@ int32_t wae_lu_analyze(wae_ctx* h, int32_t fam_id, int32_t* lu_id, int64_t* fact
   if (lu_id) *lu_id = (int)h->lus.size() - 1;
   if (factor_nnz) *factor_nnz = S->sym.factor_nnz;
   if (factor_flops) *factor_flops = S->sym.flops;
+  WAE_API_END
+}
+
+// Releases the factor storage (the largest allocation of the path: 23 GB at config 2), the symbolic data and the solve / Arnoldi
+// workspaces of one analysis.
+int32_t wae_lu_free(wae_ctx* h, int32_t lu_id) {
+  WAE_API_BEGIN
+  get_lu(h, lu_id);
+  CUDA_CHECK(cudaSetDevice(h->device));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  h->lus[lu_id].reset();
   WAE_API_END
 }
 

@@ -542,7 +542,40 @@ int32_t wae_mat_free(wae_ctx* h, int32_t mat_id) {
   WAE_API_END
 }
 
+// A pattern can go once no live matrix or family refers to it (its pair program, slot map and device index arrays go with it).
+int32_t wae_pattern_free(wae_ctx* h, int32_t pattern_id) {
+  WAE_API_BEGIN
+  h->pat(pattern_id);
+  for (auto& m : h->mats)
+    if (m && m->pattern == pattern_id) WAE_THROW(WAE_E_INVALID, "pattern %d is still used by a matrix", pattern_id);
+  for (auto& f : h->fams)
+    if (f && f->pattern == pattern_id) WAE_THROW(WAE_E_INVALID, "pattern %d is still used by a family", pattern_id);
+  CUDA_CHECK(cudaSetDevice(h->device));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  h->patterns[pattern_id].reset();
+  WAE_API_END
+}
+
 // ---- family ---------------------------------------------------------------------------------
+// Releases the value slots, term maps and staging buffers of a family.  Its matrices stay (they may serve other families); a union
+// pattern that was merged for this family alone is released too.  LU handles analysed for the family must be freed first.
+int32_t wae_family_free(wae_ctx* h, int32_t fam_id) {
+  WAE_API_BEGIN
+  Family& F = h->fam(fam_id);
+  for (auto& l : h->lus)
+    if (l && wae_lu_family_of(*l) == fam_id) WAE_THROW(WAE_E_INVALID, "family %d still has an LU handle (wae_lu_free first)", fam_id);
+  CUDA_CHECK(cudaSetDevice(h->device));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  const int pid = F.pattern;
+  const bool merged = F.owns_pattern;
+  h->fams[fam_id].reset();
+  bool used = false;
+  for (auto& m : h->mats) used |= m && m->pattern == pid;
+  for (auto& f : h->fams) used |= f && f->pattern == pid;
+  if (merged && !used) h->patterns[pid].reset();
+  WAE_API_END
+}
+
 int32_t wae_family_create(wae_ctx* h, int32_t n_terms, const int32_t* mat_ids, int32_t* fam_id, int64_t* nnz_union) {
   WAE_API_BEGIN
   CUDA_CHECK(cudaSetDevice(h->device));
@@ -580,6 +613,7 @@ int32_t wae_family_create(wae_ctx* h, int32_t n_terms, const int32_t* mat_ids, i
     upid = big;
   } else {
     upid = new_pattern(h);
+    F.owns_pattern = true;
     Pattern& U = *h->patterns[upid];
     U.dim = dim;
     U.colptr.assign(dim + 1, 0);

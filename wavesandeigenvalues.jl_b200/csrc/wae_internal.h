@@ -112,6 +112,7 @@ struct Family {
   int n_terms = 0;
   std::vector<int> mats;
   int pattern = -1;                        // union pattern id
+  bool owns_pattern = false;               // the union pattern was merged for this family (else it is a term's own pattern)
   std::vector<bool> identity;              // term pattern == union pattern
   std::vector<DevBuf<int32_t>> d_map;      // term nz -> union nz (empty if identity); terms on the same pattern share the map of the first one
   std::vector<int> map_of;                 // term -> index into d_map (the term that owns the map)
@@ -127,6 +128,7 @@ struct Family {
 };
 
 struct LuSolver;  // lu_symbolic.h
+int wae_lu_family_of(const LuSolver& S);  // lu_api.cu (LuSolver is incomplete here)
 struct WaeShapeSens;  // shape_sens.cu
 
 struct wae_ctx {

@@ -363,6 +363,15 @@ class _DeviceFamily:
             self._lu, self.lu_nnz, self.lu_flops = self.ctx.lu_analyze(self.fid)
         return self._lu
 
+    def free(self):
+        """Return the LU factor storage, value slots and term maps to the device (wae_lu_free, wae_family_free); the term matrices stay."""
+        if self._lu is not None:
+            self.ctx.lu_free(self._lu)
+            self._lu = None
+        if self.fid is not None:
+            self.ctx.family_free(self.fid)
+            self.fid = None
+
 
 class LinearOperatorFamily:
     """LinOpFam.jl:131-186.  First parameter = eigenvalue, last = auxiliary eigenvalue."""
@@ -414,6 +423,13 @@ class LinearOperatorFamily:
                 raise ValueError("empty operator family")
             self._dev = _DeviceFamily(self.terms[0].coeff.ctx, self.terms)
         return self._dev
+
+    def release(self):
+        """Explicitly drop the device side of the family (union pattern values, LU factors: what Julia's GC does for the reference's
+        SparseMatrixCSC sums and UMFPACK factors); it is rebuilt on the next use.  The term matrices are untouched."""
+        if self._dev is not None:
+            self._dev.free()
+            self._dev = None
 
     def scalars(self, derivs):
         """Per-term scalar (None if the term is skipped) -- LinOpFam.jl:501-522 without the matrices."""
