@@ -400,6 +400,15 @@ def main():
             out["shape_sensitivity"] = json.loads(line[-1]) if line else {"error": (p.stderr or p.stdout)[-400:]}
         except Exception as e:  # noqa: BLE001 -- diagnostic leg only
             out["shape_sensitivity"] = {"error": repr(e)[:400]}
+    # ------------------------------------------------------------------ diagnostic leg: numeric-LU knobs (outer block width, leaf size), same rules
+    if rank == 0 and world == 1 and not args.skip_extras:
+        try:
+            p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_lu_knobs.py"), *(str(x) for x in tube), "quad", "2"], capture_output=True,
+                               text=True, timeout=240)
+            line = [l for l in p.stdout.splitlines() if l.startswith("{")]
+            out["lu_knobs"] = json.loads(line[-1])["combos"] if line else {"error": (p.stderr or p.stdout)[-400:]}
+        except Exception as e:  # noqa: BLE001 -- diagnostic leg only
+            out["lu_knobs"] = {"error": repr(e)[:400]}
     # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1 only)
     if rank == 0 and world == 1 and not args.skip_extras:
         sample = tuple(int(x) for x in args.cpu_sample.split(","))

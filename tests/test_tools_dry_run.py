@@ -16,6 +16,7 @@ from host_standin import HostStandIn
 from wae_b200 import helmholtz, nlevp, shape
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KNOBS = ("WAE_GATHER_SLOTS", "WAE_GATHER_CTAS", "WAE_GATHER_THREADS", "WAE_ASM_VARIANT", "WAE_LU_NBO", "WAE_LU_LEAF")
 
 
 def _run(monkeypatch, tool, argv):
@@ -23,12 +24,12 @@ def _run(monkeypatch, tool, argv):
     for m in (W, helmholtz, shape, nlevp):
         monkeypatch.setattr(m, "get_context", lambda device=None: ctx)
     monkeypatch.setattr(sys, "argv", [tool] + argv)
-    for k in ("WAE_GATHER_SLOTS", "WAE_GATHER_CTAS", "WAE_GATHER_THREADS", "WAE_ASM_VARIANT"):
+    for k in KNOBS:
         monkeypatch.delenv(k, raising=False)
     buf = io.StringIO()
     with redirect_stdout(buf):
         runpy.run_path(os.path.join(ROOT, "tools", tool), run_name="__main__")
-    for k in ("WAE_GATHER_SLOTS", "WAE_GATHER_CTAS", "WAE_GATHER_THREADS", "WAE_ASM_VARIANT"):
+    for k in KNOBS:
         os.environ.pop(k, None)  # the tools set them for the library; leave the process environment clean for the other tests
     return json.loads([l for l in buf.getvalue().splitlines() if l.startswith("{\"")][-1])
 
@@ -48,3 +49,9 @@ def test_assembly_tools(monkeypatch, tool):
     else:
         assert set(out["variants"]) == {"0", "1", "2", "3", "0_again"} and all(v["ok"] for v in out["variants"].values())
         assert len(out["layouts"]) == 6 and all(r["ok"] for r in out["layouts"])
+
+
+def test_lu_knob_tool(monkeypatch):
+    out = _run(monkeypatch, "bench_lu_knobs.py", ["3", "3", "24", "quad", "1"])
+    assert len(out["combos"]) == 5 and all(r.get("ok") and "free_error" not in r for r in out["combos"]), out
+    assert [(r["nbo"], r["leaf"]) for r in out["combos"]] == [(128, 64), (64, 64), (256, 64), (128, 32), (128, 128)]

@@ -1,0 +1,67 @@
+"""Short sweep of the numeric-LU tuning knobs (WAE_LU_NBO: outer block width of the pivot-block factorisation, read at every factorisation;
+WAE_LU_LEAF: nested-dissection leaf size, read by the symbolic analysis) on the config-2 tube: per combination one analysis, `reps`
+factorisations (CUDA-event time of the numeric phase), one refined solve and its residual.  Prints ONE JSON line.  bench.py runs this in
+a subprocess as a diagnostic leg; the defaults (NBO 128, LEAF 64) are the measured configuration and are not changed by anything here.
+
+    python tools/bench_lu_knobs.py [nx=20] [ny=20] [nz=300] [order=quad] [reps=2]
+"""
+import json
+import math
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+import wae_b200 as W  # noqa: E402
+
+nx, ny, nz = (int(a) for a in (sys.argv[1:4] if len(sys.argv) > 3 else (20, 20, 300)))
+order = sys.argv[4] if len(sys.argv) > 4 else "quad"
+reps = int(sys.argv[5]) if len(sys.argv) > 5 else 2
+KNOBS = ("WAE_LU_NBO", "WAE_LU_LEAF")
+for k in KNOBS:
+    os.environ.pop(k, None)
+hz = 0.5 / nz
+mesh = W.kuhn_box((nx, ny, nz), (0, 0, -0.25), (0.05, 0.05, 0.25), jitter=0.1, seed=12345, flame_layer=(nz // 2, nz // 2 + 1))
+c = np.where(mesh.points[2, mesh.tetrahedra].sum(axis=1) / 4 < 0, 347.2, 694.4)
+gam, rho = 1.4, 1.225
+q = 101325.0 * 3 * math.pi * 0.025**2 * gam / (gam - 1)
+dscrp = {"Interior": ("interior", ()), "Outlet": ("admittance", ("Y", 1e15)),
+         "Flame": ("flame", (gam, rho, q, [0.025, 0.025, -0.6 * hz], [0, 0, 1.0], "n", "τ", 1.0, 0.001))}
+L = W.discretize(mesh, dscrp, c, order=order)
+dev = L.device()
+ctx = dev.ctx
+z = 340 * 2 * math.pi
+op = L(z)
+op.materialize(0)
+rng = np.random.default_rng(0)
+b = rng.standard_normal(L.size()) + 1j * rng.standard_normal(L.size())
+out = {"tube": [nx, ny, nz], "order": order, "dofs": int(L.size()), "reps": reps, "combos": []}
+for nbo, leaf in ((None, None), (64, None), (256, None), (None, 32), (None, 128)):
+    for k, v in zip(KNOBS, (nbo, leaf)):
+        os.environ.pop(k, None)
+        if v is not None:
+            os.environ[k] = str(v)
+    row = {"nbo": nbo or 128, "leaf": leaf or 64}
+    try:
+        lid, lu_nnz, lu_flops = ctx.lu_analyze(dev.fid)
+        ms = []
+        for _ in range(reps):
+            ctx.lu_factor(lid, 0)
+            ms.append(ctx.last_ms("factor"))
+        symf = 0.5 if ctx.last_ms("factor_sym") > 0.5 else 1.0
+        x = ctx.lu_solve(lid, b)
+        sol_ms = ctx.last_ms("solve")
+        res = float(np.abs(op.matvec(x) - b).max() / np.abs(b).max())
+        row.update({"factor_ms": float(min(ms)), "factor_nnz": float(lu_nnz), "factor_flops": float(lu_flops) * symf, "tflops": symf * lu_flops / max(min(ms), 1e-9) / 1e9,
+                    "solve_ms": float(sol_ms), "residual": res, "ok": bool(res <= 1e-6)})
+        try:
+            ctx.lu_free(lid)  # 23 GB of factors per analysis at config 2
+        except Exception as e:  # noqa: BLE001 -- the sweep fits the device without it
+            row["free_error"] = repr(e)[:120]
+    except Exception as e:  # noqa: BLE001 -- diagnostic only
+        row["error"] = repr(e)[:200]
+    out["combos"].append(row)
+for k in KNOBS:
+    os.environ.pop(k, None)
+print(json.dumps(out))
