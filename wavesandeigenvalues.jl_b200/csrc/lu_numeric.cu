@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(256) lu_gemm_kernel(LuDev D, const int32_t* __
   GemmProblem P;
   if (mode == 2) {
     if (S.r == 0) return;
-    if (sym && blockIdx.y > blockIdx.x) return;  // symmetric Schur complement: lower tiles only
+    if ((sym & 1) && blockIdx.y > blockIdx.x) return;  // symmetric Schur complement: lower tiles only
     P.m = P.n = S.r; P.K = S.s;
     P.lda = P.ldb = S.ld; P.ldc = S.r;
     P.A = S.lp + S.s; P.B = S.up + S.s;
@@ -356,6 +356,10 @@ __global__ void __launch_bounds__(256) lu_gemm_kernel(LuDev D, const int32_t* __
   } else {
     const int cend = min(S.s, cap);
     if (c0 >= cend) return;  // no trailing pivot columns in range
+    // sym bit 1 (WAE_LU_SKIP_UPPER, opt-in): tiles strictly above the diagonal of the pivot block are never read again -- the U part of
+    // the pivot block lives (transposed) in the other panel and the NB x NB diagonal blocks sit in the tiles with equal row and column index
+    // (both tile grids start at c0, a multiple of NB, and GT = 2 NB) -- so they need no update: half of the pivot-square GEMM work
+    if ((sym & 2) && blockIdx.x < blockIdx.y) return;
     P.m = S.ld - c0; P.n = cend - c0; P.K = kw;
     P.lda = P.ldb = P.ldc = S.ld;
     cplx* X = mode == 0 ? S.lp : S.up;
@@ -731,6 +735,7 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
   const int maxd = (int)Y.levels.size() - 1;
   int nbo_blocks = 4;  // outer block = 4 * NB = 128 columns
   if (const char* env = getenv("WAE_LU_NBO")) nbo_blocks = std::max(1, atoi(env) / NB);
+  const int upd_flag = (sym ? 1 : 0) | ((getenv("WAE_LU_SKIP_UPPER") && atoi(getenv("WAE_LU_SKIP_UPPER"))) ? 2 : 0);  // pivot-block updates only
   for (int d = maxd; d >= 0; d--) {
     const std::vector<int32_t>& L = Y.levels[d];
     const int nl = (int)L.size();
@@ -772,16 +777,16 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
           int tn = std::min(max_s, oend) - c0;
           if (tn > 0) {
             dim3 g((max_ld - c0 + GT - 1) / GT, (tn + GT - 1) / GT, zc);
-            lu_gemm_kernel<<<g, 256, 0, st>>>(D, lst, 0, k * NB, NB, c0, oend, nullptr, sym);
-            if (!sym) lu_gemm_kernel<<<g, 256, 0, st>>>(D, lst, 1, k * NB, NB, c0, oend, nullptr, sym);
+            lu_gemm_kernel<<<g, 256, 0, st>>>(D, lst, 0, k * NB, NB, c0, oend, nullptr, upd_flag);
+            if (!sym) lu_gemm_kernel<<<g, 256, 0, st>>>(D, lst, 1, k * NB, NB, c0, oend, nullptr, upd_flag);
             h->launches += sym ? 1 : 2;
           }
           // outer update once the outer block is complete
           if (c0 == oend && max_s > oend) {
             const int o0 = oend - nbo_blocks * NB;
             dim3 g((max_ld - oend + GT - 1) / GT, (max_s - oend + GT - 1) / GT, zc);
-            lu_gemm_kernel<<<g, 256, 0, st>>>(D, lst, 0, o0, oend - o0, oend, 1 << 30, nullptr, sym);
-            if (!sym) lu_gemm_kernel<<<g, 256, 0, st>>>(D, lst, 1, o0, oend - o0, oend, 1 << 30, nullptr, sym);
+            lu_gemm_kernel<<<g, 256, 0, st>>>(D, lst, 0, o0, oend - o0, oend, 1 << 30, nullptr, upd_flag);
+            if (!sym) lu_gemm_kernel<<<g, 256, 0, st>>>(D, lst, 1, o0, oend - o0, oend, 1 << 30, nullptr, upd_flag);
             h->launches += sym ? 1 : 2;
           }
           h->launches++;
