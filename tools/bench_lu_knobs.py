@@ -1,6 +1,6 @@
 """Short sweep of the numeric-LU tuning knobs (WAE_LU_NBO: outer block width of the pivot-block factorisation, read at every factorisation;
 WAE_LU_LEAF: nested-dissection leaf size, read by the symbolic analysis; WAE_LU_SKIP_UPPER: opt-in skip of the pivot-square tiles above the
-diagonal in the trailing updates) on the config-2 tube: per combination one analysis, `reps`
+diagonal in the trailing updates; WAE_LU_GEMM=2: opt-in cp.async ring in the DMMA GEMM) on the config-2 tube: per combination one analysis, `reps`
 factorisations (CUDA-event time of the numeric phase), one refined solve and its residual.  Prints ONE JSON line.  bench.py runs this in
 a subprocess as a diagnostic leg; the defaults (NBO 128, LEAF 64) are the measured configuration and are not changed by anything here.
 
@@ -19,7 +19,7 @@ import wae_b200 as W  # noqa: E402
 nx, ny, nz = (int(a) for a in (sys.argv[1:4] if len(sys.argv) > 3 else (20, 20, 300)))
 order = sys.argv[4] if len(sys.argv) > 4 else "quad"
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 2
-KNOBS = ("WAE_LU_NBO", "WAE_LU_LEAF", "WAE_LU_SKIP_UPPER")
+KNOBS = ("WAE_LU_NBO", "WAE_LU_LEAF", "WAE_LU_SKIP_UPPER", "WAE_LU_GEMM")
 for k in KNOBS:
     os.environ.pop(k, None)
 hz = 0.5 / nz
@@ -38,12 +38,13 @@ op.materialize(0)
 rng = np.random.default_rng(0)
 b = rng.standard_normal(L.size()) + 1j * rng.standard_normal(L.size())
 out = {"tube": [nx, ny, nz], "order": order, "dofs": int(L.size()), "reps": reps, "combos": []}
-for nbo, leaf, skip in ((None, None, None), (64, None, None), (256, None, None), (None, 32, None), (None, 128, None), (None, None, 1), (256, None, 1)):
-    for k, v in zip(KNOBS, (nbo, leaf, skip)):
+for nbo, leaf, skip, gemm in ((None, None, None, None), (64, None, None, None), (256, None, None, None), (None, 32, None, None), (None, 128, None, None),
+                              (None, None, 1, None), (256, None, 1, None), (None, None, None, 2), (None, None, 1, 2)):
+    for k, v in zip(KNOBS, (nbo, leaf, skip, gemm)):
         os.environ.pop(k, None)
         if v is not None:
             os.environ[k] = str(v)
-    row = {"nbo": nbo or 128, "leaf": leaf or 64, "skip_upper": skip or 0}
+    row = {"nbo": nbo or 128, "leaf": leaf or 64, "skip_upper": skip or 0, "gemm": gemm or 1}
     try:
         lid, lu_nnz, lu_flops = ctx.lu_analyze(dev.fid)
         ms = []

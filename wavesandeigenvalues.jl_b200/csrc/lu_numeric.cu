@@ -337,10 +337,103 @@ __device__ __forceinline__ void zgemm_nt_tile(const GemmProblem& P, int tile_m, 
       }
 }
 
+// Opt-in variant of the tile (WAE_LU_GEMM=2; written without GPU access, timed and residual-checked by tools/bench_lu_knobs.py): the
+// operands stay interleaved complex in shared memory and arrive by cp.async (16 bytes per request, zero fill outside the matrices) through a
+// ring of GP_STAGES K tiles, so that the global loads of the next tiles are in flight during the DMMAs of the current one -- the
+// single-buffered tile above exposes the full load latency on the K = 32 / K = 128 pivot-block updates (one to eight K tiles per launch).
+// Fragments come out of shared memory as one LDS.128 per complex number; leading dimension 66: (kk * 66 + row) mod 8 runs through all
+// eight 16-byte bank groups over the eight lanes of a quarter warp (kk = lane & 3, row = lane >> 2) -> conflict-free.
+// Same products in the same order per accumulator as the tile above: the results are bitwise equal.
+#define GP_STAGES 3
+#define GP_LD 66
+#define GP_SMEM (GP_STAGES * 2 * GK * GP_LD * (int)sizeof(cplx))
+
+__device__ __forceinline__ void cp_async16_zfill(void* smem, const void* gmem, bool valid) {
+  const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem);
+  const int bytes = valid ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gmem), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ void zgemm_nt_tile_async(const GemmProblem& P, int tile_m, int tile_n) {
+  extern __shared__ __align__(16) unsigned char gp_smem[];
+  typedef cplx (*Stage)[GK][GP_LD];
+  Stage As = reinterpret_cast<Stage>(gp_smem);                                                 // [stage][k][row]
+  Stage Bs = reinterpret_cast<Stage>(gp_smem + (size_t)GP_STAGES * GK * GP_LD * sizeof(cplx));
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wm = (warp & 3) * 16, wn = (warp >> 2) * 32;
+  const int m0 = tile_m * GT, n0 = tile_n * GT;
+  double acc_r[2][4][2], acc_i[2][4][2];
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) acc_r[a][b][0] = acc_r[a][b][1] = acc_i[a][b][0] = acc_i[a][b][1] = 0.0;
+  const int lr = tid & 63, lk = tid >> 6;  // loader: row lr, k-columns lk, lk+4, lk+8, lk+12
+  const bool a_row = m0 + lr < P.m, b_row = n0 + lr < P.n;
+  const cplx* a_src = P.A + (a_row ? m0 + lr : 0);
+  const cplx* b_src = P.B + (b_row ? n0 + lr : 0);
+  auto load_stage = [&](int kt, int buf) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int kk = lk + 4 * q, k = kt * GK + kk;
+      const bool kin = k < P.K;
+      cp_async16_zfill(&As[buf][kk][lr], a_src + (size_t)(kin ? k : 0) * P.lda, kin && a_row);
+      cp_async16_zfill(&Bs[buf][kk][lr], b_src + (size_t)(kin ? k : 0) * P.ldb, kin && b_row);
+    }
+  };
+  const int nk = (P.K + GK - 1) / GK;
+#pragma unroll
+  for (int s = 0; s < GP_STAGES - 1; s++) {
+    if (s < nk) load_stage(s, s);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  }
+  for (int kt = 0; kt < nk; kt++) {
+    asm volatile("cp.async.wait_group %0;" ::"n"(GP_STAGES - 2) : "memory");  // K tile kt has landed (this thread's part)
+    __syncthreads();  // ... everybody's part; and the buffer refilled below was read for the last time in iteration kt - 1
+    if (kt + GP_STAGES - 1 < nk) load_stage(kt + GP_STAGES - 1, (kt + GP_STAGES - 1) % GP_STAGES);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const int buf = kt % GP_STAGES;
+#pragma unroll
+    for (int ks = 0; ks < GK; ks += 4) {
+      const int kk = ks + (lane & 3), rr = lane >> 2;
+      cplx av[2], bv[4];
+#pragma unroll
+      for (int a = 0; a < 2; a++) av[a] = As[buf][kk][wm + a * 8 + rr];
+#pragma unroll
+      for (int b = 0; b < 4; b++) bv[b] = Bs[buf][kk][wn + b * 8 + rr];
+#pragma unroll
+      for (int a = 0; a < 2; a++)
+#pragma unroll
+        for (int b = 0; b < 4; b++) {
+          dmma(acc_r[a][b][0], acc_r[a][b][1], av[a].x, bv[b].x);
+          dmma(acc_r[a][b][0], acc_r[a][b][1], -av[a].y, bv[b].y);
+          dmma(acc_i[a][b][0], acc_i[a][b][1], av[a].x, bv[b].y);
+          dmma(acc_i[a][b][0], acc_i[a][b][1], av[a].y, bv[b].x);
+        }
+    }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        int row = m0 + wm + a * 8 + (lane >> 2), col = n0 + wn + b * 8 + (lane & 3) * 2 + e;
+        if (row < P.m && col < P.n) {
+          cplx* c = P.C + row + (size_t)col * P.ldc;
+          cplx v = *c;
+          v.x -= acc_r[a][b][e];
+          v.y -= acc_i[a][b][e];
+          *c = v;
+        }
+      }
+}
+
 // mode 0: Lp trailing pivot columns, mode 1: Up trailing pivot columns, mode 2: Schur complement.
 // Modes 0/1 update C = X[c0:ld, c0:min(s,cap)] -= X[c0:ld, k0:k0+kw] * Y[c0:min(s,cap), k0:k0+kw]^T  (X,Y = Lp,Up or Up,Lp).
 // Two-level blocking: inside an outer block of NBO columns the NB-wide steps only touch the columns of that outer block
 // (kw = NB, cap = end of the outer block); the rest of the pivot block is updated once per outer block with kw = NBO.
+template <int PIPE>  // 0: single-buffered tile (the measured kernel), 1: cp.async ring (opt-in, WAE_LU_GEMM=2)
 __global__ void __launch_bounds__(256) lu_gemm_kernel(LuDev D, const int32_t* __restrict__ list, int mode, int k0, int kw, int c0, int cap,
                                                       cplx* __restrict__ upd, int sym) {
   const int sn = list[blockIdx.z];
@@ -369,7 +462,10 @@ __global__ void __launch_bounds__(256) lu_gemm_kernel(LuDev D, const int32_t* __
     P.C = X + c0 + (size_t)c0 * S.ld;
   }
   if ((int)(blockIdx.x * GT) >= P.m || (int)(blockIdx.y * GT) >= P.n) return;
-  zgemm_nt_tile(P, blockIdx.x, blockIdx.y);
+  if constexpr (PIPE == 0)
+    zgemm_nt_tile(P, blockIdx.x, blockIdx.y);
+  else
+    zgemm_nt_tile_async(P, blockIdx.x, blockIdx.y);
 }
 
 // ---- triangular solves ---------------------------------------------------------------------------------
@@ -735,6 +831,17 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
   const int maxd = (int)Y.levels.size() - 1;
   int nbo_blocks = 4;  // outer block = 4 * NB = 128 columns
   if (const char* env = getenv("WAE_LU_NBO")) nbo_blocks = std::max(1, atoi(env) / NB);
+  const bool gemm_ring = getenv("WAE_LU_GEMM") && atoi(getenv("WAE_LU_GEMM")) == 2;
+  if (gemm_ring) {  // 99 KB of dynamic shared memory per CTA, two CTAs per SM
+    CUDA_CHECK(cudaFuncSetAttribute(lu_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GP_SMEM));
+    cudaFuncSetAttribute(lu_gemm_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  }
+  auto gemm = [&](dim3 g, const int32_t* lst, int mode, int k0, int kw, int c0, int cap, cplx* upd_, int flag) {
+    if (gemm_ring)
+      lu_gemm_kernel<1><<<g, 256, GP_SMEM, st>>>(D, lst, mode, k0, kw, c0, cap, upd_, flag);
+    else
+      lu_gemm_kernel<0><<<g, 256, 0, st>>>(D, lst, mode, k0, kw, c0, cap, upd_, flag);
+  };
   const int upd_flag = (sym ? 1 : 0) | ((getenv("WAE_LU_SKIP_UPPER") && atoi(getenv("WAE_LU_SKIP_UPPER"))) ? 2 : 0);  // pivot-block updates only
   for (int d = maxd; d >= 0; d--) {
     const std::vector<int32_t>& L = Y.levels[d];
@@ -777,16 +884,16 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
           int tn = std::min(max_s, oend) - c0;
           if (tn > 0) {
             dim3 g((max_ld - c0 + GT - 1) / GT, (tn + GT - 1) / GT, zc);
-            lu_gemm_kernel<<<g, 256, 0, st>>>(D, lst, 0, k * NB, NB, c0, oend, nullptr, upd_flag);
-            if (!sym) lu_gemm_kernel<<<g, 256, 0, st>>>(D, lst, 1, k * NB, NB, c0, oend, nullptr, upd_flag);
+            gemm(g, lst, 0, k * NB, NB, c0, oend, nullptr, upd_flag);
+            if (!sym) gemm(g, lst, 1, k * NB, NB, c0, oend, nullptr, upd_flag);
             h->launches += sym ? 1 : 2;
           }
           // outer update once the outer block is complete
           if (c0 == oend && max_s > oend) {
             const int o0 = oend - nbo_blocks * NB;
             dim3 g((max_ld - oend + GT - 1) / GT, (max_s - oend + GT - 1) / GT, zc);
-            lu_gemm_kernel<<<g, 256, 0, st>>>(D, lst, 0, o0, oend - o0, oend, 1 << 30, nullptr, upd_flag);
-            if (!sym) lu_gemm_kernel<<<g, 256, 0, st>>>(D, lst, 1, o0, oend - o0, oend, 1 << 30, nullptr, upd_flag);
+            gemm(g, lst, 0, o0, oend - o0, oend, 1 << 30, nullptr, upd_flag);
+            if (!sym) gemm(g, lst, 1, o0, oend - o0, oend, 1 << 30, nullptr, upd_flag);
             h->launches += sym ? 1 : 2;
           }
           h->launches++;
@@ -798,7 +905,7 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
       for (int z0 = 0; z0 < nl; z0 += 32768) {
         int zc = std::min(32768, nl - z0);
         dim3 g((max_r + GT - 1) / GT, (max_r + GT - 1) / GT, zc);
-        lu_gemm_kernel<<<g, 256, 0, st>>>(D, S.d_level[d].p + z0, 2, 0, 0, 0, 0, upd, sym);
+        gemm(g, S.d_level[d].p + z0, 2, 0, 0, 0, 0, upd, sym);
         h->launches++;
       }
     }
