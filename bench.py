@@ -125,6 +125,25 @@ def cpu_scaled(W, st, sample, tube):
                        "estimated_full_size_s": est, "sample_eigenpairs_per_s": 1.0 / st["total"]}
 
 
+T_START = time.perf_counter()
+DIAG_START_BY, DIAG_END_BY = 420.0, 660.0  # seconds since process start
+
+
+def diag_leg(tool, argv, timeout, env=None):
+    """Run tools/<tool> in a subprocess and return the JSON object of its last JSON line; a failure, a time-out or an exhausted wall-clock
+    budget is recorded in the result and never disturbs the bench itself."""
+    elapsed = time.perf_counter() - T_START
+    if elapsed > DIAG_START_BY:
+        return {"skipped": f"diagnostic budget: {elapsed:.0f} s into the run"}
+    try:
+        p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", tool), *argv], capture_output=True, text=True,
+                           timeout=max(30.0, min(timeout, DIAG_END_BY - elapsed)), env=env)
+        line = [l for l in p.stdout.splitlines() if l.startswith("{")]
+        return json.loads(line[-1]) if line else {"error": (p.stderr or p.stdout)[-400:]}
+    except Exception as e:  # noqa: BLE001 -- diagnostic only
+        return {"error": repr(e)[:400]}
+
+
 def W_host():
     """The package for host-only use (mesh generators, host diagnostics); importing it needs no GPU."""
     import wae_b200 as W
@@ -391,24 +410,6 @@ def main():
     # ------------------------------------------------------------------ Beyn leg (sharded over all ranks)
     if not args.skip_extras:
         out["beyn"] = beyn_leg(W, torch, dist, ctx, args, rank, world, dev, barrier, max_over_ranks)
-    # ------------------------------------------------------------------ diagnostic leg: shape sensitivity (rank 0, N = 1 only), in a subprocess
-    if rank == 0 and world == 1 and not args.skip_extras:
-        try:
-            p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_shape_sens.py"), "10", "10", "150", "5"], capture_output=True,
-                               text=True, timeout=300)
-            line = [l for l in p.stdout.splitlines() if l.startswith("{")]
-            out["shape_sensitivity"] = json.loads(line[-1]) if line else {"error": (p.stderr or p.stdout)[-400:]}
-        except Exception as e:  # noqa: BLE001 -- diagnostic leg only
-            out["shape_sensitivity"] = {"error": repr(e)[:400]}
-    # ------------------------------------------------------------------ diagnostic leg: numeric-LU knobs (outer block width, leaf size), same rules
-    if rank == 0 and world == 1 and not args.skip_extras:
-        try:
-            p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_lu_knobs.py"), *(str(x) for x in tube), "quad", "2"], capture_output=True,
-                               text=True, timeout=240)
-            line = [l for l in p.stdout.splitlines() if l.startswith("{")]
-            out["lu_knobs"] = json.loads(line[-1])["combos"] if line else {"error": (p.stderr or p.stdout)[-400:]}
-        except Exception as e:  # noqa: BLE001 -- diagnostic leg only
-            out["lu_knobs"] = {"error": repr(e)[:400]}
     # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1 only)
     if rank == 0 and world == 1 and not args.skip_extras:
         sample = tuple(int(x) for x in args.cpu_sample.split(","))
@@ -422,6 +423,13 @@ def main():
                                           f"{st['total']:.1f} s measured; value = that time scaled phase by phase to the full workload (assembly x "
                                           f"tets, factorisations x factorisation flops, rest x nnz(L+U)): an estimate, the full-size CPU run "
                                           f"takes hours; host has {os.cpu_count()} cores, SuperLU is serial")}
+    # ------------------------------------------------------------------ diagnostic legs (rank 0, N = 1 only), each in a subprocess and inside a
+    # wall-clock budget: a leg that would start later than DIAG_START_BY seconds into the run is skipped, and none may run past DIAG_END_BY
+    if rank == 0 and world == 1 and not args.skip_extras:
+        out["shape_sensitivity"] = diag_leg("bench_shape_sens.py", ["10", "10", "150", "5"], 300)
+        knobs = diag_leg("bench_lu_knobs.py", [*(str(x) for x in tube), "quad", "2"], 240)
+        out["lu_knobs"] = knobs.get("combos", knobs)
+    out["wall_s"] = time.perf_counter() - T_START
     if rank == 0:
         print(json.dumps(out))
     if world > 1:
@@ -453,16 +461,13 @@ def assembly_leg(W, ctx0, n, hbm, hbm_src):
     ctx.close()
     # opt-in kernel variants (WAE_ASM_VARIANT; prepared from the per-phase profile): timed and checked against the
     # default kernel in a SUBPROCESS, so that nothing they do can disturb this run; the headline above is always the default kernel
-    try:
-        p = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_assembly_variants.py"), str(n), "quad", "7"], capture_output=True,
-                           text=True, timeout=240, env={**os.environ, "CUDA_VISIBLE_DEVICES": os.environ.get("CUDA_VISIBLE_DEVICES", str(ctx0.device))})
-        line = [l for l in p.stdout.splitlines() if l.startswith("{")]
-        diag = json.loads(line[-1]) if line else None
-        res["variants"] = diag["variants"] if diag else {"error": (p.stderr or p.stdout)[-400:]}
-        if diag and "layouts" in diag:  # short patch-size x CTAs-per-SM sweep (the default layout stays 12288 slots, one CTA per SM)
-            res["layouts"] = diag["layouts"]
-    except Exception as e:  # noqa: BLE001 -- diagnostic leg only
-        res["variants"] = {"error": repr(e)[:400]}
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:  # the other ranks are waiting for this one: no diagnostics in the scaling runs
+        return res
+    diag = diag_leg("bench_assembly_variants.py", [str(n), "quad", "7"], 240,
+                    env={**os.environ, "CUDA_VISIBLE_DEVICES": os.environ.get("CUDA_VISIBLE_DEVICES", str(ctx0.device))})
+    res["variants"] = diag.get("variants", diag)
+    if "layouts" in diag:  # short patch-size x CTAs-per-SM sweep (the default layout stays 12288 slots, one CTA per SM)
+        res["layouts"] = diag["layouts"]
     return res
 
 
