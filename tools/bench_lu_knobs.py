@@ -1,6 +1,7 @@
 """Short sweep of the numeric-LU tuning knobs (WAE_LU_NBO: outer block width of the pivot-block factorisation, read at every factorisation;
 WAE_LU_LEAF: nested-dissection leaf size, read by the symbolic analysis; WAE_LU_SKIP_UPPER: opt-in skip of the pivot-square tiles above the
-diagonal in the trailing updates; WAE_LU_GEMM=2: opt-in cp.async ring in the DMMA GEMM) on the config-2 tube: per combination one analysis, `reps`
+diagonal in the trailing updates; WAE_LU_GEMM=2: opt-in cp.async ring in the DMMA GEMM; WAE_LU_SOLVE_PF=1: opt-in L2 prefetch
+hint in the triangular window kernels of the solves) on the config-2 tube: per combination one analysis, `reps`
 factorisations (CUDA-event time of the numeric phase), one refined solve and its residual.  Prints ONE JSON line.  bench.py runs this in
 a subprocess as a diagnostic leg; the defaults (NBO 128, LEAF 64) are the measured configuration and are not changed by anything here.
 
@@ -19,7 +20,7 @@ import wae_b200 as W  # noqa: E402
 nx, ny, nz = (int(a) for a in (sys.argv[1:4] if len(sys.argv) > 3 else (20, 20, 300)))
 order = sys.argv[4] if len(sys.argv) > 4 else "quad"
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 2
-KNOBS = ("WAE_LU_NBO", "WAE_LU_LEAF", "WAE_LU_SKIP_UPPER", "WAE_LU_GEMM")
+KNOBS = ("WAE_LU_NBO", "WAE_LU_LEAF", "WAE_LU_SKIP_UPPER", "WAE_LU_GEMM", "WAE_LU_SOLVE_PF")
 for k in KNOBS:
     os.environ.pop(k, None)
 hz = 0.5 / nz
@@ -38,13 +39,14 @@ op.materialize(0)
 rng = np.random.default_rng(0)
 b = rng.standard_normal(L.size()) + 1j * rng.standard_normal(L.size())
 out = {"tube": [nx, ny, nz], "order": order, "dofs": int(L.size()), "reps": reps, "combos": []}
-for nbo, leaf, skip, gemm in ((None, None, None, None), (64, None, None, None), (256, None, None, None), (None, 32, None, None), (None, 128, None, None),
-                              (None, None, 1, None), (256, None, 1, None), (None, None, None, 2), (None, None, 1, 2)):
-    for k, v in zip(KNOBS, (nbo, leaf, skip, gemm)):
+for nbo, leaf, skip, gemm, spf in ((None, None, None, None, None), (64, None, None, None, None), (256, None, None, None, None), (None, 32, None, None, None),
+                                   (None, 128, None, None, None), (None, None, 1, None, None), (256, None, 1, None, None), (None, None, None, 2, None),
+                                   (None, None, 1, 2, None), (None, None, None, None, 1)):
+    for k, v in zip(KNOBS, (nbo, leaf, skip, gemm, spf)):
         os.environ.pop(k, None)
         if v is not None:
             os.environ[k] = str(v)
-    row = {"nbo": nbo or 128, "leaf": leaf or 64, "skip_upper": skip or 0, "gemm": gemm or 1}
+    row = {"nbo": nbo or 128, "leaf": leaf or 64, "skip_upper": skip or 0, "gemm": gemm or 1, "solve_pf": spf or 0}
     try:
         lid, lu_nnz, lu_flops = ctx.lu_analyze(dev.fid)
         ms = []
@@ -52,8 +54,11 @@ for nbo, leaf, skip, gemm in ((None, None, None, None), (64, None, None, None), 
             ctx.lu_factor(lid, 0)
             ms.append(ctx.last_ms("factor"))
         symf = 0.5 if ctx.last_ms("factor_sym") > 0.5 else 1.0
-        x = ctx.lu_solve(lid, b)
-        sol_ms = ctx.last_ms("solve")
+        sol = []
+        for _ in range(3):
+            x = ctx.lu_solve(lid, b)
+            sol.append(ctx.last_ms("solve"))
+        sol_ms = min(sol)
         res = float(np.abs(op.matvec(x) - b).max() / np.abs(b).max())
         row.update({"factor_ms": float(min(ms)), "factor_nnz": float(lu_nnz), "factor_flops": float(lu_flops) * symf, "tflops": symf * lu_flops / max(min(ms), 1e-9) / 1e9,
                     "solve_ms": float(sol_ms), "residual": res, "ok": bool(res <= 1e-6)})

@@ -481,13 +481,33 @@ __global__ void __launch_bounds__(256) lu_gemm_kernel(LuDev D, const int32_t* __
 //   use_up = 0: T_kk^-1 = L_kk^-1            use_up = 1: T_kk = U_kk^T  ->  T_kk^-1 = (U_kk^-1)^T
 #define LU_SOLVE_W 256
 
+// Opt-in (WAE_LU_SOLVE_PF=1, bit 1 of the kernels' use_up argument; written without GPU access, timed and residual-checked by
+// tools/bench_lu_knobs.py): the block steps of a window are a serial chain in which every step waits for one load of its inverse diagonal
+// block and one of its panel rows; with the hint the lower triangle of the window's panel (<= 1 MB) and its inverse blocks (<= 128 KB) are
+// requested into L2 at kernel start, so that the steps wait for L2 instead of HBM.  Pure hints on addresses the kernel reads anyway.
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+__device__ __forceinline__ void tri_window_prefetch(const cplx* P, int ld, const cplx* dinv, int c_lo, int c_hi) {
+  const int w = c_hi - c_lo;
+  const int col = threadIdx.x >> 2;  // four threads per column of the window, 128-byte lines (8 complex) from the diagonal down
+  if (col < w) {
+    const cplx* cp = P + (size_t)(c_lo + col) * ld + c_lo;
+    for (int r = (col & ~7) + 8 * (threadIdx.x & 3); r < w; r += 32) prefetch_l2(cp + r);
+  }
+  const int nblk = (w + NB - 1) / NB;  // NB * NB complex per inverse block = 128 lines
+  for (int l = threadIdx.x; l < nblk * 128; l += blockDim.x) prefetch_l2(dinv + (size_t)(c_lo / NB + (l >> 7)) * 2 * NB * NB + (l & 127) * 8);
+}
+
 __global__ void __launch_bounds__(1024) lu_fwd_tri_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int c_lo, int64_t n, cplx* __restrict__ x) {
   const int sn = list[blockIdx.x];
   SnView S = sn_view(D, sn);
   if (c_lo >= S.s) return;
   const int c_hi = min(c_lo + LU_SOLVE_W, S.s);
+  const int pf = use_up >> 1;
+  use_up &= 1;
   const cplx* P = use_up ? S.up : S.lp;
   const cplx* dinv = D.dinv + D.dinv_off[sn] + (use_up ? NB * NB : 0);
+  if (pf) tri_window_prefetch(P, S.ld, dinv, c_lo, c_hi);
   __shared__ cplx yk[NB];
   __shared__ cplx xw[LU_SOLVE_W];  // the window of x: the block steps work on shared memory only
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -653,8 +673,11 @@ __global__ void __launch_bounds__(1024) lu_bwd_tri_kernel(LuDev D, const int32_t
   SnView S = sn_view(D, sn);
   if (c_lo >= S.s) return;
   const int c_hi = min(c_lo + LU_SOLVE_W, S.s);
+  const int pf = use_up >> 1;
+  use_up &= 1;
   const cplx* P = use_up ? S.up : S.lp;
   const cplx* dinv = D.dinv + D.dinv_off[sn] + (use_up ? NB * NB : 0);
+  if (pf) tri_window_prefetch(P, S.ld, dinv, c_lo, c_hi);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __shared__ cplx yk[NB];
   __shared__ cplx xw[LU_SOLVE_W];  // the window of x in shared memory
@@ -929,6 +952,7 @@ static void lu_sweeps_nr(wae_ctx* h, LuSolver& S, int trans_t, int nrhs, cplx* y
   LuDev D = make_dev(S);
   const int maxd = (int)Y.levels.size() - 1;
   const int fwd_up = trans_t ? 1 : 0;  // A: forward with Lp, backward with Up ; A^T: forward with Up, backward with Lp
+  const int tri_pf = (getenv("WAE_LU_SOLVE_PF") && atoi(getenv("WAE_LU_SOLVE_PF"))) ? 2 : 0;  // bit 1 of the tri kernels' use_up: L2 prefetch hint
   const int zr = (nrhs + NR - 1) / NR;
   const int W = LU_SOLVE_W;
   for (int d = maxd; d >= 0; d--) {
@@ -943,7 +967,7 @@ static void lu_sweeps_nr(wae_ctx* h, LuSolver& S, int trans_t, int nrhs, cplx* y
       const int zc = std::min<int>(32768, (int)L.size() - z0);
       const int32_t* lst = S.d_level[d].p + z0;
       for (int c_lo = 0; c_lo < max_s; c_lo += W) {
-        lu_fwd_tri_kernel<<<dim3(zc, nrhs), 1024, 0, st>>>(D, lst, fwd_up, c_lo, Y.n, y);
+        lu_fwd_tri_kernel<<<dim3(zc, nrhs), 1024, 0, st>>>(D, lst, fwd_up | tri_pf, c_lo, Y.n, y);
         h->launches++;
         const int rows = max_ld - std::min(c_lo + W, max_s);  // upper bound of the rows below the window over the level
         if (max_ld > c_lo + 1 && rows + W > 0) {
@@ -976,7 +1000,7 @@ static void lu_sweeps_nr(wae_ctx* h, LuSolver& S, int trans_t, int nrhs, cplx* y
           lu_bwd_update_kernel<NR><<<dim3(ncg * nrc, zc, zr), 256, 0, st>>>(D, lst, !fwd_up, c_lo, ncg, row_chunk, nrhs, Y.n, y);
           h->launches++;
         }
-        lu_bwd_tri_kernel<<<dim3(zc, nrhs), 1024, 0, st>>>(D, lst, !fwd_up, c_lo, Y.n, y);
+        lu_bwd_tri_kernel<<<dim3(zc, nrhs), 1024, 0, st>>>(D, lst, (int)!fwd_up | tri_pf, c_lo, Y.n, y);
         h->launches++;
       }
     }
