@@ -53,7 +53,7 @@ def test_assembly_tools(monkeypatch, tool):
 
 def test_lu_knob_tool(monkeypatch):
     out = _run(monkeypatch, "bench_lu_knobs.py", ["3", "3", "24", "quad", "1"])
-    assert len(out["combos"]) == 10 and all(r.get("ok") and "free_error" not in r for r in out["combos"]), out
+    assert len(out["combos"]) == 10 and all(r.get("ok") for r in out["combos"]) and "free_error" not in out, out
     assert [(r["nbo"], r["leaf"], r["skip_upper"], r["gemm"], r["solve_pf"]) for r in out["combos"]] == [
         (128, 64, 0, 1, 0), (64, 64, 0, 1, 0), (256, 64, 0, 1, 0), (128, 32, 0, 1, 0), (128, 128, 0, 1, 0), (128, 64, 1, 1, 0), (256, 64, 1, 1, 0),
         (128, 64, 0, 2, 0), (128, 64, 1, 2, 0), (128, 64, 0, 1, 1)]
