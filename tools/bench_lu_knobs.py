@@ -63,6 +63,14 @@ for nbo, leaf, skip, gemm, spf in ((None, None, None, None, None), (64, None, No
             sol.append(ctx.last_ms("solve"))
         sol_ms = min(sol)
         res = float(np.abs(op.matvec(x) - b).max() / np.abs(b).max())
+        if not out["combos"]:  # default configuration only: what a second / eighth right-hand side costs in the same pass over the factor
+            for nr in (2, 8):   # (2 = the direct and the adjoint Arnoldi recurrence of householder advancing together)
+                B = rng.standard_normal((L.size(), nr)) + 1j * rng.standard_normal((L.size(), nr))
+                t = []
+                for _ in range(2):
+                    ctx.lu_solve(lid, B)
+                    t.append(ctx.last_ms("solve"))
+                row[f"solve{nr}_ms"] = float(min(t))
         row.update({"factor_ms": float(min(ms)), "factor_nnz": float(lu_nnz), "factor_flops": float(lu_flops) * symf, "tflops": symf * lu_flops / max(min(ms), 1e-9) / 1e9,
                     "solve_ms": float(sol_ms), "residual": res, "ok": bool(res <= 1e-6)})
     except Exception as e:  # noqa: BLE001 -- diagnostic only
