@@ -599,7 +599,8 @@ void wae_launch_assemble_gather(wae_ctx* h, Pattern& P, const double* d_c, doubl
     CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 1024));
     // several CTAs per SM only co-reside if the L1 / shared-memory split leaves room for all of them (a hint; the one-CTA layout needs the
     // maximum anyway)
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+      cudaGetLastError();  // a refused hint must not surface as the launch's error
     kern<<<grid, threads, smem, h->stream>>>(G.d_desc.p, G.n_patch, G.d_blob.p, G.d_pxyz.p, d_c, G.d_dest.p, G.d_res.p, slot_bytes, pxyz_bytes,
                                              buf_bytes, mass_scale, d_mass, d_stiff, dbg);
   };

@@ -857,7 +857,8 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
   const bool gemm_ring = getenv("WAE_LU_GEMM") && atoi(getenv("WAE_LU_GEMM")) == 2;
   if (gemm_ring) {  // 99 KB of dynamic shared memory per CTA, two CTAs per SM
     CUDA_CHECK(cudaFuncSetAttribute(lu_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GP_SMEM));
-    cudaFuncSetAttribute(lu_gemm_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (cudaFuncSetAttribute(lu_gemm_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+      cudaGetLastError();  // a refused hint must not surface as a launch error
   }
   auto gemm = [&](dim3 g, const int32_t* lst, int mode, int k0, int kw, int c0, int cap, cplx* upd_, int flag) {
     if (gemm_ring)
