@@ -40,13 +40,17 @@ def test_shape_sensitivity_matches_oracle_and_host_replay():
     solo, _, flo = onlevp.householder(Lo, 700 * 2 * math.pi, maxiter=14, tol=1e-11)
     assert abs(solo.params["ω"] - sol.params["ω"]) <= 1e-10 * abs(solo.params["ω"])
     so, tro, tto = oshape.get_surface_points(mo)
-    want = oshape.discrete_adjoint_shape_sensitivity(mo, dscrp, c, so, tro, tto, Lo, solo)
-    scale = np.abs(want).max()
-    assert np.abs(sens - want).max() <= 1e-5 * scale
-    # same inputs through the host replay of the kernel's per-thread function
+    # the oracle's inputs through the host replay of the kernel's per-thread function: all 783 surface points
     w0, v0, va = _normalised(Lo, solo)
     rep = host_replay(mg, dscrp, c, sp_, trm, ttm, w0, v0, va)
+    scale = np.abs(rep).max()
     assert np.abs(sens - rep).max() <= 1e-5 * scale
+    # the oracle's literal loop (six discretize calls per point) on every fourth point -- the replay itself is checked against the full loop
+    # in the CPU suite (tests/test_shape_sensitivity.py), so the subset only has to tie the GPU numbers to the oracle directly
+    sub = list(range(0, len(so), 4))
+    want = oshape.discrete_adjoint_shape_sensitivity(mo, dscrp, c, [so[k] for k in sub], [tro[k] for k in sub], [tto[k] for k in sub], Lo, solo)
+    pts = [so[k] for k in sub]
+    assert np.abs(sens[:, pts] - want[:, pts]).max() <= 1e-5 * scale
     # the product's own eigenvectors through the replay: the launch path itself (indexing, accumulation over the four terms)
     v0g = sol.v / np.sqrt(np.vdot(sol.v, sol.v))
     vag = sol.v_adj / np.conj(np.vdot(sol.v_adj, L(sol.params["ω"], 1) @ v0g))
