@@ -1,0 +1,20 @@
+#!/bin/bash
+# Profiling call of round 2 (one B200): launch list of the bench command and one `ncu --set full` capture each of the assembly kernel and the
+# LU GEMM, every ncu run directly after the same command has exited 0 without ncu (B200_PROFILING.md).  Usage:
+#   gpurun --timeout 1500 -- 'bash tools/r2_profile_call.sh'          (set WAE_* switches in front to profile a non-default configuration)
+# Outputs: gpurun_out/r2p_*; summarise with tools/launch_summary.py / tools/ncu_summary.py / tools/ncu_phase_shares.py into profiles/r02_*.
+set -u
+mkdir -p gpurun_out
+B="python bench.py --steps 1 --warmup 3 --skip-extras"
+A="python tools/bench_assembly.py 64 quad 3"
+L="python tools/bench_lu.py 20 20 300 quad 1"
+$B > gpurun_out/r2p_bench_plain.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/r2p_launches_bench.csv $B > gpurun_out/r2p_bench_ncu.log 2>&1
+echo "launch list exit $?"
+$A > gpurun_out/r2p_asm_plain.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:assemble_tet_pairs -s 2 -c 1 -f -o gpurun_out/r2p_asm $A > gpurun_out/r2p_asm_ncu.log 2>&1
+echo "assembly capture exit $?"
+WAE_NFACTOR=1 WAE_PROBE_ONLY=1 $L > gpurun_out/r2p_lu_plain.log 2>&1 &&
+WAE_NFACTOR=1 WAE_PROBE_ONLY=1 ncu --set full --clock-control none --import-source on -k regex:lu_gemm_kernel -s 300 -c 3 -f -o gpurun_out/r2p_gemm $L > gpurun_out/r2p_lu_ncu.log 2>&1
+echo "gemm capture exit $?"
+ls -la gpurun_out/r2p_* | head -20
