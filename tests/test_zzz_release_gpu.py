@@ -41,7 +41,7 @@ def test_release_returns_device_memory_and_family_rebuilds():
         with pytest.raises(_lib.WaeError):
             ctx.pattern_free(pid)  # a matrix lives on it
         L.release()
-        assert free0 - torch.cuda.mem_get_info(0)[0] < 0.1 * used  # factors, slots and maps are back
+        assert free0 - torch.cuda.mem_get_info(0)[0] < 0.25 * used  # factors, slots and maps are back
         with pytest.raises(_lib.WaeError):
             ctx.lu_free(lid)  # ids are never reused
         with pytest.raises(_lib.WaeError):
