@@ -187,6 +187,15 @@ int32_t wae_pair_program_check(int32_t order, int64_t n_pts, const double* xyz, 
 int32_t wae_eigs_si(wae_ctx* h, int32_t lu_id, int32_t fam_id, int32_t m_slot, int32_t trans,
                     int32_t nev, const double* v0, double* lam, double* V, int32_t* n_solves);
 
+/* eigs(A, M) and eigs(A', M') of one householder / mslp iteration (Householder.jl:100-101; iterative_solvers.jl:132-133) advanced together:
+ * every Arnoldi step applies A^{-1} M to the direct basis vector and A^{-H} M^H to the adjoint one as the two right-hand sides of ONE pass
+ * over the factor.  Same arguments and results as two wae_eigs_si calls (trans 0 with v0 -> lam, V; trans 2 with v0_adj -> lam_adj, V_adj).
+ * Needs a factorisation in symmetric mode (complex-symmetric part + rank-k flame correction); returns WAE_E_INVALID otherwise and the
+ * caller uses wae_eigs_si twice.                                                                                                  */
+int32_t wae_eigs_si_pair(wae_ctx* h, int32_t lu_id, int32_t fam_id, int32_t m_slot, int32_t nev, const double* v0, const double* v0_adj,
+                         double* lam, double* V, double* lam_adj, double* V_adj, int32_t* n_solves);
+
+
 /* ---- Beyn moments --------------------------------------------------------------------
  * Replaces the integrand/gauss loop of beyn.jl:62-74,112-138 for the nodes handed in:
  *   A_p += w_j z_j^p L(z_j)^{-1} V,  p = 0..n_mom-1, V = first l identity columns (beyn.jl:45-48) or the

@@ -256,3 +256,33 @@ def test_release_drops_and_rebuilds_the_device_side(rijke):
         ctx.lu_free(lid)  # ids are never reused
     sol2, _, _ = W.householder(L, 340 * 2 * math.pi, maxiter=20, tol=1e-11, output=False)
     assert L.device().fid != fid and abs(sol2.params["ω"] - sol.params["ω"]) <= 1e-12 * abs(sol.params["ω"])
+
+
+def test_paired_eigs_switch_of_the_host_loop(rijke, monkeypatch):
+    """WAE_EIGS_PAIRED=1: the host loop asks the context for both Arnoldi recurrences in one call (wae_eigs_si_pair) and falls back to two
+    wae_eigs_si calls when the context refuses (general elimination); G1 either way.  (The test double has no pair routine of its own: the
+    two classes below put one over its eigs_si, so that this covers the Python branch only.)"""
+    from wae_b200 import _lib
+    mg, mo, c = rijke
+    calls = {"pair": 0, "refused": 0}
+
+    class Pairing(HostStandIn):
+        def eigs_si_pair(self, lid, fid, m_slot, nev, v0, v0_adj):
+            calls["pair"] += 1
+            lam, V, n1 = self.eigs_si(lid, fid, m_slot, nev, v0, trans=0)
+            lam_a, Va, n2 = self.eigs_si(lid, fid, m_slot, nev, v0_adj, trans=2)
+            return lam, V, lam_a, Va, n1 + n2
+
+    class Refusing(HostStandIn):
+        def eigs_si_pair(self, *a):
+            calls["refused"] += 1
+            raise _lib.WaeError(_lib.E_INVALID, "needs a symmetric-mode factorisation")
+
+    monkeypatch.setenv("WAE_EIGS_PAIRED", "1")
+    g1 = 1710.6977772393461 + 9.615018460173488j
+    for cls in (Pairing, Refusing):
+        L = W.discretize(mg, rijke_dscrp(0.01, 0.001), c, ctx=cls())
+        stats = {}
+        sol, n, flag = W.householder(L, 340 * 2 * math.pi, maxiter=20, tol=1e-11, output=False, stats=stats)
+        assert flag == 1 and abs(sol.params["ω"] - g1) / abs(g1) < TOL and stats["solves"] > 0
+    assert calls["pair"] >= 6 and calls["refused"] == 1  # the refusal is remembered for the rest of the run

@@ -16,7 +16,7 @@ from host_standin import HostStandIn
 from wae_b200 import helmholtz, nlevp, shape
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-KNOBS = ("WAE_GATHER_SLOTS", "WAE_GATHER_CTAS", "WAE_GATHER_THREADS", "WAE_ASM_VARIANT", "WAE_LU_NBO", "WAE_LU_LEAF", "WAE_LU_SKIP_UPPER", "WAE_LU_GEMM", "WAE_LU_SOLVE_PF")
+KNOBS = ("WAE_GATHER_SLOTS", "WAE_GATHER_CTAS", "WAE_GATHER_THREADS", "WAE_ASM_VARIANT", "WAE_LU_NBO", "WAE_LU_LEAF", "WAE_LU_SKIP_UPPER", "WAE_LU_GEMM", "WAE_LU_SOLVE_PF", "WAE_EIGS_PAIRED")
 
 
 def _run(monkeypatch, tool, argv):
@@ -53,6 +53,7 @@ def test_assembly_tools(monkeypatch, tool):
 
 def test_lu_knob_tool(monkeypatch):
     out = _run(monkeypatch, "bench_lu_knobs.py", ["3", "3", "24", "quad", "1"])
+    assert out["householder"]["rel_diff"] < 1e-9 and out["householder"]["paired"]["flag"] >= 0
     assert len(out["combos"]) == 10 and all(r.get("ok") for r in out["combos"]) and "free_error" not in out, out
     assert [(r["nbo"], r["leaf"], r["skip_upper"], r["gemm"], r["solve_pf"]) for r in out["combos"]] == [
         (128, 64, 0, 1, 0), (64, 64, 0, 1, 0), (256, 64, 0, 1, 0), (128, 32, 0, 1, 0), (128, 128, 0, 1, 0), (128, 64, 1, 1, 0), (256, 64, 1, 1, 0),

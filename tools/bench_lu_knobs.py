@@ -11,6 +11,7 @@ import json
 import math
 import os
 import sys
+import time
 
 import numpy as np
 
@@ -78,6 +79,27 @@ for nbo, leaf, skip, gemm, spf in ((None, None, None, None, None), (64, None, No
     out["combos"].append(row)
 for k in KNOBS:
     os.environ.pop(k, None)
+# one eigenpair with the default host loop and with WAE_EIGS_PAIRED=1 (direct and adjoint Arnoldi recurrence as the two right-hand sides of one
+# pass over the factor, wae_eigs_si_pair): wall time, solves, and the difference of the two eigenvalues
+if None in analyses:
+    dev._lu, dev.lu_nnz, dev.lu_flops = analyses[None]  # the family's own handle: no further analysis
+    hh = {}
+    for tag, flag in (("default", None), ("paired", "1")):
+        os.environ.pop("WAE_EIGS_PAIRED", None)
+        if flag:
+            os.environ["WAE_EIGS_PAIRED"] = flag
+        try:
+            st, t0 = {}, time.perf_counter()
+            sol, nit, fl = W.householder(L, z, maxiter=15, tol=1e-9 * abs(z), output=False, stats=st)
+            hh[tag] = {"wall_s": time.perf_counter() - t0, "iterations": nit, "flag": fl, "solves": st.get("solves"), "eigs_wall_s": st.get("eigs_wall_s"),
+                       "omega": [sol.params["ω"].real, sol.params["ω"].imag]}
+        except Exception as e:  # noqa: BLE001 -- diagnostic only
+            hh[tag] = {"error": repr(e)[:200]}
+    os.environ.pop("WAE_EIGS_PAIRED", None)
+    if all("omega" in v for v in hh.values()):
+        a, b2 = complex(*hh["default"]["omega"]), complex(*hh["paired"]["omega"])
+        hh["rel_diff"] = abs(a - b2) / abs(a)
+    out["householder"] = hh
 for leaf, (lid, _, _) in analyses.items():
     try:
         ctx.lu_free(lid)  # 23 GB of factors per analysis at config 2

@@ -78,6 +78,7 @@ SIGNATURES = {
     "wae_family_free": (_i32, [_vp, _i32]),
     "wae_pattern_free": (_i32, [_vp, _i32]),
     "wae_eigs_si": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _pd, _pd, _pd, _pi32]),
+    "wae_eigs_si_pair": (_i32, [_vp, _i32, _i32, _i32, _i32, _pd, _pd, _pd, _pd, _pd, _pd, _pi32]),
     "wae_beyn_moments": (_i32, [_vp, _i32, _i32, _i32, _pd, _pd, _pd, _i32, _i32, _pd, _vp]),
     "wae_assemble_wallsrc": (_i32, [_vp, _i64, _pi64, _pd, _i32, _pd]),
     "wae_shape_sens_begin": (_i32, [_vp, _i64, _pi64, _pi64, _dbl, _i32, _i64, _pd, _pd, _pi64, C.POINTER(C.c_uint8), _pd]),
@@ -325,6 +326,18 @@ class Context:
         ns = _i32()
         self._chk(self._l.wae_eigs_si(self.h, lid, fid, m_slot, trans, nev, _p(v0, _pd), _p(lam, _pd), _p(V, _pd), C.byref(ns)))
         return lam, V, ns.value
+
+    def eigs_si_pair(self, lid, fid, m_slot, nev, v0, v0_adj):
+        """eigs(A, M) and eigs(A', M') advanced together (two right-hand sides per pass over the factor) -> (lam, V, lam_adj, V_adj, solves)."""
+        v0 = np.ascontiguousarray(v0, dtype=np.complex128)
+        v0a = np.ascontiguousarray(v0_adj, dtype=np.complex128)
+        d = v0.shape[0]
+        lam, lam_a = np.empty(nev, dtype=np.complex128), np.empty(nev, dtype=np.complex128)
+        V, Va = np.empty((d, nev), dtype=np.complex128, order="F"), np.empty((d, nev), dtype=np.complex128, order="F")
+        ns = _i32()
+        self._chk(self._l.wae_eigs_si_pair(self.h, lid, fid, m_slot, nev, _p(v0, _pd), _p(v0a, _pd), _p(lam, _pd), _p(V, _pd), _p(lam_a, _pd),
+                                           _p(Va, _pd), C.byref(ns)))
+        return lam, V, lam_a, Va, ns.value
 
     def moment_buffer(self, n_mom, l, d):
         """Zeroed (n_mom, l, d) complex tensor on this context's GPU for wae_beyn_moments (== d x l x n_mom column-major); the context is

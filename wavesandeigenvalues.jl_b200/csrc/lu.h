@@ -57,6 +57,8 @@ struct LuSolver {
   DevBuf<cplx> d_work;                 // solve workspace (n x nrhs) x 3
   DevBuf<cplx> d_io;                   // cached staging buffer of wae_lu_solve / wae_beyn_moments
   DevBuf<cplx> d_arn_V, d_arn_w, d_arn_t, d_arn_c;  // cached Arnoldi workspace of wae_eigs_si
+  DevBuf<cplx> d_arn2_V, d_arn2_c, d_arn_pair;      // second Krylov basis and the n x 2 operand of wae_eigs_si_pair
+  DevBuf<double> d_arn2_dots;
   DevBuf<double> d_arn_dots;
   DevBuf<int32_t> d_flag;              // device-side status (bad pivot)
   int work_nrhs = 0;
@@ -83,3 +85,5 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
 void wae_lu_base_solve(wae_ctx* h, LuSolver& S, int tt, int nrhs, cplx* d_X);
 // X (n x nrhs, column-major, device) <- op(A)^{-1} X; trans: 0 N, 1 T, 2 C
 void wae_lu_solve_device(wae_ctx* h, LuSolver& S, int trans, int nrhs, cplx* d_X, int refine);
+// X2 (n x 2): column 0 <- A^{-1} x0, column 1 <- A^{-H} x1 in one pass over a symmetric-mode factor (no refinement)
+void wae_lu_solve_pair_device(wae_ctx* h, LuSolver& S, cplx* d_X2);

@@ -472,6 +472,191 @@ int32_t wae_lu_solve(wae_ctx* h, int32_t lu_id, int32_t trans, int32_t nrhs, dou
   WAE_API_END
 }
 
+// One shift-invert Arnoldi process of wae_eigs_si_pair as a state machine: input() names the basis vector the operator has to be applied
+// to, consume() takes the result (left in `w` by the caller) through Gram-Schmidt, the Ritz test and -- after ncv steps without
+// convergence -- the explicit restart.  Same arithmetic, tolerances and stopping rule as the loop of wae_eigs_si.
+namespace {
+struct ArnoldiProc {
+  wae_ctx* h;
+  int64_t n;
+  int m, nev;
+  cplx *V, *w, *c;  // basis n x (m+1), operator result (a column of the pair buffer), m+1 coefficients
+  double* dots;     // 2 (m+2)
+  std::vector<zc> H, Hs, theta, Y, hcol, h2;
+  std::vector<int> order;
+  int restart = 0, j = 0, jdim = 0;
+  bool converged = false, done = false;
+  double best_res = 1e300;
+  static constexpr int max_restart = 15;
+  static constexpr double tol = 1e-13;
+
+  void dot(const cplx* Vb, int nv, const cplx* x, std::vector<zc>& out) {
+    cudaStream_t st = h->stream;
+    const int dot_blocks = (int)std::min<int64_t>((n + 255) / 256, 64);
+    CUDA_CHECK(cudaMemsetAsync(dots, 0, 2 * nv * sizeof(double), st));
+    multi_dot_kernel<<<dim3(dot_blocks, nv), 256, 0, st>>>(Vb, n, x, dots);
+    h->launches++;
+    out.resize(nv);
+    CUDA_CHECK(cudaMemcpyAsync(out.data(), dots, 2 * nv * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+  void upload_c(const std::vector<zc>& cc) { CUDA_CHECK(cudaMemcpyAsync(c, cc.data(), cc.size() * sizeof(zc), cudaMemcpyHostToDevice, h->stream)); }
+  unsigned gb() const { return (unsigned)((n + 255) / 256); }
+
+  void start(const double* v0_host) {  // w is free at this point: it stages the start vector
+    cudaStream_t st = h->stream;
+    CUDA_CHECK(cudaMemcpyAsync(w, v0_host, n * sizeof(cplx), cudaMemcpyHostToDevice, st));
+    dot(w, 1, w, hcol);
+    double nrm = std::sqrt(hcol[0].real());
+    if (!(nrm > 0.0) || !std::isfinite(nrm)) WAE_THROW(WAE_E_INVALID, "start vector is zero or not finite");
+    perturb_start_kernel<<<gb(), 256, 0, st>>>(w, n, 1e-6 * nrm / std::sqrt((double)n));
+    h->launches++;
+    dot(w, 1, w, hcol);
+    nrm = std::sqrt(hcol[0].real());
+    scale_copy_kernel<<<gb(), 256, 0, st>>>(w, n, 1.0 / nrm, V);
+    h->launches++;
+    H.assign((size_t)(m + 1) * m, 0.0);
+  }
+  const cplx* input() const { return V + (size_t)j * n; }
+  void consume() {
+    cudaStream_t st = h->stream;
+    dot(V, j + 1, w, hcol);  // classical Gram-Schmidt with one reorthogonalisation
+    upload_c(hcol);
+    multi_axpy_kernel<<<gb(), 256, 0, st>>>(V, n, j + 1, c, w);
+    dot(V, j + 1, w, h2);
+    upload_c(h2);
+    multi_axpy_kernel<<<gb(), 256, 0, st>>>(V, n, j + 1, c, w);
+    h->launches += 2;
+    for (int i = 0; i <= j; i++) H[(size_t)i * m + j] = hcol[i] + h2[i];
+    std::vector<zc> nn;
+    dot(w, 1, w, nn);
+    const double beta = std::sqrt(std::max(0.0, nn[0].real()));
+    if (!std::isfinite(beta)) WAE_THROW(WAE_E_SINGULAR, "non-finite Krylov vector (singular factorisation)");
+    H[(size_t)(j + 1) * m + j] = beta;
+    jdim = j + 1;
+    Hs.assign((size_t)jdim * jdim, 0.0);
+    for (int a = 0; a < jdim; a++)
+      for (int b = 0; b < jdim; b++) Hs[(size_t)a * jdim + b] = H[(size_t)a * m + b];
+    hessenberg_eig(jdim, Hs, theta, Y);
+    order.resize(jdim);
+    for (int i = 0; i < jdim; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return std::abs(theta[a]) > std::abs(theta[b]); });
+    bool ok = jdim >= nev;
+    double worst = 0;
+    for (int i = 0; i < nev && ok; i++) {
+      const int q = order[i];
+      const double rel = beta * std::abs(Y[(size_t)(jdim - 1) * jdim + q]) / std::max(std::abs(theta[q]), 1e-300);
+      worst = std::max(worst, rel);
+      if (!(rel <= tol)) ok = false;
+    }
+    if (jdim >= nev) best_res = std::min(best_res, worst);
+    if (ok || beta <= 1e-300) {
+      converged = done = true;
+      return;
+    }
+    if (j + 1 < m) {
+      scale_copy_kernel<<<gb(), 256, 0, st>>>(w, n, 1.0 / beta, V + (size_t)(j + 1) * n);
+      h->launches++;
+      j++;
+      return;
+    }
+    if (restart == max_restart) {  // ncv steps of the last restart are used up
+      done = true;
+      return;
+    }
+    std::vector<zc> cc(jdim, 0.0);  // explicit restart with the sum of the wanted Ritz vectors
+    for (int i = 0; i < nev; i++)
+      for (int a = 0; a < jdim; a++) cc[a] += Y[(size_t)a * jdim + order[i]];
+    upload_c(cc);
+    lincomb_kernel<<<gb(), 256, 0, st>>>(V, n, jdim, c, w);
+    dot(w, 1, w, nn);
+    scale_copy_kernel<<<gb(), 256, 0, st>>>(w, n, 1.0 / std::sqrt(nn[0].real()), V);
+    h->launches += 2;
+    std::fill(H.begin(), H.end(), 0.0);
+    restart++;
+    j = 0;
+  }
+  // Ritz vectors -> host (through w); lambda = 1 / theta
+  void result(double* lam, double* Vout) {
+    cudaStream_t st = h->stream;
+    if (!converged && !(best_res <= 1e-8)) WAE_THROW(WAE_E_NOCONV, "Arnoldi did not converge (best relative Ritz residual %.3e)", best_res);
+    for (int i = 0; i < nev; i++) {
+      const int q = order[i];
+      std::vector<zc> cc(jdim);
+      for (int a = 0; a < jdim; a++) cc[a] = Y[(size_t)a * jdim + q];
+      upload_c(cc);
+      lincomb_kernel<<<gb(), 256, 0, st>>>(V, n, jdim, c, w);
+      h->launches++;
+      CUDA_CHECK(cudaMemcpyAsync(Vout + 2 * (size_t)i * n, w, n * sizeof(cplx), cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));  // w is reused by the next vector
+      const zc l = 1.0 / theta[q];
+      lam[2 * i] = l.real();
+      lam[2 * i + 1] = l.imag();
+    }
+  }
+};
+}  // namespace
+
+// The two shift-invert eigenproblems of one householder / mslp iteration -- eigs(A, M) and eigs(A', M') (Householder.jl:100-101,
+// iterative_solvers.jl:132-133) -- advanced TOGETHER: every step applies A^{-1} M to the direct basis vector and A^{-H} M^H to the adjoint
+// one as the two right-hand sides of one pass over the factor (wae_lu_solve_pair_device).  Needs the symmetric-mode factorisation; the
+// caller falls back to two wae_eigs_si calls otherwise.  Opt-in from the host mirror (WAE_EIGS_PAIRED=1); written without GPU access.
+int32_t wae_eigs_si_pair(wae_ctx* h, int32_t lu_id, int32_t fam_id, int32_t m_slot, int32_t nev, const double* v0, const double* v0_adj,
+                         double* lam, double* Vout, double* lam_adj, double* Vout_adj, int32_t* n_solves) {
+  WAE_API_BEGIN
+  CUDA_CHECK(cudaSetDevice(h->device));
+  LuSolver& S = get_lu(h, lu_id);
+  Family& F = h->fam(fam_id);
+  if (fam_id != S.fam) WAE_THROW(WAE_E_INVALID, "the LU belongs to another family");
+  if (m_slot < 0 || m_slot >= WAE_FAMILY_SLOTS || !F.slot[m_slot].p) WAE_THROW(WAE_E_INVALID, "family slot %d (M) is empty", m_slot);
+  if (!S.factored || !S.sym_mode) WAE_THROW(WAE_E_INVALID, "wae_eigs_si_pair needs a symmetric-mode factorisation (use wae_eigs_si twice)");
+  const int64_t n = S.sym.n;
+  if (nev < 1 || nev >= n || !v0 || !v0_adj || !lam || !Vout || !lam_adj || !Vout_adj) WAE_THROW(WAE_E_INVALID, "bad eigs arguments");
+  const int m = (int)std::min<int64_t>(std::max(20, 2 * nev + 1), n);
+  PhaseTimer timer(h, "eigs");
+  S.d_arn_V.reserve((size_t)n * (m + 1));
+  S.d_arn2_V.reserve((size_t)n * (m + 1));
+  S.d_arn_c.reserve(m + 1);
+  S.d_arn2_c.reserve(m + 1);
+  S.d_arn_dots.reserve(2 * (m + 2));
+  S.d_arn2_dots.reserve(2 * (m + 2));
+  S.d_arn_pair.reserve((size_t)2 * n);
+  ArnoldiProc P[2];
+  for (int q = 0; q < 2; q++) {
+    P[q].h = h;
+    P[q].n = n;
+    P[q].m = m;
+    P[q].nev = nev;
+    P[q].w = S.d_arn_pair.p + (size_t)q * n;
+  }
+  P[0].V = S.d_arn_V.p;  P[0].c = S.d_arn_c.p;  P[0].dots = S.d_arn_dots.p;
+  P[1].V = S.d_arn2_V.p; P[1].c = S.d_arn2_c.p; P[1].dots = S.d_arn2_dots.p;
+  P[0].start(v0);
+  P[1].start(v0_adj);
+  int solves = 0;
+  while (!P[0].done || !P[1].done) {
+    if (!P[0].done && !P[1].done) {
+      wae_spmm_device(h, F, m_slot, 0, 1, P[0].input(), P[0].w);
+      wae_spmm_device(h, F, m_slot, 2, 1, P[1].input(), P[1].w);
+      wae_lu_solve_pair_device(h, S, S.d_arn_pair.p);
+      solves += 2;
+      P[0].consume();
+      P[1].consume();
+    } else {  // one process has converged: the other one finishes alone
+      const int q = P[0].done ? 1 : 0;
+      wae_spmm_device(h, F, m_slot, q ? 2 : 0, 1, P[q].input(), P[q].w);
+      wae_lu_solve_device(h, S, q ? 2 : 0, 1, P[q].w, S.eigs_refine);
+      solves++;
+      P[q].consume();
+    }
+  }
+  P[0].result(lam, Vout);
+  P[1].result(lam_adj, Vout_adj);
+  timer.stop();
+  if (n_solves) *n_solves = solves;
+  WAE_API_END
+}
+
 int32_t wae_eigs_si(wae_ctx* h, int32_t lu_id, int32_t fam_id, int32_t m_slot, int32_t trans, int32_t nev, const double* v0,
                     double* lam, double* Vout, int32_t* n_solves) {
   WAE_API_BEGIN

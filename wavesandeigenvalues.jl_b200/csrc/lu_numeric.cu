@@ -1106,6 +1106,33 @@ static void lu_apply_inverse(wae_ctx* h, LuSolver& S, int trans, int nrhs, cplx*
   if (trans == 2) conj_kernel<<<gt, 256, 0, st>>>(n * nrhs, d_X);
 }
 
+// X2 (n x 2, device): column 0 <- A^{-1} x0, column 1 <- A^{-H} x1 in ONE pass over the factor.  Only with the symmetric elimination:
+// the factorised part S is complex symmetric, so A^{-H} x = conj(A^{-T} conj(x)) needs the same S^{-1} sweeps as A^{-1} x (S^{-T} = S^{-1});
+// the two columns differ in the rank-k correction alone (flame terms: Woodbury with the (Gm, Z) resp. (Sm, Zt) vectors).  No refinement.
+void wae_lu_solve_pair_device(wae_ctx* h, LuSolver& S, cplx* d_X2) {
+  if (!S.factored || !S.sym_mode) WAE_THROW(WAE_E_INVALID, "paired solve needs a symmetric-mode factorisation");
+  const int64_t n = S.sym.n;
+  cudaStream_t st = h->stream;
+  const unsigned gn = (unsigned)((n + 255) / 256);
+  conj_kernel<<<gn, 256, 0, st>>>(n, d_X2 + n);
+  wae_lu_base_solve(h, S, 0, 2, d_X2);
+  if (S.r1_k > 0) {
+    const int k = S.r1_k;
+    const int chunks = (int)std::min<int64_t>((n + 255) / 256, 64);
+    S.d_r1_t.reserve((size_t)k * 2);
+    for (int tt = 0; tt < 2; tt++) {
+      cplx* x = d_X2 + (size_t)tt * n;
+      CUDA_CHECK(cudaMemsetAsync(S.d_r1_t.p, 0, (size_t)k * sizeof(cplx), st));
+      r1_dots_kernel<<<dim3(chunks, k, 1), 256, 0, st>>>(tt ? S.d_r1_Sm.p : S.d_r1_Gm.p, n, k, x, S.d_r1_t.p);
+      r1_apply_kernel<<<gn, 256, 0, st>>>(tt ? S.d_r1_Zt.p : S.d_r1_Z.p, tt ? S.d_r1_KinvT.p : S.d_r1_Kinv.p, S.d_r1_t.p, n, k, 1, x);
+    }
+    h->launches += 4;
+  }
+  conj_kernel<<<gn, 256, 0, st>>>(n, d_X2 + n);
+  h->launches += 2;
+  CUDA_CHECK(cudaGetLastError());
+}
+
 void wae_lu_solve_device(wae_ctx* h, LuSolver& S, int trans, int nrhs, cplx* d_X, int refine) {
   Family& F = h->fam(S.fam);
   if (!S.factored) WAE_THROW(WAE_E_INVALID, "wae_lu_factor has not been called (or failed)");

@@ -16,6 +16,7 @@ Scalar coefficient functions stay on the host (they are arbitrary closures in th
 only their values cross the ABI.
 """
 import math
+import os
 import time
 
 import numpy as np
@@ -760,6 +761,7 @@ def _iterate(L, z, maxiter, tol, relax, order, nev, v0, v0_adj, kind, num_order,
     mcoef = [None] * len(L.terms)
     mcoef[-1] = -1.0
     dev.combine(dev.flat(mcoef), 1)
+    paired = os.environ.get("WAE_EIGS_PAIRED", "0") == "1" and hasattr(ctx, "eigs_si_pair")
     try:
         while abs(z - z0) > tol and n < maxiter:
             if output:
@@ -772,8 +774,17 @@ def _iterate(L, z, maxiter, tol, relax, order, nev, v0, v0_adj, kind, num_order,
             L(z).materialize(0)
             ctx.lu_factor(lu, 0)
             _t1 = time.perf_counter()
-            lams, v, ns1 = ctx.eigs_si(lu, dev.fid, 1, nev, v0, trans=0)
-            lams_adj, v_adj, ns2 = ctx.eigs_si(lu, dev.fid, 1, nev, v0_adj, trans=2)
+            if paired:  # opt-in: both Arnoldi recurrences as the two right-hand sides of one pass over the factor
+                try:
+                    lams, v, lams_adj, v_adj, ns1 = ctx.eigs_si_pair(lu, dev.fid, 1, nev, v0, v0_adj)
+                    ns2 = 0
+                except _lib.WaeError as e:
+                    if e.code != _lib.E_INVALID:
+                        raise
+                    paired = False  # general (unsymmetric) elimination: two separate calls
+            if not paired:
+                lams, v, ns1 = ctx.eigs_si(lu, dev.fid, 1, nev, v0, trans=0)
+                lams_adj, v_adj, ns2 = ctx.eigs_si(lu, dev.fid, 1, nev, v0_adj, trans=2)
             _t2 = time.perf_counter()
             if stats is not None:
                 stats["factorizations"] = stats.get("factorizations", 0) + 1
