@@ -427,8 +427,7 @@ def main():
     # wall-clock budget: a leg that would start later than DIAG_START_BY seconds into the run is skipped, and none may run past DIAG_END_BY
     if rank == 0 and world == 1 and not args.skip_extras:
         out["shape_sensitivity"] = diag_leg("bench_shape_sens.py", ["10", "10", "150", "5"], 300)
-        knobs = diag_leg("bench_lu_knobs.py", [*(str(x) for x in tube), "quad", "2"], 240)
-        out["lu_knobs"] = knobs.get("combos", knobs)
+        out["lu_knobs"] = diag_leg("bench_lu_knobs.py", [*(str(x) for x in tube), "quad", "2"], 240)  # "combos" + "householder" (default vs paired)
     out["wall_s"] = time.perf_counter() - T_START
     if rank == 0:
         print(json.dumps(out))
