@@ -180,6 +180,16 @@ int32_t wae_lu_symbolic_stats(int64_t n, const int64_t* colptr, const int64_t* r
 int32_t wae_pair_program_check(int32_t order, int64_t n_pts, const double* xyz, int64_t n_tet, const uint32_t* tets,
                                int32_t slot_cap, double* out);
 
+/* Host-only diagnostic (needs no GPU and no context): build the sparsity pattern and the STAR program of the third-generation
+ * M/K assembly kernel (csrc/assembly_star*.c*) for a tetrahedral mesh and replay the kernel's three passes (geometry, star sums
+ * and roles, chunked stores) on the host with the kernel's own arithmetic, c constant per element (n_tet values).  Returns the
+ * CSC pattern (colptr: dim + 1, rowval / val_m / val_k: up to nnz_cap entries, 0-based) and stats[0..7] = nnz, patches, staged
+ * elements, sub-simplices, star sources, shared memory of one CTA (bytes), program size (bytes), number of violated invariants
+ * (every nonzero written exactly once, alignment of the staged pieces, bounds).                                               */
+int32_t wae_star_program_check(int32_t order, int64_t n_pts, const double* xyz, int64_t n_tet, const uint32_t* tets, const double* c,
+                               int64_t smem_budget, int64_t nnz_cap, int64_t* colptr, int32_t* rowval, double* val_m, double* val_k,
+                               double* stats);
+
 /* ---- shift-invert Arnoldi: nev eigenpairs of A v = lambda M v nearest 0 ----------------
  * Replaces Arpack.eigs(A,M;nev,sigma=0,v0) (Householder.jl:100-101, iterative_solvers.jl:132-133).
  * A is the matrix factorised in lu_id, M the family slot m_slot.  trans=2 gives the adjoint

@@ -209,6 +209,80 @@ def test_assembly_pair_program_on_host(meshes):
     assert one["patches"] == 1 and one["staged"] == one["ntet"] and one["sources"] == 10 * one["ntet"]
 
 
+def _star_program_check(mesh, order, budget, c):
+    from wae_b200 import _lib
+    _, tets, dim = W.aggregate_elements(mesh, order)
+    lib = _lib.lib()
+    pd, pi64 = C.POINTER(C.c_double), C.POINTER(C.c_int64)
+    lib.wae_star_program_check.restype = C.c_int32
+    lib.wae_star_program_check.argtypes = [C.c_int32, C.c_int64, pd, C.c_int64, C.POINTER(C.c_uint32), pd, C.c_int64, C.c_int64, pi64,
+                                           C.POINTER(C.c_int32), pd, pd, pd]
+    xyz = np.ascontiguousarray(mesh.points.T, dtype=np.float64)
+    t32 = np.ascontiguousarray(tets, dtype=np.uint32)
+    nloc = t32.shape[1]
+    cap = len(t32) * nloc * nloc
+    colptr, rowval = np.zeros(dim + 1, dtype=np.int64), np.zeros(cap, dtype=np.int32)
+    vm, vk, st = np.zeros(cap), np.zeros(cap), np.zeros(8)
+    cc = np.ascontiguousarray(c, dtype=np.float64)
+    rc = lib.wae_star_program_check(1 if order == "lin" else 2, xyz.shape[0], xyz.ctypes.data_as(pd), len(t32), t32.ctypes.data_as(C.POINTER(C.c_uint32)),
+                                    cc.ctypes.data_as(pd), budget, cap, colptr.ctypes.data_as(pi64), rowval.ctypes.data_as(C.POINTER(C.c_int32)),
+                                    vm.ctypes.data_as(pd), vk.ctypes.data_as(pd), st.ctypes.data_as(pd))
+    assert rc == 0
+    nnz = int(st[0])
+    return dict(nnz=nnz, patches=int(st[1]), staged=int(st[2]), simplices=int(st[3]), sources=int(st[4]), smem=int(st[5]), program=int(st[6]),
+                bad=int(st[7]), ntet=len(t32), colptr=colptr, rowval=rowval[:nnz], vm=vm[:nnz], vk=vk[:nnz], tets=t32, xyz=xyz, dim=dim)
+
+
+def _oracle_mk(xyz, tets, c, order, dim):
+    """M and K = -c^2 int grad.grad as sparse() of the element triplets, from the oracle's exact tables (vectorised over the elements)."""
+    import scipy.sparse as sp
+    from oracle import fem
+    T = fem.tables(1 if order == "lin" else 2, 4)
+    X = xyz[tets[:, :4].astype(np.int64)]                       # n x 4 x 3
+    J = np.transpose(X[:, :3, :] - X[:, 3:4, :], (0, 2, 1))       # columns = edges
+    inv = np.linalg.inv(J)
+    det = np.abs(np.linalg.det(J))
+    G = np.concatenate([inv, -inv.sum(axis=1, keepdims=True)], axis=1)
+    GG = np.einsum("nad,nbd->nab", G, G)
+    Ke = np.einsum("ijab,nab->nij", np.asarray(T["stiff"], dtype=float), GG) * (-(c ** 2) * det)[:, None, None]
+    Me = np.asarray(T["mass"], dtype=float)[None] * det[:, None, None]
+    nloc = tets.shape[1]
+    I = np.repeat(tets.astype(np.int64), nloc, axis=1).ravel()
+    Jc = np.tile(tets.astype(np.int64), (1, nloc)).ravel()
+    M = sp.coo_matrix((Me.ravel(), (I, Jc)), shape=(dim, dim)).tocsc()
+    K = sp.coo_matrix((Ke.ravel(), (I, Jc)), shape=(dim, dim)).tocsc()
+    for A in (M, K):
+        A.sum_duplicates()
+        A.sort_indices()
+    return M, K
+
+
+def test_assembly_star_program_on_host(meshes):
+    """The star program of the third-generation M/K assembly kernel, replayed on the host with the kernel's own arithmetic (no GPU):
+    pattern identical to sparse() of the element triplets, every nonzero written exactly once, values equal to the oracle's element
+    tables summed per nonzero; unstructured Rijke mesh (P1, P2) and a jittered Kuhn box cut into many patches, few patches, one patch."""
+    mg, _ = meshes
+    box = W.kuhn_box((6, 5, 7), (0, 0, 0), (1, 1, 1), jitter=0.1, seed=5)
+    rng = np.random.default_rng(3)
+    for mesh, order, budget in ((mg, "lin", 40 * 1024), (mg, "quad", 112 * 1024), (mg, "quad", 60 * 1024), (box, "quad", 224 * 1024),
+                                (box, "quad", 112 * 1024), (box, "quad", 48 * 1024), (box, "lin", 224 * 1024), (box, "lin", 24 * 1024)):
+        ntet = len(mesh.tetrahedra)
+        c = 300.0 + 400.0 * rng.random(ntet)
+        r = _star_program_check(mesh, order, budget, c)
+        assert r["bad"] == 0, {k: v for k, v in r.items() if np.isscalar(v)}
+        assert r["smem"] <= budget
+        M, K = _oracle_mk(r["xyz"], r["tets"], c, order, r["dim"])
+        assert np.array_equal(r["colptr"], M.indptr) and np.array_equal(r["rowval"], M.indices)
+        assert np.abs(r["vm"] - M.data).max() <= 1e-12 * np.abs(M.data).max()
+        assert np.abs(r["vk"] - K.data).max() <= 1e-12 * np.abs(K.data).max()
+        # every sub-simplex of every element is a source at least once; patches only repeat stars on their rim
+        per = 10 if order == "lin" else 15
+        assert per * ntet <= r["sources"] <= 4 * per * ntet and r["staged"] >= ntet
+    small = W.kuhn_box((3, 3, 4), (0, 0, 0), (1, 1, 1), jitter=0.1, seed=6)
+    one = _star_program_check(small, "lin", 224 * 1024, np.full(len(small.tetrahedra), 340.0))
+    assert one["patches"] == 1 and one["staged"] == one["ntet"] and one["sources"] == 10 * one["ntet"]
+
+
 def test_kuhn_box_is_conforming():
     m = W.kuhn_box((3, 2, 4), (0, 0, 0), (3, 2, 4), jitter=0.1, seed=3, flame_layer=(1, 2))
     X = m.points[:, m.tetrahedra]

@@ -69,8 +69,84 @@ def sym_table(name, n, fn):
     return f"static __device__ const double {name}[{n * n}] = {{{', '.join(vals)}}};\n"
 
 
+# ---- star program (assembly generation 3) ----------------------------------------------------------------------------
+# Every nonzero (p, q) of M and K belongs to the sub-simplex spanned by the vertices of its two DOFs (a vertex, an edge, a face or
+# the tetrahedron); its sources are the elements of that simplex's star.  Because the Lagrange bases are invariant under vertex
+# permutations, K_e[p, q] is the SAME linear combination of the element's gram entries g_xy (x, y vertices of the simplex) in every
+# element of the star, and M_e[p, q] is one coefficient times |det|.  The kernel therefore sums g_xy and |det| over the star once
+# per simplex and forms all nonzeros of the simplex from those sums ("roles").  This function derives the combinations from the
+# exact integrals, checks the permutation invariance it relies on, and emits them.
+def star_section(order, tag, phi, dphi):
+    from itertools import permutations
+    n = len(phi)
+    edges = [(a, b) for a in range(4) for b in range(a + 1, 4)]
+
+    def dof_verts(i):
+        return (i,) if i < 4 else edges[i - 4]
+
+    def dof_of(verts):
+        verts = tuple(sorted(verts))
+        return verts[0] if len(verts) == 1 else 4 + edges.index(verts)
+
+    def kcoef(i, j):  # {(x, y) x<=y: coefficient of g_xy in K[i][j]}
+        r = {}
+        for a in range(4):
+            for b in range(4):
+                c = pint(pmul(dphi[i][a], dphi[j][b]), 4)
+                if c != 0:
+                    key = (min(a, b), max(a, b))
+                    r[key] = r.get(key, 0) + c
+        return {k: v for k, v in r.items() if v != 0}
+
+    if order == 1:
+        ents = [("vert", (0,), [(0, 0)], [(0, 0)]), ("edge", (0, 1), [(0, 1)], [(0, 1)])]
+    else:
+        ents = [
+            ("vert", (0,), [(0, 0)], [(0, 0)]),
+            ("edge", (0, 1), [(0, 0), (1, 1), (0, 1)], [(0, 1), (0, 4), (1, 4), (4, 4)]),
+            ("face", (0, 1, 2), [(0, 0), (1, 1), (2, 2), (0, 1), (0, 2), (1, 2)], [(2, 4), (1, 5), (0, 7), (4, 5), (4, 7), (5, 7)]),
+            ("tet", (0, 1, 2, 3), [(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)], [(4, 9), (5, 8), (6, 7)]),
+        ]
+    out = [f"// ---- star program, {tag}: roles of the nonzeros of a vertex / edge / face / tetrahedron star (see tools/gen_fem_tables.py)\n"]
+    mass = []
+    nrole = 0
+    for name, verts, sums, roles in ents:
+        body = []
+        for r, (p, q) in enumerate(roles):
+            kc = kcoef(p, q)
+            assert set(kc) <= set(sums), (name, p, q, kc)
+            # permutation invariance: relabelling the vertices maps the role onto an entry with the same coefficients
+            for perm in permutations(range(4)):
+                pp = dof_of([perm[v] for v in dof_verts(p)])
+                qq = dof_of([perm[v] for v in dof_verts(q)])
+                kp = kcoef(pp, qq)
+                mapped = {(min(perm[x], perm[y]), max(perm[x], perm[y])): c for (x, y), c in kc.items()}
+                assert kp == mapped, (name, p, q, perm)
+                assert pint(pmul(phi[pp], phi[qq]), 4) == pint(pmul(phi[p], phi[q]), 4)
+            # group equal coefficients: c1 * (S[i] + S[j]) + ...
+            bycoef = {}
+            for key, c in kc.items():
+                bycoef.setdefault(c, []).append(sums.index(key))
+            terms = []
+            for c, idx in sorted(bycoef.items(), key=lambda t: min(t[1])):
+                inner = " + ".join(f"S[{i}]" for i in sorted(idx))
+                terms.append(f"{lit(c)} * ({inner})" if len(idx) > 1 else f"{lit(c)} * {inner}")
+            body.append(f"    K[{r}] = {' + '.join(terms)};\n")
+            mass.append(lit(pint(pmul(phi[p], phi[q]), 4)))
+            nrole += 1
+        sums_txt = ", ".join(f"g{x}{y}" for x, y in sums)
+        roles_txt = ", ".join(f"({p},{q})" for p, q in roles)
+        out.append(f"// {name}: S = sums over the star of [{sums_txt}] (local vertices of the simplex in canonical order), K = entries {roles_txt} of the canonical frame\n")
+        out.append(f"static WAE_HD inline void wae_{tag.lower()}_star_{name}(const double* S, double* K) {{\n{''.join(body)}}}\n")
+    out.append(f"// mass coefficient of every role (times the star's sum of |det|), roles in the order vert, edge, face, tet\n")
+    fill = "".join(f"    m[{i}] = {v};\n" for i, v in enumerate(mass))
+    out.append(f"static WAE_HD inline void wae_{tag.lower()}_star_mass(double* m) {{\n{fill}}}\n")
+    out.append(f"#define WAE_{tag}_STAR_ROLES {nrole}\n")
+    return "".join(out)
+
+
 def main():
-    out = ["// GENERATED by tools/gen_fem_tables.py -- do not edit.\n#pragma once\ntemplate <int S>\nstruct WaeIdx {\n  static constexpr int value = S;\n};\n"]
+    out = ["// GENERATED by tools/gen_fem_tables.py -- do not edit.\n#pragma once\n#ifdef __CUDACC__\n#define WAE_HD __host__ __device__\n#else\n#define WAE_HD\n#endif\ntemplate <int S>\nstruct WaeIdx {\n  static constexpr int value = S;\n};\n"]
     for order, tag in ((1, "P1"), (2, "P2")):
         phi = basis(order, 4)
         n = len(phi)
@@ -128,6 +204,7 @@ def main():
                         c = pint(pmul(gab, pmul(lam[k], lam[l])), 4) * (1 if k == l else 2)
                         scc.append(lit(c))
         out.append(f"static __device__ const double WAE_{tag}_TET_STIFFCC[{n * n * 100}] = {{{', '.join(scc)}}};\n")
+        out.append(star_section(order, tag, phi, dphi))
         # triangles
         phit = basis(order, 3)
         nt = len(phit)

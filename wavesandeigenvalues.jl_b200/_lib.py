@@ -87,7 +87,7 @@ SIGNATURES = {
     "wae_sorted_unique_simplices": (_i32, [_i64, _i32, _pi64, _pi64, _pi64, _pi64]),  # host-only: no context argument
 }
 # host-only diagnostics (no context, no GPU): used by the CPU tests, never by the product path
-HOST_DIAGNOSTICS = ("wae_lu_symbolic_stats", "wae_pair_program_check", "wae_shape_sens_check")
+HOST_DIAGNOSTICS = ("wae_lu_symbolic_stats", "wae_pair_program_check", "wae_star_program_check", "wae_shape_sens_check")
 SENS_MASS, SENS_STIFF, SENS_BOUNDARY, SENS_FLAME = 1, 2, 3, 4
 
 

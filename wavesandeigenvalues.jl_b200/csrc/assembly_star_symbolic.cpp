@@ -1,0 +1,419 @@
+// Host-side symbolic phase of the third-generation assembly: the STAR PROGRAM.
+//
+// Replaces, like the pair program before it, the triplet growth + SparseArrays.sparse() duplicate summation of the reference
+// (src/Helmholtz.jl:405-445,515; src/FEM/FEM.jl:22-43,704-738,1745-1874) for the symmetric tetrahedral operators M and K.
+//
+// Idea.  Every nonzero (p, q) of M and K belongs to the sub-simplex sigma spanned by the mesh vertices of its two DOFs: a vertex,
+// an edge, a face or the tetrahedron itself (P1: a vertex or an edge).  Its sources are exactly the elements of the star of sigma,
+// and -- because the Lagrange bases are invariant under vertex permutations -- the element entry K_e[p, q] is the same linear
+// combination of the element's gram entries  g_xy = -c^2 |det| grad(l_x).grad(l_y)  (x, y vertices of sigma) in every element of the
+// star, and M_e[p, q] = m_role |det|.  So instead of moving 100 element entries per P2 tetrahedron through shared memory
+// (generation 2), the kernel sums g_xy and |det| ONCE per sub-simplex over its star, in registers, and forms all nonzeros of the
+// sub-simplex ("roles": 1 per vertex, 4 per edge, 6 per face, 3 per tetrahedron, each written to (p, q) and (q, p)) from those sums.
+// Per P2 tetrahedron of a Kuhn mesh that is 15 star sources instead of 74 slot sources, and one 8-byte record entry per role.
+//
+//  * elements are ranked on a Morton curve, a DOF is owned by its incident element of lowest rank, DOFs in owner order are cut
+//    into patches (as in generation 2).  A patch owns the COLUMNS of its DOFs, stages every element touching one of them
+//    (geometry pass: gram matrix + |det| per staged element in shared memory) and runs every sub-simplex that has at least one
+//    nonzero in an owned column; all elements of such a star are staged, because they all contain the owned DOF.
+//  * a source word (16 bits) is (staged element << 2 n) | the n local vertex numbers of the sub-simplex in canonical order (vertices
+//    sorted by mesh number, so every element of the star agrees on the frame of the roles); a tetrahedron is its own star and uses
+//    the element's local frame (word = staged element).  Patches stage fewer than 1024 (P2) / 4096 (P1) elements.
+//  * the sub-simplices of a patch are sorted by type and source count and cut into groups of 32 (one per lane); source k of lane l
+//    is word  group_base + 32 k + l  (coalesced).  The records of a group are stored entry-major: row 0 holds the 32 sums of |det|,
+//    row 1 + j the 32 values of role j (conflict-free 8-byte stores).
+//  * the store pass walks the owned columns in DOF order, 32 consecutive nonzeros per warp step; 2 bytes per nonzero name the
+//    group (7 bits), the lane (5 bits) and the role (4 bits); codes are stored back to back, a chunk header holds the first
+//    nonzero, the length and the offset of its codes.  Every nonzero is written exactly once, in a fixed summation order.
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "wae_internal.h"
+
+#include "host_parallel.h"
+
+namespace {
+struct Src {
+  uint64_t a, b;  // canonical vertex numbers: a = v0 << 32 | v1, b = v2 << 32 | v3 (unused = 0xFFFFFFFF)
+  int32_t type;   // number of vertices - 1
+  uint32_t word;
+};
+struct Ent {
+  int32_t type, first, cnt, slot;  // slot = group << 5 | lane
+};
+struct PatchOut {
+  std::vector<int32_t> tets;
+  std::vector<uint16_t> lvtx;
+  std::vector<uint32_t> gv;
+  std::vector<uint32_t> grp;   // two words per group
+  std::vector<uint8_t> cnt;    // 32 per group
+  std::vector<uint16_t> src;   // group-major source words
+  std::vector<uint32_t> chunk; // pairs: first global nonzero, length | code offset << 6
+  std::vector<uint16_t> code;  // one per owned nonzero, in chunk order
+  int rows = 0;  // record rows (32 doubles each)
+  int64_t entities = 0, sources = 0;
+  int bad = 0;
+};
+const int EIDX[4][4] = {{-1, 0, 1, 2}, {0, -1, 3, 4}, {1, 3, -1, 5}, {2, 4, 5, -1}};  // local edge number of two local vertices
+}  // namespace
+
+// a source word has 16 bits: staged element << 2 n | n local vertex numbers (n <= 3)
+int wae_star_max_staged(int nloc) { return nloc == 4 ? 4095 : 1023; }
+
+// rows of a group's record block: the sums of |det| + one row per role of the simplex type
+int wae_star_record_rows(int nloc, int type) {
+  if (nloc == 4) return 2;                                    // P1: [W, K0]
+  return type == 0 ? 2 : type == 1 ? 5 : type == 2 ? 7 : 4;   // P2: vertex [W,K0], edge [W,K0..K3], face [W,K0..K5], tet [W,K0..K2]
+}
+
+static void build_patch(const uint32_t* conn, int nloc, const Pattern& P, const OwnerOrder& OO, int32_t lo, int32_t hi, PatchOut& O) {
+  const std::vector<int64_t>& nptr = OO.nptr;
+  const std::vector<int32_t>& nadj = OO.nadj;
+  const std::vector<int32_t>& rank = OO.rank;
+  const std::vector<int32_t>& order = OO.order;
+  const std::vector<int32_t>& pos = OO.pos;
+  const bool p2 = nloc == 10;
+  auto owned = [&](uint32_t dof) { const int32_t o = pos[dof]; return o >= lo && o < hi; };
+  // staged elements: everything touching an owned DOF, in Morton order
+  std::vector<std::pair<int32_t, int32_t>> st;
+  for (int32_t q = lo; q < hi; q++) {
+    const int32_t j = order[q];
+    for (int64_t r = nptr[j]; r < nptr[j + 1]; r++) st.emplace_back(rank[nadj[r]], nadj[r]);
+  }
+  std::sort(st.begin(), st.end());
+  st.erase(std::unique(st.begin(), st.end()), st.end());
+  const int nt = (int)st.size();
+  O.tets.resize(nt);
+  O.lvtx.resize((size_t)nt * 4);
+  O.gv.clear();
+  for (int t = 0; t < nt; t++) {
+    const uint32_t* d = conn + (size_t)P.elems[st[t].second] * nloc;
+    for (int a = 0; a < 4; a++) O.gv.push_back(d[a]);
+  }
+  std::sort(O.gv.begin(), O.gv.end());
+  O.gv.erase(std::unique(O.gv.begin(), O.gv.end()), O.gv.end());
+  if (O.gv.size() >= 0xFFFF || nt > wae_star_max_staged(nloc)) O.bad |= 1;
+  // sources of every sub-simplex with a nonzero in an owned column
+  std::vector<Src> src;
+  src.reserve((size_t)nt * 15);
+  for (int t = 0; t < nt; t++) {
+    const int32_t e = st[t].second;
+    O.tets[t] = e;
+    const uint32_t* d = conn + (size_t)P.elems[e] * nloc;
+    for (int a = 0; a < 4; a++) O.lvtx[(size_t)t * 4 + a] = (uint16_t)(std::lower_bound(O.gv.begin(), O.gv.end(), d[a]) - O.gv.begin());
+    bool ow[10];
+    for (int a = 0; a < nloc; a++) ow[a] = owned(d[a]);
+    for (int m = 1; m < 16; m++) {
+      int lv[4], n = 0;
+      for (int a = 0; a < 4; a++)
+        if (m >> a & 1) lv[n++] = a;
+      if (!p2 && n > 2) continue;
+      bool need = false;
+      if (n < 4)
+        for (int i = 0; i < n; i++) need |= ow[lv[i]];
+      if (p2)
+        for (int i = 0; i < n; i++)
+          for (int j = i + 1; j < n; j++) need |= ow[4 + EIDX[lv[i]][lv[j]]];
+      if (!need) continue;
+      // canonical frame: vertices by mesh number (a tetrahedron has one source: the element's own frame)
+      uint32_t v[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};
+      uint32_t w = (uint32_t)t;
+      if (n < 4) {
+        for (int i = 1; i < n; i++)
+          for (int j = i; j > 0 && d[lv[j]] < d[lv[j - 1]]; j--) std::swap(lv[j], lv[j - 1]);
+        w <<= 2 * n;
+        for (int i = 0; i < n; i++) w |= (uint32_t)lv[i] << (2 * i);
+      }
+      for (int i = 0; i < n; i++) v[i] = d[lv[i]];
+      if (n == 4) std::sort(v, v + 4);  // key only
+      src.push_back(Src{((uint64_t)v[0] << 32) | v[1], ((uint64_t)v[2] << 32) | v[3], n - 1, w});
+    }
+  }
+  O.sources = (int64_t)src.size();
+  // generated in ascending staged element: a stable sort by (type, vertices) keeps the summation order = Morton order
+  std::stable_sort(src.begin(), src.end(), [](const Src& x, const Src& y) {
+    if (x.type != y.type) return x.type < y.type;
+    if (x.a != y.a) return x.a < y.a;
+    return x.b < y.b;
+  });
+  std::vector<Ent> ent;
+  for (size_t i = 0; i < src.size();) {
+    size_t j = i;
+    while (j < src.size() && src[j].type == src[i].type && src[j].a == src[i].a && src[j].b == src[i].b) j++;
+    if (j - i > 255) O.bad |= 2;
+    ent.push_back(Ent{src[i].type, (int32_t)i, (int32_t)(j - i), -1});
+    i = j;
+  }
+  O.entities = (int64_t)ent.size();
+  std::vector<int32_t> by(ent.size());
+  for (size_t i = 0; i < ent.size(); i++) by[i] = (int32_t)i;
+  std::stable_sort(by.begin(), by.end(), [&](int32_t x, int32_t y) {
+    if (ent[x].type != ent[y].type) return ent[x].type < ent[y].type;
+    return ent[x].cnt > ent[y].cnt;
+  });
+  // groups of 32 sub-simplices of one type
+  O.grp.clear();
+  O.cnt.clear();
+  O.src.clear();
+  int rows = 0;
+  for (size_t i = 0; i < by.size();) {
+    const int type = ent[by[i]].type;
+    size_t j = i;
+    while (j < by.size() && j < i + 32 && ent[by[j]].type == type) j++;
+    const int niter = ent[by[i]].cnt;
+    const size_t sb = O.src.size();
+    const int g = (int)O.grp.size() / 2;
+    O.src.resize(sb + (size_t)32 * niter, (uint16_t)0);
+    O.cnt.resize(O.cnt.size() + 32, 0);
+    O.grp.push_back((uint32_t)sb);
+    O.grp.push_back((uint32_t)rows | ((uint32_t)type << 16) | ((uint32_t)niter << 24));
+    for (size_t l = 0; i + l < j; l++) {
+      Ent& E = ent[by[i + l]];
+      E.slot = (g << 5) | (int)l;
+      O.cnt[O.cnt.size() - 32 + l] = (uint8_t)E.cnt;
+      for (int k = 0; k < E.cnt; k++) {
+        if (src[E.first + k].word > 0xFFFFu) O.bad |= 1;
+        O.src[sb + (size_t)32 * k + l] = (uint16_t)src[E.first + k].word;
+      }
+    }
+    rows += wae_star_record_rows(nloc, type);
+    i = j;
+  }
+  O.rows = rows;
+  if (O.grp.size() / 2 > 128 || rows >= 0xFFFF) O.bad |= 8;  // 7 bits of a code word name the group
+  // store program: owned columns by DOF number
+  std::vector<int32_t> cols(hi - lo);
+  for (int32_t q = lo; q < hi; q++) cols[q - lo] = order[q];
+  std::sort(cols.begin(), cols.end());
+  std::vector<int64_t> coloff(cols.size() + 1, 0);
+  for (size_t c = 0; c < cols.size(); c++) coloff[c + 1] = coloff[c] + (P.colptr[cols[c] + 1] - P.colptr[cols[c]]);
+  std::vector<uint16_t> flat((size_t)coloff.back(), 0xFFFF);
+  auto put = [&](uint32_t prow, uint32_t qcol, int slot_, int role) {
+    if (!owned(qcol)) return;
+    const size_t c = std::lower_bound(cols.begin(), cols.end(), (int32_t)qcol) - cols.begin();
+    const int32_t* b = P.rowval.data() + P.colptr[qcol];
+    const int32_t* e = P.rowval.data() + P.colptr[qcol + 1];
+    const int32_t* it = std::lower_bound(b, e, (int32_t)prow);
+    if (it == e || *it != (int32_t)prow) { O.bad |= 16; return; }
+    uint16_t& f = flat[(size_t)coloff[c] + (it - b)];
+    if (f != 0xFFFF) O.bad |= 32;
+    f = (uint16_t)((slot_ << 4) | role);
+  };
+  auto put2 = [&](uint32_t p_, uint32_t q_, int slot_, int role) {
+    put(p_, q_, slot_, role);
+    if (p_ != q_) put(q_, p_, slot_, role);
+  };
+  for (const Ent& E : ent) {
+    const Src& s0 = src[E.first];
+    const int n = E.type + 1;
+    const int t = (int)(n < 4 ? s0.word >> (2 * n) : s0.word);
+    const uint32_t* d = conn + (size_t)P.elems[st[t].second] * nloc;
+    int l[4] = {0, 1, 2, 3};
+    if (n < 4)
+      for (int i = 0; i < n; i++) l[i] = (s0.word >> (2 * i)) & 3;
+    const uint32_t va = d[l[0]];
+    if (E.type == 0) {
+      put2(va, va, E.slot, 0);
+    } else if (E.type == 1) {
+      const uint32_t vb = d[l[1]];
+      put2(va, vb, E.slot, 1);
+      if (p2) {
+        const uint32_t eab = d[4 + EIDX[l[0]][l[1]]];
+        put2(va, eab, E.slot, 2);
+        put2(vb, eab, E.slot, 3);
+        put2(eab, eab, E.slot, 4);
+      }
+    } else if (E.type == 2) {
+      const uint32_t vb = d[l[1]], vc = d[l[2]];
+      const uint32_t eab = d[4 + EIDX[l[0]][l[1]]], eac = d[4 + EIDX[l[0]][l[2]]], ebc = d[4 + EIDX[l[1]][l[2]]];
+      put2(vc, eab, E.slot, 5);
+      put2(vb, eac, E.slot, 6);
+      put2(va, ebc, E.slot, 7);
+      put2(eab, eac, E.slot, 8);
+      put2(eab, ebc, E.slot, 9);
+      put2(eac, ebc, E.slot, 10);
+    } else {
+      const uint32_t eab = d[4 + EIDX[l[0]][l[1]]], eac = d[4 + EIDX[l[0]][l[2]]], ead = d[4 + EIDX[l[0]][l[3]]];
+      const uint32_t ebc = d[4 + EIDX[l[1]][l[2]]], ebd = d[4 + EIDX[l[1]][l[3]]], ecd = d[4 + EIDX[l[2]][l[3]]];
+      put2(eab, ecd, E.slot, 11);
+      put2(eac, ebd, E.slot, 12);
+      put2(ead, ebc, E.slot, 13);
+    }
+  }
+  O.chunk.clear();
+  O.code.clear();
+  for (size_t c = 0; c < cols.size(); c++) {
+    const int32_t j = cols[c];
+    for (int64_t z = P.colptr[j]; z < P.colptr[j + 1]; z++) {
+      const uint16_t f = flat[(size_t)coloff[c] + (z - P.colptr[j])];
+      if (f == 0xFFFF) O.bad |= 64;
+      const size_t nc = O.chunk.size();
+      if (nc && O.chunk[nc - 2] + (O.chunk[nc - 1] & 63u) == (uint32_t)z && (z & 31) != 0)
+        O.chunk[nc - 1]++;
+      else {
+        O.chunk.push_back((uint32_t)z);
+        O.chunk.push_back(1u | ((uint32_t)O.code.size() << 6));
+      }
+      O.code.push_back(f);
+    }
+  }
+}
+
+static inline int64_t pad16(int64_t x) { return (x + 15) & ~(int64_t)15; }
+
+// shared memory one CTA needs for a patch: gram + |det| of the staged elements (17 doubles), the records, the staged source words
+// and the patch's vertex coordinates
+static int64_t patch_smem(int nloc, const PatchOut& O) {
+  (void)nloc;
+  return pad16((int64_t)O.tets.size() * 17 * 8) + (int64_t)O.rows * 256 + pad16((int64_t)O.src.size() * 2) + pad16((int64_t)O.gv.size() * 24) +
+         pad16((int64_t)(O.grp.size() / 2) * 4);
+}
+
+void wae_build_star(const double* xyz, const uint32_t* conn, int nloc, const Pattern& P, int64_t smem_budget, StarHost& G) {
+  const bool timing = getenv("WAE_SYMB_TIMING") != nullptr;
+  auto t0 = std::chrono::steady_clock::now();
+  auto tick = [&](const char* what) {
+    auto n = std::chrono::steady_clock::now();
+    if (timing) fprintf(stderr, "[wae symbolic] %-34s %8.3f s\n", what, std::chrono::duration<double>(n - t0).count());
+    t0 = n;
+  };
+  OwnerOrder OO;
+  wae_build_owner_order(xyz, conn, nloc, P, OO);
+  const int64_t ne = (int64_t)P.elems.size(), npos = (int64_t)OO.order.size();
+  if (OO.max_inc > 255) WAE_THROW(WAE_E_INVALID, "a DOF is shared by %d elements; the star program holds at most 255 sources per star", OO.max_inc);
+  // cut by the number of staged elements (exact, with a stamp per element); the shared memory a patch needs is very nearly
+  // proportional to it.  The factor is calibrated on a sample of patches, the cut repeated, and shrunk if a patch still overflows.
+  std::vector<int64_t> cut;
+  std::vector<int32_t> stamp(ne);
+  auto do_cut = [&](int64_t cap_nt) {
+    cap_nt = std::min<int64_t>(cap_nt, wae_star_max_staged(nloc));
+    cut.assign(1, 0);
+    std::fill(stamp.begin(), stamp.end(), -1);
+    int64_t staged = 0;
+    int32_t cur = 0;
+    for (int64_t q = 0; q < npos; q++) {
+      const int32_t j = OO.order[q];
+      int64_t fresh = 0;
+      for (int64_t r = OO.nptr[j]; r < OO.nptr[j + 1]; r++) fresh += stamp[OO.nadj[r]] != cur;
+      if (staged + fresh > cap_nt && staged > 0) {
+        cut.push_back(q);
+        cur++;
+        staged = 0;
+        fresh = OO.nptr[j + 1] - OO.nptr[j];
+      }
+      for (int64_t r = OO.nptr[j]; r < OO.nptr[j + 1]; r++) stamp[OO.nadj[r]] = cur;
+      staged += fresh;
+    }
+    cut.push_back(npos);
+  };
+  const double guess = nloc == 4 ? 220.0 : 420.0;  // bytes of shared memory per staged element, first guess
+  int64_t cap_nt = std::max<int64_t>(2 * OO.max_inc, (int64_t)(smem_budget / guess));
+  do_cut(cap_nt);
+  tick("star: first cut");
+  {
+    const int64_t np = (int64_t)cut.size() - 1, ns = std::min<int64_t>(np, 24);
+    double per = 0;
+    std::vector<double> pers(ns, 0.0);
+    parallel_for(ns, [&](int64_t a, int64_t b) {
+      for (int64_t i = a; i < b; i++) {
+        const int64_t p = i * np / ns;
+        PatchOut O;
+        build_patch(conn, nloc, P, OO, (int32_t)cut[p], (int32_t)cut[p + 1], O);
+        pers[i] = (double)patch_smem(nloc, O) / std::max<size_t>(1, O.tets.size());
+      }
+    }, 2);
+    for (double x : pers) per = std::max(per, x);
+    cap_nt = std::max<int64_t>(2 * OO.max_inc, (int64_t)(0.96 * smem_budget / std::max(per, 1.0)));
+  }
+  tick("star: calibration");
+  std::vector<PatchOut> po;
+  int64_t npatch = 0;
+  for (int attempt = 0;; attempt++) {
+    do_cut(cap_nt);
+    npatch = (int64_t)cut.size() - 1;
+    po.clear();
+    po.resize(npatch);
+    parallel_for(npatch, [&](int64_t a, int64_t b) {
+      for (int64_t p = a; p < b; p++) build_patch(conn, nloc, P, OO, (int32_t)cut[p], (int32_t)cut[p + 1], po[p]);
+    }, 16);
+    int bad = 0;
+    int64_t worst = 0;
+    int worst_ng = 0;
+    for (auto& O : po) {
+      bad |= O.bad & ~8;
+      worst = std::max(worst, patch_smem(nloc, O));
+      worst_ng = std::max(worst_ng, (int)O.grp.size() / 2);
+    }
+    if (bad) WAE_THROW(WAE_E_INVALID, "star program: inconsistent program (flags %d)", bad);
+    if (worst <= smem_budget && worst_ng <= 128) break;
+    if (attempt >= 6 || cap_nt <= 2 * OO.max_inc) WAE_THROW(WAE_E_INVALID, "star program does not fit %lld bytes of shared memory", (long long)smem_budget);
+    const double f = std::min(0.9, std::min((double)smem_budget / (double)worst, 128.0 / (double)std::max(worst_ng, 1)) * 0.97);
+    cap_nt = std::max<int64_t>(2 * OO.max_inc, (int64_t)(cap_nt * f));
+  }
+  tick("star: per-patch programs");
+  // ---- pack --------------------------------------------------------------------------------------------------------------
+  //   blob = [ lvtx: nt x 4 u16 | tets: nt i32 | grp: ng x (u32, u32) | cnt: ng x 32 u8 | chunk: nc x (u32 first, u32 length | code offset << 6) ]
+  G = StarHost();
+  G.nloc = nloc;
+  G.n_patch = (int)npatch;
+  G.desc.assign((size_t)npatch * 8, 0);
+  int64_t blob_total = 0, pv_total = 0, src_total = 0, chunk_total = 0, code_total = 0;
+  for (int64_t p = 0; p < npatch; p++) {
+    PatchOut& O = po[p];
+    if (O.gv.size() & 1) O.gv.push_back(O.gv.back());
+    while (O.src.size() & 7) O.src.push_back((uint16_t)0);  // 16-byte pieces for the asynchronous copies
+    while (O.code.size() & 7) O.code.push_back((uint16_t)0);
+    const int64_t nt = (int64_t)O.tets.size(), ng = (int64_t)O.grp.size() / 2, nc = (int64_t)O.chunk.size() / 2, nv = (int64_t)O.gv.size();
+    const int64_t o_tets = pad16(8 * nt), o_grp = o_tets + pad16(4 * nt), o_cnt = o_grp + pad16(8 * ng), o_chunk = o_cnt + 32 * ng;
+    const int64_t bytes = o_chunk + pad16(8 * nc);
+    int64_t* D = &G.desc[(size_t)p * 8];
+    D[0] = blob_total;
+    D[1] = pv_total * 3;
+    D[2] = src_total;
+    D[3] = code_total;
+    int32_t* I = reinterpret_cast<int32_t*>(D + 4);
+    I[0] = (int32_t)nt; I[1] = (int32_t)nv; I[2] = (int32_t)ng; I[3] = (int32_t)nc;
+    I[4] = (int32_t)O.src.size(); I[5] = (int32_t)O.code.size(); I[6] = (int32_t)o_grp; I[7] = (int32_t)o_cnt;
+    blob_total += bytes;
+    pv_total += nv;
+    src_total += (int64_t)O.src.size();
+    chunk_total += nc;
+    code_total += (int64_t)O.code.size();
+    G.max_nt = std::max<int>(G.max_nt, (int)nt);
+    G.max_nv = std::max<int>(G.max_nv, (int)nv);
+    G.max_rows = std::max(G.max_rows, O.rows);
+    G.max_ng = std::max<int>(G.max_ng, (int)ng);
+    G.max_src = std::max<int>(G.max_src, (int)O.src.size());
+    G.max_smem = std::max(G.max_smem, patch_smem(nloc, O));
+    G.n_staged += nt;
+    G.n_entities += O.entities;
+    G.n_sources += O.sources;
+  }
+  G.n_chunks = chunk_total;
+  G.blob.resize((size_t)blob_total);
+  G.gvtx.resize(pv_total);
+  G.src.resize((size_t)src_total);
+  G.code.resize((size_t)code_total);
+  parallel_for(npatch, [&](int64_t pa, int64_t pb) {
+    for (int64_t p = pa; p < pb; p++) {
+      PatchOut& O = po[p];
+      const int64_t* D = &G.desc[(size_t)p * 8];
+      const int32_t* I = reinterpret_cast<const int32_t*>(D + 4);
+      uint8_t* B = G.blob.data() + D[0];
+      std::memcpy(B, O.lvtx.data(), O.lvtx.size() * 2);
+      std::memcpy(B + pad16(8 * (int64_t)I[0]), O.tets.data(), O.tets.size() * 4);
+      std::memcpy(B + I[6], O.grp.data(), O.grp.size() * 4);
+      std::memcpy(B + I[7], O.cnt.data(), O.cnt.size());
+      std::memcpy(B + I[7] + 32 * (int64_t)I[2], O.chunk.data(), O.chunk.size() * 4);
+      std::copy(O.gv.begin(), O.gv.end(), G.gvtx.begin() + D[1] / 3);
+      std::copy(O.src.begin(), O.src.end(), G.src.begin() + D[2]);
+      std::copy(O.code.begin(), O.code.end(), G.code.begin() + (size_t)D[3]);
+      O = PatchOut();
+    }
+  }, 16);
+  tick("star: pack");
+}

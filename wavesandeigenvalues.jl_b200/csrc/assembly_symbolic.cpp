@@ -151,17 +151,19 @@ static inline uint64_t spread21(uint64_t v) {  // interleave helper: 21 bits -> 
   return v;
 }
 
-void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const Pattern& P, int slot_cap, GatherHost& G) {
+// Morton rank of every element, DOF owner (incident element of lowest rank) and the owner order of the DOFs: shared by the pair
+// program (generation 2) and the star program (generation 3, assembly_star_symbolic.cpp).
+void wae_build_owner_order(const double* xyz, const uint32_t* conn, int nloc, const Pattern& P, OwnerOrder& O) {
   const int64_t ne = (int64_t)P.elems.size();
   const int64_t dim = P.dim;
-  const int nsym = nloc * (nloc + 1) / 2;
   PhaseClock clk;
-  std::vector<int64_t> nptr;
-  std::vector<int32_t> nadj;
+  std::vector<int64_t>& nptr = O.nptr;
+  std::vector<int32_t>& nadj = O.nadj;
   node_to_elem(conn, nloc, P.elems, dim, nptr, nadj);
   clk.tick("node -> element adjacency");
   // Morton rank of every element (centroid on a 2^21 grid over the bounding box)
-  std::vector<int32_t> rank(ne);
+  std::vector<int32_t>& rank = O.rank;
+  rank.resize(ne);
   {
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
     std::vector<double> cen(3 * ne);
@@ -191,8 +193,10 @@ void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const P
   }
   clk.tick("Morton ranks");
   // owner of a DOF = its incident element of lowest Morton rank; position = index in owner order
-  std::vector<int32_t> order;      // position -> DOF
-  std::vector<int32_t> pos(dim, -1);  // DOF -> position (-1: DOF not touched by the pattern's elements)
+  std::vector<int32_t>& order = O.order;  // position -> DOF
+  std::vector<int32_t>& pos = O.pos;      // DOF -> position (-1: DOF not touched by the pattern's elements)
+  order.clear();
+  pos.assign(dim, -1);
   int max_inc = 1;
   {
     std::vector<std::pair<int32_t, int32_t>> key;
@@ -211,9 +215,25 @@ void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const P
       order.push_back(k.second);
     }
   }
+  O.max_inc = max_inc;
+  clk.tick("DOF owner order");
+}
+
+void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const Pattern& P, int slot_cap, GatherHost& G) {
+  const int64_t ne = (int64_t)P.elems.size();
+  (void)ne;
+  const int nsym = nloc * (nloc + 1) / 2;
+  PhaseClock clk;
+  OwnerOrder OO;
+  wae_build_owner_order(xyz, conn, nloc, P, OO);
+  const std::vector<int64_t>& nptr = OO.nptr;
+  const std::vector<int32_t>& nadj = OO.nadj;
+  const std::vector<int32_t>& rank = OO.rank;
+  const std::vector<int32_t>& order = OO.order;
+  const std::vector<int32_t>& pos = OO.pos;
+  const int max_inc = OO.max_inc;
   if (max_inc > 255) WAE_THROW(WAE_E_INVALID, "a DOF is shared by %d elements; the pair program holds at most 255 sources per entry", max_inc);
   const int64_t npos = (int64_t)order.size();
-  clk.tick("DOF owner order");
   // ---- cut the positions into patches by their exact number of sources --------------------------------------------------
   // A patch [lo, hi) owns the columns of its positions.  Its sources are the (element, local pair {a,b}) with at least one of the
   // two DOFs owned; a pair with BOTH DOFs owned is one source feeding nz(i,j) and nz(j,i).  Adding position q to the patch

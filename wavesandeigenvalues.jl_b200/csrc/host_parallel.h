@@ -6,10 +6,11 @@
 #include <vector>
 
 namespace {
+// min_parallel: below this many items the loop runs on the calling thread (cheap bodies); loops over patches pass a small value
 template <typename F>
-void parallel_for(int64_t n, F f) {
+void parallel_for(int64_t n, F f, int64_t min_parallel = 4096) {
   unsigned nt = std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
-  if (n < 4096) nt = 1;
+  if (n < min_parallel) nt = 1;
   std::vector<std::thread> th;
   int64_t chunk = (n + nt - 1) / nt;
   for (unsigned t = 0; t < nt; t++) {

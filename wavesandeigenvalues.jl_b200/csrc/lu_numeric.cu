@@ -854,7 +854,7 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
   const int maxd = (int)Y.levels.size() - 1;
   int nbo_blocks = 4;  // outer block = 4 * NB = 128 columns
   if (const char* env = getenv("WAE_LU_NBO")) nbo_blocks = std::max(1, atoi(env) / NB);
-  const bool gemm_ring = getenv("WAE_LU_GEMM") && atoi(getenv("WAE_LU_GEMM")) == 2;
+  const bool gemm_ring = !(getenv("WAE_LU_GEMM") && atoi(getenv("WAE_LU_GEMM")) == 1);  // default: cp.async ring (2); 1 = single-buffered tile
   if (gemm_ring) {  // 99 KB of dynamic shared memory per CTA, two CTAs per SM
     CUDA_CHECK(cudaFuncSetAttribute(lu_gemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GP_SMEM));
     if (cudaFuncSetAttribute(lu_gemm_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
@@ -866,7 +866,7 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
     else
       lu_gemm_kernel<0><<<g, 256, 0, st>>>(D, lst, mode, k0, kw, c0, cap, upd_, flag);
   };
-  const int upd_flag = (sym ? 1 : 0) | ((getenv("WAE_LU_SKIP_UPPER") && atoi(getenv("WAE_LU_SKIP_UPPER"))) ? 2 : 0);  // pivot-block updates only
+  const int upd_flag = (sym ? 1 : 0) | ((getenv("WAE_LU_SKIP_UPPER") && !atoi(getenv("WAE_LU_SKIP_UPPER"))) ? 0 : 2);  // pivot-block updates only; default: skip
   for (int d = maxd; d >= 0; d--) {
     const std::vector<int32_t>& L = Y.levels[d];
     const int nl = (int)L.size();

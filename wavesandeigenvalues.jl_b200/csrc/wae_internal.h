@@ -90,6 +90,21 @@ struct Pattern {
     uint64_t xyz_version = 0;             // h->xyz_version the pxyz copy was gathered from
     bool built = false;
   } gather;
+  // star program (assembly generation 3): built lazily, see assembly_star_symbolic.cpp
+  struct Star {
+    int n_patch = 0, max_nt = 0, max_nv = 0, max_rows = 0, max_ng = 0, max_src = 0;
+    int64_t max_smem = 0;
+    DevBuf<int64_t> d_desc;               // 64-byte patch descriptors
+    DevBuf<uint8_t> d_blob;               // per patch: local vertex numbers, element ids, group headers, lane counts, store chunks
+    DevBuf<uint32_t> d_gvtx;              // patch-local vertex -> mesh vertex
+    DevBuf<double> d_pxyz;                // vertex coordinates in patch order
+    DevBuf<uint16_t> d_src;               // star sources (16-bit words), group-major
+    DevBuf<uint16_t> d_code;              // per owned nonzero: group << 9 | lane << 4 | role
+    int64_t n_staged = 0, n_entities = 0, n_sources = 0, n_chunks = 0, n_pv = 0, program_bytes = 0;
+    uint64_t xyz_version = 0;
+    int64_t budget = 0;                   // shared-memory budget the program was cut for
+    bool built = false, failed = false;
+  } star;
   // scatter map for the atomic (first-generation) kernels: n_loc^2 slots per element
   DevBuf<int32_t> d_slotmap;
   bool slotmap_built = false;
@@ -218,6 +233,29 @@ struct GatherHost {
   int64_t n_pairs = 0, n_sources = 0, n_staged = 0;
 };
 void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const Pattern& P, int slot_cap, GatherHost& G);
+struct StarHost {
+  std::vector<int64_t> desc;     // 8 words per patch: blob offset (bytes), pxyz offset (doubles), first source word, first code,
+                                 // then 8 x int32: nt, nv, ng, nc, source words, codes, offsets of the grp / cnt sections
+  raw_vector<uint8_t> blob;
+  raw_vector<uint32_t> gvtx;
+  raw_vector<uint16_t> src, code;
+  int nloc = 0, n_patch = 0, max_nt = 0, max_nv = 0, max_rows = 0, max_ng = 0, max_src = 0;
+  int64_t max_smem = 0, n_staged = 0, n_entities = 0, n_sources = 0, n_chunks = 0;
+};
+int wae_star_record_rows(int nloc, int type);
+int wae_star_max_staged(int nloc);
+void wae_build_star(const double* xyz, const uint32_t* conn, int nloc, const Pattern& P, int64_t smem_budget, StarHost& G);
+bool wae_ensure_star(wae_ctx* h, Pattern& P);  // false: no star program for this pattern (the caller falls back to the pair program)
+// Morton rank of the elements, DOF -> incident elements, DOF owner order (shared by the pair and the star program)
+struct OwnerOrder {
+  std::vector<int64_t> nptr;   // DOF -> incident elements (positions in P.elems), CSR
+  std::vector<int32_t> nadj;
+  std::vector<int32_t> rank;   // element -> Morton rank
+  std::vector<int32_t> order;  // position -> DOF (owner order)
+  std::vector<int32_t> pos;    // DOF -> position, -1 if untouched
+  int max_inc = 1;             // largest number of elements around one DOF
+};
+void wae_build_owner_order(const double* xyz, const uint32_t* conn, int nloc, const Pattern& P, OwnerOrder& O);
 void wae_ensure_gather(wae_ctx* h, Pattern& P);
 void wae_build_bloch(const uint32_t* conn, int nloc, const std::vector<int64_t>& elems, int64_t dim_red, const int64_t* dof_new,
                      const uint8_t* dof_flag, int n_class, std::vector<Pattern>& P, std::vector<int32_t>& slotmap,
@@ -228,6 +266,7 @@ void wae_launch_assemble_atomic(wae_ctx* h, Pattern& P, int kind, const double* 
                                 double scale, double* d_out_a, double* d_out_b);
 void wae_launch_assemble_gather(wae_ctx* h, Pattern& P, const double* d_c, double* d_mass, double* d_stiff,
                                 double mass_scale);
+void wae_launch_assemble_star(wae_ctx* h, Pattern& P, const double* d_c, double* d_mass, double* d_stiff, double mass_scale);
 void wae_launch_wallsrc(wae_ctx* h, const int32_t* d_elems, int64_t n, const double* d_c, int c_per_elem, double* d_out);
 void wae_combine_device(wae_ctx* h, Family& F, const double* coeffs_host, int slot);
 void wae_spmm_device(wae_ctx* h, Family& F, int slot, int trans, int nrhs, const cplx* X, cplx* Y);

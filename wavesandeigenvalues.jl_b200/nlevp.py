@@ -761,7 +761,7 @@ def _iterate(L, z, maxiter, tol, relax, order, nev, v0, v0_adj, kind, num_order,
     mcoef = [None] * len(L.terms)
     mcoef[-1] = -1.0
     dev.combine(dev.flat(mcoef), 1)
-    paired = os.environ.get("WAE_EIGS_PAIRED", "0") == "1" and hasattr(ctx, "eigs_si_pair")
+    paired = os.environ.get("WAE_EIGS_PAIRED", "1") == "1" and hasattr(ctx, "eigs_si_pair")
     try:
         while abs(z - z0) > tol and n < maxiter:
             if output:
