@@ -185,7 +185,8 @@ int32_t wae_pair_program_check(int32_t order, int64_t n_pts, const double* xyz, 
  * and roles, chunked stores) on the host with the kernel's own arithmetic, c constant per element (n_tet values).  Returns the
  * CSC pattern (colptr: dim + 1, rowval / val_m / val_k: up to nnz_cap entries, 0-based) and stats[0..7] = nnz, patches, staged
  * elements, sub-simplices, star sources, shared memory of one CTA (bytes), program size (bytes), number of violated invariants
- * (every nonzero written exactly once, alignment of the staged pieces, bounds).                                               */
+ * (every nonzero written exactly once, alignment of the staged pieces, bounds); stats[8..11] = simulated shared-memory wavefronts of
+ * the star pass's gram gathers and their conflict-free count, the same for the store pass's record gathers (stats holds 16 doubles). */
 int32_t wae_star_program_check(int32_t order, int64_t n_pts, const double* xyz, int64_t n_tet, const uint32_t* tets, const double* c,
                                int64_t smem_budget, int64_t nnz_cap, int64_t* colptr, int32_t* rowval, double* val_m, double* val_k,
                                double* stats);

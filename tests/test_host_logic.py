@@ -222,7 +222,7 @@ def _star_program_check(mesh, order, budget, c):
     nloc = t32.shape[1]
     cap = len(t32) * nloc * nloc
     colptr, rowval = np.zeros(dim + 1, dtype=np.int64), np.zeros(cap, dtype=np.int32)
-    vm, vk, st = np.zeros(cap), np.zeros(cap), np.zeros(8)
+    vm, vk, st = np.zeros(cap), np.zeros(cap), np.zeros(16)
     cc = np.ascontiguousarray(c, dtype=np.float64)
     rc = lib.wae_star_program_check(1 if order == "lin" else 2, xyz.shape[0], xyz.ctypes.data_as(pd), len(t32), t32.ctypes.data_as(C.POINTER(C.c_uint32)),
                                     cc.ctypes.data_as(pd), budget, cap, colptr.ctypes.data_as(pi64), rowval.ctypes.data_as(C.POINTER(C.c_int32)),
@@ -230,7 +230,7 @@ def _star_program_check(mesh, order, budget, c):
     assert rc == 0
     nnz = int(st[0])
     return dict(nnz=nnz, patches=int(st[1]), staged=int(st[2]), simplices=int(st[3]), sources=int(st[4]), smem=int(st[5]), program=int(st[6]),
-                bad=int(st[7]), ntet=len(t32), colptr=colptr, rowval=rowval[:nnz], vm=vm[:nnz], vk=vk[:nnz], tets=t32, xyz=xyz, dim=dim)
+                bad=int(st[7]), wavefronts=st[8:12].copy(), ntet=len(t32), colptr=colptr, rowval=rowval[:nnz], vm=vm[:nnz], vk=vk[:nnz], tets=t32, xyz=xyz, dim=dim)
 
 
 def _oracle_mk(xyz, tets, c, order, dim):

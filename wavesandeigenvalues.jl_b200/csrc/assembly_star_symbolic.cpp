@@ -23,8 +23,9 @@
 //    is word  group_base + 32 k + l  (coalesced).  The records of a group are stored entry-major: row 0 holds the 32 sums of |det|,
 //    row 1 + j the 32 values of role j (conflict-free 8-byte stores).
 //  * the store pass walks the owned columns in DOF order, 32 consecutive nonzeros per warp step; 2 bytes per nonzero name the
-//    group (7 bits), the lane (5 bits) and the role (4 bits); codes are stored back to back, a chunk header holds the first
-//    nonzero, the length and the offset of its codes.  Every nonzero is written exactly once, in a fixed summation order.
+//    record entry of its K value (13 bits: row * 33 + lane; a patch has at most 248 record rows = 64 KB) and the distance to the row
+//    of its M value (3 bits); codes are stored back to back, a chunk header holds the first nonzero, the length and the offset of
+//    its codes.  Every nonzero is written exactly once, in a fixed summation order.
 #include <algorithm>
 #include <atomic>
 #include <chrono>
@@ -32,6 +33,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "assembly_star.h"
 #include "wae_internal.h"
 
 #include "host_parallel.h"
@@ -43,7 +45,7 @@ struct Src {
   uint32_t word;
 };
 struct Ent {
-  int32_t type, first, cnt, slot;  // slot = group << 5 | lane
+  int32_t type, first, cnt, slot;  // slot = first record row of the group * 32 + lane
 };
 struct PatchOut {
   std::vector<int32_t> tets;
@@ -63,12 +65,6 @@ const int EIDX[4][4] = {{-1, 0, 1, 2}, {0, -1, 3, 4}, {1, 3, -1, 5}, {2, 4, 5, -
 
 // a source word has 16 bits: staged element << 2 n | n local vertex numbers (n <= 3)
 int wae_star_max_staged(int nloc) { return nloc == 4 ? 4095 : 1023; }
-
-// rows of a group's record block: the sums of |det| + one row per role of the simplex type
-int wae_star_record_rows(int nloc, int type) {
-  if (nloc == 4) return 2;                                    // P1: [W, K0]
-  return type == 0 ? 2 : type == 1 ? 5 : type == 2 ? 7 : 4;   // P2: vertex [W,K0], edge [W,K0..K3], face [W,K0..K5], tet [W,K0..K2]
-}
 
 static void build_patch(const uint32_t* conn, int nloc, const Pattern& P, const OwnerOrder& OO, int32_t lo, int32_t hi, PatchOut& O) {
   const std::vector<int64_t>& nptr = OO.nptr;
@@ -151,9 +147,13 @@ static void build_patch(const uint32_t* conn, int nloc, const Pattern& P, const 
   O.entities = (int64_t)ent.size();
   std::vector<int32_t> by(ent.size());
   for (size_t i = 0; i < ent.size(); i++) by[i] = (int32_t)i;
+  // by type, then by source count (lanes of a group run the same trip count), then by the first source element: neighbouring lanes
+  // read neighbouring gram blocks
+  auto first_elem = [&](const Ent& E) { return E.type == 3 ? src[E.first].word : src[E.first].word >> (2 * (E.type + 1)); };
   std::stable_sort(by.begin(), by.end(), [&](int32_t x, int32_t y) {
     if (ent[x].type != ent[y].type) return ent[x].type < ent[y].type;
-    return ent[x].cnt > ent[y].cnt;
+    if (ent[x].cnt != ent[y].cnt) return ent[x].cnt > ent[y].cnt;
+    return first_elem(ent[x]) < first_elem(ent[y]);
   });
   // groups of 32 sub-simplices of one type
   O.grp.clear();
@@ -162,29 +162,33 @@ static void build_patch(const uint32_t* conn, int nloc, const Pattern& P, const 
   int rows = 0;
   for (size_t i = 0; i < by.size();) {
     const int type = ent[by[i]].type;
+    const int split = type == 0 ? WAE_STAR_VSPLIT : 1, per = 32 / split;  // simplices per group
     size_t j = i;
-    while (j < by.size() && j < i + 32 && ent[by[j]].type == type) j++;
-    const int niter = ent[by[i]].cnt;
+    while (j < by.size() && j < i + per && ent[by[j]].type == type) j++;
+    const int niter = (ent[by[i]].cnt + split - 1) / split;
     const size_t sb = O.src.size();
-    const int g = (int)O.grp.size() / 2;
     O.src.resize(sb + (size_t)32 * niter, (uint16_t)0);
     O.cnt.resize(O.cnt.size() + 32, 0);
     O.grp.push_back((uint32_t)sb);
     O.grp.push_back((uint32_t)rows | ((uint32_t)type << 16) | ((uint32_t)niter << 24));
     for (size_t l = 0; i + l < j; l++) {
       Ent& E = ent[by[i + l]];
-      E.slot = (g << 5) | (int)l;
-      O.cnt[O.cnt.size() - 32 + l] = (uint8_t)E.cnt;
-      for (int k = 0; k < E.cnt; k++) {
-        if (src[E.first + k].word > 0xFFFFu) O.bad |= 1;
-        O.src[sb + (size_t)32 * k + l] = (uint16_t)src[E.first + k].word;
+      E.slot = rows * WAE_STAR_RS + (int)(l * split);
+      const int q = (E.cnt + split - 1) / split;  // sources per lane of a split star
+      for (int sl = 0; sl < split; sl++) {
+        const int k0 = sl * q, k1 = std::min(E.cnt, k0 + q), lane = (int)(l * split) + sl;
+        O.cnt[O.cnt.size() - 32 + lane] = (uint8_t)std::max(0, k1 - k0);
+        for (int k = k0; k < k1; k++) {
+          if (src[E.first + k].word > 0xFFFFu) O.bad |= 1;
+          O.src[sb + (size_t)32 * (k - k0) + lane] = (uint16_t)src[E.first + k].word;
+        }
       }
     }
-    rows += wae_star_record_rows(nloc, type);
+    rows += star_rows(nloc, type);
     i = j;
   }
   O.rows = rows;
-  if (O.grp.size() / 2 > 128 || rows >= 0xFFFF) O.bad |= 8;  // 7 bits of a code word name the group
+  if (rows * WAE_STAR_RS > 8192) O.bad |= 8;  // 13 bits of a code word name the record entry
   // store program: owned columns by DOF number
   std::vector<int32_t> cols(hi - lo);
   for (int32_t q = lo; q < hi; q++) cols[q - lo] = order[q];
@@ -201,7 +205,7 @@ static void build_patch(const uint32_t* conn, int nloc, const Pattern& P, const 
     if (it == e || *it != (int32_t)prow) { O.bad |= 16; return; }
     uint16_t& f = flat[(size_t)coloff[c] + (it - b)];
     if (f != 0xFFFF) O.bad |= 32;
-    f = (uint16_t)((slot_ << 4) | role);
+    f = (uint16_t)(((slot_ + WAE_STAR_RS * star_krow(nloc, role)) << 3) | (star_mrow(nloc, role) - star_krow(nloc, role)));
   };
   auto put2 = [&](uint32_t p_, uint32_t q_, int slot_, int role) {
     put(p_, q_, slot_, role);
@@ -261,16 +265,21 @@ static void build_patch(const uint32_t* conn, int nloc, const Pattern& P, const 
       O.code.push_back(f);
     }
   }
+  while ((O.chunk.size() / 2) & 3) {  // the store pass takes four chunks per warp step
+    O.chunk.push_back(0u);
+    O.chunk.push_back(0u);
+  }
 }
 
 static inline int64_t pad16(int64_t x) { return (x + 15) & ~(int64_t)15; }
 
-// shared memory one CTA needs for a patch: gram + |det| of the staged elements (17 doubles), the records, the staged source words
-// and the patch's vertex coordinates
+// shared memory one CTA needs for a patch: gram + |det| of the staged elements (17 doubles), the records, blob A + the patch's vertex
+// coordinates, blob B, the group table
 static int64_t patch_smem(int nloc, const PatchOut& O) {
   (void)nloc;
-  return pad16((int64_t)O.tets.size() * 17 * 8) + (int64_t)O.rows * 256 + pad16((int64_t)O.src.size() * 2) + pad16((int64_t)O.gv.size() * 24) +
-         pad16((int64_t)(O.grp.size() / 2) * 4);
+  const StarBlob L((int)O.tets.size(), (int)O.grp.size() / 2, (int)O.src.size(), (int)O.chunk.size() / 2, (int)O.code.size());
+  return pad16((int64_t)O.tets.size() * 17 * 8) + pad16((int64_t)O.rows * WAE_STAR_RS * 8) + L.bytesA + L.bytesB + pad16(((int64_t)O.gv.size() + 1) * 24) +
+         512;  // + descriptor ring, mbarriers
 }
 
 void wae_build_star(const double* xyz, const uint32_t* conn, int nloc, const Pattern& P, int64_t smem_budget, StarHost& G) {
@@ -342,76 +351,80 @@ void wae_build_star(const double* xyz, const uint32_t* conn, int nloc, const Pat
     }, 16);
     int bad = 0;
     int64_t worst = 0;
-    int worst_ng = 0;
-    for (auto& O : po) {
-      bad |= O.bad & ~8;
-      worst = std::max(worst, patch_smem(nloc, O));
-      worst_ng = std::max(worst_ng, (int)O.grp.size() / 2);
+    int worst_rows = 0;
+    {  // the kernel's buffers are sized by the largest patch of each section
+      int m_nt = 0, m_a = 0, m_b = 0, m_nv = 0;
+      for (auto& O : po) {
+        bad |= O.bad & ~8;
+        const StarBlob L((int)O.tets.size(), (int)O.grp.size() / 2, (int)O.src.size(), (int)O.chunk.size() / 2, (int)O.code.size());
+        m_nt = std::max(m_nt, (int)O.tets.size());
+        m_a = std::max(m_a, L.bytesA);
+        m_b = std::max(m_b, L.bytesB);
+        m_nv = std::max(m_nv, (int)O.gv.size() + 1);
+        worst_rows = std::max(worst_rows, O.rows);
+      }
+      worst = StarLayout(m_nt, worst_rows, m_a, m_b, m_nv).total + WAE_STAR_STATIC_SMEM;
     }
     if (bad) WAE_THROW(WAE_E_INVALID, "star program: inconsistent program (flags %d)", bad);
-    if (worst <= smem_budget && worst_ng <= 128) break;
+    if (worst <= smem_budget && worst_rows * WAE_STAR_RS <= 8192) break;
     if (attempt >= 6 || cap_nt <= 2 * OO.max_inc) WAE_THROW(WAE_E_INVALID, "star program does not fit %lld bytes of shared memory", (long long)smem_budget);
-    const double f = std::min(0.9, std::min((double)smem_budget / (double)worst, 128.0 / (double)std::max(worst_ng, 1)) * 0.97);
+    const double f = std::min(0.9, std::min((double)smem_budget / (double)worst, (8192.0 / WAE_STAR_RS) / (double)std::max(worst_rows, 1)) * 0.97);
     cap_nt = std::max<int64_t>(2 * OO.max_inc, (int64_t)(cap_nt * f));
   }
   tick("star: per-patch programs");
-  // ---- pack --------------------------------------------------------------------------------------------------------------
-  //   blob = [ lvtx: nt x 4 u16 | tets: nt i32 | grp: ng x (u32, u32) | cnt: ng x 32 u8 | chunk: nc x (u32 first, u32 length | code offset << 6) ]
+  // ---- pack: descriptor + blob A + blob B + patch vertices per patch (assembly_star.h) -----------------------------------------------
   G = StarHost();
   G.nloc = nloc;
   G.n_patch = (int)npatch;
   G.desc.assign((size_t)npatch * 8, 0);
-  int64_t blob_total = 0, pv_total = 0, src_total = 0, chunk_total = 0, code_total = 0;
+  int64_t a_total = 0, b_total = 0, pv_total = 0, chunk_total = 0;
   for (int64_t p = 0; p < npatch; p++) {
     PatchOut& O = po[p];
     if (O.gv.size() & 1) O.gv.push_back(O.gv.back());
-    while (O.src.size() & 7) O.src.push_back((uint16_t)0);  // 16-byte pieces for the asynchronous copies
-    while (O.code.size() & 7) O.code.push_back((uint16_t)0);
-    const int64_t nt = (int64_t)O.tets.size(), ng = (int64_t)O.grp.size() / 2, nc = (int64_t)O.chunk.size() / 2, nv = (int64_t)O.gv.size();
-    const int64_t o_tets = pad16(8 * nt), o_grp = o_tets + pad16(4 * nt), o_cnt = o_grp + pad16(8 * ng), o_chunk = o_cnt + 32 * ng;
-    const int64_t bytes = o_chunk + pad16(8 * nc);
-    int64_t* D = &G.desc[(size_t)p * 8];
-    D[0] = blob_total;
-    D[1] = pv_total * 3;
-    D[2] = src_total;
-    D[3] = code_total;
-    int32_t* I = reinterpret_cast<int32_t*>(D + 4);
-    I[0] = (int32_t)nt; I[1] = (int32_t)nv; I[2] = (int32_t)ng; I[3] = (int32_t)nc;
-    I[4] = (int32_t)O.src.size(); I[5] = (int32_t)O.code.size(); I[6] = (int32_t)o_grp; I[7] = (int32_t)o_cnt;
-    blob_total += bytes;
+    const int nt = (int)O.tets.size(), ng = (int)O.grp.size() / 2, nc = (int)O.chunk.size() / 2, nv = (int)O.gv.size();
+    const StarBlob L(nt, ng, (int)O.src.size(), nc, (int)O.code.size());
+    StarDesc& D = *reinterpret_cast<StarDesc*>(&G.desc[(size_t)p * 8]);
+    D.blobA = a_total;
+    D.pxyz = pv_total * 3;
+    D.blobB = b_total;
+    D.nt = nt; D.nv = nv; D.ng = ng; D.nc = nc;
+    D.nsrc = (int)O.src.size(); D.ncode = (int)O.code.size(); D.bytesA = L.bytesA; D.bytesB = L.bytesB;
+    a_total += L.bytesA;
+    b_total += L.bytesB;
     pv_total += nv;
-    src_total += (int64_t)O.src.size();
     chunk_total += nc;
-    code_total += (int64_t)O.code.size();
-    G.max_nt = std::max<int>(G.max_nt, (int)nt);
-    G.max_nv = std::max<int>(G.max_nv, (int)nv);
+    G.max_nt = std::max(G.max_nt, nt);
+    G.max_nv = std::max(G.max_nv, nv);
     G.max_rows = std::max(G.max_rows, O.rows);
-    G.max_ng = std::max<int>(G.max_ng, (int)ng);
-    G.max_src = std::max<int>(G.max_src, (int)O.src.size());
+    G.max_ng = std::max(G.max_ng, ng);
+    G.max_a = std::max(G.max_a, L.bytesA);
+    G.max_b = std::max(G.max_b, L.bytesB);
     G.max_smem = std::max(G.max_smem, patch_smem(nloc, O));
     G.n_staged += nt;
     G.n_entities += O.entities;
     G.n_sources += O.sources;
   }
   G.n_chunks = chunk_total;
-  G.blob.resize((size_t)blob_total);
+  G.blob.resize((size_t)a_total);
+  G.blobB.resize((size_t)b_total);
   G.gvtx.resize(pv_total);
-  G.src.resize((size_t)src_total);
-  G.code.resize((size_t)code_total);
   parallel_for(npatch, [&](int64_t pa, int64_t pb) {
     for (int64_t p = pa; p < pb; p++) {
       PatchOut& O = po[p];
-      const int64_t* D = &G.desc[(size_t)p * 8];
-      const int32_t* I = reinterpret_cast<const int32_t*>(D + 4);
-      uint8_t* B = G.blob.data() + D[0];
-      std::memcpy(B, O.lvtx.data(), O.lvtx.size() * 2);
-      std::memcpy(B + pad16(8 * (int64_t)I[0]), O.tets.data(), O.tets.size() * 4);
-      std::memcpy(B + I[6], O.grp.data(), O.grp.size() * 4);
-      std::memcpy(B + I[7], O.cnt.data(), O.cnt.size());
-      std::memcpy(B + I[7] + 32 * (int64_t)I[2], O.chunk.data(), O.chunk.size() * 4);
-      std::copy(O.gv.begin(), O.gv.end(), G.gvtx.begin() + D[1] / 3);
-      std::copy(O.src.begin(), O.src.end(), G.src.begin() + D[2]);
-      std::copy(O.code.begin(), O.code.end(), G.code.begin() + (size_t)D[3]);
+      const StarDesc& D = *reinterpret_cast<const StarDesc*>(&G.desc[(size_t)p * 8]);
+      const StarBlob L(D.nt, D.ng, D.nsrc, D.nc, D.ncode);
+      uint8_t* A = G.blob.data() + D.blobA;
+      std::memset(A, 0, (size_t)L.bytesA);
+      std::memcpy(A, O.lvtx.data(), O.lvtx.size() * 2);
+      std::memcpy(A + L.o_tets, O.tets.data(), O.tets.size() * 4);
+      std::memcpy(A + L.o_grp, O.grp.data(), O.grp.size() * 4);
+      std::memcpy(A + L.o_cnt, O.cnt.data(), O.cnt.size());
+      std::memcpy(A + L.o_src, O.src.data(), O.src.size() * 2);
+      uint8_t* B = G.blobB.data() + D.blobB;
+      std::memset(B, 0, (size_t)L.bytesB);
+      std::memcpy(B, O.chunk.data(), O.chunk.size() * 4);
+      std::memcpy(B + L.o_code, O.code.data(), O.code.size() * 2);
+      std::copy(O.gv.begin(), O.gv.end(), G.gvtx.begin() + D.pxyz / 3);
       O = PatchOut();
     }
   }, 16);

@@ -92,14 +92,13 @@ struct Pattern {
   } gather;
   // star program (assembly generation 3): built lazily, see assembly_star_symbolic.cpp
   struct Star {
-    int n_patch = 0, max_nt = 0, max_nv = 0, max_rows = 0, max_ng = 0, max_src = 0;
+    int n_patch = 0, max_nt = 0, max_nv = 0, max_rows = 0, max_ng = 0, max_a = 0, max_b = 0;
     int64_t max_smem = 0;
     DevBuf<int64_t> d_desc;               // 64-byte patch descriptors
-    DevBuf<uint8_t> d_blob;               // per patch: local vertex numbers, element ids, group headers, lane counts, store chunks
+    DevBuf<uint8_t> d_blob;               // blob A per patch: local vertex numbers, element ids, group headers, lane counts, star sources
+    DevBuf<uint8_t> d_blobB;              // blob B per patch: store chunks, codes (group << 9 | lane << 4 | role per owned nonzero)
     DevBuf<uint32_t> d_gvtx;              // patch-local vertex -> mesh vertex
     DevBuf<double> d_pxyz;                // vertex coordinates in patch order
-    DevBuf<uint16_t> d_src;               // star sources (16-bit words), group-major
-    DevBuf<uint16_t> d_code;              // per owned nonzero: group << 9 | lane << 4 | role
     int64_t n_staged = 0, n_entities = 0, n_sources = 0, n_chunks = 0, n_pv = 0, program_bytes = 0;
     uint64_t xyz_version = 0;
     int64_t budget = 0;                   // shared-memory budget the program was cut for
@@ -234,15 +233,12 @@ struct GatherHost {
 };
 void wae_build_gather(const double* xyz, const uint32_t* conn, int nloc, const Pattern& P, int slot_cap, GatherHost& G);
 struct StarHost {
-  std::vector<int64_t> desc;     // 8 words per patch: blob offset (bytes), pxyz offset (doubles), first source word, first code,
-                                 // then 8 x int32: nt, nv, ng, nc, source words, codes, offsets of the grp / cnt sections
-  raw_vector<uint8_t> blob;
+  std::vector<int64_t> desc;     // one StarDesc (64 bytes) per patch, see assembly_star.h
+  raw_vector<uint8_t> blob, blobB;  // blob A (geometry + star pass) and blob B (store pass) of all patches
   raw_vector<uint32_t> gvtx;
-  raw_vector<uint16_t> src, code;
-  int nloc = 0, n_patch = 0, max_nt = 0, max_nv = 0, max_rows = 0, max_ng = 0, max_src = 0;
+  int nloc = 0, n_patch = 0, max_nt = 0, max_nv = 0, max_rows = 0, max_ng = 0, max_a = 0, max_b = 0;
   int64_t max_smem = 0, n_staged = 0, n_entities = 0, n_sources = 0, n_chunks = 0;
 };
-int wae_star_record_rows(int nloc, int type);
 int wae_star_max_staged(int nloc);
 void wae_build_star(const double* xyz, const uint32_t* conn, int nloc, const Pattern& P, int64_t smem_budget, StarHost& G);
 bool wae_ensure_star(wae_ctx* h, Pattern& P);  // false: no star program for this pattern (the caller falls back to the pair program)
