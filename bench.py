@@ -14,8 +14,16 @@ With N > 1 every rank solves its own replica (tau differs per rank): householder
 ("replicas only", weak scaling).  The path that does shard -- Beyn's quadrature nodes -- is timed on every N
 as well and reported under "beyn" (strong scaling: 128 nodes in total, one NCCL all-reduce of the moments).
 
-Extra objects on the JSON line: roofline (numeric LU = DMMA ZGEMM, FP64 tensor pipe), roofline_assembly (HBM),
-assembly (Mtets/s on a larger box), beyn, cpu_baseline (the scipy/SuperLU oracle on a bounded sample), clocks.
+The `value` and `e2e` steps ALTERNATE inside one timed region (every step bracketed by its own CUDA events), so that neither
+is measured on a warmer device than the other.
+
+Objects on the JSON line: roofline (numeric LU = DMMA ZGEMM on the FP64 tensor pipe; `roofline.legs` holds the other kernels of the
+path with their own rooflines -- assembly Mtets/s + HBM fraction, triangular solves, Beyn (BASELINE.json configs[2], sharded over the
+ranks) -- and `roofline.phases_ms_per_step` the split of a step), cpu_baseline (the scipy/SuperLU oracle MEASURED on a bounded sample
+of the same tube, the GPU path timed on that very sample beside it and the two eigenvalues compared: `cpu_baseline.same_problem`; the
+phase-wise extrapolation to the full workload is a labelled side note there, never a headline), e2e, clocks.
+
+`--impl reference`: the CPU oracle alone, `value` = its MEASURED rate on the bounded sample (it never loads libwae_b200.so).
 """
 import argparse
 import json
@@ -47,6 +55,18 @@ def tube_case(W, ncube, order="quad"):
     dscrp = {"Interior": ("interior", ()), "Outlet": ("admittance", ("Y", 1e15)),
              "Flame": ("flame", (GAMMA, RHO, Q02U0, [0.025, 0.025, -0.6 * hz], [0.0, 0.0, 1.0], "n", "τ", 1.0, 0.001))}
     return mesh, c, dscrp
+
+
+def workload_config(tube, sample):
+    """The `config` object: identical in both arms (the driver compares them)."""
+    return {"workload": (f"BASELINE.json configs[1]: Rijke tube {tube[0]}x{tube[1]}x{tube[2]} Kuhn cubes, P2, interior + outlet admittance (Y=1e15) + "
+                         "n-tau flame (n=1, tau=1 ms); step = numeric re-assembly of all operators + householder(order 1) from 340*2*pi to |dw| <= 1e-9 |w| "
+                         "= one eigenpair"),
+            "tube_cubes": list(tube), "elements": "P2 tetrahedra", "arithmetic": "complex fp64",
+            "cpu_sample": (f"the CPU arm times the same step on a bounded sample of this workload: the same tube at {sample[0]}x{sample[1]}x{sample[2]} cubes "
+                           "(the full-size CPU step takes hours); the GPU arm times that sample too (cpu_baseline.same_problem)"),
+            "l2": "working set (LU factors, 21 GB) is far larger than the 126 MB L2; no flush needed",
+            "parallelism": "replicas only (householder does not shard); Beyn's quadrature nodes are sharded under roofline.legs.beyn"}
 
 
 def oracle_step(ncube):
@@ -84,7 +104,8 @@ def oracle_step(ncube):
     finally:
         ar.splu = orig
     return {"total": t2 - t0, "asm": t1 - t0, "factor": acc["factor"], "other": (t2 - t1) - acc["factor"], "n_fact": acc["n_fact"],
-            "dim": L.size(), "ntet": len(m.tetrahedra), "nit": n, "threads": max(1, round((time.process_time() - c0) / (t2 - t0)))}
+            "dim": L.size(), "ntet": len(m.tetrahedra), "nit": n, "threads": max(1, round((time.process_time() - c0) / (t2 - t0))),
+            "omega": complex(sol.params["ω"]), "flag": flag}
 
 
 def lu_cost(W, mesh):
@@ -121,8 +142,10 @@ def cpu_scaled(W, st, sample, tube):
     fs, ns, ts = lu_cost(W, tube_case(W, sample)[0])
     ff, nf, tf = lu_cost(W, tube_case(W, tube)[0])
     est = st["asm"] * tf / ts + st["factor"] * ff / fs + st["other"] * nf / ns
-    return 1.0 / est, {"sample_s": {k: st[k] for k in ("total", "asm", "factor", "other")}, "growth": {"tets": tf / ts, "factor_flops": ff / fs, "factor_nnz": nf / ns},
-                       "estimated_full_size_s": est, "sample_eigenpairs_per_s": 1.0 / st["total"]}
+    return {"what": ("SIDE NOTE, an estimate and not a measurement: the measured sample scaled phase by phase to the full workload (assembly x "
+                     "tetrahedra, factorisations x factorisation flops, rest x nnz(L+U), both counts from one nested-dissection analysis of the two "
+                     "patterns; SuperLU's own fill grows faster, so this favours the CPU)"),
+            "growth": {"tets": tf / ts, "factor_flops": ff / fs, "factor_nnz": nf / ns}, "estimated_full_size_s_per_eigenpair": est}
 
 
 T_START = time.perf_counter()
@@ -195,12 +218,14 @@ class Clocks:
 
 def ncu_traffic(key):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of a kernel, from the committed `ncu --set full` summaries
-    (profiles/r01_traffic.json: kernel/workload -> bytes, with the capture it was read from); None if not captured."""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[key]
-        return t["dram_bytes_per_launch"] / 1e9, t["source"]
-    except Exception:
-        return None, None
+    (profiles/r02_traffic.json, else r01: kernel/workload -> bytes, with the capture it was read from); None if not captured."""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            t = json.load(open(os.path.join(ROOT, "profiles", name)))[key]
+            return t["dram_bytes_per_launch"] / 1e9, t["source"]
+        except Exception:
+            continue
+    return None, None
 
 
 def fp64_peak(torch, dev):
@@ -232,25 +257,31 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--tube", default="20,20,300", help="cubes of the Rijke tube grid (config 2: 20,20,300)")
-    ap.add_argument("--beyn-box", default="32,32,64", help="cubes of the P1 tube used for the sharded Beyn leg")
+    ap.add_argument("--beyn-grid", default="32,32,236", help="cubes of the squircle cylinder of the sharded Beyn leg (config 3: 32,32,236, P2)")
+    ap.add_argument("--beyn-order", default="quad")
     ap.add_argument("--beyn-edge-nodes", type=int, default=32, help="Gauss-Legendre nodes per polygon edge (4 edges -> 128 nodes)")
     ap.add_argument("--assembly-cubes", type=int, default=64, help="n for the n^3-cube P2 assembly-only leg (0 = skip)")
-    ap.add_argument("--cpu-sample", default="4,4,60")
-    ap.add_argument("--ref-sample", default="4,4,60")
+    ap.add_argument("--cpu-sample", default="4,4,60", help="cubes of the bounded sample both CPU legs (and the GPU same-problem leg) run")
     ap.add_argument("--skip-extras", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     tube = tuple(int(x) for x in args.tube.split(","))
-    workload = (f"Rijke tube {tube[0]}x{tube[1]}x{tube[2]} Kuhn cubes, P2, interior+outlet admittance+n-tau flame; "
-                "step = GPU re-assembly + householder(order 1) to |dw|<=1e-9|w|")
+    sample = tuple(int(x) for x in args.cpu_sample.split(","))
+    config = workload_config(tube, sample)
+    metric = "NLEVP eigenpairs/s (householder, config 2)"
 
-    # ------------------------------------------------------------------ reference arm: the CPU oracle
+    def cpu_sample_text(st):
+        return (f"reference cannot run here (pure Julia, no julia binary): CPU restatement (numpy + scipy SuperLU/ARPACK, NOT Julia/UMFPACK) MEASURED "
+                f"on a bounded sample of the workload: tube {sample[0]}x{sample[1]}x{sample[2]} cubes, {st['ntet']} tets, {st['dim']} P2 DOFs, assembly + "
+                f"householder to convergence = one eigenpair per step ({st['total']:.2f} s, {st['n_fact']} factorisations, {st['nit']} Newton iterations); "
+                f"value = measured eigenpairs/s ON THAT SAMPLE; host has {os.cpu_count()} cores, SuperLU is serial, OpenBLAS threads the dense kernels")
+
+    # ------------------------------------------------------------------ reference arm: the CPU oracle, measured (never loads libwae_b200.so)
     if args.impl == "reference":
         if rank != 0:
             return
-        sample = tuple(int(x) for x in args.ref_sample.split(","))
         for _ in range(args.warmup):
             oracle_step(sample)
         t0 = time.perf_counter()
@@ -261,19 +292,14 @@ def main():
         dt = time.perf_counter() - t0
         for k in ("total", "asm", "factor", "other"):
             acc[k] /= args.steps
-        val, scaling = cpu_scaled(W_host(), acc, sample, tube)
-        smp = (f"reference cannot run here (pure Julia, no julia binary): CPU restatement (numpy + scipy SuperLU/ARPACK, not "
-               f"Julia/UMFPACK) timed on a bounded sample of the workload: tube {sample[0]}x{sample[1]}x{sample[2]} cubes, {acc['ntet']} tets, "
-               f"{acc['dim']} P2 DOFs, assembly + householder to convergence per step ({acc['total']:.2f} s, {acc['n_fact']} factorisations); "
-               f"value = that time scaled phase by phase to the full workload (assembly x tets, factorisations x factorisation flops, "
-               f"rest x nnz(L+U); see cpu_baseline.scaling) -- an ESTIMATE of the full-size CPU rate, the full-size CPU run itself takes hours")
-        print(json.dumps({"impl": "reference", "metric": "NLEVP eigenpairs/s (householder, config 2)", "value": val, "unit": "eigenpairs/s",
-                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
-                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "c128", "data": "synthetic",
-                          "config": {"workload": workload, "sample": smp},
-                          "cpu_baseline": {"value": val, "unit": "eigenpairs/s", "cores": acc["threads"], "kind": "port", "sample": smp, "extrapolated": True,
-                                           "cores_note": f"process CPU time / wall time of the sample (SuperLU is serial, OpenBLAS threads the dense kernels); host has {os.cpu_count()} cores",
-                                           "scaling": scaling},
+        val = args.steps / dt
+        print(json.dumps({"impl": "reference", "metric": metric, "value": val, "unit": "eigenpairs/s", "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "c128", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": val, "unit": "eigenpairs/s", "cores": acc["threads"], "kind": "port", "sample": cpu_sample_text(acc),
+                                           "extrapolated": False, "sample_dofs": acc["dim"], "sample_tets": acc["ntet"],
+                                           "phases_s": {k: acc[k] for k in ("asm", "factor", "other")}, "omega": [acc["omega"].real, acc["omega"].imag],
+                                           "cores_note": f"process CPU time / wall time of the sample; host has {os.cpu_count()} cores"},
                           "e2e": {"value": val, "unit": "eigenpairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
@@ -298,6 +324,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    pin_rank_to_cores(local, world)
     ctx = W.get_context(local)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     t_setup = time.perf_counter()
@@ -329,22 +356,30 @@ def main():
         sol = step(False, {})
     omega = sol.params["ω"]
 
-    def timed(e2e):
-        stats = {}
-        barrier()
-        l0 = ctx.launch_count()
-        clk = Clocks(local) if rank == 0 else None
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            step(e2e, stats)
-        e1.record()
-        barrier()
-        ms = max_over_ranks(e0.elapsed_time(e1))
-        return ms, stats, ctx.launch_count() - l0, (clk.stop() if clk else None)
-
-    ms, stats, launches, clocks = timed(False)
-    ms_e2e, stats_e2e, _, _ = timed(True)
+    # value and e2e steps alternate inside ONE timed region; every step has its own pair of CUDA events
+    stats, stats_e2e = {}, {}
+    ms_plain = ms_e2e = 0.0
+    launches = 0
+    barrier()
+    clk = Clocks(local) if rank == 0 else None
+    t_region = time.perf_counter()
+    for _ in range(args.steps):
+        for e2e, st in ((False, stats), (True, stats_e2e)):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0 = ctx.launch_count()
+            e0.record()
+            step(e2e, st)
+            e1.record()
+            e1.synchronize()
+            if e2e:
+                ms_e2e += e0.elapsed_time(e1)
+            else:
+                ms_plain += e0.elapsed_time(e1)
+                launches += ctx.launch_count() - l0
+    barrier()
+    t_region = time.perf_counter() - t_region
+    clocks = clk.stop() if clk else None
+    ms, ms_e2e = max_over_ranks(ms_plain), max_over_ranks(ms_e2e)
     value = world * args.steps / (ms * 1e-3)
     value_e2e = world * args.steps / (ms_e2e * 1e-3)
     nfac = stats["factorizations"]
@@ -355,23 +390,23 @@ def main():
     h2d = 3 * npts * 8 + ntet * 8 + (iters / args.steps) * 2 * 16 * dv.dim  # points + c + Krylov start vectors per iteration
     d2h = (iters / args.steps) * 2 * 16 * dv.dim                              # eigenvector pairs back to the host
 
-    out = {"metric": "NLEVP eigenpairs/s (householder, config 2)", "value": value, "unit": "eigenpairs/s", "n_gpus": world,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-           "vs_baseline": None, "dtype": "c128", "data": "synthetic",
-           "config": {"workload": workload, "tets": ntet, "dofs": dv.dim, "nnz": dv.nnz, "factor_nnz": dv.lu_nnz,
-                      "factor_flops": dv.lu_flops, "parallelism": "replicas only (householder does not shard); Beyn nodes sharded under 'beyn'",
-                      "l2": "working set (LU factors, %.1f GB) is far larger than the 126 MB L2; no flush needed" % (dv.lu_nnz * 16 / 1e9),
-                      "setup_s_not_timed": t_setup, "omega": [omega.real, omega.imag]},
-           "e2e": {"value": value_e2e, "unit": "eigenpairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
-           "gpu_launches": int(launches), "clocks": clocks,
-           "phases_ms_per_step_e2e": {"assemble": stats_e2e["assemble_ms"] / args.steps, "numeric_lu": stats_e2e["factor_ms"] / args.steps,
-                                      "eigs_wall": 1e3 * stats_e2e["eigs_wall_s"] / args.steps, "iterations": stats_e2e["iterations"] / args.steps,
-                                      "solves": stats_e2e["solves"] / args.steps},
-           "phases_ms_per_step": {"assemble": stats["assemble_ms"] / args.steps, "numeric_lu": stats["factor_ms"] / args.steps,
-                                  "eigs_wall": 1e3 * stats["eigs_wall_s"] / args.steps, "perturb_wall": 1e3 * stats["perturb_wall_s"] / args.steps,
-                                  "iterations": iters / args.steps, "factorizations": nfac / args.steps, "solves": stats["solves"] / args.steps}}
+    def phases(st):
+        return {"assemble": st["assemble_ms"] / args.steps, "numeric_lu": st["factor_ms"] / args.steps,
+                "combine_factor_wall": 1e3 * st["combine_factor_wall_s"] / args.steps, "eigs_wall": 1e3 * st["eigs_wall_s"] / args.steps,
+                "perturb_wall": 1e3 * st.get("perturb_wall_s", 0.0) / args.steps, "iterations": st["iterations"] / args.steps,
+                "factorizations": st["factorizations"] / args.steps, "solves": st["solves"] / args.steps}
 
-    # ------------------------------------------------------------------ roofline of the dominant kernel
+    out = {"metric": metric, "value": value, "unit": "eigenpairs/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "c128", "data": "synthetic", "config": config,
+           "details": {"tets": ntet, "dofs": dv.dim, "nnz": dv.nnz, "factor_nnz": dv.lu_nnz, "factor_flops": dv.lu_flops, "setup_s_not_timed": t_setup,
+                       "omega": [omega.real, omega.imag], "timed_region_wall_s": t_region,
+                       "timed_region": "value and e2e steps alternate; ms_per_step = sum of the value steps' CUDA-event times / steps (max over ranks)"},
+           "e2e": {"value": value_e2e, "unit": "eigenpairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                   "ms_per_step": ms_e2e / args.steps},
+           "gpu_launches": int(launches), "clocks": clocks}
+
+    # ------------------------------------------------------------------ roofline of the dominant kernel (+ the other kernels under "legs")
     peaks = fp64_peak(torch, dev)
     peak = max(peaks.values())
     out["roofline"] = {"bound": "tensor", "achieved": fac_tflops, "peak": peak, "unit": "TFLOP/s", "frac": fac_tflops / peak,
@@ -383,7 +418,9 @@ def main():
                        "note": ("achieved = factorisation flops from the symbolic phase (8 real flops per complex multiply-add; half of the LU "
                                 "count for the symmetric elimination; includes the 2 extra solves of the Woodbury set-up in the time) / "
                                 "CUDA-event time of the numeric LU (all its kernels); peak = cuBLAS FP64 GEMM measured in this run "
-                                f"(dgemm 8192^3 {peaks['dgemm']:.1f}, zgemm 4096^3 {peaks['zgemm']:.1f} TFLOP/s) -- MEASURED_PEAKS.json has no FP64 figure")}
+                                f"(dgemm 8192^3 {peaks['dgemm']:.1f}, zgemm 4096^3 {peaks['zgemm']:.1f} TFLOP/s) -- MEASURED_PEAKS.json has no FP64 figure"),
+                       "phases_ms_per_step": phases(stats), "phases_ms_per_step_e2e": phases(stats_e2e), "legs": {}}
+    legs = out["roofline"]["legs"]
     # triangular solves vs HBM: one refined solve (2 sweeps pairs: L then U^T panel each) of a random right-hand side
     hbm = 6548.5
     try:
@@ -392,42 +429,43 @@ def main():
     except Exception:
         hbm_src = "fallback"
     rng = np.random.default_rng(1)
-    bvec = rng.standard_normal(dv.dim) + 1j * rng.standard_normal(dv.dim)
-    sol_ms = []
-    for _ in range(4):
-        ctx.lu_solve(lu, bvec)
-        sol_ms.append(ctx.last_ms("solve"))
-    sol_med = float(np.median(sol_ms[1:]))
-    sol_bytes = 2 * (16.0 * dv.lu_nnz + 2 * 16.0 * dv.dim)  # 16 (nnz(L)+nnz(U)) + 16 d nrhs 2 per solve; one refinement step = 2 solves
-    out["solve"] = {"ms": sol_med, "nrhs": 1, "refinement_steps": 1,
-                    "roofline": {"bound": "hbm", "achieved": sol_bytes / sol_med / 1e6, "peak": hbm, "unit": "GB/s", "frac": sol_bytes / sol_med / 1e6 / hbm,
-                                 "traffic": None, "peak_source": hbm_src,
-                                 "kernel": "lu_fwd_update / lu_bwd_update / lu_fwd_tri / lu_bwd_tri (level-scheduled, windowed)",
-                                 "algorithmic_bytes": sol_bytes}}
-    if not args.skip_extras and rank == 0:
-        out["assembly"] = assembly_leg(W, ctx, args.assembly_cubes, hbm, hbm_src) if args.assembly_cubes else None
-        # re-establish the tube mesh on the context for anything that follows
-    # ------------------------------------------------------------------ Beyn leg (sharded over all ranks)
-    if not args.skip_extras:
-        out["beyn"] = beyn_leg(W, torch, dist, ctx, args, rank, world, dev, barrier, max_over_ranks)
-    # ------------------------------------------------------------------ CPU baseline (rank 0, N = 1 only)
+    for nrhs in (1, 8):
+        bvec = rng.standard_normal((dv.dim, nrhs)) + 1j * rng.standard_normal((dv.dim, nrhs))
+        sol_ms = []
+        for _ in range(4):
+            ctx.lu_solve(lu, bvec if nrhs > 1 else bvec[:, 0])
+            sol_ms.append(ctx.last_ms("solve"))
+        sol_med = float(np.median(sol_ms[1:]))
+        sol_bytes = 2 * (16.0 * dv.lu_nnz + 2 * 16.0 * dv.dim * nrhs)  # 16 (nnz(L)+nnz(U)) + 16 d nrhs 2 per solve; one refinement step = 2 solves
+        legs["solve_nrhs%d" % nrhs] = {"ms": sol_med, "nrhs": nrhs, "refinement_steps": 1, "bound": "hbm", "achieved": sol_bytes / sol_med / 1e6, "peak": hbm,
+                                       "unit": "GB/s", "frac": sol_bytes / sol_med / 1e6 / hbm, "traffic": None, "peak_source": hbm_src,
+                                       "kernel": "lu_fwd_update / lu_bwd_update / lu_fwd_tri / lu_bwd_tri (level-scheduled, windowed)",
+                                       "algorithmic_bytes": sol_bytes}
+    # ------------------------------------------------------------------ the same problem on both sides (rank 0, N = 1): the CPU oracle's bounded
+    # sample, measured, and the GPU path on that very mesh; the two eigenvalues are the tube-geometry parity check
     if rank == 0 and world == 1 and not args.skip_extras:
-        sample = tuple(int(x) for x in args.cpu_sample.split(","))
         st = oracle_step(sample)
-        val, scaling = cpu_scaled(W, st, sample, tube)
-        out["cpu_baseline"] = {"value": val, "unit": "eigenpairs/s", "cores": st["threads"], "kind": "port", "extrapolated": True, "scaling": scaling,
+        same = same_problem_leg(W, ctx, sample, st)
+        out["cpu_baseline"] = {"value": 1.0 / st["total"], "unit": "eigenpairs/s", "cores": st["threads"], "kind": "port", "extrapolated": False,
+                               "sample": cpu_sample_text(st), "sample_dofs": st["dim"], "sample_tets": st["ntet"],
+                               "phases_s": {k: st[k] for k in ("asm", "factor", "other")},
                                "cores_note": f"process CPU time / wall time of the sample (SuperLU is serial, OpenBLAS threads the dense kernels); host has {os.cpu_count()} cores",
-                               "sample": (f"numpy/scipy (SuperLU+ARPACK) restatement of the reference path, NOT Julia/UMFPACK; one eigenpair on "
-                                          f"the same tube at {sample[0]}x{sample[1]}x{sample[2]} cubes = {st['ntet']} tets, {st['dim']} P2 DOFs "
-                                          f"({dv.dim / st['dim']:.0f}x fewer DOFs than the GPU workload), {st['nit']} Newton iterations, "
-                                          f"{st['total']:.1f} s measured; value = that time scaled phase by phase to the full workload (assembly x "
-                                          f"tets, factorisations x factorisation flops, rest x nnz(L+U)): an estimate, the full-size CPU run "
-                                          f"takes hours; host has {os.cpu_count()} cores, SuperLU is serial")}
+                               "same_problem": same}
+        try:
+            out["cpu_baseline"]["full_size_estimate"] = cpu_scaled(W, st, sample, tube)
+        except Exception as e:  # noqa: BLE001 -- a side note only
+            out["cpu_baseline"]["full_size_estimate"] = {"error": repr(e)[:200]}
+    # the 23 GB of factors of the tube are not needed any more: the Beyn leg's cylinder needs 78 GB per GPU
+    L.release()
+    if not args.skip_extras and rank == 0 and args.assembly_cubes:
+        legs["assembly"] = assembly_leg(W, ctx, args.assembly_cubes, hbm, hbm_src)
+    # ------------------------------------------------------------------ Beyn leg (BASELINE.json configs[2], sharded over all ranks)
+    if not args.skip_extras:
+        legs["beyn"] = beyn_leg(W, torch, dist, ctx, args, rank, world, dev, barrier, max_over_ranks)
     # ------------------------------------------------------------------ diagnostic legs (rank 0, N = 1 only), each in a subprocess and inside a
     # wall-clock budget: a leg that would start later than DIAG_START_BY seconds into the run is skipped, and none may run past DIAG_END_BY
     if rank == 0 and world == 1 and not args.skip_extras:
         out["shape_sensitivity"] = diag_leg("bench_shape_sens.py", ["10", "10", "150", "5"], 300)
-        out["lu_knobs"] = diag_leg("bench_lu_knobs.py", [*(str(x) for x in tube), "quad", "2"], 240)  # "combos" + "householder" (default vs paired)
     out["wall_s"] = time.perf_counter() - T_START
     if rank == 0:
         print(json.dumps(out))
@@ -435,8 +473,59 @@ def main():
         dist.destroy_process_group()
 
 
+def pin_rank_to_cores(local, world):
+    """One core set per rank (N replicas share the host: without this the ranks' Python threads migrate and collide)."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+        if world > 1 and len(cores) >= 2 * world:
+            per = len(cores) // world
+            os.sched_setaffinity(0, cores[local * per:(local + 1) * per])
+    except (AttributeError, OSError):
+        pass
+
+
+def same_problem_leg(W, ctx0, sample, st_cpu):
+    """The GPU path on the CPU oracle's own sample (same mesh, same descriptor, same start value and tolerance): eigenpairs/s and the
+    relative difference of the two eigenvalues."""
+    import torch
+
+    from wae_b200 import _lib
+    ctx = _lib.Context(ctx0.device)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    mesh, c, dscrp = tube_case(W, sample)
+    L = W.discretize(mesh, dscrp, c, order="quad", ctx=ctx)
+    disc = L.discretization
+    L.device().lu()
+
+    def one():
+        disc.reassemble(c)
+        sol, n, flag = W.householder(L, Z0, maxiter=15, tol=1e-9 * Z0, output=False)
+        return sol, n, flag
+    for _ in range(2):
+        one()
+    reps = 5
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        sol, n, flag = one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    om_g, om_c = complex(sol.params["ω"]), st_cpu["omega"]
+    res = {"mesh": f"tube {sample[0]}x{sample[1]}x{sample[2]} cubes, {len(mesh.tetrahedra)} tets, {L.size()} P2 DOFs (identical on both sides)",
+           "gpu_eigenpairs_per_s": 1e3 / ms, "gpu_ms_per_eigenpair": ms, "gpu_iterations": n, "gpu_flag": flag,
+           "cpu_eigenpairs_per_s": 1.0 / st_cpu["total"], "cpu_s_per_eigenpair": st_cpu["total"], "cpu_iterations": st_cpu["nit"],
+           "measured_ratio_gpu_over_cpu": (1e3 / ms) * st_cpu["total"],
+           "omega_gpu": [om_g.real, om_g.imag], "omega_cpu": [om_c.real, om_c.imag], "omega_rel_diff": abs(om_g - om_c) / abs(om_c),
+           "note": "both sides measured on the same problem in the same run; a 10^4-DOF problem is launch-latency-bound on the GPU"}
+    ctx.close()
+    return res
+
+
 def assembly_leg(W, ctx0, n, hbm, hbm_src):
-    """M+K assembly of an n^3-cube P2 box (config 5 geometry at bench size), kernel time by CUDA events."""
+    """M+K assembly of an n^3-cube P2 box (config 5 geometry at bench size), kernel time by CUDA events: the star kernel (generation 3,
+    the default) and, beside it, the pair-program kernel of round 1 (generation 2)."""
     from wae_b200 import _lib
     ctx = _lib.Context(ctx0.device)
     mesh = W.kuhn_box((n, n, n), (0, 0, 0), (1, 1, 1), jitter=0.1, seed=7)
@@ -444,49 +533,62 @@ def assembly_leg(W, ctx0, n, hbm, hbm_src):
     ctx.mesh_set(2, mesh.points.T, tets, tris, dim)
     pid, nnz = ctx.pattern_build(3, None)
     c = np.random.default_rng(7).uniform(300, 700, len(tets))
-    im, ik = ctx.assemble_mk(pid, c)
-    ms = []
-    for _ in range(5):
-        ctx.assemble_mk(pid, c, reuse=(im, ik))
-        ms.append(ctx.last_ms("assemble"))
-    med = float(np.median(ms))
     ntet, npts = len(tets), mesh.points.shape[1]
     alg = ntet * (4 * 10 + 8) + 24 * npts + 2 * nnz * 8
+
+    def timed(gen):
+        old = os.environ.pop("WAE_ASM_GEN", None)
+        if gen is not None:
+            os.environ["WAE_ASM_GEN"] = gen
+        try:
+            im, ik = ctx.assemble_mk(pid, c)
+            ms = []
+            for _ in range(7):
+                ctx.assemble_mk(pid, c, reuse=(im, ik))
+                ms.append(ctx.last_ms("assemble"))
+            ctx.mat_free(im); ctx.mat_free(ik)
+        finally:
+            os.environ.pop("WAE_ASM_GEN", None)
+            if old is not None:
+                os.environ["WAE_ASM_GEN"] = old
+        return float(np.median(ms))
+    med = timed(None)
+    prog = ctx.last_ms("star_program_bytes")
+    layout = {k: ctx.last_ms("star_" + k) for k in ("patches", "staged", "simplices", "sources", "smem", "threads", "ctas_per_sm")}
+    med2 = timed("2")
+    traffic, tsrc = ncu_traffic(f"assemble_tet_stars/p2_box_{n}")
     res = {"value": ntet / med / 1e3, "unit": "Mtets/s", "tets": ntet, "dofs": dim, "nnz": int(nnz), "kernel_ms": med,
-           "roofline": {"bound": "hbm", "achieved": alg / med / 1e6, "peak": hbm, "unit": "GB/s", "frac": alg / med / 1e6 / hbm,
-                        "traffic": ncu_traffic(f"assemble_tet_pairs/p2_box_{n}")[0], "traffic_note": "GB per launch, " + str(ncu_traffic(f"assemble_tet_pairs/p2_box_{n}")[1]),
-                        "peak_source": hbm_src, "algorithmic_bytes_per_tet": alg / ntet,
-                        "kernel": "assemble_tet_pairs<10,3> (P2 M+K, owner-computes pair program, persistent, TMA-staged)"}}
+           "bound": "hbm", "achieved": alg / med / 1e6, "peak": hbm, "frac": alg / med / 1e6 / hbm, "achieved_unit": "GB/s",
+           "traffic": traffic, "traffic_note": "GB per launch (dram read + write), " + str(tsrc), "peak_source": hbm_src,
+           "algorithmic_bytes_per_tet": alg / ntet, "program_bytes_per_tet": prog / ntet if prog > 0 else None, "layout": layout,
+           "kernel": "assemble_tet_stars<10,3> (P2 M+K, star program: sub-simplex stars summed in registers, persistent, TMA-staged program)",
+           "generation_2": {"kernel": "assemble_tet_pairs<10,3> (round 1, WAE_ASM_GEN=2)", "kernel_ms": med2, "value": ntet / med2 / 1e3,
+                            "frac": alg / med2 / 1e6 / hbm}}
     ctx.close()
-    # opt-in kernel variants (WAE_ASM_VARIANT; prepared from the per-phase profile): timed and checked against the
-    # default kernel in a SUBPROCESS, so that nothing they do can disturb this run; the headline above is always the default kernel
-    if int(os.environ.get("WORLD_SIZE", "1")) > 1:  # the other ranks are waiting for this one: no diagnostics in the scaling runs
-        return res
-    diag = diag_leg("bench_assembly_variants.py", [str(n), "quad", "7"], 240,
-                    env={**os.environ, "CUDA_VISIBLE_DEVICES": os.environ.get("CUDA_VISIBLE_DEVICES", str(ctx0.device))})
-    res["variants"] = diag.get("variants", diag)
-    if "layouts" in diag:  # short patch-size x CTAs-per-SM sweep (the default layout stays 12288 slots, one CTA per SM)
-        res["layouts"] = diag["layouts"]
     return res
 
 
 def beyn_leg(W, torch, dist, ctx0, args, rank, world, dev, barrier, max_over_ranks):
-    """Beyn contour integration, 4 x beyn_edge_nodes quadrature nodes sharded round-robin over the ranks,
-    one NCCL all-reduce of the moments (strong scaling: the total work is fixed)."""
+    """BASELINE.json configs[2]: Beyn contour integration, 4 x beyn_edge_nodes quadrature nodes on the ~2 M-DOF squircle cylinder (P2 32 x 32 x
+    236 cubes, 1 998 425 DOFs), l = 8, nodes sharded round-robin over the ranks, one NCCL all-reduce of the moments (strong scaling: the
+    total work is fixed; reported at every N, N = 1 included)."""
     from wae_b200 import _lib, nlevp
-    nb = tuple(int(x) for x in args.beyn_box.split(","))
+    nb = tuple(int(x) for x in args.beyn_grid.split(","))
     ctx = _lib.Context(ctx0.device)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
-    mesh = W.kuhn_box(nb, (0, 0, -0.5), (0.1, 0.1, 0.5), jitter=0.1, seed=2024, name="beyn_tube")
+    t0 = time.perf_counter()
+    R, Lz = 0.05, 1.0
+    mesh = W.kuhn_box(nb, (-R, -R, 0.0), (R, R, Lz), jitter=0.1, seed=2024, name="cylinder")
+    x, y = mesh.points[0] / R, mesh.points[1] / R
+    mesh.points[0], mesh.points[1] = R * x * np.sqrt(1 - 0.5 * y * y), R * y * np.sqrt(1 - 0.5 * x * x)  # square -> disc
     c = np.full(len(mesh.tetrahedra), 347.2)
     dscrp = {"Interior": ("interior", ()), "Outlet": ("admittance", ("Y", 1e15))}
-    L = W.discretize(mesh, dscrp, c, order="lin", ctx=ctx)
+    L = W.discretize(mesh, dscrp, c, order=args.beyn_order, ctx=ctx)
     dv = L.device()
     dv.lu()
-    G = [z * 2 * math.pi for z in (50 + 40j, 50 - 40j, 800 - 40j, 800 + 40j)]
+    t_setup = time.perf_counter() - t0
+    G = [z * 2 * math.pi for z in (50 + 100j, 50 - 100j, 850 - 100j, 850 + 100j)]
     l, N = 8, args.beyn_edge_nodes
-    # warm-up: one node per rank
-    nlevp.compute_moment_matrices(L, G[:2], l=l, K=1, N=1)
     stats = {}
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -498,11 +600,19 @@ def beyn_leg(W, torch, dist, ctx0, args, rank, world, dev, barrier, max_over_ran
     e1.record()
     barrier()
     ms = max_over_ranks(e0.elapsed_time(e1))
-    res = {"value": len(Om) / (ms * 1e-3), "unit": "eigenpairs/s", "scaling": "strong", "n_gpus": world, "nodes": 4 * N, "l": l,
-           "dofs": dv.dim, "tets": len(mesh.tetrahedra), "eigenvalues_found": len(Om), "ms": ms,
-           "node_solves_per_s": 4 * N / (ms * 1e-3), "factor_ms_rank0": stats.get("factor_ms"), "solve_ms_rank0": stats.get("solve_ms"),
+    fac = max_over_ranks(stats.get("factor_ms", 0.0))
+    sol = max_over_ranks(stats.get("solve_ms", 0.0))
+    sym = ctx.last_ms("factor_sym") > 0.5
+    nper = len(nlevp.shard_nodes(4 * N, 0, world))
+    flops = dv.lu_flops * (0.5 if sym else 1.0)
+    res = {"config": f"BASELINE.json configs[2]: Beyn, {4 * N} quadrature nodes, l = {l}, K = 1, squircle cylinder {args.beyn_grid} cubes, {args.beyn_order}",
+           "value": len(Om) / (ms * 1e-3), "unit": "eigenpairs/s", "scaling": "strong", "n_gpus": world, "nodes": 4 * N, "l": l,
+           "dofs": dv.dim, "tets": len(mesh.tetrahedra), "factor_nnz": dv.lu_nnz, "eigenvalues_found": len(Om), "ms": ms, "seconds": ms * 1e-3,
+           "node_solves_per_s": 4 * N / (ms * 1e-3), "max_rank_factor_ms": fac, "max_rank_solve_ms": sol, "nodes_per_rank": nper,
+           "factor_tflops_rank0": flops * nper / (max(stats.get("factor_ms", 1.0), 1e-9) * 1e-3) / 1e12, "setup_s_not_timed": t_setup,
            "freq_hz": sorted(float(x) for x in (Om.real / 2 / math.pi))[:8],
-           "collective": "one all_reduce (NCCL) of the 2K x l x d complex moment tensor"}
+           "collective": "one all_reduce (NCCL) of the 2K x l x d complex moment tensor",
+           "speedup_note": "strong scaling: seconds at N GPUs against seconds at N = 1 of the same leg (SCALE_r02.json holds every N)"}
     ctx.close()
     return res
 

@@ -147,6 +147,11 @@ int32_t wae_family_spmm(wae_ctx* h, int32_t fam_id, int32_t slot, int32_t trans,
  * triangular solves run on the device.                                                      */
 int32_t wae_lu_analyze(wae_ctx* h, int32_t fam_id, int32_t* lu_id, int64_t* factor_nnz, double* factor_flops);
 int32_t wae_lu_factor(wae_ctx* h, int32_t lu_id, int32_t slot);
+/* check = 1: as wae_lu_factor -- an exactly zero pivot (the matrix is singular for an LU without row exchanges; UMFPACK would raise
+ * SingularException or pivot) returns WAE_E_SINGULAR instead of factors that solve to garbage.  check = 0: the reference's
+ * lu(L(0,0), check=false) of the deliberately singular operator in perturb (perturbation.jl:329): tiny and zero pivots are replaced
+ * (static pivoting) and the factors are kept.                                                                                   */
+int32_t wae_lu_factor_ex(wae_ctx* h, int32_t lu_id, int32_t slot, int32_t check);
 /* In-place solve op(A) X = B; trans as above; X dim x nrhs column-major complex host array. */
 int32_t wae_lu_solve(wae_ctx* h, int32_t lu_id, int32_t trans, int32_t nrhs, double* X);
 
@@ -218,6 +223,17 @@ int32_t wae_beyn_moments(wae_ctx* h, int32_t fam_id, int32_t lu_id, int32_t n_no
                          const double* z, const double* w, const double* coeffs,
                          int32_t l, int32_t n_mom, const double* V /* dim x l complex host array, NULL = identity columns */,
                          void* A_out_device);
+
+/* The same for ALL GPUs of the box from one host process -- the reference's beyn is one process with one loop over all quadrature
+ * nodes (beyn.jl:34-74, 112-138), so a single ccall must scale.  hs[0..n_ctx) are contexts on n_ctx different devices, each holding
+ * the same family (fam_ids[r]) and an analysed LU of it (lu_ids[r]) -- the caller builds them with one loop over the devices
+ * (INTEGRATION.md).  Node j goes to context j mod n_ctx; every context runs its nodes on its own host thread; the partial moments
+ * are summed with ONE ncclAllReduce over NVLink inside the library (NCCL is loaded at run time: libnccl.so.2 or WAE_NCCL_LIB; not
+ * needed for n_ctx = 1) and returned in the HOST array A_out (dim x l x n_mom complex, column-major).  The moment update
+ * A_p += w z^p X is fused into the last kernel of every node's solve.  Errors of a device are reported on hs[0] (wae_last_error). */
+int32_t wae_beyn_moments_multi(int32_t n_ctx, wae_ctx* const* hs, const int32_t* fam_ids, const int32_t* lu_ids, int32_t n_nodes,
+                               const double* z, const double* w, const double* coeffs, int32_t l, int32_t n_mom,
+                               const double* V /* dim x l complex host array, NULL = identity columns */, double* A_out);
 
 /* ---- discrete-adjoint shape sensitivity ------------------------------------------------
  * Replaces the loop of discrete_adjoint_shape_sensitivity (src/shape_sensitivity.jl:16-141; non-unit meshes): per surface

@@ -237,7 +237,7 @@ class HostStandIn:
             raise _lib.WaeError(_lib.E_INVALID, f"family {fid} still has an LU handle (wae_lu_free first)")
         self.fams[fid] = None
 
-    def lu_factor(self, lid, slot):
+    def lu_factor(self, lid, slot, check=True):
         S = self.lus[lid]
         S["A"] = self._slot(S["fid"], slot)
         try:

@@ -329,24 +329,34 @@ def test_fancyflame_and_state_space_scalars():
 
 
 def test_bench_reference_arm_contract():
-    """`bench.py --impl reference` (the CPU arm the driver times beside the GPU arm) prints one JSON line with the contract's keys."""
+    """`bench.py --impl reference` (the CPU arm the driver times beside the GPU arm) prints one JSON line with the contract's keys; its
+    value is MEASURED on the bounded sample (no extrapolation), its `config` is the GPU arm's, and it never loads libwae_b200.so."""
     import json
     import subprocess
     import sys
     root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
-    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--ref-sample", "2,2,8"], capture_output=True, text=True, timeout=600, cwd=root)
+    code = ("import sys, runpy; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '0', '--cpu-sample', '2,2,8']; "
+            "runpy.run_path('bench.py', run_name='__main__'); "
+            "print('NATIVE', [l.split()[-1] for l in open('/proc/self/maps') if 'libwae_b200' in l])")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=root)
     assert out.returncode == 0, out.stderr[-2000:]
     line = [l for l in out.stdout.splitlines() if l.startswith("{")][-1]
     d = json.loads(line)
     assert d["impl"] == "reference" and d["unit"] == "eigenpairs/s" and d["higher_is_better"] is True
     assert d["value"] > 0 and d["steps"] == 1 and d["vs_baseline"] is None
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
-    # the value is the sample scaled to the full workload (config 2), phase by phase, and says so
-    sc = d["cpu_baseline"]["scaling"]
-    assert d["cpu_baseline"]["extrapolated"] is True and sc["growth"]["factor_flops"] > sc["growth"]["factor_nnz"] > sc["growth"]["tets"] > 1
-    assert abs(d["value"] * sc["estimated_full_size_s"] - 1) < 1e-12 and d["value"] < sc["sample_eigenpairs_per_s"]
-    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["extrapolated"] is False
+    # measured: one step of the sample took ms_per_step, and that is the value
+    assert abs(d["value"] * d["ms_per_step"] * 1e-3 - 1) < 1e-9 and cb["value"] == d["value"]
+    assert "scaling" not in cb and cb["sample_dofs"] == 5 * 5 * 17
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    # the same config object as the GPU arm (the driver compares them)
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert d["config"] == bench.workload_config((20, 20, 300), (2, 2, 8))
+    assert [l for l in out.stdout.splitlines() if l.startswith("NATIVE")][-1] == "NATIVE []"
 
 
 @pytest.mark.parametrize("name,scale", [("rijke_mm", 0.001), ("ntnu_12", 1.0)])

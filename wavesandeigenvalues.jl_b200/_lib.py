@@ -73,6 +73,7 @@ SIGNATURES = {
     "wae_family_spmm": (_i32, [_vp, _i32, _i32, _i32, _i32, _pd, _pd]),
     "wae_lu_analyze": (_i32, [_vp, _i32, _pi32, _pi64, _pd]),
     "wae_lu_factor": (_i32, [_vp, _i32, _i32]),
+    "wae_lu_factor_ex": (_i32, [_vp, _i32, _i32, _i32]),
     "wae_lu_solve": (_i32, [_vp, _i32, _i32, _i32, _pd]),
     "wae_lu_free": (_i32, [_vp, _i32]),
     "wae_family_free": (_i32, [_vp, _i32]),
@@ -80,6 +81,7 @@ SIGNATURES = {
     "wae_eigs_si": (_i32, [_vp, _i32, _i32, _i32, _i32, _i32, _pd, _pd, _pd, _pi32]),
     "wae_eigs_si_pair": (_i32, [_vp, _i32, _i32, _i32, _i32, _pd, _pd, _pd, _pd, _pd, _pd, _pi32]),
     "wae_beyn_moments": (_i32, [_vp, _i32, _i32, _i32, _pd, _pd, _pd, _i32, _i32, _pd, _vp]),
+    "wae_beyn_moments_multi": (_i32, [_i32, C.POINTER(_vp), _pi32, _pi32, _i32, _pd, _pd, _pd, _i32, _i32, _pd, _pd]),
     "wae_assemble_wallsrc": (_i32, [_vp, _i64, _pi64, _pd, _i32, _pd]),
     "wae_shape_sens_begin": (_i32, [_vp, _i64, _pi64, _pi64, _dbl, _i32, _i64, _pd, _pd, _pi64, C.POINTER(C.c_uint8), _pd]),
     "wae_shape_sens_add": (_i32, [_vp, _i32, _pi64, _pi64, _pd, _i32, _pd, _i64, _pd, _dbl]),
@@ -117,12 +119,14 @@ def sorted_unique_simplices(simp):
 
 
 class Context:
-    """One wae_ctx (one GPU, one host thread).  Index base 0 on the Python side."""
+    """One wae_ctx (one GPU, one host thread).  Index base 0 on the Python side; base=1 is what the Julia shim of INTEGRATION.md creates
+    (element / DOF / nonzero indices cross the ABI as Julia holds them) and what tests/test_zv_index_base_gpu.py exercises."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, base=0):
         self._l = lib()
         h = _vp()
-        rc = self._l.wae_create(C.byref(h), device, 0)
+        self.base = base
+        rc = self._l.wae_create(C.byref(h), device, base)
         if rc != OK:
             raise WaeError(rc, "wae_create failed (no CUDA device? this package has no CPU fallback)")
         self.h = h
@@ -299,8 +303,9 @@ class Context:
         self._chk(self._l.wae_lu_analyze(self.h, fid, C.byref(lid), C.byref(nnz), C.byref(fl)))
         return lid.value, nnz.value, fl.value
 
-    def lu_factor(self, lid, slot):
-        self._chk(self._l.wae_lu_factor(self.h, lid, slot))
+    def lu_factor(self, lid, slot, check=True):
+        """check=False: lu(A, check=false) of perturbation.jl:329 (a singular matrix is factorised with static pivoting instead of raising)."""
+        self._chk(self._l.wae_lu_factor_ex(self.h, lid, slot, 1 if check else 0))
 
     def lu_solve(self, lid, B, trans=0):
         B = np.asarray(B, dtype=np.complex128)
@@ -354,6 +359,23 @@ class Context:
         if V is not None:
             V = np.asfortranarray(V, dtype=np.complex128)
         self._chk(self._l.wae_beyn_moments(self.h, fid, lid, len(z), _p(z, _pd), _p(w, _pd), _p(cf, _pd), l, n_mom, _p(V, _pd), _vp(out_ptr)))
+
+    @staticmethod
+    def beyn_moments_multi(ctxs, fids, lids, z, w, coeffs, l, n_mom, dim, V=None):
+        """wae_beyn_moments_multi: all nodes from ONE host process, node j on ctxs[j mod len(ctxs)] (one context per device), the partial
+        moments all-reduced with NCCL inside the library.  Returns the (dim, l, n_mom) complex moments as a Fortran-ordered host array."""
+        z = np.ascontiguousarray(z, dtype=np.complex128)
+        w = np.ascontiguousarray(w, dtype=np.complex128)
+        cf = np.ascontiguousarray(coeffs, dtype=np.complex128)
+        if V is not None:
+            V = np.asfortranarray(V, dtype=np.complex128)
+        hs = (_vp * len(ctxs))(*[c.h for c in ctxs])
+        fa = np.ascontiguousarray(fids, dtype=np.int32)
+        la = np.ascontiguousarray(lids, dtype=np.int32)
+        out = np.zeros((dim, l, n_mom), dtype=np.complex128, order="F")
+        ctxs[0]._chk(ctxs[0]._l.wae_beyn_moments_multi(len(ctxs), hs, _p(fa, _pi32), _p(la, _pi32), len(z), _p(z, _pd), _p(w, _pd), _p(cf, _pd),
+                                                        l, n_mom, _p(V, _pd), _p(out, _pd)))
+        return out
 
     # -- shape sensitivity -----------------------------------------------------------------------
     def shape_sens_begin(self, points, step, v, v_adj, partner=None, cylindrical=False, dof_new=None, dof_flag=None, phase=None):

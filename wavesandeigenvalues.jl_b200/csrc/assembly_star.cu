@@ -447,7 +447,7 @@ bool wae_ensure_star(wae_ctx* h, Pattern& P) {
 
 // ---- host replay (no GPU, no context): pattern + star program of a tetrahedral mesh, then the three passes of
 // assemble_tet_stars with the kernel's own arithmetic (the functions above compiled for the host).  See include/wae_b200.h.
-static int64_t g_sim[8];
+static int64_t g_sim[8], g_simtype[4][2];
 // shared-memory wavefronts of one 8-byte warp load: per half-warp, the largest number of distinct addresses in one bank pair
 static int wavefronts64(const int64_t* addr, const bool* act, int* ideal) {
   int tot = 0;
@@ -520,8 +520,11 @@ static void star_replay(const StarHost& G, const double* xyz, const double* c, d
             ii[l] = idx;
           }
           int id = 0;
-          wf[0] += wavefronts64(addr, act, &id);
+          const int w0 = wavefronts64(addr, act, &id);
+          wf[0] += w0;
           wf[1] += id;
+          g_simtype[type][0] += w0;
+          g_simtype[type][1] += id;
           if (getenv("WAE_STAR_SIM")) {  // layout experiments: other element strides, entry-major (SoA) storage
             static const int S[6] = {17, 19, 21, 23, 25, 27};
             for (int q = 0; q < 6; q++) {
@@ -626,6 +629,8 @@ extern "C" int32_t wae_star_program_check(int32_t order, int64_t n_pts, const do
     if (getenv("WAE_STAR_SIM")) {
       fprintf(stderr, "[star sim] gram gathers, wavefronts per tetrahedron: strides 17 19 21 23 25 27 | SoA | SoA+1:");
       for (int q = 0; q < 8; q++) fprintf(stderr, " %.2f", (double)g_sim[q] / (double)n_tet), g_sim[q] = 0;
+      fprintf(stderr, "\n[star sim] gram gathers by type (wavefronts / conflict-free per tetrahedron):");
+      for (int q = 0; q < 4; q++) fprintf(stderr, "  %.2f / %.2f", (double)g_simtype[q][0] / (double)n_tet, (double)g_simtype[q][1] / (double)n_tet), g_simtype[q][0] = g_simtype[q][1] = 0;
       fprintf(stderr, "\n");
     }
     for (int i = 0; i < 4; i++) stats[8 + i] = (double)wf[i];  // shared-memory wavefronts of the gathers (simulated) and their conflict-free count

@@ -155,7 +155,95 @@ static void build_patch(const uint32_t* conn, int nloc, const Pattern& P, const 
     if (ent[x].cnt != ent[y].cnt) return ent[x].cnt > ent[y].cnt;
     return first_elem(ent[x]) < first_elem(ent[y]);
   });
-  // groups of 32 sub-simplices of one type
+  // ---- store program first (it depends on the owned columns only): owned columns by DOF number, chunks of at most 32 consecutive
+  // nonzeros that do not straddle a 32-nonzero (256-byte) boundary of the value arrays; hc[i] = half-warp (2 * chunk + lane / 16) that
+  // will read the record entry of local nonzero i
+  std::vector<int32_t> cols(hi - lo);
+  for (int32_t q = lo; q < hi; q++) cols[q - lo] = order[q];
+  std::sort(cols.begin(), cols.end());
+  std::vector<int64_t> coloff(cols.size() + 1, 0);
+  for (size_t c = 0; c < cols.size(); c++) coloff[c + 1] = coloff[c] + (P.colptr[cols[c] + 1] - P.colptr[cols[c]]);
+  const size_t nnz_own = (size_t)coloff.back();
+  std::vector<int32_t> hc(nnz_own);
+  O.chunk.clear();
+  for (size_t c = 0; c < cols.size(); c++) {
+    const int32_t j = cols[c];
+    for (int64_t z = P.colptr[j]; z < P.colptr[j + 1]; z++) {
+      const size_t nc = O.chunk.size();
+      if (nc && O.chunk[nc - 2] + (O.chunk[nc - 1] & 63u) == (uint32_t)z && (z & 31) != 0)
+        O.chunk[nc - 1]++;
+      else {
+        O.chunk.push_back((uint32_t)z);
+        O.chunk.push_back(1u | ((uint32_t)(coloff[c] + (z - P.colptr[j])) << 6));  // codes are stored in the same order
+      }
+      const size_t ch = O.chunk.size() / 2 - 1;
+      hc[(size_t)coloff[c] + (z - P.colptr[j])] = (int32_t)(2 * ch + (((O.chunk[2 * ch + 1] & 63u) - 1) >> 4));
+    }
+  }
+  const size_t n_half = O.chunk.size();  // 2 per chunk
+  // ---- the nonzeros every sub-simplex feeds: (local nonzero, role), owned columns only
+  std::vector<int32_t> enz_ptr(ent.size() + 1, 0);
+  std::vector<std::pair<int32_t, int32_t>> enz;
+  enz.reserve(nnz_own);
+  {
+    auto put = [&](uint32_t prow, uint32_t qcol, int role) {
+      if (!owned(qcol)) return;
+      const size_t c = std::lower_bound(cols.begin(), cols.end(), (int32_t)qcol) - cols.begin();
+      const int32_t* b = P.rowval.data() + P.colptr[qcol];
+      const int32_t* e = P.rowval.data() + P.colptr[qcol + 1];
+      const int32_t* it = std::lower_bound(b, e, (int32_t)prow);
+      if (it == e || *it != (int32_t)prow) { O.bad |= 16; return; }
+      enz.emplace_back((int32_t)(coloff[c] + (it - b)), role);
+    };
+    auto put2 = [&](uint32_t p_, uint32_t q_, int role) {
+      put(p_, q_, role);
+      if (p_ != q_) put(q_, p_, role);
+    };
+    for (size_t ei = 0; ei < ent.size(); ei++) {
+      const Ent& E = ent[ei];
+      const Src& s0 = src[E.first];
+      const int n = E.type + 1;
+      const int t = (int)(n < 4 ? s0.word >> (2 * n) : s0.word);
+      const uint32_t* d = conn + (size_t)P.elems[st[t].second] * nloc;
+      int l[4] = {0, 1, 2, 3};
+      if (n < 4)
+        for (int i = 0; i < n; i++) l[i] = (s0.word >> (2 * i)) & 3;
+      const uint32_t va = d[l[0]];
+      if (E.type == 0) {
+        put2(va, va, 0);
+      } else if (E.type == 1) {
+        const uint32_t vb = d[l[1]];
+        put2(va, vb, 1);
+        if (p2) {
+          const uint32_t eab = d[4 + EIDX[l[0]][l[1]]];
+          put2(va, eab, 2);
+          put2(vb, eab, 3);
+          put2(eab, eab, 4);
+        }
+      } else if (E.type == 2) {
+        const uint32_t vb = d[l[1]], vc = d[l[2]];
+        const uint32_t eab = d[4 + EIDX[l[0]][l[1]]], eac = d[4 + EIDX[l[0]][l[2]]], ebc = d[4 + EIDX[l[1]][l[2]]];
+        put2(vc, eab, 5);
+        put2(vb, eac, 6);
+        put2(va, ebc, 7);
+        put2(eab, eac, 8);
+        put2(eab, ebc, 9);
+        put2(eac, ebc, 10);
+      } else {
+        const uint32_t eab = d[4 + EIDX[l[0]][l[1]]], eac = d[4 + EIDX[l[0]][l[2]]], ead = d[4 + EIDX[l[0]][l[3]]];
+        const uint32_t ebc = d[4 + EIDX[l[1]][l[2]]], ebd = d[4 + EIDX[l[1]][l[3]]], ecd = d[4 + EIDX[l[2]][l[3]]];
+        put2(eab, ecd, 11);
+        put2(eac, ebd, 12);
+        put2(ead, ebc, 13);
+      }
+      enz_ptr[ei + 1] = (int32_t)enz.size();
+    }
+  }
+  // ---- groups of 32 lanes of one type.  Which 16 simplices share a half-warp is fixed by the order above; their lanes inside the
+  // half-warp are chosen greedily so that the record entries one half-warp of the store pass reads (hc) fall into different
+  // shared-memory bank pairs: occ[half][bank] counts the entries placed so far.  WAE_STAR_NO_LANE_OPT=1 keeps the plain order.
+  static const bool lane_opt = getenv("WAE_STAR_NO_LANE_OPT") == nullptr;
+  std::vector<uint8_t> occ(n_half * 32, 0);  // [half][0..15] K entries, [half][16..31] M entries
   O.grp.clear();
   O.cnt.clear();
   O.src.clear();
@@ -171,16 +259,51 @@ static void build_patch(const uint32_t* conn, int nloc, const Pattern& P, const 
     O.cnt.resize(O.cnt.size() + 32, 0);
     O.grp.push_back((uint32_t)sb);
     O.grp.push_back((uint32_t)rows | ((uint32_t)type << 16) | ((uint32_t)niter << 24));
-    for (size_t l = 0; i + l < j; l++) {
-      Ent& E = ent[by[i + l]];
-      E.slot = rows * WAE_STAR_RS + (int)(l * split);
-      const int q = (E.cnt + split - 1) / split;  // sources per lane of a split star
-      for (int sl = 0; sl < split; sl++) {
-        const int k0 = sl * q, k1 = std::min(E.cnt, k0 + q), lane = (int)(l * split) + sl;
-        O.cnt[O.cnt.size() - 32 + lane] = (uint8_t)std::max(0, k1 - k0);
-        for (int k = k0; k < k1; k++) {
-          if (src[E.first + k].word > 0xFFFFu) O.bad |= 1;
-          O.src[sb + (size_t)32 * (k - k0) + lane] = (uint16_t)src[E.first + k].word;
+    for (int half = 0; half < 2; half++) {
+      const size_t h0 = i + (size_t)half * (per / 2), h1 = std::min(j, h0 + per / 2);
+      bool used[16] = {false};
+      // simplices with many nonzeros choose first
+      std::vector<size_t> ord;
+      for (size_t x = h0; x < h1; x++) ord.push_back(x);
+      std::stable_sort(ord.begin(), ord.end(), [&](size_t x, size_t y) {
+        return enz_ptr[by[x] + 1] - enz_ptr[by[x]] > enz_ptr[by[y] + 1] - enz_ptr[by[y]];
+      });
+      for (size_t x : ord) {
+        const int ei = by[x];
+        Ent& E = ent[ei];
+        int best = -1;
+        long bestc = 0;
+        for (int r = 0; r < 16; r += split) {
+          if (used[r]) continue;
+          if (!lane_opt) {
+            if (r == (int)((x - h0) * split)) best = r;
+            continue;
+          }
+          long cst = 0;
+          for (int32_t q = enz_ptr[ei]; q < enz_ptr[ei + 1]; q++) {
+            const int role = enz[q].second;
+            const uint8_t* oc = &occ[(size_t)hc[enz[q].first] * 32];
+            cst += oc[((rows + star_krow(nloc, role)) * WAE_STAR_RS + r) & 15] + oc[16 + (((rows + star_mrow(nloc, role)) * WAE_STAR_RS + r) & 15)];
+          }
+          if (best < 0 || cst < bestc) best = r, bestc = cst;
+        }
+        used[best] = true;
+        const int lane0 = 16 * half + best;
+        E.slot = rows * WAE_STAR_RS + lane0;
+        for (int32_t q = enz_ptr[ei]; q < enz_ptr[ei + 1]; q++) {
+          const int role = enz[q].second;
+          uint8_t* oc = &occ[(size_t)hc[enz[q].first] * 32];
+          oc[((rows + star_krow(nloc, role)) * WAE_STAR_RS + lane0) & 15]++;
+          oc[16 + (((rows + star_mrow(nloc, role)) * WAE_STAR_RS + lane0) & 15)]++;
+        }
+        const int q = (E.cnt + split - 1) / split;  // sources per lane of a split star
+        for (int sl = 0; sl < split; sl++) {
+          const int k0 = sl * q, k1 = std::min(E.cnt, k0 + q), lane = lane0 + sl;
+          O.cnt[O.cnt.size() - 32 + lane] = (uint8_t)std::max(0, k1 - k0);
+          for (int k = k0; k < k1; k++) {
+            if (src[E.first + k].word > 0xFFFFu) O.bad |= 1;
+            O.src[sb + (size_t)32 * (k - k0) + lane] = (uint16_t)src[E.first + k].word;
+          }
         }
       }
     }
@@ -189,82 +312,17 @@ static void build_patch(const uint32_t* conn, int nloc, const Pattern& P, const 
   }
   O.rows = rows;
   if (rows * WAE_STAR_RS > 8192) O.bad |= 8;  // 13 bits of a code word name the record entry
-  // store program: owned columns by DOF number
-  std::vector<int32_t> cols(hi - lo);
-  for (int32_t q = lo; q < hi; q++) cols[q - lo] = order[q];
-  std::sort(cols.begin(), cols.end());
-  std::vector<int64_t> coloff(cols.size() + 1, 0);
-  for (size_t c = 0; c < cols.size(); c++) coloff[c + 1] = coloff[c] + (P.colptr[cols[c] + 1] - P.colptr[cols[c]]);
-  std::vector<uint16_t> flat((size_t)coloff.back(), 0xFFFF);
-  auto put = [&](uint32_t prow, uint32_t qcol, int slot_, int role) {
-    if (!owned(qcol)) return;
-    const size_t c = std::lower_bound(cols.begin(), cols.end(), (int32_t)qcol) - cols.begin();
-    const int32_t* b = P.rowval.data() + P.colptr[qcol];
-    const int32_t* e = P.rowval.data() + P.colptr[qcol + 1];
-    const int32_t* it = std::lower_bound(b, e, (int32_t)prow);
-    if (it == e || *it != (int32_t)prow) { O.bad |= 16; return; }
-    uint16_t& f = flat[(size_t)coloff[c] + (it - b)];
-    if (f != 0xFFFF) O.bad |= 32;
-    f = (uint16_t)(((slot_ + WAE_STAR_RS * star_krow(nloc, role)) << 3) | (star_mrow(nloc, role) - star_krow(nloc, role)));
-  };
-  auto put2 = [&](uint32_t p_, uint32_t q_, int slot_, int role) {
-    put(p_, q_, slot_, role);
-    if (p_ != q_) put(q_, p_, slot_, role);
-  };
-  for (const Ent& E : ent) {
-    const Src& s0 = src[E.first];
-    const int n = E.type + 1;
-    const int t = (int)(n < 4 ? s0.word >> (2 * n) : s0.word);
-    const uint32_t* d = conn + (size_t)P.elems[st[t].second] * nloc;
-    int l[4] = {0, 1, 2, 3};
-    if (n < 4)
-      for (int i = 0; i < n; i++) l[i] = (s0.word >> (2 * i)) & 3;
-    const uint32_t va = d[l[0]];
-    if (E.type == 0) {
-      put2(va, va, E.slot, 0);
-    } else if (E.type == 1) {
-      const uint32_t vb = d[l[1]];
-      put2(va, vb, E.slot, 1);
-      if (p2) {
-        const uint32_t eab = d[4 + EIDX[l[0]][l[1]]];
-        put2(va, eab, E.slot, 2);
-        put2(vb, eab, E.slot, 3);
-        put2(eab, eab, E.slot, 4);
-      }
-    } else if (E.type == 2) {
-      const uint32_t vb = d[l[1]], vc = d[l[2]];
-      const uint32_t eab = d[4 + EIDX[l[0]][l[1]]], eac = d[4 + EIDX[l[0]][l[2]]], ebc = d[4 + EIDX[l[1]][l[2]]];
-      put2(vc, eab, E.slot, 5);
-      put2(vb, eac, E.slot, 6);
-      put2(va, ebc, E.slot, 7);
-      put2(eab, eac, E.slot, 8);
-      put2(eab, ebc, E.slot, 9);
-      put2(eac, ebc, E.slot, 10);
-    } else {
-      const uint32_t eab = d[4 + EIDX[l[0]][l[1]]], eac = d[4 + EIDX[l[0]][l[2]]], ead = d[4 + EIDX[l[0]][l[3]]];
-      const uint32_t ebc = d[4 + EIDX[l[1]][l[2]]], ebd = d[4 + EIDX[l[1]][l[3]]], ecd = d[4 + EIDX[l[2]][l[3]]];
-      put2(eab, ecd, E.slot, 11);
-      put2(eac, ebd, E.slot, 12);
-      put2(ead, ebc, E.slot, 13);
+  // ---- codes, in the order of the owned nonzeros
+  O.code.assign(nnz_own, (uint16_t)0xFFFF);
+  for (size_t ei = 0; ei < ent.size(); ei++)
+    for (int32_t q = enz_ptr[ei]; q < enz_ptr[ei + 1]; q++) {
+      const int role = enz[q].second;
+      uint16_t& f = O.code[enz[q].first];
+      if (f != 0xFFFF) O.bad |= 32;
+      f = (uint16_t)(((ent[ei].slot + WAE_STAR_RS * star_krow(nloc, role)) << 3) | (star_mrow(nloc, role) - star_krow(nloc, role)));
     }
-  }
-  O.chunk.clear();
-  O.code.clear();
-  for (size_t c = 0; c < cols.size(); c++) {
-    const int32_t j = cols[c];
-    for (int64_t z = P.colptr[j]; z < P.colptr[j + 1]; z++) {
-      const uint16_t f = flat[(size_t)coloff[c] + (z - P.colptr[j])];
-      if (f == 0xFFFF) O.bad |= 64;
-      const size_t nc = O.chunk.size();
-      if (nc && O.chunk[nc - 2] + (O.chunk[nc - 1] & 63u) == (uint32_t)z && (z & 31) != 0)
-        O.chunk[nc - 1]++;
-      else {
-        O.chunk.push_back((uint32_t)z);
-        O.chunk.push_back(1u | ((uint32_t)O.code.size() << 6));
-      }
-      O.code.push_back(f);
-    }
-  }
+  for (uint16_t f : O.code)
+    if (f == 0xFFFF) O.bad |= 64;
   while ((O.chunk.size() / 2) & 3) {  // the store pass takes four chunks per warp step
     O.chunk.push_back(0u);
     O.chunk.push_back(0u);

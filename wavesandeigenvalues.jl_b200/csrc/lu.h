@@ -63,6 +63,7 @@ struct LuSolver {
   DevBuf<int32_t> d_flag;              // device-side status (bad pivot)
   int work_nrhs = 0;
   bool factored = false;
+  bool check_singular = true;          // raise WAE_E_SINGULAR on an exactly zero pivot (wae_lu_factor_ex with check = 0 clears it)
   bool sym_mode = false;               // last factorisation used the symmetric elimination
   // rank-k correction A = S + sum_j f_j s_j g_j^T (flame terms) on top of the symmetric factorisation of S
   int r1_k = 0;
@@ -84,6 +85,12 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
 // X <- (LU)^-1 X (tt = 0) or (LU)^-T X (tt = 1): factors only, no rank-k correction, no refinement
 void wae_lu_base_solve(wae_ctx* h, LuSolver& S, int tt, int nrhs, cplx* d_X);
 // X (n x nrhs, column-major, device) <- op(A)^{-1} X; trans: 0 N, 1 T, 2 C
-void wae_lu_solve_device(wae_ctx* h, LuSolver& S, int trans, int nrhs, cplx* d_X, int refine);
+// Beyn: A_p += w z^p x for p < n_mom, fused into the last kernel of the solve (A: dim x nrhs x n_mom complex on the device)
+struct LuMomentEpilogue {
+  int n_mom;
+  cplx w, z;
+  cplx* A;
+};
+void wae_lu_solve_device(wae_ctx* h, LuSolver& S, int trans, int nrhs, cplx* d_X, int refine, const LuMomentEpilogue* ep = nullptr);
 // X2 (n x 2): column 0 <- A^{-1} x0, column 1 <- A^{-H} x1 in one pass over a symmetric-mode factor (no refinement)
 void wae_lu_solve_pair_device(wae_ctx* h, LuSolver& S, cplx* d_X2);

@@ -1,11 +1,18 @@
 // C-ABI entry points for the sparse LU, the shift-invert Arnoldi eigensolver and the Beyn
 // moment accumulation (see include/wae_b200.h).
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <cmath>
 #include <complex>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
 
 #include "lu.h"
 
@@ -444,17 +451,24 @@ int32_t wae_lu_free(wae_ctx* h, int32_t lu_id) {
   WAE_API_END
 }
 
-int32_t wae_lu_factor(wae_ctx* h, int32_t lu_id, int32_t slot) {
+int32_t wae_lu_factor_ex(wae_ctx* h, int32_t lu_id, int32_t slot, int32_t check) {
   WAE_API_BEGIN
   CUDA_CHECK(cudaSetDevice(h->device));
   LuSolver& S = get_lu(h, lu_id);
   Family& F = h->fam(S.fam);
   if (slot < 0 || slot >= WAE_FAMILY_SLOTS || !F.slot[slot].p) WAE_THROW(WAE_E_INVALID, "family slot %d is empty", slot);
+  struct Restore {  // the flag is a property of this call only
+    LuSolver& S;
+    ~Restore() { S.check_singular = true; }
+  } restore{S};
+  S.check_singular = check != 0;
   PhaseTimer t(h, "factor");
   factor_slot(h, S, F, slot);
   t.stop();
   WAE_API_END
 }
+
+int32_t wae_lu_factor(wae_ctx* h, int32_t lu_id, int32_t slot) { return wae_lu_factor_ex(h, lu_id, slot, 1); }
 
 int32_t wae_lu_solve(wae_ctx* h, int32_t lu_id, int32_t trans, int32_t nrhs, double* X) {
   WAE_API_BEGIN
@@ -791,15 +805,15 @@ int32_t wae_eigs_si(wae_ctx* h, int32_t lu_id, int32_t fam_id, int32_t m_slot, i
   WAE_API_END
 }
 
-int32_t wae_beyn_moments(wae_ctx* h, int32_t fam_id, int32_t lu_id, int32_t n_nodes, const double* z, const double* w,
-                         const double* coeffs, int32_t l, int32_t n_mom, const double* V, void* A_out) {
-  WAE_API_BEGIN
+// The node loop of one device: combine -> factorise -> solve l right-hand sides -> moments (in the solve's last kernel).  Throws.
+static void beyn_moments_device(wae_ctx* h, int32_t fam_id, int32_t lu_id, int32_t n_nodes, const double* z, const double* w,
+                                const double* coeffs, int32_t l, int32_t n_mom, const double* V, cplx* A_out) {
   CUDA_CHECK(cudaSetDevice(h->device));
   LuSolver& S = get_lu(h, lu_id);
   Family& F = h->fam(fam_id);
   if (fam_id != S.fam) WAE_THROW(WAE_E_INVALID, "the LU belongs to another family");
   const int64_t n = S.sym.n;
-  if (n_nodes < 0 || !z || !w || !coeffs || l < 1 || l > n || n_mom < 1 || !A_out) WAE_THROW(WAE_E_INVALID, "bad Beyn arguments");
+  if (n_nodes < 0 || (n_nodes && (!z || !w || !coeffs)) || l < 1 || l > n || n_mom < 1 || !A_out) WAE_THROW(WAE_E_INVALID, "bad Beyn arguments");
   cudaStream_t st = h->stream;
   DevBuf<cplx>& X = S.d_io;
   X.reserve((size_t)n * l);
@@ -819,16 +833,150 @@ int32_t wae_beyn_moments(wae_ctx* h, int32_t fam_id, int32_t lu_id, int32_t n_no
       CUDA_CHECK(cudaMemcpyAsync(X.p, S.d_arn_V.p, (size_t)n * l * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
     else
       identity_cols_kernel<<<(unsigned)(((size_t)n * l + 255) / 256), 256, 0, st>>>(n, l, X.p);
-    wae_lu_solve_device(h, S, 0, l, X.p, S.refine_steps);
-    moment_accum_kernel<<<(unsigned)(((size_t)n * l + 255) / 256), 256, 0, st>>>(X.p, n * l, n_mom, make_double2(w[2 * j], w[2 * j + 1]),
-                                                                                 make_double2(z[2 * j], z[2 * j + 1]), (cplx*)A_out);
-    h->launches += 2;
+    const LuMomentEpilogue ep{n_mom, make_double2(w[2 * j], w[2 * j + 1]), make_double2(z[2 * j], z[2 * j + 1]), A_out};
+    wae_lu_solve_device(h, S, 0, l, X.p, S.refine_steps, &ep);
+    h->launches += 1;
     t.stop();
     t_sol += h->last_ms["solve"];
   }
   h->last_ms["beyn_factor_total"] = t_fac;
   h->last_ms["beyn_solve_total"] = t_sol;
   CUDA_CHECK(cudaStreamSynchronize(st));
+}
+
+int32_t wae_beyn_moments(wae_ctx* h, int32_t fam_id, int32_t lu_id, int32_t n_nodes, const double* z, const double* w,
+                         const double* coeffs, int32_t l, int32_t n_mom, const double* V, void* A_out) {
+  WAE_API_BEGIN
+  beyn_moments_device(h, fam_id, lu_id, n_nodes, z, w, coeffs, l, n_mom, V, (cplx*)A_out);
+  WAE_API_END
+}
+
+// ---- all GPUs of the box from ONE host process (the reference's beyn is one process, one loop over all nodes: beyn.jl:34-74,112-138)
+// NCCL is loaded at run time (libnccl.so.2, or the library named by WAE_NCCL_LIB): libwae_b200.so has no link-time dependency on it, and
+// a single-GPU caller never touches it.
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  std::map<std::vector<int>, std::vector<ncclComm_t>> comms;  // one communicator set per device list, kept for the process lifetime
+  std::mutex mu;
+};
+NcclApi& nccl_api() {
+  static NcclApi api;
+  std::lock_guard<std::mutex> lock(api.mu);
+  if (api.lib) return api;
+  const char* names[] = {getenv("WAE_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names)
+    if (nm && *nm && (api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL))) break;
+  if (!api.lib) WAE_THROW(WAE_E_CUDA, "NCCL not found (libnccl.so.2; set WAE_NCCL_LIB): %s", dlerror());
+  auto sym = [&](const char* nm) {
+    void* f = dlsym(api.lib, nm);
+    if (!f) WAE_THROW(WAE_E_CUDA, "NCCL symbol %s missing", nm);
+    return f;
+  };
+  api.CommInitAll = (decltype(api.CommInitAll))sym("ncclCommInitAll");
+  api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+  api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+  api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+  api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
+  api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+  return api;
+}
+#define NCCL_CHECK(api, x)                                                                                   \
+  do {                                                                                                       \
+    ncclResult_t _r = (x);                                                                                   \
+    if (_r != ncclSuccess) WAE_THROW(WAE_E_CUDA, "%s failed: %s", #x, (api).GetErrorString(_r));             \
+  } while (0)
+}  // namespace
+
+int32_t wae_beyn_moments_multi(int32_t n_ctx, wae_ctx* const* hs, const int32_t* fam_ids, const int32_t* lu_ids, int32_t n_nodes,
+                               const double* z, const double* w, const double* coeffs, int32_t l, int32_t n_mom, const double* V,
+                               double* A_out) {
+  if (n_ctx < 1 || !hs || !hs[0]) return WAE_E_INVALID;
+  wae_ctx* h = hs[0];
+  WAE_API_BEGIN
+  if (!fam_ids || !lu_ids || n_nodes < 0 || !A_out) WAE_THROW(WAE_E_INVALID, "bad Beyn arguments");
+  int64_t n = -1;
+  int n_terms = -1;
+  std::vector<int> devs(n_ctx);
+  for (int r = 0; r < n_ctx; r++) {
+    if (!hs[r]) WAE_THROW(WAE_E_INVALID, "context %d is NULL", r);
+    LuSolver& S = get_lu(hs[r], lu_ids[r]);
+    Family& F = hs[r]->fam(fam_ids[r]);
+    if (r == 0) n = S.sym.n, n_terms = F.n_terms;
+    if (S.sym.n != n || F.n_terms != n_terms) WAE_THROW(WAE_E_INVALID, "context %d holds a different family (dimension / number of terms)", r);
+    devs[r] = hs[r]->device;
+    for (int q = 0; q < r; q++)
+      if (devs[q] == devs[r]) WAE_THROW(WAE_E_INVALID, "contexts %d and %d sit on the same device", q, r);
+  }
+  const size_t total = (size_t)n * l * n_mom;
+  // quadrature node j -> context j mod n_ctx, every context accumulates its own partial moments
+  std::vector<std::vector<double>> zr(n_ctx), wr(n_ctx), cr(n_ctx);
+  for (int j = 0; j < n_nodes; j++) {
+    const int r = j % n_ctx;
+    zr[r].insert(zr[r].end(), z + 2 * j, z + 2 * j + 2);
+    wr[r].insert(wr[r].end(), w + 2 * j, w + 2 * j + 2);
+    cr[r].insert(cr[r].end(), coeffs + 2 * (size_t)j * n_terms, coeffs + 2 * (size_t)(j + 1) * n_terms);
+  }
+  std::vector<DevBuf<cplx>> A(n_ctx);
+  std::vector<WaeError> errs(n_ctx, WaeError{WAE_OK, ""});
+  {
+    std::vector<std::thread> th;
+    for (int r = 0; r < n_ctx; r++)
+      th.emplace_back([&, r]() {
+        try {
+          CUDA_CHECK(cudaSetDevice(hs[r]->device));
+          A[r].alloc(total);
+          CUDA_CHECK(cudaMemsetAsync(A[r].p, 0, total * sizeof(cplx), hs[r]->stream));
+          beyn_moments_device(hs[r], fam_ids[r], lu_ids[r], (int32_t)(zr[r].size() / 2), zr[r].data(), wr[r].data(), cr[r].data(), l, n_mom, V, A[r].p);
+        } catch (const WaeError& e) {
+          errs[r] = e;
+        } catch (const std::exception& e) {
+          errs[r] = WaeError{WAE_E_INVALID, e.what()};
+        }
+      });
+    for (auto& t : th) t.join();
+  }
+  for (int r = 0; r < n_ctx; r++)
+    if (errs[r].code != WAE_OK) {
+      hs[r]->err = errs[r].msg;
+      throw WaeError{errs[r].code, "device " + std::to_string(devs[r]) + ": " + errs[r].msg};
+    }
+  if (n_ctx > 1) {  // one all-reduce of the 2K x l x d complex moment tensor over NVLink
+    NcclApi& api = nccl_api();
+    std::vector<ncclComm_t>* comm;
+    {
+      std::lock_guard<std::mutex> lock(api.mu);
+      auto it = api.comms.find(devs);
+      if (it == api.comms.end()) {
+        std::vector<ncclComm_t> c(n_ctx);
+        NCCL_CHECK(api, api.CommInitAll(c.data(), n_ctx, devs.data()));
+        it = api.comms.emplace(devs, c).first;
+      }
+      comm = &it->second;
+    }
+    NCCL_CHECK(api, api.GroupStart());
+    for (int r = 0; r < n_ctx; r++)
+      NCCL_CHECK(api, api.AllReduce(A[r].p, A[r].p, 2 * total, ncclDouble, ncclSum, (*comm)[r], hs[r]->stream));
+    NCCL_CHECK(api, api.GroupEnd());
+    for (int r = 0; r < n_ctx; r++) {
+      CUDA_CHECK(cudaSetDevice(hs[r]->device));
+      CUDA_CHECK(cudaStreamSynchronize(hs[r]->stream));
+    }
+  }
+  CUDA_CHECK(cudaSetDevice(h->device));
+  CUDA_CHECK(cudaMemcpyAsync(A_out, A[0].p, total * sizeof(cplx), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_CHECK(cudaStreamSynchronize(h->stream));
+  for (int r = 0; r < n_ctx; r++) {  // device buffers are released on their own device
+    cudaSetDevice(hs[r]->device);
+    A[r].release();
+  }
+  cudaSetDevice(h->device);
   WAE_API_END
 }
 

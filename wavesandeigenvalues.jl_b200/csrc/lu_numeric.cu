@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(NB * NB) lu_diag_kernel(LuDev D, const int32_t
       if (!(m >= eps * eps)) {  // tiny, zero or NaN pivot -> static pivoting
         if (!isfinite(m)) atomicOr(flag, 2);
         else atomicAdd(flag + 1, 1);
+        if (m == 0.0) atomicOr(flag, 4);  // an exactly zero pivot: structurally / exactly singular for an LU without row exchanges
         T[p][p] = make_double2(m > 0.0 && isfinite(m) ? d.x * eps / sqrt(m) : eps, m > 0.0 && isfinite(m) ? d.y * eps / sqrt(m) : 0.0);
       }
     }
@@ -944,6 +945,14 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
     WAE_THROW(WAE_E_SINGULAR, "non-finite pivot in the numeric factorisation");
   }
   h->last_ms["static_pivots"] = flag[1];
+  h->last_ms["zero_pivots"] = (flag[0] & 4) ? 1.0 : 0.0;
+  // UMFPACK (the reference's lu / factorize) raises SingularException on an exactly singular matrix; here an exactly zero pivot is the
+  // case the static perturbation cannot repair (the solves would return garbage).  perturb's lu(...; check=false) of the deliberately
+  // singular L(0,0) (perturbation.jl:329) goes through wae_lu_factor_ex(check = 0).
+  if ((flag[0] & 4) && S.check_singular) {
+    S.factored = false;
+    WAE_THROW(WAE_E_SINGULAR, "exactly zero pivot in the numeric factorisation (%d perturbed pivots): the matrix is singular for an LU without row exchanges", flag[1]);
+  }
 }
 
 template <int NR>
@@ -1133,7 +1142,26 @@ void wae_lu_solve_pair_device(wae_ctx* h, LuSolver& S, cplx* d_X2) {
   CUDA_CHECK(cudaGetLastError());
 }
 
-void wae_lu_solve_device(wae_ctx* h, LuSolver& S, int trans, int nrhs, cplx* d_X, int refine) {
+// x <- x + r, and with it the Beyn moments A_p += w z^p x (the epilogue of the last refinement step of a quadrature node's solve)
+__global__ void add_moment_kernel(const cplx* __restrict__ r, int64_t total, cplx* __restrict__ x, int n_mom, cplx w, cplx z, cplx* __restrict__ A) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  cplx v = x[i];
+  if (r) {
+    v.x += r[i].x;
+    v.y += r[i].y;
+    x[i] = v;
+  }
+  cplx f = w;
+  for (int p = 0; p < n_mom; p++) {
+    cplx* a = A + (size_t)p * total + i;
+    a->x += f.x * v.x - f.y * v.y;
+    a->y += f.x * v.y + f.y * v.x;
+    f = make_double2(f.x * z.x - f.y * z.y, f.x * z.y + f.y * z.x);
+  }
+}
+
+void wae_lu_solve_device(wae_ctx* h, LuSolver& S, int trans, int nrhs, cplx* d_X, int refine, const LuMomentEpilogue* ep) {
   Family& F = h->fam(S.fam);
   if (!S.factored) WAE_THROW(WAE_E_INVALID, "wae_lu_factor has not been called (or failed)");
   const int64_t n = S.sym.n;
@@ -1152,8 +1180,15 @@ void wae_lu_solve_device(wae_ctx* h, LuSolver& S, int trans, int nrhs, cplx* d_X
     wae_spmm_values(h, F, S.d_Aval.p, trans, nrhs, d_X, res);
     lu_residual_kernel<<<gt, 256, 0, st>>>(b0, n * nrhs, res);
     lu_apply_inverse(h, S, trans, nrhs, res);
-    add_kernel<<<gt, 256, 0, st>>>(res, n * nrhs, d_X);
+    if (ep && it == refine - 1)
+      add_moment_kernel<<<gt, 256, 0, st>>>(res, n * nrhs, d_X, ep->n_mom, ep->w, ep->z, ep->A);
+    else
+      add_kernel<<<gt, 256, 0, st>>>(res, n * nrhs, d_X);
     h->launches += 2;
+  }
+  if (ep && refine <= 0) {
+    add_moment_kernel<<<gt, 256, 0, st>>>(nullptr, n * nrhs, d_X, ep->n_mom, ep->w, ep->z, ep->A);
+    h->launches++;
   }
   CUDA_CHECK(cudaGetLastError());
 }

@@ -517,6 +517,8 @@ int32_t wae_mat_set(wae_ctx* h, int64_t dim, const int64_t* colptr, const int64_
   for (int64_t j = 0; j <= dim; j++) P.colptr[j] = colptr[j] - h->base;
   P.nnz = P.colptr[dim];
   if (P.colptr[0] != 0 || P.nnz < 0 || P.nnz >= ((int64_t)1 << 31)) WAE_THROW(WAE_E_INVALID, "bad colptr");
+  for (int64_t j = 0; j < dim; j++)  // monotone and inside [0, nnz]: the row loop below indexes rowval with it
+    if (P.colptr[j] < 0 || P.colptr[j] > P.colptr[j + 1] || P.colptr[j + 1] > P.nnz) WAE_THROW(WAE_E_INVALID, "colptr must be non-decreasing (column %lld)", (long long)j);
   P.rowval.resize(P.nnz);
   for (int64_t j = 0; j < dim; j++)
     for (int64_t k = P.colptr[j]; k < P.colptr[j + 1]; k++) {
@@ -551,6 +553,10 @@ int32_t wae_mat_set(wae_ctx* h, int64_t dim, const int64_t* colptr, const int64_
 int32_t wae_mat_free(wae_ctx* h, int32_t mat_id) {
   WAE_API_BEGIN
   h->mat(mat_id);
+  for (size_t f = 0; f < h->fams.size(); f++)
+    if (h->fams[f])
+      for (int m : h->fams[f]->mats)
+        if (m == mat_id) WAE_THROW(WAE_E_INVALID, "matrix %d is still a term of family %d (wae_family_free first)", mat_id, (int)f);
   CUDA_CHECK(cudaStreamSynchronize(h->stream));
   h->mats[mat_id].reset();
   WAE_API_END

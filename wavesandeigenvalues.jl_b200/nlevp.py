@@ -373,6 +373,13 @@ class _DeviceFamily:
             self.ctx.family_free(self.fid)
             self.fid = None
 
+    def __del__(self):  # a dropped family returns its device storage (the reference relies on Julia's GC for the same objects)
+        try:
+            if getattr(self.ctx, "h", None):
+                self.free()
+        except Exception:  # noqa: BLE001 -- interpreter shutdown, context already destroyed
+            pass
+
 
 class LinearOperatorFamily:
     """LinOpFam.jl:131-186.  First parameter = eigenvalue, last = auxiliary eigenvalue."""
@@ -390,7 +397,7 @@ class LinearOperatorFamily:
 
     # -- push! (LinOpFam.jl:305-346) -------------------------------------------------------------
     def push(self, T):
-        self._dev = None
+        self.release()  # the device side (value slots, term maps, LU factors: 23 GB at config 2) belongs to the old term list
         for idx, t in enumerate(self.terms):
             if (t.func, t.params) == (T.func, T.params):
                 coeff = t.coeff + T.coeff
@@ -569,7 +576,7 @@ def perturb(L, N, v0, v0Adj):
             if lu is None:
                 L(0, 0).materialize(3)
                 lu = L.device().lu()
-                ctx.lu_factor(lu, 3)
+                ctx.lu_factor(lu, 3, check=False)  # lu(L(0,0), check=false): the operator is singular by construction
             vk = ctx.lu_solve(lu, -(r + lam[k] * L10v0))
             v[k] = vk - np.vdot(v0, vk) * v0
     return lam, v
@@ -599,7 +606,7 @@ def perturb_disk(L, N, v0, v0Adj, weighted=False):
     v[0] = v0
     L(0, 0).materialize(3)
     lu = dv.lu()
-    ctx.lu_factor(lu, 3)
+    ctx.lu_factor(lu, 3, check=False)  # lu(L(0,0), check=false), perturbation.jl:385,493: singular by construction
     for k in range(1, N + 1):
         w = {(0, n): v[k - n].copy() for n in range(1, k + 1)}
         for W in range(1, k + 1):
@@ -832,6 +839,15 @@ def _iterate(L, z, maxiter, tol, relax, order, nev, v0, v0_adj, kind, num_order,
         L.params[L.eigval] = z
         if output:
             print("Error occured:", e)
+    except _lib.WaeError as e:
+        # any other failure of the device path (CUDA error, out of memory, invalid argument): as the reference's catch-all
+        # (Householder.jl:131-149, iterative_solvers.jl:192-210) the solver state is restored and the flag is "unknown"
+        err = "unknown"
+        L.params[L.eigval] = z
+        L.active, L.mode = active, mode
+        if output:
+            print("Error occured:", e)
+        return Solution(L.params, v0, v0_adj, L.eigval), n, z, z0, lam, err
     if err is None:
         L.params[L.eigval] = z
         if output:
@@ -856,6 +872,8 @@ def householder(L, z, maxiter=10, tol=0.0, relax=1.0, lam_tol=float("inf"), orde
         flag = -4
     elif err == "singular":
         flag = -6
+    elif err == "unknown":
+        flag = -2
     elif n >= maxiter:
         flag = -1
     elif abs(lam) <= lam_tol:
@@ -890,6 +908,8 @@ def mslp(L, z, maxiter=10, tol=0.0, relax=1.0, lam_tol=float("inf"), order=1, ne
         flag = itsol_arpack_exception
     elif err == "singular":
         flag = itsol_singular_exception
+    elif err == "unknown":
+        flag = itsol_unknown
     elif n >= maxiter:
         flag = itsol_maxiter
     elif abs(lam) <= lam_tol:
@@ -948,19 +968,36 @@ def allreduce_moments(A, group=None):
     return A
 
 
-def compute_moment_matrices(L, G, l=5, K=1, N=16, group=None, stats=None, V=None):
+def compute_moment_matrices(L, G, l=5, K=1, N=16, group=None, stats=None, V=None, replicas=None):
     """Moments A_p = sum_j w_j z_j^p L(z_j)^{-1} V, p < 2K, V = first l identity columns (beyn.jl:62-74).
 
     The quadrature nodes are sharded round-robin over the ranks of ``group`` (torch.distributed, NCCL):
     each GPU factorises its own nodes, the moments are summed with one all-reduce.  Returns a (d, l, 2K)
-    complex numpy array (on every rank)."""
-    import torch
-    import torch.distributed as dist
+    complex numpy array (on every rank).
+
+    ``replicas``: the same family discretised on OTHER devices of this process (``discretize(..., ctx=Context(dev))``): all nodes
+    are then run from this one process through wae_beyn_moments_multi -- node j on device j mod (1 + len(replicas)), one host
+    thread per device and one in-library ncclAllReduce -- which is how a single-process caller (the reference's Julia beyn) scales."""
     dev = L.device()
     ctx = dev.ctx
     d = dev.dim
     L(0)
     zs, ws = contour_nodes(G, N)
+    if replicas:
+        fams = [L] + list(replicas)
+        coeffs = np.zeros((len(zs), dev.n_flat), dtype=np.complex128)
+        for j in range(len(zs)):
+            L.params[L.eigval] = complex(zs[j])
+            coeffs[j] = dev.flat(L.scalars([0] * len(L.active)))
+        devs = [f.device() for f in fams]
+        A = _lib.Context.beyn_moments_multi([x.ctx for x in devs], [x.fid for x in devs], [x.lu() for x in devs], zs, ws, coeffs, l, 2 * K, d, V=V)
+        if stats is not None:
+            stats["factorizations"] = stats.get("factorizations", 0) + len(zs)
+            stats["factor_ms"] = stats.get("factor_ms", 0.0) + max(max(0.0, x.ctx.last_ms("beyn_factor_total")) for x in devs)
+            stats["solve_ms"] = stats.get("solve_ms", 0.0) + max(max(0.0, x.ctx.last_ms("beyn_solve_total")) for x in devs)
+        return np.ascontiguousarray(A)
+    import torch
+    import torch.distributed as dist
     rank, world = 0, 1
     if dist.is_available() and dist.is_initialized():
         rank, world = dist.get_rank(group), dist.get_world_size(group)
@@ -974,8 +1011,9 @@ def compute_moment_matrices(L, G, l=5, K=1, N=16, group=None, stats=None, V=None
         ctx.beyn_moments(dev.fid, dev.lu(), zs[mine], ws[mine], coeffs, l, 2 * K, A.data_ptr(), V=V)
     if stats is not None:
         stats["factorizations"] = stats.get("factorizations", 0) + len(mine)
-        stats["factor_ms"] = stats.get("factor_ms", 0.0) + ctx.last_ms("beyn_factor_total")
-        stats["solve_ms"] = stats.get("solve_ms", 0.0) + ctx.last_ms("beyn_solve_total")
+        if len(mine):  # (a rank without nodes has no timings: wae_last_ms answers -1)
+            stats["factor_ms"] = stats.get("factor_ms", 0.0) + max(0.0, ctx.last_ms("beyn_factor_total"))
+            stats["solve_ms"] = stats.get("solve_ms", 0.0) + max(0.0, ctx.last_ms("beyn_solve_total"))
     allreduce_moments(A, group)
     return A.permute(2, 1, 0).cpu().numpy()
 
@@ -1006,8 +1044,8 @@ def moments2eigs(A, G=None, tol=0.0, pos_test=True, output=False, rtol=0.0):
     return Om, P
 
 
-def beyn(L, G, l=5, K=1, N=16, tol=0.0, pos_test=True, output=True, random=False, group=None, stats=None, seed=0):
-    """beyn.jl:34-110.  N is the number of quadrature nodes PER polygon edge."""
+def beyn(L, G, l=5, K=1, N=16, tol=0.0, pos_test=True, output=True, random=False, group=None, stats=None, seed=0, replicas=None):
+    """beyn.jl:34-110.  N is the number of quadrature nodes PER polygon edge.  ``group`` / ``replicas``: see compute_moment_matrices."""
     d = L.size()
     K = max(K, l // d + int(l % d != 0))
     V = None
@@ -1016,7 +1054,7 @@ def beyn(L, G, l=5, K=1, N=16, tol=0.0, pos_test=True, output=True, random=False
         # sharded run draws the same V (and runs are reproducible)
         rng = np.random.default_rng(seed)
         V = rng.random((d, l)) + 1j * rng.random((d, l))
-    A = compute_moment_matrices(L, G, l=min(l, d), K=K, N=N, group=group, stats=stats, V=V)
+    A = compute_moment_matrices(L, G, l=min(l, d), K=K, N=N, group=group, stats=stats, V=V, replicas=replicas)
     return moments2eigs(A, G, tol=tol, pos_test=pos_test, output=output)
 
 
