@@ -56,7 +56,8 @@ def test_beyn_config3_geometry_reduced():
     import wae_b200 as W
     from oracle.helmholtz import discretize as odisc
     from oracle.mesh import Mesh as OMesh
-    from oracle.nlevp import beyn as obeyn
+    from oracle.nlevp import beyn_moments as omoments
+    from oracle.nlevp import moments2eigs as om2e
     mesh = _cylinder(W, (4, 4, 32))
     c = np.full(len(mesh.tetrahedra), 347.2)
     dscrp = {"Interior": ("interior", ()), "Outlet": ("admittance", ("Y", 1e15))}
@@ -67,10 +68,15 @@ def test_beyn_config3_geometry_reduced():
     Lo = odisc(mo, dscrp, np.full(len(mo.tetrahedra), 347.2), order="quad")
     assert Lo.size() == Lg.size() == 9 * 9 * 65
     G = [z * 2 * math.pi for z in (50 + 100j, 50 - 100j, 500 - 100j, 500 + 100j)]
-    Oo, _ = obeyn(Lo, G, l=8, K=1, N=6, tol=1e-8)
-    Og, _ = W.beyn(Lg, G, l=8, K=1, N=6, tol=1e-8, output=False)
+    Ao = omoments(Lo, G, 8, 1, 6)
+    Ag = W.compute_moment_matrices(Lg, G, l=8, K=1, N=6)
+    assert np.abs(Ag - Ao).max() <= 1e-9 * np.abs(Ao).max()
+    # the first l identity columns probe one corner of the mesh (beyn.jl:45-48), where the duct modes are small: the eigenvalues are
+    # extracted from singular values ~1e-6 below the largest, which amplifies the 1e-10 agreement of the moments
+    Oo = om2e(Ao, G, 8, 1, 1e-8, True)[0]
+    Og, _ = W.moments2eigs(Ag, G, tol=1e-8, pos_test=True)
     assert len(Og) == len(Oo) == 3   # quarter-wave modes of the closed-open duct: 86.8, 260.4, 434 Hz
-    assert np.abs(np.sort_complex(Og) - np.sort_complex(Oo)).max() <= 1e-7 * np.abs(Oo).max()
+    assert np.abs(np.sort_complex(Og) - np.sort_complex(Oo)).max() <= 1e-5 * np.abs(Oo).max()
     for om in Og:
         sol, n, flag = W.householder(Lg, om, maxiter=8, tol=1e-9 * abs(om), output=False)
         assert flag >= 0 and abs(sol.params["ω"] - om) <= 1e-4 * abs(om)
