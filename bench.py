@@ -34,7 +34,28 @@ import sys
 import tempfile
 import time
 
-import numpy as np
+
+def _pin_rank_to_cores():
+    """N replicas share one host: give every rank its own core set and cap the BLAS / OpenMP pools to it BEFORE numpy, scipy and torch
+    start their thread pools (round 1: 8 unpinned ranks with 16-thread pools each lost 35 % at N = 8 without a single collective)."""
+    try:
+        local, world = int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("LOCAL_WORLD_SIZE", os.environ.get("WORLD_SIZE", "1")))
+        cores = sorted(os.sched_getaffinity(0))
+        if world > 1 and len(cores) >= world:
+            per = len(cores) // world
+            mine = cores[local * per:(local + 1) * per]
+            os.sched_setaffinity(0, mine)
+            for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+                os.environ[k] = str(max(1, len(mine)))
+            return len(mine)
+        return len(cores)
+    except (AttributeError, OSError, ValueError):
+        return None
+
+
+HOST_CORES_OF_RANK = _pin_rank_to_cores()
+
+import numpy as np  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -324,7 +345,6 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    pin_rank_to_cores(local, world)
     ctx = W.get_context(local)
     ctx.set_stream(torch.cuda.current_stream().cuda_stream)
     t_setup = time.perf_counter()
@@ -401,7 +421,8 @@ def main():
            "vs_baseline": None, "dtype": "c128", "data": "synthetic", "config": config,
            "details": {"tets": ntet, "dofs": dv.dim, "nnz": dv.nnz, "factor_nnz": dv.lu_nnz, "factor_flops": dv.lu_flops, "setup_s_not_timed": t_setup,
                        "omega": [omega.real, omega.imag], "timed_region_wall_s": t_region,
-                       "timed_region": "value and e2e steps alternate; ms_per_step = sum of the value steps' CUDA-event times / steps (max over ranks)"},
+                       "timed_region": "value and e2e steps alternate; ms_per_step = sum of the value steps' CUDA-event times / steps (max over ranks)",
+                       "host_cores_of_this_rank": HOST_CORES_OF_RANK},
            "e2e": {"value": value_e2e, "unit": "eigenpairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                    "ms_per_step": ms_e2e / args.steps},
            "gpu_launches": int(launches), "clocks": clocks}
@@ -471,17 +492,6 @@ def main():
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
-
-
-def pin_rank_to_cores(local, world):
-    """One core set per rank (N replicas share the host: without this the ranks' Python threads migrate and collide)."""
-    try:
-        cores = sorted(os.sched_getaffinity(0))
-        if world > 1 and len(cores) >= 2 * world:
-            per = len(cores) // world
-            os.sched_setaffinity(0, cores[local * per:(local + 1) * per])
-    except (AttributeError, OSError):
-        pass
 
 
 def same_problem_leg(W, ctx0, sample, st_cpu):
