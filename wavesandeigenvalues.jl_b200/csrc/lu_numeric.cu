@@ -16,6 +16,8 @@
 // pivoting) and the solve applies iterative refinement against the original matrix.
 #include <cuda_runtime.h>
 
+#include <array>
+
 #include <algorithm>
 
 #include "lu.h"
@@ -868,14 +870,43 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
       lu_gemm_kernel<0><<<g, 256, 0, st>>>(D, lst, mode, k0, kw, c0, cap, upd_, flag);
   };
   const int upd_flag = (sym ? 1 : 0) | ((getenv("WAE_LU_SKIP_UPPER") && !atoi(getenv("WAE_LU_SKIP_UPPER"))) ? 0 : 2);  // pivot-block updates only; default: skip
+  // WAE_LU_TRACE=1 (diagnostic): every launch class is timed with its own pair of events (serialising the stream) and summed per tree
+  // depth; the table goes to stderr and the totals to wae_last_ms("lu_trace_<class>")
+  const bool trace = getenv("WAE_LU_TRACE") != nullptr;
+  enum { T_MEMSET, T_XADD, T_DIAG, T_COPY, T_PANEL, T_GIN, T_GOUT, T_SCHUR, T_N };
+  static const char* tname[T_N] = {"memset", "extend_add", "diag", "sym_copy", "panel", "gemm_inner", "gemm_outer", "gemm_schur"};
+  std::vector<std::array<double, T_N>> tms(maxd + 1);
+  for (auto& a : tms) a.fill(0.0);
+  cudaEvent_t te0 = nullptr, te1 = nullptr;
+  if (trace) {
+    CUDA_CHECK(cudaEventCreate(&te0));
+    CUDA_CHECK(cudaEventCreate(&te1));
+  }
+  int cur_d = maxd;
+  auto timed = [&](int cls, auto&& launch) {
+    if (!trace) {
+      launch();
+      return;
+    }
+    cudaEventRecord(te0, st);
+    launch();
+    cudaEventRecord(te1, st);
+    cudaEventSynchronize(te1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, te0, te1);
+    tms[cur_d][cls] += ms;
+  };
   for (int d = maxd; d >= 0; d--) {
+    cur_d = d;
     const std::vector<int32_t>& L = Y.levels[d];
     const int nl = (int)L.size();
     cplx* upd = S.d_upd[d & 1].p;
-    if (Y.level_upd_size[d]) CUDA_CHECK(cudaMemsetAsync(upd, 0, (size_t)Y.level_upd_size[d] * sizeof(cplx), st));
+    if (Y.level_upd_size[d]) timed(T_MEMSET, [&] { CUDA_CHECK(cudaMemsetAsync(upd, 0, (size_t)Y.level_upd_size[d] * sizeof(cplx), st)); });
     if (d < maxd && S.xa_tiles[d + 1] > 0) {
-      lu_extend_add_kernel<<<S.xa_tiles[d + 1], dim3(32, 8), 0, st>>>(D, S.d_level[d + 1].p, S.d_xa_tile_ptr[d + 1].p,
-                                                                        (int)Y.levels[d + 1].size(), S.d_upd[(d + 1) & 1].p, upd, sym);
+      timed(T_XADD, [&] {
+        lu_extend_add_kernel<<<S.xa_tiles[d + 1], dim3(32, 8), 0, st>>>(D, S.d_level[d + 1].p, S.d_xa_tile_ptr[d + 1].p,
+                                                                          (int)Y.levels[d + 1].size(), S.d_upd[(d + 1) & 1].p, upd, sym);
+      });
       h->launches++;
     }
     // blocked partial factorisation of all fronts of this depth
@@ -895,30 +926,34 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
       for (int z0 = 0; z0 < cnt; z0 += 32768) {
         int zc = std::min(32768, cnt - z0);
         const int32_t* lst = S.d_level[d].p + z0;
-        lu_diag_kernel<<<zc, dim3(NB, NB), 0, st>>>(D, lst, k, S.pivot_eps, S.d_flag.p);
+        timed(T_DIAG, [&] { lu_diag_kernel<<<zc, dim3(NB, NB), 0, st>>>(D, lst, k, S.pivot_eps, S.d_flag.p); });
         int rows = max_ld - k * NB - 1;  // upper bound of ld - (c0 + nb) over the batch (nb >= 1)
         if (rows > 0) {
           if (sym) {
-            lu_sym_copy_kernel<<<dim3((rows + 127) / 128, 1, zc), 128, 0, st>>>(D, lst, k);
+            timed(T_COPY, [&] { lu_sym_copy_kernel<<<dim3((rows + 127) / 128, 1, zc), 128, 0, st>>>(D, lst, k); });
             h->launches++;
           }
-          lu_panel_kernel<<<dim3((rows + 127) / 128, 2, zc), 128, 0, st>>>(D, lst, k);
+          timed(T_PANEL, [&] { lu_panel_kernel<<<dim3((rows + 127) / 128, 2, zc), 128, 0, st>>>(D, lst, k); });
           // inner update: columns of the current outer block only
           const int c0 = (k + 1) * NB;
           const int oend = (k / nbo_blocks + 1) * nbo_blocks * NB;  // end column of the outer block
           int tn = std::min(max_s, oend) - c0;
           if (tn > 0) {
             dim3 g((max_ld - c0 + GT - 1) / GT, (tn + GT - 1) / GT, zc);
-            gemm(g, lst, 0, k * NB, NB, c0, oend, nullptr, upd_flag);
-            if (!sym) gemm(g, lst, 1, k * NB, NB, c0, oend, nullptr, upd_flag);
+            timed(T_GIN, [&] {
+              gemm(g, lst, 0, k * NB, NB, c0, oend, nullptr, upd_flag);
+              if (!sym) gemm(g, lst, 1, k * NB, NB, c0, oend, nullptr, upd_flag);
+            });
             h->launches += sym ? 1 : 2;
           }
           // outer update once the outer block is complete
           if (c0 == oend && max_s > oend) {
             const int o0 = oend - nbo_blocks * NB;
             dim3 g((max_ld - oend + GT - 1) / GT, (max_s - oend + GT - 1) / GT, zc);
-            gemm(g, lst, 0, o0, oend - o0, oend, 1 << 30, nullptr, upd_flag);
-            if (!sym) gemm(g, lst, 1, o0, oend - o0, oend, 1 << 30, nullptr, upd_flag);
+            timed(T_GOUT, [&] {
+              gemm(g, lst, 0, o0, oend - o0, oend, 1 << 30, nullptr, upd_flag);
+              if (!sym) gemm(g, lst, 1, o0, oend - o0, oend, 1 << 30, nullptr, upd_flag);
+            });
             h->launches += sym ? 1 : 2;
           }
           h->launches++;
@@ -930,10 +965,38 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
       for (int z0 = 0; z0 < nl; z0 += 32768) {
         int zc = std::min(32768, nl - z0);
         dim3 g((max_r + GT - 1) / GT, (max_r + GT - 1) / GT, zc);
-        gemm(g, S.d_level[d].p + z0, 2, 0, 0, 0, 0, upd, sym);
+        timed(T_SCHUR, [&] { gemm(g, S.d_level[d].p + z0, 2, 0, 0, 0, 0, upd, sym); });
         h->launches++;
       }
     }
+  }
+  if (trace) {
+    std::array<double, T_N> tot;
+    tot.fill(0.0);
+    fprintf(stderr, "[wae lu trace] depth  fronts  max_s  max_r ");
+    for (int c = 0; c < T_N; c++) fprintf(stderr, " %10s", tname[c]);
+    fprintf(stderr, "   (ms)\n");
+    for (int d = maxd; d >= 0; d--) {
+      int max_s = 0, max_r = 0;
+      for (int32_t k : Y.levels[d]) {
+        max_s = std::max(max_s, (int)(Y.sn_first[k + 1] - Y.sn_first[k]));
+        max_r = std::max(max_r, (int)(Y.struct_ptr[k + 1] - Y.struct_ptr[k]));
+      }
+      fprintf(stderr, "[wae lu trace] %5d %7d %6d %6d ", d, (int)Y.levels[d].size(), max_s, max_r);
+      for (int c = 0; c < T_N; c++) {
+        fprintf(stderr, " %10.3f", tms[d][c]);
+        tot[c] += tms[d][c];
+      }
+      fprintf(stderr, "\n");
+    }
+    fprintf(stderr, "[wae lu trace] total                      ");
+    for (int c = 0; c < T_N; c++) {
+      fprintf(stderr, " %10.3f", tot[c]);
+      h->last_ms[std::string("lu_trace_") + tname[c]] = tot[c];
+    }
+    fprintf(stderr, "\n");
+    cudaEventDestroy(te0);
+    cudaEventDestroy(te1);
   }
   CUDA_CHECK(cudaGetLastError());
   int32_t flag[2] = {0, 0};
@@ -965,7 +1028,31 @@ static void lu_sweeps_nr(wae_ctx* h, LuSolver& S, int trans_t, int nrhs, cplx* y
   const int tri_pf = (getenv("WAE_LU_SOLVE_PF") && atoi(getenv("WAE_LU_SOLVE_PF"))) ? 2 : 0;  // bit 1 of the tri kernels' use_up: L2 prefetch hint
   const int zr = (nrhs + NR - 1) / NR;
   const int W = LU_SOLVE_W;
+  // WAE_LU_TRACE=2 (diagnostic): the four kernel classes of a sweep pair timed per tree depth with their own events (serialising)
+  const bool trace = getenv("WAE_LU_TRACE") && atoi(getenv("WAE_LU_TRACE")) == 2;
+  std::vector<std::array<double, 4>> tms(maxd + 1);
+  for (auto& a : tms) a.fill(0.0);
+  cudaEvent_t te0 = nullptr, te1 = nullptr;
+  if (trace) {
+    CUDA_CHECK(cudaEventCreate(&te0));
+    CUDA_CHECK(cudaEventCreate(&te1));
+  }
+  int cur_d = 0;
+  auto timed = [&](int cls, auto&& launch) {
+    if (!trace) {
+      launch();
+      return;
+    }
+    cudaEventRecord(te0, st);
+    launch();
+    cudaEventRecord(te1, st);
+    cudaEventSynchronize(te1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, te0, te1);
+    tms[cur_d][cls] += ms;
+  };
   for (int d = maxd; d >= 0; d--) {
+    cur_d = d;
     const std::vector<int32_t>& L = Y.levels[d];
     int max_s = 0, max_ld = 0;
     for (int32_t k : L) {
@@ -977,18 +1064,19 @@ static void lu_sweeps_nr(wae_ctx* h, LuSolver& S, int trans_t, int nrhs, cplx* y
       const int zc = std::min<int>(32768, (int)L.size() - z0);
       const int32_t* lst = S.d_level[d].p + z0;
       for (int c_lo = 0; c_lo < max_s; c_lo += W) {
-        lu_fwd_tri_kernel<<<dim3(zc, nrhs), 1024, 0, st>>>(D, lst, fwd_up | tri_pf, c_lo, Y.n, y);
+        timed(0, [&] { lu_fwd_tri_kernel<<<dim3(zc, nrhs), 1024, 0, st>>>(D, lst, fwd_up | tri_pf, c_lo, Y.n, y); });
         h->launches++;
         const int rows = max_ld - std::min(c_lo + W, max_s);  // upper bound of the rows below the window over the level
         if (max_ld > c_lo + 1 && rows + W > 0) {
           const int rmax = max_ld - c_lo;  // a supernode with a short pivot block has its window end (and first row) earlier
-          lu_fwd_update_kernel<NR><<<dim3((rmax + 63) / 64, zc, zr), 256, 0, st>>>(D, lst, fwd_up, c_lo, nrhs, Y.n, y);
+          timed(1, [&] { lu_fwd_update_kernel<NR><<<dim3((rmax + 63) / 64, zc, zr), 256, 0, st>>>(D, lst, fwd_up, c_lo, nrhs, Y.n, y); });
           h->launches++;
         }
       }
     }
   }
   for (int d = 0; d <= maxd; d++) {
+    cur_d = d;
     const std::vector<int32_t>& L = Y.levels[d];
     int max_s = 0, max_ld = 0;
     for (int32_t k : L) {
@@ -1007,13 +1095,31 @@ static void lu_sweeps_nr(wae_ctx* h, LuSolver& S, int trans_t, int nrhs, cplx* y
           int row_chunk = rmax;
           if (zc * ncg < 4 * h->sm_count) row_chunk = std::max(256, (int)((int64_t)rmax * zc * ncg / (4 * h->sm_count)) / 32 * 32 + 32);
           const int nrc = (rmax + row_chunk - 1) / row_chunk;
-          lu_bwd_update_kernel<NR><<<dim3(ncg * nrc, zc, zr), 256, 0, st>>>(D, lst, !fwd_up, c_lo, ncg, row_chunk, nrhs, Y.n, y);
+          timed(2, [&] { lu_bwd_update_kernel<NR><<<dim3(ncg * nrc, zc, zr), 256, 0, st>>>(D, lst, !fwd_up, c_lo, ncg, row_chunk, nrhs, Y.n, y); });
           h->launches++;
         }
-        lu_bwd_tri_kernel<<<dim3(zc, nrhs), 1024, 0, st>>>(D, lst, (int)!fwd_up | tri_pf, c_lo, Y.n, y);
+        timed(3, [&] { lu_bwd_tri_kernel<<<dim3(zc, nrhs), 1024, 0, st>>>(D, lst, (int)!fwd_up | tri_pf, c_lo, Y.n, y); });
         h->launches++;
       }
     }
+  }
+  if (trace) {
+    double tot[4] = {0, 0, 0, 0};
+    fprintf(stderr, "[wae solve trace] nrhs %d  depth  fronts  max_s  max_ld    fwd_tri   fwd_upd   bwd_upd   bwd_tri (ms)\n", nrhs);
+    for (int d = maxd; d >= 0; d--) {
+      int max_s = 0, max_ld = 0;
+      for (int32_t k : Y.levels[d]) {
+        const int s = Y.sn_first[k + 1] - Y.sn_first[k];
+        max_s = std::max(max_s, s);
+        max_ld = std::max(max_ld, s + (int)(Y.struct_ptr[k + 1] - Y.struct_ptr[k]));
+      }
+      fprintf(stderr, "[wae solve trace]         %5d %7d %6d %7d  %9.3f %9.3f %9.3f %9.3f\n", d, (int)Y.levels[d].size(), max_s, max_ld, tms[d][0], tms[d][1],
+              tms[d][2], tms[d][3]);
+      for (int c = 0; c < 4; c++) tot[c] += tms[d][c];
+    }
+    fprintf(stderr, "[wae solve trace] total                              %9.3f %9.3f %9.3f %9.3f\n", tot[0], tot[1], tot[2], tot[3]);
+    cudaEventDestroy(te0);
+    cudaEventDestroy(te1);
   }
 }
 
