@@ -137,32 +137,63 @@ __global__ void __launch_bounds__(256) lu_extend_add_kernel(LuDev D, const int32
 }
 
 // ---- step k, part 1: LU of the NB x NB diagonal block (no pivoting, static perturbation) ------------
+// One thread per entry, ONE barrier per pivot: every thread forms its multiplier l_i = T[i][p] / pivot itself from the unscaled column
+// (the owner of L[i][p] stores it one barrier later, when nobody reads column p any more), and the same row operations are applied to
+// an identity block in the same step, which yields L^-1 for free (Gauss-Jordan).  U^-1 follows from a second sweep (columns last to
+// first, again one barrier each).  Both inverses are kept for the triangular solves (a block step there is a matrix-vector product).
 __global__ void __launch_bounds__(NB * NB) lu_diag_kernel(LuDev D, const int32_t* __restrict__ list, int k, double eps, int* __restrict__ flag) {
   SnView S = sn_view(D, list[blockIdx.x]);
   const int c0 = k * NB;
   if (c0 >= S.s) return;
   const int nb = min(NB, S.s - c0);
-  __shared__ cplx T[NB][NB + 1];
+  __shared__ cplx T[NB][NB + 1];  // in place: strict lower = L, upper incl. diagonal = U
+  __shared__ cplx X[NB][NB + 1];  // strict lower = L^-1 (unit diagonal implied), upper incl. diagonal = U^-1
+  __shared__ cplx piv[NB];        // pivots after the static perturbation
   const int i = threadIdx.x, j = threadIdx.y;  // element (row i, col j)
+  const cplx zero = make_double2(0.0, 0.0), one = make_double2(1.0, 0.0);
   cplx* blk = S.lp + c0 + (size_t)c0 * S.ld;
-  if (i < nb && j < nb) T[i][j] = blk[i + (size_t)j * S.ld];
+  T[i][j] = (i < nb && j < nb) ? blk[i + (size_t)j * S.ld] : (i == j ? one : zero);  // identity padding of a short last block
+  X[i][j] = i == j ? one : zero;
   __syncthreads();
+  cplx lown = zero;
   for (int p = 0; p < nb; p++) {
-    if (i == 0 && j == 0) {
-      cplx d = T[p][p];
-      double m = d.x * d.x + d.y * d.y;
-      if (!(m >= eps * eps)) {  // tiny, zero or NaN pivot -> static pivoting
+    cplx d = T[p][p];
+    const double m = d.x * d.x + d.y * d.y;
+    if (!(m >= eps * eps)) {  // tiny, zero or NaN pivot -> static pivoting (every thread derives the same replacement)
+      if (i == p && j == p) {
         if (!isfinite(m)) atomicOr(flag, 2);
         else atomicAdd(flag + 1, 1);
         if (m == 0.0) atomicOr(flag, 4);  // an exactly zero pivot: structurally / exactly singular for an LU without row exchanges
-        T[p][p] = make_double2(m > 0.0 && isfinite(m) ? d.x * eps / sqrt(m) : eps, m > 0.0 && isfinite(m) ? d.y * eps / sqrt(m) : 0.0);
       }
+      d = make_double2(m > 0.0 && isfinite(m) ? d.x * eps / sqrt(m) : eps, m > 0.0 && isfinite(m) ? d.y * eps / sqrt(m) : 0.0);
+    }
+    if (i == p && j == p) piv[p] = d;
+    if (i > p) {
+      const cplx l = cmul(T[i][p], cinv(d));
+      if (j > p)
+        T[i][j] = csub(T[i][j], cmul(l, T[p][j]));
+      else if (j == p) {
+        lown = l;
+        X[i][p] = make_double2(-l.x, -l.y);  // row i of the identity block minus l times row p (unit diagonal)
+      } else
+        X[i][j] = csub(X[i][j], cmul(l, X[p][j]));
     }
     __syncthreads();
-    cplx ip = cinv(T[p][p]);
-    if (j == p && i > p && i < nb) T[i][p] = cmul(T[i][p], ip);
-    __syncthreads();
-    if (i > p && j > p && i < nb && j < nb) T[i][j] = csub(T[i][j], cmul(T[i][p], T[p][j]));
+    if (j == p && i > p) T[i][p] = lown;  // column p is not read any more
+  }
+  if (i == j && i < nb) T[i][i] = piv[i];
+  __syncthreads();
+  // U^-1 by Gauss-Jordan from the last column to the first: row p of the right-hand block is final up to the division by the pivot when
+  // column p is eliminated; the rows above use the unscaled row and the (unchanged) entries U[i][p]
+  cplx uown = zero;  // entry (i, j), i <= j, of U^-1: final at step p = i (row p itself stays unscaled in shared memory)
+  for (int p = nb - 1; p >= 0; p--) {
+    if (j >= p && i <= p) {
+      const cplx xp = cmul(X[p][j], cinv(T[p][p]));  // final entry (p, j) of U^-1
+      if (i == p)
+        uown = xp;
+      else
+        X[i][j] = csub(X[i][j], cmul(T[i][p], xp));
+    }
     __syncthreads();
   }
   if (i < nb && j < nb) {
@@ -170,33 +201,12 @@ __global__ void __launch_bounds__(NB * NB) lu_diag_kernel(LuDev D, const int32_t
     // U_kk^T into the U^T panel (lower triangle incl. diagonal)
     if (i >= j) S.up[(c0 + i) + (size_t)(c0 + j) * S.ld] = T[j][i];
   }
-  // explicit inverses of the two triangular factors (used by the solves): thread (c,0) builds column c of L^-1 by
-  // forward substitution, thread (c,1) column c of U^-1 by back substitution; stored NB x NB column-major, zero padded
-  // (both triangles share one array: strict lower = L^-1 (unit diagonal implied), upper incl. diagonal = U^-1)
-  __shared__ cplx X[NB][NB + 1];
-  X[i][j] = make_double2(0.0, 0.0);
-  __syncthreads();
-  if (j == 0 && i < nb) {
-    const int c = i;
-    for (int r = c + 1; r < nb; r++) {
-      cplx acc = make_double2(-T[r][c].x, -T[r][c].y);  // m = c term: X[c][c] = 1
-      for (int m = c + 1; m < r; m++) acc = csub(acc, cmul(T[r][m], X[m][c]));
-      X[r][c] = acc;
-    }
-  } else if (j == 1 && i < nb) {
-    const int c = i;
-    X[c][c] = cinv(T[c][c]);
-    for (int r = c - 1; r >= 0; r--) {
-      cplx acc = make_double2(0.0, 0.0);
-      for (int m = r + 1; m <= c; m++) acc = csub(acc, cmul(T[r][m], X[m][c]));
-      X[r][c] = cmul(acc, cinv(T[r][r]));
-    }
-  }
-  __syncthreads();
+  // stored NB x NB column-major, zero padded (both triangles share one array: strict lower = L^-1 (unit diagonal implied), upper incl.
+  // diagonal = U^-1)
   cplx* inv = D.dinv + D.dinv_off[list[blockIdx.x]] + (size_t)k * 2 * NB * NB;
-  const cplx zero = make_double2(0.0, 0.0), one = make_double2(1.0, 0.0);
-  inv[i + j * NB] = i > j ? X[i][j] : (i == j && i < nb ? one : zero);
-  inv[NB * NB + i + j * NB] = i <= j ? X[i][j] : zero;
+  const bool in = i < nb && j < nb;
+  inv[i + j * NB] = i > j ? (in ? X[i][j] : zero) : (i == j && i < nb ? one : zero);
+  inv[NB * NB + i + j * NB] = (i <= j && in) ? uown : zero;
 }
 
 // ---- step k, part 2: panel solves below the diagonal block -------------------------------------------
@@ -217,7 +227,9 @@ __global__ void __launch_bounds__(128) lu_sym_copy_kernel(LuDev D, const int32_t
   for (int j = 0; j < nb; j++) dst[(size_t)j * S.ld] = src[(size_t)j * S.ld];
 }
 
-__global__ void __launch_bounds__(128) lu_panel_kernel(LuDev D, const int32_t* __restrict__ list, int k) {
+// sym_scale != 0 (symmetric elimination, grid.y == 1): U = D L^T, so the U^T-panel rows are the solved L-panel rows with column j scaled
+// by the pivot U_jj -- no copy of the unsolved rows and no second triangular solve.
+__global__ void __launch_bounds__(128) lu_panel_kernel(LuDev D, const int32_t* __restrict__ list, int k, int sym_scale) {
   SnView S = sn_view(D, list[blockIdx.z]);
   const int c0 = k * NB;
   if (c0 >= S.s) return;
@@ -227,13 +239,16 @@ __global__ void __launch_bounds__(128) lu_panel_kernel(LuDev D, const int32_t* _
   if ((int)(blockIdx.x * 128) >= nrows) return;
   const bool upper = blockIdx.y == 1;  // 0: Lp with U_kk, 1: Up with L_kk^T
   __shared__ cplx T[NB][NB + 1];       // T[m][j] = coefficient multiplying x_m in the equation of x_j
-  __shared__ cplx idiag[NB];
+  __shared__ cplx idiag[NB], diag[NB];
   const cplx* blk = S.lp + c0 + (size_t)c0 * S.ld;
   for (int e = threadIdx.x; e < NB * NB; e += 128) {
     int m = e % NB, j = e / NB;
     if (m < nb && j < nb) T[m][j] = upper ? blk[j + (size_t)m * S.ld] /* L[j][m] */ : blk[m + (size_t)j * S.ld] /* U[m][j] */;
   }
-  if (threadIdx.x < nb) idiag[threadIdx.x] = upper ? make_double2(1.0, 0.0) : cinv(blk[threadIdx.x + (size_t)threadIdx.x * S.ld]);
+  if (threadIdx.x < nb) {
+    diag[threadIdx.x] = blk[threadIdx.x + (size_t)threadIdx.x * S.ld];
+    idiag[threadIdx.x] = upper ? make_double2(1.0, 0.0) : cinv(diag[threadIdx.x]);
+  }
   __syncthreads();
   const int row = blockIdx.x * 128 + threadIdx.x;
   if (row >= nrows) return;
@@ -253,6 +268,12 @@ __global__ void __launch_bounds__(128) lu_panel_kernel(LuDev D, const int32_t* _
 #pragma unroll
   for (int j = 0; j < NB; j++)
     if (j < nb) base[(size_t)j * S.ld] = x[j];
+  if (sym_scale) {
+    cplx* ub = S.up + (r0 + row) + (size_t)c0 * S.ld;
+#pragma unroll
+    for (int j = 0; j < NB; j++)
+      if (j < nb) ub[(size_t)j * S.ld] = cmul(x[j], diag[j]);
+  }
 }
 
 // ---- complex GEMM  C -= A * B^T  on the FP64 tensor cores -----------------------------------------------
@@ -870,6 +891,8 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
       lu_gemm_kernel<0><<<g, 256, 0, st>>>(D, lst, mode, k0, kw, c0, cap, upd_, flag);
   };
   const int upd_flag = (sym ? 1 : 0) | ((getenv("WAE_LU_SKIP_UPPER") && !atoi(getenv("WAE_LU_SKIP_UPPER"))) ? 0 : 2);  // pivot-block updates only; default: skip
+  // symmetric elimination: U^T panel = L panel * D inside the panel kernel (WAE_LU_SYM_PANEL=0: round-1 path, copy + second solve)
+  const bool sym_panel = !(getenv("WAE_LU_SYM_PANEL") && !atoi(getenv("WAE_LU_SYM_PANEL")));
   // WAE_LU_TRACE=1 (diagnostic): every launch class is timed with its own pair of events (serialising the stream) and summed per tree
   // depth; the table goes to stderr and the totals to wae_last_ms("lu_trace_<class>")
   const bool trace = getenv("WAE_LU_TRACE") != nullptr;
@@ -929,11 +952,12 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
         timed(T_DIAG, [&] { lu_diag_kernel<<<zc, dim3(NB, NB), 0, st>>>(D, lst, k, S.pivot_eps, S.d_flag.p); });
         int rows = max_ld - k * NB - 1;  // upper bound of ld - (c0 + nb) over the batch (nb >= 1)
         if (rows > 0) {
-          if (sym) {
+          if (sym && !sym_panel) {
             timed(T_COPY, [&] { lu_sym_copy_kernel<<<dim3((rows + 127) / 128, 1, zc), 128, 0, st>>>(D, lst, k); });
             h->launches++;
           }
-          timed(T_PANEL, [&] { lu_panel_kernel<<<dim3((rows + 127) / 128, 2, zc), 128, 0, st>>>(D, lst, k); });
+          const int py = (sym && sym_panel) ? 1 : 2;
+          timed(T_PANEL, [&] { lu_panel_kernel<<<dim3((rows + 127) / 128, py, zc), 128, 0, st>>>(D, lst, k, py == 1); });
           // inner update: columns of the current outer block only
           const int c0 = (k + 1) * NB;
           const int oend = (k / nbo_blocks + 1) * nbo_blocks * NB;  // end column of the outer block
