@@ -562,7 +562,7 @@ def assembly_leg(W, ctx0, n, hbm, hbm_src):
             if old is not None:
                 os.environ["WAE_ASM_GEN"] = old
         return float(np.median(ms))
-    med = timed(None)
+    med = timed("3")
     prog = ctx.last_ms("star_program_bytes")
     layout = {k: ctx.last_ms("star_" + k) for k in ("patches", "staged", "simplices", "sources", "smem", "threads", "ctas_per_sm")}
     med2 = timed("2")

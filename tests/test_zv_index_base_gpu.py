@@ -56,8 +56,9 @@ def test_one_based_context(order):
             assert np.array_equal(a0 + 1, a1), key
     for key in ("M", "K", "C"):
         assert np.array_equal(res[0][key], res[1][key]), key
-    for key in ("Q", "x"):  # (the flame source is summed with atomics: equal to rounding, not bitwise)
-        assert np.abs(res[0][key] - res[1][key]).max() <= 1e-12 * np.abs(res[0][key]).max(), key
+    # (the flame source and the solve sweeps sum with atomics: equal to rounding -- times the condition number for x --, not bitwise)
+    assert np.abs(res[0]["Q"] - res[1]["Q"]).max() <= 1e-12 * np.abs(res[0]["Q"]).max()
+    assert np.abs(res[0]["x"] - res[1]["x"]).max() <= 1e-9 * np.abs(res[0]["x"]).max()
     # Julia's SparseMatrixCSC of the oracle's triplets: colptr and rowval as the reference holds them (1-based)
     mo = omesh.Mesh("m", scale=0.001, raw=raw)
     trip = {}

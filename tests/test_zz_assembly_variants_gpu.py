@@ -22,6 +22,7 @@ def test_variants_reproduce_the_default_kernel(order):
     try:
         for mesh in meshes:
             c = mesh.generate_field(speedofsound) if "Flame" in mesh.domains else np.full(len(mesh.tetrahedra), 340.0)
+            os.environ["WAE_ASM_GEN"] = "3"
             L = W.discretize(mesh, {"Interior": ("interior", ())}, c, order=order)
             ref = [t.coeff.csc()[2].copy() for t in L.terms]  # star kernel, default layout
             os.environ["WAE_ASM_GEN"] = "2"
@@ -32,7 +33,7 @@ def test_variants_reproduce_the_default_kernel(order):
                     v = t.coeff.csc()[2]
                     assert np.abs(v - r).max() <= 1e-12 * np.abs(r).max(), (var, t.operator)
             os.environ.pop("WAE_ASM_VARIANT", None)
-            os.environ.pop("WAE_ASM_GEN", None)
+            os.environ["WAE_ASM_GEN"] = "3"
             for smem, thr in (("230400", "1024"), ("76800", "256"), ("57344", "256"), ("114688", "512")):
                 os.environ["WAE_STAR_SMEM"], os.environ["WAE_STAR_THREADS"] = smem, thr
                 L.discretization.reassemble(c)  # a changed budget rebuilds the star program
@@ -43,7 +44,13 @@ def test_variants_reproduce_the_default_kernel(order):
             os.environ.pop("WAE_STAR_THREADS", None)
             L.discretization.reassemble(c)
             for t, r in zip(L.terms, ref):
-                assert np.array_equal(t.coeff.csc()[2], r)  # the default kernel is bit-reproducible
+                assert np.array_equal(t.coeff.csc()[2], r)  # the star kernel is bit-reproducible
+            os.environ.pop("WAE_ASM_GEN", None)  # the default generation of this element order (P2: stars, P1: pairs), twice
+            L.discretization.reassemble(c)
+            first = [t.coeff.csc()[2].copy() for t in L.terms]
+            L.discretization.reassemble(c)
+            for t, r in zip(L.terms, first):
+                assert np.array_equal(t.coeff.csc()[2], r)
     finally:
         for k in knobs:
             os.environ.pop(k, None)

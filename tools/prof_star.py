@@ -15,6 +15,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 order = sys.argv[2] if len(sys.argv) > 2 else "quad"
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
 phases = len(sys.argv) > 4
+os.environ["WAE_ASM_GEN"] = "3"
 mesh = W.kuhn_box((n, n, n), (0, 0, 0), (1, 1, 1), jitter=0.1, seed=7)
 tris, tets, dim = W.aggregate_elements(mesh, order)
 ctx = W.get_context()

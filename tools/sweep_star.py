@@ -48,7 +48,7 @@ def timed(label, extra=()):
 os.environ["WAE_ASM_GEN"] = "2"
 ref_row, ref = timed("pairs(gen2)")
 print(ref_row, flush=True)
-os.environ.pop("WAE_ASM_GEN")
+os.environ["WAE_ASM_GEN"] = "3"
 scale = (np.abs(ref[0]).max(), np.abs(ref[1]).max())
 rows = [ref_row]
 extra = ("star_patches", "star_staged", "star_program_bytes", "star_smem", "star_threads", "star_ctas_per_sm")

@@ -220,10 +220,12 @@ static int reuse_or_new_matrix(wae_ctx* h, const int32_t* mat_id, int pattern, b
   return new_matrix(h, pattern, is_complex, nnz, zero);
 }
 
-// M/K assembly kernel generation: 3 = star program (default), 2 = owner-computes pair program (WAE_ASM_GEN=2)
-static int asm_generation() {
+// M/K assembly kernel generation: 3 = star program (default for P2: 0.37 ms against 0.78 ms on the 64^3 box), 2 = owner-computes pair
+// program (default for P1, where the two are within 5 % and the pair program is slightly ahead); WAE_ASM_GEN=2|3 forces one
+static int asm_generation(const wae_ctx* h) {
   const char* env = getenv("WAE_ASM_GEN");
-  return env && atoi(env) == 2 ? 2 : 3;
+  if (env && (atoi(env) == 2 || atoi(env) == 3)) return atoi(env);
+  return h->nloc == 10 ? 3 : 2;
 }
 
 static void upload_c(wae_ctx* h, Pattern& P, const double* c, int c_per_elem, DevBuf<double>& d_c) {
@@ -242,7 +244,7 @@ int32_t wae_assemble(wae_ctx* h, int32_t pattern_id, int32_t kind, const double*
     WAE_THROW(WAE_E_INVALID, "operator kind %d does not match the pattern's element kind", kind);
   if (kind < WAE_OP_MASS || kind > WAE_OP_BOUNDARY) WAE_THROW(WAE_E_INVALID, "unknown operator kind %d", kind);
   const bool use_gather = kind == WAE_OP_MASS && !getenv("WAE_FORCE_ATOMIC");
-  const bool use_star = use_gather && asm_generation() == 3 && wae_ensure_star(h, P);
+  const bool use_star = use_gather && asm_generation(h) == 3 && wae_ensure_star(h, P);
   if (use_star) {
   } else if (use_gather) wae_ensure_gather(h, P); else ensure_slotmap(h, P);
   DevBuf<double> d_c;
@@ -278,7 +280,7 @@ int32_t wae_assemble_mk(wae_ctx* h, int32_t pattern_id, const double* c, int32_t
   const bool use_gather = c_per_elem == 1 && !getenv("WAE_FORCE_ATOMIC");
   int im = reuse_or_new_matrix(h, mass_id, pattern_id, false, P.nnz, !use_gather);
   int ik = reuse_or_new_matrix(h, stiff_id, pattern_id, false, P.nnz, !use_gather);
-  if (use_gather && asm_generation() == 3 && wae_ensure_star(h, P)) {
+  if (use_gather && asm_generation(h) == 3 && wae_ensure_star(h, P)) {
     PhaseTimer t(h, "assemble");
     wae_launch_assemble_star(h, P, d_c.p, h->mats[im]->d_val.p, h->mats[ik]->d_val.p, 1.0);
     t.stop();
