@@ -218,7 +218,7 @@ class Clocks:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         for line in self.f.read().splitlines():
             parts = [x.strip() for x in line.split(",")]
             if len(parts) < 7:
@@ -228,11 +228,16 @@ class Clocks:
                 mx.append(float(parts[1]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(parts[2]))
+            except ValueError:
+                pass
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         if sm:
-            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm),
+                   "sm_mhz_min": float(min(sm)), "power_w_median": float(np.median(pw)) if pw else None, "power_w_max": float(max(pw)) if pw else None}
         os.unlink(self.f.name)
         return out
 
@@ -284,6 +289,7 @@ def main():
     ap.add_argument("--assembly-cubes", type=int, default=64, help="n for the n^3-cube P2 assembly-only leg (0 = skip)")
     ap.add_argument("--cpu-sample", default="4,4,60", help="cubes of the bounded sample both CPU legs (and the GPU same-problem leg) run")
     ap.add_argument("--skip-extras", action="store_true")
+    ap.add_argument("--host-profile", action="store_true", help="one extra, untimed step under cProfile on rank 0: the host-side hot spots go to details.host_profile")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -361,12 +367,16 @@ def main():
     tol = 1e-9 * Z0
 
     def step(e2e, stats):
+        w0 = time.perf_counter()
         if e2e:
             ctx.mesh_update_points(pts_pinned.numpy())
         ms = disc.reassemble(c_pinned.numpy())
+        w1 = time.perf_counter()
         stats["assemble_ms"] = stats.get("assemble_ms", 0.0) + ms
         L.params["n"], L.params["τ"] = 1.0 + 0j, complex(tau)
         sol, n, flag = W.householder(L, Z0, maxiter=15, tol=tol, output=False, stats=stats)
+        stats["reassemble_wall_s"] = stats.get("reassemble_wall_s", 0.0) + w1 - w0
+        stats["householder_wall_s"] = stats.get("householder_wall_s", 0.0) + time.perf_counter() - w1
         stats["iterations"] = stats.get("iterations", 0) + n
         if flag < 0:
             raise RuntimeError(f"householder failed with flag {flag}")
@@ -376,12 +386,27 @@ def main():
         sol = step(False, {})
     omega = sol.params["ω"]
 
+    host_profile = None
+    if args.host_profile:
+        import cProfile
+        import io
+        import pstats
+        barrier()
+        pr = cProfile.Profile()
+        pr.enable()
+        step(False, {})
+        pr.disable()
+        barrier()
+        if rank == 0:
+            buf = io.StringIO()
+            pstats.Stats(pr, stream=buf).sort_stats("tottime").print_stats(18)
+            host_profile = [l.strip() for l in buf.getvalue().splitlines() if l.strip()][-20:]
     # value and e2e steps alternate inside ONE timed region; every step has its own pair of CUDA events
     stats, stats_e2e = {}, {}
     ms_plain = ms_e2e = 0.0
     launches = 0
     barrier()
-    clk = Clocks(local) if rank == 0 else None
+    clk = Clocks(local)  # every rank samples its own GPU (rank 0's record is the line's "clocks", all of them go to details.per_rank)
     t_region = time.perf_counter()
     for _ in range(args.steps):
         for e2e, st in ((False, stats), (True, stats_e2e)):
@@ -398,7 +423,16 @@ def main():
                 launches += ctx.launch_count() - l0
     barrier()
     t_region = time.perf_counter() - t_region
-    clocks = clk.stop() if clk else None
+    clocks = clk.stop()
+    per_rank = None
+    if world > 1:  # every rank's own step time and phase split (rank 0 prints them: which rank, and which phase, is the slow one)
+        mine = {"rank": rank, "ms_per_step": ms_plain / args.steps, "numeric_lu": stats["factor_ms"] / args.steps,
+                "eigs_wall": 1e3 * stats["eigs_wall_s"] / args.steps, "perturb_wall": 1e3 * stats.get("perturb_wall_s", 0.0) / args.steps,
+                "reassemble_wall": 1e3 * stats["reassemble_wall_s"] / args.steps, "householder_wall": 1e3 * stats["householder_wall_s"] / args.steps,
+                "cores": HOST_CORES_OF_RANK, "lu_tflops": (dv.lu_flops * (0.5 if ctx.last_ms("factor_sym") > 0.5 else 1.0)) * stats["factorizations"] / (stats["factor_ms"] * 1e-3) / 1e12,
+                "clocks": clocks}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
     ms, ms_e2e = max_over_ranks(ms_plain), max_over_ranks(ms_e2e)
     value = world * args.steps / (ms * 1e-3)
     value_e2e = world * args.steps / (ms_e2e * 1e-3)
@@ -413,7 +447,8 @@ def main():
     def phases(st):
         return {"assemble": st["assemble_ms"] / args.steps, "numeric_lu": st["factor_ms"] / args.steps,
                 "combine_factor_wall": 1e3 * st["combine_factor_wall_s"] / args.steps, "eigs_wall": 1e3 * st["eigs_wall_s"] / args.steps,
-                "perturb_wall": 1e3 * st.get("perturb_wall_s", 0.0) / args.steps, "iterations": st["iterations"] / args.steps,
+                "perturb_wall": 1e3 * st.get("perturb_wall_s", 0.0) / args.steps, "reassemble_wall": 1e3 * st["reassemble_wall_s"] / args.steps,
+                "householder_wall": 1e3 * st["householder_wall_s"] / args.steps, "iterations": st["iterations"] / args.steps,
                 "factorizations": st["factorizations"] / args.steps, "solves": st["solves"] / args.steps}
 
     out = {"metric": metric, "value": value, "unit": "eigenpairs/s", "n_gpus": world,
@@ -422,7 +457,7 @@ def main():
            "details": {"tets": ntet, "dofs": dv.dim, "nnz": dv.nnz, "factor_nnz": dv.lu_nnz, "factor_flops": dv.lu_flops, "setup_s_not_timed": t_setup,
                        "omega": [omega.real, omega.imag], "timed_region_wall_s": t_region,
                        "timed_region": "value and e2e steps alternate; ms_per_step = sum of the value steps' CUDA-event times / steps (max over ranks)",
-                       "host_cores_of_this_rank": HOST_CORES_OF_RANK},
+                       "host_cores_of_this_rank": HOST_CORES_OF_RANK, "per_rank": per_rank, "host_profile": host_profile},
            "e2e": {"value": value_e2e, "unit": "eigenpairs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                    "ms_per_step": ms_e2e / args.steps},
            "gpu_launches": int(launches), "clocks": clocks}
