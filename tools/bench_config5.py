@@ -49,8 +49,8 @@ tick("sparsity pattern (host symbolic)", t)
 rng = np.random.default_rng(7)
 c = rng.uniform(300, 700, ntet)
 t = time.time()
-im, ik = ctx.assemble_mk(pid, c)  # includes the one-off pair-program build
-tick("pair program (host symbolic) + first M,K assembly", t)
+im, ik = ctx.assemble_mk(pid, c)  # includes the one-off build of the assembly program (P2: star program)
+tick("assembly program (host symbolic) + first M,K assembly", t)
 ms = []
 for _ in range(reps):
     ctx.assemble_mk(pid, c, reuse=(im, ik))
@@ -60,7 +60,10 @@ alg_mk = ntet * (4 * 10 + 8) + 24 * npts + 2 * nnz * 8
 out.update({"tets": ntet, "dofs": int(dim), "points": int(npts), "nnz": int(nnz)})
 out["assemble_MK"] = {"kernel_ms": mk_ms, "all_ms": ms, "Mtets_per_s": ntet / mk_ms / 1e3, "algorithmic_GB": alg_mk / 1e9,
                       "achieved_GBs": alg_mk / mk_ms / 1e6, "frac_of_hbm": alg_mk / mk_ms / 1e6 / HBM,
-                      "kernel": "assemble_tet_pairs<10,3>"}
+                      "kernel": "assemble_tet_stars<10,3>" if ctx.last_ms("star_patches") > 0 else "assemble_tet_pairs<10,3>"}
+if ctx.last_ms("star_patches") > 0:
+    out["assemble_MK"]["star_layout"] = {k: ctx.last_ms("star_" + k) for k in ("patches", "staged", "simplices", "sources", "smem", "threads", "ctas_per_sm")}
+    out["assemble_MK"]["program_bytes_per_tet"] = ctx.last_ms("star_program_bytes") / ntet
 # boundary admittance: the z = 1 face ("Outlet"), per-triangle c = 500
 outlet = np.asarray(mesh.domains["Outlet"]["simplices"], dtype=np.int64)
 t = time.time()
