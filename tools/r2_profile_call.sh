@@ -6,13 +6,13 @@
 set -u
 mkdir -p gpurun_out
 B="python bench.py --steps 1 --warmup 3 --skip-extras"
-A="python tools/bench_assembly.py 64 quad 3"
+A="python tools/prof_star.py 64 quad 3"
 L="python tools/bench_lu.py 20 20 300 quad 1"
 $B > gpurun_out/r2p_bench_plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file gpurun_out/r2p_launches_bench.csv $B > gpurun_out/r2p_bench_ncu.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 3200 --csv --log-file gpurun_out/r2p_launches_bench.csv $B > gpurun_out/r2p_bench_ncu.log 2>&1
 echo "launch list exit $?"
 $A > gpurun_out/r2p_asm_plain.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:assemble_tet_pairs -s 2 -c 1 -f -o gpurun_out/r2p_asm $A > gpurun_out/r2p_asm_ncu.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:assemble_tet_stars -s 2 -c 1 -f -o gpurun_out/r2p_asm $A > gpurun_out/r2p_asm_ncu.log 2>&1
 echo "assembly capture exit $?"
 WAE_NFACTOR=1 WAE_PROBE_ONLY=1 $L > gpurun_out/r2p_lu_plain.log 2>&1 &&
 WAE_NFACTOR=1 WAE_PROBE_ONLY=1 ncu --set full --clock-control none --import-source on -k regex:lu_gemm_kernel -s 300 -c 3 -f -o gpurun_out/r2p_gemm $L > gpurun_out/r2p_lu_ncu.log 2>&1

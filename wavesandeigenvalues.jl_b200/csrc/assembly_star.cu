@@ -635,6 +635,9 @@ extern "C" int32_t wae_star_program_check(int32_t order, int64_t n_pts, const do
     }
     for (int i = 0; i < 4; i++) stats[8 + i] = (double)wf[i];  // shared-memory wavefronts of the gathers (simulated) and their conflict-free count
     return WAE_OK;
+  } catch (const WaeError& e) {
+    if (getenv("WAE_SYMB_TIMING")) fprintf(stderr, "[wae_star_program_check] %s\n", e.msg.c_str());
+    return e.code;
   } catch (...) {
     return WAE_E_INVALID;
   }

@@ -32,6 +32,9 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
+#include <mutex>
+#include <thread>
 
 #include "assembly_star.h"
 #include "wae_internal.h"
@@ -352,21 +355,87 @@ void wae_build_star(const double* xyz, const uint32_t* conn, int nloc, const Pat
   wae_build_owner_order(xyz, conn, nloc, P, OO);
   const int64_t ne = (int64_t)P.elems.size(), npos = (int64_t)OO.order.size();
   if (OO.max_inc > 255) WAE_THROW(WAE_E_INVALID, "a DOF is shared by %d elements; the star program holds at most 255 sources per star", OO.max_inc);
-  // cut by the number of staged elements (exact, with a stamp per element); the shared memory a patch needs is very nearly
-  // proportional to it.  The factor is calibrated on a sample of patches, the cut repeated, and shrunk if a patch still overflows.
+  // ---- two ways to cut the DOFs into patches; the one that stages fewer elements per owned DOF on a sample of patches is used.
+  //  (M) consecutive ranges of the Morton owner order of generation 2, cut by their exact number of staged elements: compact when the
+  //      cells line up with the curve's power-of-two boxes (64^3 grid: 2.35 staged elements per tetrahedron), ragged otherwise (203^3: 3.2);
+  //  (B) leaves of a recursive coordinate bisection of the DOF positions (vertices; P2: edge midpoints): a range of k leaves is split at
+  //      the k/2 : k - k/2 quantile of its longest axis -- box-shaped clusters of equal DOF count whatever the mesh (47^3 grid: 2.6 instead
+  //      of 3.0).  WAE_STAR_CUT=morton|bisect forces one.
   std::vector<int64_t> cut;
-  std::vector<int32_t> stamp(ne);
-  auto do_cut = [&](int64_t cap_nt) {
-    cap_nt = std::min<int64_t>(cap_nt, wae_star_max_staged(nloc));
+  const std::vector<int32_t> order_m = OO.order, pos_m = OO.pos;
+  std::vector<float> dpos((size_t)3 * P.dim, 0.0f);
+  {
+    static const int EVL[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+    parallel_for(ne, [&](int64_t e0, int64_t e1) {
+      for (int64_t e = e0; e < e1; e++) {
+        const uint32_t* d = conn + (size_t)P.elems[e] * nloc;
+        for (int a2 = 0; a2 < 4; a2++)
+          for (int r = 0; r < 3; r++) dpos[3 * (size_t)d[a2] + r] = (float)xyz[3 * (size_t)d[a2] + r];
+        if (nloc == 10)
+          for (int k = 0; k < 6; k++)
+            for (int r = 0; r < 3; r++)
+              dpos[3 * (size_t)d[4 + k] + r] = (float)(0.5 * (xyz[3 * (size_t)d[EVL[k][0]] + r] + xyz[3 * (size_t)d[EVL[k][1]] + r]));
+      }
+    });
+  }
+  std::function<void(int32_t*, int64_t, int64_t, int)> bisect = [&](int32_t* idx, int64_t n, int64_t k, int depth) {
+    if (k <= 1 || n <= 1) return;
+    float lo[3] = {3e38f, 3e38f, 3e38f}, hi[3] = {-3e38f, -3e38f, -3e38f};
+    for (int64_t i = 0; i < n; i++)
+      for (int r = 0; r < 3; r++) {
+        const float v = dpos[3 * (size_t)idx[i] + r];
+        lo[r] = std::min(lo[r], v);
+        hi[r] = std::max(hi[r], v);
+      }
+    int ax = 0;
+    for (int r = 1; r < 3; r++)
+      if (hi[r] - lo[r] > hi[ax] - lo[ax]) ax = r;
+    const int64_t kl = k / 2, nl = n * kl / k;
+    std::nth_element(idx, idx + nl, idx + n, [&](int32_t x, int32_t y) {
+      const float a2 = dpos[3 * (size_t)x + ax], b2 = dpos[3 * (size_t)y + ax];
+      return a2 < b2 || (a2 == b2 && x < y);
+    });
+    if (depth < 4 && n > 200000) {  // the top of the tree runs on sixteen threads
+      std::thread t([&] { bisect(idx, nl, kl, depth + 1); });
+      bisect(idx + nl, n - nl, k - kl, depth + 1);
+      t.join();
+    } else {
+      bisect(idx, nl, kl, depth + 1);
+      bisect(idx + nl, n - nl, k - kl, depth + 1);
+    }
+  };
+  std::vector<int32_t> stamp;
+  // cap: staged elements per patch (Morton) / DOFs per patch (bisection)
+  auto do_cut = [&](bool morton, int64_t cap) {
     cut.assign(1, 0);
-    std::fill(stamp.begin(), stamp.end(), -1);
+    if (!morton) {
+      const int64_t k = std::max<int64_t>(1, (npos + cap - 1) / cap);
+      OO.order = order_m;
+      bisect(OO.order.data(), npos, k, 0);
+      for (int64_t q = 0; q < npos; q++) OO.pos[OO.order[q]] = (int32_t)q;
+      std::function<void(int64_t, int64_t, int64_t)> bounds = [&](int64_t lo, int64_t n, int64_t kk) {  // the recursion's own splits
+        if (kk <= 1 || n <= 1) {
+          if (n > 0) cut.push_back(lo + n);
+          return;
+        }
+        const int64_t kl = kk / 2, nl = n * kl / kk;
+        bounds(lo, nl, kl);
+        bounds(lo + nl, n - nl, kk - kl);
+      };
+      bounds(0, npos, k);
+      return;
+    }
+    OO.order = order_m;
+    OO.pos = pos_m;
+    cap = std::min<int64_t>(cap, wae_star_max_staged(nloc));
+    stamp.assign(ne, -1);
     int64_t staged = 0;
     int32_t cur = 0;
     for (int64_t q = 0; q < npos; q++) {
       const int32_t j = OO.order[q];
       int64_t fresh = 0;
       for (int64_t r = OO.nptr[j]; r < OO.nptr[j + 1]; r++) fresh += stamp[OO.nadj[r]] != cur;
-      if (staged + fresh > cap_nt && staged > 0) {
+      if (staged + fresh > cap && staged > 0) {
         cut.push_back(q);
         cur++;
         staged = 0;
@@ -377,30 +446,57 @@ void wae_build_star(const double* xyz, const uint32_t* conn, int nloc, const Pat
     }
     cut.push_back(npos);
   };
-  const double guess = nloc == 4 ? 220.0 : 420.0;  // bytes of shared memory per staged element, first guess
-  int64_t cap_nt = std::max<int64_t>(2 * OO.max_inc, (int64_t)(smem_budget / guess));
-  do_cut(cap_nt);
-  tick("star: first cut");
-  {
-    const int64_t np = (int64_t)cut.size() - 1, ns = std::min<int64_t>(np, 24);
-    double per = 0;
-    std::vector<double> pers(ns, 0.0);
-    parallel_for(ns, [&](int64_t a, int64_t b) {
-      for (int64_t i = a; i < b; i++) {
+  // a sample of patches of the current cut: largest shared memory per unit of the cut, staged elements per owned DOF
+  auto sample = [&](bool morton, double& per_unit, double& staged_per_dof) {
+    const int64_t np = (int64_t)cut.size() - 1, ns = std::min<int64_t>(np, 32);
+    std::vector<double> pers(ns, 0.0), st(ns, 0.0), dofs(ns, 0.0);
+    parallel_for(ns, [&](int64_t a2, int64_t b2) {
+      for (int64_t i = a2; i < b2; i++) {
         const int64_t p = i * np / ns;
         PatchOut O;
         build_patch(conn, nloc, P, OO, (int32_t)cut[p], (int32_t)cut[p + 1], O);
-        pers[i] = (double)patch_smem(nloc, O) / std::max<size_t>(1, O.tets.size());
+        const double unit = morton ? (double)std::max<size_t>(1, O.tets.size()) : (double)std::max<int64_t>(1, cut[p + 1] - cut[p]);
+        pers[i] = (double)patch_smem(nloc, O) / unit;
+        st[i] = (double)O.tets.size();
+        dofs[i] = (double)(cut[p + 1] - cut[p]);
       }
     }, 2);
-    for (double x : pers) per = std::max(per, x);
-    cap_nt = std::max<int64_t>(2 * OO.max_inc, (int64_t)(0.96 * smem_budget / std::max(per, 1.0)));
+    per_unit = 0;
+    double s1 = 0, s2 = 0;
+    for (int64_t i = 0; i < ns; i++) {
+      per_unit = std::max(per_unit, pers[i]);
+      s1 += st[i];
+      s2 += dofs[i];
+    }
+    staged_per_dof = s1 / std::max(s2, 1.0);
+  };
+  const int64_t cap_min_of[2] = {2 * (int64_t)OO.max_inc, 4};
+  int64_t cap_of[2] = {0, 0};
+  double ratio_of[2] = {1e300, 1e300};
+  const char* force = getenv("WAE_STAR_CUT");
+  for (int mode = 0; mode < 2; mode++) {  // 0: Morton, 1: bisection
+    if (force && ((mode == 0) != (force[0] == 'm'))) continue;
+    const bool morton = mode == 0;
+    const double guess = morton ? (nloc == 4 ? 220.0 : 420.0) : (nloc == 4 ? 2600.0 : 1150.0);  // shared memory per unit, first guess
+    double per = 0, ratio = 0;
+    do_cut(morton, std::max<int64_t>(cap_min_of[mode], (int64_t)(smem_budget / guess)));
+    sample(morton, per, ratio);
+    cap_of[mode] = std::max<int64_t>(cap_min_of[mode], (int64_t)(0.95 * smem_budget / std::max(per, 1.0)));
+    do_cut(morton, cap_of[mode]);
+    sample(morton, per, ratio);
+    ratio_of[mode] = ratio;
   }
-  tick("star: calibration");
+  const bool morton = ratio_of[0] <= ratio_of[1];
+  int64_t cap_nt = cap_of[morton ? 0 : 1];
+  const int64_t cap_min = cap_min_of[morton ? 0 : 1];
+  if (timing)
+    fprintf(stderr, "[wae symbolic] star: staged elements per owned DOF on the samples: Morton %.3f, bisection %.3f -> %s\n", ratio_of[0], ratio_of[1],
+            morton ? "Morton" : "bisection");
+  tick("star: cut + calibration");
   std::vector<PatchOut> po;
   int64_t npatch = 0;
   for (int attempt = 0;; attempt++) {
-    do_cut(cap_nt);
+    do_cut(morton, cap_nt);
     npatch = (int64_t)cut.size() - 1;
     po.clear();
     po.resize(npatch);
@@ -425,11 +521,21 @@ void wae_build_star(const double* xyz, const uint32_t* conn, int nloc, const Pat
     }
     if (bad) WAE_THROW(WAE_E_INVALID, "star program: inconsistent program (flags %d)", bad);
     if (worst <= smem_budget && worst_rows * WAE_STAR_RS <= 8192) break;
-    if (attempt >= 6 || cap_nt <= 2 * OO.max_inc) WAE_THROW(WAE_E_INVALID, "star program does not fit %lld bytes of shared memory", (long long)smem_budget);
+    if (attempt >= 8 || cap_nt <= cap_min) WAE_THROW(WAE_E_INVALID, "star program does not fit %lld bytes of shared memory", (long long)smem_budget);
     const double f = std::min(0.9, std::min((double)smem_budget / (double)worst, (8192.0 / WAE_STAR_RS) / (double)std::max(worst_rows, 1)) * 0.97);
-    cap_nt = std::max<int64_t>(2 * OO.max_inc, (int64_t)(cap_nt * f));
+    cap_nt = std::max<int64_t>(cap_min, (int64_t)(cap_nt * f));
   }
   tick("star: per-patch programs");
+  if (timing) {
+    double mn = 1e300, mx = 0, sum = 0, dmn = 1e300, dmx = 0;
+    for (int64_t p = 0; p < npatch; p++) {
+      const double b2 = (double)patch_smem(nloc, po[p]), nd = (double)(cut[p + 1] - cut[p]);
+      mn = std::min(mn, b2); mx = std::max(mx, b2); sum += b2;
+      dmn = std::min(dmn, b2 / nd); dmx = std::max(dmx, b2 / nd);
+    }
+    fprintf(stderr, "[wae symbolic] star: %lld patches, shared memory per patch min %.0f mean %.0f max %.0f (budget %lld), per owned DOF %.0f .. %.0f, cap %lld\n",
+            (long long)npatch, mn, sum / (double)npatch, mx, (long long)smem_budget, dmn, dmx, (long long)cap_nt);
+  }
   // ---- pack: descriptor + blob A + blob B + patch vertices per patch (assembly_star.h) -----------------------------------------------
   G = StarHost();
   G.nloc = nloc;
