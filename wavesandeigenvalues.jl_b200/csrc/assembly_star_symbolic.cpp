@@ -355,16 +355,21 @@ void wae_build_star(const double* xyz, const uint32_t* conn, int nloc, const Pat
   wae_build_owner_order(xyz, conn, nloc, P, OO);
   const int64_t ne = (int64_t)P.elems.size(), npos = (int64_t)OO.order.size();
   if (OO.max_inc > 255) WAE_THROW(WAE_E_INVALID, "a DOF is shared by %d elements; the star program holds at most 255 sources per star", OO.max_inc);
-  // ---- two ways to cut the DOFs into patches; the one that stages fewer elements per owned DOF on a sample of patches is used.
-  //  (M) consecutive ranges of the Morton owner order of generation 2, cut by their exact number of staged elements: compact when the
-  //      cells line up with the curve's power-of-two boxes (64^3 grid: 2.35 staged elements per tetrahedron), ragged otherwise (203^3: 3.2);
-  //  (B) leaves of a recursive coordinate bisection of the DOF positions (vertices; P2: edge midpoints): a range of k leaves is split at
-  //      the k/2 : k - k/2 quantile of its longest axis -- box-shaped clusters of equal DOF count whatever the mesh (47^3 grid: 2.6 instead
-  //      of 3.0).  WAE_STAR_CUT=morton|bisect forces one.
+  // ---- two ways to cut the DOFs into patches:
+  //  (M, default) consecutive ranges of the Morton owner order of generation 2, cut by their exact number of staged elements: uniform use
+  //      of the shared-memory budget; compact when the cells line up with the curve's power-of-two boxes (64^3 grid: 2.35 staged elements per
+  //      tetrahedron), ragged otherwise (203^3: 3.2);
+  //  (B, WAE_STAR_CUT=bisect) leaves of a recursive coordinate bisection of the DOF positions (vertices; P2: edge midpoints): a range of k
+  //      leaves is split at the k/2 : k - k/2 quantile of its longest axis -- box-shaped clusters of equal DOF count whatever the mesh (203^3:
+  //      2.86 staged), but leaves of equal DOF count need very different amounts of shared memory (44 .. 114 KB), so the patches are smaller
+  //      on average and the kernel is not faster for it (config 5: 14.4 ms against 14.0 ms) while the host phase takes three times as long.
+  //  WAE_STAR_CUT=auto builds both cuts and keeps the one that stages fewer elements per owned DOF on a sample of patches.
   std::vector<int64_t> cut;
   const std::vector<int32_t> order_m = OO.order, pos_m = OO.pos;
-  std::vector<float> dpos((size_t)3 * P.dim, 0.0f);
-  {
+  const char* cut_env = getenv("WAE_STAR_CUT");
+  std::vector<float> dpos;
+  if (cut_env && cut_env[0] != 'm') {
+    dpos.assign((size_t)3 * P.dim, 0.0f);
     static const int EVL[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
     parallel_for(ne, [&](int64_t e0, int64_t e1) {
       for (int64_t e = e0; e < e1; e++) {
@@ -474,8 +479,9 @@ void wae_build_star(const double* xyz, const uint32_t* conn, int nloc, const Pat
   int64_t cap_of[2] = {0, 0};
   double ratio_of[2] = {1e300, 1e300};
   const char* force = getenv("WAE_STAR_CUT");
+  if (!force) force = "morton";
   for (int mode = 0; mode < 2; mode++) {  // 0: Morton, 1: bisection
-    if (force && ((mode == 0) != (force[0] == 'm'))) continue;
+    if (force[0] != 'a' && ((mode == 0) != (force[0] == 'm'))) continue;
     const bool morton = mode == 0;
     const double guess = morton ? (nloc == 4 ? 220.0 : 420.0) : (nloc == 4 ? 2600.0 : 1150.0);  // shared memory per unit, first guess
     double per = 0, ratio = 0;
@@ -489,7 +495,7 @@ void wae_build_star(const double* xyz, const uint32_t* conn, int nloc, const Pat
   const bool morton = ratio_of[0] <= ratio_of[1];
   int64_t cap_nt = cap_of[morton ? 0 : 1];
   const int64_t cap_min = cap_min_of[morton ? 0 : 1];
-  if (timing)
+  if (timing && force[0] == 'a')
     fprintf(stderr, "[wae symbolic] star: staged elements per owned DOF on the samples: Morton %.3f, bisection %.3f -> %s\n", ratio_of[0], ratio_of[1],
             morton ? "Morton" : "bisection");
   tick("star: cut + calibration");
