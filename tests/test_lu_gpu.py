@@ -185,8 +185,10 @@ def test_fancyflame_and_state_space_admittance_match_oracle():
         z = 1000.0 + 200.0j
         assert abs(Lg(z).to_scipy() - Lo(z)).max() <= 1e-11 * abs(Lo(z)).max(), name
         assert abs(Lg(z, 1).to_scipy() - Lo(z, 1)).max() <= 1e-11 * abs(Lo(z, 1)).max(), name
-        sg, ng, fg = W.householder(Lg, 340 * 2 * math.pi, maxiter=25, tol=1e-11, output=False)
-        so, no, fo = ohouse(Lo, 340 * 2 * math.pi, maxiter=25, tol=1e-11)
+        # tol: 1e-13 relative; 1e-11 sits at the rounding floor of the step |d omega| (2e-11 ... 5e-12 from one iteration to the next, on the
+        # GPU and in the oracle alike) and made the iteration count a coin toss
+        sg, ng, fg = W.householder(Lg, 340 * 2 * math.pi, maxiter=25, tol=1e-10, output=False)
+        so, no, fo = ohouse(Lo, 340 * 2 * math.pi, maxiter=25, tol=1e-10)
         assert fg == fo and fg >= 0
         assert abs(sg.params["ω"] - so.params["ω"]) <= TOL * abs(so.params["ω"]), (name, sg.params["ω"], so.params["ω"])
 

@@ -46,11 +46,17 @@ for rep in range(nsolve):
     ms = ctx.last_ms("solve")
 r = L(z).matvec(x) - b
 print(f"solve {ms:.1f} ms (1 rhs, 1 refinement step; {2*16*dev.lu_nnz/ms/1e6:.0f} GB/s of factor traffic), residual max|Ax-b|/max|b| = {np.abs(r).max()/np.abs(b).max():.2e}")
-if os.environ.get("WAE_PROBE_ONLY"):
+if os.environ.get("WAE_PROBE_ONLY") == "1":
     sys.exit(0)
 B = rng.standard_normal((L.size(), 8)) + 1j * rng.standard_normal((L.size(), 8))
-X = ctx.lu_solve(lid, B)
-print(f"solve 8 rhs {ctx.last_ms('solve'):.1f} ms")
+for k in (2, 8):
+    for rep in range(3):
+        X = ctx.lu_solve(lid, B[:, :k])
+    ms = ctx.last_ms("solve")
+    r = L(z).matvec(X[:, k - 1]) - B[:, k - 1]
+    print(f"solve {k} rhs {ms:.1f} ms ({2*16*dev.lu_nnz/ms/1e6:.0f} GB/s of factor traffic, {k*2*16*dev.lu_nnz/ms/1e6:.0f} GB/s x rhs), residual {np.abs(r).max()/np.abs(B[:, k - 1]).max():.2e}")
+if os.environ.get("WAE_PROBE_ONLY") == "2":
+    sys.exit(0)
 st = {}
 t5 = time.time()
 sol, n, flag = W.householder(L, z, maxiter=15, tol=1e-9 * abs(z), output=True, stats=st)

@@ -61,6 +61,9 @@ struct LuSolver {
   DevBuf<double> d_arn2_dots;
   DevBuf<double> d_arn_dots;
   DevBuf<int32_t> d_flag;              // device-side status (bad pivot)
+  DevBuf<int32_t> d_wininv_items;      // (supernode, block) work items of the window inverses, grouped by the number of blocks below
+  int wininv_ptr[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // items with exactly c blocks below: [wininv_ptr[c], wininv_ptr[c + 1]), c = 1 .. 7
+  bool wininv = false;                 // the last factorisation stored the window inverses (the solves use the product kernels)
   int work_nrhs = 0;
   bool factored = false;
   bool check_singular = true;          // raise WAE_E_SINGULAR on an exactly zero pivot (wae_lu_factor_ex with check = 0 clears it)

@@ -535,8 +535,9 @@ __global__ void __launch_bounds__(1024) lu_fwd_tri_kernel(LuDev D, const int32_t
   __shared__ cplx yk[NB];
   __shared__ cplx xw[LU_SOLVE_W];  // the window of x: the block steps work on shared memory only
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  cplx* xg = x + (size_t)blockIdx.y * n + S.first;  // one CTA per (supernode, right-hand side)
-  if (threadIdx.x < c_hi - c_lo) xw[threadIdx.x] = xg[c_lo + threadIdx.x];
+  const int nrhs = gridDim.y;  // one CTA per (supernode, right-hand side); x is stored position-major: x[pos * nrhs + rhs]
+  cplx* xg = x + (size_t)S.first * nrhs + blockIdx.y;
+  if (threadIdx.x < c_hi - c_lo) xw[threadIdx.x] = xg[(size_t)(c_lo + threadIdx.x) * nrhs];
   __syncthreads();
   cplx* xs = xw - c_lo;  // xs[i] = entry i of the pivot block, valid for c_lo <= i < c_hi
   for (int c0 = c_lo, kb = c_lo / NB; c0 < c_hi; c0 += NB, kb++) {
@@ -578,7 +579,7 @@ __global__ void __launch_bounds__(1024) lu_fwd_tri_kernel(LuDev D, const int32_t
     }
     __syncthreads();
   }
-  if (threadIdx.x < c_hi - c_lo) xg[c_lo + threadIdx.x] = xw[threadIdx.x];
+  if (threadIdx.x < c_hi - c_lo) xg[(size_t)(c_lo + threadIdx.x) * nrhs] = xw[threadIdx.x];
 }
 
 // x[rows below the window] -= P[rows, window] * y_window.  grid.x row chunks of 64, grid.y supernode, grid.z groups of NR
@@ -603,7 +604,7 @@ __global__ void __launch_bounds__(256) lu_fwd_update_kernel(LuDev D, const int32
   for (int j = threadIdx.x; j < ncol; j += 256)
 #pragma unroll
     for (int q = 0; q < NR; q++)
-      if (q < nr) ys[q][j] = x[(size_t)(rhs0 + q) * n + S.first + c_lo + j];
+      if (q < nr) ys[q][j] = x[(size_t)(S.first + c_lo + j) * nrhs + rhs0 + q];
   __syncthreads();
   cplx acc[NR];
 #pragma unroll
@@ -637,12 +638,11 @@ __global__ void __launch_bounds__(256) lu_fwd_update_kernel(LuDev D, const int32
           t.x += ys[q][u * 64 + r].x;
           t.y += ys[q][u * 64 + r].y;
         }
-        cplx* xr = x + (size_t)(rhs0 + q) * n;
         if (g < S.s) {
-          cplx* d = xr + S.first + g;
+          cplx* d = x + (size_t)(S.first + g) * nrhs + rhs0 + q;
           *d = csub(*d, t);
         } else
-          catomic_sub(xr + st[g - S.s], t);
+          catomic_sub(x + (size_t)st[g - S.s] * nrhs + rhs0 + q, t);
       }
   }
 }
@@ -674,7 +674,7 @@ __global__ void __launch_bounds__(256) lu_bwd_update_kernel(LuDev D, const int32
 #pragma unroll
     for (int q = 0; q < NR; q++)
       if (q < nr) {
-        const cplx v = x[(size_t)(rhs0 + q) * n + idx];
+        const cplx v = x[(size_t)idx * nrhs + rhs0 + q];
         sr[q] += a.x * v.x - a.y * v.y;
         si[q] += a.x * v.y + a.y * v.x;
       }
@@ -686,7 +686,7 @@ __global__ void __launch_bounds__(256) lu_bwd_update_kernel(LuDev D, const int32
       sr[q] += __shfl_xor_sync(0xffffffffu, sr[q], off);
       si[q] += __shfl_xor_sync(0xffffffffu, si[q], off);
     }
-    if (lane == 0 && q < nr) catomic_sub(x + (size_t)(rhs0 + q) * n + S.first + c, make_double2(sr[q], si[q]));
+    if (lane == 0 && q < nr) catomic_sub(x + (size_t)(S.first + c) * nrhs + rhs0 + q, make_double2(sr[q], si[q]));
   }
 }
 
@@ -705,8 +705,9 @@ __global__ void __launch_bounds__(1024) lu_bwd_tri_kernel(LuDev D, const int32_t
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   __shared__ cplx yk[NB];
   __shared__ cplx xw[LU_SOLVE_W];  // the window of x in shared memory
-  cplx* xg = x + (size_t)blockIdx.y * n + S.first;
-  if (threadIdx.x < c_hi - c_lo) xw[threadIdx.x] = xg[c_lo + threadIdx.x];
+  const int nrhs = gridDim.y;
+  cplx* xg = x + (size_t)S.first * nrhs + blockIdx.y;
+  if (threadIdx.x < c_hi - c_lo) xw[threadIdx.x] = xg[(size_t)(c_lo + threadIdx.x) * nrhs];
   __syncthreads();
   cplx* xs = xw - c_lo;
   for (int kb = (c_hi - 1) / NB; kb >= c_lo / NB; kb--) {
@@ -745,7 +746,479 @@ __global__ void __launch_bounds__(1024) lu_bwd_tri_kernel(LuDev D, const int32_t
     }
     __syncthreads();
   }
-  if (threadIdx.x < c_hi - c_lo) xg[c_lo + threadIdx.x] = xw[threadIdx.x];
+  if (threadIdx.x < c_hi - c_lo) xg[(size_t)(c_lo + threadIdx.x) * nrhs] = xw[threadIdx.x];
+}
+
+// ---- round 2: window inverses ---------------------------------------------------------------------------------
+// The W x W lower triangle T of a window (blocks T_ik = P[block i, block k], k <= i) is inverted ONCE per factorisation, so that a
+// window step of the solves is a matrix-vector product instead of a chain of W / NB dependent block steps (round 1: 45 us per window on
+// one CTA, 40 % of a solve at the top of the tree).  The diagonal blocks of the inverse are the NB x NB inverses the diagonal-block kernel
+// already keeps (dinv); block (i, j), i > j, of the inverse,
+//     Inv_ij = -T_ii^-1  sum_{k = j}^{i-1}  T_ik Inv_kj ,
+// is stored TRANSPOSED at block (j, i) of the same panel -- the strictly upper block triangle of the pivot block is unused by the
+// factorisation (L lives below the block diagonal of Lp, U^T below the block diagonal of Up) -- so no storage is added and T itself stays
+// intact.  In that position the forward product reads COLUMNS of the panel (y_rho = column rho above its block . x: contiguous) and the
+// backward (transposed) product reads ROWS (thread per row: coalesced), like the panel below the window.
+#define LU_WBLK (LU_SOLVE_W / NB)
+#define LU_TILE_BYTES (NB * (NB + 1) * (int)sizeof(cplx))
+
+// items: (supernode, block j) pairs; the CTA computes Inv_ij for i = j+1 .. end of j's window (exactly nI blocks), blockIdx.y = 0 Lp, 1 Up
+__global__ void __launch_bounds__(NB * NB) lu_wininv_kernel(LuDev D, const int32_t* __restrict__ items, int nI, int sym_dual) {
+  extern __shared__ __align__(16) unsigned char wininv_smem[];
+  typedef cplx Tile[NB][NB + 1];
+  Tile* Is = reinterpret_cast<Tile*>(wininv_smem);  // Is[m][b][c] = Inv_{j+m, j}[c, b], m = 0 .. nI
+  Tile& Ts = Is[nI + 1];                            // Ts[c][a] = left operand [a, c]
+  Tile& Ss = Is[nI + 2];                            // Ss[b][c] = sum [c, b]
+  const int sn = items[2 * blockIdx.x], j = items[2 * blockIdx.x + 1];
+  SnView S = sn_view(D, sn);
+  const bool up = blockIdx.y == 1;
+  cplx* P = up ? S.up : S.lp;
+  const cplx* dinv = D.dinv + D.dinv_off[sn] + (up ? NB * NB : 0);
+  const int nblk = (S.s + NB - 1) / NB;
+  const int wend = min((j / LU_WBLK + 1) * LU_WBLK, nblk);
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const cplx zero = make_double2(0.0, 0.0);
+  {
+    // T_jj^-1: Lp: L^-1[tx, ty] is entry [c = tx, b = ty]; Up: T_jj^-1 = (U^-1)^T, U^-1[tx, ty] is entry [c = ty, b = tx]
+    const cplx v = dinv[(size_t)j * 2 * NB * NB + tx + ty * NB];
+    if (up) Is[0][tx][ty] = v; else Is[0][ty][tx] = v;
+  }
+  for (int i = j + 1; i < wend; i++) {
+    cplx acc = zero;
+    const int row = NB * i + tx;
+    for (int k = j; k < i; k++) {
+      __syncthreads();  // Ts free again, Is[k - j] complete
+      Ts[ty][tx] = row < S.s ? P[row + (size_t)(NB * k + ty) * S.ld] : zero;  // T_ik[a = tx, c = ty]; rows past the pivot block are not part of T
+      __syncthreads();
+      const cplx* ik = &Is[k - j][ty][0];
+#pragma unroll 8
+      for (int c = 0; c < NB; c++) {
+        const cplx a = Ts[c][tx], b = ik[c];
+        acc.x += a.x * b.x - a.y * b.y;
+        acc.y += a.x * b.y + a.y * b.x;
+      }
+    }
+    __syncthreads();
+    Ss[ty][tx] = acc;
+    {
+      // T_ii^-1[a, c]: Lp: L^-1[a, c] at a + c NB (a = tx, c = ty); Up: U^-1[c, a] at c + a NB (c = tx, a = ty)
+      const cplx v = dinv[(size_t)i * 2 * NB * NB + tx + ty * NB];
+      if (up) Ts[tx][ty] = v; else Ts[ty][tx] = v;
+    }
+    __syncthreads();
+    cplx r = zero;
+    const cplx* sb = &Ss[ty][0];
+#pragma unroll 8
+    for (int c = 0; c < NB; c++) {
+      const cplx a = Ts[c][tx], b = sb[c];
+      r.x -= a.x * b.x - a.y * b.y;
+      r.y -= a.x * b.y + a.y * b.x;
+    }
+    Is[i - j][ty][tx] = r;  // Inv_ij[a = tx, b = ty]
+  }
+  __syncthreads();
+  // Inv_ij[a, b] -> P[(NB j + b) + (NB i + a) ld]: b = tx (contiguous), a = ty
+  // sym_dual (symmetric elimination, U = D L^T, launched for the L panel only): the inverse of the U^T window is D^-1 times the inverse of
+  // the L window, i.e. the stored (transposed) block with column rho divided by the pivot U_rho,rho -- written here instead of computed
+  for (int i = j + 1; i < wend; i++) {
+    const int col = NB * i + ty;
+    if (col < S.s) {
+      const cplx v = Is[i - j][tx][ty];
+      P[(NB * j + tx) + (size_t)col * S.ld] = v;
+      if (sym_dual) {
+        const cplx di = D.dinv[D.dinv_off[sn] + (size_t)i * 2 * NB * NB + NB * NB + ty + ty * NB];  // 1 / U_col,col
+        S.up[(NB * j + tx) + (size_t)col * S.ld] = cmul(v, di);
+      }
+    }
+  }
+}
+
+// forward product of one window: ys[q][rho] = sum_{m < NB (rho / NB)} P[c_lo + m, c_lo + rho] xs[q][m] + (T_ii^-1 xs[q][block i])[rho]
+// (warp per output row, lanes along the contiguous column segment).  xs / ys: [NR][stride] in shared memory, w = width of the window.
+template <int NR>
+__device__ __forceinline__ void win_fwd_matvec(const cplx* __restrict__ P, int ld, const cplx* __restrict__ dinv, int use_up, int c_lo, int w,
+                                               const cplx* xs, cplx* ys, int stride, int nwarps) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int rho = warp; rho < w; rho += nwarps) {
+    const int i = rho / NB, a = rho % NB;
+    const cplx* col = P + c_lo + (size_t)(c_lo + rho) * ld;
+    double sr[NR], si[NR];
+#pragma unroll
+    for (int q = 0; q < NR; q++) sr[q] = si[q] = 0.0;
+    for (int m = lane; m < NB * i; m += 32) {
+      const cplx v = col[m];
+#pragma unroll
+      for (int q = 0; q < NR; q++) {
+        const cplx xv = xs[q * stride + m];
+        sr[q] += v.x * xv.x - v.y * xv.y;
+        si[q] += v.x * xv.y + v.y * xv.x;
+      }
+    }
+    {
+      const cplx* Tinv = dinv + (size_t)(c_lo / NB + i) * 2 * NB * NB;
+      const int m = NB * i + lane;
+      if (m < w) {  // the inverse block is zero-padded, but the padded entries of xs are not initialised
+        const cplx v = use_up ? Tinv[lane + a * NB] : Tinv[a + lane * NB];
+#pragma unroll
+        for (int q = 0; q < NR; q++) {
+          const cplx xv = xs[q * stride + m];
+          sr[q] += v.x * xv.x - v.y * xv.y;
+          si[q] += v.x * xv.y + v.y * xv.x;
+        }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NR; q++) {
+#pragma unroll
+      for (int off = 16; off; off >>= 1) {
+        sr[q] += __shfl_xor_sync(0xffffffffu, sr[q], off);
+        si[q] += __shfl_xor_sync(0xffffffffu, si[q], off);
+      }
+      if (lane == 0) ys[q * stride + rho] = make_double2(sr[q], si[q]);
+    }
+  }
+}
+
+// backward (transposed) product of one window, the part one thread owns: row rho of the panel over the columns kappa = k0, k0 + kstep, ...
+// of the blocks behind rho's block, plus (first == true) the diagonal block:  sum_a T_jj^-1[a, b] v[NB j + a]
+template <int NR>
+__device__ __forceinline__ void win_bwd_row(const cplx* __restrict__ P, int ld, const cplx* __restrict__ dinv, int use_up, int c_lo, int w, int rho,
+                                            int kpart, int kstep, const cplx* vs, int stride, cplx* acc) {
+  const int j = rho / NB, b = rho % NB;
+  const cplx* row = P + (c_lo + rho) + (size_t)c_lo * ld;
+#pragma unroll 8
+  for (int kappa = NB * (j + 1) + kpart; kappa < w; kappa += kstep) {
+    const cplx v = row[(size_t)kappa * ld];
+#pragma unroll
+    for (int q = 0; q < NR; q++) {
+      const cplx xv = vs[q * stride + kappa];
+      acc[q].x += v.x * xv.x - v.y * xv.y;
+      acc[q].y += v.x * xv.y + v.y * xv.x;
+    }
+  }
+  const cplx* Tinv = dinv + (size_t)(c_lo / NB + j) * 2 * NB * NB;
+  const int a1 = min(NB, w - NB * j);
+#pragma unroll 8
+  for (int a = kpart; a < a1; a += kstep) {
+    const cplx v = use_up ? Tinv[b + a * NB] : Tinv[a + b * NB];
+#pragma unroll
+    for (int q = 0; q < NR; q++) {
+      const cplx xv = vs[q * stride + NB * j + a];
+      acc[q].x += v.x * xv.x - v.y * xv.y;
+      acc[q].y += v.x * xv.y + v.y * xv.x;
+    }
+  }
+}
+
+// All CTAs of a cluster have read the window of x before any of them overwrites its part of it
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;\n\tbarrier.cluster.wait.aligned;" ::: "memory");
+}
+#define LU_WIN_CLUSTER 8
+
+// window step of the forward sweep with the inverted window: a cluster of 8 CTAs per (supernode, right-hand side), one output row per
+// warp (CTA c, warp p: row c + 8 p, so that every CTA holds rows of every block) -- the <= 8 loads of a row are in flight together and
+// the step costs one memory latency instead of the 8 rows per warp a single CTA needs
+__global__ void __cluster_dims__(LU_WIN_CLUSTER, 1, 1) __launch_bounds__(1024)
+    lu_fwd_win_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int c_lo, int64_t n, cplx* __restrict__ x) {
+  const int sn = list[blockIdx.x / LU_WIN_CLUSTER], rank = blockIdx.x % LU_WIN_CLUSTER;
+  SnView S = sn_view(D, sn);
+  if (c_lo >= S.s) return;  // the whole cluster leaves
+  const int w = min(c_lo + LU_SOLVE_W, S.s) - c_lo;
+  __shared__ cplx xs[LU_SOLVE_W];
+  const int nrhs = gridDim.y;  // x is stored position-major: x[pos * nrhs + rhs]
+  cplx* xg = x + (size_t)(S.first + c_lo) * nrhs + blockIdx.y;
+  if (threadIdx.x < w) xs[threadIdx.x] = xg[(size_t)threadIdx.x * nrhs];
+  __syncthreads();
+  cluster_sync_all();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int rho = rank + LU_WIN_CLUSTER * warp;
+  if (rho >= w) return;
+  const cplx* P = use_up ? S.up : S.lp;
+  const cplx* dinv = D.dinv + D.dinv_off[sn] + (use_up ? NB * NB : 0);
+  const int i = rho / NB, a = rho % NB;
+  const cplx* col = P + c_lo + (size_t)(c_lo + rho) * S.ld;
+  cplx v[LU_WBLK];
+#pragma unroll
+  for (int t = 0; t < LU_WBLK - 1; t++) v[t] = t < i ? col[lane + 32 * t] : make_double2(0.0, 0.0);
+  {
+    const cplx* Tinv = dinv + (size_t)(c_lo / NB + i) * 2 * NB * NB;
+    v[LU_WBLK - 1] = NB * i + lane < w ? (use_up ? Tinv[lane + a * NB] : Tinv[a + lane * NB]) : make_double2(0.0, 0.0);
+  }
+  double sr = 0.0, si = 0.0;
+#pragma unroll
+  for (int t = 0; t < LU_WBLK - 1; t++)
+    if (t < i) {
+      const cplx xv = xs[lane + 32 * t];
+      sr += v[t].x * xv.x - v[t].y * xv.y;
+      si += v[t].x * xv.y + v[t].y * xv.x;
+    }
+  if (NB * i + lane < w) {
+    const cplx xv = xs[NB * i + lane];
+    sr += v[LU_WBLK - 1].x * xv.x - v[LU_WBLK - 1].y * xv.y;
+    si += v[LU_WBLK - 1].x * xv.y + v[LU_WBLK - 1].y * xv.x;
+  }
+#pragma unroll
+  for (int off = 16; off; off >>= 1) {
+    sr += __shfl_xor_sync(0xffffffffu, sr, off);
+    si += __shfl_xor_sync(0xffffffffu, si, off);
+  }
+  if (lane == 0) xg[(size_t)rho * nrhs] = make_double2(sr, si);
+}
+
+// window step of the backward sweep: cluster of 8 CTAs, CTA j owns block row j of the window: thread = (row, one of 32 column parts)
+__global__ void __cluster_dims__(LU_WIN_CLUSTER, 1, 1) __launch_bounds__(1024)
+    lu_bwd_win_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int c_lo, int64_t n, cplx* __restrict__ x) {
+  const int sn = list[blockIdx.x / LU_WIN_CLUSTER], rank = blockIdx.x % LU_WIN_CLUSTER;
+  SnView S = sn_view(D, sn);
+  if (c_lo >= S.s) return;
+  const int w = min(c_lo + LU_SOLVE_W, S.s) - c_lo;
+  __shared__ cplx vs[LU_SOLVE_W], part[32][NB + 1];
+  const int nrhs = gridDim.y;
+  cplx* xg = x + (size_t)(S.first + c_lo) * nrhs + blockIdx.y;
+  if (threadIdx.x < w) vs[threadIdx.x] = xg[(size_t)threadIdx.x * nrhs];
+  __syncthreads();
+  cluster_sync_all();
+  const int rr = threadIdx.x & 31, p = threadIdx.x >> 5;
+  const int rho = NB * rank + rr;
+  cplx acc = make_double2(0.0, 0.0);
+  if (rho < w) win_bwd_row<1>(use_up ? S.up : S.lp, S.ld, D.dinv + D.dinv_off[sn] + (use_up ? NB * NB : 0), use_up, c_lo, w, rho, p, 32, vs, LU_SOLVE_W, &acc);
+  part[p][rr] = acc;
+  __syncthreads();
+  if (p == 0 && rho < w) {
+    double tr = 0.0, ti = 0.0;
+#pragma unroll 8
+    for (int u = 0; u < 32; u++) {
+      tr += part[u][rr].x;
+      ti += part[u][rr].y;
+    }
+    xg[(size_t)rho * nrhs] = make_double2(tr, ti);
+  }
+}
+
+// x[rows below the window] -= P[rows, window] * y_window with PARTS column parts per row (64 rows per CTA): PARTS = 16 keeps a level with
+// few supernodes (the top of the tree: 7 windows per supernode, one after the other) short -- 16 loads per thread, all in flight at once.
+template <int NR, int PARTS>
+__global__ void __launch_bounds__(64 * PARTS) lu_fwd_update2_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int c_lo, int nrhs, int64_t n,
+                                                                   cplx* __restrict__ x) {
+  SnView S = sn_view(D, list[blockIdx.y]);
+  if (c_lo >= S.s) return;
+  const int c_hi = min(c_lo + LU_SOLVE_W, S.s);
+  const int nrows = S.ld - c_hi;
+  if (blockIdx.x * 64 >= nrows) return;
+  const int r = threadIdx.x & 63, part = threadIdx.x >> 6;
+  const int i = blockIdx.x * 64 + r;
+  const int rhs0 = blockIdx.z * NR, nr = min(NR, nrhs - rhs0);
+  const cplx* P = (use_up ? S.up : S.lp) + c_hi;
+  const int32_t* st = D.struct_idx + D.struct_ptr[list[blockIdx.y]];
+  __shared__ cplx ys[NR][LU_SOLVE_W];
+  __shared__ cplx red[NR][PARTS - 1][64];
+  const int ncol = c_hi - c_lo;
+  for (int j = threadIdx.x; j < ncol; j += 64 * PARTS)
+#pragma unroll
+    for (int q = 0; q < NR; q++)
+      if (q < nr) ys[q][j] = x[(size_t)(S.first + c_lo + j) * nrhs + rhs0 + q];
+  __syncthreads();
+  cplx acc[NR];
+#pragma unroll
+  for (int q = 0; q < NR; q++) acc[q] = make_double2(0.0, 0.0);
+  if (i < nrows) {
+    constexpr int CP = LU_SOLVE_W / PARTS;
+    const int j0 = part * CP, j1 = min(ncol, j0 + CP);
+    const cplx* row = P + i + (size_t)c_lo * S.ld;
+#pragma unroll 16
+    for (int j = j0; j < j1; j++) {
+      const cplx a = row[(size_t)j * S.ld];
+#pragma unroll
+      for (int q = 0; q < NR; q++) {
+        acc[q].x += a.x * ys[q][j].x - a.y * ys[q][j].y;
+        acc[q].y += a.x * ys[q][j].y + a.y * ys[q][j].x;
+      }
+    }
+  }
+  if (part)
+#pragma unroll
+    for (int q = 0; q < NR; q++) red[q][part - 1][r] = acc[q];
+  __syncthreads();
+  if (part == 0 && i < nrows) {
+    const int g = c_hi + i;
+#pragma unroll
+    for (int q = 0; q < NR; q++)
+      if (q < nr) {
+        cplx t = acc[q];
+#pragma unroll
+        for (int u = 0; u < PARTS - 1; u++) {
+          t.x += red[q][u][r].x;
+          t.y += red[q][u][r].y;
+        }
+        if (g < S.s) {
+          cplx* d = x + (size_t)(S.first + g) * nrhs + rhs0 + q;
+          *d = csub(*d, t);
+        } else
+          catomic_sub(x + (size_t)st[g - S.s] * nrhs + rhs0 + q, t);
+      }
+  }
+}
+
+// CW adjacent columns per warp, lanes along the rows [r_begin, r_end) below row c_hi of the panel: sums[cw][q] = sum_i P[c_hi + i, c + cw] x_q[idx(i)].
+// One gather of x serves CW columns (round 1: one gather per column -- as many bytes from L2 as the panel brings from HBM).
+template <int NR, int CW>
+__device__ __forceinline__ void col_dots(const cplx* __restrict__ colbase, int ld, int ncw, int r_begin, int r_end, int c_hi, int s, int first,
+                                         const int32_t* __restrict__ st, const cplx* __restrict__ x, int nrhs, int nr, double (*sr)[NR], double (*si)[NR]) {
+  const int lane = threadIdx.x & 31;
+  for (int i = r_begin + lane; i < r_end; i += 32) {
+    const int g = c_hi + i;
+    const int64_t idx = g < s ? (int64_t)first + g : (int64_t)st[g - s];
+    cplx a[CW];
+#pragma unroll
+    for (int cw = 0; cw < CW; cw++) a[cw] = cw < ncw ? colbase[i + (size_t)cw * ld] : make_double2(0.0, 0.0);
+#pragma unroll
+    for (int q = 0; q < NR; q++)
+      if (q < nr) {
+        const cplx v = x[(size_t)idx * nrhs + q];
+#pragma unroll
+        for (int cw = 0; cw < CW; cw++) {
+          sr[cw][q] += a[cw].x * v.x - a[cw].y * v.y;
+          si[cw][q] += a[cw].x * v.y + a[cw].y * v.x;
+        }
+      }
+  }
+#pragma unroll
+  for (int cw = 0; cw < CW; cw++)
+#pragma unroll
+    for (int q = 0; q < NR; q++)
+#pragma unroll
+      for (int off = 16; off; off >>= 1) {
+        sr[cw][q] += __shfl_xor_sync(0xffffffffu, sr[cw][q], off);
+        si[cw][q] += __shfl_xor_sync(0xffffffffu, si[cw][q], off);
+      }
+}
+
+// columns per warp of the backward kernels: 4, or 2 when 8 right-hand sides already fill the register file
+#define LU_CW(NR) ((NR) >= 8 ? 2 : 4)
+
+// backward update, CW columns per warp: grid.x = (column groups of 8 warps x CW) x (row chunks), grid.y supernode, grid.z groups of NR
+template <int NR>
+__global__ void __launch_bounds__(256) lu_bwd_update2_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int c_lo, int ncg, int row_chunk,
+                                                             int nrhs, int64_t n, cplx* __restrict__ x) {
+  SnView S = sn_view(D, list[blockIdx.y]);
+  if (c_lo >= S.s) return;
+  const int c_hi = min(c_lo + LU_SOLVE_W, S.s);
+  const int nrows = S.ld - c_hi;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int CW = LU_CW(NR);
+  const int c = c_lo + (blockIdx.x % ncg) * (8 * CW) + warp * CW;
+  const int r_begin = (blockIdx.x / ncg) * row_chunk;
+  if (c >= c_hi || r_begin >= nrows) return;
+  const int r_end = min(nrows, r_begin + row_chunk);
+  const int rhs0 = blockIdx.z * NR, nr = min(NR, nrhs - rhs0);
+  double sr[CW][NR], si[CW][NR];
+#pragma unroll
+  for (int cw = 0; cw < CW; cw++)
+#pragma unroll
+    for (int q = 0; q < NR; q++) sr[cw][q] = si[cw][q] = 0.0;
+  const int ncw = min(CW, c_hi - c);
+  col_dots<NR, CW>((use_up ? S.up : S.lp) + c_hi + (size_t)c * S.ld, S.ld, ncw, r_begin, r_end, c_hi, S.s, S.first,
+                  D.struct_idx + D.struct_ptr[list[blockIdx.y]], x + rhs0, nrhs, nr, sr, si);
+  if (lane == 0)
+#pragma unroll
+    for (int cw = 0; cw < CW; cw++)
+      if (cw < ncw)
+#pragma unroll
+        for (int q = 0; q < NR; q++)
+          if (q < nr) catomic_sub(x + (size_t)(S.first + c + cw) * nrhs + rhs0 + q, make_double2(sr[cw][q], si[cw][q]));
+}
+
+// ---- fused sweeps of the deep levels: one CTA per supernode (pivot block within one window of LU_FW columns) ----------------------
+// Thousands of small fronts per level: one launch per level and direction instead of a triangle and an update launch, the panel read once.
+#define LU_FW 128
+template <int NR>
+__global__ void __launch_bounds__(256) lu_fwd_fused_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int nrhs, int64_t n, cplx* __restrict__ x) {
+  const int sn = list[blockIdx.x];
+  SnView S = sn_view(D, sn);
+  const int rhs0 = blockIdx.y * NR, nr = min(NR, nrhs - rhs0);
+  const cplx* P = use_up ? S.up : S.lp;
+  __shared__ cplx xs[NR][LU_FW], ys[NR][LU_FW];
+  cplx* xg = x + (size_t)S.first * nrhs + rhs0;  // x[pos * nrhs + rhs]
+  for (int e = threadIdx.x; e < NR * S.s; e += 256) {
+    const int m = e / NR, q = e - m * NR;
+    xs[q][m] = q < nr ? xg[(size_t)m * nrhs + q] : make_double2(0.0, 0.0);
+  }
+  __syncthreads();
+  win_fwd_matvec<NR>(P, S.ld, D.dinv + D.dinv_off[sn] + (use_up ? NB * NB : 0), use_up, 0, S.s, &xs[0][0], &ys[0][0], LU_FW, 8);
+  __syncthreads();
+  for (int e = threadIdx.x; e < NR * S.s; e += 256) {
+    const int m = e / NR, q = e - m * NR;
+    if (q < nr) xg[(size_t)m * nrhs + q] = ys[q][m];
+  }
+  // structure rows: one row per thread over all columns of the pivot block
+  const int32_t* st = D.struct_idx + D.struct_ptr[sn];
+  for (int i = threadIdx.x; i < S.r; i += 256) {
+    const cplx* row = P + S.s + i;
+    cplx acc[NR];
+#pragma unroll
+    for (int q = 0; q < NR; q++) acc[q] = make_double2(0.0, 0.0);
+#pragma unroll 8
+    for (int j = 0; j < S.s; j++) {
+      const cplx a = row[(size_t)j * S.ld];
+#pragma unroll
+      for (int q = 0; q < NR; q++) {
+        acc[q].x += a.x * ys[q][j].x - a.y * ys[q][j].y;
+        acc[q].y += a.x * ys[q][j].y + a.y * ys[q][j].x;
+      }
+    }
+    const int64_t g = st[i];
+#pragma unroll
+    for (int q = 0; q < NR; q++)
+      if (q < nr) catomic_sub(x + (size_t)g * nrhs + rhs0 + q, acc[q]);
+  }
+}
+
+template <int NR>
+__global__ void __launch_bounds__(256) lu_bwd_fused_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int nrhs, int64_t n, cplx* __restrict__ x) {
+  const int sn = list[blockIdx.x];
+  SnView S = sn_view(D, sn);
+  const int rhs0 = blockIdx.y * NR, nr = min(NR, nrhs - rhs0);
+  const cplx* P = use_up ? S.up : S.lp;
+  __shared__ cplx vs[NR][LU_FW];
+  cplx* xg = x + (size_t)S.first * nrhs + rhs0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int32_t* st = D.struct_idx + D.struct_ptr[sn];
+  // v_c = x_c - sum_{structure rows i} P[s + i, c] x[st[i]]: CW columns per warp
+  constexpr int CW = LU_CW(NR);
+  for (int c = warp * CW; c < S.s; c += 8 * CW) {
+    double sr[CW][NR], si[CW][NR];
+#pragma unroll
+    for (int cw = 0; cw < CW; cw++)
+#pragma unroll
+      for (int q = 0; q < NR; q++) sr[cw][q] = si[cw][q] = 0.0;
+    const int ncw = min(CW, S.s - c);
+    col_dots<NR, CW>(P + S.s + (size_t)c * S.ld, S.ld, ncw, 0, S.r, S.s, S.s, S.first, st, x + rhs0, nrhs, nr, sr, si);
+    if (lane < ncw) {
+#pragma unroll
+      for (int q = 0; q < NR; q++) {
+        double tr = 0.0, ti = 0.0;
+#pragma unroll
+        for (int cw = 0; cw < CW; cw++)
+          if (cw == lane) {
+            tr = sr[cw][q];
+            ti = si[cw][q];
+          }
+        const cplx xv = q < nr ? xg[(size_t)(c + lane) * nrhs + q] : make_double2(0.0, 0.0);
+        vs[q][c + lane] = make_double2(xv.x - tr, xv.y - ti);
+      }
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < S.s) {
+    cplx acc[NR];
+#pragma unroll
+    for (int q = 0; q < NR; q++) acc[q] = make_double2(0.0, 0.0);
+    win_bwd_row<NR>(P, S.ld, D.dinv + D.dinv_off[sn] + (use_up ? NB * NB : 0), use_up, 0, S.s, threadIdx.x, 0, 1, &vs[0][0], LU_FW, acc);
+#pragma unroll
+    for (int q = 0; q < NR; q++)
+      if (q < nr) xg[(size_t)threadIdx.x * nrhs + q] = acc[q];
+  }
 }
 
 // ---- vector utilities -------------------------------------------------------------------------------------
@@ -758,7 +1231,7 @@ __global__ void lu_permute_in_kernel(const cplx* __restrict__ b, const int32_t* 
   double s = d[o];
   for (int r = 0; r < nrhs; r++) {
     cplx v = b[(size_t)r * n + o];
-    y[(size_t)r * n + p] = make_double2(v.x * s, conj ? -v.y * s : v.y * s);
+    y[(size_t)p * nrhs + r] = make_double2(v.x * s, conj ? -v.y * s : v.y * s);
   }
 }
 __global__ void lu_permute_out_kernel(const cplx* __restrict__ y, const int32_t* __restrict__ perm, const double* __restrict__ d,
@@ -768,7 +1241,7 @@ __global__ void lu_permute_out_kernel(const cplx* __restrict__ y, const int32_t*
   int32_t o = perm[p];
   double s = d[o];
   for (int r = 0; r < nrhs; r++) {
-    cplx v = y[(size_t)r * n + p];
+    cplx v = y[(size_t)p * nrhs + r];
     v = make_double2(v.x * s, conj ? -v.y * s : v.y * s);
     cplx* dst = x + (size_t)r * n + o;
     if (accumulate) {
@@ -840,6 +1313,30 @@ void wae_lu_setup_device(wae_ctx* h, LuSolver& S) {
     }
     S.xa_tiles[d] = tile_ptr.back();
     S.d_xa_tile_ptr[d].upload(tile_ptr, st);
+  }
+  // work items of the window inverses: every block j that is not the last one of its window, grouped by the blocks below it
+  {
+    std::vector<std::vector<int32_t>> cls(LU_WBLK);
+    for (int d = 0; d < (int)Y.levels.size(); d++)  // top of the tree (the long items) first
+      for (int32_t k : Y.levels[d]) {
+        const int nblk = (Y.sn_first[k + 1] - Y.sn_first[k] + NB - 1) / NB;
+        for (int j = 0; j < nblk; j++) {
+          const int wend = std::min((j / LU_WBLK + 1) * LU_WBLK, nblk);
+          const int below = wend - 1 - j;
+          if (below > 0) {
+            cls[below].push_back(k);
+            cls[below].push_back(j);
+          }
+        }
+      }
+    std::vector<int32_t> items;
+    S.wininv_ptr[0] = S.wininv_ptr[1] = 0;
+    for (int c = 1; c < LU_WBLK; c++) {
+      items.insert(items.end(), cls[c].begin(), cls[c].end());
+      S.wininv_ptr[c + 1] = (int)(items.size() / 2);
+    }
+    if (items.empty()) items.assign(2, 0);
+    S.d_wininv_items.upload(items, st);
   }
   // column index of every nonzero of A
   {
@@ -994,6 +1491,36 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
       }
     }
   }
+  // window inverses for the solves (WAE_LU_WININV=0: round-1 solve kernels, block-by-block substitution inside a window)
+  S.wininv = !(getenv("WAE_LU_WININV") && !atoi(getenv("WAE_LU_WININV")));
+  if (S.wininv) {
+    CUDA_CHECK(cudaFuncSetAttribute(lu_wininv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (LU_WBLK + 2) * LU_TILE_BYTES));
+    cudaEvent_t w0 = nullptr, w1 = nullptr;
+    if (trace) {
+      CUDA_CHECK(cudaEventCreate(&w0));
+      CUDA_CHECK(cudaEventCreate(&w1));
+      cudaEventRecord(w0, st);
+    }
+    const int dual = sym && sym_panel;  // the U^T panel is exactly L D there
+    for (int c = LU_WBLK - 1; c >= 1; c--) {
+      const int cnt = S.wininv_ptr[c + 1] - S.wininv_ptr[c];
+      for (int z0 = 0; z0 < cnt; z0 += 1 << 20) {
+        const int zc = std::min(1 << 20, cnt - z0);
+        lu_wininv_kernel<<<dim3(zc, dual ? 1 : 2), dim3(NB, NB), (c + 3) * LU_TILE_BYTES, st>>>(D, S.d_wininv_items.p + 2 * (size_t)(S.wininv_ptr[c] + z0), c, dual);
+        h->launches++;
+      }
+    }
+    if (trace) {
+      cudaEventRecord(w1, st);
+      cudaEventSynchronize(w1);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, w0, w1);
+      fprintf(stderr, "[wae lu trace] window inverses %.3f ms\n", ms);
+      h->last_ms["lu_trace_wininv"] = ms;
+      cudaEventDestroy(w0);
+      cudaEventDestroy(w1);
+    }
+  }
   if (trace) {
     std::array<double, T_N> tot;
     tot.fill(0.0);
@@ -1052,6 +1579,12 @@ static void lu_sweeps_nr(wae_ctx* h, LuSolver& S, int trans_t, int nrhs, cplx* y
   const int tri_pf = (getenv("WAE_LU_SOLVE_PF") && atoi(getenv("WAE_LU_SOLVE_PF"))) ? 2 : 0;  // bit 1 of the tri kernels' use_up: L2 prefetch hint
   const int zr = (nrhs + NR - 1) / NR;
   const int W = LU_SOLVE_W;
+  // round-2 kernels (each can be switched off for A/B runs): fused deep levels (needs the window inverses), 16-part forward update and
+  // 4-columns-per-warp backward update
+  const bool fused_ok = S.wininv && !(getenv("WAE_LU_SOLVE_FUSED") && !atoi(getenv("WAE_LU_SOLVE_FUSED")));
+  const bool upd2_ok = !(getenv("WAE_LU_SOLVE_UPD2") && !atoi(getenv("WAE_LU_SOLVE_UPD2")));
+  // a level goes through the fused kernels when it has at least this many supernodes (one CTA each must fill the GPU); tests set 1
+  const int fused_min = getenv("WAE_LU_SOLVE_FUSED_MIN") ? atoi(getenv("WAE_LU_SOLVE_FUSED_MIN")) : 2 * h->sm_count;
   // WAE_LU_TRACE=2 (diagnostic): the four kernel classes of a sweep pair timed per tree depth with their own events (serialising)
   const bool trace = getenv("WAE_LU_TRACE") && atoi(getenv("WAE_LU_TRACE")) == 2;
   std::vector<std::array<double, 4>> tms(maxd + 1);
@@ -1087,13 +1620,32 @@ static void lu_sweeps_nr(wae_ctx* h, LuSolver& S, int trans_t, int nrhs, cplx* y
     for (int z0 = 0; z0 < (int)L.size(); z0 += 32768) {
       const int zc = std::min<int>(32768, (int)L.size() - z0);
       const int32_t* lst = S.d_level[d].p + z0;
+      if (fused_ok && max_s <= LU_FW && (int)L.size() >= fused_min) {  // deep level: one CTA per supernode does triangle + update
+        timed(0, [&] { lu_fwd_fused_kernel<NR><<<dim3(zc, zr), 256, 0, st>>>(D, lst, fwd_up, nrhs, Y.n, y); });
+        h->launches++;
+        continue;
+      }
       for (int c_lo = 0; c_lo < max_s; c_lo += W) {
-        timed(0, [&] { lu_fwd_tri_kernel<<<dim3(zc, nrhs), 1024, 0, st>>>(D, lst, fwd_up | tri_pf, c_lo, Y.n, y); });
+        timed(0, [&] {
+          if (S.wininv)
+            lu_fwd_win_kernel<<<dim3(zc * LU_WIN_CLUSTER, nrhs), 1024, 0, st>>>(D, lst, fwd_up, c_lo, Y.n, y);
+          else
+            lu_fwd_tri_kernel<<<dim3(zc, nrhs), 1024, 0, st>>>(D, lst, fwd_up | tri_pf, c_lo, Y.n, y);
+        });
         h->launches++;
         const int rows = max_ld - std::min(c_lo + W, max_s);  // upper bound of the rows below the window over the level
         if (max_ld > c_lo + 1 && rows + W > 0) {
           const int rmax = max_ld - c_lo;  // a supernode with a short pivot block has its window end (and first row) earlier
-          timed(1, [&] { lu_fwd_update_kernel<NR><<<dim3((rmax + 63) / 64, zc, zr), 256, 0, st>>>(D, lst, fwd_up, c_lo, nrhs, Y.n, y); });
+          const dim3 g((rmax + 63) / 64, zc, zr);
+          timed(1, [&] {
+            if constexpr (NR <= 2) {
+              if (upd2_ok && (int)(g.x * g.y) < 2 * h->sm_count) {  // few CTAs: 16 column parts per row instead of 4
+                lu_fwd_update2_kernel<NR, 16><<<g, 1024, 0, st>>>(D, lst, fwd_up, c_lo, nrhs, Y.n, y);
+                return;
+              }
+            }
+            lu_fwd_update_kernel<NR><<<g, 256, 0, st>>>(D, lst, fwd_up, c_lo, nrhs, Y.n, y);
+          });
           h->launches++;
         }
       }
@@ -1111,18 +1663,34 @@ static void lu_sweeps_nr(wae_ctx* h, LuSolver& S, int trans_t, int nrhs, cplx* y
     for (int z0 = 0; z0 < (int)L.size(); z0 += 32768) {
       const int zc = std::min<int>(32768, (int)L.size() - z0);
       const int32_t* lst = S.d_level[d].p + z0;
+      if (fused_ok && max_s <= LU_FW && (int)L.size() >= fused_min) {
+        timed(3, [&] { lu_bwd_fused_kernel<NR><<<dim3(zc, zr), 256, 0, st>>>(D, lst, !fwd_up, nrhs, Y.n, y); });
+        h->launches++;
+        continue;
+      }
       for (int c_lo = ((max_s - 1) / W) * W; c_lo >= 0; c_lo -= W) {
         const int rmax = max_ld - c_lo;
         if (rmax > 1) {
           // few supernodes on the level: cut the rows into chunks so that the level still fills the GPU
-          const int ncg = (std::min(W, max_s - c_lo) + 7) / 8;
+          const int cpc = upd2_ok ? 8 * LU_CW(NR) : 8;  // columns per CTA: 8 warps x CW columns (round 2) or 8 warps x 1
+          const int ncg = (std::min(W, max_s - c_lo) + cpc - 1) / cpc;
           int row_chunk = rmax;
           if (zc * ncg < 4 * h->sm_count) row_chunk = std::max(256, (int)((int64_t)rmax * zc * ncg / (4 * h->sm_count)) / 32 * 32 + 32);
           const int nrc = (rmax + row_chunk - 1) / row_chunk;
-          timed(2, [&] { lu_bwd_update_kernel<NR><<<dim3(ncg * nrc, zc, zr), 256, 0, st>>>(D, lst, !fwd_up, c_lo, ncg, row_chunk, nrhs, Y.n, y); });
+          timed(2, [&] {
+            if (upd2_ok)
+              lu_bwd_update2_kernel<NR><<<dim3(ncg * nrc, zc, zr), 256, 0, st>>>(D, lst, !fwd_up, c_lo, ncg, row_chunk, nrhs, Y.n, y);
+            else
+              lu_bwd_update_kernel<NR><<<dim3(ncg * nrc, zc, zr), 256, 0, st>>>(D, lst, !fwd_up, c_lo, ncg, row_chunk, nrhs, Y.n, y);
+          });
           h->launches++;
         }
-        timed(3, [&] { lu_bwd_tri_kernel<<<dim3(zc, nrhs), 1024, 0, st>>>(D, lst, (int)!fwd_up | tri_pf, c_lo, Y.n, y); });
+        timed(3, [&] {
+          if (S.wininv)
+            lu_bwd_win_kernel<<<dim3(zc * LU_WIN_CLUSTER, nrhs), 1024, 0, st>>>(D, lst, (int)!fwd_up, c_lo, Y.n, y);
+          else
+            lu_bwd_tri_kernel<<<dim3(zc, nrhs), 1024, 0, st>>>(D, lst, (int)!fwd_up | tri_pf, c_lo, Y.n, y);
+        });
         h->launches++;
       }
     }
@@ -1137,8 +1705,13 @@ static void lu_sweeps_nr(wae_ctx* h, LuSolver& S, int trans_t, int nrhs, cplx* y
         max_s = std::max(max_s, s);
         max_ld = std::max(max_ld, s + (int)(Y.struct_ptr[k + 1] - Y.struct_ptr[k]));
       }
-      fprintf(stderr, "[wae solve trace]         %5d %7d %6d %7d  %9.3f %9.3f %9.3f %9.3f\n", d, (int)Y.levels[d].size(), max_s, max_ld, tms[d][0], tms[d][1],
-              tms[d][2], tms[d][3]);
+      double mb = 0.0;  // one panel (L or U^T) of every supernode of the depth: what one sweep reads
+      for (int32_t k : Y.levels[d]) {
+        const double s = Y.sn_first[k + 1] - Y.sn_first[k];
+        mb += (s + (double)(Y.struct_ptr[k + 1] - Y.struct_ptr[k])) * s * sizeof(cplx) / 1e6;
+      }
+      fprintf(stderr, "[wae solve trace]         %5d %7d %6d %7d  %9.3f %9.3f %9.3f %9.3f   %8.1f MB  fwd %5.0f bwd %5.0f GB/s\n", d, (int)Y.levels[d].size(), max_s,
+              max_ld, tms[d][0], tms[d][1], tms[d][2], tms[d][3], mb, mb / (tms[d][0] + tms[d][1]), mb / (tms[d][2] + tms[d][3]));
       for (int c = 0; c < 4; c++) tot[c] += tms[d][c];
     }
     fprintf(stderr, "[wae solve trace] total                              %9.3f %9.3f %9.3f %9.3f\n", tot[0], tot[1], tot[2], tot[3]);
