@@ -54,8 +54,10 @@ def test_one_based_context(order):
     for key in ("mk", "b", "q", "u"):
         for a0, a1 in zip(res[0][key], res[1][key]):
             assert np.array_equal(a0 + 1, a1), key
-    for key in ("M", "K", "C"):
+    for key in ("M", "K"):
         assert np.array_equal(res[0][key], res[1][key]), key
+    # (the boundary mass goes through the atomic kernel: the order of the additions is not fixed, equal to rounding)
+    assert np.abs(res[0]["C"] - res[1]["C"]).max() <= 1e-14 * np.abs(res[0]["C"]).max()
     # (the flame source and the solve sweeps sum with atomics: equal to rounding -- times the condition number for x --, not bitwise)
     assert np.abs(res[0]["Q"] - res[1]["Q"]).max() <= 1e-12 * np.abs(res[0]["Q"]).max()
     assert np.abs(res[0]["x"] - res[1]["x"]).max() <= 1e-9 * np.abs(res[0]["x"]).max()

@@ -90,7 +90,8 @@ __global__ void lu_scatter_kernel(const cplx* __restrict__ A, const int64_t* __r
 // sym != 0: the update matrices hold their lower triangle only (x >= y); upper entries are read from the mirror position
 // and only the lower part of the parent front is written (its U^T panel is regenerated from the L panel).
 __global__ void __launch_bounds__(256) lu_extend_add_kernel(LuDev D, const int32_t* __restrict__ children, const int32_t* __restrict__ tile_ptr,
-                                                            int nchild, const cplx* __restrict__ upd_child, cplx* __restrict__ upd_parent, int sym) {
+                                                            int nchild, const cplx* __restrict__ upd_child, cplx* __restrict__ upd_parent, int sym, int part) {
+  // part 0: every target; 1: targets in the parent's pivot panels only; 2: targets in the parent's update matrix only
   // locate the child of this tile
   int t = blockIdx.x;
   int lo = 0, hi = nchild;
@@ -118,15 +119,16 @@ __global__ void __launch_bounds__(256) lu_extend_add_kernel(LuDev D, const int32
     int jb = rel[y];
     cplx* dst;
     if (jb < P.s) {
+      if (part == 2) continue;
       if (ia >= P.s || ia / NB >= jb / NB) dst = P.lp + ia + (size_t)jb * P.ld;
       else if (sym) continue;
       else dst = P.up + jb + (size_t)ia * P.ld;
     } else {
       if (ia < P.s) {
-        if (sym) continue;
+        if (sym || part == 2) continue;
         dst = P.up + jb + (size_t)ia * P.ld;
       } else {
-        if (sym && ia < jb) continue;
+        if (part == 1 || (sym && ia < jb)) continue;
         dst = A22 + (ia - P.s) + (size_t)(jb - P.s) * P.r;
       }
     }
@@ -276,6 +278,160 @@ __global__ void __launch_bounds__(128) lu_panel_kernel(LuDev D, const int32_t* _
   }
 }
 
+// ---- round 2: diagonal block on ONE WARP ---------------------------------------------------------------------------------------
+// Phase 1 (LU): lane i holds row i of the NB x NB block in registers, the pivot row travels by shuffles, every register index is static
+// (fully unrolled).  Phase 2 / 3 (L^-1, U^-1): the factors go to shared memory and lane c computes COLUMN c of the inverse by
+// substitution -- every lane reads the same factor entry at the same time (broadcast), its own column stays in registers, nothing is
+// written to shared memory.  No block barrier at all (round 2a: 64 barriers of a 1024-thread CTA, 34 us per block at the top of the
+// tree, 1.7 ms per launch on the levels with 8000 fronts); two blocks share a 64-thread CTA.  Same LU arithmetic as lu_diag_kernel
+// (multiplier l = T[i][p] / pivot, static perturbation of tiny pivots); the inverses come from substitution instead of Gauss-Jordan.
+__device__ __forceinline__ cplx shfl_c(cplx v, int src) {
+  return make_double2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+
+#define LU_DIAG_WARPS 2
+__global__ void __launch_bounds__(32 * LU_DIAG_WARPS) lu_diag_warp_kernel(LuDev D, const int32_t* __restrict__ list, int nlist, int k, double eps,
+                                                                       int* __restrict__ flag) {
+  __shared__ cplx Fs[LU_DIAG_WARPS][NB][NB + 1];  // the factors, row-major: strict lower = L, upper incl. diagonal = U
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  const int item = blockIdx.x * LU_DIAG_WARPS + wp;
+  if (item >= nlist) return;
+  const int sn = list[item];
+  SnView S = sn_view(D, sn);
+  const int c0 = k * NB;
+  if (c0 >= S.s) return;
+  const int nb = min(NB, S.s - c0);
+  const cplx zero = make_double2(0.0, 0.0), one = make_double2(1.0, 0.0);
+  cplx* blk = S.lp + c0 + (size_t)c0 * S.ld;
+  cplx (*F)[NB + 1] = Fs[wp];
+  cplx* inv = D.dinv + D.dinv_off[sn] + (size_t)k * 2 * NB * NB;
+  {
+    cplx T[NB];
+#pragma unroll
+    for (int j = 0; j < NB; j++)
+      T[j] = (lane < nb && j < nb) ? blk[lane + (size_t)j * S.ld] : (lane == j ? one : zero);  // identity padding of a short last block
+#pragma unroll
+    for (int p = 0; p < NB; p++) {
+      cplx d = shfl_c(T[p], p);
+      const double m = d.x * d.x + d.y * d.y;
+      if (!(m >= eps * eps)) {  // tiny, zero or NaN pivot -> static pivoting (every lane derives the same replacement)
+        if (lane == p) {
+          if (!isfinite(m)) atomicOr(flag, 2);
+          else atomicAdd(flag + 1, 1);
+          if (m == 0.0) atomicOr(flag, 4);
+        }
+        d = make_double2(m > 0.0 && isfinite(m) ? d.x * eps / sqrt(m) : eps, m > 0.0 && isfinite(m) ? d.y * eps / sqrt(m) : 0.0);
+        if (lane == p) T[p] = d;
+      }
+      const bool below = lane > p;
+      const cplx l = cmul(T[p], cinv(d));
+#pragma unroll
+      for (int j = p + 1; j < NB; j++) {
+        const cplx t = shfl_c(T[j], p);
+        if (below) T[j] = csub(T[j], cmul(l, t));
+      }
+      if (below) T[p] = l;
+    }
+    // L \ U back into the panel, U_kk^T into the U^T panel (lower triangle incl. diagonal: lane i owns row i of U = column i there)
+#pragma unroll
+    for (int j = 0; j < NB; j++) {
+      F[lane][j] = T[j];
+      if (lane < nb && j < nb) {
+        blk[lane + (size_t)j * S.ld] = T[j];
+        if (j >= lane) S.up[(c0 + j) + (size_t)(c0 + lane) * S.ld] = T[j];
+      }
+    }
+  }
+  __syncwarp();
+  {
+    // column c = lane of L^-1 (unit lower): x_c = 1, x_i = -sum_{c <= kk < i} L[i][kk] x_kk
+    cplx x[NB];
+#pragma unroll
+    for (int i = 0; i < NB; i++) {
+      cplx acc = zero;
+#pragma unroll
+      for (int kk = 0; kk < i; kk++) {
+        const cplx f = F[i][kk];  // broadcast
+        if (kk >= lane) {
+          acc.x -= f.x * x[kk].x - f.y * x[kk].y;
+          acc.y -= f.x * x[kk].y + f.y * x[kk].x;
+        }
+      }
+      x[i] = i == lane ? one : acc;  // rows above the diagonal: acc == 0
+    }
+    // inv[i + c NB], zero padded (unit diagonal stored for i < nb)
+#pragma unroll
+    for (int i = 0; i < NB; i++) inv[i + lane * NB] = (i < nb && lane < nb && i >= lane) ? x[i] : zero;
+  }
+  {
+    // column c = lane of U^-1 (upper): x_i = (delta_ic - sum_{i < kk <= c} U[i][kk] x_kk) / U[i][i], from i = c upwards
+    cplx x[NB];
+#pragma unroll
+    for (int i = NB - 1; i >= 0; i--) {
+      cplx acc = i == lane ? one : zero;
+#pragma unroll
+      for (int kk = i + 1; kk < NB; kk++) {
+        const cplx f = F[i][kk];
+        if (kk <= lane) {
+          acc.x -= f.x * x[kk].x - f.y * x[kk].y;
+          acc.y -= f.x * x[kk].y + f.y * x[kk].x;
+        }
+      }
+      x[i] = i <= lane ? cmul(acc, cinv(F[i][i])) : zero;
+    }
+#pragma unroll
+    for (int i = 0; i < NB; i++) inv[NB * NB + i + lane * NB] = (i < nb && lane < nb && i <= lane) ? x[i] : zero;
+  }
+}
+
+// ---- round 2: panel rows times the explicit inverse of the diagonal block ---------------------------------------------------------
+//   Lp rows:  X <- X * U_kk^-1        Up rows (general elimination only):  X <- X * L_kk^-T
+// CTA = 64 rows x 4 interleaved column groups (thread: columns g, g + 4, ...): the NB entries of the row are loaded at once, then 8
+// independent accumulators per thread -- instead of the serial substitution of lu_panel_kernel (496 dependent multiply-adds per row).
+__global__ void __launch_bounds__(256) lu_panel_inv_kernel(LuDev D, const int32_t* __restrict__ list, int k, int sym_scale) {
+  const int sn = list[blockIdx.z];
+  SnView S = sn_view(D, sn);
+  const int c0 = k * NB;
+  if (c0 >= S.s) return;
+  const int nb = min(NB, S.s - c0);
+  const int r0 = c0 + nb;
+  const int nrows = S.ld - r0;
+  if ((int)(blockIdx.x * 64) >= nrows) return;
+  const bool upper = blockIdx.y == 1;
+  __shared__ cplx M[NB][NB];  // M[m][j]: x_new[j] = sum_{m <= j} x[m] M[m][j]
+  __shared__ cplx diag[NB];
+  const int row = blockIdx.x * 64 + (threadIdx.x & 63), g = threadIdx.x >> 6;
+  const bool live = row < nrows;
+  cplx* base = (upper ? S.up : S.lp) + (r0 + (live ? row : 0)) + (size_t)c0 * S.ld;
+  cplx x[NB];
+#pragma unroll
+  for (int m = 0; m < NB; m++) x[m] = (live && m < nb) ? base[(size_t)m * S.ld] : make_double2(0.0, 0.0);
+  const cplx* inv = D.dinv + D.dinv_off[sn] + (size_t)k * 2 * NB * NB;
+  for (int e = threadIdx.x; e < NB * NB; e += 256) {
+    const int m = e % NB, j = e / NB;
+    // Lp: U^-1[m][j] at NB^2 + m + j NB;  Up: L^-T[m][j] = L^-1[j][m] at j + m NB
+    M[m][j] = upper ? inv[j + m * NB] : inv[NB * NB + m + j * NB];
+  }
+  if (threadIdx.x < NB) diag[threadIdx.x] = threadIdx.x < nb ? S.lp[(c0 + threadIdx.x) + (size_t)(c0 + threadIdx.x) * S.ld] : make_double2(0.0, 0.0);
+  __syncthreads();  // M is there -- and the four column groups of a row have all read it before any of them overwrites its columns
+  if (!live) return;
+#pragma unroll
+  for (int u = 0; u < NB / 4; u++) {
+    const int j = g + 4 * u;
+    cplx acc = make_double2(0.0, 0.0);
+#pragma unroll
+    for (int m = 0; m <= 4 * u + 3; m++) {  // m <= j; the entries of the inverse below the diagonal are zero
+      const cplx c = M[m][j];
+      acc.x += x[m].x * c.x - x[m].y * c.y;
+      acc.y += x[m].x * c.y + x[m].y * c.x;
+    }
+    if (j < nb) {
+      base[(size_t)j * S.ld] = acc;
+      if (sym_scale) S.up[(r0 + row) + (size_t)(c0 + j) * S.ld] = cmul(acc, diag[j]);
+    }
+  }
+}
+
 // ---- complex GEMM  C -= A * B^T  on the FP64 tensor cores -----------------------------------------------
 // A: m x K (lda), B: n x K (ldb), C: m x n (ldc), all column-major complex.  CTA tile 64x64, 8 warps (4 along m,
 // 2 along n), warp tile 16x32 = 2x4 DMMA m8n8k4 tiles, K tile 16, operands split into re/im planes in smem.
@@ -289,6 +445,7 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
 
 struct GemmProblem {
   int m, n, K, lda, ldb, ldc;
+  bool beta0;  // C = -A B^T (C is not read: the Schur complement of a front whose update matrix receives its children afterwards)
   const cplx *A, *B;
   cplx* C;
 };
@@ -353,7 +510,7 @@ __device__ __forceinline__ void zgemm_nt_tile(const GemmProblem& P, int tile_m, 
         int row = m0 + wm + a * 8 + (lane >> 2), col = n0 + wn + b * 8 + (lane & 3) * 2 + e;
         if (row < P.m && col < P.n) {
           cplx* c = P.C + row + (size_t)col * P.ldc;
-          cplx v = *c;
+          cplx v = P.beta0 ? make_double2(0.0, 0.0) : *c;
           v.x -= acc_r[a][b][e];
           v.y -= acc_i[a][b][e];
           *c = v;
@@ -445,7 +602,7 @@ __device__ __forceinline__ void zgemm_nt_tile_async(const GemmProblem& P, int ti
         int row = m0 + wm + a * 8 + (lane >> 2), col = n0 + wn + b * 8 + (lane & 3) * 2 + e;
         if (row < P.m && col < P.n) {
           cplx* c = P.C + row + (size_t)col * P.ldc;
-          cplx v = *c;
+          cplx v = P.beta0 ? make_double2(0.0, 0.0) : *c;
           v.x -= acc_r[a][b][e];
           v.y -= acc_i[a][b][e];
           *c = v;
@@ -463,7 +620,9 @@ __global__ void __launch_bounds__(256) lu_gemm_kernel(LuDev D, const int32_t* __
   const int sn = list[blockIdx.z];
   SnView S = sn_view(D, sn);
   GemmProblem P;
+  P.beta0 = false;
   if (mode == 2) {
+    P.beta0 = (sym & 4) != 0;
     if (S.r == 0) return;
     if ((sym & 1) && blockIdx.y > blockIdx.x) return;  // symmetric Schur complement: lower tiles only
     P.m = P.n = S.r; P.K = S.s;
@@ -1390,6 +1549,13 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
   const int upd_flag = (sym ? 1 : 0) | ((getenv("WAE_LU_SKIP_UPPER") && !atoi(getenv("WAE_LU_SKIP_UPPER"))) ? 0 : 2);  // pivot-block updates only; default: skip
   // symmetric elimination: U^T panel = L panel * D inside the panel kernel (WAE_LU_SYM_PANEL=0: round-1 path, copy + second solve)
   const bool sym_panel = !(getenv("WAE_LU_SYM_PANEL") && !atoi(getenv("WAE_LU_SYM_PANEL")));
+  // round-2 kernels, each with its switch for A/B runs: one-warp diagonal blocks, panel rows times the explicit inverse, Schur complement
+  // written instead of accumulated
+  // (measured on config 2: the one-warp diagonal block wins where a launch holds >= 1024 blocks -- 1.07 vs 1.70 ms on the 8000-front levels --
+  // and loses where a launch is one block on one warp, 58 vs 34 us; the inverse-times-row panel wins only on launches of one or two fronts)
+  const int diag_warp_min = getenv("WAE_LU_DIAG") ? atoi(getenv("WAE_LU_DIAG")) : 1024;   // 0: never
+  const int panel_inv_max = (!sym || sym_panel) ? (getenv("WAE_LU_PANEL") ? atoi(getenv("WAE_LU_PANEL")) : 2) : 0;  // 0: never
+  const bool late_xadd = !(getenv("WAE_LU_LATE_XADD") && !atoi(getenv("WAE_LU_LATE_XADD")));
   // WAE_LU_TRACE=1 (diagnostic): every launch class is timed with its own pair of events (serialising the stream) and summed per tree
   // depth; the table goes to stderr and the totals to wae_last_ms("lu_trace_<class>")
   const bool trace = getenv("WAE_LU_TRACE") != nullptr;
@@ -1421,14 +1587,18 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
     const std::vector<int32_t>& L = Y.levels[d];
     const int nl = (int)L.size();
     cplx* upd = S.d_upd[d & 1].p;
-    if (Y.level_upd_size[d]) timed(T_MEMSET, [&] { CUDA_CHECK(cudaMemsetAsync(upd, 0, (size_t)Y.level_upd_size[d] * sizeof(cplx), st)); });
-    if (d < maxd && S.xa_tiles[d + 1] > 0) {
+    // late_xadd (default): the Schur complement is WRITTEN (C = -A B^T, no memset and no read of C) and the children's contributions to
+    // the update matrix are added after it; only their contributions to the pivot panels have to be there before the factorisation
+    if (Y.level_upd_size[d] && !late_xadd) timed(T_MEMSET, [&] { CUDA_CHECK(cudaMemsetAsync(upd, 0, (size_t)Y.level_upd_size[d] * sizeof(cplx), st)); });
+    const bool has_children = d < maxd && S.xa_tiles[d + 1] > 0;
+    auto xadd = [&](int part) {
       timed(T_XADD, [&] {
         lu_extend_add_kernel<<<S.xa_tiles[d + 1], dim3(32, 8), 0, st>>>(D, S.d_level[d + 1].p, S.d_xa_tile_ptr[d + 1].p,
-                                                                          (int)Y.levels[d + 1].size(), S.d_upd[(d + 1) & 1].p, upd, sym);
+                                                                          (int)Y.levels[d + 1].size(), S.d_upd[(d + 1) & 1].p, upd, sym, part);
       });
       h->launches++;
-    }
+    };
+    if (has_children) xadd(late_xadd ? 1 : 0);
     // blocked partial factorisation of all fronts of this depth
     int max_s = 0, max_ld = 0, max_r = 0;
     for (int32_t k : L) {
@@ -1446,7 +1616,12 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
       for (int z0 = 0; z0 < cnt; z0 += 32768) {
         int zc = std::min(32768, cnt - z0);
         const int32_t* lst = S.d_level[d].p + z0;
-        timed(T_DIAG, [&] { lu_diag_kernel<<<zc, dim3(NB, NB), 0, st>>>(D, lst, k, S.pivot_eps, S.d_flag.p); });
+        timed(T_DIAG, [&] {
+          if (diag_warp_min > 0 && zc >= diag_warp_min)
+            lu_diag_warp_kernel<<<(zc + LU_DIAG_WARPS - 1) / LU_DIAG_WARPS, 32 * LU_DIAG_WARPS, 0, st>>>(D, lst, zc, k, S.pivot_eps, S.d_flag.p);
+          else
+            lu_diag_kernel<<<zc, dim3(NB, NB), 0, st>>>(D, lst, k, S.pivot_eps, S.d_flag.p);
+        });
         int rows = max_ld - k * NB - 1;  // upper bound of ld - (c0 + nb) over the batch (nb >= 1)
         if (rows > 0) {
           if (sym && !sym_panel) {
@@ -1454,7 +1629,12 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
             h->launches++;
           }
           const int py = (sym && sym_panel) ? 1 : 2;
-          timed(T_PANEL, [&] { lu_panel_kernel<<<dim3((rows + 127) / 128, py, zc), 128, 0, st>>>(D, lst, k, py == 1); });
+          timed(T_PANEL, [&] {
+            if (zc <= panel_inv_max)
+              lu_panel_inv_kernel<<<dim3((rows + 63) / 64, py, zc), 256, 0, st>>>(D, lst, k, py == 1);
+            else
+              lu_panel_kernel<<<dim3((rows + 127) / 128, py, zc), 128, 0, st>>>(D, lst, k, py == 1);
+          });
           // inner update: columns of the current outer block only
           const int c0 = (k + 1) * NB;
           const int oend = (k / nbo_blocks + 1) * nbo_blocks * NB;  // end column of the outer block
@@ -1486,9 +1666,10 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
       for (int z0 = 0; z0 < nl; z0 += 32768) {
         int zc = std::min(32768, nl - z0);
         dim3 g((max_r + GT - 1) / GT, (max_r + GT - 1) / GT, zc);
-        timed(T_SCHUR, [&] { gemm(g, S.d_level[d].p + z0, 2, 0, 0, 0, 0, upd, sym); });
+        timed(T_SCHUR, [&] { gemm(g, S.d_level[d].p + z0, 2, 0, 0, 0, 0, upd, sym | (late_xadd ? 4 : 0)); });
         h->launches++;
       }
+      if (late_xadd && has_children) xadd(2);
     }
   }
   // window inverses for the solves (WAE_LU_WININV=0: round-1 solve kernels, block-by-block substitution inside a window)
@@ -1538,7 +1719,16 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
         fprintf(stderr, " %10.3f", tms[d][c]);
         tot[c] += tms[d][c];
       }
-      fprintf(stderr, "\n");
+      // useful work of the depth (8 real flops per complex multiply-add; symmetric mode: lower halves only) and the rate it ran at
+      double f_schur = 0.0, f_piv = 0.0;
+      for (int32_t k : Y.levels[d]) {
+        const double s = Y.sn_first[k + 1] - Y.sn_first[k], r = (double)(Y.struct_ptr[k + 1] - Y.struct_ptr[k]);
+        f_schur += 8.0 * r * r * s * (sym ? 0.5 : 1.0);
+        f_piv += 8.0 * (s * s * s / 3.0 + r * s * s * (sym ? 0.5 : 1.0));  // LU of the pivot block + the panel updates
+      }
+      const double t_piv = tms[d][T_DIAG] + tms[d][T_COPY] + tms[d][T_PANEL] + tms[d][T_GIN] + tms[d][T_GOUT];
+      fprintf(stderr, "   schur %6.1f GF %5.1f TF/s   pivot block %6.1f GF %5.1f TF/s\n", f_schur / 1e9, tms[d][T_SCHUR] > 0 ? f_schur / tms[d][T_SCHUR] / 1e9 : 0.0,
+              f_piv / 1e9, t_piv > 0 ? f_piv / t_piv / 1e9 : 0.0);
     }
     fprintf(stderr, "[wae lu trace] total                      ");
     for (int c = 0; c < T_N; c++) {
