@@ -54,7 +54,11 @@ int32_t wae_sync(wae_ctx* h);
 /* Number of kernels this library has launched since creation (bench.py: gpu_launches). */
 int64_t wae_launch_count(wae_ctx* h);
 /* Device-side duration of the most recent call of the named phase, in ms (CUDA events on the
- * context stream).  Phases: "assemble", "combine", "factor", "solve", "spmv", "eigs". */
+ * context stream).  Phases: "assemble", "combine", "factor", "solve", "spmv", "eigs".
+ * Further keys (plain numbers, not times): "factor_sym" (1 if the last factorisation used the symmetric
+ * elimination), "static_pivots" / "zero_pivots" (perturbed / exactly zero pivots of the last factorisation),
+ * "eigs_residual" (worst relative Ritz residual of the pairs the last wae_eigs_si / wae_eigs_si_pair
+ * returned), "star_*" (layout of the assembly program), "lu_trace_*" (WAE_LU_TRACE=1).  -1 if never set. */
 double wae_last_ms(wae_ctx* h, const char* phase);
 
 /* ---- mesh + element DOF lists ---------------------------------------------------

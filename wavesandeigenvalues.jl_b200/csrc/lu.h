@@ -46,6 +46,9 @@ struct LuSolver {
   DevBuf<int64_t> d_struct_ptr, d_lp_off, d_up_off, d_upd_off, d_dinv_off, d_amap;
   DevBuf<int32_t> d_colidx_nz;         // column index of every nonzero of A (for the scaling in the scatter)
   std::vector<DevBuf<int32_t>> d_level;  // supernode ids per depth
+  std::vector<int32_t> level_half[2];      // per depth, concatenated: the even / odd entries of the size-sorted list (two front groups)
+  std::vector<int64_t> level_half_ptr[2];  // depth d: [ptr[d], ptr[d + 1])
+  DevBuf<int32_t> d_level_half[2];
   std::vector<DevBuf<int32_t>> d_xa_tile_ptr;  // per depth: extend-add tile prefix over the supernodes of that depth
   std::vector<int32_t> xa_tiles;       // per depth: number of extend-add tiles
   DevBuf<cplx> d_Aval;                 // copy of the factorised matrix (iterative refinement)

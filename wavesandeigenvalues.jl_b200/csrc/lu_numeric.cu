@@ -14,6 +14,7 @@
 // C -= A B^T on the FP64 tensor cores (mma.sync m8n8k4 f64 -> SASS DMMA.8x8x4).
 // No pivoting across blocks (the symbolic structure is static); tiny pivots are replaced (static
 // pivoting) and the solve applies iterative refinement against the original matrix.
+#include <cuda_profiler_api.h>
 #include <cuda_runtime.h>
 
 #include <array>
@@ -1460,6 +1461,15 @@ void wae_lu_setup_device(wae_ctx* h, LuSolver& S) {
     });
     S.d_level[d].upload(L, st);
   }
+  for (int g = 0; g < 2; g++) {  // two front groups per depth (both stay sorted by pivot size)
+    S.level_half[g].clear();
+    S.level_half_ptr[g].assign(Y.levels.size() + 1, 0);
+    for (size_t d = 0; d < Y.levels.size(); d++) {
+      for (size_t i = g; i < Y.levels[d].size(); i += 2) S.level_half[g].push_back(Y.levels[d][i]);
+      S.level_half_ptr[g][d + 1] = (int64_t)S.level_half[g].size();
+    }
+    S.d_level_half[g].upload(S.level_half[g].empty() ? std::vector<int32_t>(1, 0) : S.level_half[g], st);
+  }
   S.d_xa_tile_ptr.resize(Y.levels.size());
   S.xa_tiles.assign(Y.levels.size(), 0);
   for (size_t d = 0; d < Y.levels.size(); d++) {
@@ -1540,11 +1550,11 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
     if (cudaFuncSetAttribute(lu_gemm_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
       cudaGetLastError();  // a refused hint must not surface as a launch error
   }
-  auto gemm = [&](dim3 g, const int32_t* lst, int mode, int k0, int kw, int c0, int cap, cplx* upd_, int flag) {
+  auto gemm = [&](cudaStream_t s, dim3 g, const int32_t* lst, int mode, int k0, int kw, int c0, int cap, cplx* upd_, int flag) {
     if (gemm_ring)
-      lu_gemm_kernel<1><<<g, 256, GP_SMEM, st>>>(D, lst, mode, k0, kw, c0, cap, upd_, flag);
+      lu_gemm_kernel<1><<<g, 256, GP_SMEM, s>>>(D, lst, mode, k0, kw, c0, cap, upd_, flag);
     else
-      lu_gemm_kernel<0><<<g, 256, 0, st>>>(D, lst, mode, k0, kw, c0, cap, upd_, flag);
+      lu_gemm_kernel<0><<<g, 256, 0, s>>>(D, lst, mode, k0, kw, c0, cap, upd_, flag);
   };
   const int upd_flag = (sym ? 1 : 0) | ((getenv("WAE_LU_SKIP_UPPER") && !atoi(getenv("WAE_LU_SKIP_UPPER"))) ? 0 : 2);  // pivot-block updates only; default: skip
   // symmetric elimination: U^T panel = L panel * D inside the panel kernel (WAE_LU_SYM_PANEL=0: round-1 path, copy + second solve)
@@ -1556,6 +1566,21 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
   const int diag_warp_min = getenv("WAE_LU_DIAG") ? atoi(getenv("WAE_LU_DIAG")) : 1024;   // 0: never
   const int panel_inv_max = (!sym || sym_panel) ? (getenv("WAE_LU_PANEL") ? atoi(getenv("WAE_LU_PANEL")) : 2) : 0;  // 0: never
   const bool late_xadd = !(getenv("WAE_LU_LATE_XADD") && !atoi(getenv("WAE_LU_LATE_XADD")));
+  const bool two_groups = !(getenv("WAE_LU_GROUPS") && atoi(getenv("WAE_LU_GROUPS")) == 1);
+  const int prof_depth = getenv("WAE_LU_PROFILE_DEPTH") ? atoi(getenv("WAE_LU_PROFILE_DEPTH")) : -1;
+  if (two_groups && !h->aux_stream[0]) {
+    // group 0 on a high-priority stream, group 1 on a low-priority one: CTAs are dispatched kernel by kernel, so with equal priorities the
+    // small kernels of one group would queue behind the whole GEMM grid of the other; with priorities group 0 never waits and group 1's
+    // GEMMs fill the gaps its serial steps leave (WAE_LU_GROUPS=3: equal priorities)
+    int prio_lo = 0, prio_hi = 0;
+    CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    const bool equal_prio = getenv("WAE_LU_GROUPS") && atoi(getenv("WAE_LU_GROUPS")) == 3;
+    for (int g = 0; g < 2; g++) {
+      CUDA_CHECK(cudaStreamCreateWithPriority(&h->aux_stream[g], cudaStreamNonBlocking, equal_prio ? prio_lo : (g == 0 ? prio_hi : prio_lo)));
+      CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_join[g], cudaEventDisableTiming));
+    }
+    CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  }
   // WAE_LU_TRACE=1 (diagnostic): every launch class is timed with its own pair of events (serialising the stream) and summed per tree
   // depth; the table goes to stderr and the totals to wae_last_ms("lu_trace_<class>")
   const bool trace = getenv("WAE_LU_TRACE") != nullptr;
@@ -1599,9 +1624,11 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
       h->launches++;
     };
     if (has_children) xadd(late_xadd ? 1 : 0);
-    // blocked partial factorisation of all fronts of this depth
+    // blocked partial factorisation + Schur complement of a group of fronts of this depth (host list Lh / device list Ld, size-sorted) on stream s_
+    auto front_group = [&](const int32_t* Lh, int nl_, const int32_t* Ld, cudaStream_t s_) {
     int max_s = 0, max_ld = 0, max_r = 0;
-    for (int32_t k : L) {
+    for (int i_ = 0; i_ < nl_; i_++) {
+      const int32_t k = Lh[i_];
       int s = Y.sn_first[k + 1] - Y.sn_first[k], r = (int)(Y.struct_ptr[k + 1] - Y.struct_ptr[k]);
       max_s = std::max(max_s, s);
       max_ld = std::max(max_ld, s + r);
@@ -1611,29 +1638,29 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
     for (int k = 0; k < nsteps; k++) {
       // supernodes with more than k blocks form a prefix of the (size-sorted) list
       int cnt = 0;
-      while (cnt < nl && Y.sn_first[L[cnt] + 1] - Y.sn_first[L[cnt]] > k * NB) cnt++;
+      while (cnt < nl_ && Y.sn_first[Lh[cnt] + 1] - Y.sn_first[Lh[cnt]] > k * NB) cnt++;
       if (!cnt) break;
       for (int z0 = 0; z0 < cnt; z0 += 32768) {
         int zc = std::min(32768, cnt - z0);
-        const int32_t* lst = S.d_level[d].p + z0;
+        const int32_t* lst = Ld + z0;
         timed(T_DIAG, [&] {
           if (diag_warp_min > 0 && zc >= diag_warp_min)
-            lu_diag_warp_kernel<<<(zc + LU_DIAG_WARPS - 1) / LU_DIAG_WARPS, 32 * LU_DIAG_WARPS, 0, st>>>(D, lst, zc, k, S.pivot_eps, S.d_flag.p);
+            lu_diag_warp_kernel<<<(zc + LU_DIAG_WARPS - 1) / LU_DIAG_WARPS, 32 * LU_DIAG_WARPS, 0, s_>>>(D, lst, zc, k, S.pivot_eps, S.d_flag.p);
           else
-            lu_diag_kernel<<<zc, dim3(NB, NB), 0, st>>>(D, lst, k, S.pivot_eps, S.d_flag.p);
+            lu_diag_kernel<<<zc, dim3(NB, NB), 0, s_>>>(D, lst, k, S.pivot_eps, S.d_flag.p);
         });
         int rows = max_ld - k * NB - 1;  // upper bound of ld - (c0 + nb) over the batch (nb >= 1)
         if (rows > 0) {
           if (sym && !sym_panel) {
-            timed(T_COPY, [&] { lu_sym_copy_kernel<<<dim3((rows + 127) / 128, 1, zc), 128, 0, st>>>(D, lst, k); });
+            timed(T_COPY, [&] { lu_sym_copy_kernel<<<dim3((rows + 127) / 128, 1, zc), 128, 0, s_>>>(D, lst, k); });
             h->launches++;
           }
           const int py = (sym && sym_panel) ? 1 : 2;
           timed(T_PANEL, [&] {
             if (zc <= panel_inv_max)
-              lu_panel_inv_kernel<<<dim3((rows + 63) / 64, py, zc), 256, 0, st>>>(D, lst, k, py == 1);
+              lu_panel_inv_kernel<<<dim3((rows + 63) / 64, py, zc), 256, 0, s_>>>(D, lst, k, py == 1);
             else
-              lu_panel_kernel<<<dim3((rows + 127) / 128, py, zc), 128, 0, st>>>(D, lst, k, py == 1);
+              lu_panel_kernel<<<dim3((rows + 127) / 128, py, zc), 128, 0, s_>>>(D, lst, k, py == 1);
           });
           // inner update: columns of the current outer block only
           const int c0 = (k + 1) * NB;
@@ -1642,8 +1669,8 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
           if (tn > 0) {
             dim3 g((max_ld - c0 + GT - 1) / GT, (tn + GT - 1) / GT, zc);
             timed(T_GIN, [&] {
-              gemm(g, lst, 0, k * NB, NB, c0, oend, nullptr, upd_flag);
-              if (!sym) gemm(g, lst, 1, k * NB, NB, c0, oend, nullptr, upd_flag);
+              gemm(s_, g, lst, 0, k * NB, NB, c0, oend, nullptr, upd_flag);
+              if (!sym) gemm(s_, g, lst, 1, k * NB, NB, c0, oend, nullptr, upd_flag);
             });
             h->launches += sym ? 1 : 2;
           }
@@ -1652,8 +1679,8 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
             const int o0 = oend - nbo_blocks * NB;
             dim3 g((max_ld - oend + GT - 1) / GT, (max_s - oend + GT - 1) / GT, zc);
             timed(T_GOUT, [&] {
-              gemm(g, lst, 0, o0, oend - o0, oend, 1 << 30, nullptr, upd_flag);
-              if (!sym) gemm(g, lst, 1, o0, oend - o0, oend, 1 << 30, nullptr, upd_flag);
+              gemm(s_, g, lst, 0, o0, oend - o0, oend, 1 << 30, nullptr, upd_flag);
+              if (!sym) gemm(s_, g, lst, 1, o0, oend - o0, oend, 1 << 30, nullptr, upd_flag);
             });
             h->launches += sym ? 1 : 2;
           }
@@ -1663,12 +1690,44 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
       }
     }
     if (max_r > 0) {
-      for (int z0 = 0; z0 < nl; z0 += 32768) {
-        int zc = std::min(32768, nl - z0);
+      for (int z0 = 0; z0 < nl_; z0 += 32768) {
+        int zc = std::min(32768, nl_ - z0);
         dim3 g((max_r + GT - 1) / GT, (max_r + GT - 1) / GT, zc);
-        timed(T_SCHUR, [&] { gemm(g, S.d_level[d].p + z0, 2, 0, 0, 0, 0, upd, sym | (late_xadd ? 4 : 0)); });
+        // WAE_LU_PROFILE_DEPTH=d (diagnostic): the profiler range covers the Schur-complement launches of depth d (ncu --profile-from-start off)
+        const bool prof = prof_depth == d;
+        if (prof) {
+          cudaStreamSynchronize(s_);
+          cudaProfilerStart();
+        }
+        timed(T_SCHUR, [&] { gemm(s_, g, Ld + z0, 2, 0, 0, 0, 0, upd, sym | (late_xadd ? 4 : 0)); });
+        if (prof) {
+          cudaStreamSynchronize(s_);
+          cudaProfilerStop();
+        }
         h->launches++;
       }
+    }
+    };
+    // two groups of fronts on two auxiliary streams (levels with 2 ... 1023 fronts of more than one block step): the serial chain of small
+    // kernels of one group (diagonal block -> panel -> K = 32 update, 53 times on the top levels) runs under the GEMMs of the other
+    int lvl_max_s = 0, lvl_max_r = 0;
+    for (int32_t k : L) {
+      lvl_max_s = std::max(lvl_max_s, (int)(Y.sn_first[k + 1] - Y.sn_first[k]));
+      lvl_max_r = std::max(lvl_max_r, (int)(Y.struct_ptr[k + 1] - Y.struct_ptr[k]));
+    }
+    if (two_groups && !trace && nl >= 2 && nl < 1024 && lvl_max_s > NB) {
+      CUDA_CHECK(cudaEventRecord(h->ev_fork, st));
+      for (int g = 0; g < 2; g++) {
+        CUDA_CHECK(cudaStreamWaitEvent(h->aux_stream[g], h->ev_fork, 0));
+        const int64_t o = S.level_half_ptr[g][d];
+        front_group(S.level_half[g].data() + o, (int)(S.level_half_ptr[g][d + 1] - o), S.d_level_half[g].p + o, h->aux_stream[g]);
+        CUDA_CHECK(cudaEventRecord(h->ev_join[g], h->aux_stream[g]));
+        CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_join[g], 0));
+      }
+    } else {
+      front_group(L.data(), nl, S.d_level[d].p, st);
+    }
+    if (lvl_max_r > 0) {
       if (late_xadd && has_children) xadd(2);
     }
   }

@@ -59,6 +59,11 @@ int32_t wae_destroy(wae_ctx* h) {
   h->fams.clear();
   h->mats.clear();
   h->patterns.clear();
+  for (int g = 0; g < 2; g++) {
+    if (h->aux_stream[g]) cudaStreamDestroy(h->aux_stream[g]);
+    if (h->ev_join[g]) cudaEventDestroy(h->ev_join[g]);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   delete h;

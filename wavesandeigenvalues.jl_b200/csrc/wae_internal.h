@@ -154,6 +154,10 @@ struct wae_ctx {
   std::map<std::string, double> last_ms;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   int sm_count = 148;
+  // two auxiliary streams + fork / join events: the numeric LU runs the fronts of a tree level in two groups, so that the latency-bound
+  // diagonal-block / panel steps of one group run under the GEMMs of the other (created on first use, destroyed with the context)
+  cudaStream_t aux_stream[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
 
   // mesh
   int order = 0, nloc = 0, nloc3 = 0;
