@@ -142,15 +142,16 @@ __global__ void __launch_bounds__(256) lu_extend_add_kernel(LuDev D, const int32
 // ---- step k, part 1: LU of the NB x NB diagonal block (no pivoting, static perturbation) ------------
 // One thread per entry, ONE barrier per pivot: every thread forms its multiplier l_i = T[i][p] / pivot itself from the unscaled column
 // (the owner of L[i][p] stores it one barrier later, when nobody reads column p any more), and the same row operations are applied to
-// an identity block in the same step, which yields L^-1 for free (Gauss-Jordan).  U^-1 follows from a second sweep (columns last to
-// first, again one barrier each).  Both inverses are kept for the triangular solves (a block step there is a matrix-vector product).
+// an identity block in the same step, which yields L^-1 for free (Gauss-Jordan); U^-1 comes out of the same sweep through the
+// transposed problem (see below).  Both inverses are kept: the panel and the triangular solves multiply by them.
 __global__ void __launch_bounds__(NB * NB) lu_diag_kernel(LuDev D, const int32_t* __restrict__ list, int k, double eps, int* __restrict__ flag) {
   SnView S = sn_view(D, list[blockIdx.x]);
   const int c0 = k * NB;
   if (c0 >= S.s) return;
   const int nb = min(NB, S.s - c0);
   __shared__ cplx T[NB][NB + 1];  // in place: strict lower = L, upper incl. diagonal = U
-  __shared__ cplx X[NB][NB + 1];  // strict lower = L^-1 (unit diagonal implied), upper incl. diagonal = U^-1
+  __shared__ cplx X[NB][NB + 1];  // strict lower = L^-1 (unit diagonal implied); upper incl. diagonal = U^-1, built as the transpose
+                                  // of Z = (U^T)^-1: Z[a][b] (a >= b) lives at X[b][a]
   __shared__ cplx piv[NB];        // pivots after the static perturbation
   const int i = threadIdx.x, j = threadIdx.y;  // element (row i, col j)
   const cplx zero = make_double2(0.0, 0.0), one = make_double2(1.0, 0.0);
@@ -158,7 +159,12 @@ __global__ void __launch_bounds__(NB * NB) lu_diag_kernel(LuDev D, const int32_t
   T[i][j] = (i < nb && j < nb) ? blk[i + (size_t)j * S.ld] : (i == j ? one : zero);  // identity padding of a short last block
   X[i][j] = i == j ? one : zero;
   __syncthreads();
-  cplx lown = zero;
+  // One sweep, one barrier per pivot.  Row p of U is final when step p starts, and so is column p of W = U^T (W[i][p] = U[p][i]): the
+  // forward Gauss-Jordan step of the LOWER triangular W on an identity block -- row p scaled by 1 / pivot, rows below minus W[i][p] times
+  // it -- runs in the same step as the elimination of column p of T and the Gauss-Jordan step for L^-1 (round 2a: a second sweep of NB
+  // barriers for U^-1).  Every thread forms its multiplier / scaled entry itself from the unscaled values; the owners store them one
+  // barrier later, when nobody reads them any more.
+  cplx lown = zero, zown = zero;
   for (int p = 0; p < nb; p++) {
     cplx d = T[p][p];
     const double m = d.x * d.x + d.y * d.y;
@@ -170,35 +176,40 @@ __global__ void __launch_bounds__(NB * NB) lu_diag_kernel(LuDev D, const int32_t
       }
       d = make_double2(m > 0.0 && isfinite(m) ? d.x * eps / sqrt(m) : eps, m > 0.0 && isfinite(m) ? d.y * eps / sqrt(m) : 0.0);
     }
+    const cplx di = cinv(d);
     if (i == p && j == p) piv[p] = d;
+    cplx tnew = zero, xnew = zero, znew = zero;
+    bool tw = false, xw = false, zw = false;
     if (i > p) {
-      const cplx l = cmul(T[i][p], cinv(d));
-      if (j > p)
-        T[i][j] = csub(T[i][j], cmul(l, T[p][j]));
-      else if (j == p) {
+      const cplx l = cmul(T[i][p], di);
+      if (j > p) {
+        tnew = csub(T[i][j], cmul(l, T[p][j]));
+        tw = true;
+      } else if (j == p) {
         lown = l;
-        X[i][p] = make_double2(-l.x, -l.y);  // row i of the identity block minus l times row p (unit diagonal)
-      } else
-        X[i][j] = csub(X[i][j], cmul(l, X[p][j]));
+        xnew = make_double2(-l.x, -l.y);  // row i of the identity block minus l times row p (unit diagonal)
+        xw = true;
+      } else {
+        xnew = csub(X[i][j], cmul(l, X[p][j]));
+        xw = true;
+      }
+      if (j <= p) {  // Z[i][j] -= W[i][p] * (Z[p][j] / pivot),  W[i][p] = U[p][i] = T[p][i]
+        znew = csub(X[j][i], cmul(T[p][i], cmul(X[j][p], di)));
+        zw = true;
+      }
+    } else if (i == p && j <= p) {
+      zown = cmul(X[j][p], di);  // row p of Z, scaled
     }
+    // writes of this step that nobody else reads in this step (own element only): rows i > p are read by their owners alone
+    if (tw) T[i][j] = tnew;
+    if (xw) X[i][j] = xnew;
+    if (zw) X[j][i] = znew;
     __syncthreads();
-    if (j == p && i > p) T[i][p] = lown;  // column p is not read any more
+    if (j == p && i > p) T[i][p] = lown;   // column p of T is not read any more
+    if (i == p && j <= p) X[j][p] = zown;  // row p of Z is not read any more
   }
   if (i == j && i < nb) T[i][i] = piv[i];
   __syncthreads();
-  // U^-1 by Gauss-Jordan from the last column to the first: row p of the right-hand block is final up to the division by the pivot when
-  // column p is eliminated; the rows above use the unscaled row and the (unchanged) entries U[i][p]
-  cplx uown = zero;  // entry (i, j), i <= j, of U^-1: final at step p = i (row p itself stays unscaled in shared memory)
-  for (int p = nb - 1; p >= 0; p--) {
-    if (j >= p && i <= p) {
-      const cplx xp = cmul(X[p][j], cinv(T[p][p]));  // final entry (p, j) of U^-1
-      if (i == p)
-        uown = xp;
-      else
-        X[i][j] = csub(X[i][j], cmul(T[i][p], xp));
-    }
-    __syncthreads();
-  }
   if (i < nb && j < nb) {
     blk[i + (size_t)j * S.ld] = T[i][j];
     // U_kk^T into the U^T panel (lower triangle incl. diagonal)
@@ -209,7 +220,7 @@ __global__ void __launch_bounds__(NB * NB) lu_diag_kernel(LuDev D, const int32_t
   cplx* inv = D.dinv + D.dinv_off[list[blockIdx.x]] + (size_t)k * 2 * NB * NB;
   const bool in = i < nb && j < nb;
   inv[i + j * NB] = i > j ? (in ? X[i][j] : zero) : (i == j && i < nb ? one : zero);
-  inv[NB * NB + i + j * NB] = (i <= j && in) ? uown : zero;
+  inv[NB * NB + i + j * NB] = (i <= j && in) ? X[i][j] : zero;  // U^-1[i][j] = Z[j][i]
 }
 
 // ---- step k, part 2: panel solves below the diagonal block -------------------------------------------
@@ -387,9 +398,10 @@ __global__ void __launch_bounds__(32 * LU_DIAG_WARPS) lu_diag_warp_kernel(LuDev 
 
 // ---- round 2: panel rows times the explicit inverse of the diagonal block ---------------------------------------------------------
 //   Lp rows:  X <- X * U_kk^-1        Up rows (general elimination only):  X <- X * L_kk^-T
-// CTA = 64 rows x 4 interleaved column groups (thread: columns g, g + 4, ...): the NB entries of the row are loaded at once, then 8
-// independent accumulators per thread -- instead of the serial substitution of lu_panel_kernel (496 dependent multiply-adds per row).
-__global__ void __launch_bounds__(256) lu_panel_inv_kernel(LuDev D, const int32_t* __restrict__ list, int k, int sym_scale) {
+// One thread per row as in lu_panel_kernel, but a PRODUCT with the inverse the diagonal-block kernel keeps instead of a substitution: the
+// 528 multiply-adds of a row are independent accumulations (the substitution is a chain of 496 dependent ones: 19 us per launch on the
+// top levels, where the step is pure latency).
+__global__ void __launch_bounds__(128) lu_panel_inv_kernel(LuDev D, const int32_t* __restrict__ list, int k, int sym_scale) {
   const int sn = list[blockIdx.z];
   SnView S = sn_view(D, sn);
   const int c0 = k * NB;
@@ -397,38 +409,44 @@ __global__ void __launch_bounds__(256) lu_panel_inv_kernel(LuDev D, const int32_
   const int nb = min(NB, S.s - c0);
   const int r0 = c0 + nb;
   const int nrows = S.ld - r0;
-  if ((int)(blockIdx.x * 64) >= nrows) return;
+  if ((int)(blockIdx.x * 128) >= nrows) return;
   const bool upper = blockIdx.y == 1;
   __shared__ cplx M[NB][NB];  // M[m][j]: x_new[j] = sum_{m <= j} x[m] M[m][j]
   __shared__ cplx diag[NB];
-  const int row = blockIdx.x * 64 + (threadIdx.x & 63), g = threadIdx.x >> 6;
+  const int row = blockIdx.x * 128 + threadIdx.x;
   const bool live = row < nrows;
   cplx* base = (upper ? S.up : S.lp) + (r0 + (live ? row : 0)) + (size_t)c0 * S.ld;
   cplx x[NB];
 #pragma unroll
   for (int m = 0; m < NB; m++) x[m] = (live && m < nb) ? base[(size_t)m * S.ld] : make_double2(0.0, 0.0);
   const cplx* inv = D.dinv + D.dinv_off[sn] + (size_t)k * 2 * NB * NB;
-  for (int e = threadIdx.x; e < NB * NB; e += 256) {
+  for (int e = threadIdx.x; e < NB * NB; e += 128) {
     const int m = e % NB, j = e / NB;
     // Lp: U^-1[m][j] at NB^2 + m + j NB;  Up: L^-T[m][j] = L^-1[j][m] at j + m NB
     M[m][j] = upper ? inv[j + m * NB] : inv[NB * NB + m + j * NB];
   }
   if (threadIdx.x < NB) diag[threadIdx.x] = threadIdx.x < nb ? S.lp[(c0 + threadIdx.x) + (size_t)(c0 + threadIdx.x) * S.ld] : make_double2(0.0, 0.0);
-  __syncthreads();  // M is there -- and the four column groups of a row have all read it before any of them overwrites its columns
+  __syncthreads();
   if (!live) return;
+  cplx* ub = S.up + (r0 + row) + (size_t)c0 * S.ld;
 #pragma unroll
-  for (int u = 0; u < NB / 4; u++) {
-    const int j = g + 4 * u;
-    cplx acc = make_double2(0.0, 0.0);
+  for (int j = 0; j < NB; j++) {
+    cplx a0 = make_double2(0.0, 0.0), a1 = make_double2(0.0, 0.0);  // two chains per column
 #pragma unroll
-    for (int m = 0; m <= 4 * u + 3; m++) {  // m <= j; the entries of the inverse below the diagonal are zero
+    for (int m = 0; m <= j; m++) {
       const cplx c = M[m][j];
-      acc.x += x[m].x * c.x - x[m].y * c.y;
-      acc.y += x[m].x * c.y + x[m].y * c.x;
+      if (m & 1) {
+        a1.x += x[m].x * c.x - x[m].y * c.y;
+        a1.y += x[m].x * c.y + x[m].y * c.x;
+      } else {
+        a0.x += x[m].x * c.x - x[m].y * c.y;
+        a0.y += x[m].x * c.y + x[m].y * c.x;
+      }
     }
     if (j < nb) {
+      const cplx acc = make_double2(a0.x + a1.x, a0.y + a1.y);
       base[(size_t)j * S.ld] = acc;
-      if (sym_scale) S.up[(r0 + row) + (size_t)(c0 + j) * S.ld] = cmul(acc, diag[j]);
+      if (sym_scale) ub[(size_t)j * S.ld] = cmul(acc, diag[j]);
     }
   }
 }
@@ -1564,7 +1582,7 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
   // (measured on config 2: the one-warp diagonal block wins where a launch holds >= 1024 blocks -- 1.07 vs 1.70 ms on the 8000-front levels --
   // and loses where a launch is one block on one warp, 58 vs 34 us; the inverse-times-row panel wins only on launches of one or two fronts)
   const int diag_warp_min = getenv("WAE_LU_DIAG") ? atoi(getenv("WAE_LU_DIAG")) : 1024;   // 0: never
-  const int panel_inv_max = (!sym || sym_panel) ? (getenv("WAE_LU_PANEL") ? atoi(getenv("WAE_LU_PANEL")) : 2) : 0;  // 0: never
+  const int panel_inv_max = (!sym || sym_panel) ? (getenv("WAE_LU_PANEL") ? atoi(getenv("WAE_LU_PANEL")) : (1 << 30)) : 0;  // 0: never
   const bool late_xadd = !(getenv("WAE_LU_LATE_XADD") && !atoi(getenv("WAE_LU_LATE_XADD")));
   const bool two_groups = !(getenv("WAE_LU_GROUPS") && atoi(getenv("WAE_LU_GROUPS")) == 1);
   const int prof_depth = getenv("WAE_LU_PROFILE_DEPTH") ? atoi(getenv("WAE_LU_PROFILE_DEPTH")) : -1;
@@ -1658,7 +1676,7 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
           const int py = (sym && sym_panel) ? 1 : 2;
           timed(T_PANEL, [&] {
             if (zc <= panel_inv_max)
-              lu_panel_inv_kernel<<<dim3((rows + 63) / 64, py, zc), 256, 0, s_>>>(D, lst, k, py == 1);
+              lu_panel_inv_kernel<<<dim3((rows + 127) / 128, py, zc), 128, 0, s_>>>(D, lst, k, py == 1);
             else
               lu_panel_kernel<<<dim3((rows + 127) / 128, py, zc), 128, 0, s_>>>(D, lst, k, py == 1);
           });

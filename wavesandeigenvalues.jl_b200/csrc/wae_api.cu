@@ -252,7 +252,7 @@ int32_t wae_assemble(wae_ctx* h, int32_t pattern_id, int32_t kind, const double*
   const bool use_star = use_gather && asm_generation(h) == 3 && wae_ensure_star(h, P);
   if (use_star) {
   } else if (use_gather) wae_ensure_gather(h, P); else ensure_slotmap(h, P);
-  DevBuf<double> d_c;
+  DevBuf<double>& d_c = h->scratch_c;
   if (kind != WAE_OP_MASS) upload_c(h, P, c, c_per_elem, d_c);
   int id = reuse_or_new_matrix(h, mat_id, pattern_id, kind == WAE_OP_BOUNDARY, P.nnz, !use_gather);
   Matrix& M = *h->mats[id];
@@ -280,7 +280,7 @@ int32_t wae_assemble_mk(wae_ctx* h, int32_t pattern_id, const double* c, int32_t
   CUDA_CHECK(cudaSetDevice(h->device));
   Pattern& P = h->pat(pattern_id);
   if (P.elem_kind != 3) WAE_THROW(WAE_E_INVALID, "wae_assemble_mk needs a tetrahedral pattern");
-  DevBuf<double> d_c;
+  DevBuf<double>& d_c = h->scratch_c;
   upload_c(h, P, c, c_per_elem, d_c);
   const bool use_gather = c_per_elem == 1 && !getenv("WAE_FORCE_ATOMIC");
   int im = reuse_or_new_matrix(h, mass_id, pattern_id, false, P.nnz, !use_gather);
@@ -375,13 +375,13 @@ int32_t wae_assemble_flame(wae_ctx* h, int64_t n_flame, const int64_t* flame_tet
   }
   std::vector<int32_t> colsrc(nloc);
   for (int c = 0; c < nloc; c++) colsrc[c] = cols[c].second;
-  DevBuf<int32_t> d_ft, d_rowpos, d_colsrc;
-  DevBuf<double> d_S, d_G;
+  DevBuf<int32_t>&d_ft = h->scratch_i[0], &d_rowpos = h->scratch_i[1], &d_colsrc = h->scratch_i[2];
+  DevBuf<double>&d_S = h->scratch_d[0], &d_G = h->scratch_d[1];
   d_ft.upload(ft, h->stream);
   d_rowpos.upload(rowpos, h->stream);
   d_colsrc.upload(colsrc, h->stream);
-  d_S.alloc(nr + 1);
-  d_G.alloc(nloc);
+  d_S.reserve(nr + 1);
+  d_G.reserve(nloc);
   CUDA_CHECK(cudaMemsetAsync(d_S.p, 0, (nr + 1) * sizeof(double), h->stream));
   int mid = reuse_or_new_matrix(h, mat_id, pid, false, P.nnz);
   PhaseTimer t(h, "assemble");

@@ -157,6 +157,10 @@ struct wae_ctx {
   // two auxiliary streams + fork / join events: the numeric LU runs the fronts of a tree level in two groups, so that the latency-bound
   // diagonal-block / panel steps of one group run under the GEMMs of the other (created on first use, destroyed with the context)
   cudaStream_t aux_stream[2] = {nullptr, nullptr};
+  // device scratch of the assembly entry points (speed of sound, flame work arrays): kept between calls -- every cudaMalloc / cudaFree is a
+  // device-wide synchronisation under the driver's allocation lock, a dozen of them per re-assembly cost more than the kernels
+  DevBuf<double> scratch_c, scratch_d[2];
+  DevBuf<int32_t> scratch_i[3];
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
 
   // mesh
