@@ -1,6 +1,6 @@
 """Per-kernel histogram of the SASS mnemonics that identify the Blackwell paths of libwae_b200.so (B200_PROFILING.md, "What proves a
 Blackwell-native kernel"): DMMA (FP64 tensor op, mma.sync.m8n8k4.f64 -- tcgen05 has no f64 kind), UBLKCP / UTMALDG (TMA bulk copies),
-SYNCS (mbarrier), LDGSTS (cp.async), UTC*MMA / LDTM / STTM (tcgen05 + TMEM: none expected for an FP64 path), HMMA (legacy tensor path:
+SYNCS (mbarrier), UCGABAR (thread-block-cluster barrier), LDGSTS (cp.async), UTC*MMA / LDTM / STTM (tcgen05 + TMEM: none expected for an FP64 path), HMMA (legacy tensor path:
 none expected), RED / ATOM (atomics).
 
     python tools/sass_ops.py [path to libwae_b200.so] > profiles/r02_sass_ops.txt
@@ -14,7 +14,7 @@ import sys
 so = sys.argv[1] if len(sys.argv) > 1 else os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "wavesandeigenvalues.jl_b200", "libwae_b200.so")
 out = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True, check=True).stdout
 WATCH = [("DMMA", r"\bDMMA\b"), ("UBLKCP", r"\bUBLKCP\b"), ("UBLKPF", r"\bUBLKPF\b"), ("UTMALDG", r"\bUTMALDG\b"), ("UTMASTG", r"\bUTMASTG\b"),
-         ("SYNCS", r"\bSYNCS\b"), ("LDGSTS", r"\bLDGSTS\b"), ("UTCxMMA", r"\bUTC\w*MMA\b"), ("LDTM", r"\bLDTM\b"), ("STTM", r"\bSTTM\b"),
+         ("SYNCS", r"\bSYNCS\b"), ("UCGABAR", r"\bUCGABAR_\w+\b"), ("LDGSTS", r"\bLDGSTS\b"), ("UTCxMMA", r"\bUTC\w*MMA\b"), ("LDTM", r"\bLDTM\b"), ("STTM", r"\bSTTM\b"),
          ("HMMA", r"\bHMMA\b"), ("RED", r"\bREDG?\b"), ("ATOM", r"\bATOM[SG]?\b"), ("LDS", r"\bLDS\b"), ("STS", r"\bSTS\b"), ("SHFL", r"\bSHFL\b"),
          ("BAR", r"\bBAR\b"), ("DFMA", r"\bDFMA\b"), ("DADD", r"\bDADD\b"), ("DMUL", r"\bDMUL\b")]
 kern, rows, arch = None, {}, None

@@ -799,10 +799,11 @@ def _iterate(L, z, maxiter, tol, relax, order, nev, v0, v0_adj, kind, num_order,
                 stats["factor_ms"] = stats.get("factor_ms", 0.0) + ctx.last_ms("factor")
                 stats["combine_factor_wall_s"] = stats.get("combine_factor_wall_s", 0.0) + _t1 - _t0
                 stats["eigs_wall_s"] = stats.get("eigs_wall_s", 0.0) + _t2 - _t1
-            idx = np.argsort(np.abs(lams), kind="stable")
-            lams, v = lams[idx], v[:, idx]
-            idx = np.argsort(np.abs(lams_adj), kind="stable")
-            lams_adj, v_adj = lams_adj[idx], v_adj[:, idx]
+            if nev > 1:  # (one pair: nothing to sort, and v[:, idx] would copy the vectors)
+                idx = np.argsort(np.abs(lams), kind="stable")
+                lams, v = lams[idx], v[:, idx]
+                idx = np.argsort(np.abs(lams_adj), kind="stable")
+                lams_adj, v_adj = lams_adj[idx], v_adj[:, idx]
             dzs, back = [], []
             L.active = [L.auxval, L.eigval]
             for i in range(nev):
@@ -827,8 +828,11 @@ def _iterate(L, z, maxiter, tol, relax, order, nev, v0, v0_adj, kind, num_order,
             if kind == "mslp":
                 z0, lam0 = z, lam
             z = z + relax * dzs[sel]
-            v0 = (1 - relax) * v0 + relax * v[:, sel]
-            v0_adj = (1 - relax) * v0_adj + relax * v_adj[:, sel]
+            if relax == 1.0:  # the reference's formula with relax = 1, without three passes over each vector
+                v0, v0_adj = v[:, sel], v_adj[:, sel]
+            else:
+                v0 = (1 - relax) * v0 + relax * v[:, sel]
+                v0_adj = (1 - relax) * v0_adj + relax * v_adj[:, sel]
             n += 1
     except _lib.ArpackException as e:
         err = "arpack"
