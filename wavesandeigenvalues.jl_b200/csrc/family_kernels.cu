@@ -166,6 +166,28 @@ void wae_spmm_device(wae_ctx* h, Family& F, int slot, int trans, int nrhs, const
   wae_spmm_values(h, F, (const cplx*)F.slot[slot].p, trans, nrhs, X, Y);
 }
 
+// val_csr[q] = val[perm[q]]: the values of the union pattern in the order of the CSR view (one gather, so that repeated products y = A x with
+// the same values -- the refinement steps of the solves -- stream them instead of gathering them)
+__global__ void permute_values_kernel(const double2* __restrict__ val, const int32_t* __restrict__ perm, int64_t nnz, double2* __restrict__ out) {
+  int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (q < nnz) out[q] = val[perm[q]];
+}
+void wae_values_to_csr(wae_ctx* h, Family& F, const cplx* val, cplx* val_csr) {
+  Pattern& U = h->pat(F.pattern);
+  wae_family_ensure_csr(h, F);
+  permute_values_kernel<<<(unsigned)((U.nnz + 255) / 256), 256, 0, h->stream>>>(val, F.d_tr_perm.p, U.nnz, val_csr);
+  h->launches++;
+  CUDA_CHECK(cudaGetLastError());
+}
+// Y = A X with the values already in CSR order (wae_values_to_csr)
+void wae_spmm_values_csr(wae_ctx* h, Family& F, const cplx* val_csr, int nrhs, const cplx* X, cplx* Y) {
+  Pattern& U = h->pat(F.pattern);
+  wae_family_ensure_csr(h, F);
+  spmm_gather_kernel<<<(unsigned)((U.dim * 32 + 255) / 256), 256, 0, h->stream>>>(F.d_rowptr.p, F.d_colidx.p, nullptr, val_csr, 0, U.dim, nrhs, X, Y);
+  h->launches++;
+  CUDA_CHECK(cudaGetLastError());
+}
+
 void wae_spmm_values(wae_ctx* h, Family& F, const cplx* val, int trans, int nrhs, const cplx* X, cplx* Y) {
   Pattern& U = h->pat(F.pattern);
   unsigned blocks = (unsigned)((U.dim * 32 + 255) / 256);

@@ -3,6 +3,9 @@
 // calls of the reference (perturbation.jl:329,359; beyn.jl:65; inside Arpack.eigs at
 // Householder.jl:100-101).  Internal interface.
 #pragma once
+#include <array>
+#include <map>
+
 #include "wae_internal.h"
 
 #define WAE_LU_NB 32  // pivot block width of the blocked partial factorisation
@@ -52,6 +55,8 @@ struct LuSolver {
   std::vector<DevBuf<int32_t>> d_xa_tile_ptr;  // per depth: extend-add tile prefix over the supernodes of that depth
   std::vector<int32_t> xa_tiles;       // per depth: number of extend-add tiles
   DevBuf<cplx> d_Aval;                 // copy of the factorised matrix (iterative refinement)
+  DevBuf<cplx> d_Aval_csr;             // the same values in CSR order, built by the first refinement product y = A x after a factorisation
+  bool aval_csr_valid = false;
   // numeric
   DevBuf<cplx> d_fac;
   DevBuf<cplx> d_dinv;                 // explicit inverses of the NB x NB diagonal blocks (triangular solves without a serial chain)
@@ -67,6 +72,14 @@ struct LuSolver {
   DevBuf<int32_t> d_wininv_items;      // (supernode, block) work items of the window inverses, grouped by the number of blocks below
   int wininv_ptr[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};  // items with exactly c blocks below: [wininv_ptr[c], wininv_ptr[c + 1]), c = 1 .. 7
   bool wininv = false;                 // the last factorisation stored the window inverses (the solves use the product kernels)
+  // CUDA graphs of the sweep pairs: the launch sequence of a sweep pair depends only on the symbolic structure, the number of right-hand
+  // sides, the transposition and the kernel switches, so it is captured once per such key and replayed (lu_numeric.cu: lu_sweeps)
+  struct SweepGraph {
+    void* exec = nullptr;  // cudaGraphExec_t
+    int64_t launches = 0;
+  };
+  std::map<std::array<int64_t, 8>, SweepGraph> sweep_graphs;
+  ~LuSolver();
   int work_nrhs = 0;
   bool factored = false;
   bool check_singular = true;          // raise WAE_E_SINGULAR on an exactly zero pivot (wae_lu_factor_ex with check = 0 clears it)

@@ -1553,6 +1553,7 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
   wae_family_ensure_csr(h, F);
   CUDA_CHECK(cudaMemcpyAsync(S.d_Aval.p, d_full ? d_full : d_Aval, (size_t)U.nnz * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
   S.sym_mode = sym != 0;
+  S.aval_csr_valid = false;
   LuDev D = make_dev(S);
   CUDA_CHECK(cudaMemsetAsync(S.d_fac.p, 0, (size_t)Y.fac_size * sizeof(cplx), st));
   CUDA_CHECK(cudaMemsetAsync(S.d_flag.p, 0, 2 * sizeof(int32_t), st));
@@ -1987,11 +1988,73 @@ static void lu_sweeps_nr(wae_ctx* h, LuSolver& S, int trans_t, int nrhs, cplx* y
   }
 }
 
-static void lu_sweeps(wae_ctx* h, LuSolver& S, int trans_t, int nrhs, cplx* y) {
+static void lu_sweeps_direct(wae_ctx* h, LuSolver& S, int trans_t, int nrhs, cplx* y) {
   if (nrhs >= 8) lu_sweeps_nr<8>(h, S, trans_t, nrhs, y);
   else if (nrhs >= 4) lu_sweeps_nr<4>(h, S, trans_t, nrhs, y);
   else if (nrhs >= 2) lu_sweeps_nr<2>(h, S, trans_t, nrhs, y);
   else lu_sweeps_nr<1>(h, S, trans_t, nrhs, y);
+}
+
+LuSolver::~LuSolver() {
+  for (auto& kv : sweep_graphs)
+    if (kv.second.exec) cudaGraphExecDestroy((cudaGraphExec_t)kv.second.exec);
+}
+
+// A sweep pair is ~190 small, dependent launches (two per window of every top level); its sequence is a function of the symbolic
+// structure and of (transposition, right-hand sides, work vector, kernel switches) alone.  It is captured into a CUDA graph the first
+// time a key is seen and replayed afterwards: the dependent launches then follow each other without the per-launch stream overhead.
+// Not under WAE_LU_TRACE, and WAE_LU_GRAPH=0 switches it off; any failure of the capture falls back to the direct launches.
+static void lu_sweeps(wae_ctx* h, LuSolver& S, int trans_t, int nrhs, cplx* y) {
+  cudaStream_t st = h->stream;
+  const bool off = (getenv("WAE_LU_GRAPH") && !atoi(getenv("WAE_LU_GRAPH"))) || getenv("WAE_LU_TRACE");
+  if (off) {
+    lu_sweeps_direct(h, S, trans_t, nrhs, y);
+    return;
+  }
+  auto envi = [](const char* n, int64_t dflt) { return getenv(n) ? (int64_t)atoll(getenv(n)) : dflt; };
+  const std::array<int64_t, 8> key = {trans_t, nrhs, (int64_t)(uintptr_t)y, S.wininv ? 1 : 0, envi("WAE_LU_SOLVE_FUSED", 1), envi("WAE_LU_SOLVE_UPD2", 1),
+                                      envi("WAE_LU_SOLVE_FUSED_MIN", -1), envi("WAE_LU_SOLVE_PF", 0)};
+  auto it = S.sweep_graphs.find(key);
+  if (it == S.sweep_graphs.end()) {
+    LuSolver::SweepGraph g;
+    const int64_t l0 = h->launches;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    // captured on the context's own auxiliary stream (the context stream may be the legacy default stream, which cannot capture); the
+    // graph is then launched on the context stream like any other work
+    if (!h->cap_stream && cudaStreamCreateWithFlags(&h->cap_stream, cudaStreamNonBlocking) != cudaSuccess) h->cap_stream = nullptr;
+    bool ok = h->cap_stream && cudaStreamBeginCapture(h->cap_stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+    if (ok) {
+      h->stream = h->cap_stream;
+      try {
+        lu_sweeps_direct(h, S, trans_t, nrhs, y);  // recorded, not executed
+      } catch (...) {
+        h->stream = st;
+        cudaStreamEndCapture(h->cap_stream, &graph);
+        if (graph) cudaGraphDestroy(graph);
+        cudaGetLastError();
+        throw;
+      }
+      h->stream = st;
+      ok = cudaStreamEndCapture(h->cap_stream, &graph) == cudaSuccess && graph != nullptr;
+    }
+    if (ok) ok = cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess;
+    if (graph) cudaGraphDestroy(graph);
+    g.launches = h->launches - l0;
+    h->launches = l0;
+    if (!ok) {
+      cudaGetLastError();  // the failed capture must not surface as a launch error
+      g.exec = nullptr;
+    } else
+      g.exec = exec;
+    it = S.sweep_graphs.emplace(key, g).first;
+  }
+  if (!it->second.exec) {  // capture failed once for this key: direct launches from now on
+    lu_sweeps_direct(h, S, trans_t, nrhs, y);
+    return;
+  }
+  CUDA_CHECK(cudaGraphLaunch((cudaGraphExec_t)it->second.exec, st));
+  h->launches += it->second.launches;
 }
 
 // ---- rank-k (Sherman-Morrison-Woodbury) correction on top of the symmetric factorisation ------------------------------
@@ -2147,7 +2210,15 @@ void wae_lu_solve_device(wae_ctx* h, LuSolver& S, int trans, int nrhs, cplx* d_X
   lu_apply_inverse(h, S, trans, nrhs, d_X);
   for (int it = 0; it < refine; it++) {
     // res = b - op(A) x ; x += op(A)^{-1} res
-    wae_spmm_values(h, F, S.d_Aval.p, trans, nrhs, d_X, res);
+    if (trans == 0) {  // y = A x walks the CSR view: gather the values into that order once per factorisation, stream them afterwards
+      if (!S.aval_csr_valid) {
+        S.d_Aval_csr.reserve(S.d_Aval.n);
+        wae_values_to_csr(h, F, S.d_Aval.p, S.d_Aval_csr.p);
+        S.aval_csr_valid = true;
+      }
+      wae_spmm_values_csr(h, F, S.d_Aval_csr.p, nrhs, d_X, res);
+    } else
+      wae_spmm_values(h, F, S.d_Aval.p, trans, nrhs, d_X, res);
     lu_residual_kernel<<<gt, 256, 0, st>>>(b0, n * nrhs, res);
     lu_apply_inverse(h, S, trans, nrhs, res);
     if (ep && it == refine - 1)

@@ -64,6 +64,7 @@ int32_t wae_destroy(wae_ctx* h) {
     if (h->ev_join[g]) cudaEventDestroy(h->ev_join[g]);
   }
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->cap_stream) cudaStreamDestroy(h->cap_stream);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   delete h;

@@ -157,6 +157,7 @@ struct wae_ctx {
   // two auxiliary streams + fork / join events: the numeric LU runs the fronts of a tree level in two groups, so that the latency-bound
   // diagonal-block / panel steps of one group run under the GEMMs of the other (created on first use, destroyed with the context)
   cudaStream_t aux_stream[2] = {nullptr, nullptr};
+  cudaStream_t cap_stream = nullptr;  // stream the sweep graphs of the solves are captured on (never executes anything)
   // device scratch of the assembly entry points (speed of sound, flame work arrays): kept between calls -- every cudaMalloc / cudaFree is a
   // device-wide synchronisation under the driver's allocation lock, a dozen of them per re-assembly cost more than the kernels
   DevBuf<double> scratch_c, scratch_d[2];
@@ -275,5 +276,7 @@ void wae_launch_wallsrc(wae_ctx* h, const int32_t* d_elems, int64_t n, const dou
 void wae_combine_device(wae_ctx* h, Family& F, const double* coeffs_host, int slot);
 void wae_spmm_device(wae_ctx* h, Family& F, int slot, int trans, int nrhs, const cplx* X, cplx* Y);
 void wae_spmm_values(wae_ctx* h, Family& F, const cplx* val, int trans, int nrhs, const cplx* X, cplx* Y);
+void wae_values_to_csr(wae_ctx* h, Family& F, const cplx* val, cplx* val_csr);
+void wae_spmm_values_csr(wae_ctx* h, Family& F, const cplx* val_csr, int nrhs, const cplx* X, cplx* Y);
 void wae_family_ensure_csr(wae_ctx* h, Family& F);
 void wae_axpy_term(wae_ctx* h, Family& F, int t, double cr, double ci, cplx* out);
