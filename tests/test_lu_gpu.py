@@ -89,7 +89,9 @@ G_HOUSEHOLDER = [
 def test_householder_goldens_gpu(tau, omega):
     import wae_b200 as W
     L = _gpu_family("lin", n=0.01, tau=tau)
-    sol, n, flag = W.householder(L, 340 * 2 * math.pi, maxiter=20, tol=1e-11, output=False)
+    # tol: |d omega| <= 1e-10 (6e-14 relative).  1e-11 sits at the rounding floor of the Newton step on the device (the fp64 atomics of the
+    # factorisation do not fix the order of the additions), so that reaching it within maxiter was a matter of luck
+    sol, n, flag = W.householder(L, 340 * 2 * math.pi, maxiter=20, tol=1e-10, output=False)
     assert flag in (0, 1)
     assert abs(sol.params["ω"] - omega) / abs(omega) < TOL
 
@@ -105,7 +107,7 @@ G_MSLP = [
 def test_mslp_goldens_gpu(tau, start, omega):
     import wae_b200 as W
     L = _gpu_family("lin", n=1.0, tau=tau)
-    sol, n, flag = W.mslp(L, start, maxiter=20, tol=1e-11, output=False)
+    sol, n, flag = W.mslp(L, start, maxiter=20, tol=1e-10, output=False)
     assert flag == 0
     assert abs(sol.params["ω"] - omega) / abs(omega) < TOL
 
@@ -203,7 +205,7 @@ def test_perturb_fast_goldens_on_the_gpu():
     from oracle.nlevp import mslp as omslp
     from oracle.nlevp import perturb_fast_bang as ofast
     L = _gpu_family("lin", n=1.0)
-    sol, n, flag = W.mslp(L, 150 * 2 * math.pi, maxiter=30, tol=1e-11, output=False)
+    sol, n, flag = W.mslp(L, 150 * 2 * math.pi, maxiter=30, tol=1e-10, output=False)
     assert flag == 0
     W.perturb_fast_bang(sol, L, "τ", 20)
     tay = sol.eigval_pert["τ/Taylor"]

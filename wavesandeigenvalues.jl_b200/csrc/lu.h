@@ -54,6 +54,14 @@ struct LuSolver {
   DevBuf<int32_t> d_level_half[2];
   std::vector<DevBuf<int32_t>> d_xa_tile_ptr;  // per depth: extend-add tile prefix over the supernodes of that depth
   std::vector<int32_t> xa_tiles;       // per depth: number of extend-add tiles
+  // extend-add in rounds: round k holds the k-th child of every parent, so no two supernodes of a round write the same front and the
+  // additions are plain read-modify-writes (no atomics).  Per depth: the children in round order, per round its offset, count and tiles
+  struct XaRound {
+    int32_t off = 0, count = 0, tiles = 0;
+  };
+  std::vector<std::vector<XaRound>> xa_rounds;          // [depth of the children][round]
+  std::vector<DevBuf<int32_t>> d_xa_round_children;     // per depth: children in round order
+  std::vector<DevBuf<int32_t>> d_xa_round_tile_ptr;     // per depth: per round a tile prefix (count + 1 entries each), concatenated
   DevBuf<cplx> d_Aval;                 // copy of the factorised matrix (iterative refinement)
   DevBuf<cplx> d_Aval_csr;             // the same values in CSR order, built by the first refinement product y = A x after a factorisation
   bool aval_csr_valid = false;

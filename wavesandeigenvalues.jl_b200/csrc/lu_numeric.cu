@@ -91,7 +91,7 @@ __global__ void lu_scatter_kernel(const cplx* __restrict__ A, const int64_t* __r
 // sym != 0: the update matrices hold their lower triangle only (x >= y); upper entries are read from the mirror position
 // and only the lower part of the parent front is written (its U^T panel is regenerated from the L panel).
 __global__ void __launch_bounds__(256) lu_extend_add_kernel(LuDev D, const int32_t* __restrict__ children, const int32_t* __restrict__ tile_ptr,
-                                                            int nchild, const cplx* __restrict__ upd_child, cplx* __restrict__ upd_parent, int sym, int part) {
+                                                            int nchild, const cplx* __restrict__ upd_child, cplx* __restrict__ upd_parent, int sym, int part, int atomic) {
   // part 0: every target; 1: targets in the parent's pivot panels only; 2: targets in the parent's update matrix only
   // locate the child of this tile
   int t = blockIdx.x;
@@ -134,8 +134,15 @@ __global__ void __launch_bounds__(256) lu_extend_add_kernel(LuDev D, const int32
       }
     }
     cplx v = (sym && x < y) ? U[y + (size_t)x * rc] : U[x + (size_t)y * rc];
-    atomicAdd(&dst->x, v.x);
-    atomicAdd(&dst->y, v.y);
+    if (atomic) {
+      atomicAdd(&dst->x, v.x);
+      atomicAdd(&dst->y, v.y);
+    } else {  // a round of the extend-add: this supernode is the only writer of its parent's front
+      cplx o = *dst;
+      o.x += v.x;
+      o.y += v.y;
+      *dst = o;
+    }
   }
 }
 
@@ -1501,6 +1508,40 @@ void wae_lu_setup_device(wae_ctx* h, LuSolver& S) {
     S.xa_tiles[d] = tile_ptr.back();
     S.d_xa_tile_ptr[d].upload(tile_ptr, st);
   }
+  // rounds of the extend-add: sibling rank of every supernode among the children of its parent
+  {
+    std::vector<int32_t> nchild_seen(Y.nsn, 0), rank(Y.nsn, 0);
+    for (int k = 0; k < Y.nsn; k++)
+      if (Y.sn_parent[k] >= 0) rank[k] = nchild_seen[Y.sn_parent[k]]++;
+    S.xa_rounds.assign(Y.levels.size(), {});
+    S.d_xa_round_children.resize(Y.levels.size());
+    S.d_xa_round_tile_ptr.resize(Y.levels.size());
+    for (size_t d = 0; d < Y.levels.size(); d++) {
+      const std::vector<int32_t>& C = Y.levels[d];
+      int nround = 0;
+      for (int32_t k : C)
+        if (Y.sn_parent[k] >= 0) nround = std::max(nround, rank[k] + 1);
+      std::vector<int32_t> order, tptr;
+      for (int r = 0; r < nround; r++) {
+        LuSolver::XaRound R;
+        R.off = (int32_t)order.size();
+        const size_t t0 = tptr.size();
+        tptr.push_back(0);
+        for (int32_t k : C) {
+          if (Y.sn_parent[k] < 0 || rank[k] != r) continue;
+          const int64_t rr = Y.struct_ptr[k + 1] - Y.struct_ptr[k], nt = (rr + 31) / 32;
+          order.push_back(k);
+          tptr.push_back(tptr.back() + (int32_t)(nt * nt));
+        }
+        R.count = (int32_t)order.size() - R.off;
+        R.tiles = tptr.back();
+        (void)t0;
+        S.xa_rounds[d].push_back(R);
+      }
+      S.d_xa_round_children[d].upload(order.empty() ? std::vector<int32_t>(1, 0) : order, st);
+      S.d_xa_round_tile_ptr[d].upload(tptr.empty() ? std::vector<int32_t>(1, 0) : tptr, st);
+    }
+  }
   // work items of the window inverses: every block j that is not the last one of its window, grouped by the blocks below it
   {
     std::vector<std::vector<int32_t>> cls(LU_WBLK);
@@ -1586,6 +1627,8 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
   const int panel_inv_max = (!sym || sym_panel) ? (getenv("WAE_LU_PANEL") ? atoi(getenv("WAE_LU_PANEL")) : (1 << 30)) : 0;  // 0: never
   const bool late_xadd = !(getenv("WAE_LU_LATE_XADD") && !atoi(getenv("WAE_LU_LATE_XADD")));
   const bool two_groups = !(getenv("WAE_LU_GROUPS") && atoi(getenv("WAE_LU_GROUPS")) == 1);
+  // extend-add in rounds of sibling rank without atomics (WAE_LU_XADD_ROUNDS=0: one launch with fp64 atomics)
+  const bool xadd_rounds = !(getenv("WAE_LU_XADD_ROUNDS") && !atoi(getenv("WAE_LU_XADD_ROUNDS")));
   const int prof_depth = getenv("WAE_LU_PROFILE_DEPTH") ? atoi(getenv("WAE_LU_PROFILE_DEPTH")) : -1;
   if (two_groups && !h->aux_stream[0]) {
     // group 0 on a high-priority stream, group 1 on a low-priority one: CTAs are dispatched kernel by kernel, so with equal priorities the
@@ -1636,9 +1679,23 @@ void wae_lu_factor_device(wae_ctx* h, LuSolver& S, const cplx* d_Aval, const cpl
     if (Y.level_upd_size[d] && !late_xadd) timed(T_MEMSET, [&] { CUDA_CHECK(cudaMemsetAsync(upd, 0, (size_t)Y.level_upd_size[d] * sizeof(cplx), st)); });
     const bool has_children = d < maxd && S.xa_tiles[d + 1] > 0;
     auto xadd = [&](int part) {
+      if (xadd_rounds) {  // one launch per sibling rank, plain read-modify-writes
+        int tp = 0;  // round r's tile prefix starts after the (count + 1) entries of every earlier round
+        for (const LuSolver::XaRound& R : S.xa_rounds[d + 1]) {
+          if (R.tiles > 0) {
+            timed(T_XADD, [&] {
+              lu_extend_add_kernel<<<R.tiles, dim3(32, 8), 0, st>>>(D, S.d_xa_round_children[d + 1].p + R.off, S.d_xa_round_tile_ptr[d + 1].p + tp, R.count,
+                                                                    S.d_upd[(d + 1) & 1].p, upd, sym, part, 0);
+            });
+            h->launches++;
+          }
+          tp += R.count + 1;
+        }
+        return;
+      }
       timed(T_XADD, [&] {
         lu_extend_add_kernel<<<S.xa_tiles[d + 1], dim3(32, 8), 0, st>>>(D, S.d_level[d + 1].p, S.d_xa_tile_ptr[d + 1].p,
-                                                                          (int)Y.levels[d + 1].size(), S.d_upd[(d + 1) & 1].p, upd, sym, part);
+                                                                          (int)Y.levels[d + 1].size(), S.d_upd[(d + 1) & 1].p, upd, sym, part, 1);
       });
       h->launches++;
     };
