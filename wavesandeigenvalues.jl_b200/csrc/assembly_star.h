@@ -53,6 +53,24 @@ WAE_STAR_HD inline int star_rows(int nloc, int type) { return nloc == 4 ? 2 : (t
 WAE_STAR_HD inline int star_krow(int nloc, int role) { return nloc == 4 ? 0 : (int)((0x21054321032100ULL >> (4 * role)) & 7); }
 WAE_STAR_HD inline int star_mrow(int nloc, int role) { return nloc == 4 ? 1 : (int)((0x33377766665541ULL >> (4 * role)) & 7); }
 
+// The shared-memory words (8 bytes each, relative to the start of the gram blocks) one source word makes its lane read in the star pass, in
+// the order of the kernel's loads (star_sums in assembly_star.cu; the determinant comes last here, the order is irrelevant for the banks).
+// Used by the bank-conflict simulator of the host replay and by the builder, which orders the sources of a lane so that the lanes of a
+// half-warp read different bank pairs in the same iteration.
+WAE_STAR_HD inline int star_load_words(int nloc, int type, unsigned w, int* word) {
+  const int ia = w & 3, ib = (w >> 2) & 3, ic = (w >> 4) & 3;
+  const int t = type < 3 ? (int)(w >> (2 * (type + 1))) : (int)w;
+  int idx[7], n = 0;
+  if (type == 0) idx[n++] = 5 * ia;
+  else if (type == 1 && nloc == 4) idx[n++] = 4 * ia + ib;
+  else if (type == 1) { idx[n++] = 5 * ia; idx[n++] = 5 * ib; idx[n++] = 4 * ia + ib; }
+  else if (type == 2) { idx[n++] = 5 * ia; idx[n++] = 5 * ib; idx[n++] = 5 * ic; idx[n++] = 4 * ia + ib; idx[n++] = 4 * ia + ic; idx[n++] = 4 * ib + ic; }
+  else { idx[n++] = 1; idx[n++] = 2; idx[n++] = 3; idx[n++] = 6; idx[n++] = 7; idx[n++] = 11; }
+  idx[n++] = 16;
+  for (int j = 0; j < n; j++) word[j] = t * 17 + idx[j];
+  return n;
+}
+
 // ---- shared memory of one CTA: gram blocks of the staged elements (17 doubles each) | record rows | blob A | coordinates | blob B ------
 struct StarLayout {
   int off_rec, off_a, off_px, off_b;

@@ -310,6 +310,62 @@ static void build_patch(const uint32_t* conn, int nloc, const Pattern& P, const 
         }
       }
     }
+    // ---- order of the sources inside every lane: in iteration k the 16 lanes of a half-warp issue the same loads (one per gram entry of
+    // the sub-simplex type) at data-dependent addresses; two lanes that hit the same bank pair with different addresses cost a second
+    // wavefront.  The sum over a star does not depend on the order, so every lane walks its sources in the order that a greedy schedule
+    // (iteration by iteration, lane by lane, cheapest remaining source first) finds -- fixed once per pattern, so the summation order is
+    // still fixed.  WAE_STAR_NO_SRC_OPT=1 keeps the element order.
+    static const bool src_opt = getenv("WAE_STAR_NO_SRC_OPT") == nullptr;
+    if (src_opt && niter > 1) {
+      const uint8_t* cn = &O.cnt[O.cnt.size() - 32];
+      for (int half = 0; half < 2; half++) {
+        std::vector<uint16_t> rem[16];
+        for (int l = 0; l < 16; l++)
+          for (int k = 0; k < cn[16 * half + l]; k++) rem[l].push_back(O.src[sb + (size_t)32 * k + 16 * half + l]);
+        for (int k = 0; k < niter; k++) {
+          // occupancy of this iteration: per load j and bank pair the distinct addresses placed so far
+          int nadr[7][16] = {{0}}, adr[7][16][16], worst[7] = {0};
+          // lanes with the fewest remaining choices first (they cannot avoid anything later)
+          int lanes[16], nl = 0;
+          for (int l = 0; l < 16; l++)
+            if (!rem[l].empty()) lanes[nl++] = l;
+          std::stable_sort(lanes, lanes + nl, [&](int a, int b) { return rem[a].size() < rem[b].size(); });
+          for (int q = 0; q < nl; q++) {
+            const int l = lanes[q];
+            int best = -1;
+            long bestc = 0;
+            for (size_t cand = 0; cand < rem[l].size(); cand++) {
+              int wd[7];
+              const int n = star_load_words(nloc, type, rem[l][cand], wd);
+              long cst = 0;
+              for (int jj = 0; jj < n; jj++) {
+                const int b = wd[jj] & 15;
+                bool dup = false;
+                for (int z = 0; z < nadr[jj][b]; z++) dup |= adr[jj][b][z] == wd[jj];
+                if (dup) continue;
+                cst += nadr[jj][b] + 1 > worst[jj] ? 1000 : 0;  // a new wavefront of load jj
+                cst += nadr[jj][b];                              // otherwise prefer the emptier bank pair
+              }
+              if (best < 0 || cst < bestc) best = (int)cand, bestc = cst;
+            }
+            const uint16_t wsel = rem[l][best];
+            rem[l].erase(rem[l].begin() + best);
+            O.src[sb + (size_t)32 * k + 16 * half + l] = wsel;
+            int wd[7];
+            const int n = star_load_words(nloc, type, wsel, wd);
+            for (int jj = 0; jj < n; jj++) {
+              const int b = wd[jj] & 15;
+              bool dup = false;
+              for (int z = 0; z < nadr[jj][b]; z++) dup |= adr[jj][b][z] == wd[jj];
+              if (!dup) {
+                adr[jj][b][nadr[jj][b]++] = wd[jj];
+                worst[jj] = std::max(worst[jj], nadr[jj][b]);
+              }
+            }
+          }
+        }
+      }
+    }
     rows += star_rows(nloc, type);
     i = j;
   }
