@@ -541,12 +541,19 @@ def _part2mult(p):
     return mu
 
 
-def perturb(L, N, v0, v0Adj):
+def perturb(L, N, v0, v0Adj, vectors=True):
     """perturbation.jl:319-367.  L must be in mode :householder/:compact with two active variables.
 
     Device work: L(m,n)*v products (combine + SpMV).  The factorisation of the (deliberately near-singular)
     L(0,0) and its N solves are only needed for N >= 2 -- v_N is never used for the eigenvalue coefficients --
     so Newton (order 1) runs without any extra LU (the reference factorises and solves regardless)."""
+    if N == 1 and not vectors:
+        # first order, coefficients only (the Newton step of householder): lam_1 = -(v0Adj^H L01 v0) / (v0Adj^H L10 v0) does not depend on
+        # the scaling of v0 and v0Adj, so the normalisations of the reference (five passes over the vectors) are skipped
+        L10v0 = L(1, 0).matvec(v0, slot=2)
+        den = np.vdot(v0Adj, L10v0)
+        lam1 = -np.vdot(v0Adj, L(0, 1).matvec(v0, slot=2)) / den
+        return np.array([0.0, lam1], dtype=complex), [None, None]
     v0 = v0 / np.sqrt(np.vdot(v0, v0))
     L10v0 = L(1, 0).matvec(v0, slot=2)
     v0Adj = v0Adj / np.vdot(v0Adj, L10v0)
@@ -676,15 +683,16 @@ def conv_radius(sol_or_coeffs, param=None):
     return np.abs(a[:-1] / a[1:])
 
 
-def perturb_bang(sol, L, param, N, mode="compact"):
-    """perturb! (LinOpFam.jl:546-560)"""
+def perturb_bang(sol, L, param, N, mode="compact", vectors=True):
+    """perturb! (LinOpFam.jl:546-560).  vectors=False (internal: the Newton step of householder / mslp uses the eigenvalue coefficients
+    only) lets a first-order call skip the normalisation of the eigenvector pair."""
     active, params, cur = L.active, L.params, L.mode
     L.params = sol.params
     L.active = [sol.eigval, param]
     L.mode = mode
     key = f"{param}/Taylor"
     try:
-        sol.eigval_pert[key], sol.v_pert[key] = perturb(L, N, sol.v, sol.v_adj)
+        sol.eigval_pert[key], sol.v_pert[key] = perturb(L, N, sol.v, sol.v_adj, vectors=vectors)
         sol.eigval_pert[key][0] = sol.params[sol.eigval]
     finally:
         L.active, L.mode, L.params = active, cur, params
@@ -809,7 +817,7 @@ def _iterate(L, z, maxiter, tol, relax, order, nev, v0, v0_adj, kind, num_order,
             for i in range(nev):
                 L.params[L.auxval] = lams[i]
                 sol = Solution(L.params, v[:, i], v_adj[:, i], L.auxval)
-                perturb_bang(sol, L, L.eigval, order, mode="householder")
+                perturb_bang(sol, L, L.eigval, order, mode="householder", vectors=False)
                 coeffs = sol.eigval_pert[f"{L.eigval}/Taylor"]
                 if kind == "householder":
                     dzs.append(householder_update([math.factorial(k) * c for k, c in enumerate(coeffs)]))
