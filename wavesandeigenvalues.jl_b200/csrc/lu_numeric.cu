@@ -1284,7 +1284,7 @@ __device__ __forceinline__ void col_dots(const cplx* __restrict__ colbase, int l
 
 // backward update, CW columns per warp: grid.x = (column groups of 8 warps x CW) x (row chunks), grid.y supernode, grid.z groups of NR
 template <int NR>
-__global__ void __launch_bounds__(256) lu_bwd_update2_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int c_lo, int ncg, int row_chunk,
+__global__ void __launch_bounds__(256, NR <= 2 ? 4 : 2) lu_bwd_update2_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int c_lo, int ncg, int row_chunk,
                                                              int nrhs, int64_t n, cplx* __restrict__ x) {
   SnView S = sn_view(D, list[blockIdx.y]);
   if (c_lo >= S.s) return;
@@ -1360,7 +1360,7 @@ __global__ void __launch_bounds__(256) lu_fwd_fused_kernel(LuDev D, const int32_
 }
 
 template <int NR>
-__global__ void __launch_bounds__(256) lu_bwd_fused_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int nrhs, int64_t n, cplx* __restrict__ x) {
+__global__ void __launch_bounds__(256, NR <= 2 ? 4 : 2) lu_bwd_fused_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int nrhs, int64_t n, cplx* __restrict__ x) {
   const int sn = list[blockIdx.x];
   SnView S = sn_view(D, sn);
   const int rhs0 = blockIdx.y * NR, nr = min(NR, nrhs - rhs0);
