@@ -170,21 +170,26 @@ __global__ void __launch_bounds__(NB * NB) lu_diag_kernel(LuDev D, const int32_t
   // forward Gauss-Jordan step of the LOWER triangular W on an identity block -- row p scaled by 1 / pivot, rows below minus W[i][p] times
   // it -- runs in the same step as the elimination of column p of T and the Gauss-Jordan step for L^-1 (round 2a: a second sweep of NB
   // barriers for U^-1).  Every thread forms its multiplier / scaled entry itself from the unscaled values; the owners store them one
-  // barrier later, when nobody reads them any more.
-  cplx lown = zero, zown = zero;
-  for (int p = 0; p < nb; p++) {
-    cplx d = T[p][p];
+  // barrier later, when nobody reads them any more.  The pivot of step p + 1 (static perturbation included) and its reciprocal are
+  // formed by the ONE thread that owns T[p+1][p+1], inside step p, and read by everybody after the barrier -- instead of 1024 threads
+  // each doing the double-precision division.
+  __shared__ cplx pinv[NB];  // reciprocals of the pivots
+  auto make_pivot = [&](int q, cplx d) {
     const double m = d.x * d.x + d.y * d.y;
-    if (!(m >= eps * eps)) {  // tiny, zero or NaN pivot -> static pivoting (every thread derives the same replacement)
-      if (i == p && j == p) {
-        if (!isfinite(m)) atomicOr(flag, 2);
-        else atomicAdd(flag + 1, 1);
-        if (m == 0.0) atomicOr(flag, 4);  // an exactly zero pivot: structurally / exactly singular for an LU without row exchanges
-      }
+    if (!(m >= eps * eps)) {  // tiny, zero or NaN pivot -> static pivoting
+      if (!isfinite(m)) atomicOr(flag, 2);
+      else atomicAdd(flag + 1, 1);
+      if (m == 0.0) atomicOr(flag, 4);  // an exactly zero pivot: structurally / exactly singular for an LU without row exchanges
       d = make_double2(m > 0.0 && isfinite(m) ? d.x * eps / sqrt(m) : eps, m > 0.0 && isfinite(m) ? d.y * eps / sqrt(m) : 0.0);
     }
-    const cplx di = cinv(d);
-    if (i == p && j == p) piv[p] = d;
+    piv[q] = d;
+    pinv[q] = cinv(d);
+  };
+  if (i == 0 && j == 0) make_pivot(0, T[0][0]);
+  __syncthreads();
+  cplx lown = zero, zown = zero;
+  for (int p = 0; p < nb; p++) {
+    const cplx di = pinv[p];
     cplx tnew = zero, xnew = zero, znew = zero;
     bool tw = false, xw = false, zw = false;
     if (i > p) {
@@ -192,6 +197,7 @@ __global__ void __launch_bounds__(NB * NB) lu_diag_kernel(LuDev D, const int32_t
       if (j > p) {
         tnew = csub(T[i][j], cmul(l, T[p][j]));
         tw = true;
+        if (i == p + 1 && j == p + 1 && p + 1 < nb) make_pivot(p + 1, tnew);
       } else if (j == p) {
         lown = l;
         xnew = make_double2(-l.x, -l.y);  // row i of the identity block minus l times row p (unit diagonal)
