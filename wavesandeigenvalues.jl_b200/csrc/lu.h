@@ -97,6 +97,7 @@ struct LuSolver {
   DevBuf<cplx> d_Sval;                 // values of the symmetric part
   DevBuf<cplx> d_r1_Sm, d_r1_Gm;       // n x k dense copies of the s_j / g_j vectors
   DevBuf<cplx> d_r1_Z, d_r1_Zt;        // S^-1 Sm, S^-1 Gm
+  DevBuf<cplx> d_r1_ZZ;                // both, side by side: the right-hand sides of the one solve that produces them
   DevBuf<cplx> d_r1_Kinv, d_r1_KinvT;  // (F^-1 + Gm^T Z)^-1 and its transpose, k x k
   DevBuf<cplx> d_r1_t;                 // k x nrhs scratch
   int refine_steps = 1;   // iterative refinement steps of wae_lu_solve / wae_beyn_moments

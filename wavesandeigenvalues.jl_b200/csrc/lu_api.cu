@@ -334,10 +334,13 @@ static void factor_slot(wae_ctx* h, LuSolver& S, Family& F, int slot) {
     scatter_real_kernel<<<(nc + 255) / 256, 256, 0, st>>>(Q.d_r1_G.p, Q.d_r1_cols.p, nc, S.d_r1_Gm.p + (size_t)j * n);
     h->launches += 2;
   }
-  CUDA_CHECK(cudaMemcpyAsync(S.d_r1_Z.p, S.d_r1_Sm.p, (size_t)n * k * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
-  CUDA_CHECK(cudaMemcpyAsync(S.d_r1_Zt.p, S.d_r1_Gm.p, (size_t)n * k * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
-  wae_lu_base_solve(h, S, 0, k, S.d_r1_Z.p);   // Z  = S^-1 Sm
-  wae_lu_base_solve(h, S, 0, k, S.d_r1_Zt.p);  // Zt = S^-1 Gm  (S symmetric: S^-T = S^-1)
+  // Z = S^-1 Sm and Zt = S^-1 Gm (S symmetric: S^-T = S^-1) as the 2 k right-hand sides of ONE pass over the factor
+  S.d_r1_ZZ.reserve((size_t)n * 2 * k);
+  CUDA_CHECK(cudaMemcpyAsync(S.d_r1_ZZ.p, S.d_r1_Sm.p, (size_t)n * k * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
+  CUDA_CHECK(cudaMemcpyAsync(S.d_r1_ZZ.p + (size_t)n * k, S.d_r1_Gm.p, (size_t)n * k * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
+  wae_lu_base_solve(h, S, 0, 2 * k, S.d_r1_ZZ.p);
+  CUDA_CHECK(cudaMemcpyAsync(S.d_r1_Z.p, S.d_r1_ZZ.p, (size_t)n * k * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
+  CUDA_CHECK(cudaMemcpyAsync(S.d_r1_Zt.p, S.d_r1_ZZ.p + (size_t)n * k, (size_t)n * k * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
   // K = F^-1 + Gm^T Z  (k x k), inverted on the host
   S.d_arn_dots.reserve(2 * (size_t)k * k + 64);
   CUDA_CHECK(cudaMemsetAsync(S.d_arn_dots.p, 0, 2 * (size_t)k * k * sizeof(double), st));
