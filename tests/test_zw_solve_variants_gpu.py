@@ -2,7 +2,8 @@
 (round 2, the default: csrc/lu_numeric.cu lu_wininv_kernel, lu_fwd_win / lu_bwd_win, the fused deep-level kernels, the 16-part forward
 and 4-columns-per-warp backward updates) against the block-by-block substitution of round 1 (WAE_LU_WININV=0, WAE_LU_SOLVE_UPD2=0), on a
 box whose top separators span several 256-column windows and whose deep levels are forced through the fused kernels
-(WAE_LU_SOLVE_FUSED_MIN=1), for 1, 2, 3 and 8 right-hand sides and the three transposition modes."""
+(WAE_LU_SOLVE_FUSED_MIN=1), for 1, 2, 3, 5 and 8 right-hand sides (kernel instantiations for 1, 2, 4 and 8; the staged backward kernels
+of the 4- and 8-wide ones) and the three transposition modes."""
 import math
 import os
 
@@ -54,7 +55,7 @@ def test_solve_kernel_generations_agree(order):
                 os.environ.pop(k, None)
             os.environ.update(env)
             ctx.lu_factor(lid, 0)  # the window inverses are written by the factorisation
-            for nrhs in (1, 2, 3, 8):
+            for nrhs in (1, 2, 3, 5, 8):
                 for trans in (0, 1, 2):
                     X = ctx.lu_solve(lid, B[:, :nrhs] if nrhs > 1 else B[:, 0], trans=trans)
                     X = X.reshape(d, -1)

@@ -1412,6 +1412,161 @@ __global__ void __launch_bounds__(256, NR <= 2 ? 4 : 2) lu_bwd_fused_kernel(LuDe
   }
 }
 
+// ---- backward kernels for 4 ... 8 right-hand sides: the rows of x a CTA needs are STAGED in shared memory ---------------------------
+// With NR right-hand sides every lane of col_dots gathers NR values of x per row and CW columns -- for NR = 8, CW = 2 that is four times
+// the bytes of the panel itself, from L2 (measured: the backward half of an 8-rhs sweep pair took twice the forward half).  Here a
+// chunk of LU_XCH rows of x is gathered once per CTA (all its warps and columns use it), position-major -> [rhs][row] in shared memory.
+#define LU_XCH 128
+template <int NR>
+__device__ __forceinline__ void stage_x_rows(cplx (*xs)[LU_XCH + 1], int base, int r_end, int c_hi, int s, int first, const int32_t* __restrict__ st,
+                                             const cplx* __restrict__ x /* + rhs0 */, int nrhs, int nr) {
+  for (int e = threadIdx.x; e < LU_XCH * NR; e += blockDim.x) {
+    const int i = e / NR, q = e - i * NR, row = base + i;
+    if (row < r_end && q < nr) {
+      const int g = c_hi + row;
+      const int64_t idx = g < s ? (int64_t)first + g : (int64_t)st[g - s];
+      xs[q][i] = x[(size_t)idx * nrhs + q];
+    }
+  }
+}
+// partial sums of CW columns over the staged chunk: lanes along the rows
+template <int NR, int CW>
+__device__ __forceinline__ void col_dots_staged(const cplx* __restrict__ colbase /* row `base` of the first column */, int ld, int ncw, int nrows_chunk,
+                                                const cplx (*xs)[LU_XCH + 1], int nr, double (*sr)[NR], double (*si)[NR]) {
+  const int lane = threadIdx.x & 31;
+  for (int i = lane; i < nrows_chunk; i += 32) {
+    cplx a[CW];
+#pragma unroll
+    for (int cw = 0; cw < CW; cw++) a[cw] = cw < ncw ? colbase[i + (size_t)cw * ld] : make_double2(0.0, 0.0);
+#pragma unroll
+    for (int q = 0; q < NR; q++)
+      if (q < nr) {
+        const cplx v = xs[q][i];
+#pragma unroll
+        for (int cw = 0; cw < CW; cw++) {
+          sr[cw][q] += a[cw].x * v.x - a[cw].y * v.y;
+          si[cw][q] += a[cw].x * v.y + a[cw].y * v.x;
+        }
+      }
+  }
+}
+
+template <int NR>
+__global__ void __launch_bounds__(256, 2) lu_bwd_update3_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int c_lo, int ncg, int row_chunk,
+                                                                int nrhs, int64_t n, cplx* __restrict__ x) {
+  SnView S = sn_view(D, list[blockIdx.y]);
+  if (c_lo >= S.s) return;
+  const int c_hi = min(c_lo + LU_SOLVE_W, S.s);
+  const int nrows = S.ld - c_hi;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int CW = LU_CW(NR);
+  const int c = c_lo + (blockIdx.x % ncg) * (8 * CW) + warp * CW;
+  const int r_begin = (blockIdx.x / ncg) * row_chunk;
+  if (r_begin >= nrows || c_lo + (int)(blockIdx.x % ncg) * (8 * CW) >= c_hi) return;  // CTA-uniform
+  const int r_end = min(nrows, r_begin + row_chunk);
+  const int rhs0 = blockIdx.z * NR, nr = min(NR, nrhs - rhs0);
+  __shared__ cplx xs[NR][LU_XCH + 1];
+  const bool active = c < c_hi;
+  const int ncw = active ? min(CW, c_hi - c) : 0;
+  const int32_t* st = D.struct_idx + D.struct_ptr[list[blockIdx.y]];
+  const cplx* col0 = (use_up ? S.up : S.lp) + c_hi + (size_t)(active ? c : c_lo) * S.ld;
+  double sr[CW][NR], si[CW][NR];
+#pragma unroll
+  for (int cw = 0; cw < CW; cw++)
+#pragma unroll
+    for (int q = 0; q < NR; q++) sr[cw][q] = si[cw][q] = 0.0;
+  for (int base = r_begin; base < r_end; base += LU_XCH) {
+    __syncthreads();
+    stage_x_rows<NR>(xs, base, r_end, c_hi, S.s, S.first, st, x + rhs0, nrhs, nr);
+    __syncthreads();
+    if (active) col_dots_staged<NR, CW>(col0 + base, S.ld, ncw, min(LU_XCH, r_end - base), xs, nr, sr, si);
+  }
+  if (!active) return;
+#pragma unroll
+  for (int cw = 0; cw < CW; cw++)
+#pragma unroll
+    for (int q = 0; q < NR; q++)
+#pragma unroll
+      for (int off = 16; off; off >>= 1) {
+        sr[cw][q] += __shfl_xor_sync(0xffffffffu, sr[cw][q], off);
+        si[cw][q] += __shfl_xor_sync(0xffffffffu, si[cw][q], off);
+      }
+  if (lane == 0)
+#pragma unroll
+    for (int cw = 0; cw < CW; cw++)
+      if (cw < ncw)
+#pragma unroll
+        for (int q = 0; q < NR; q++)
+          if (q < nr) catomic_sub(x + (size_t)(S.first + c + cw) * nrhs + rhs0 + q, make_double2(sr[cw][q], si[cw][q]));
+}
+
+template <int NR>
+__global__ void __launch_bounds__(256, 2) lu_bwd_fused2_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int nrhs, int64_t n, cplx* __restrict__ x) {
+  const int sn = list[blockIdx.x];
+  SnView S = sn_view(D, sn);
+  const int rhs0 = blockIdx.y * NR, nr = min(NR, nrhs - rhs0);
+  const cplx* P = use_up ? S.up : S.lp;
+  __shared__ cplx vs[NR][LU_FW];
+  __shared__ cplx xs[NR][LU_XCH + 1];
+  cplx* xg = x + (size_t)S.first * nrhs + rhs0;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int32_t* st = D.struct_idx + D.struct_ptr[sn];
+  constexpr int CW = LU_CW(NR);
+  for (int e = threadIdx.x; e < NR * S.s; e += 256) {
+    const int m = e / NR, q = e - m * NR;
+    vs[q][m] = q < nr ? xg[(size_t)m * nrhs + q] : make_double2(0.0, 0.0);
+  }
+  // v_c = x_c - sum_{structure rows i} P[s + i, c] x[st[i]], chunk of rows by chunk; a warp owns its columns of vs
+  for (int base = 0; base < S.r; base += LU_XCH) {
+    __syncthreads();
+    stage_x_rows<NR>(xs, base, S.r, S.s, S.s, S.first, st, x + rhs0, nrhs, nr);
+    __syncthreads();
+    const int nch = min(LU_XCH, S.r - base);
+    for (int c = warp * CW; c < S.s; c += 8 * CW) {
+      double sr[CW][NR], si[CW][NR];
+#pragma unroll
+      for (int cw = 0; cw < CW; cw++)
+#pragma unroll
+        for (int q = 0; q < NR; q++) sr[cw][q] = si[cw][q] = 0.0;
+      const int ncw = min(CW, S.s - c);
+      col_dots_staged<NR, CW>(P + S.s + base + (size_t)c * S.ld, S.ld, ncw, nch, xs, nr, sr, si);
+#pragma unroll
+      for (int cw = 0; cw < CW; cw++)
+#pragma unroll
+        for (int q = 0; q < NR; q++)
+#pragma unroll
+          for (int off = 16; off; off >>= 1) {
+            sr[cw][q] += __shfl_xor_sync(0xffffffffu, sr[cw][q], off);
+            si[cw][q] += __shfl_xor_sync(0xffffffffu, si[cw][q], off);
+          }
+      if (lane < ncw) {
+#pragma unroll
+        for (int q = 0; q < NR; q++) {
+          double tr = 0.0, ti = 0.0;
+#pragma unroll
+          for (int cw = 0; cw < CW; cw++)
+            if (cw == lane) {
+              tr = sr[cw][q];
+              ti = si[cw][q];
+            }
+          vs[q][c + lane].x -= tr;
+          vs[q][c + lane].y -= ti;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < S.s) {
+    cplx acc[NR];
+#pragma unroll
+    for (int q = 0; q < NR; q++) acc[q] = make_double2(0.0, 0.0);
+    win_bwd_row<NR>(P, S.ld, D.dinv + D.dinv_off[sn] + (use_up ? NB * NB : 0), use_up, 0, S.s, threadIdx.x, 0, 1, &vs[0][0], LU_FW, acc);
+#pragma unroll
+    for (int q = 0; q < NR; q++)
+      if (q < nr) xg[(size_t)threadIdx.x * nrhs + q] = acc[q];
+  }
+}
+
 // ---- vector utilities -------------------------------------------------------------------------------------
 // y[pos] = d[perm[pos]] * b[perm[pos]] (optionally conjugated)      /      x[perm[pos]] = d[perm[pos]] * y[pos]
 __global__ void lu_permute_in_kernel(const cplx* __restrict__ b, const int32_t* __restrict__ perm, const double* __restrict__ d,
@@ -1914,6 +2069,7 @@ static void lu_sweeps_nr(wae_ctx* h, LuSolver& S, int trans_t, int nrhs, cplx* y
   // 4-columns-per-warp backward update
   const bool fused_ok = S.wininv && !(getenv("WAE_LU_SOLVE_FUSED") && !atoi(getenv("WAE_LU_SOLVE_FUSED")));
   const bool upd2_ok = !(getenv("WAE_LU_SOLVE_UPD2") && !atoi(getenv("WAE_LU_SOLVE_UPD2")));
+  const bool stage_ok = !(getenv("WAE_LU_SOLVE_STAGE") && !atoi(getenv("WAE_LU_SOLVE_STAGE")));  // 4 ... 8 rhs: backward kernels with staged x rows
   // a level goes through the fused kernels when it has at least this many supernodes (one CTA each must fill the GPU); tests set 1
   const int fused_min = getenv("WAE_LU_SOLVE_FUSED_MIN") ? atoi(getenv("WAE_LU_SOLVE_FUSED_MIN")) : 2 * h->sm_count;
   // WAE_LU_TRACE=2 (diagnostic): the four kernel classes of a sweep pair timed per tree depth with their own events (serialising)
@@ -1995,7 +2151,15 @@ static void lu_sweeps_nr(wae_ctx* h, LuSolver& S, int trans_t, int nrhs, cplx* y
       const int zc = std::min<int>(32768, (int)L.size() - z0);
       const int32_t* lst = S.d_level[d].p + z0;
       if (fused_ok && max_s <= LU_FW && (int)L.size() >= fused_min) {
-        timed(3, [&] { lu_bwd_fused_kernel<NR><<<dim3(zc, zr), 256, 0, st>>>(D, lst, !fwd_up, nrhs, Y.n, y); });
+        timed(3, [&] {
+          if constexpr (NR >= 4) {
+            if (stage_ok) {
+              lu_bwd_fused2_kernel<NR><<<dim3(zc, zr), 256, 0, st>>>(D, lst, !fwd_up, nrhs, Y.n, y);
+              return;
+            }
+          }
+          lu_bwd_fused_kernel<NR><<<dim3(zc, zr), 256, 0, st>>>(D, lst, !fwd_up, nrhs, Y.n, y);
+        });
         h->launches++;
         continue;
       }
@@ -2009,6 +2173,12 @@ static void lu_sweeps_nr(wae_ctx* h, LuSolver& S, int trans_t, int nrhs, cplx* y
           if (zc * ncg < 4 * h->sm_count) row_chunk = std::max(256, (int)((int64_t)rmax * zc * ncg / (4 * h->sm_count)) / 32 * 32 + 32);
           const int nrc = (rmax + row_chunk - 1) / row_chunk;
           timed(2, [&] {
+            if constexpr (NR >= 4) {
+              if (upd2_ok && stage_ok) {
+                lu_bwd_update3_kernel<NR><<<dim3(ncg * nrc, zc, zr), 256, 0, st>>>(D, lst, !fwd_up, c_lo, ncg, row_chunk, nrhs, Y.n, y);
+                return;
+              }
+            }
             if (upd2_ok)
               lu_bwd_update2_kernel<NR><<<dim3(ncg * nrc, zc, zr), 256, 0, st>>>(D, lst, !fwd_up, c_lo, ncg, row_chunk, nrhs, Y.n, y);
             else
@@ -2076,7 +2246,7 @@ static void lu_sweeps(wae_ctx* h, LuSolver& S, int trans_t, int nrhs, cplx* y) {
   }
   auto envi = [](const char* n, int64_t dflt) { return getenv(n) ? (int64_t)atoll(getenv(n)) : dflt; };
   const std::array<int64_t, 8> key = {trans_t, nrhs, (int64_t)(uintptr_t)y, S.wininv ? 1 : 0, envi("WAE_LU_SOLVE_FUSED", 1), envi("WAE_LU_SOLVE_UPD2", 1),
-                                      envi("WAE_LU_SOLVE_FUSED_MIN", -1), envi("WAE_LU_SOLVE_PF", 0)};
+                                      envi("WAE_LU_SOLVE_FUSED_MIN", -1), envi("WAE_LU_SOLVE_PF", 0) | (envi("WAE_LU_SOLVE_STAGE", 1) << 4)};
   auto it = S.sweep_graphs.find(key);
   if (it == S.sweep_graphs.end()) {
     LuSolver::SweepGraph g;
