@@ -152,7 +152,9 @@ int32_t wae_family_spmm(wae_ctx* h, int32_t fam_id, int32_t slot, int32_t trans,
 int32_t wae_lu_analyze(wae_ctx* h, int32_t fam_id, int32_t* lu_id, int64_t* factor_nnz, double* factor_flops);
 int32_t wae_lu_factor(wae_ctx* h, int32_t lu_id, int32_t slot);
 /* check = 1: as wae_lu_factor -- an exactly zero pivot (the matrix is singular for an LU without row exchanges; UMFPACK would raise
- * SingularException or pivot) returns WAE_E_SINGULAR instead of factors that solve to garbage.  check = 0: the reference's
+ * SingularException or pivot) returns WAE_E_SINGULAR instead of factors that solve to garbage; and when pivots were perturbed (tiny but
+ * not zero), a probe solve A x = (1, ..., 1) with one refinement step follows: a relative residual above 1e-6 returns WAE_E_SINGULAR as
+ * well ("factor_probe_residual" in wae_last_ms).  check = 0: the reference's
  * lu(L(0,0), check=false) of the deliberately singular operator in perturb (perturbation.jl:329): tiny and zero pivots are replaced
  * (static pivoting) and the factors are kept.                                                                                   */
 int32_t wae_lu_factor_ex(wae_ctx* h, int32_t lu_id, int32_t slot, int32_t check);

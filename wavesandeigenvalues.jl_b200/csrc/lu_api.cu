@@ -468,6 +468,43 @@ int32_t wae_lu_factor_ex(wae_ctx* h, int32_t lu_id, int32_t slot, int32_t check)
   PhaseTimer t(h, "factor");
   factor_slot(h, S, F, slot);
   t.stop();
+  // Safety net of the static pivoting (only when pivots WERE perturbed, and not for lu(...; check = false)): UMFPACK would have exchanged
+  // rows; here a perturbed pivot that mattered shows as a solve whose refinement does not contract.  One probe solve A x = (1, ..., 1)
+  // with one refinement step; a relative residual above 1e-6 raises WAE_E_SINGULAR instead of returning garbage from later solves.
+  if (check != 0 && h->last_ms["static_pivots"] > 0.0) {
+    const int64_t n = S.sym.n;
+    cudaStream_t st = h->stream;
+    S.d_io.reserve((size_t)3 * n);
+    cplx *x = S.d_io.p, *r = S.d_io.p + n, *b = S.d_io.p + 2 * n;
+    std::vector<zc> ones((size_t)n, zc(1.0, 0.0));
+    CUDA_CHECK(cudaMemcpyAsync(b, ones.data(), (size_t)n * sizeof(cplx), cudaMemcpyHostToDevice, st));
+    CUDA_CHECK(cudaMemcpyAsync(x, b, (size_t)n * sizeof(cplx), cudaMemcpyDeviceToDevice, st));
+    wae_lu_solve_device(h, S, 0, 1, x, 1);
+    wae_spmm_values(h, F, S.d_Aval.p, 0, 1, x, r);  // r = A x
+    S.d_arn_dots.reserve(64);
+    auto norm2 = [&](const cplx* u, const cplx* v) {  // |u - v|^2 via three dots
+      double hd[6];
+      CUDA_CHECK(cudaMemsetAsync(S.d_arn_dots.p, 0, 6 * sizeof(double), st));
+      const int blocks = (int)std::min<int64_t>((n + 255) / 256, 64);
+      multi_dot_kernel<<<dim3(blocks, 1), 256, 0, st>>>(u, n, u, S.d_arn_dots.p);
+      multi_dot_kernel<<<dim3(blocks, 1), 256, 0, st>>>(v, n, v, S.d_arn_dots.p + 2);
+      multi_dot_kernel<<<dim3(blocks, 1), 256, 0, st>>>(u, n, v, S.d_arn_dots.p + 4);
+      h->launches += 3;
+      CUDA_CHECK(cudaMemcpyAsync(hd, S.d_arn_dots.p, sizeof(hd), cudaMemcpyDeviceToHost, st));
+      CUDA_CHECK(cudaStreamSynchronize(st));
+      return hd[0] + hd[2] - 2.0 * hd[4];
+    };
+    const double res2 = norm2(r, b);
+    const double rel = std::sqrt(std::max(0.0, res2) / (double)n);
+    h->last_ms["factor_probe_residual"] = rel;
+    if (!(rel <= 1e-6)) {
+      S.factored = false;
+      WAE_THROW(WAE_E_SINGULAR,
+                "%d pivots were perturbed and a probe solve does not reach its right-hand side (relative residual %.2e): the matrix is singular or needs row "
+                "exchanges this factorisation does not do",
+                (int)h->last_ms["static_pivots"], rel);
+    }
+  }
   WAE_API_END
 }
 
