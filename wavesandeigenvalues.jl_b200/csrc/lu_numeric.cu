@@ -1107,19 +1107,23 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 #define LU_WIN_CLUSTER 8
 
-// window step of the forward sweep with the inverted window: a cluster of 8 CTAs per (supernode, right-hand side), one output row per
-// warp (CTA c, warp p: row c + 8 p, so that every CTA holds rows of every block) -- the <= 8 loads of a row are in flight together and
-// the step costs one memory latency instead of the 8 rows per warp a single CTA needs
+// window step of the forward sweep with the inverted window: a cluster of 8 CTAs per (supernode, group of NR <= 4 right-hand sides), one
+// output row per warp (CTA c, warp p: row c + 8 p, so that every CTA holds rows of every block) -- the <= 8 loads of a row are in flight
+// together, serve all right-hand sides of the group, and the step costs one memory latency instead of the 8 rows per warp a single CTA needs
+template <int NR>
 __global__ void __cluster_dims__(LU_WIN_CLUSTER, 1, 1) __launch_bounds__(1024)
-    lu_fwd_win_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int c_lo, int64_t n, cplx* __restrict__ x) {
+    lu_fwd_win_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int c_lo, int nrhs, cplx* __restrict__ x) {
   const int sn = list[blockIdx.x / LU_WIN_CLUSTER], rank = blockIdx.x % LU_WIN_CLUSTER;
   SnView S = sn_view(D, sn);
   if (c_lo >= S.s) return;  // the whole cluster leaves
   const int w = min(c_lo + LU_SOLVE_W, S.s) - c_lo;
-  __shared__ cplx xs[LU_SOLVE_W];
-  const int nrhs = gridDim.y;  // x is stored position-major: x[pos * nrhs + rhs]
-  cplx* xg = x + (size_t)(S.first + c_lo) * nrhs + blockIdx.y;
-  if (threadIdx.x < w) xs[threadIdx.x] = xg[(size_t)threadIdx.x * nrhs];
+  const int rhs0 = blockIdx.y * NR, nr = min(NR, nrhs - rhs0);
+  __shared__ cplx xs[NR][LU_SOLVE_W];
+  cplx* xg = x + (size_t)(S.first + c_lo) * nrhs + rhs0;  // x is stored position-major: x[pos * nrhs + rhs]
+  for (int e = threadIdx.x; e < w * NR; e += 1024) {
+    const int m = e / NR, q = e - m * NR;
+    xs[q][m] = q < nr ? xg[(size_t)m * nrhs + q] : make_double2(0.0, 0.0);
+  }
   __syncthreads();
   cluster_sync_all();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1136,54 +1140,68 @@ __global__ void __cluster_dims__(LU_WIN_CLUSTER, 1, 1) __launch_bounds__(1024)
     const cplx* Tinv = dinv + (size_t)(c_lo / NB + i) * 2 * NB * NB;
     v[LU_WBLK - 1] = NB * i + lane < w ? (use_up ? Tinv[lane + a * NB] : Tinv[a + lane * NB]) : make_double2(0.0, 0.0);
   }
-  double sr = 0.0, si = 0.0;
 #pragma unroll
-  for (int t = 0; t < LU_WBLK - 1; t++)
-    if (t < i) {
-      const cplx xv = xs[lane + 32 * t];
-      sr += v[t].x * xv.x - v[t].y * xv.y;
-      si += v[t].x * xv.y + v[t].y * xv.x;
+  for (int q = 0; q < NR; q++) {
+    if (q >= nr) break;
+    double sr = 0.0, si = 0.0;
+#pragma unroll
+    for (int t = 0; t < LU_WBLK - 1; t++)
+      if (t < i) {
+        const cplx xv = xs[q][lane + 32 * t];
+        sr += v[t].x * xv.x - v[t].y * xv.y;
+        si += v[t].x * xv.y + v[t].y * xv.x;
+      }
+    if (NB * i + lane < w) {
+      const cplx xv = xs[q][NB * i + lane];
+      sr += v[LU_WBLK - 1].x * xv.x - v[LU_WBLK - 1].y * xv.y;
+      si += v[LU_WBLK - 1].x * xv.y + v[LU_WBLK - 1].y * xv.x;
     }
-  if (NB * i + lane < w) {
-    const cplx xv = xs[NB * i + lane];
-    sr += v[LU_WBLK - 1].x * xv.x - v[LU_WBLK - 1].y * xv.y;
-    si += v[LU_WBLK - 1].x * xv.y + v[LU_WBLK - 1].y * xv.x;
-  }
 #pragma unroll
-  for (int off = 16; off; off >>= 1) {
-    sr += __shfl_xor_sync(0xffffffffu, sr, off);
-    si += __shfl_xor_sync(0xffffffffu, si, off);
+    for (int off = 16; off; off >>= 1) {
+      sr += __shfl_xor_sync(0xffffffffu, sr, off);
+      si += __shfl_xor_sync(0xffffffffu, si, off);
+    }
+    if (lane == 0) xg[(size_t)rho * nrhs + q] = make_double2(sr, si);
   }
-  if (lane == 0) xg[(size_t)rho * nrhs] = make_double2(sr, si);
 }
 
 // window step of the backward sweep: cluster of 8 CTAs, CTA j owns block row j of the window: thread = (row, one of 32 column parts)
+template <int NR>
 __global__ void __cluster_dims__(LU_WIN_CLUSTER, 1, 1) __launch_bounds__(1024)
-    lu_bwd_win_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int c_lo, int64_t n, cplx* __restrict__ x) {
+    lu_bwd_win_kernel(LuDev D, const int32_t* __restrict__ list, int use_up, int c_lo, int nrhs, cplx* __restrict__ x) {
   const int sn = list[blockIdx.x / LU_WIN_CLUSTER], rank = blockIdx.x % LU_WIN_CLUSTER;
   SnView S = sn_view(D, sn);
   if (c_lo >= S.s) return;
   const int w = min(c_lo + LU_SOLVE_W, S.s) - c_lo;
-  __shared__ cplx vs[LU_SOLVE_W], part[32][NB + 1];
-  const int nrhs = gridDim.y;
-  cplx* xg = x + (size_t)(S.first + c_lo) * nrhs + blockIdx.y;
-  if (threadIdx.x < w) vs[threadIdx.x] = xg[(size_t)threadIdx.x * nrhs];
+  const int rhs0 = blockIdx.y * NR, nr = min(NR, nrhs - rhs0);
+  __shared__ cplx vs[NR][LU_SOLVE_W], part[32][NB + 1];
+  cplx* xg = x + (size_t)(S.first + c_lo) * nrhs + rhs0;
+  for (int e = threadIdx.x; e < w * NR; e += 1024) {
+    const int m = e / NR, q = e - m * NR;
+    vs[q][m] = q < nr ? xg[(size_t)m * nrhs + q] : make_double2(0.0, 0.0);
+  }
   __syncthreads();
   cluster_sync_all();
   const int rr = threadIdx.x & 31, p = threadIdx.x >> 5;
   const int rho = NB * rank + rr;
-  cplx acc = make_double2(0.0, 0.0);
-  if (rho < w) win_bwd_row<1>(use_up ? S.up : S.lp, S.ld, D.dinv + D.dinv_off[sn] + (use_up ? NB * NB : 0), use_up, c_lo, w, rho, p, 32, vs, LU_SOLVE_W, &acc);
-  part[p][rr] = acc;
-  __syncthreads();
-  if (p == 0 && rho < w) {
-    double tr = 0.0, ti = 0.0;
+  cplx acc[NR];
+#pragma unroll
+  for (int q = 0; q < NR; q++) acc[q] = make_double2(0.0, 0.0);
+  if (rho < w) win_bwd_row<NR>(use_up ? S.up : S.lp, S.ld, D.dinv + D.dinv_off[sn] + (use_up ? NB * NB : 0), use_up, c_lo, w, rho, p, 32, &vs[0][0], LU_SOLVE_W, acc);
+#pragma unroll
+  for (int q = 0; q < NR; q++) {  // the 32 column parts of a row are summed through shared memory, one right-hand side after the other
+    part[p][rr] = acc[q];
+    __syncthreads();
+    if (p == 0 && rho < w && q < nr) {
+      double tr = 0.0, ti = 0.0;
 #pragma unroll 8
-    for (int u = 0; u < 32; u++) {
-      tr += part[u][rr].x;
-      ti += part[u][rr].y;
+      for (int u = 0; u < 32; u++) {
+        tr += part[u][rr].x;
+        ti += part[u][rr].y;
+      }
+      xg[(size_t)rho * nrhs + q] = make_double2(tr, ti);
     }
-    xg[(size_t)rho * nrhs] = make_double2(tr, ti);
+    if (q + 1 < NR) __syncthreads();
   }
 }
 
@@ -2065,6 +2083,7 @@ static void lu_sweeps_nr(wae_ctx* h, LuSolver& S, int trans_t, int nrhs, cplx* y
   const int tri_pf = (getenv("WAE_LU_SOLVE_PF") && atoi(getenv("WAE_LU_SOLVE_PF"))) ? 2 : 0;  // bit 1 of the tri kernels' use_up: L2 prefetch hint
   const int zr = (nrhs + NR - 1) / NR;
   const int W = LU_SOLVE_W;
+  constexpr int WNR = NR > 4 ? 4 : NR;  // right-hand sides per cluster of the window kernels (shared memory: 2 x WNR x 256 complex)
   // round-2 kernels (each can be switched off for A/B runs): fused deep levels (needs the window inverses), 16-part forward update and
   // 4-columns-per-warp backward update
   const bool fused_ok = S.wininv && !(getenv("WAE_LU_SOLVE_FUSED") && !atoi(getenv("WAE_LU_SOLVE_FUSED")));
@@ -2115,7 +2134,7 @@ static void lu_sweeps_nr(wae_ctx* h, LuSolver& S, int trans_t, int nrhs, cplx* y
       for (int c_lo = 0; c_lo < max_s; c_lo += W) {
         timed(0, [&] {
           if (S.wininv)
-            lu_fwd_win_kernel<<<dim3(zc * LU_WIN_CLUSTER, nrhs), 1024, 0, st>>>(D, lst, fwd_up, c_lo, Y.n, y);
+            lu_fwd_win_kernel<WNR><<<dim3(zc * LU_WIN_CLUSTER, (nrhs + WNR - 1) / WNR), 1024, 0, st>>>(D, lst, fwd_up, c_lo, nrhs, y);
           else
             lu_fwd_tri_kernel<<<dim3(zc, nrhs), 1024, 0, st>>>(D, lst, fwd_up | tri_pf, c_lo, Y.n, y);
         });
@@ -2188,7 +2207,7 @@ static void lu_sweeps_nr(wae_ctx* h, LuSolver& S, int trans_t, int nrhs, cplx* y
         }
         timed(3, [&] {
           if (S.wininv)
-            lu_bwd_win_kernel<<<dim3(zc * LU_WIN_CLUSTER, nrhs), 1024, 0, st>>>(D, lst, (int)!fwd_up, c_lo, Y.n, y);
+            lu_bwd_win_kernel<WNR><<<dim3(zc * LU_WIN_CLUSTER, (nrhs + WNR - 1) / WNR), 1024, 0, st>>>(D, lst, (int)!fwd_up, c_lo, nrhs, y);
           else
             lu_bwd_tri_kernel<<<dim3(zc, nrhs), 1024, 0, st>>>(D, lst, (int)!fwd_up | tri_pf, c_lo, Y.n, y);
         });
