@@ -286,3 +286,24 @@ def test_paired_eigs_switch_of_the_host_loop(rijke, monkeypatch):
         sol, n, flag = W.householder(L, 340 * 2 * math.pi, maxiter=20, tol=1e-11, output=False, stats=stats)
         assert flag == 1 and abs(sol.params["ω"] - g1) / abs(g1) < TOL and stats["solves"] > 0
     assert calls["pair"] >= 6 and calls["refused"] == 1  # the refusal is remembered for the rest of the run
+
+
+def test_first_order_perturbation_without_the_normalisations(rijke):
+    """householder / mslp take their Newton step from perturb(..., vectors=False): lam_1 = -(v_adj^H L01 v) / (v_adj^H L10 v) is free of the
+    scaling of the vector pair, so the shortcut must reproduce the coefficient of the reference's normalised recipe (perturbation.jl:319-367)."""
+    from wae_b200.nlevp import perturb
+    mg, mo, c = rijke
+    L = W.discretize(mg, rijke_dscrp(0.01, 0.001), c, ctx=HostStandIn())
+    sol, n, flag = W.householder(L, 340 * 2 * math.pi, maxiter=20, tol=1e-11, output=False)
+    rng = np.random.default_rng(5)
+    v = sol.v * (3.0 - 2.0j) + 1e-3 * (rng.standard_normal(L.size()) + 1j * rng.standard_normal(L.size()))
+    va = sol.v_adj * (0.5 + 4.0j) + 1e-3 * (rng.standard_normal(L.size()) + 1j * rng.standard_normal(L.size()))
+    active, mode = L.active, L.mode
+    L.active, L.mode = ["ω", "τ"], "householder"
+    try:
+        lam_ref, vecs = perturb(L, 1, v, va)
+        lam_fast, none = perturb(L, 1, v, va, vectors=False)
+    finally:
+        L.active, L.mode = active, mode
+    assert none == [None, None] and vecs[0] is not None
+    assert abs(lam_fast[1] - lam_ref[1]) <= 1e-12 * abs(lam_ref[1])
